@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the matching hot path (BASELINE.json): reads/s and text Gbp/s.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c3|c2|c1|tiny] [--impl reference]
+
+A step = one pass of the hot path over the synthetic workload: read packing + read-side signature
+index build (K1+K2), text scan with probe/verify (K3), result reduction (and, for N>1, the one
+cross-shard exchange of matchUnique).  The text is sharded across ranks with a read-length halo,
+the read index is replicated; total work is fixed as N grows ("strong").
+
+`value`  : whole-job reads/s with inputs resident in HBM (device pointers through the C ABI).
+`e2e`    : the same through the host-pointer C ABI (pinned host buffers; H2D of text + reads and
+           D2H of the per-read results inside the timed region).
+`roofline`: the text-scan kernel against the measured HBM peak, algorithmic bytes per SURVEY 8(d).
+`cpu_baseline` / --impl reference: the reference's own CPU code (oracle/_ref/ref_harness, compiled
+from the reference sources) on a bounded sample, extrapolated linearly to the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: text bases, reads, read length, -e, mode, scores, substitution rate, records, N per million
+    "c3": dict(n=3_100_000_000, reads=50_000_000, L=100, e=4, mode="unique", scores=False, sub=0.01, nrec=24, npm=1000,
+               desc="C3: synthetic 3.1 Gbp genome (24 records, 0.1% N), 50M x 100bp reads, matchUnique -s 2 -e 4 -l 32 -q 0"),
+    "c2": dict(n=250_000_000, reads=10_000_000, L=100, e=4, mode="all", scores=True, sub=0.01, nrec=1, npm=0,
+               desc="C2: synthetic 250 Mbp chromosome, 10M x 100bp FastQ reads, matchAll -e 4 with ComputeScore"),
+    "c1": dict(n=10_000_000, reads=1_000_000, L=36, e=2, mode="all", scores=False, sub=0.02, nrec=1, npm=0,
+               desc="C1: 10 Mbp text, 1M x 36bp reads, matchAll -e 2, no scores"),
+    "c5": dict(n=3_100_000_000, reads=20_000_000, L=250, e=8, mode="all", scores=False, sub=0.01, nrec=24, npm=1000,
+               desc="C5: 3.1 Gbp genome, 20M x 250bp reads, matchAll -e 8"),
+    "tiny": dict(n=20_000_000, reads=500_000, L=100, e=4, mode="unique", scores=False, sub=0.01, nrec=3, npm=1000,
+                 desc="tiny: 20 Mbp, 500k x 100bp reads, matchUnique -e 4 (smoke-size)"),
+}
+SEED = 0x5EA1
+
+
+def record_starts(n: int, nrec: int):
+    import numpy as np
+    from real_b200 import synth
+    if nrec <= 1:
+        return np.asarray([0, n], dtype=np.uint64)
+    cuts = sorted(set(int(x % np.uint64(n)) for x in synth.splitmix64(np.arange(nrec - 1, dtype=np.uint64) ^ synth.stream(SEED, 3))))
+    return np.asarray([0] + [c for c in cuts if c > 0] + [n], dtype=np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference leg
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference(wl: dict, sample_text: int, sample_reads: int, threads: int) -> dict:
+    """Times the reference's own CPU path (oracle/_ref/ref_harness: its index build per text block and its
+    OpenMP matching region) on a bounded sample of the workload, and extrapolates linearly: index time
+    with the text length, match time with reads x text blocks (one block assumed at full scale, which
+    favours the CPU).  Falls back to the oracle port when the harness binary is absent."""
+    import numpy as np
+    from real_b200 import synth
+    from oracle import oracle_py as O
+    n_s = min(sample_text, wl["n"])
+    r_s = min(sample_reads, wl["reads"])
+    text = synth.make_text(SEED, n_s, nrecords=min(wl["nrec"], 4), n_per_million=wl["npm"])
+    fastq = bool(wl["scores"])
+    reads = synth.make_reads(text, SEED + 1, r_s, wl["L"], wl["sub"], fastq=fastq)
+    if O.have_ref():
+        work = tempfile.mkdtemp(prefix="bench_ref_")
+        try:
+            synth.write_fasta(os.path.join(work, "t.fa"), text)
+            rf = os.path.join(work, "r.fq" if fastq else "r.fa")
+            synth.write_reads(rf, reads, fastq)
+            args = ["-t", os.path.join(work, "t.fa"), "-p", rf, "-o", "x", "-u", "1" if wl["mode"] == "unique" else "0", "-R", "0",
+                    "-s", "2", "-e", str(wl["e"]), "-l", "32", "-q", "1" if wl["scores"] else "0", "-T", str(threads)]
+            if fastq:
+                args += ["-Q", "33"]
+            timing, _, _ = O.run_ref(wl["mode"], work, args, threads=threads)
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        index_s, match_s, kind = timing["index_s"], timing["match_s"], "reference"
+    else:
+        O.lib()
+        t0 = time.perf_counter()
+        if wl["mode"] == "unique":
+            info, sc = O.unique_init(reads.nreads, wl["scores"])
+            O.match_unique(text, reads, info, sc, totalkmax=wl["e"], scores=wl["scores"])
+        else:
+            O.match_all(text, reads, totalkmax=wl["e"], scores=wl["scores"])
+        index_s, match_s, kind, threads = 0.0, time.perf_counter() - t0, "port", 1
+    full_s = index_s * (wl["n"] / n_s) + match_s * (wl["reads"] / r_s)
+    return {"value": wl["reads"] / full_s, "unit": "reads/s", "cores": threads, "kind": kind,
+            "text_gbp_per_s": wl["n"] / full_s / 1e9,
+            "sample": "%d bp text + %d reads of the workload: index build %.2f s, OpenMP matching region %.2f s; extrapolated linearly "
+                      "(index x text length, matching x reads, one text block at full scale)" % (n_s, r_s, index_s, match_s),
+            "sample_index_s": index_s, "sample_match_s": match_s, "extrapolated_full_s": full_s}
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference(wl, args.ref_text, args.ref_reads, threads)
+        if i >= args.warmup:
+            vals.append(last)
+    v = statistics.mean(x["value"] for x in vals)
+    full_s = statistics.mean(x["extrapolated_full_s"] for x in vals)
+    line = {"impl": "reference", "metric": "matching-path reads/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": full_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": {"workload": wl["desc"], "text_bases": wl["n"], "reads": wl["reads"], "read_len": wl["L"]},
+            "text_gbp_per_s": wl["n"] / full_s / 1e9,
+            "cpu_baseline": {k: last[k] for k in ("kind", "cores", "sample")} | {"value": v, "unit": "reads/s"},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--table-bits", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-text", type=int, default=16_000_000, help="reference arm: text bases of the sample")
+    ap.add_argument("--ref-reads", type=int, default=400_000, help="reference arm: reads of the sample")
+    ap.add_argument("--cpu-text", type=int, default=4_000_000)
+    ap.add_argument("--cpu-reads", type=int, default=100_000)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.warmup < 3 and args.impl == "ours":
+        print("note: fewer than 3 warm-up steps; not a reportable number", file=sys.stderr)
+
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from real_b200 import devsynth, matcher
+    from real_b200 import dist as rdist
+    from real_b200 import lib as rlib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the matching path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+
+    n, R, L = wl["n"], wl["reads"], wl["L"]
+    unique = wl["mode"] == "unique"
+    rs = record_starts(n, wl["nrec"])
+    ob, oe, sb, sl = matcher.shard_ranges(n, world, L)[rank]
+
+    # ---- synthetic inputs, generated on the device: this rank's text shard and the whole read set.
+    # Reads are cut from the whole text, so they are generated from a transient full copy.
+    full_w, full_m = devsynth.text_device(SEED, n, device=local, n_per_million=wl["npm"])
+    mapped, qual, offs = devsynth.reads_device(SEED + 1, full_w, full_m if wl["npm"] else None, n, R, L, wl["sub"], device=local,
+                                               quality=wl["scores"])
+    w0, w1 = sb // 32, (sb + sl + 31) // 32
+    m0, m1 = sb // 64, (sb + sl + 63) // 64
+    sh_w = full_w[w0:w1 + 2].clone()
+    sh_m = full_m[m0:m1 + 2].clone()
+    del full_w, full_m
+    torch.cuda.empty_cache()
+
+    ll = matcher.scoring_table() if wl["scores"] else None
+    h = rlib.Handle(seedl=32, seedkmax=2, totalkmax=wl["e"], scores=wl["scores"], ll_table=ll, device=local, table_bits=args.table_bits)
+    shard = rdist.HandleShard(h, R)
+    keys = torch.empty(R, dtype=torch.int64, device=dev) if unique else None
+    ties = torch.empty(R, dtype=torch.uint8, device=dev) if unique else None
+    hstream = torch.cuda.ExternalStream(h.stream(), device=dev)
+
+    phase = {"pack_ms": [], "index_ms": [], "scan_ms": [], "post_ms": [], "exchange_ms": []}
+    last_stats = {}
+    nhits_holder = [0]
+
+    def step_device():
+        h.set_reads_device(mapped.data_ptr(), offs.data_ptr(), R, R * L, L, d_quality=qual.data_ptr() if qual is not None else None)
+        h.set_text_device(sh_w.data_ptr(), sh_m.data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+        if unique:
+            h.match_unique()
+            st = h.stats()
+            t0 = time.perf_counter()
+            if world > 1:
+                rdist.unique_exchange(shard, keys=keys, ties=ties)
+            st["exchange_ms"] = (time.perf_counter() - t0) * 1e3
+        else:
+            nhits_holder[0] = h.match_all_count()
+            st = h.stats()
+            st["exchange_ms"] = 0.0
+        return st
+
+    def timed(fn, steps, warmup, collect=None):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        launches0 = h.stats()["total_launches"]
+        e0.record(hstream)
+        for _ in range(steps):
+            st = fn()
+            if collect is not None:
+                collect(st)
+        e1.record(hstream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), h.stats()["total_launches"] - launches0
+
+    def collect(st):
+        for k in phase:
+            phase[k].append(st.get(k, 0.0))
+        last_stats.update(st)
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    total_ms, launches = timed(step_device, args.steps, args.warmup, collect)
+    clk = clocks.stop() if rank == 0 else {}
+    ms_per_step = total_ms / args.steps
+    value = R / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (K3 text scan), algorithmic bytes per SURVEY.md 8(d)
+    scan_ms = statistics.mean(phase["scan_ms"])
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_text_local = last_stats["n_windows"]
+    nwin_tot = torch.tensor([last_stats["n_windows"], last_stats["n_candidates"], last_stats["n_hits"], last_stats["n_seedpass"]],
+                            dtype=torch.float64, device=dev)
+    alg_bytes = 0.375 * n_text_local + 192.0 * last_stats["n_windows"] + 64.0 * last_stats["n_candidates"] + 16.0 * last_stats["n_hits"]
+    design_bytes = 0.375 * n_text_local + 32.0 * last_stats["n_probes"] + 64.0 * last_stats["n_candidates"] + 16.0 * last_stats["n_hits"]
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                "traffic": None, "alg_bytes_per_launch": alg_bytes, "scan_ms": scan_ms,
+                "design_bytes_per_launch": design_bytes, "design_frac": design_bytes / (scan_ms * 1e-3) / 1e9 / peak,
+                "note": "alg bytes = 0.375*N_text + 6*32*N_win + 64*N_cand + 16*N_hit (SURVEY 8d, six lists); the kernel probes 3 merged "
+                        "tables per window (design bytes = 3*32*N_win + ...), so frac can exceed the sector-traffic fraction"}
+    if world > 1:
+        dist.all_reduce(nwin_tot, op=dist.ReduceOp.SUM)
+
+    # ---- e2e: host buffers through the host-pointer ABI, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_mapped = torch.empty(R * L, dtype=torch.uint8).pin_memory()
+        h_mapped.copy_(mapped)
+        h_qual = None
+        if qual is not None:
+            h_qual = torch.empty(R * L, dtype=torch.uint8).pin_memory()
+            h_qual.copy_(qual)
+        h_offs = (np.arange(R + 1, dtype=np.uint64) * np.uint64(L))
+        h_w = sh_w.cpu().pin_memory()
+        h_m = sh_m.cpu().pin_memory()
+        h_info = torch.empty(R, dtype=torch.int64).pin_memory()
+        np_w = h_w.numpy().view(np.uint64)
+        np_m = h_m.numpy().view(np.uint64)
+        np_mapped = h_mapped.numpy()
+        np_qual = h_qual.numpy() if h_qual is not None else None
+        np_info = h_info.numpy().view(np.uint64)
+        d2h = [0]
+
+        def step_host():
+            h.set_reads(np_mapped, h_offs, np_qual)
+            h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+            if unique:
+                h.match_unique()
+                if world > 1:
+                    rdist.unique_exchange(shard, keys=keys, ties=ties)
+                if rank == 0 or world == 1:
+                    h.get_unique(out=np_info)
+                    d2h[0] = R * 8
+            else:
+                nh = h.match_all_count()          # records land in the library's pinned host buffer
+                d2h[0] = nh * 40
+            return {}
+
+        e_steps = max(1, min(args.steps, 3))
+        e_ms, _ = timed(step_host, e_steps, 1)
+        h2d = R * L * (2 if qual is not None else 1) + (R + 1) * 8 + np_w.nbytes + np_m.nbytes + rs.nbytes
+        e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
+               "ms_per_step": e_ms / e_steps, "steps": e_steps}
+        del h_mapped, h_qual, h_w, h_m
+
+    dev_bytes = h.device_bytes()
+    h.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(wl, args.cpu_text, args.cpu_reads, os.cpu_count() or 1)
+
+    if rank == 0:
+        tot = nwin_tot.tolist()
+        line = {
+            "metric": "matching-path reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "text_bases": n, "reads": R, "read_len": L, "mode": wl["mode"], "scores": wl["scores"],
+                       "parallelism": "text sharded x%d with %d-base halo, read index replicated" % (world, L),
+                       "l2": "inputs larger than L2 (text %.0f MB/GPU, index tables > 1.8 GB): no flush needed" % (sl / 4 / 1e6),
+                       "table_bits": args.table_bits or 32},
+            "text_gbp_per_s": n / (ms_per_step * 1e-3) / 1e9,
+            "scan_only": {"ms": scan_ms, "text_gbp_per_s_per_gpu": last_stats["n_windows"] / (scan_ms * 1e-3) / 1e9,
+                          "reads_per_s": R / (scan_ms * 1e-3)},
+            "phases_ms": {k: statistics.mean(v) for k, v in phase.items()},
+            "counts": {"windows": tot[0], "candidates": tot[1], "hits": tot[2], "seedpass": tot[3], "matchall_hits": nhits_holder[0]},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "device_bytes": dev_bytes,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

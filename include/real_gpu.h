@@ -1,0 +1,204 @@
+/* real_gpu.h -- C ABI of the B200-native REAL matching path (libreal_gpu.so).
+ *
+ * Drop-in boundary for the hot path of solonas13/REAL v0.0.31.  The reference has no FFI
+ * layer; the seams this ABI replaces are the per-read matcher entry points that its run
+ * drivers call inside the text-block loop:
+ *
+ *   AllMatcher::match(pattern, fi, RWB, handled, localmatches)       matchAllImplementation.cpp:261-355
+ *     + unifyMatches(localmatches)                                   matchAllImplementation.cpp:150-161
+ *   UniqueMatcher::match(pattern, info, fi, RWB, handled)            matchUniqueImplementation.cpp:369-500
+ *   UniqueMatcher::matchGaps(pattern, info, RWB, gapinfos, handled)  matchUniqueImplementation.cpp:501-572
+ *   ListSetBlockReader::readNextBlock() (index build)                ListSetBlockReader.hpp:24-56
+ *
+ * Those are per-read calls over a text-side index; here they are batched and the index is on
+ * the read side (BASELINE.json north_star): the host hands over one text file (or a shard of
+ * it) and the whole read set, and gets back exactly what the per-read calls would have
+ * accumulated -- the set of MatchPosAndError rows in unifyMatches order, or the array of
+ * UniqueMatchInfo words.
+ *
+ * Conventions: every entry point is extern "C", takes plain pointers and sizes, returns 0 on
+ * success or a negative REAL_GPU_E_* code, never throws.  real_gpu_last_error() gives the text.
+ * Host buffers passed in belong to the caller and may be reused as soon as the call returns.
+ * Buffers handed out by the library stay valid until the next call on the same handle.
+ * A handle is single-threaded and bound to one CUDA device.  There is no CPU fallback: if no
+ * device is present real_gpu_create fails with REAL_GPU_E_CUDA.
+ */
+#ifndef REAL_GPU_H
+#define REAL_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REAL_GPU_ABI_VERSION 1
+
+enum
+{
+        REAL_GPU_OK = 0,
+        REAL_GPU_E_ARG = -1,       /* bad argument (also: option outside what RealOptions accepts) */
+        REAL_GPU_E_CUDA = -2,      /* CUDA runtime error, no device, out of device memory */
+        REAL_GPU_E_STATE = -3,     /* call order: text or reads not set */
+        REAL_GPU_E_LIMIT = -4      /* input exceeds a format limit (see real_gpu_set_text / set_reads) */
+};
+
+typedef struct real_gpu real_gpu;
+
+/* Run parameters: the subset of RealOptions (RealOptions.hpp:29-77) the hot path reads. */
+typedef struct
+{
+        uint32_t struct_size;   /* sizeof(real_gpu_params), for ABI evolution */
+        int32_t device;         /* CUDA device ordinal */
+        uint32_t seedl;         /* -l  seed length, multiple of 4, 4..64 (RealOptions.cpp:434-447) */
+        uint32_t seedkmax;      /* -s  mismatches allowed in the seed, 0..2 (RealOptions.cpp:449-453) */
+        uint32_t totalkmax;     /* -e  mismatches allowed in the read, 0..15 (RealOptions.cpp:176-180) */
+        uint32_t scores;        /* -q  quality-aware scores on/off */
+        double filter_mult;     /* epsilon(patl) = (float)(filter_mult * patl) (RealOptions.hpp:74-77, RealOptions.cpp:455-463) */
+        const double * ll_table;/* Scoring::LL, 4*4*64 doubles indexed (ref<<8)|(read<<6)|q (Scoring.hpp:70-73);
+                                   required when scores != 0 or for real_gpu_match_gaps; copied */
+        uint32_t table_bits;    /* 0 = automatic; else log2 of the slots of each signature presence table */
+        uint32_t reserved;
+} real_gpu_params;
+
+/* One reported match == MatchPosAndError (matchAllImplementation.cpp:99-120) plus the read ordinal. */
+typedef struct
+{
+        uint64_t patid;         /* 0-based ordinal of the read in the set (Pattern::patid) */
+        uint64_t pos;           /* 0-based start in the concatenated text of the file */
+        uint32_t file;          /* fileid given to real_gpu_set_text */
+        uint32_t frag;          /* FASTA record index, RangeVector::positionToRange(pos) */
+        uint32_t k;             /* mismatches over the whole read */
+        uint32_t inverted;      /* 0 = '+', 1 = '-' (read reverse complemented) */
+        float score;            /* ComputeScore::computeScore; 1.0f when scores are off */
+        uint32_t reserved;
+} real_gpu_hit;
+
+/* GapInfo (match.hpp:420-426) of a read whose state is Gapped and whose entry survived. */
+typedef struct
+{
+        uint32_t patid;
+        uint32_t mingap;
+        uint32_t where;
+        uint32_t start;
+        uint32_t gap_pos;
+        uint32_t present;
+} real_gpu_gapinfo;
+
+/* Device-side phase timings of the last calls, milliseconds, measured with CUDA events on the
+ * handle's stream. */
+typedef struct
+{
+        float h2d_text_ms;
+        float h2d_reads_ms;
+        float pack_ms;          /* K1: read packing + seed extraction */
+        float index_ms;         /* K2: entry generation + radix sorts + table build */
+        float scan_ms;          /* K3: text scan (probe + verify), the dominant kernel */
+        float post_ms;          /* K4/K6: scoring, per-read ordering */
+        float d2h_ms;
+        uint32_t scan_launches; /* kernels launched by the last match call */
+        uint32_t total_launches;/* kernels launched since create */
+        uint64_t n_windows;     /* text positions scanned by the last scan */
+        uint64_t n_probes;      /* presence-table probes issued */
+        uint64_t n_candidates;  /* signature-equal (window, entry) pairs examined */
+        uint64_t n_seedpass;    /* candidates that passed the seed test and the canonical-list rule */
+        uint64_t n_hits;        /* hits emitted */
+} real_gpu_stats;
+
+int real_gpu_abi_version(void);
+
+/* Creates a handle on params->device.  Replaces the construction of SignatureConstruction,
+ * Scoring and the matcher object (matchAllImplementation.cpp:381-390,447). */
+int real_gpu_create(const real_gpu_params * params, real_gpu ** out);
+int real_gpu_destroy(real_gpu * h);
+const char * real_gpu_last_error(const real_gpu * h);
+
+/* Text of one file, or a shard of it (replaces getText + AutoTextArray + RangeVector construction,
+ * getText.hpp:31-58, and the text side of MatcherBase, MatcherBase.hpp:18-33).
+ *   words         2 bit/base, 32 bases per u64, base i of the shard at bits 63-2(i%32).. (AutoTextArray.hpp:27-43)
+ *   nmask         1 bit/base, 64 per u64, base i at bit 63-(i%64) (AutoTextArray.hpp:45-61)
+ *   n_total       length of the whole file in bases (positions are file-global everywhere)
+ *   shard_begin   global position of base 0 of words/nmask; must be a multiple of 64
+ *   shard_len     bases present in words/nmask
+ *   own_begin/own_end  half-open range of hit START positions this shard reports; the shard must
+ *                 contain [own_begin, min(n_total, own_end + maxreadlen)) (read-length halo)
+ *   record_starts nrecords+1 global offsets, last == n_total (countReads.cpp:58,81)
+ * Limits (REAL_GPU_E_LIMIT): n_total < 2^35, fileid < 64, nrecords <= 65535 for unique matching
+ * (UniqueMatchInfo.hpp:29-33). */
+int real_gpu_set_text(real_gpu * h, uint32_t fileid,
+                      const uint64_t * words, const uint64_t * nmask,
+                      uint64_t n_total, uint64_t shard_begin, uint64_t shard_len,
+                      uint64_t own_begin, uint64_t own_end,
+                      const uint64_t * record_starts, uint32_t nrecords);
+/* Same, with words/nmask already resident in device memory (record_starts stays a host pointer). */
+int real_gpu_set_text_device(real_gpu * h, uint32_t fileid,
+                             const uint64_t * d_words, const uint64_t * d_nmask,
+                             uint64_t n_total, uint64_t shard_begin, uint64_t shard_len,
+                             uint64_t own_begin, uint64_t own_end,
+                             const uint64_t * record_starts, uint32_t nrecords);
+
+/* Read set (replaces reader_type::fillPatternBlock + Pattern::computeMapped + RestWordBuffer::setup*
+ * + SignatureConstruction::signatureMapped/reverseMappedSignature per read, and the index build
+ * ListSet::sort + getLookupTable, here on the read side).
+ *   mapped   one byte per base, 0..3 = ACGT, anything >3 = wildcard (Pattern.hpp:105-128)
+ *   quality  one byte per base, PHRED minus offset (FastQReader.hpp:168); NULL = constant 30 (Pattern.hpp:42-45)
+ *   offsets  nreads+1 byte offsets into mapped/quality
+ * Reads shorter than seedl or containing a wildcard are kept but never match
+ * (matchAllImplementation.cpp:273-289).  Resets the unique-match state.
+ * Limits: nreads < 2^28, read length <= 65535. */
+int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * quality,
+                       const uint64_t * offsets, uint64_t nreads);
+int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint8_t * d_quality,
+                              const uint64_t * d_offsets, uint64_t nreads, uint64_t total_bases, uint32_t maxlen);
+
+/* All matches of every read against the current text: what AllMatcher::match + unifyMatches
+ * accumulate over the file, sorted by (patid, k, pos, file, frag, score, inverted)
+ * (matchAllImplementation.cpp:122-136).  *hits points to library-owned pinned host memory. */
+int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhits);
+
+/* Folds the current text into the per-read unique state (UniqueMatcher::match for every read);
+ * call once per file/shard, state persists like the reference's uniqueinfo array
+ * (matchUniqueImplementation.cpp:1097). */
+int real_gpu_match_unique(real_gpu * h);
+/* Copies out the state: info[nreads] in UniqueMatchInfo bit layout (UniqueMatchInfo.hpp:26-39:
+ * pos 35 | file 6 | err 4 | frag 16 | state 3, low to high), scores[nreads] or NULL. */
+int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores);
+/* Clears the unique state (fresh UniqueMatchInfo objects). */
+int real_gpu_reset_unique(real_gpu * h);
+
+/* Cross-shard exchange for matchUnique without scores: the per-read state is
+ * exported as an order-preserving u64 key so that a MIN all-reduce followed by a SUM all-reduce of
+ * the tie counts reproduces the reference's reduction over disjoint text shards.
+ *   step 1: real_gpu_unique_export_keys   -> d_keys[nreads]   (device pointer owned by caller)
+ *   step 2: caller all-reduces d_keys with MIN
+ *   step 3: real_gpu_unique_export_ties   -> d_ties[nreads] u8: 1 where this shard holds a hit at the winning error count on a DIFFERENT position
+ *   step 4: caller all-reduces d_ties with SUM
+ *   step 5: real_gpu_unique_import        <- d_keys, d_ties; replaces the state by the merged one */
+int real_gpu_unique_export_keys(real_gpu * h, uint64_t * d_keys);
+int real_gpu_unique_export_ties(real_gpu * h, const uint64_t * d_min_keys, uint8_t * d_ties);
+int real_gpu_unique_import(real_gpu * h, const uint64_t * d_min_keys, const uint8_t * d_tie_sums);
+
+/* Gapped extension pass (UniqueMatcher::matchGaps) for reads still NoMatch/Gapped; updates the
+ * unique state (state Gapped, score, seed position).  gaps[nreads], present==1 where a GapInfo
+ * entry exists. */
+int real_gpu_match_gaps(real_gpu * h, uint64_t n_list_windows);
+int real_gpu_get_gaps(real_gpu * h, real_gpu_gapinfo * gaps);
+
+/* Introspection for benchmarks and tests. */
+int real_gpu_get_stats(real_gpu * h, real_gpu_stats * out);
+void * real_gpu_stream(real_gpu * h);                  /* cudaStream_t the kernels are launched on */
+uint64_t real_gpu_device_bytes(const real_gpu * h);    /* device memory currently held */
+
+/* Counter-based synthetic inputs generated directly in device memory (benchmark tooling; the same
+ * formulas as real_b200/synth.py). */
+int real_gpu_synth_text(int device, uint64_t seed, uint64_t first_word, uint64_t nwords,
+                        uint32_t n_per_million, uint64_t * d_words, uint64_t * d_nmask_or_null);
+                        /* first_word must be even when d_nmask_or_null is given; it receives ceil(nwords/2) words */
+int real_gpu_synth_reads(int device, uint64_t seed, const uint64_t * d_words, const uint64_t * d_nmask_or_null,
+                         uint64_t text_n, uint64_t total_reads, uint64_t first_read, uint64_t nreads,
+                         uint32_t length, uint32_t sub_per_16384, uint8_t * d_mapped, uint8_t * d_quality_or_null);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,127 @@
+// Shared device/host helpers of libreal_gpu.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+#include <cstdio>
+
+namespace realgpu
+{
+
+struct CudaError : public std::runtime_error
+{
+        explicit CudaError(std::string const & s) : std::runtime_error(s) {}
+};
+
+#define RG_CUDA(expr)                                                                          \
+        do {                                                                                   \
+                cudaError_t rg_e_ = (expr);                                                    \
+                if ( rg_e_ != cudaSuccess )                                                    \
+                {                                                                              \
+                        char rg_buf_[512];                                                     \
+                        snprintf(rg_buf_, sizeof(rg_buf_), "%s failed: %s (%s:%d)", #expr,     \
+                                 cudaGetErrorString(rg_e_), __FILE__, __LINE__);               \
+                        throw realgpu::CudaError(rg_buf_);                                     \
+                }                                                                              \
+        } while (0)
+
+#define RG_KERNEL_CHECK() RG_CUDA(cudaGetLastError())
+
+// ---- layouts shared by kernels -------------------------------------------------------------
+
+// zero words kept in front of and behind the device copy of the text / N mask so that unaligned
+// extracts and tile halos never leave the allocation
+static const uint32_t TEXT_PAD_WORDS = 64;
+
+// presence-table sector: 32 bytes = rank header + 224 slot bits
+static const uint32_t SECTOR_SLOTS = 224;
+static const uint32_t SECTOR_WORDS = 8;
+
+static const uint32_t ENTRY_NONE = 0xFFFFFFFFu;
+
+// one index entry: the read strand's whole seed, (strand id << 2 | fragment offset), chain link
+struct __align__(16) Entry
+{
+        uint64_t seed;
+        uint32_t val;
+        uint32_t next;
+};
+
+// raw hit as emitted by the scan kernel (16 bytes)
+struct __align__(16) RawHit
+{
+        uint64_t pm;     // pos:35 | k:4 | strand:1 | frag:24
+        uint32_t read;
+        float score;
+};
+
+__host__ __device__ inline uint64_t rawhit_pack(uint64_t pos, uint32_t k, uint32_t strand, uint32_t frag)
+{
+        return pos | ((uint64_t)k << 35) | ((uint64_t)strand << 39) | ((uint64_t)frag << 40);
+}
+__host__ __device__ inline uint64_t rawhit_pos(uint64_t pm) { return pm & ((1ULL << 35) - 1); }
+__host__ __device__ inline uint32_t rawhit_k(uint64_t pm) { return (uint32_t)((pm >> 35) & 15); }
+__host__ __device__ inline uint32_t rawhit_strand(uint64_t pm) { return (uint32_t)((pm >> 39) & 1); }
+__host__ __device__ inline uint32_t rawhit_frag(uint64_t pm) { return (uint32_t)((pm >> 40) & 0xFFFFFF); }
+
+// UniqueMatchInfo word (UniqueMatchInfo.hpp:26-39)
+#define UMI_FILESHIFT 35
+#define UMI_ERRSHIFT 41
+#define UMI_FRAGSHIFT 45
+#define UMI_STATESHIFT 61
+#define UMI_POSMASK ((1ULL << 35) - 1)
+enum { ST_NOMATCH = 0, ST_STRAIGHT = 1, ST_REVERSE = 2, ST_GAPPED = 3, ST_NONUNIQUE = 4 };
+
+__host__ __device__ inline uint32_t umi_state(uint64_t d) { uint64_t s = d >> UMI_STATESHIFT; return s > 4 ? 4u : (uint32_t)s; }
+__host__ __device__ inline uint64_t umi_pos(uint64_t d) { return d & UMI_POSMASK; }
+__host__ __device__ inline uint32_t umi_file(uint64_t d) { return (uint32_t)((d >> UMI_FILESHIFT) & 63); }
+__host__ __device__ inline uint32_t umi_err(uint64_t d) { return (uint32_t)((d >> UMI_ERRSHIFT) & 15); }
+__host__ __device__ inline uint32_t umi_frag(uint64_t d) { return (uint32_t)((d >> UMI_FRAGSHIFT) & 0xFFFF); }
+__host__ __device__ inline uint64_t umi_make(uint32_t state, uint32_t file, uint64_t pos, uint32_t k, uint32_t frag)
+{
+        return pos | ((uint64_t)file << UMI_FILESHIFT) | ((uint64_t)k << UMI_ERRSHIFT) | ((uint64_t)frag << UMI_FRAGSHIFT) | ((uint64_t)state << UMI_STATESHIFT);
+}
+__host__ __device__ inline uint64_t umi_with_state(uint64_t d, uint32_t s) { return (d & ~(7ULL << UMI_STATESHIFT)) | ((uint64_t)s << UMI_STATESHIFT); }
+
+// ---- bit helpers ----------------------------------------------------------------------------
+
+// number of differing 2-bit symbols (PopCountTable.hpp:113-131)
+__device__ __forceinline__ uint32_t diffcount64(uint64_t a, uint64_t b)
+{
+        uint64_t x = a ^ b;
+        x = ((x >> 1) | x) & 0x5555555555555555ULL;
+        return (uint32_t)__popcll(x);
+}
+
+// l (1..32) bases starting at base i, right aligned (AutoTextArray.hpp:122-125); `words` may be
+// indexed one word past the last base (padding)
+__device__ __forceinline__ uint64_t text_word(const uint64_t * __restrict__ words, uint64_t i, uint32_t l)
+{
+        uint64_t const w = i >> 5;
+        uint32_t const sh = (uint32_t)(i & 31) << 1;
+        uint64_t const a = __ldg(words + w);
+        uint64_t const b = __ldg(words + w + 1);
+        uint64_t v = sh ? ((a << sh) | (b >> (64 - sh))) : a;
+        return v >> (64 - 2*l);
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+        uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+}
+
+// slot of a pair signature in a presence table with 2^hb slots.  Signatures that already fit are
+// used as they are (no collisions between different signatures); wider ones are folded.
+__host__ __device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t keybits, uint32_t hb)
+{
+        if ( keybits <= hb )
+                return (uint32_t)key;
+        return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - hb));
+}
+
+} // namespace realgpu

@@ -1,0 +1,231 @@
+// K4 (quality-aware score), K6 (per-read ordering of matchAll hits) and the key transforms of the
+// cross-shard unique reduction (K5).
+#pragma once
+
+#include "common.cuh"
+
+namespace realgpu
+{
+
+// ---- K4 : ComputeScore<...,true>::computeScore (ComputeScore.hpp:50-190) ----------------------
+// float(1.0 + sum_i LL[ref_i][read_i][q_i]), double accumulation in index order; the '-' strand is
+// scored with the reverse complement and the qualities back to front (ComputeScore.hpp:79).
+// One thread per hit: the additions are a dependent chain by definition of the result.
+__device__ __forceinline__ float score_hit(const double * __restrict__ sll, const uint64_t * __restrict__ text, uint64_t lpos,
+                                           const uint64_t * __restrict__ rp, const uint8_t * __restrict__ q, uint32_t L, uint32_t strand)
+{
+        double raw = 1.0;
+        for ( uint32_t w = 0; w * 32 < L; ++w )
+        {
+                uint32_t const len = (L - 32*w < 32) ? (L - 32*w) : 32;
+                uint64_t const tw = text_word(text, lpos + 32*w, len) << (64 - 2*len);   // left aligned
+                uint64_t const rw = __ldg(rp + w);
+                for ( uint32_t j = 0; j < len; ++j )
+                {
+                        uint32_t const i = 32*w + j;
+                        uint32_t const refb = (uint32_t)(tw >> (62 - 2*j)) & 3;
+                        uint32_t const readb = (uint32_t)(rw >> (62 - 2*j)) & 3;
+                        uint32_t const qq = q ? (uint32_t)__ldg(q + (strand ? (L - 1 - i) : i)) : 30u;
+                        raw = __dadd_rn(raw, sll[((refb << 8) | (readb << 6) | qq) & 1023]);
+                }
+        }
+        return (float)raw;
+}
+
+__global__ void __launch_bounds__(256) k_score_hits(RawHit * __restrict__ hits, uint64_t nhits, const double * __restrict__ ll,
+                                                  const uint64_t * __restrict__ text, uint64_t shard_begin,
+                                                  const uint64_t * __restrict__ rpack, uint32_t W, const uint32_t * __restrict__ rlen,
+                                                  const uint8_t * __restrict__ quality, const uint64_t * __restrict__ offsets)
+{
+        __shared__ double sll[1024];
+        for ( int i = threadIdx.x; i < 1024; i += blockDim.x ) sll[i] = ll[i];
+        __syncthreads();
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= nhits ) return;
+        RawHit h = hits[i];
+        uint32_t const strand = rawhit_strand(h.pm);
+        uint32_t const L = rlen[h.read];
+        const uint8_t * q = quality ? (quality + offsets[h.read]) : nullptr;
+        h.score = score_hit(sll, text, rawhit_pos(h.pm) - shard_begin, rpack + ((uint64_t)h.read * 2 + strand) * W, q, L, strand);
+        hits[i] = h;
+}
+
+// ---- K6 : unifyMatches order (matchAllImplementation.cpp:122-161) -----------------------------
+
+__global__ void __launch_bounds__(256) k_hit_count(const RawHit * __restrict__ hits, uint64_t nhits, uint32_t * __restrict__ counts)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i < nhits ) atomicAdd(&counts[hits[i].read], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_hit_scatter(const RawHit * __restrict__ hits, uint64_t nhits, const uint32_t * __restrict__ starts,
+                                                   uint32_t * __restrict__ cursor, RawHit * __restrict__ out)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= nhits ) return;
+        RawHit const h = hits[i];
+        uint32_t const o = starts[h.read] + atomicAdd(&cursor[h.read], 1u);
+        out[o] = h;
+}
+
+// (k, pos, file, frag, score, inverted); file is constant within one call and frag is a function of pos
+__device__ __forceinline__ bool hit_before(RawHit const & a, RawHit const & b)
+{
+        uint32_t const ka = rawhit_k(a.pm), kb = rawhit_k(b.pm);
+        if ( ka != kb ) return ka < kb;
+        uint64_t const pa = rawhit_pos(a.pm), pb = rawhit_pos(b.pm);
+        if ( pa != pb ) return pa < pb;
+        if ( a.score != b.score ) return a.score < b.score;
+        return rawhit_strand(a.pm) < rawhit_strand(b.pm);
+}
+
+// one thread per read: insertion sort of its (short) segment, then expansion to the ABI record
+template<typename HitOut>
+__global__ void __launch_bounds__(128) k_hit_order(RawHit * __restrict__ seg, const uint32_t * __restrict__ starts, const uint32_t * __restrict__ counts,
+                                                 uint64_t nreads, uint32_t fileid, HitOut * __restrict__ out)
+{
+        uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( r >= nreads ) return;
+        uint32_t const n = counts[r];
+        if ( ! n ) return;
+        RawHit * s = seg + starts[r];
+        for ( uint32_t i = 1; i < n; ++i )
+        {
+                RawHit const x = s[i];
+                uint32_t j = i;
+                while ( j > 0 && hit_before(x, s[j-1]) ) { s[j] = s[j-1]; --j; }
+                s[j] = x;
+        }
+        HitOut * o = out + starts[r];
+        for ( uint32_t i = 0; i < n; ++i )
+        {
+                HitOut H;
+                H.patid = r;
+                H.pos = rawhit_pos(s[i].pm);
+                H.file = fileid;
+                H.frag = rawhit_frag(s[i].pm);
+                H.k = rawhit_k(s[i].pm);
+                H.inverted = rawhit_strand(s[i].pm);
+                H.score = s[i].score;
+                H.reserved = 0;
+                o[i] = H;
+        }
+}
+
+// ---- K5 : cross-shard reduction keys --------------------------------------------
+// key, most significant first: err(4) | unique flag (0 = NonUnique, sorts first) | file(6) | pos(35) | strand(1) | frag(16)
+// (63 bits, so the key orders the same as u64 and as i64 -- torch/NCCL reduce it as int64).
+// "no hit" = UNIQUE_KEY_NONE = 2^63-1.  MIN over shards picks the lowest error count, prefers an already-NonUnique
+// shard, then the smallest (file,pos), then '+'.
+#define UNIQUE_KEY_NONE 0x7FFFFFFFFFFFFFFFULL
+__device__ __forceinline__ uint64_t unique_key(uint64_t d)
+{
+        uint32_t const st = umi_state(d);
+        if ( st == ST_NOMATCH || st == ST_GAPPED ) return UNIQUE_KEY_NONE;
+        uint64_t const uniq = (st == ST_NONUNIQUE) ? 0 : 1;
+        uint64_t const strand = (st == ST_REVERSE) ? 1 : 0;
+        return ((uint64_t)umi_err(d) << 59) | (uniq << 58) | ((uint64_t)umi_file(d) << 52) | (umi_pos(d) << 17) | (strand << 16) | umi_frag(d);
+}
+
+__global__ void __launch_bounds__(256) k_unique_export(const unsigned long long * __restrict__ info, uint64_t n, uint64_t * __restrict__ keys)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i < n ) keys[i] = unique_key(info[i]);
+}
+
+__global__ void __launch_bounds__(256) k_unique_ties(const unsigned long long * __restrict__ info, uint64_t n, const uint64_t * __restrict__ minkeys, uint8_t * __restrict__ ties)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= n ) return;
+        uint64_t const mine = unique_key(info[i]);
+        uint64_t const win = minkeys[i];
+        // a DIFFERENT (file,pos) at the winning error count; shards that merely carry the same merged
+        // state from an earlier file do not count
+        bool const samepos = (((mine ^ win) >> 17) & ((1ULL << 41) - 1)) == 0;
+        ties[i] = (mine != UNIQUE_KEY_NONE && (mine >> 59) == (win >> 59) && ! samepos) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_unique_import(unsigned long long * __restrict__ info, uint64_t n, const uint64_t * __restrict__ minkeys, const uint8_t * __restrict__ tiesum)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= n ) return;
+        uint64_t const key = minkeys[i];
+        if ( key == UNIQUE_KEY_NONE )
+                return;    // no shard has a hit: keep the local NoMatch/Gapped word
+        uint32_t const err = (uint32_t)(key >> 59);
+        bool const uniq = ((key >> 58) & 1) && (tiesum[i] == 0);
+        uint32_t const file = (uint32_t)((key >> 52) & 63);
+        uint64_t const pos = (key >> 17) & UMI_POSMASK;
+        uint32_t const strand = (uint32_t)((key >> 16) & 1);
+        uint32_t const frag = (uint32_t)(key & 0xFFFF);
+        info[i] = umi_make(uniq ? (strand ? ST_REVERSE : ST_STRAIGHT) : ST_NONUNIQUE, file, pos, err, frag);
+}
+
+// ---- synthetic inputs (same formulas as real_b200/synth.py) -------------------------------------
+
+__device__ __forceinline__ uint64_t synth_stream(uint64_t seed, uint64_t tag) { return splitmix64(splitmix64(seed) + tag); }
+
+__device__ __forceinline__ bool synth_nhit(uint64_t seed_stream2, uint64_t maskword, uint32_t n_per_million)
+{
+        return n_per_million && (splitmix64(maskword ^ seed_stream2) % 1000000ULL) < n_per_million;
+}
+
+// text word w = splitmix64(stream(seed,1) ^ w); words under an all-N mask word are stored as A
+__global__ void __launch_bounds__(256) k_synth_text(uint64_t seed, uint64_t first_word, uint64_t nwords, uint32_t n_per_million,
+                                                  uint64_t * __restrict__ words)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= nwords ) return;
+        uint64_t const w = first_word + i;
+        uint64_t v = splitmix64(w ^ synth_stream(seed, 1));
+        if ( synth_nhit(synth_stream(seed, 2), w >> 1, n_per_million) ) v = 0;
+        words[i] = v;
+}
+
+// N mask: each 64-base mask word is all-N with probability n_per_million / 1e6
+__global__ void __launch_bounds__(256) k_synth_nmask(uint64_t seed, uint64_t first_mask_word, uint64_t nmaskwords, uint32_t n_per_million,
+                                                   uint64_t * __restrict__ nmask)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= nmaskwords ) return;
+        nmask[i] = synth_nhit(synth_stream(seed, 2), first_mask_word + i, n_per_million) ? ~0ULL : 0ULL;
+}
+
+// one thread per read; writes `length` mapped bytes (+ qualities).  Text must be resident (global coordinates
+// from word 0).  Reads over wildcards get the code 4 like genpat prints 'N'.
+__global__ void __launch_bounds__(128) k_synth_reads(uint64_t seed, const uint64_t * __restrict__ words, const uint64_t * __restrict__ nmask,
+                                                   uint64_t text_n, uint64_t total, uint64_t first, uint64_t count, uint32_t L, uint32_t thr,
+                                                   uint8_t * __restrict__ mapped, uint8_t * __restrict__ quality)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= count ) return;
+        uint64_t const r = first + i;
+        uint64_t const span = text_n - L + 1;
+        // stratified start: (r*span)/total without overflow for span < 2^36, total < 2^28
+        uint64_t const lo = (uint64_t)(((unsigned __int128)r * span) / total);
+        uint64_t const hi = (uint64_t)(((unsigned __int128)(r + 1) * span) / total);
+        uint64_t const width = (hi > lo) ? (hi - lo) : 1;
+        uint64_t pos = lo + splitmix64(r ^ synth_stream(seed, 4)) % width;
+        if ( pos > span - 1 ) pos = span - 1;
+        uint32_t const strand = (uint32_t)(splitmix64(r ^ synth_stream(seed, 5)) >> 63);
+        uint64_t const s6 = synth_stream(seed, 6);
+        uint8_t * out = mapped + i * L;
+        uint8_t * qo = quality ? (quality + i * L) : nullptr;
+        uint64_t hc = 0;
+        for ( uint32_t j = 0; j < L; ++j )
+        {
+                if ( (j & 3) == 0 ) hc = splitmix64((r * 64 + (j >> 2)) ^ s6);
+                uint32_t const u16 = (uint32_t)(hc >> (16 * (j & 3))) & 0xFFFF;
+                uint64_t const tp = strand ? (pos + L - 1 - j) : (pos + j);
+                uint32_t b = (uint32_t)(words[tp >> 5] >> (62 - 2*(tp & 31))) & 3;
+                bool const isn = nmask && ((nmask[tp >> 6] >> (63 - (tp & 63))) & 1);
+                if ( strand ) b = 3 - b;
+                bool changed = false;
+                if ( isn ) b = 4;
+                else if ( (u16 >> 2) < thr ) { b = (b + 1 + (u16 & 3) % 3) & 3; changed = true; }
+                out[j] = (uint8_t)b;
+                if ( qo ) qo[j] = changed ? (42 - 33) : (68 - 33);
+        }
+}
+
+} // namespace realgpu

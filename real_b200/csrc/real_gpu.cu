@@ -1,0 +1,790 @@
+// libreal_gpu.so -- C ABI (include/real_gpu.h) and host orchestration of the sm_100a kernels.
+// No CPU fallback: every entry point that computes runs CUDA kernels on the handle's device.
+#include "../../include/real_gpu.h"
+
+#include "common.cuh"
+#include "prims.cuh"
+#include "index.cuh"
+#include "scan.cuh"
+#include "post.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+using namespace realgpu;
+
+namespace
+{
+
+struct DevBuf
+{
+        void * p;
+        size_t bytes;
+        DevBuf() : p(nullptr), bytes(0) {}
+};
+
+struct Table
+{
+        DevBuf bitmap, E;
+        uint32_t hb, nlists, nsectors;
+        uint64_t nentries, ndistinct;
+        Table() : hb(0), nlists(0), nsectors(0), nentries(0), ndistinct(0) {}
+};
+
+} // namespace
+
+struct real_gpu
+{
+        real_gpu_params prm;
+        std::string err;
+        cudaStream_t st;
+        cudaEvent_t ev[8];
+        uint64_t held;
+        int sm_count;
+
+        // text
+        bool have_text;
+        DevBuf text, nmask, rec;
+        uint64_t n_total, shard_begin, shard_len, own_begin, own_end;
+        uint32_t nrec, fileid;
+
+        // reads
+        bool have_reads;
+        DevBuf mapped, qual, offs, rpack, rlen, seeds, usable, usable_rank, bad;
+        uint64_t nreads, n_usable, total_bases;
+        uint32_t W, maxlen;
+        bool qual_present;
+
+        // index
+        Table tab[3];
+        uint32_t F, keybits;
+
+        // results
+        DevBuf ll, hits_raw, hits_seg, hits_out, counters, counts, starts, cursor, scantmp, info, scores;
+        uint64_t hit_cap;
+        real_gpu_hit * host_hits;
+        uint64_t host_hits_cap;
+
+        real_gpu_stats stats;
+
+        real_gpu() : st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+                     nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
+                     F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
+        {
+                memset(&prm, 0, sizeof(prm));
+                memset(&stats, 0, sizeof(stats));
+                for ( int i = 0; i < 8; ++i ) ev[i] = nullptr;
+        }
+};
+
+namespace
+{
+
+void dev_free(real_gpu * h, DevBuf & b)
+{
+        if ( b.p )
+        {
+                cudaFree(b.p);
+                h->held -= b.bytes;
+        }
+        b.p = nullptr; b.bytes = 0;
+}
+
+void dev_alloc(real_gpu * h, DevBuf & b, size_t bytes)
+{
+        dev_free(h, b);
+        if ( bytes == 0 ) bytes = 16;
+        RG_CUDA(cudaMalloc(&b.p, bytes));
+        b.bytes = bytes;
+        h->held += bytes;
+}
+
+// grows only
+void dev_reserve(real_gpu * h, DevBuf & b, size_t bytes)
+{
+        if ( b.bytes < bytes || ! b.p )
+                dev_alloc(h, b, bytes);
+}
+
+template<typename T> T * ptr(DevBuf const & b) { return reinterpret_cast<T *>(b.p); }
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+void launch_count(real_gpu * h, uint32_t n = 1) { h->stats.total_launches += n; }
+
+float elapsed(cudaEvent_t a, cudaEvent_t b)
+{
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+}
+
+int fail(real_gpu * h, int code, std::string const & msg)
+{
+        if ( h ) h->err = msg;
+        return code;
+}
+
+#define RG_API_BEGIN(h)  if ( ! (h) ) return REAL_GPU_E_ARG; try { RG_CUDA(cudaSetDevice((h)->prm.device));
+#define RG_API_END(h)    } catch ( realgpu::CudaError const & e ) { return fail((h), REAL_GPU_E_CUDA, e.what()); } \
+                           catch ( std::exception const & e ) { return fail((h), REAL_GPU_E_CUDA, e.what()); }
+
+// ---------------------------------------------------------------------------------------------
+// text
+// ---------------------------------------------------------------------------------------------
+
+int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const uint64_t * nmask, bool on_device,
+                    uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
+                    const uint64_t * record_starts, uint32_t nrecords)
+{
+        if ( ! words || ! nmask || ! record_starts || nrecords == 0 )
+                return fail(h, REAL_GPU_E_ARG, "set_text: null pointer or no records");
+        if ( shard_begin % 64 )
+                return fail(h, REAL_GPU_E_ARG, "set_text: shard_begin must be a multiple of 64");
+        if ( shard_begin + shard_len > n_total || own_begin > own_end || own_end > n_total || own_begin < shard_begin )
+                return fail(h, REAL_GPU_E_ARG, "set_text: inconsistent shard/own ranges");
+        if ( n_total >= (1ULL << 35) )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text: text longer than 2^35 bases (UniqueMatchInfo.hpp:29-33)");
+        if ( fileid >= 64 )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text: fileid >= 64 (UniqueMatchInfo.hpp:31)");
+        if ( record_starts[nrecords] != n_total )
+                return fail(h, REAL_GPU_E_ARG, "set_text: record_starts[nrecords] must equal n_total");
+
+        uint64_t const nw = (shard_len + 31) / 32, nmw = (shard_len + 63) / 64;
+        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS;
+        size_t const tbytes = (TEXT_PAD_WORDS + nw + tail) * 8, mbytes = (TEXT_PAD_WORDS + nmw + tail) * 8;
+
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        dev_alloc(h, h->text, tbytes);
+        dev_alloc(h, h->nmask, mbytes);
+        dev_alloc(h, h->rec, (size_t)(nrecords + 1) * 8);
+        RG_CUDA(cudaMemsetAsync(h->text.p, 0, tbytes, h->st));
+        RG_CUDA(cudaMemsetAsync(h->nmask.p, 0, mbytes, h->st));
+        cudaMemcpyKind const kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, words, nw * 8, kind, h->st));
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, nmask, nmw * 8, kind, h->st));
+        RG_CUDA(cudaMemcpyAsync(h->rec.p, record_starts, (size_t)(nrecords + 1) * 8, cudaMemcpyHostToDevice, h->st));
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.h2d_text_ms = elapsed(h->ev[0], h->ev[1]);
+
+        h->fileid = fileid; h->n_total = n_total; h->shard_begin = shard_begin; h->shard_len = shard_len;
+        h->own_begin = own_begin; h->own_end = own_end; h->nrec = nrecords;
+        h->have_text = true;
+        return REAL_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reads + index
+// ---------------------------------------------------------------------------------------------
+
+void build_table(real_gpu * h, int t, DevBuf & k0, DevBuf & v0, DevBuf & k1, DevBuf & v1, DevBuf & flags, RadixSortTemp const & rst)
+{
+        Table & T = h->tab[t];
+        T.nlists = table_lists(t, h->prm.seedkmax);
+        T.hb = h->prm.table_bits ? std::min<uint32_t>(h->prm.table_bits, std::min<uint32_t>(h->keybits, 32)) : std::min<uint32_t>(h->keybits, 32);
+        T.nentries = h->n_usable * 2 * T.nlists;
+        T.ndistinct = 0;
+        uint64_t const nslots = 1ULL << T.hb;
+        T.nsectors = (uint32_t)((nslots + SECTOR_SLOTS - 1) / SECTOR_SLOTS);
+        dev_alloc(h, T.bitmap, (size_t)T.nsectors * SECTOR_WORDS * 4);
+        RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap.bytes, h->st));
+        dev_alloc(h, T.E, std::max<size_t>(16, T.nentries * sizeof(Entry)));
+        if ( T.nentries == 0 )
+                return;
+        if ( T.nentries >= (1ULL << 32) )
+                throw CudaError("index: more than 2^32 entries in one table");
+        uint32_t const n = (uint32_t)T.nentries;
+
+        TableGeom G; G.F = h->F; G.keybits = h->keybits; G.hb = T.hb; G.nlists = T.nlists; G.table = t;
+        k_gen_entries<<<blocks_for(2 * h->nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable_rank), ptr<uint32_t>(h->usable),
+                                                                        h->nreads, G, ptr<uint32_t>(k0), ptr<uint32_t>(v0));
+        RG_KERNEL_CHECK(); launch_count(h);
+
+        uint32_t nl = 0;
+        int const where = radix_sort_pairs(ptr<uint32_t>(k0), ptr<uint32_t>(v0), ptr<uint32_t>(k1), ptr<uint32_t>(v1), n, T.hb, rst, h->st, &nl);
+        launch_count(h, nl);
+        uint32_t * sk = where ? ptr<uint32_t>(k1) : ptr<uint32_t>(k0);
+        uint32_t * sv = where ? ptr<uint32_t>(v1) : ptr<uint32_t>(v0);
+        uint32_t * other = where ? ptr<uint32_t>(k0) : ptr<uint32_t>(k1);    // free ping-pong half: head flags + their scan
+
+        k_mark_heads<<<blocks_for(n, 256), 256, 0, h->st>>>(sk, n, ptr<uint32_t>(flags));
+        RG_KERNEL_CHECK(); launch_count(h);
+        nl = 0;
+        exclusive_scan_u32(ptr<uint32_t>(flags), other, n, rst.scan_tmp, h->st, &nl);
+        launch_count(h, nl);
+        uint32_t last_scan = 0, last_flag = 0;
+        RG_CUDA(cudaMemcpyAsync(&last_scan, other + (n - 1), 4, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaMemcpyAsync(&last_flag, ptr<uint32_t>(flags) + (n - 1), 4, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        T.ndistinct = (uint64_t)last_scan + last_flag;
+
+        k_place_entries<<<blocks_for(n, 256), 256, 0, h->st>>>(sk, sv, other, n, (uint32_t)T.ndistinct, ptr<uint64_t>(h->seeds), ptr<Entry>(T.E), ptr<uint32_t>(T.bitmap));
+        RG_KERNEL_CHECK(); launch_count(h);
+
+        // rank headers: per-sector popcount -> exclusive scan -> header word
+        uint32_t * cnt = ptr<uint32_t>(flags);       // reuse (nsectors may exceed n: flags is sized for both)
+        k_sector_counts<<<blocks_for(T.nsectors, 256), 256, 0, h->st>>>(ptr<uint32_t>(T.bitmap), T.nsectors, cnt);
+        RG_KERNEL_CHECK(); launch_count(h);
+        nl = 0;
+        exclusive_scan_u32(cnt, cnt, T.nsectors, rst.scan_tmp, h->st, &nl);
+        launch_count(h, nl);
+        k_sector_headers<<<blocks_for(T.nsectors, 256), 256, 0, h->st>>>(ptr<uint32_t>(T.bitmap), T.nsectors, cnt);
+        RG_KERNEL_CHECK(); launch_count(h);
+}
+
+int build_from_device(real_gpu * h)
+{
+        uint32_t const seedl = h->prm.seedl;
+        h->F = seedl / 4;
+        h->keybits = seedl;                    // two fragments of F bases = 4F bits
+        h->W = std::max<uint32_t>(1, (h->maxlen + 31) / 32);
+        uint64_t const nreads = h->nreads;
+
+        RG_CUDA(cudaEventRecord(h->ev[2], h->st));
+        dev_alloc(h, h->rpack, (size_t)nreads * 2 * h->W * 8 + 16);
+        dev_alloc(h, h->rlen, (size_t)nreads * 4 + 16);
+        dev_alloc(h, h->seeds, (size_t)nreads * 2 * 8 + 16);
+        dev_alloc(h, h->usable, (size_t)nreads * 4 + 16);
+        dev_alloc(h, h->usable_rank, (size_t)nreads * 4 + 16);
+        dev_alloc(h, h->bad, (size_t)nreads * 4 + 16);
+        RG_CUDA(cudaMemsetAsync(h->bad.p, 0, h->bad.bytes, h->st));
+        if ( nreads )
+        {
+                k_pack_reads<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(ptr<uint8_t>(h->mapped), ptr<uint64_t>(h->offs), nreads, h->W,
+                                                                                  ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->bad));
+                RG_KERNEL_CHECK(); launch_count(h);
+                k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
+                                                                       ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        RG_CUDA(cudaEventRecord(h->ev[3], h->st));
+
+        // compaction rank of usable reads
+        dev_reserve(h, h->scantmp, scan_temp_elems(std::max<uint64_t>(nreads, 1)) * 4 + 64);
+        h->n_usable = 0;
+        if ( nreads )
+        {
+                uint32_t nl = 0;
+                exclusive_scan_u32(ptr<uint32_t>(h->usable), ptr<uint32_t>(h->usable_rank), nreads, ptr<uint32_t>(h->scantmp), h->st, &nl);
+                launch_count(h, nl);
+                uint32_t lr = 0, lu = 0;
+                RG_CUDA(cudaMemcpyAsync(&lr, ptr<uint32_t>(h->usable_rank) + (nreads - 1), 4, cudaMemcpyDeviceToHost, h->st));
+                RG_CUDA(cudaMemcpyAsync(&lu, ptr<uint32_t>(h->usable) + (nreads - 1), 4, cudaMemcpyDeviceToHost, h->st));
+                RG_CUDA(cudaStreamSynchronize(h->st));
+                h->n_usable = (uint64_t)lr + lu;
+        }
+
+        // sort workspace sized for the largest table (A: 3 lists)
+        uint64_t const maxent = std::max<uint64_t>(1, h->n_usable * 2 * table_lists(0, h->prm.seedkmax));
+        uint32_t const hbmax = std::min<uint32_t>(h->keybits, 32);
+        uint64_t const maxsectors = ((1ULL << hbmax) + SECTOR_SLOTS - 1) / SECTOR_SLOTS;
+        DevBuf k0, v0, k1, v1, flags, hist, stmp;
+        dev_alloc(h, k0, maxent * 4 + 16); dev_alloc(h, v0, maxent * 4 + 16);
+        dev_alloc(h, k1, maxent * 4 + 16); dev_alloc(h, v1, maxent * 4 + 16);
+        dev_alloc(h, flags, std::max<uint64_t>(maxent, maxsectors) * 4 + 16);
+        uint64_t const nblk = rs_num_blocks(maxent);
+        dev_alloc(h, hist, (size_t)RS_BINS * nblk * 4 + 16);
+        uint64_t const scan_need = std::max<uint64_t>(std::max<uint64_t>((uint64_t)RS_BINS * nblk, maxent), maxsectors);
+        dev_alloc(h, stmp, scan_temp_elems(scan_need) * 4 + 64);
+        RadixSortTemp rst; rst.hist = ptr<uint32_t>(hist); rst.scan_tmp = ptr<uint32_t>(stmp);
+
+        for ( int t = 0; t < 3; ++t )
+                build_table(h, t, k0, v0, k1, v1, flags, rst);
+        RG_CUDA(cudaEventRecord(h->ev[4], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        dev_free(h, k0); dev_free(h, v0); dev_free(h, k1); dev_free(h, v1); dev_free(h, flags); dev_free(h, hist); dev_free(h, stmp);
+        // mapped bytes are not needed once packed
+        dev_free(h, h->mapped);
+        dev_free(h, h->bad);
+
+        h->stats.pack_ms = elapsed(h->ev[2], h->ev[3]);
+        h->stats.index_ms = elapsed(h->ev[3], h->ev[4]);
+
+        // fresh unique state (UniqueMatchInfo.hpp:172,190)
+        dev_alloc(h, h->info, (size_t)nreads * 8 + 16);
+        RG_CUDA(cudaMemsetAsync(h->info.p, 0, h->info.bytes, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->have_reads = true;
+        return REAL_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan
+// ---------------------------------------------------------------------------------------------
+
+void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
+{
+        memset(&P, 0, sizeof(P));
+        P.text = ptr<uint64_t>(h->text) + TEXT_PAD_WORDS;
+        P.nmask = ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS;
+        P.shard_begin = h->shard_begin;
+        uint32_t const seedl = h->prm.seedl;
+        // seed windows this shard evaluates: every window whose hit start (p for '+', p-(L-seedl) for '-')
+        // may fall into [own_begin, own_end)
+        uint64_t gwin_b = h->own_begin;
+        uint64_t gwin_e = h->own_end + (h->maxlen > seedl ? h->maxlen - seedl : 0);
+        uint64_t const last_window_end = (h->n_total >= seedl) ? (h->n_total - seedl + 1) : 0;
+        gwin_e = std::min(gwin_e, last_window_end);
+        uint64_t const shard_end = h->shard_begin + h->shard_len;
+        if ( gwin_e + seedl > shard_end + 1 )
+                gwin_e = (shard_end + 1 >= seedl) ? (shard_end + 1 - seedl) : 0;
+        if ( gwin_e < gwin_b ) gwin_e = gwin_b;
+        P.win_begin = gwin_b - h->shard_begin;
+        P.win_end = gwin_e - h->shard_begin;
+        P.x_begin = P.win_begin;
+        P.x_end = (P.win_end > P.win_begin) ? std::min<uint64_t>(P.win_end + 2 * h->F, h->shard_len) : P.win_begin;
+        P.own_begin = h->own_begin;
+        P.own_end = h->own_end;
+        for ( int t = 0; t < 3; ++t )
+        {
+                P.tab[t].bitmap = ptr<uint32_t>(h->tab[t].bitmap);
+                P.tab[t].E = ptr<Entry>(h->tab[t].E);
+                P.tab[t].hb = h->tab[t].hb;
+                P.tab[t].nlists = h->tab[t].nentries ? h->tab[t].nlists : 0;
+        }
+        P.seedl = seedl; P.F = h->F; P.keybits = h->keybits; P.seedkmax = h->prm.seedkmax; P.totalkmax = h->prm.totalkmax;
+        P.rpack = ptr<uint64_t>(h->rpack); P.W = h->W; P.rlen = ptr<uint32_t>(h->rlen);
+        P.rec = ptr<uint64_t>(h->rec); P.nrec = h->nrec; P.fileid = h->fileid;
+        P.mode = mode;
+        P.hits = ptr<RawHit>(h->hits_raw);
+        P.hit_cap = h->hit_cap;
+        P.hit_count = ptr<unsigned long long>(h->counters);
+        P.stats = ptr<unsigned long long>(h->counters) + 1;
+        P.info = ptr<unsigned long long>(h->info);
+}
+
+// launches K3 once; returns the number of hits the kernel counted
+uint64_t run_scan(real_gpu * h, int mode)
+{
+        dev_reserve(h, h->counters, 8 * 8);
+        RG_CUDA(cudaMemsetAsync(h->counters.p, 0, 8 * 8, h->st));
+        ScanParams P;
+        fill_scan_params(h, P, mode);
+        uint64_t const first_tile = P.x_begin / SC_TILE_POS, end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
+        uint64_t const ntiles = (P.x_end > P.x_begin) ? (end_tile - first_tile) : 0;
+        RG_CUDA(cudaEventRecord(h->ev[5], h->st));
+        if ( ntiles )
+        {
+                int occ = 0;
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, SC_THREADS, 0));
+                if ( occ < 1 ) occ = 1;
+                unsigned const grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * occ);
+                k_scan<<<grid, SC_THREADS, 0, h->st>>>(P);
+                RG_KERNEL_CHECK(); launch_count(h);
+                h->stats.scan_launches += 1;
+        }
+        RG_CUDA(cudaEventRecord(h->ev[6], h->st));
+        unsigned long long c[4] = {0, 0, 0, 0};
+        RG_CUDA(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.scan_ms = elapsed(h->ev[5], h->ev[6]);
+        h->stats.n_windows = P.x_end - P.x_begin;
+        uint32_t nt = 0;
+        for ( int t = 0; t < 3; ++t ) if ( P.tab[t].nlists ) ++nt;
+        h->stats.n_probes = h->stats.n_windows * nt;
+        h->stats.n_candidates = c[1];
+        h->stats.n_seedpass = c[2];
+        h->stats.n_hits = c[3];
+        return (mode == 0) ? (uint64_t)c[0] : (uint64_t)c[3];
+}
+
+int check_ready(real_gpu * h)
+{
+        if ( ! h->have_text ) return fail(h, REAL_GPU_E_STATE, "no text set");
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        return REAL_GPU_OK;
+}
+
+} // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+
+extern "C" {
+
+int real_gpu_abi_version(void) { return REAL_GPU_ABI_VERSION; }
+
+int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
+{
+        if ( ! params || ! out ) return REAL_GPU_E_ARG;
+        *out = nullptr;
+        if ( params->struct_size != sizeof(real_gpu_params) ) return REAL_GPU_E_ARG;
+        real_gpu * h = new real_gpu();
+        h->prm = *params;
+        h->prm.ll_table = nullptr;
+        int code = REAL_GPU_OK;
+        try
+        {
+                // option domain = what RealOptions lets through (RealOptions.cpp:434-453,176-180)
+                if ( params->seedl < 4 || params->seedl > 64 || params->seedl % 4 )
+                        throw std::invalid_argument("seed length must be a multiple of 4 in 4..64");
+                if ( params->seedl > 32 )
+                        throw std::invalid_argument("seed lengths above 32 (64-bit signatures) are not built in this version");
+                if ( params->seedkmax > 2 ) throw std::invalid_argument("seedkmax > 2");
+                if ( params->totalkmax > 15 ) throw std::invalid_argument("totalkmax > 15");
+                if ( params->scores && ! params->ll_table ) throw std::invalid_argument("scores requested without ll_table");
+                int ndev = 0;
+                RG_CUDA(cudaGetDeviceCount(&ndev));
+                if ( params->device < 0 || params->device >= ndev ) throw CudaError("no such CUDA device");
+                RG_CUDA(cudaSetDevice(params->device));
+                cudaDeviceProp prop;
+                RG_CUDA(cudaGetDeviceProperties(&prop, params->device));
+                if ( prop.major < 10 ) throw CudaError("device is not sm_100 class; this library only carries sm_100a code");
+                h->sm_count = prop.multiProcessorCount;
+                RG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+                for ( int i = 0; i < 8; ++i ) RG_CUDA(cudaEventCreate(&h->ev[i]));
+                if ( params->ll_table )
+                {
+                        dev_alloc(h, h->ll, 1024 * 8);
+                        RG_CUDA(cudaMemcpyAsync(h->ll.p, params->ll_table, 1024 * 8, cudaMemcpyHostToDevice, h->st));
+                        RG_CUDA(cudaStreamSynchronize(h->st));
+                }
+        }
+        catch ( std::invalid_argument const & e ) { h->err = e.what(); code = REAL_GPU_E_ARG; }
+        catch ( std::exception const & e ) { h->err = e.what(); code = REAL_GPU_E_CUDA; }
+        if ( code != REAL_GPU_OK )
+        {
+                fprintf(stderr, "real_gpu_create: %s\n", h->err.c_str());
+                real_gpu_destroy(h);
+                return code;
+        }
+        *out = h;
+        return REAL_GPU_OK;
+}
+
+int real_gpu_destroy(real_gpu * h)
+{
+        if ( ! h ) return REAL_GPU_OK;
+        cudaSetDevice(h->prm.device);
+        DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
+                           &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
+        for ( DevBuf * b : all ) dev_free(h, *b);
+        for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
+        if ( h->host_hits ) cudaFreeHost(h->host_hits);
+        for ( int i = 0; i < 8; ++i ) if ( h->ev[i] ) cudaEventDestroy(h->ev[i]);
+        if ( h->st ) cudaStreamDestroy(h->st);
+        delete h;
+        return REAL_GPU_OK;
+}
+
+const char * real_gpu_last_error(const real_gpu * h) { return h ? h->err.c_str() : "null handle"; }
+
+int real_gpu_set_text(real_gpu * h, uint32_t fileid, const uint64_t * words, const uint64_t * nmask,
+                      uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
+                      const uint64_t * record_starts, uint32_t nrecords)
+{
+        RG_API_BEGIN(h)
+        return set_text_common(h, fileid, words, nmask, false, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords);
+        RG_API_END(h)
+}
+
+int real_gpu_set_text_device(real_gpu * h, uint32_t fileid, const uint64_t * d_words, const uint64_t * d_nmask,
+                             uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
+                             const uint64_t * record_starts, uint32_t nrecords)
+{
+        RG_API_BEGIN(h)
+        return set_text_common(h, fileid, d_words, d_nmask, true, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords);
+        RG_API_END(h)
+}
+
+int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * quality, const uint64_t * offsets, uint64_t nreads)
+{
+        RG_API_BEGIN(h)
+        if ( ! offsets || (nreads && ! mapped) ) return fail(h, REAL_GPU_E_ARG, "set_reads: null pointer");
+        if ( nreads >= (1ULL << 28) ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: more than 2^28 reads in one set");
+        uint64_t const total = offsets[nreads] - offsets[0];
+        uint32_t maxlen = 0;
+        for ( uint64_t i = 0; i < nreads; ++i )
+        {
+                if ( offsets[i+1] < offsets[i] ) return fail(h, REAL_GPU_E_ARG, "set_reads: offsets not ascending");
+                uint64_t const L = offsets[i+1] - offsets[i];
+                if ( L > 65535 ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: read longer than 65535 bases");
+                maxlen = std::max<uint32_t>(maxlen, (uint32_t)L);
+        }
+        h->have_reads = false;
+        h->nreads = nreads; h->total_bases = total; h->maxlen = maxlen;
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        dev_alloc(h, h->mapped, total + 64);
+        dev_alloc(h, h->offs, (nreads + 1) * 8);
+        if ( total ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, mapped + offsets[0], total, cudaMemcpyHostToDevice, h->st));
+        if ( offsets[0] != 0 )
+        {
+                std::vector<uint64_t> rel(nreads + 1);
+                for ( uint64_t i = 0; i <= nreads; ++i ) rel[i] = offsets[i] - offsets[0];
+                RG_CUDA(cudaMemcpyAsync(h->offs.p, rel.data(), (nreads + 1) * 8, cudaMemcpyHostToDevice, h->st));
+                RG_CUDA(cudaStreamSynchronize(h->st));
+        }
+        else
+                RG_CUDA(cudaMemcpyAsync(h->offs.p, offsets, (nreads + 1) * 8, cudaMemcpyHostToDevice, h->st));
+        h->qual_present = false;
+        if ( quality && (h->prm.scores || h->ll.p) )
+        {
+                dev_alloc(h, h->qual, total + 64);
+                if ( total ) RG_CUDA(cudaMemcpyAsync(h->qual.p, quality + offsets[0], total, cudaMemcpyHostToDevice, h->st));
+                h->qual_present = true;
+        }
+        else
+                dev_free(h, h->qual);
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
+        return build_from_device(h);
+        RG_API_END(h)
+}
+
+int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint8_t * d_quality, const uint64_t * d_offsets,
+                              uint64_t nreads, uint64_t total_bases, uint32_t maxlen)
+{
+        RG_API_BEGIN(h)
+        if ( ! d_offsets || (nreads && ! d_mapped) ) return fail(h, REAL_GPU_E_ARG, "set_reads_device: null pointer");
+        if ( nreads >= (1ULL << 28) ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: more than 2^28 reads in one set");
+        if ( maxlen > 65535 ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: read longer than 65535 bases");
+        h->have_reads = false;
+        h->nreads = nreads; h->total_bases = total_bases; h->maxlen = maxlen;
+        dev_alloc(h, h->mapped, total_bases + 64);
+        dev_alloc(h, h->offs, (nreads + 1) * 8);
+        if ( total_bases ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, d_mapped, total_bases, cudaMemcpyDeviceToDevice, h->st));
+        RG_CUDA(cudaMemcpyAsync(h->offs.p, d_offsets, (nreads + 1) * 8, cudaMemcpyDeviceToDevice, h->st));
+        h->qual_present = false;
+        if ( d_quality && (h->prm.scores || h->ll.p) )
+        {
+                dev_alloc(h, h->qual, total_bases + 64);
+                if ( total_bases ) RG_CUDA(cudaMemcpyAsync(h->qual.p, d_quality, total_bases, cudaMemcpyDeviceToDevice, h->st));
+                h->qual_present = true;
+        }
+        else
+                dev_free(h, h->qual);
+        h->stats.h2d_reads_ms = 0;
+        return build_from_device(h);
+        RG_API_END(h)
+}
+
+int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhits)
+{
+        RG_API_BEGIN(h)
+        if ( ! hits || ! nhits ) return fail(h, REAL_GPU_E_ARG, "match_all: null pointer");
+        int const rc = check_ready(h);
+        if ( rc ) return rc;
+        *hits = nullptr; *nhits = 0;
+        h->stats.scan_launches = 0;
+        if ( h->hit_cap == 0 )
+        {
+                h->hit_cap = std::max<uint64_t>(1u << 16, 2 * h->nreads);
+                dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
+        }
+        uint64_t found = run_scan(h, 0);
+        if ( found > h->hit_cap )
+        {
+                // the buffer was too small: the kernel counted everything, so size it exactly and rescan
+                h->hit_cap = found + found / 8 + 1024;
+                dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
+                found = run_scan(h, 0);
+                if ( found > h->hit_cap ) return fail(h, REAL_GPU_E_CUDA, "match_all: hit count changed between scans");
+        }
+        if ( found >= (1ULL << 32) ) return fail(h, REAL_GPU_E_LIMIT, "match_all: more than 2^32 hits in one call");
+
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        if ( found )
+        {
+                if ( h->prm.scores )
+                {
+                        k_score_hits<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<double>(h->ll),
+                                ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, h->shard_begin, ptr<uint64_t>(h->rpack), h->W, ptr<uint32_t>(h->rlen),
+                                h->qual_present ? ptr<uint8_t>(h->qual) : nullptr, ptr<uint64_t>(h->offs));
+                        RG_KERNEL_CHECK(); launch_count(h);
+                }
+                // counting sort by read, then per-read ordering
+                dev_reserve(h, h->counts, h->nreads * 4 + 16);
+                dev_reserve(h, h->starts, h->nreads * 4 + 16);
+                dev_reserve(h, h->cursor, h->nreads * 4 + 16);
+                dev_reserve(h, h->scantmp, scan_temp_elems(h->nreads) * 4 + 64);
+                dev_reserve(h, h->hits_seg, found * sizeof(RawHit));
+                dev_reserve(h, h->hits_out, found * sizeof(real_gpu_hit));
+                RG_CUDA(cudaMemsetAsync(h->counts.p, 0, h->nreads * 4, h->st));
+                RG_CUDA(cudaMemsetAsync(h->cursor.p, 0, h->nreads * 4, h->st));
+                k_hit_count<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<uint32_t>(h->counts));
+                RG_KERNEL_CHECK(); launch_count(h);
+                uint32_t nl = 0;
+                exclusive_scan_u32(ptr<uint32_t>(h->counts), ptr<uint32_t>(h->starts), h->nreads, ptr<uint32_t>(h->scantmp), h->st, &nl);
+                launch_count(h, nl);
+                k_hit_scatter<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<uint32_t>(h->starts), ptr<uint32_t>(h->cursor), ptr<RawHit>(h->hits_seg));
+                RG_KERNEL_CHECK(); launch_count(h);
+                k_hit_order<real_gpu_hit><<<blocks_for(h->nreads, 128), 128, 0, h->st>>>(ptr<RawHit>(h->hits_seg), ptr<uint32_t>(h->starts), ptr<uint32_t>(h->counts),
+                                                                                        h->nreads, h->fileid, ptr<real_gpu_hit>(h->hits_out));
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        if ( found > h->host_hits_cap )
+        {
+                if ( h->host_hits ) cudaFreeHost(h->host_hits);
+                h->host_hits = nullptr; h->host_hits_cap = 0;
+                uint64_t const cap = found + found / 4 + 1024;
+                RG_CUDA(cudaMallocHost(&h->host_hits, cap * sizeof(real_gpu_hit)));
+                h->host_hits_cap = cap;
+        }
+        if ( found )
+                RG_CUDA(cudaMemcpyAsync(h->host_hits, h->hits_out.p, found * sizeof(real_gpu_hit), cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaEventRecord(h->ev[2], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.post_ms = elapsed(h->ev[0], h->ev[1]);
+        h->stats.d2h_ms = elapsed(h->ev[1], h->ev[2]);
+        *hits = h->host_hits;
+        *nhits = found;
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_match_unique(real_gpu * h)
+{
+        RG_API_BEGIN(h)
+        int const rc = check_ready(h);
+        if ( rc ) return rc;
+        if ( h->prm.scores )
+                return fail(h, REAL_GPU_E_ARG, "match_unique with scores (order-dependent epsilon rule, matchUniqueImplementation.cpp:179-248) is not built in this version");
+        if ( h->nrec + 1 > 65536 )
+                return REAL_GPU_OK;   // the reference skips such files (matchUniqueImplementation.cpp:1139-1143)
+        h->stats.scan_launches = 0;
+        run_scan(h, 1);
+        h->stats.post_ms = 0; h->stats.d2h_ms = 0;
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( ! info ) return fail(h, REAL_GPU_E_ARG, "get_unique: null pointer");
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        if ( h->nreads ) RG_CUDA(cudaMemcpyAsync(info, h->info.p, h->nreads * 8, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.d2h_ms = elapsed(h->ev[0], h->ev[1]);
+        if ( scores ) for ( uint64_t i = 0; i < h->nreads; ++i ) scores[i] = 0.0f;
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_reset_unique(real_gpu * h)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        RG_CUDA(cudaMemsetAsync(h->info.p, 0, h->info.bytes, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_unique_export_keys(real_gpu * h, uint64_t * d_keys)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( ! d_keys ) return fail(h, REAL_GPU_E_ARG, "null pointer");
+        if ( h->nreads )
+        {
+                k_unique_export<<<blocks_for(h->nreads, 256), 256, 0, h->st>>>(ptr<unsigned long long>(h->info), h->nreads, d_keys);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_unique_export_ties(real_gpu * h, const uint64_t * d_min_keys, uint8_t * d_ties)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( ! d_min_keys || ! d_ties ) return fail(h, REAL_GPU_E_ARG, "null pointer");
+        if ( h->nreads )
+        {
+                k_unique_ties<<<blocks_for(h->nreads, 256), 256, 0, h->st>>>(ptr<unsigned long long>(h->info), h->nreads, d_min_keys, d_ties);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_unique_import(real_gpu * h, const uint64_t * d_min_keys, const uint8_t * d_tie_sums)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( ! d_min_keys || ! d_tie_sums ) return fail(h, REAL_GPU_E_ARG, "null pointer");
+        if ( h->nreads )
+        {
+                k_unique_import<<<blocks_for(h->nreads, 256), 256, 0, h->st>>>(ptr<unsigned long long>(h->info), h->nreads, d_min_keys, d_tie_sums);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_match_gaps(real_gpu * h, uint64_t)
+{
+        return fail(h, REAL_GPU_E_ARG, "match_gaps: the gapped extension kernel is not built in this version");
+}
+
+int real_gpu_get_gaps(real_gpu * h, real_gpu_gapinfo *)
+{
+        return fail(h, REAL_GPU_E_ARG, "get_gaps: the gapped extension kernel is not built in this version");
+}
+
+int real_gpu_get_stats(real_gpu * h, real_gpu_stats * out)
+{
+        if ( ! h || ! out ) return REAL_GPU_E_ARG;
+        *out = h->stats;
+        return REAL_GPU_OK;
+}
+
+void * real_gpu_stream(real_gpu * h) { return h ? (void *)h->st : nullptr; }
+uint64_t real_gpu_device_bytes(const real_gpu * h) { return h ? h->held : 0; }
+
+int real_gpu_synth_text(int device, uint64_t seed, uint64_t first_word, uint64_t nwords, uint32_t n_per_million,
+                        uint64_t * d_words, uint64_t * d_nmask_or_null)
+{
+        try
+        {
+                RG_CUDA(cudaSetDevice(device));
+                if ( nwords )
+                {
+                        k_synth_text<<<blocks_for(nwords, 256), 256>>>(seed, first_word, nwords, d_nmask_or_null ? n_per_million : 0, d_words);
+                        RG_KERNEL_CHECK();
+                        if ( d_nmask_or_null )
+                        {
+                                if ( first_word & 1 ) return REAL_GPU_E_ARG;
+                                uint64_t const nm = (nwords + 1) / 2;
+                                k_synth_nmask<<<blocks_for(nm, 256), 256>>>(seed, first_word >> 1, nm, n_per_million, d_nmask_or_null);
+                                RG_KERNEL_CHECK();
+                        }
+                }
+                RG_CUDA(cudaDeviceSynchronize());
+        }
+        catch ( std::exception const & e ) { fprintf(stderr, "real_gpu_synth_text: %s\n", e.what()); return REAL_GPU_E_CUDA; }
+        return REAL_GPU_OK;
+}
+
+int real_gpu_synth_reads(int device, uint64_t seed, const uint64_t * d_words, const uint64_t * d_nmask_or_null, uint64_t text_n,
+                         uint64_t total_reads, uint64_t first_read, uint64_t nreads, uint32_t length, uint32_t sub_per_16384,
+                         uint8_t * d_mapped, uint8_t * d_quality_or_null)
+{
+        try
+        {
+                RG_CUDA(cudaSetDevice(device));
+                if ( length == 0 || length > 256 || text_n < length || total_reads == 0 ) return REAL_GPU_E_ARG;
+                if ( nreads )
+                {
+                        k_synth_reads<<<blocks_for(nreads, 128), 128>>>(seed, d_words, d_nmask_or_null, text_n, total_reads, first_read, nreads, length,
+                                                                       sub_per_16384, d_mapped, d_quality_or_null);
+                        RG_KERNEL_CHECK();
+                }
+                RG_CUDA(cudaDeviceSynchronize());
+        }
+        catch ( std::exception const & e ) { fprintf(stderr, "real_gpu_synth_reads: %s\n", e.what()); return REAL_GPU_E_CUDA; }
+        return REAL_GPU_OK;
+}
+
+} // extern "C"

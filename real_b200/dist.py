@@ -1,0 +1,60 @@
+"""Multi-GPU layer of the matching path: one process per GPU, text sharded, read index replicated.
+
+matchAll needs no exchange (every shard reports the hits that START in its own range).  matchUnique
+has exactly one exchange step per text file, the cross-shard fold of the per-read UniqueMatchInfo
+(the reference folds hits into `uniqueinfo[patID]` inside one process,
+matchUniqueImplementation.cpp:1097,1282): a MIN all-reduce of order-preserving 63-bit keys followed
+by a SUM all-reduce of tie flags (include/real_gpu.h, "cross-shard exchange").  torch.distributed is
+the plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests); the key transforms are device
+kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+UNIQUE_KEY_NONE = 0x7FFFFFFFFFFFFFFF
+
+
+class HandleShard:
+    """Adapter: one real_gpu handle as a participant of the exchange."""
+
+    def __init__(self, handle, nreads: int):
+        self.handle = handle
+        self.nreads = nreads
+        self.device = torch.device("cuda", handle.device)
+
+    def export_keys(self, keys: torch.Tensor) -> None:
+        self.handle.unique_export_keys(keys.data_ptr())
+
+    def export_ties(self, min_keys: torch.Tensor, ties: torch.Tensor) -> None:
+        self.handle.unique_export_ties(min_keys.data_ptr(), ties.data_ptr())
+
+    def import_merged(self, min_keys: torch.Tensor, tie_sums: torch.Tensor) -> None:
+        self.handle.unique_import(min_keys.data_ptr(), tie_sums.data_ptr())
+
+    def sync(self) -> None:
+        torch.cuda.synchronize(self.device)
+
+
+def unique_exchange(shard, group: Optional[dist.ProcessGroup] = None, keys: Optional[torch.Tensor] = None,
+                    ties: Optional[torch.Tensor] = None) -> None:
+    """Folds the per-read unique state of all ranks into the state every rank would hold had it
+    scanned the whole text.  `shard` provides export_keys / export_ties / import_merged / sync and
+    the attributes nreads, device (HandleShard on GPUs)."""
+    n = shard.nreads
+    if keys is None:
+        keys = torch.empty(n, dtype=torch.int64, device=shard.device)
+    if ties is None:
+        ties = torch.empty(n, dtype=torch.uint8, device=shard.device)
+    shard.export_keys(keys)                                   # returns after the kernel has finished
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+        shard.sync()
+    shard.export_ties(keys, ties)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(ties, op=dist.ReduceOp.SUM, group=group)
+        shard.sync()
+    shard.import_merged(keys, ties)

@@ -1,0 +1,239 @@
+"""ctypes binding of the C ABI in include/real_gpu.h (libreal_gpu.so, sm_100a CUDA).
+
+This is the only way the Python host layer reaches the kernels; there is no CPU path.  Loading
+fails loudly when the shared library is missing or exports less than the header declares.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import List
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libreal_gpu.so")
+HEADER_PATH = os.path.join(HERE, "..", "include", "real_gpu.h")
+
+REAL_GPU_OK = 0
+REAL_GPU_E_ARG = -1
+REAL_GPU_E_CUDA = -2
+REAL_GPU_E_STATE = -3
+REAL_GPU_E_LIMIT = -4
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("seedl", C.c_uint32), ("seedkmax", C.c_uint32),
+                ("totalkmax", C.c_uint32), ("scores", C.c_uint32), ("filter_mult", C.c_double), ("ll_table", C.c_void_p),
+                ("table_bits", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("h2d_text_ms", C.c_float), ("h2d_reads_ms", C.c_float), ("pack_ms", C.c_float), ("index_ms", C.c_float),
+                ("scan_ms", C.c_float), ("post_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("scan_launches", C.c_uint32), ("total_launches", C.c_uint32),
+                ("n_windows", C.c_uint64), ("n_probes", C.c_uint64), ("n_candidates", C.c_uint64),
+                ("n_seedpass", C.c_uint64), ("n_hits", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+HIT_DTYPE = np.dtype([("patid", "<u8"), ("pos", "<u8"), ("file", "<u4"), ("frag", "<u4"),
+                      ("k", "<u4"), ("inverted", "<u4"), ("score", "<f4"), ("reserved", "<u4")])
+GAP_DTYPE = np.dtype([("patid", "<u4"), ("mingap", "<u4"), ("where", "<u4"), ("start", "<u4"),
+                      ("gap_pos", "<u4"), ("present", "<u4")])
+
+
+def declared_symbols() -> List[str]:
+    """Every function name include/real_gpu.h declares."""
+    with open(HEADER_PATH) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(real_gpu_[a-z_0-9]+)\s*\(", src)))
+
+
+class RealGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("real_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    """Loads libreal_gpu.so; raises if it is absent (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _b
+        if _b.needs_build():
+            _b.build()
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libreal_gpu.so is missing: run `python -m real_b200.build` (the CUDA extension is mandatory)")
+    L = C.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    if missing:
+        raise RuntimeError("libreal_gpu.so does not export: %s" % ", ".join(missing))
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.real_gpu_abi_version.restype = i32
+    L.real_gpu_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.real_gpu_destroy.argtypes = [vp]
+    L.real_gpu_last_error.argtypes = [vp]
+    L.real_gpu_last_error.restype = C.c_char_p
+    L.real_gpu_set_text.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
+    L.real_gpu_set_text_device.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
+    L.real_gpu_set_reads.argtypes = [vp, vp, vp, vp, u64]
+    L.real_gpu_set_reads_device.argtypes = [vp, vp, vp, vp, u64, u64, u32]
+    L.real_gpu_match_all.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.real_gpu_match_unique.argtypes = [vp]
+    L.real_gpu_get_unique.argtypes = [vp, vp, vp]
+    L.real_gpu_reset_unique.argtypes = [vp]
+    L.real_gpu_unique_export_keys.argtypes = [vp, vp]
+    L.real_gpu_unique_export_ties.argtypes = [vp, vp, vp]
+    L.real_gpu_unique_import.argtypes = [vp, vp, vp]
+    L.real_gpu_match_gaps.argtypes = [vp, u64]
+    L.real_gpu_get_gaps.argtypes = [vp, vp]
+    L.real_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.real_gpu_stream.argtypes = [vp]
+    L.real_gpu_stream.restype = vp
+    L.real_gpu_device_bytes.argtypes = [vp]
+    L.real_gpu_device_bytes.restype = u64
+    L.real_gpu_synth_text.argtypes = [i32, u64, u64, u64, u32, vp, vp]
+    L.real_gpu_synth_reads.argtypes = [i32, u64, vp, vp, u64, u64, u64, u64, u32, u32, vp, vp]
+    for name in declared_symbols():
+        fn = getattr(L, name)
+        if name not in ("real_gpu_last_error", "real_gpu_stream", "real_gpu_device_bytes"):
+            fn.restype = i32
+    if L.real_gpu_abi_version() != 1:
+        raise RuntimeError("libreal_gpu.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _np_ptr(a: np.ndarray, dtype) -> int:
+    assert a.dtype == np.dtype(dtype) and a.flags["C_CONTIGUOUS"], (a.dtype, dtype)
+    return a.ctypes.data
+
+
+class Handle:
+    """Thin RAII wrapper of one real_gpu handle (one CUDA device, single-threaded)."""
+
+    def __init__(self, seedl: int = 32, seedkmax: int = 2, totalkmax: int = 5, scores: bool = False,
+                 filter_mult: float = 0.0, ll_table: np.ndarray | None = None, device: int = 0, table_bits: int = 0):
+        self.L = load()
+        self._ll = None
+        if ll_table is not None:
+            self._ll = np.ascontiguousarray(ll_table, dtype=np.float64)
+            assert self._ll.size == 1024
+        P = Params(C.sizeof(Params), device, seedl, seedkmax, totalkmax, 1 if scores else 0, filter_mult,
+                   self._ll.ctypes.data if self._ll is not None else None, table_bits, 0)
+        h = C.c_void_p()
+        rc = self.L.real_gpu_create(C.byref(P), C.byref(h))
+        if rc != 0:
+            raise RealGpuError(rc, "real_gpu_create failed (see stderr)")
+        self.h = h
+        self.device = device
+        self.nreads = 0
+        self.scores = scores
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.real_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RealGpuError(rc, self.L.real_gpu_last_error(self.h).decode())
+
+    # ---- text
+    def set_text(self, words: np.ndarray, nmask: np.ndarray, n_total: int, record_starts: np.ndarray, fileid: int = 0,
+                 shard_begin: int = 0, shard_len: int | None = None, own_begin: int | None = None, own_end: int | None = None):
+        shard_len = n_total - shard_begin if shard_len is None else shard_len
+        own_begin = shard_begin if own_begin is None else own_begin
+        own_end = shard_begin + shard_len if own_end is None else own_end
+        rs = np.ascontiguousarray(record_starts, dtype=np.uint64)
+        self._check(self.L.real_gpu_set_text(self.h, fileid, _np_ptr(words, np.uint64), _np_ptr(nmask, np.uint64), n_total,
+                                             shard_begin, shard_len, own_begin, own_end, rs.ctypes.data, rs.size - 1))
+
+    def set_text_device(self, d_words: int, d_nmask: int, n_total: int, record_starts: np.ndarray, fileid: int = 0,
+                        shard_begin: int = 0, shard_len: int | None = None, own_begin: int | None = None, own_end: int | None = None):
+        shard_len = n_total - shard_begin if shard_len is None else shard_len
+        own_begin = shard_begin if own_begin is None else own_begin
+        own_end = shard_begin + shard_len if own_end is None else own_end
+        rs = np.ascontiguousarray(record_starts, dtype=np.uint64)
+        self._check(self.L.real_gpu_set_text_device(self.h, fileid, d_words, d_nmask, n_total, shard_begin, shard_len,
+                                                    own_begin, own_end, rs.ctypes.data, rs.size - 1))
+
+    # ---- reads
+    def set_reads(self, mapped: np.ndarray, offsets: np.ndarray, quality: np.ndarray | None = None):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        mapped = np.ascontiguousarray(mapped, dtype=np.uint8)
+        q = None
+        if quality is not None:
+            quality = np.ascontiguousarray(quality, dtype=np.uint8)
+            q = quality.ctypes.data
+        self.nreads = int(offsets.size - 1)
+        self._check(self.L.real_gpu_set_reads(self.h, mapped.ctypes.data if mapped.size else None, q, offsets.ctypes.data, self.nreads))
+
+    def set_reads_device(self, d_mapped: int, d_offsets: int, nreads: int, total_bases: int, maxlen: int, d_quality: int | None = None):
+        self.nreads = nreads
+        self._check(self.L.real_gpu_set_reads_device(self.h, d_mapped, d_quality, d_offsets, nreads, total_bases, maxlen))
+
+    # ---- matching
+    def match_all(self) -> np.ndarray:
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.L.real_gpu_match_all(self.h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=HIT_DTYPE)
+        buf = (C.c_char * (n.value * HIT_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=HIT_DTYPE).copy()
+
+    def match_all_count(self) -> int:
+        """match_all without copying the records out of the library's pinned buffer."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.L.real_gpu_match_all(self.h, C.byref(p), C.byref(n)))
+        return int(n.value)
+
+    def match_unique(self):
+        self._check(self.L.real_gpu_match_unique(self.h))
+
+    def get_unique(self, out: np.ndarray | None = None):
+        info = out if out is not None else np.zeros(self.nreads, dtype=np.uint64)
+        sc = np.zeros(self.nreads, dtype=np.float32) if self.scores else None
+        self._check(self.L.real_gpu_get_unique(self.h, info.ctypes.data, sc.ctypes.data if sc is not None else None))
+        return info, sc
+
+    def reset_unique(self):
+        self._check(self.L.real_gpu_reset_unique(self.h))
+
+    def unique_export_keys(self, d_keys: int):
+        self._check(self.L.real_gpu_unique_export_keys(self.h, d_keys))
+
+    def unique_export_ties(self, d_min_keys: int, d_ties: int):
+        self._check(self.L.real_gpu_unique_export_ties(self.h, d_min_keys, d_ties))
+
+    def unique_import(self, d_min_keys: int, d_tie_sums: int):
+        self._check(self.L.real_gpu_unique_import(self.h, d_min_keys, d_tie_sums))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.L.real_gpu_get_stats(self.h, C.byref(s)))
+        return s.asdict()
+
+    def stream(self) -> int:
+        return int(self.L.real_gpu_stream(self.h) or 0)
+
+    def device_bytes(self) -> int:
+        return int(self.L.real_gpu_device_bytes(self.h))
