@@ -253,24 +253,32 @@ def main():
     ties = torch.empty(R, dtype=torch.uint8, device=dev) if unique else None
     hstream = torch.cuda.ExternalStream(h.stream(), device=dev)
 
-    phase = {"pack_ms": [], "index_ms": [], "scan_ms": [], "post_ms": [], "exchange_ms": []}
+    phase = {"pack_ms": [], "index_ms": [], "scan_ms": [], "post_ms": [], "d2h_ms": [], "h2d_text_ms": [], "exchange_ms": [],
+             "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": []}
     last_stats = {}
     nhits_holder = [0]
 
     def step_device():
+        t0 = time.perf_counter()
         h.set_reads_device(mapped.data_ptr(), offs.data_ptr(), R, R * L, L, d_quality=qual.data_ptr() if qual is not None else None)
+        t1 = time.perf_counter()
         h.set_text_device(sh_w.data_ptr(), sh_m.data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+        t2 = time.perf_counter()
         if unique:
             h.match_unique()
+            t3 = time.perf_counter()
             st = h.stats()
-            t0 = time.perf_counter()
             if world > 1:
                 rdist.unique_exchange(shard, keys=keys, ties=ties)
-            st["exchange_ms"] = (time.perf_counter() - t0) * 1e3
+            t4 = time.perf_counter()
         else:
             nhits_holder[0] = h.match_all_count()
+            t3 = t4 = time.perf_counter()
             st = h.stats()
-            st["exchange_ms"] = 0.0
+        st["exchange_ms"] = (t4 - t3) * 1e3
+        st["api_set_reads_ms"] = (t1 - t0) * 1e3
+        st["api_set_text_ms"] = (t2 - t1) * 1e3
+        st["api_match_ms"] = (t3 - t2) * 1e3
         return st
 
     def timed(fn, steps, warmup, collect=None):
