@@ -368,10 +368,10 @@ uint64_t run_scan(real_gpu * h, int mode)
         if ( ntiles )
         {
                 int occ = 0;
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, SC_THREADS, 0));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_text_scan, SC_THREADS, 0));
                 if ( occ < 1 ) occ = 1;
                 unsigned const grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * occ);
-                k_scan<<<grid, SC_THREADS, 0, h->st>>>(P);
+                k_text_scan<<<grid, SC_THREADS, 0, h->st>>>(P);
                 RG_KERNEL_CHECK(); launch_count(h);
                 h->stats.scan_launches += 1;
         }

@@ -272,7 +272,7 @@ __device__ __forceinline__ void follow_slot(ScanParams const & P, int table, uin
         }
 }
 
-__global__ void __launch_bounds__(SC_THREADS) k_scan(ScanParams P)
+__global__ void __launch_bounds__(SC_THREADS) k_text_scan(ScanParams P)
 {
         __shared__ __align__(128) uint64_t tile[2][SC_SMEM_WORDS];
         __shared__ __align__(8) uint64_t bar[2];
