@@ -116,12 +116,17 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 }
 
 // slot of a pair signature in a presence table with 2^hb slots.  Signatures that already fit are
-// used as they are (no collisions between different signatures); wider ones are folded.
+// used as they are (no collisions between different signatures); wider ones are folded, keeping
+// their top SLOT_PREFIX_BITS bits in place so that a key prefix still selects a contiguous slice of the
+// table (the multi-pass scan relies on that).
+static const uint32_t SLOT_PREFIX_BITS = 8;
 __host__ __device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t keybits, uint32_t hb)
 {
         if ( keybits <= hb )
                 return (uint32_t)key;
-        return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - hb));
+        uint32_t const low = hb - SLOT_PREFIX_BITS;
+        uint32_t const top = (uint32_t)(key >> (keybits - SLOT_PREFIX_BITS));
+        return (top << low) | (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - low));
 }
 
 } // namespace realgpu

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 using namespace realgpu;
@@ -67,8 +68,10 @@ struct real_gpu
         uint64_t host_hits_cap;
 
         real_gpu_stats stats;
+        int pass_bits_override;        // REAL_GPU_PASS_BITS (tuning), -1 = automatic
+        uint64_t l2_slice_bytes;       // table bytes one scan launch may touch (REAL_GPU_L2_SLICE_MB)
 
-        real_gpu() : st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : pass_bits_override(-1), l2_slice_bytes(32ull << 20), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -183,8 +186,16 @@ void build_table(real_gpu * h, int t, DevBuf & k0, DevBuf & v0, DevBuf & k1, Dev
 {
         Table & T = h->tab[t];
         T.nlists = table_lists(t, h->prm.seedkmax);
-        T.hb = h->prm.table_bits ? std::min<uint32_t>(h->prm.table_bits, std::min<uint32_t>(h->keybits, 32)) : std::min<uint32_t>(h->keybits, 32);
         T.nentries = h->n_usable * 2 * T.nlists;
+        {
+                // automatic: about 32 slots per entry of the largest table, at least 2^20, at most the key width / 32 bits
+                uint32_t const cap = std::min<uint32_t>(h->keybits, 32);
+                uint64_t const want = std::max<uint64_t>(1, h->n_usable * 2 * table_lists(0, h->prm.seedkmax)) * 32;
+                uint32_t autob = 20;
+                while ( autob < cap && (1ULL << autob) < want ) ++autob;
+                T.hb = h->prm.table_bits ? std::min<uint32_t>(h->prm.table_bits, cap) : std::min<uint32_t>(autob, cap);
+                if ( T.hb < h->keybits && T.hb < SLOT_PREFIX_BITS + 4 ) T.hb = std::min<uint32_t>(cap, SLOT_PREFIX_BITS + 4);
+        }
         T.ndistinct = 0;
         uint64_t const nslots = 1ULL << T.hb;
         T.nsectors = (uint32_t)((nslots + SECTOR_SLOTS - 1) / SECTOR_SLOTS);
@@ -367,13 +378,31 @@ uint64_t run_scan(real_gpu * h, int mode)
         RG_CUDA(cudaEventRecord(h->ev[5], h->st));
         if ( ntiles )
         {
+                // passes: cut the tables into key-prefix slices that stay resident in L2
+                uint64_t table_bytes = 0;
+                uint32_t maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
+                for ( int t = 0; t < 3; ++t )
+                        if ( P.tab[t].nlists )
+                                table_bytes += h->tab[t].bitmap.bytes;
+                uint32_t pass_bits = 0;
+                if ( h->pass_bits_override >= 0 )
+                        pass_bits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
+                else
+                        while ( pass_bits < maxbits && (table_bytes >> pass_bits) > h->l2_slice_bytes ) ++pass_bits;
+                size_t const smem = sizeof(ScanSmem);
+                RG_CUDA(cudaFuncSetAttribute(k_text_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 0;
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_text_scan, SC_THREADS, 0));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_text_scan, SC_THREADS, smem));
                 if ( occ < 1 ) occ = 1;
                 unsigned const grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * occ);
-                k_text_scan<<<grid, SC_THREADS, 0, h->st>>>(P);
-                RG_KERNEL_CHECK(); launch_count(h);
-                h->stats.scan_launches += 1;
+                P.pass_bits = pass_bits;
+                for ( uint32_t pass = 0; pass < (1u << pass_bits); ++pass )
+                {
+                        P.pass_id = pass;
+                        k_text_scan<<<grid, SC_THREADS, smem, h->st>>>(P);
+                        RG_KERNEL_CHECK(); launch_count(h);
+                        h->stats.scan_launches += 1;
+                }
         }
         RG_CUDA(cudaEventRecord(h->ev[6], h->st));
         unsigned long long c[4] = {0, 0, 0, 0};
@@ -434,6 +463,8 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 RG_CUDA(cudaGetDeviceProperties(&prop, params->device));
                 if ( prop.major < 10 ) throw CudaError("device is not sm_100 class; this library only carries sm_100a code");
                 h->sm_count = prop.multiProcessorCount;
+                if ( const char * e = getenv("REAL_GPU_PASS_BITS") ) h->pass_bits_override = atoi(e);
+                if ( const char * e = getenv("REAL_GPU_L2_SLICE_MB") ) h->l2_slice_bytes = (uint64_t)atoi(e) << 20;
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
                 for ( int i = 0; i < 8; ++i ) RG_CUDA(cudaEventCreate(&h->ev[i]));
                 if ( params->ll_table )

@@ -23,11 +23,11 @@ namespace realgpu
 {
 
 static const int SC_THREADS = 256;
-static const int SC_TILE_WORDS = SC_THREADS;                 // one text word per thread
-static const int SC_TILE_POS = SC_TILE_WORDS * 32;           // 8192 window starts per tile
+static const int SC_WPT = 2;                                 // text words per thread and tile
+static const int SC_TILE_WORDS = SC_THREADS * SC_WPT;
+static const int SC_TILE_POS = SC_TILE_WORDS * 32;           // 16384 window starts per tile
 static const int SC_HALO = 2;                                // words of halo in front and behind
-static const int SC_SMEM_WORDS = SC_TILE_WORDS + 2 * SC_HALO; // 260 words = 2080 bytes (multiple of 16)
-static const int SC_BATCH = 8;                               // positions probed per batch
+static const int SC_SMEM_WORDS = SC_TILE_WORDS + 2 * SC_HALO; // 516 words = 4128 bytes (multiple of 16)
 
 struct TableDev
 {
@@ -53,6 +53,7 @@ struct ScanParams
         const uint64_t * rec;         // nrec+1 global record starts
         uint32_t nrec;
         uint32_t fileid;
+        uint32_t pass_bits, pass_id;  // this launch handles the windows whose first bases spell pass_id (2^pass_bits launches)
         int mode;                     // 0 = report all hits, 1 = fold into the unique state, 2 = gapped seed candidates
         RawHit * hits;
         unsigned long long hit_cap;
@@ -272,20 +273,78 @@ __device__ __forceinline__ void follow_slot(ScanParams const & P, int table, uin
         }
 }
 
+// positions (as bits 62-2j of a word, j = base index) whose base equals `code`; with `half` only the
+// high bit of the base is compared
+__device__ __forceinline__ uint64_t base_eq_mask(uint64_t w, uint32_t code, bool half)
+{
+        uint64_t const y = w ^ (0x5555555555555555ULL * code);
+        uint64_t const z = half ? (y >> 1) : (y | (y >> 1));
+        return ~z & 0x5555555555555555ULL;
+}
+
+// The scan is run as 2^pass_bits launches.  Launch `pass_id` handles the text positions whose window
+// starts with the pass's base prefix, i.e. whose three table keys (they all start with fragment 0)
+// carry pass_id in their top pass_bits bits -- so one launch only ever touches 1/2^pass_bits of every
+// presence table, a slice that stays resident in L2 (measured on B200: random 32-byte sector reads run
+// at ~290 G/s out of L2 against ~40 G/s out of HBM, tools/gather_bench.cu).
+//
+// Per tile of 16384 positions (TMA-staged, double buffered): (1) every thread derives, with a few
+// 64-bit mask operations, which of the 64 positions of its two text words belong to the pass;
+// (2) the selected positions are compacted into a shared-memory queue; (3) the queue is probed with
+// all lanes busy: 3 independent 4-byte sector reads per position; (4) probes that found a set slot bit
+// are compacted into a second queue and followed up (rank, entry chain, seed test, verification)
+// in batches.
+static const int SC_Q2_CAP = 2048;
+static const int SC_Q2_DRAIN = 512;
+
+struct ScanSmem
+{
+        uint64_t tile[2][SC_SMEM_WORDS];          // 2 x 4128 bytes, 16-byte aligned for the bulk copies
+        unsigned long long q2[SC_Q2_CAP];
+        uint64_t bar[2];
+        uint16_t q1[SC_TILE_POS];
+        uint32_t q1n, q2n;
+};
+
+__device__ __forceinline__ void drain_candidates(ScanParams const & P, unsigned long long * q2, uint32_t n2, unsigned long long * lstats)
+{
+        for ( uint32_t i = threadIdx.x; i < n2; i += SC_THREADS )
+        {
+                unsigned long long const it = q2[i];
+                int const table = (int)(it & 3);
+                uint64_t const lx = it >> 2;
+                uint64_t const win = text_word(P.text, lx, P.seedl);
+                uint32_t const F = P.F;
+                uint64_t const fm = (1ULL << (2*F)) - 1;
+                uint64_t const m0 = (win >> (6*F)) & fm;
+                uint64_t const mo = (win >> (2*F*(2 - table))) & fm;
+                uint32_t const h = slot_of((m0 << (2*F)) | mo, P.keybits, P.tab[table].hb);
+                follow_slot(P, table, h, lx, lstats);
+        }
+}
+
 __global__ void __launch_bounds__(SC_THREADS) k_text_scan(ScanParams P)
 {
-        __shared__ __align__(128) uint64_t tile[2][SC_SMEM_WORDS];
-        __shared__ __align__(8) uint64_t bar[2];
+        extern __shared__ __align__(128) unsigned char sc_smem[];
+        ScanSmem & S = *reinterpret_cast<ScanSmem *>(sc_smem);
+        uint64_t (& tile)[2][SC_SMEM_WORDS] = S.tile;
+        uint64_t (& bar)[2] = S.bar;
+        uint16_t (& q1)[SC_TILE_POS] = S.q1;
+        unsigned long long (& q2)[SC_Q2_CAP] = S.q2;
+        uint32_t & q1n = S.q1n;
+        uint32_t & q2n = S.q2n;
 
         uint64_t const first_tile = P.x_begin / SC_TILE_POS;
         uint64_t const end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
         unsigned long long lstats[3] = {0, 0, 0};
+        int const lane = threadIdx.x & 31;
 
         if ( threadIdx.x == 0 )
         {
                 mbar_init(&bar[0], 1);
                 mbar_init(&bar[1], 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                q1n = 0; q2n = 0;
         }
         __syncthreads();
 
@@ -301,6 +360,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_text_scan(ScanParams P)
         uint32_t const fsh = 64 - 2 * P.seedl;          // window is kept left aligned in 64 bits
         uint64_t const fm = (1ULL << (2*F)) - 1;
         bool const nlA = P.tab[0].nlists != 0, nlB = P.tab[1].nlists != 0, nlC = P.tab[2].nlists != 0;
+        uint32_t const pbits = P.pass_bits, pid = P.pass_id;
+        uint32_t const nb = (pbits + 1) >> 1;           // bases that decide the pass
 
         for ( uint32_t it = 0; tile_id < end_tile; tile_id += gridDim.x, ++it )
         {
@@ -312,70 +373,109 @@ __global__ void __launch_bounds__(SC_THREADS) k_text_scan(ScanParams P)
                         bulk_load(&tile[buf ^ 1][0], P.text + (int64_t)next_tile * SC_TILE_WORDS - SC_HALO, SC_SMEM_WORDS * 8, &bar[buf ^ 1]);
                 }
                 mbar_wait(&bar[buf], (it >> 1) & 1);
+                const uint64_t * tw = &tile[buf][SC_HALO];
+                uint64_t const tile_x0 = tile_id * SC_TILE_POS;
 
-                uint64_t const w0 = tile[buf][SC_HALO + threadIdx.x];
-                uint64_t const w1 = tile[buf][SC_HALO + threadIdx.x + 1];
-                uint64_t const lx0 = tile_id * SC_TILE_POS + (uint64_t)threadIdx.x * 32;
-
-                if ( lx0 < P.x_end && lx0 + 32 > P.x_begin )
+                // (1)+(2) select the pass's positions and queue them
+                #pragma unroll
+                for ( int k = 0; k < SC_WPT; ++k )
                 {
-                        #pragma unroll 1
-                        for ( uint32_t jb = 0; jb < 32; jb += SC_BATCH )
+                        uint32_t const wi = threadIdx.x + k * SC_THREADS;
+                        uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
+                        uint64_t sel = 0x5555555555555555ULL;
+                        for ( uint32_t t = 0; t < nb; ++t )
                         {
-                                // fast path: 3 independent 4-byte probes per position, SC_BATCH positions in flight
-                                uint32_t mA = 0, mB = 0, mC = 0;
-                                #pragma unroll
-                                for ( uint32_t u = 0; u < SC_BATCH; ++u )
-                                {
-                                        uint32_t const j = jb + u;
-                                        // seedl bases starting at position j of this word, right aligned
-                                        uint64_t const win = (j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0) >> fsh;
-                                        uint64_t const m0 = (win >> (6*F)) & fm, m1 = (win >> (4*F)) & fm, m2 = (win >> (2*F)) & fm, m3 = win & fm;
-                                        if ( nlA )
-                                        {
-                                                uint32_t const h = slot_of((m0 << (2*F)) | m1, kb, P.tab[0].hb);
-                                                uint32_t const sc = h / SECTOR_SLOTS, r = h - sc * SECTOR_SLOTS;
-                                                mA |= ((ld_probe(P.tab[0].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (r >> 5)) >> (r & 31)) & 1) << u;
-                                        }
-                                        if ( nlB )
-                                        {
-                                                uint32_t const h = slot_of((m0 << (2*F)) | m2, kb, P.tab[1].hb);
-                                                uint32_t const sc = h / SECTOR_SLOTS, r = h - sc * SECTOR_SLOTS;
-                                                mB |= ((ld_probe(P.tab[1].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (r >> 5)) >> (r & 31)) & 1) << u;
-                                        }
-                                        if ( nlC )
-                                        {
-                                                uint32_t const h = slot_of((m0 << (2*F)) | m3, kb, P.tab[2].hb);
-                                                uint32_t const sc = h / SECTOR_SLOTS, r = h - sc * SECTOR_SLOTS;
-                                                mC |= ((ld_probe(P.tab[2].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (r >> 5)) >> (r & 31)) & 1) << u;
-                                        }
-                                }
-                                // slow path (a few % of positions): second level for every set slot bit
-                                if ( mA | mB | mC )
-                                {
-                                        #pragma unroll 1
-                                        for ( int table = 0; table < 3; ++table )
-                                        {
-                                                uint32_t m = table == 0 ? mA : (table == 1 ? mB : mC);
-                                                while ( m )
-                                                {
-                                                        uint32_t const u = __ffs(m) - 1;
-                                                        m &= m - 1;
-                                                        uint32_t const j = jb + u;
-                                                        uint64_t const lx = lx0 + j;
-                                                        if ( lx < P.x_begin || lx >= P.x_end )
-                                                                continue;
-                                                        uint64_t const win = (j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0) >> fsh;
-                                                        uint64_t const m0 = (win >> (6*F)) & fm;
-                                                        uint64_t const mo = (win >> (2*F*(2 - table))) & fm;
-                                                        uint32_t const h = slot_of((m0 << (2*F)) | mo, kb, P.tab[table].hb);
-                                                        follow_slot(P, table, h, lx, lstats);
-                                                }
-                                        }
-                                }
+                                bool const half = (2*(t+1) > pbits);
+                                uint32_t const code = half ? ((pid & 1) << 1) : ((pid >> (pbits - 2*(t+1))) & 3);
+                                uint64_t const e0 = base_eq_mask(w0, code, half), e1 = base_eq_mask(w1, code, half);
+                                sel &= t ? ((e0 << (2*t)) | (e1 >> (64 - 2*t))) : e0;
+                        }
+                        // clip to [x_begin, x_end)
+                        uint64_t const lx0 = tile_x0 + (uint64_t)wi * 32;
+                        if ( lx0 + 32 <= P.x_begin || lx0 >= P.x_end ) sel = 0;
+                        else
+                        {
+                                if ( lx0 < P.x_begin ) sel &= (~0ULL) >> (2 * (P.x_begin - lx0));
+                                if ( lx0 + 32 > P.x_end ) sel &= (~0ULL) << (2 * (lx0 + 32 - P.x_end));
+                        }
+                        uint32_t const c = (uint32_t)__popcll(sel);
+                        uint32_t const incl = warp_incl_scan(c, lane);
+                        uint32_t base = 0;
+                        if ( lane == 31 && incl ) base = atomicAdd(&q1n, incl);
+                        base = __shfl_sync(0xffffffffu, base, 31);
+                        uint32_t o = base + incl - c;
+                        while ( sel )
+                        {
+                                uint32_t const b = 63 - __clzll(sel);
+                                sel ^= 1ULL << b;
+                                q1[o++] = (uint16_t)(wi * 32 + ((62 - b) >> 1));
                         }
                 }
-                __syncthreads();   // everyone is done with tile[buf] before it is refilled
+                __syncthreads();
+                uint32_t const n1 = q1n;
+
+                // (3) probe the queue, (4) queue the candidates
+                for ( uint32_t i0 = 0; i0 < n1; i0 += SC_THREADS )
+                {
+                        uint32_t const i = i0 + threadIdx.x;
+                        uint32_t cand = 0;
+                        uint64_t lx = 0;
+                        if ( i < n1 )
+                        {
+                                uint32_t const lp = q1[i];
+                                uint32_t const wi = lp >> 5, j = lp & 31;
+                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
+                                uint64_t const win = (j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0) >> fsh;
+                                uint64_t const m0 = (win >> (6*F)) & fm, m1 = (win >> (4*F)) & fm, m2 = (win >> (2*F)) & fm, m3 = win & fm;
+                                lx = tile_x0 + lp;
+                                uint32_t vA = 0, vB = 0, vC = 0, rA = 0, rB = 0, rC = 0;
+                                if ( nlA )
+                                {
+                                        uint32_t const h = slot_of((m0 << (2*F)) | m1, kb, P.tab[0].hb);
+                                        uint32_t const sc = h / SECTOR_SLOTS; rA = h - sc * SECTOR_SLOTS;
+                                        vA = ld_probe(P.tab[0].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rA >> 5));
+                                }
+                                if ( nlB )
+                                {
+                                        uint32_t const h = slot_of((m0 << (2*F)) | m2, kb, P.tab[1].hb);
+                                        uint32_t const sc = h / SECTOR_SLOTS; rB = h - sc * SECTOR_SLOTS;
+                                        vB = ld_probe(P.tab[1].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rB >> 5));
+                                }
+                                if ( nlC )
+                                {
+                                        uint32_t const h = slot_of((m0 << (2*F)) | m3, kb, P.tab[2].hb);
+                                        uint32_t const sc = h / SECTOR_SLOTS; rC = h - sc * SECTOR_SLOTS;
+                                        vC = ld_probe(P.tab[2].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rC >> 5));
+                                }
+                                cand = ((vA >> (rA & 31)) & 1) | (((vB >> (rB & 31)) & 1) << 1) | (((vC >> (rC & 31)) & 1) << 2);
+                        }
+                        uint32_t const c = __popc(cand);
+                        uint32_t const incl = warp_incl_scan(c, lane);
+                        uint32_t base = 0;
+                        if ( lane == 31 && incl ) base = atomicAdd(&q2n, incl);
+                        base = __shfl_sync(0xffffffffu, base, 31);
+                        uint32_t o = base + incl - c;
+                        #pragma unroll
+                        for ( int table = 0; table < 3; ++table )
+                                if ( (cand >> table) & 1 )
+                                        q2[o++] = ((unsigned long long)lx << 2) | (unsigned long long)table;
+                        __syncthreads();
+                        uint32_t const n2 = q2n;
+                        if ( n2 >= SC_Q2_DRAIN )
+                        {
+                                drain_candidates(P, q2, n2, lstats);
+                                __syncthreads();
+                                if ( threadIdx.x == 0 ) q2n = 0;
+                                __syncthreads();
+                        }
+                }
+                __syncthreads();   // everyone is done with tile[buf] and q1 before they are refilled
+                if ( threadIdx.x == 0 ) q1n = 0;
+                __syncthreads();
+        }
+        {
+                uint32_t const n2 = q2n;
+                if ( n2 ) drain_candidates(P, q2, n2, lstats);
         }
 
         // statistics: one atomic per warp and counter
