@@ -332,7 +332,7 @@ def main():
     alg_bytes = 0.375 * n_text_local + 192.0 * last_stats["n_windows"] + 64.0 * last_stats["n_candidates"] + 16.0 * last_stats["n_hits"]
     design_bytes = 0.375 * n_text_local + 32.0 * last_stats["n_probes"] + 64.0 * last_stats["n_candidates"] + 16.0 * last_stats["n_hits"]
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_text_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_bucket_probe (+k_part): text scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                 "traffic": None, "alg_bytes_per_launch": alg_bytes, "scan_ms": scan_ms,
                 "design_bytes_per_launch": design_bytes, "design_frac": design_bytes / (scan_ms * 1e-3) / 1e9 / peak,

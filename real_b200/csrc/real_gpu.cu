@@ -62,6 +62,7 @@ struct real_gpu
         uint32_t F, keybits;
 
         // results
+        DevBuf rec_win, rec_pos, part_meta;
         DevBuf ll, hits_raw, hits_seg, hits_out, counters, counts, starts, cursor, scantmp, info, scores;
         uint64_t hit_cap;
         real_gpu_hit * host_hits;
@@ -69,9 +70,10 @@ struct real_gpu
 
         real_gpu_stats stats;
         int pass_bits_override;        // REAL_GPU_PASS_BITS (tuning), -1 = automatic
-        uint64_t l2_slice_bytes;       // table bytes one scan launch may touch (REAL_GPU_L2_SLICE_MB)
+        uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
+        uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
 
-        real_gpu() : pass_bits_override(-1), l2_slice_bytes(32ull << 20), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -378,31 +380,68 @@ uint64_t run_scan(real_gpu * h, int mode)
         RG_CUDA(cudaEventRecord(h->ev[5], h->st));
         if ( ntiles )
         {
-                // passes: cut the tables into key-prefix slices that stay resident in L2
+                // buckets: cut the tables into key-prefix slices that stay resident in L2 while a bucket is probed
                 uint64_t table_bytes = 0;
-                uint32_t maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
+                uint32_t const maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
                 for ( int t = 0; t < 3; ++t )
                         if ( P.tab[t].nlists )
-                                table_bytes += h->tab[t].bitmap.bytes;
-                uint32_t pass_bits = 0;
+                                table_bytes += h->tab[t].bitmap.bytes + h->tab[t].nentries * sizeof(Entry);
+                uint32_t bbits = 0;
                 if ( h->pass_bits_override >= 0 )
-                        pass_bits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
+                        bbits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
                 else
-                        while ( pass_bits < maxbits && (table_bytes >> pass_bits) > h->l2_slice_bytes ) ++pass_bits;
-                size_t const smem = sizeof(ScanSmem);
-                RG_CUDA(cudaFuncSetAttribute(k_text_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int occ = 0;
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_text_scan, SC_THREADS, smem));
-                if ( occ < 1 ) occ = 1;
-                unsigned const grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * occ);
-                P.pass_bits = pass_bits;
-                for ( uint32_t pass = 0; pass < (1u << pass_bits); ++pass )
+                        while ( bbits < maxbits && (table_bytes >> bbits) > h->l2_slice_bytes ) ++bbits;
+                P.bucket_bits = bbits;
+                if ( const char * e = getenv("REAL_GPU_DEBUG") ) P.debug_flags = (uint32_t)atoi(e);
+
+                uint64_t const chunk_max = h->chunk_positions;
+                uint64_t const x_begin = P.x_begin, x_end = P.x_end;
+                uint64_t const chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
+                dev_reserve(h, h->rec_win, chunk_cap * 8 + 64);
+                dev_reserve(h, h->rec_pos, chunk_cap * 4 + 64);
+                dev_reserve(h, h->part_meta, (1100 + 256 * SC_CURSOR_STRIDE) * 4);
+                uint32_t * meta = ptr<uint32_t>(h->part_meta);
+                P.rec_win = ptr<uint64_t>(h->rec_win);
+                P.rec_pos = ptr<uint32_t>(h->rec_pos);
+                P.bucket_count = meta;
+                P.bucket_start = meta + 256;
+                P.unit_start = meta + 256 + 260;
+                P.unit_counter = meta + 256 + 520;
+                P.bucket_cursor = meta + 1088;
+
+                size_t const psmem = sizeof(PartSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem);
+                RG_CUDA(cudaFuncSetAttribute(k_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                RG_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+                RG_CUDA(cudaFuncSetAttribute(k_bucket_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+                int occ_p = 0, occ_b = 0, occ_s = 0;
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part<false>, SC_THREADS, psmem));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_part_scatter, SC_THREADS, ssmem));
+                if ( occ_s < 1 ) occ_s = 1;
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bucket_probe, SC_THREADS, bsmem));
+                if ( occ_p < 1 ) occ_p = 1;
+                if ( occ_b < 1 ) occ_b = 1;
+
+                for ( uint64_t cb = x_begin; cb < x_end; cb += chunk_cap )
                 {
-                        P.pass_id = pass;
-                        k_text_scan<<<grid, SC_THREADS, smem, h->st>>>(P);
-                        RG_KERNEL_CHECK(); launch_count(h);
-                        h->stats.scan_launches += 1;
+                        P.x_begin = cb;
+                        P.x_end = std::min<uint64_t>(x_end, cb + chunk_cap);
+                        uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
+                        unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * occ_p);
+                        RG_CUDA(cudaMemsetAsync(meta, 0, 256 * 4, h->st));
+                        k_part<false><<<pgrid, SC_THREADS, psmem, h->st>>>(P);
+                        RG_KERNEL_CHECK();
+                        k_part_offsets<<<1, SC_MAX_BUCKETS, 0, h->st>>>(P);
+                        RG_KERNEL_CHECK();
+                        uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
+                        unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
+                        k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
+                        RG_KERNEL_CHECK();
+                        k_bucket_probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
+                        RG_KERNEL_CHECK();
+                        launch_count(h, 4);
+                        h->stats.scan_launches += 4;
                 }
+                P.x_begin = x_begin; P.x_end = x_end;
         }
         RG_CUDA(cudaEventRecord(h->ev[6], h->st));
         unsigned long long c[4] = {0, 0, 0, 0};
@@ -465,6 +504,7 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 h->sm_count = prop.multiProcessorCount;
                 if ( const char * e = getenv("REAL_GPU_PASS_BITS") ) h->pass_bits_override = atoi(e);
                 if ( const char * e = getenv("REAL_GPU_L2_SLICE_MB") ) h->l2_slice_bytes = (uint64_t)atoi(e) << 20;
+                if ( const char * e = getenv("REAL_GPU_CHUNK_MPOS") ) h->chunk_positions = std::max<uint64_t>(SC_TILE_POS, ((uint64_t)atoi(e) << 20) / SC_TILE_POS * SC_TILE_POS);
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
                 for ( int i = 0; i < 8; ++i ) RG_CUDA(cudaEventCreate(&h->ev[i]));
                 if ( params->ll_table )
@@ -491,7 +531,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
         if ( h->host_hits ) cudaFreeHost(h->host_hits);

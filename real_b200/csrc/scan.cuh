@@ -1,4 +1,4 @@
-// K3: the text scan -- probe + verify + report, the dominant kernel of the path.
+// K3: the text scan -- partition + probe + verify + report, the dominant kernels of the path.
 //
 // Replaces, for every seed window of the text and every read at once, the reference's per-read
 // ::match (match.hpp:335-416): directory lookup + equal_range on the signature, seed error count
@@ -6,14 +6,23 @@
 // (:391-398, RangeVector.hpp:59-66, AutoTextArray.hpp:167-172), rest-of-read Hamming distance
 // (RestMatch.hpp:39-81) and the updater call (:410).
 //
-// Shape: persistent CTAs walk tiles of 8192 text positions.  A tile of 2-bit text (+2 words of halo
-// on either side) is staged in shared memory by one bulk asynchronous copy (cp.async.bulk, TMA unit)
-// into a double buffer guarded by mbarriers while the previous tile is being probed.  Each thread
-// owns one text word = 32 consecutive window starts, slides the 4-fragment window through registers
-// with funnel shifts, and for every position issues one 4-byte load into each presence table
-// (3 independent random sector reads per position, issued in batches of 8 positions for
-// memory-level parallelism).  Only positions whose slot bit is set (a few %) take the second level:
-// sector rank -> entry -> seed test -> canonical-list rule -> verification against the packed read.
+// Measured on B200 (tools/gather_bench.cu): random 32-byte sector reads run at ~40 G/s out of HBM
+// (every one drags a 128-byte line: ~5 TB/s of DRAM traffic for 1.3 TB/s of useful sectors) but at
+// ~290 G/s out of L2.  Three random table probes per text position straight into multi-GB tables
+// therefore top out near 13 G positions/s.  So the scan first PARTITIONS the window starts of a text
+// chunk by the first bases of their window -- all three table keys of a position begin with
+// fragment 0, so that prefix is the top bits of every key -- and then probes bucket after bucket:
+// while a bucket is being probed only 1/2^bucket_bits of each table is touched, a slice that stays
+// in L2.
+//
+//   k_part_hist     TMA-staged text tiles -> bucket histogram
+//   k_part_offsets  bucket starts + work-unit directory (one small block)
+//   k_part_scatter  TMA-staged text tiles -> (window word, position) records grouped by bucket
+//   k_bucket_probe  persistent CTAs pull 1024-record units in bucket order; every thread issues its
+//                   12 independent 4-byte probes; set slot bits are compacted into a shared-memory
+//                   queue (stage A: rank -> entry chain -> seed test -> canonical-list rule), the
+//                   survivors into a second queue (stage B: record / wildcard predicates, whole-read
+//                   XOR+popcount distance, report), so that each stage runs with full warps.
 #pragma once
 
 #include "common.cuh"
@@ -28,6 +37,14 @@ static const int SC_TILE_WORDS = SC_THREADS * SC_WPT;
 static const int SC_TILE_POS = SC_TILE_WORDS * 32;           // 16384 window starts per tile
 static const int SC_HALO = 2;                                // words of halo in front and behind
 static const int SC_SMEM_WORDS = SC_TILE_WORDS + 2 * SC_HALO; // 516 words = 4128 bytes (multiple of 16)
+static const int SC_MAX_BUCKETS = 256;
+static const int SC_CURSOR_STRIDE = 32;                      // u32 per bucket cursor: one 128-byte line each, so the global atomics spread over the L2 slices
+static const int SC_UNIT = 512;                              // records per work unit of the probe kernel
+static const int SC_RPT = SC_UNIT / SC_THREADS;              // records per thread and unit
+static const int SC_QA_DRAIN = 512;                          // stage A queue (set slot bits): drained at this fill
+static const int SC_QA_CAP = SC_QA_DRAIN + 3 * SC_UNIT;      //   one more unit always fits
+static const int SC_QB_CAP = 512;                            // stage B queue (seed test passed)
+static const int SC_QB_DRAIN = 256;
 
 struct TableDev
 {
@@ -53,7 +70,16 @@ struct ScanParams
         const uint64_t * rec;         // nrec+1 global record starts
         uint32_t nrec;
         uint32_t fileid;
-        uint32_t pass_bits, pass_id;  // this launch handles the windows whose first bases spell pass_id (2^pass_bits launches)
+        // partition of the chunk [x_begin, x_end): x0 = first position of the chunk
+        uint32_t bucket_bits;
+        uint32_t debug_flags;         // development only (REAL_GPU_DEBUG): 1 = count set slot bits but do not follow them
+        uint64_t * rec_win;           // window word of every record, grouped by bucket
+        uint32_t * rec_pos;           // position of every record relative to x_begin
+        uint32_t * bucket_count;      // [SC_MAX_BUCKETS]
+        uint32_t * bucket_start;      // [SC_MAX_BUCKETS+1] record index
+        uint32_t * unit_start;        // [SC_MAX_BUCKETS+1] work unit index
+        uint32_t * bucket_cursor;     // [SC_MAX_BUCKETS]
+        uint32_t * unit_counter;      // work distribution of k_bucket_probe
         int mode;                     // 0 = report all hits, 1 = fold into the unique state, 2 = gapped seed candidates
         RawHit * hits;
         unsigned long long hit_cap;
@@ -62,10 +88,27 @@ struct ScanParams
         unsigned long long * stats;   // [0] candidates  [1] seed-pass  [2] hits
 };
 
-__device__ __forceinline__ uint32_t ld_probe(const uint32_t * p)
+// Loads from the hot table slices (presence bits, entries).  Measured on B200
+// (tools/l2_resident_bench.cu): loads issued as ld.global.nc.L1::no_allocate are kept in L2 with low
+// priority -- a randomly probed 32 MB table already drops from ~278 to ~180 G probes/s, 64 MB to
+// ~105 -- while plain loads or loads carrying an evict_last policy hold ~275 G/s up to 64 MB, also with
+// a stream of touch-once data flowing through L2 at the same time.
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+        return pol;
+}
+__device__ __forceinline__ uint32_t ld_hot_u32(const uint32_t * p, uint64_t pol)
 {
         uint32_t v;
-        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+        return v;
+}
+__device__ __forceinline__ uint4 ld_hot_v4(const void * p, uint64_t pol)
+{
+        uint4 v;
+        asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
         return v;
 }
 
@@ -172,35 +215,351 @@ __device__ __forceinline__ bool wildcard_free(const uint64_t * __restrict__ nmas
         return true;
 }
 
-// one signature-equal entry at seed window lp (local): seed test, canonical-list rule, verification
-__device__ __forceinline__ void examine_candidate(ScanParams const & P, int table, Entry const & en, uint64_t lx, unsigned long long * lstats)
+
+// ---- partition ---------------------------------------------------------------------------------
+
+struct PartSmem
 {
-        uint32_t const t = en.val & 3;
-        uint32_t const id = en.val >> 2;
-        if ( lx < (uint64_t)t * P.F ) return;
-        uint64_t const lp = lx - (uint64_t)t * P.F;                      // seed window start (local)
-        if ( lp < P.win_begin || lp >= P.win_end ) return;
-        lstats[0] += 1;
+        uint64_t tile[2][SC_SMEM_WORDS];
+        uint64_t bar[2];
+        uint32_t cnt[SC_MAX_BUCKETS];                      // histogram variant: whole-grid-stride counts
+        uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];    // scatter variant: per-warp counts, then output offsets
+        uint16_t rank[SC_TILE_POS];                        // scatter variant: rank of a position inside its (warp, bucket) group
+};
 
-        // seed errors: the whole seed of the read strand against the text window (match.hpp:386-388)
-        uint64_t const win = text_word(P.text, lp, P.seedl);
-        uint64_t x = en.seed ^ win;
-        x = ((x >> 1) | x) & 0x5555555555555555ULL;
-        uint32_t const seedk = (uint32_t)__popcll(x);
-        if ( seedk > P.seedkmax ) return;
-        // canonical list: the pair made of the two lowest exact fragments reports the match, so a
-        // position reached through several lists is reported once (replaces unifyMatches' dedup)
-        uint64_t const fm = (1ULL << (2*P.F)) - 1;
-        int first = -1, second = -1;
-        #pragma unroll
-        for ( int f = 0; f < 4; ++f )
+// valid positions of the word that starts at local position lx0, as a 32-bit mask (bit j = base j)
+__device__ __forceinline__ uint32_t clip_mask(uint64_t lx0, uint64_t x_begin, uint64_t x_end)
+{
+        if ( lx0 + 32 <= x_begin || lx0 >= x_end ) return 0;
+        uint32_t m = 0xFFFFFFFFu;
+        if ( lx0 < x_begin ) m &= 0xFFFFFFFFu << (uint32_t)(x_begin - lx0);
+        if ( lx0 + 32 > x_end ) m &= 0xFFFFFFFFu >> (uint32_t)(lx0 + 32 - x_end);
+        return m;
+}
+
+// SCATTER = false: bucket histogram of the chunk (shared-memory reductions, no ranks needed).
+// SCATTER = true : the records.  Ranks come from a warp-level multisplit (__match_any_sync on the bucket
+// id, one text position per lane and step) -- shared-memory atomics that return a value serialise far
+// too much for this (measured: 10 ms per 250 M positions, all stalls on the shared-memory pipe).
+template<bool SCATTER>
+__global__ void __launch_bounds__(SC_THREADS) k_part(ScanParams P)
+{
+        extern __shared__ __align__(128) unsigned char sc_smem[];
+        PartSmem & S = *reinterpret_cast<PartSmem *>(sc_smem);
+
+        uint64_t const first_tile = P.x_begin / SC_TILE_POS;
+        uint64_t const end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
+        uint32_t const bbits = P.bucket_bits;
+        uint32_t const bsh = 64 - (bbits ? bbits : 1);
+        uint32_t const bmask = bbits ? 0xFFFFFFFFu : 0u;
+        uint32_t const fsh = 64 - 2 * P.seedl;
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        uint32_t const lt = (1u << lane) - 1;
+
+        if ( threadIdx.x == 0 )
         {
-                bool const exact = ((x >> (2*P.F*(3-f))) & fm) == 0;
-                if ( exact ) { if ( first < 0 ) first = f; else if ( second < 0 ) second = f; }
+                mbar_init(&S.bar[0], 1);
+                mbar_init(&S.bar[1], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        if ( first != (int)t || second != pair_second(table, (int)t) ) return;
-        lstats[1] += 1;
+        S.cnt[threadIdx.x] = 0;
+        #pragma unroll
+        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
 
+        uint64_t tile_id = first_tile + blockIdx.x;
+        if ( threadIdx.x == 0 && tile_id < end_tile )
+        {
+                mbar_expect_tx(&S.bar[0], SC_SMEM_WORDS * 8);
+                bulk_load(&S.tile[0][0], P.text + (int64_t)tile_id * SC_TILE_WORDS - SC_HALO, SC_SMEM_WORDS * 8, &S.bar[0]);
+        }
+
+        for ( uint32_t it = 0; tile_id < end_tile; tile_id += gridDim.x, ++it )
+        {
+                uint32_t const buf = it & 1;
+                uint64_t const next_tile = tile_id + gridDim.x;
+                if ( threadIdx.x == 0 && next_tile < end_tile )
+                {
+                        mbar_expect_tx(&S.bar[buf ^ 1], SC_SMEM_WORDS * 8);
+                        bulk_load(&S.tile[buf ^ 1][0], P.text + (int64_t)next_tile * SC_TILE_WORDS - SC_HALO, SC_SMEM_WORDS * 8, &S.bar[buf ^ 1]);
+                }
+                mbar_wait(&S.bar[buf], (it >> 1) & 1);
+                const uint64_t * tw = &S.tile[buf][SC_HALO];
+                uint64_t const tile_x0 = tile_id * SC_TILE_POS;
+
+                if ( ! SCATTER )
+                {
+                        #pragma unroll
+                        for ( int k = 0; k < SC_WPT; ++k )
+                        {
+                                uint32_t const wi = threadIdx.x + k * SC_THREADS;
+                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
+                                uint32_t m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
+                                while ( m )
+                                {
+                                        uint32_t const j = __ffs(m) - 1;
+                                        m &= m - 1;
+                                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                        atomicAdd(&S.cnt[(uint32_t)(v >> bsh) & bmask], 1u);
+                                }
+                        }
+                }
+                else
+                {
+                        // (1) rank of every position inside its (warp, bucket) group
+                        #pragma unroll
+                        for ( int k = 0; k < SC_WPT; ++k )
+                        {
+                                uint32_t const wi = threadIdx.x + k * SC_THREADS;
+                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
+                                uint32_t const m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
+                                #pragma unroll 4
+                                for ( uint32_t j = 0; j < 32; ++j )
+                                {
+                                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                        bool const ok = (m >> j) & 1;
+                                        uint32_t const b = (uint32_t)(v >> bsh) & bmask;
+                                        uint32_t const peers = __match_any_sync(0xffffffffu, ok ? b : 0x100u);
+                                        uint32_t const below = __popc(peers & lt);
+                                        uint32_t pre = 0;
+                                        if ( ok ) pre = S.wcnt[wid][b];
+                                        __syncwarp();
+                                        if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers);
+                                        __syncwarp();
+                                        S.rank[wi * 32 + j] = (uint16_t)(pre + below);
+                                }
+                        }
+                        __syncthreads();
+                        // (2) bucket b (thread b): reserve the tile's run in the bucket, turn the per-warp counts into offsets
+                        {
+                                uint32_t tot = 0;
+                                #pragma unroll
+                                for ( int w = 0; w < SC_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                                uint32_t run = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
+                                #pragma unroll
+                                for ( int w = 0; w < SC_THREADS / 32; ++w )
+                                {
+                                        uint32_t const c = S.wcnt[w][threadIdx.x];
+                                        S.wcnt[w][threadIdx.x] = run;
+                                        run += c;
+                                }
+                        }
+                        __syncthreads();
+                        // (3) write the records
+                        #pragma unroll
+                        for ( int k = 0; k < SC_WPT; ++k )
+                        {
+                                uint32_t const wi = threadIdx.x + k * SC_THREADS;
+                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
+                                uint64_t const lx0 = tile_x0 + (uint64_t)wi * 32;
+                                uint32_t const m = clip_mask(lx0, P.x_begin, P.x_end);
+                                #pragma unroll 4
+                                for ( uint32_t j = 0; j < 32; ++j )
+                                {
+                                        if ( (m >> j) & 1 )
+                                        {
+                                                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                                uint32_t const b = (uint32_t)(v >> bsh) & bmask;
+                                                uint32_t const o = S.wcnt[wid][b] + S.rank[wi * 32 + j];
+                                                P.rec_win[o] = v >> fsh;
+                                                P.rec_pos[o] = (uint32_t)(lx0 + j - P.x_begin);
+                                        }
+                                }
+                        }
+                        __syncthreads();
+                        #pragma unroll
+                        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+                }
+                __syncthreads();   // tile[buf], rank and the counters are free again
+        }
+        if ( ! SCATTER )
+        {
+                uint32_t const c = S.cnt[threadIdx.x];
+                if ( c ) atomicAdd(P.bucket_count + threadIdx.x, c);
+        }
+}
+
+// ---- partition, scatter pass ---------------------------------------------------------------------
+// Tiles of 8192 positions.  Records are first laid out bucket by bucket in shared memory and then copied
+// out run by run, so every global store instruction writes whole consecutive records of one bucket:
+// scattering 8-byte records straight from the threads that produce them leaves ~200 KB of half-written
+// lines open per CTA, more than L2 holds for a full grid (measured: 2 GB of DRAM reads and 5 GB of writes
+// for 3 GB of records, 10 ms per 250 M positions).
+static const int PS_TILE_WORDS = SC_THREADS;                  // one text word per thread
+static const int PS_TILE_POS = PS_TILE_WORDS * 32;            // 8192
+static const int PS_SMEM_WORDS = PS_TILE_WORDS + 2 * SC_HALO; // 260 words = 2080 bytes
+
+struct ScatterSmem
+{
+        uint64_t stage_win[PS_TILE_POS];
+        uint64_t tile[2][PS_SMEM_WORDS];
+        uint64_t bar[2];
+        uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];    // per-warp counts, then running slots
+        uint32_t loc[SC_MAX_BUCKETS + 1];                  // first staging slot of a bucket
+        uint32_t base[SC_MAX_BUCKETS];                     // first global record of the tile's run in a bucket
+        uint16_t stage_pos[PS_TILE_POS];
+        uint8_t stage_b[PS_TILE_POS];
+};
+
+__global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
+{
+        extern __shared__ __align__(128) unsigned char sc_smem[];
+        ScatterSmem & S = *reinterpret_cast<ScatterSmem *>(sc_smem);
+
+        uint64_t const first_tile = P.x_begin / PS_TILE_POS;
+        uint64_t const end_tile = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
+        uint32_t const bbits = P.bucket_bits;
+        uint32_t const bsh = 64 - (bbits ? bbits : 1);
+        uint32_t const bmask = bbits ? 0xFFFFFFFFu : 0u;
+        uint32_t const fsh = 64 - 2 * P.seedl;
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        uint32_t const lt = (1u << lane) - 1;
+
+        if ( threadIdx.x == 0 )
+        {
+                mbar_init(&S.bar[0], 1);
+                mbar_init(&S.bar[1], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        #pragma unroll
+        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+
+        uint64_t tile_id = first_tile + blockIdx.x;
+        if ( threadIdx.x == 0 && tile_id < end_tile )
+        {
+                mbar_expect_tx(&S.bar[0], PS_SMEM_WORDS * 8);
+                bulk_load(&S.tile[0][0], P.text + (int64_t)tile_id * PS_TILE_WORDS - SC_HALO, PS_SMEM_WORDS * 8, &S.bar[0]);
+        }
+
+        for ( uint32_t it = 0; tile_id < end_tile; tile_id += gridDim.x, ++it )
+        {
+                uint32_t const buf = it & 1;
+                uint64_t const next_tile = tile_id + gridDim.x;
+                if ( threadIdx.x == 0 && next_tile < end_tile )
+                {
+                        mbar_expect_tx(&S.bar[buf ^ 1], PS_SMEM_WORDS * 8);
+                        bulk_load(&S.tile[buf ^ 1][0], P.text + (int64_t)next_tile * PS_TILE_WORDS - SC_HALO, PS_SMEM_WORDS * 8, &S.bar[buf ^ 1]);
+                }
+                mbar_wait(&S.bar[buf], (it >> 1) & 1);
+                uint64_t const tile_x0 = tile_id * PS_TILE_POS;
+                uint32_t const wi = threadIdx.x;
+                uint64_t const w0 = S.tile[buf][SC_HALO + wi], w1 = S.tile[buf][SC_HALO + wi + 1];
+                uint32_t const m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
+
+                // (1) per-warp bucket counts (reductions without return value)
+                {
+                        uint32_t mm = m;
+                        while ( mm )
+                        {
+                                uint32_t const j = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                atomicAdd(&S.wcnt[wid][(uint32_t)(v >> bsh) & bmask], 1u);
+                        }
+                }
+                __syncthreads();
+                // (2) bucket b (thread b): totals -> staging layout, global run reservation, per-warp running slots
+                {
+                        uint32_t tot = 0;
+                        #pragma unroll
+                        for ( int w = 0; w < SC_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                        uint32_t blocktot;
+                        uint32_t const ex = block_excl_scan(tot, &blocktot);
+                        S.loc[threadIdx.x] = ex;
+                        if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
+                        S.base[threadIdx.x] = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
+                        uint32_t run = ex;
+                        #pragma unroll
+                        for ( int w = 0; w < SC_THREADS / 32; ++w )
+                        {
+                                uint32_t const c = S.wcnt[w][threadIdx.x];
+                                S.wcnt[w][threadIdx.x] = run;
+                                run += c;
+                        }
+                }
+                __syncthreads();
+                // (3) warp multisplit: one position per lane and step; the group leader advances the warp's slot counter
+                #pragma unroll 4
+                for ( uint32_t j = 0; j < 32; ++j )
+                {
+                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                        bool const ok = (m >> j) & 1;
+                        uint32_t const b = (uint32_t)(v >> bsh) & bmask;
+                        uint32_t const peers = __match_any_sync(0xffffffffu, ok ? b : 0x100u);
+                        uint32_t const below = __popc(peers & lt);
+                        uint32_t pre = 0;
+                        if ( ok ) pre = S.wcnt[wid][b];
+                        __syncwarp();
+                        if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers);
+                        __syncwarp();
+                        if ( ok )
+                        {
+                                uint32_t const slot = pre + below;
+                                S.stage_win[slot] = v >> fsh;
+                                S.stage_pos[slot] = (uint16_t)(wi * 32 + j);
+                                S.stage_b[slot] = (uint8_t)b;
+                        }
+                }
+                __syncthreads();
+                // (4) copy out: consecutive threads write consecutive records of a bucket run
+                {
+                        uint32_t const n = S.loc[SC_MAX_BUCKETS];
+                        uint32_t const pos0 = (uint32_t)(tile_x0 - P.x_begin);      // may wrap for the clipped first tile; offsets below are relative
+                        for ( uint32_t i = threadIdx.x; i < n; i += SC_THREADS )
+                        {
+                                uint32_t const b = S.stage_b[i];
+                                uint32_t const o = S.base[b] + (i - S.loc[b]);
+                                P.rec_win[o] = S.stage_win[i];
+                                P.rec_pos[o] = pos0 + S.stage_pos[i];
+                        }
+                }
+                __syncthreads();
+                #pragma unroll
+                for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+                __syncthreads();   // tile[buf], staging and the counters are free again
+        }
+}
+
+// one block: bucket starts, unit directory, cursors
+__global__ void __launch_bounds__(SC_MAX_BUCKETS) k_part_offsets(ScanParams P)
+{
+        __shared__ uint32_t sc[SC_MAX_BUCKETS], su[SC_MAX_BUCKETS];
+        uint32_t const c = P.bucket_count[threadIdx.x];
+        sc[threadIdx.x] = c;
+        su[threadIdx.x] = (c + SC_UNIT - 1) / SC_UNIT;
+        __syncthreads();
+        if ( threadIdx.x == 0 )
+        {
+                uint32_t a = 0, u = 0;
+                for ( int b = 0; b < SC_MAX_BUCKETS; ++b )
+                {
+                        P.bucket_start[b] = a; P.unit_start[b] = u;
+                        a += sc[b]; u += su[b];
+                }
+                P.bucket_start[SC_MAX_BUCKETS] = a; P.unit_start[SC_MAX_BUCKETS] = u;
+                *P.unit_counter = 0;
+        }
+        P.bucket_cursor[threadIdx.x * SC_CURSOR_STRIDE] = 0;
+}
+
+// ---- probe -------------------------------------------------------------------------------------
+
+struct ItemA { uint64_t win; uint32_t pos; uint32_t table; };          // a set slot bit
+struct ItemB { uint64_t lp; uint32_t id; uint32_t seedk; };           // an entry that passed the seed test
+
+struct ProbeSmem
+{
+        ItemA qa[SC_QA_CAP];
+        ItemB qb[SC_QB_CAP];
+        uint32_t ustart[SC_MAX_BUCKETS + 1];
+        uint32_t qan, qbn, unit[2];
+};
+
+// stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
+// whole-read distance, report
+__device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, unsigned long long * lstats)
+{
         uint32_t const strand = id & 1;
         uint32_t const read = id >> 1;
         uint32_t const L = __ldg(P.rlen + read);
@@ -245,12 +604,20 @@ __device__ __forceinline__ void examine_candidate(ScanParams const & P, int tabl
         }
 }
 
-// second level of a probe whose slot bit is set: rank inside the sector, then the entry chain
-__device__ __forceinline__ void follow_slot(ScanParams const & P, int table, uint32_t h, uint64_t lx, unsigned long long * lstats)
+// stage A: a set slot bit -> rank inside the sector -> entry chain; per entry the seed test
+// (match.hpp:386-388) and the canonical-list rule: of the up to six lists that reach a position,
+// only the pair made of the two LOWEST exact fragments reports it (replaces unifyMatches' dedup)
+__device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, ProbeSmem & S, unsigned long long * lstats, uint64_t pol)
 {
+        int const table = (int)it.table;
+        uint32_t const F = P.F;
+        uint64_t const fm = (1ULL << (2*F)) - 1;
+        uint64_t const m0 = (it.win >> (6*F)) & fm;
+        uint64_t const mo = (it.win >> (2*F*(2 - table))) & fm;
+        uint32_t const h = slot_of((m0 << (2*F)) | mo, P.keybits, P.tab[table].hb);
         uint32_t const sector = h / SECTOR_SLOTS, slot = h - sector * SECTOR_SLOTS;
         const uint4 * sp = reinterpret_cast<const uint4 *>(P.tab[table].bitmap + (uint64_t)sector * SECTOR_WORDS);
-        uint4 const a = __ldg(sp), b = __ldg(sp + 1);
+        uint4 const a = ld_hot_v4(sp, pol), b = ld_hot_v4(sp + 1, pol);
         uint32_t const wv[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
         uint32_t rank = wv[0];
         uint32_t const wi = slot >> 5;
@@ -260,234 +627,230 @@ __device__ __forceinline__ void follow_slot(ScanParams const & P, int table, uin
                 if ( w < wi ) rank += __popc(wv[1+w]);
                 else if ( w == wi ) rank += __popc(wv[1+w] & ((1u << (slot & 31)) - 1));
         }
+        uint64_t const lx = P.x_begin + it.pos;
         uint32_t e = rank;
         while ( e != ENTRY_NONE )
         {
-                uint4 const raw = __ldg(reinterpret_cast<const uint4 *>(P.tab[table].E + e));
-                Entry en;
-                en.seed = ((uint64_t)raw.y << 32) | raw.x;
-                en.val = raw.z;
-                en.next = raw.w;
-                examine_candidate(P, table, en, lx, lstats);
-                e = en.next;
+                uint4 const raw = ld_hot_v4(P.tab[table].E + e, pol);
+                uint64_t const eseed = ((uint64_t)raw.y << 32) | raw.x;
+                uint32_t const t = raw.z & 3, id = raw.z >> 2;
+                e = raw.w;
+                if ( lx < (uint64_t)t * F ) continue;
+                uint64_t const lp = lx - (uint64_t)t * F;                      // seed window start (local)
+                if ( lp < P.win_begin || lp >= P.win_end ) continue;
+                lstats[0] += 1;
+                uint64_t const win = t ? text_word(P.text, lp, P.seedl) : it.win;
+                uint64_t x = eseed ^ win;
+                x = ((x >> 1) | x) & 0x5555555555555555ULL;
+                uint32_t const seedk = (uint32_t)__popcll(x);
+                if ( seedk > P.seedkmax ) continue;
+                int first = -1, second = -1;
+                #pragma unroll
+                for ( int f = 0; f < 4; ++f )
+                {
+                        bool const exact = ((x >> (2*F*(3-f))) & fm) == 0;
+                        if ( exact ) { if ( first < 0 ) first = f; else if ( second < 0 ) second = f; }
+                }
+                if ( first != (int)t || second != pair_second(table, (int)t) ) continue;
+                lstats[1] += 1;
+                uint32_t const o = atomicAdd(&S.qbn, 1u);
+                if ( o < SC_QB_CAP )
+                {
+                        ItemB ib; ib.lp = lp; ib.id = id; ib.seedk = seedk;
+                        S.qb[o] = ib;
+                }
+                else
+                        verify_and_report(P, lp, id, lstats);          // queue full: handle it here
         }
 }
 
-// positions (as bits 62-2j of a word, j = base index) whose base equals `code`; with `half` only the
-// high bit of the base is compared
-__device__ __forceinline__ uint64_t base_eq_mask(uint64_t w, uint32_t code, bool half)
+__device__ __forceinline__ void drain_b(ScanParams const & P, ProbeSmem & S, unsigned long long * lstats)
 {
-        uint64_t const y = w ^ (0x5555555555555555ULL * code);
-        uint64_t const z = half ? (y >> 1) : (y | (y >> 1));
-        return ~z & 0x5555555555555555ULL;
-}
-
-// The scan is run as 2^pass_bits launches.  Launch `pass_id` handles the text positions whose window
-// starts with the pass's base prefix, i.e. whose three table keys (they all start with fragment 0)
-// carry pass_id in their top pass_bits bits -- so one launch only ever touches 1/2^pass_bits of every
-// presence table, a slice that stays resident in L2 (measured on B200: random 32-byte sector reads run
-// at ~290 G/s out of L2 against ~40 G/s out of HBM, tools/gather_bench.cu).
-//
-// Per tile of 16384 positions (TMA-staged, double buffered): (1) every thread derives, with a few
-// 64-bit mask operations, which of the 64 positions of its two text words belong to the pass;
-// (2) the selected positions are compacted into a shared-memory queue; (3) the queue is probed with
-// all lanes busy: 3 independent 4-byte sector reads per position; (4) probes that found a set slot bit
-// are compacted into a second queue and followed up (rank, entry chain, seed test, verification)
-// in batches.
-static const int SC_Q2_CAP = 2048;
-static const int SC_Q2_DRAIN = 512;
-
-struct ScanSmem
-{
-        uint64_t tile[2][SC_SMEM_WORDS];          // 2 x 4128 bytes, 16-byte aligned for the bulk copies
-        unsigned long long q2[SC_Q2_CAP];
-        uint64_t bar[2];
-        uint16_t q1[SC_TILE_POS];
-        uint32_t q1n, q2n;
-};
-
-__device__ __forceinline__ void drain_candidates(ScanParams const & P, unsigned long long * q2, uint32_t n2, unsigned long long * lstats)
-{
-        for ( uint32_t i = threadIdx.x; i < n2; i += SC_THREADS )
+        uint32_t const n = min(S.qbn, (uint32_t)SC_QB_CAP);
+        for ( uint32_t i = threadIdx.x; i < n; i += SC_THREADS )
         {
-                unsigned long long const it = q2[i];
-                int const table = (int)(it & 3);
-                uint64_t const lx = it >> 2;
-                uint64_t const win = text_word(P.text, lx, P.seedl);
-                uint32_t const F = P.F;
-                uint64_t const fm = (1ULL << (2*F)) - 1;
-                uint64_t const m0 = (win >> (6*F)) & fm;
-                uint64_t const mo = (win >> (2*F*(2 - table))) & fm;
-                uint32_t const h = slot_of((m0 << (2*F)) | mo, P.keybits, P.tab[table].hb);
-                follow_slot(P, table, h, lx, lstats);
-        }
-}
-
-__global__ void __launch_bounds__(SC_THREADS) k_text_scan(ScanParams P)
-{
-        extern __shared__ __align__(128) unsigned char sc_smem[];
-        ScanSmem & S = *reinterpret_cast<ScanSmem *>(sc_smem);
-        uint64_t (& tile)[2][SC_SMEM_WORDS] = S.tile;
-        uint64_t (& bar)[2] = S.bar;
-        uint16_t (& q1)[SC_TILE_POS] = S.q1;
-        unsigned long long (& q2)[SC_Q2_CAP] = S.q2;
-        uint32_t & q1n = S.q1n;
-        uint32_t & q2n = S.q2n;
-
-        uint64_t const first_tile = P.x_begin / SC_TILE_POS;
-        uint64_t const end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
-        unsigned long long lstats[3] = {0, 0, 0};
-        int const lane = threadIdx.x & 31;
-
-        if ( threadIdx.x == 0 )
-        {
-                mbar_init(&bar[0], 1);
-                mbar_init(&bar[1], 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                q1n = 0; q2n = 0;
+                ItemB const ib = S.qb[i];
+                verify_and_report(P, ib.lp, ib.id, lstats);
         }
         __syncthreads();
+        if ( threadIdx.x == 0 ) S.qbn = 0;
+        __syncthreads();
+}
 
-        uint64_t tile_id = first_tile + blockIdx.x;
-        if ( threadIdx.x == 0 && tile_id < end_tile )
+__device__ __forceinline__ void drain_a(ScanParams const & P, ProbeSmem & S, unsigned long long * lstats, bool flush, uint64_t pol)
+{
+        uint32_t const n = S.qan;
+        for ( uint32_t i0 = 0; i0 < n; i0 += SC_THREADS )
         {
-                mbar_expect_tx(&bar[0], SC_SMEM_WORDS * 8);
-                bulk_load(&tile[0][0], P.text + (int64_t)tile_id * SC_TILE_WORDS - SC_HALO, SC_SMEM_WORDS * 8, &bar[0]);
+                uint32_t const i = i0 + threadIdx.x;
+                if ( i < n )
+                        follow_item(P, S.qa[i], S, lstats, pol);
+                __syncthreads();
+                if ( S.qbn >= SC_QB_DRAIN )
+                        drain_b(P, S, lstats);
         }
+        __syncthreads();
+        if ( threadIdx.x == 0 ) S.qan = 0;
+        __syncthreads();
+        if ( flush && S.qbn )
+                drain_b(P, S, lstats);
+}
+
+__device__ __forceinline__ void locate_unit(ScanParams const & P, const uint32_t * ustart, uint32_t u, uint32_t & r0, uint32_t & r1)
+{
+        // bucket of the unit: last b with ustart[b] <= u
+        uint32_t lo = 0, hi = SC_MAX_BUCKETS;
+        while ( lo < hi )
+        {
+                uint32_t const mid = (lo + hi + 1) >> 1;
+                if ( ustart[mid] <= u ) lo = mid; else hi = mid - 1;
+        }
+        r0 = __ldg(P.bucket_start + lo) + (u - ustart[lo]) * SC_UNIT;
+        r1 = min(r0 + (uint32_t)SC_UNIT, __ldg(P.bucket_start + lo + 1));
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
+{
+        extern __shared__ __align__(128) unsigned char sc_smem[];
+        ProbeSmem & S = *reinterpret_cast<ProbeSmem *>(sc_smem);
+        unsigned long long lstats[3] = {0, 0, 0};
+        int const lane = threadIdx.x & 31;
+        uint64_t const pol = policy_evict_last();
+
+        for ( int i = threadIdx.x; i <= SC_MAX_BUCKETS; i += SC_THREADS )
+                S.ustart[i] = P.unit_start[i];
+        if ( threadIdx.x == 0 ) { S.qan = 0; S.qbn = 0; }
+        __syncthreads();
+        uint32_t const nunits = S.ustart[SC_MAX_BUCKETS];
 
         uint32_t const F = P.F;
         uint32_t const kb = P.keybits;
-        uint32_t const fsh = 64 - 2 * P.seedl;          // window is kept left aligned in 64 bits
         uint64_t const fm = (1ULL << (2*F)) - 1;
         bool const nlA = P.tab[0].nlists != 0, nlB = P.tab[1].nlists != 0, nlC = P.tab[2].nlists != 0;
-        uint32_t const pbits = P.pass_bits, pid = P.pass_id;
-        uint32_t const nb = (pbits + 1) >> 1;           // bases that decide the pass
 
-        for ( uint32_t it = 0; tile_id < end_tile; tile_id += gridDim.x, ++it )
+        // units are handed out in bucket order by a global counter, so all CTAs work on the same bucket (slice)
+        // at any time; unit ids are drawn two iterations ahead and the records of the next unit are requested
+        // before the current one is probed
+        if ( threadIdx.x == 0 )
         {
-                uint32_t const buf = it & 1;
-                uint64_t const next_tile = tile_id + gridDim.x;
-                if ( threadIdx.x == 0 && next_tile < end_tile )
+                S.unit[0] = atomicAdd(P.unit_counter, 1u);
+                S.unit[1] = atomicAdd(P.unit_counter, 1u);
+        }
+        __syncthreads();
+        uint32_t r0n = 0, r1n = 0;
+        uint64_t win_next[SC_RPT];
+        {
+                uint32_t const u0 = S.unit[0];
+                if ( u0 < nunits )
                 {
-                        mbar_expect_tx(&bar[buf ^ 1], SC_SMEM_WORDS * 8);
-                        bulk_load(&tile[buf ^ 1][0], P.text + (int64_t)next_tile * SC_TILE_WORDS - SC_HALO, SC_SMEM_WORDS * 8, &bar[buf ^ 1]);
-                }
-                mbar_wait(&bar[buf], (it >> 1) & 1);
-                const uint64_t * tw = &tile[buf][SC_HALO];
-                uint64_t const tile_x0 = tile_id * SC_TILE_POS;
-
-                // (1)+(2) select the pass's positions and queue them
-                #pragma unroll
-                for ( int k = 0; k < SC_WPT; ++k )
-                {
-                        uint32_t const wi = threadIdx.x + k * SC_THREADS;
-                        uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
-                        uint64_t sel = 0x5555555555555555ULL;
-                        for ( uint32_t t = 0; t < nb; ++t )
-                        {
-                                bool const half = (2*(t+1) > pbits);
-                                uint32_t const code = half ? ((pid & 1) << 1) : ((pid >> (pbits - 2*(t+1))) & 3);
-                                uint64_t const e0 = base_eq_mask(w0, code, half), e1 = base_eq_mask(w1, code, half);
-                                sel &= t ? ((e0 << (2*t)) | (e1 >> (64 - 2*t))) : e0;
-                        }
-                        // clip to [x_begin, x_end)
-                        uint64_t const lx0 = tile_x0 + (uint64_t)wi * 32;
-                        if ( lx0 + 32 <= P.x_begin || lx0 >= P.x_end ) sel = 0;
-                        else
-                        {
-                                if ( lx0 < P.x_begin ) sel &= (~0ULL) >> (2 * (P.x_begin - lx0));
-                                if ( lx0 + 32 > P.x_end ) sel &= (~0ULL) << (2 * (lx0 + 32 - P.x_end));
-                        }
-                        uint32_t const c = (uint32_t)__popcll(sel);
-                        uint32_t const incl = warp_incl_scan(c, lane);
-                        uint32_t base = 0;
-                        if ( lane == 31 && incl ) base = atomicAdd(&q1n, incl);
-                        base = __shfl_sync(0xffffffffu, base, 31);
-                        uint32_t o = base + incl - c;
-                        while ( sel )
-                        {
-                                uint32_t const b = 63 - __clzll(sel);
-                                sel ^= 1ULL << b;
-                                q1[o++] = (uint16_t)(wi * 32 + ((62 - b) >> 1));
-                        }
-                }
-                __syncthreads();
-                uint32_t const n1 = q1n;
-
-                // (3) probe the queue, (4) queue the candidates
-                for ( uint32_t i0 = 0; i0 < n1; i0 += SC_THREADS )
-                {
-                        uint32_t const i = i0 + threadIdx.x;
-                        uint32_t cand = 0;
-                        uint64_t lx = 0;
-                        if ( i < n1 )
-                        {
-                                uint32_t const lp = q1[i];
-                                uint32_t const wi = lp >> 5, j = lp & 31;
-                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
-                                uint64_t const win = (j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0) >> fsh;
-                                uint64_t const m0 = (win >> (6*F)) & fm, m1 = (win >> (4*F)) & fm, m2 = (win >> (2*F)) & fm, m3 = win & fm;
-                                lx = tile_x0 + lp;
-                                uint32_t vA = 0, vB = 0, vC = 0, rA = 0, rB = 0, rC = 0;
-                                if ( nlA )
-                                {
-                                        uint32_t const h = slot_of((m0 << (2*F)) | m1, kb, P.tab[0].hb);
-                                        uint32_t const sc = h / SECTOR_SLOTS; rA = h - sc * SECTOR_SLOTS;
-                                        vA = ld_probe(P.tab[0].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rA >> 5));
-                                }
-                                if ( nlB )
-                                {
-                                        uint32_t const h = slot_of((m0 << (2*F)) | m2, kb, P.tab[1].hb);
-                                        uint32_t const sc = h / SECTOR_SLOTS; rB = h - sc * SECTOR_SLOTS;
-                                        vB = ld_probe(P.tab[1].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rB >> 5));
-                                }
-                                if ( nlC )
-                                {
-                                        uint32_t const h = slot_of((m0 << (2*F)) | m3, kb, P.tab[2].hb);
-                                        uint32_t const sc = h / SECTOR_SLOTS; rC = h - sc * SECTOR_SLOTS;
-                                        vC = ld_probe(P.tab[2].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rC >> 5));
-                                }
-                                cand = ((vA >> (rA & 31)) & 1) | (((vB >> (rB & 31)) & 1) << 1) | (((vC >> (rC & 31)) & 1) << 2);
-                        }
-                        uint32_t const c = __popc(cand);
-                        uint32_t const incl = warp_incl_scan(c, lane);
-                        uint32_t base = 0;
-                        if ( lane == 31 && incl ) base = atomicAdd(&q2n, incl);
-                        base = __shfl_sync(0xffffffffu, base, 31);
-                        uint32_t o = base + incl - c;
+                        locate_unit(P, S.ustart, u0, r0n, r1n);
                         #pragma unroll
-                        for ( int table = 0; table < 3; ++table )
-                                if ( (cand >> table) & 1 )
-                                        q2[o++] = ((unsigned long long)lx << 2) | (unsigned long long)table;
-                        __syncthreads();
-                        uint32_t const n2 = q2n;
-                        if ( n2 >= SC_Q2_DRAIN )
+                        for ( int k = 0; k < SC_RPT; ++k )
                         {
-                                drain_candidates(P, q2, n2, lstats);
-                                __syncthreads();
-                                if ( threadIdx.x == 0 ) q2n = 0;
-                                __syncthreads();
+                                uint32_t const r = r0n + k * SC_THREADS + threadIdx.x;
+                                win_next[k] = (r < r1n) ? __ldcs(P.rec_win + r) : 0;
                         }
                 }
-                __syncthreads();   // everyone is done with tile[buf] and q1 before they are refilled
-                if ( threadIdx.x == 0 ) q1n = 0;
-                __syncthreads();
         }
+        uint32_t u = S.unit[0];
+        __syncthreads();
+        for ( uint32_t iter = 0; u < nunits; ++iter )
         {
-                uint32_t const n2 = q2n;
-                if ( n2 ) drain_candidates(P, q2, n2, lstats);
+                uint32_t const r0 = r0n, r1 = r1n;
+                uint64_t win[SC_RPT];
+                #pragma unroll
+                for ( int k = 0; k < SC_RPT; ++k ) win[k] = win_next[k];
+                uint32_t const unext = S.unit[(iter + 1) & 1];
+                if ( unext < nunits )
+                {
+                        locate_unit(P, S.ustart, unext, r0n, r1n);
+                        #pragma unroll
+                        for ( int k = 0; k < SC_RPT; ++k )
+                        {
+                                uint32_t const r = r0n + k * SC_THREADS + threadIdx.x;
+                                win_next[k] = (r < r1n) ? __ldcs(P.rec_win + r) : 0;
+                        }
+                }
+                if ( threadIdx.x == 0 ) S.unit[iter & 1] = atomicAdd(P.unit_counter, 1u);      // for iteration iter+2
+                u = unext;
+
+                uint32_t v[SC_RPT][3], bit[SC_RPT][3];
+                #pragma unroll
+                for ( int k = 0; k < SC_RPT; ++k )
+                {
+                        uint32_t const r = r0 + k * SC_THREADS + threadIdx.x;
+                        bool const ok = r < r1;
+                        uint64_t const m0 = (win[k] >> (6*F)) & fm, m1 = (win[k] >> (4*F)) & fm, m2 = (win[k] >> (2*F)) & fm, m3 = win[k] & fm;
+                        v[k][0] = v[k][1] = v[k][2] = 0; bit[k][0] = bit[k][1] = bit[k][2] = 0;
+                        if ( ok && nlA )
+                        {
+                                uint32_t const h = slot_of((m0 << (2*F)) | m1, kb, P.tab[0].hb);
+                                uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][0] = rr & 31;
+                                v[k][0] = ld_hot_u32(P.tab[0].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
+                        }
+                        if ( ok && nlB )
+                        {
+                                uint32_t const h = slot_of((m0 << (2*F)) | m2, kb, P.tab[1].hb);
+                                uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][1] = rr & 31;
+                                v[k][1] = ld_hot_u32(P.tab[1].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
+                        }
+                        if ( ok && nlC )
+                        {
+                                uint32_t const h = slot_of((m0 << (2*F)) | m3, kb, P.tab[2].hb);
+                                uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][2] = rr & 31;
+                                v[k][2] = ld_hot_u32(P.tab[2].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
+                        }
+                }
+                // compact the set slot bits into the stage A queue
+                uint32_t cand = 0;
+                #pragma unroll
+                for ( int k = 0; k < SC_RPT; ++k )
+                        #pragma unroll
+                        for ( int t = 0; t < 3; ++t )
+                                cand |= ((v[k][t] >> bit[k][t]) & 1u) << (k * 3 + t);
+                uint32_t const c = __popc(cand);
+                uint32_t const incl = warp_incl_scan(c, lane);
+                uint32_t base = 0;
+                if ( lane == 31 && incl ) base = atomicAdd(&S.qan, incl);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                uint32_t o = base + incl - c;
+                #pragma unroll
+                for ( int k = 0; k < SC_RPT; ++k )
+                {
+                        if ( (cand >> (k * 3)) & 7u )
+                        {
+                                uint32_t const r = r0 + k * SC_THREADS + threadIdx.x;
+                                uint32_t const pos = __ldcs(P.rec_pos + r);
+                                #pragma unroll
+                                for ( int t = 0; t < 3; ++t )
+                                        if ( (cand >> (k * 3 + t)) & 1u )
+                                        {
+                                                ItemA ia; ia.win = win[k]; ia.pos = pos; ia.table = (uint32_t)t;
+                                                S.qa[o++] = ia;
+                                        }
+                        }
+                }
+                __syncthreads();
+                if ( P.debug_flags & 1 )
+                {
+                        if ( threadIdx.x == 0 ) { lstats[0] += S.qan; S.qan = 0; }
+                        __syncthreads();
+                }
+                else if ( S.qan >= SC_QA_DRAIN )
+                        drain_a(P, S, lstats, false, pol);
         }
+        drain_a(P, S, lstats, true, pol);
 
         // statistics: one atomic per warp and counter
         #pragma unroll
         for ( int s = 0; s < 3; ++s )
         {
-                unsigned long long v = lstats[s];
+                unsigned long long v2 = lstats[s];
                 #pragma unroll
                 for ( int o = 16; o > 0; o >>= 1 )
-                        v += __shfl_xor_sync(0xffffffffu, v, o);
-                if ( (threadIdx.x & 31) == 0 && v )
-                        atomicAdd(P.stats + s, v);
+                        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+                if ( (threadIdx.x & 31) == 0 && v2 )
+                        atomicAdd(P.stats + s, v2);
         }
 }
 
