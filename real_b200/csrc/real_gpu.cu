@@ -30,7 +30,8 @@ struct Table
         DevBuf bitmap, E;
         uint32_t hb, nlists, nsectors;
         uint64_t nentries, ndistinct;
-        Table() : hb(0), nlists(0), nsectors(0), nentries(0), ndistinct(0) {}
+        size_t bitmap_bytes;
+        Table() : hb(0), nlists(0), nsectors(0), nentries(0), ndistinct(0), bitmap_bytes(0) {}
 };
 
 } // namespace
@@ -63,6 +64,9 @@ struct real_gpu
 
         // results
         DevBuf rec_win, rec_pos, part_meta;
+        DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
+        uint32_t table_counts[6];      // per table: entries, distinct slots (read back after the build)
+        const uint8_t * src_mapped;    // device pointer the reads are packed from (caller's buffer or h->mapped)
         DevBuf ll, hits_raw, hits_seg, hits_out, counters, counts, starts, cursor, scantmp, info, scores;
         uint64_t hit_cap;
         real_gpu_hit * host_hits;
@@ -73,7 +77,7 @@ struct real_gpu
         uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
 
-        real_gpu() : pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -161,9 +165,9 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
         size_t const tbytes = (TEXT_PAD_WORDS + nw + tail) * 8, mbytes = (TEXT_PAD_WORDS + nmw + tail) * 8;
 
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
-        dev_alloc(h, h->text, tbytes);
-        dev_alloc(h, h->nmask, mbytes);
-        dev_alloc(h, h->rec, (size_t)(nrecords + 1) * 8);
+        dev_reserve(h, h->text, tbytes);
+        dev_reserve(h, h->nmask, mbytes);
+        dev_reserve(h, h->rec, (size_t)(nrecords + 1) * 8);
         RG_CUDA(cudaMemsetAsync(h->text.p, 0, tbytes, h->st));
         RG_CUDA(cudaMemsetAsync(h->nmask.p, 0, mbytes, h->st));
         cudaMemcpyKind const kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -184,15 +188,17 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
 // reads + index
 // ---------------------------------------------------------------------------------------------
 
-void build_table(real_gpu * h, int t, DevBuf & k0, DevBuf & v0, DevBuf & k1, DevBuf & v1, DevBuf & flags, RadixSortTemp const & rst)
+// one table: partition the entries by slot prefix, set the presence bits, rank them, place the entries
+void build_table(real_gpu * h, int t, uint32_t * meta)
 {
         Table & T = h->tab[t];
         T.nlists = table_lists(t, h->prm.seedkmax);
-        T.nentries = h->n_usable * 2 * T.nlists;
+        uint64_t const cap_entries = h->nreads * 2 * T.nlists;        // upper bound (unusable reads produce none)
+        T.nentries = 0;
         {
                 // automatic: about 32 slots per entry of the largest table, at least 2^20, at most the key width / 32 bits
                 uint32_t const cap = std::min<uint32_t>(h->keybits, 32);
-                uint64_t const want = std::max<uint64_t>(1, h->n_usable * 2 * table_lists(0, h->prm.seedkmax)) * 32;
+                uint64_t const want = std::max<uint64_t>(1, h->nreads * 2 * table_lists(0, h->prm.seedkmax)) * 32;
                 uint32_t autob = 20;
                 while ( autob < cap && (1ULL << autob) < want ) ++autob;
                 T.hb = h->prm.table_bits ? std::min<uint32_t>(h->prm.table_bits, cap) : std::min<uint32_t>(autob, cap);
@@ -201,50 +207,56 @@ void build_table(real_gpu * h, int t, DevBuf & k0, DevBuf & v0, DevBuf & k1, Dev
         T.ndistinct = 0;
         uint64_t const nslots = 1ULL << T.hb;
         T.nsectors = (uint32_t)((nslots + SECTOR_SLOTS - 1) / SECTOR_SLOTS);
-        dev_alloc(h, T.bitmap, (size_t)T.nsectors * SECTOR_WORDS * 4);
-        RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap.bytes, h->st));
-        dev_alloc(h, T.E, std::max<size_t>(16, T.nentries * sizeof(Entry)));
-        if ( T.nentries == 0 )
+        T.bitmap_bytes = (size_t)T.nsectors * SECTOR_WORDS * 4;
+        dev_reserve(h, T.bitmap, T.bitmap_bytes);
+        dev_reserve(h, T.E, std::max<size_t>(16, 2 * cap_entries * sizeof(Entry)));   // [0,cap): by rank; [cap,2cap): same-slot overflow, by grouped index
+        RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap_bytes, h->st));
+        if ( T.nlists == 0 || h->nreads == 0 )
                 return;
-        if ( T.nentries >= (1ULL << 32) )
+        if ( 2 * cap_entries >= 0xFFFFFFFFULL )
                 throw CudaError("index: more than 2^32 entries in one table");
-        uint32_t const n = (uint32_t)T.nentries;
 
-        TableGeom G; G.F = h->F; G.keybits = h->keybits; G.hb = T.hb; G.nlists = T.nlists; G.table = t;
-        k_gen_entries<<<blocks_for(2 * h->nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable_rank), ptr<uint32_t>(h->usable),
-                                                                        h->nreads, G, ptr<uint32_t>(k0), ptr<uint32_t>(v0));
-        RG_KERNEL_CHECK(); launch_count(h);
+        // meta layout (u32): [0,256) bucket counts, [256,513) bucket starts, 520 total, 521 ndistinct, 522 overflow counter, [1024, ...) cursors
+        EntryPartParams EP;
+        EP.seeds = ptr<uint64_t>(h->seeds); EP.usable = ptr<uint32_t>(h->usable); EP.nids = 2 * h->nreads;
+        EP.G.F = h->F; EP.G.keybits = h->keybits; EP.G.hb = T.hb; EP.G.nlists = T.nlists; EP.G.table = t;
+        EP.ebits = std::min<uint32_t>(8, T.hb);
+        EP.ent_seed = ptr<uint64_t>(h->ws_k0); EP.ent_val = ptr<uint32_t>(h->ws_v0);
+        EP.bucket_count = meta; EP.bucket_start = meta + 256; EP.bucket_cursor = meta + 1024;
+        uint32_t * d_total = meta + 520, * d_ndist = meta + 521;
+        RG_CUDA(cudaMemsetAsync(meta, 0, 1024 * 4, h->st));
 
-        uint32_t nl = 0;
-        int const where = radix_sort_pairs(ptr<uint32_t>(k0), ptr<uint32_t>(v0), ptr<uint32_t>(k1), ptr<uint32_t>(v1), n, T.hb, rst, h->st, &nl);
-        launch_count(h, nl);
-        uint32_t * sk = where ? ptr<uint32_t>(k1) : ptr<uint32_t>(k0);
-        uint32_t * sv = where ? ptr<uint32_t>(v1) : ptr<uint32_t>(v0);
-        uint32_t * other = where ? ptr<uint32_t>(k0) : ptr<uint32_t>(k1);    // free ping-pong half: head flags + their scan
+        unsigned const grid = (unsigned)(h->sm_count * 8);
+        k_ent_hist<<<grid, 256, 0, h->st>>>(EP);
+        RG_KERNEL_CHECK();
+        k_ent_offsets<<<1, EP_MAX_BUCKETS, 0, h->st>>>(EP, d_total);
+        RG_KERNEL_CHECK();
+        size_t const esmem = sizeof(EntryPartSmem);
+        RG_CUDA(cudaFuncSetAttribute(k_ent_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+        int occ = 0;
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ent_scatter, 256, esmem));
+        if ( occ < 1 ) occ = 1;
+        uint64_t const etiles = (EP.nids + EP_TILE_IDS - 1) / EP_TILE_IDS;
+        k_ent_scatter<<<(unsigned)std::min<uint64_t>(etiles, (uint64_t)h->sm_count * occ), 256, esmem, h->st>>>(EP);
+        RG_KERNEL_CHECK();
+        k_build_bits<<<grid, 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap));
+        RG_KERNEL_CHECK();
+        launch_count(h, 4);
 
-        k_mark_heads<<<blocks_for(n, 256), 256, 0, h->st>>>(sk, n, ptr<uint32_t>(flags));
-        RG_KERNEL_CHECK(); launch_count(h);
-        nl = 0;
-        exclusive_scan_u32(ptr<uint32_t>(flags), other, n, rst.scan_tmp, h->st, &nl);
-        launch_count(h, nl);
-        uint32_t last_scan = 0, last_flag = 0;
-        RG_CUDA(cudaMemcpyAsync(&last_scan, other + (n - 1), 4, cudaMemcpyDeviceToHost, h->st));
-        RG_CUDA(cudaMemcpyAsync(&last_flag, ptr<uint32_t>(flags) + (n - 1), 4, cudaMemcpyDeviceToHost, h->st));
-        RG_CUDA(cudaStreamSynchronize(h->st));
-        T.ndistinct = (uint64_t)last_scan + last_flag;
-
-        k_place_entries<<<blocks_for(n, 256), 256, 0, h->st>>>(sk, sv, other, n, (uint32_t)T.ndistinct, ptr<uint64_t>(h->seeds), ptr<Entry>(T.E), ptr<uint32_t>(T.bitmap));
-        RG_KERNEL_CHECK(); launch_count(h);
-
-        // rank headers: per-sector popcount -> exclusive scan -> header word
-        uint32_t * cnt = ptr<uint32_t>(flags);       // reuse (nsectors may exceed n: flags is sized for both)
+        // rank headers: per-sector popcount -> exclusive scan -> header word (+ number of distinct slots)
+        uint32_t * cnt = ptr<uint32_t>(h->ws_flags);
         k_sector_counts<<<blocks_for(T.nsectors, 256), 256, 0, h->st>>>(ptr<uint32_t>(T.bitmap), T.nsectors, cnt);
         RG_KERNEL_CHECK(); launch_count(h);
-        nl = 0;
-        exclusive_scan_u32(cnt, cnt, T.nsectors, rst.scan_tmp, h->st, &nl);
+        uint32_t nl = 0;
+        exclusive_scan_u32(cnt, cnt, T.nsectors, ptr<uint32_t>(h->ws_stmp), h->st, &nl);
         launch_count(h, nl);
-        k_sector_headers<<<blocks_for(T.nsectors, 256), 256, 0, h->st>>>(ptr<uint32_t>(T.bitmap), T.nsectors, cnt);
+        k_sector_headers<<<blocks_for(T.nsectors, 256), 256, 0, h->st>>>(ptr<uint32_t>(T.bitmap), T.nsectors, cnt, d_ndist);
         RG_KERNEL_CHECK(); launch_count(h);
+
+        RG_CUDA(cudaMemsetAsync(T.E.p, 0xFF, cap_entries * sizeof(Entry), h->st));
+        k_build_entries<<<grid, 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap), (uint32_t)cap_entries, ptr<Entry>(T.E));
+        RG_KERNEL_CHECK(); launch_count(h);
+        RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
 }
 
 int build_from_device(real_gpu * h)
@@ -256,68 +268,46 @@ int build_from_device(real_gpu * h)
         uint64_t const nreads = h->nreads;
 
         RG_CUDA(cudaEventRecord(h->ev[2], h->st));
-        dev_alloc(h, h->rpack, (size_t)nreads * 2 * h->W * 8 + 16);
-        dev_alloc(h, h->rlen, (size_t)nreads * 4 + 16);
-        dev_alloc(h, h->seeds, (size_t)nreads * 2 * 8 + 16);
-        dev_alloc(h, h->usable, (size_t)nreads * 4 + 16);
-        dev_alloc(h, h->usable_rank, (size_t)nreads * 4 + 16);
-        dev_alloc(h, h->bad, (size_t)nreads * 4 + 16);
-        RG_CUDA(cudaMemsetAsync(h->bad.p, 0, h->bad.bytes, h->st));
+        dev_reserve(h, h->rpack, (size_t)nreads * 2 * h->W * 8 + 16);
+        dev_reserve(h, h->rlen, (size_t)nreads * 4 + 16);
+        dev_reserve(h, h->seeds, (size_t)nreads * 2 * 8 + 16);
+        dev_reserve(h, h->usable, (size_t)nreads * 4 + 16);
         if ( nreads )
         {
-                k_pack_reads<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(ptr<uint8_t>(h->mapped), ptr<uint64_t>(h->offs), nreads, h->W,
-                                                                                  ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->bad));
-                RG_KERNEL_CHECK(); launch_count(h);
-                k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
-                                                                       ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
+                k_pack_reads<<<blocks_for(nreads * 32, 256), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W, seedl,
+                                                                              ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
                 RG_KERNEL_CHECK(); launch_count(h);
         }
         RG_CUDA(cudaEventRecord(h->ev[3], h->st));
 
-        // compaction rank of usable reads
-        dev_reserve(h, h->scantmp, scan_temp_elems(std::max<uint64_t>(nreads, 1)) * 4 + 64);
-        h->n_usable = 0;
-        if ( nreads )
-        {
-                uint32_t nl = 0;
-                exclusive_scan_u32(ptr<uint32_t>(h->usable), ptr<uint32_t>(h->usable_rank), nreads, ptr<uint32_t>(h->scantmp), h->st, &nl);
-                launch_count(h, nl);
-                uint32_t lr = 0, lu = 0;
-                RG_CUDA(cudaMemcpyAsync(&lr, ptr<uint32_t>(h->usable_rank) + (nreads - 1), 4, cudaMemcpyDeviceToHost, h->st));
-                RG_CUDA(cudaMemcpyAsync(&lu, ptr<uint32_t>(h->usable) + (nreads - 1), 4, cudaMemcpyDeviceToHost, h->st));
-                RG_CUDA(cudaStreamSynchronize(h->st));
-                h->n_usable = (uint64_t)lr + lu;
-        }
-
-        // sort workspace sized for the largest table (A: 3 lists)
-        uint64_t const maxent = std::max<uint64_t>(1, h->n_usable * 2 * table_lists(0, h->prm.seedkmax));
+        // workspace sized for the largest table (A: up to 3 entries per read strand)
+        uint64_t const maxent = std::max<uint64_t>(1, nreads * 2 * table_lists(0, h->prm.seedkmax));
         uint32_t const hbmax = std::min<uint32_t>(h->keybits, 32);
         uint64_t const maxsectors = ((1ULL << hbmax) + SECTOR_SLOTS - 1) / SECTOR_SLOTS;
-        DevBuf k0, v0, k1, v1, flags, hist, stmp;
-        dev_alloc(h, k0, maxent * 4 + 16); dev_alloc(h, v0, maxent * 4 + 16);
-        dev_alloc(h, k1, maxent * 4 + 16); dev_alloc(h, v1, maxent * 4 + 16);
-        dev_alloc(h, flags, std::max<uint64_t>(maxent, maxsectors) * 4 + 16);
-        uint64_t const nblk = rs_num_blocks(maxent);
-        dev_alloc(h, hist, (size_t)RS_BINS * nblk * 4 + 16);
-        uint64_t const scan_need = std::max<uint64_t>(std::max<uint64_t>((uint64_t)RS_BINS * nblk, maxent), maxsectors);
-        dev_alloc(h, stmp, scan_temp_elems(scan_need) * 4 + 64);
-        RadixSortTemp rst; rst.hist = ptr<uint32_t>(hist); rst.scan_tmp = ptr<uint32_t>(stmp);
-
+        dev_reserve(h, h->ws_k0, maxent * 8 + 16);           // grouped entry seeds
+        dev_reserve(h, h->ws_v0, maxent * 4 + 16);           // grouped entry values
+        dev_reserve(h, h->ws_flags, maxsectors * 4 + 16);    // sector counts / ranks
+        dev_reserve(h, h->ws_stmp, scan_temp_elems(maxsectors) * 4 + 64);
+        dev_reserve(h, h->ws_hist, (1024 + 256 * EP_CURSOR_STRIDE) * 4);
+        memset(h->table_counts, 0, sizeof(h->table_counts));
         for ( int t = 0; t < 3; ++t )
-                build_table(h, t, k0, v0, k1, v1, flags, rst);
+                build_table(h, t, ptr<uint32_t>(h->ws_hist));
         RG_CUDA(cudaEventRecord(h->ev[4], h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
-        dev_free(h, k0); dev_free(h, v0); dev_free(h, k1); dev_free(h, v1); dev_free(h, flags); dev_free(h, hist); dev_free(h, stmp);
-        // mapped bytes are not needed once packed
-        dev_free(h, h->mapped);
-        dev_free(h, h->bad);
+        h->n_usable = 0;
+        for ( int t = 0; t < 3; ++t )
+        {
+                h->tab[t].nentries = h->table_counts[2*t];
+                h->tab[t].ndistinct = h->table_counts[2*t+1];
+        }
+        if ( h->tab[0].nlists ) h->n_usable = h->tab[0].nentries / (2 * h->tab[0].nlists);
 
         h->stats.pack_ms = elapsed(h->ev[2], h->ev[3]);
         h->stats.index_ms = elapsed(h->ev[3], h->ev[4]);
 
         // fresh unique state (UniqueMatchInfo.hpp:172,190)
-        dev_alloc(h, h->info, (size_t)nreads * 8 + 16);
-        RG_CUDA(cudaMemsetAsync(h->info.p, 0, h->info.bytes, h->st));
+        dev_reserve(h, h->info, (size_t)nreads * 8 + 16);
+        RG_CUDA(cudaMemsetAsync(h->info.p, 0, (size_t)nreads * 8 + 16, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->have_reads = true;
         return REAL_GPU_OK;
@@ -385,7 +375,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                 uint32_t const maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
                 for ( int t = 0; t < 3; ++t )
                         if ( P.tab[t].nlists )
-                                table_bytes += h->tab[t].bitmap.bytes + h->tab[t].nentries * sizeof(Entry);
+                                table_bytes += h->tab[t].bitmap_bytes + 2 * h->tab[t].nentries * sizeof(Entry);
                 uint32_t bbits = 0;
                 if ( h->pass_bits_override >= 0 )
                         bbits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
@@ -531,7 +521,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
@@ -578,8 +568,9 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
         h->have_reads = false;
         h->nreads = nreads; h->total_bases = total; h->maxlen = maxlen;
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
-        dev_alloc(h, h->mapped, total + 64);
-        dev_alloc(h, h->offs, (nreads + 1) * 8);
+        dev_reserve(h, h->mapped, total + 64);
+        dev_reserve(h, h->offs, (nreads + 1) * 8);
+        h->src_mapped = ptr<uint8_t>(h->mapped);
         if ( total ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, mapped + offsets[0], total, cudaMemcpyHostToDevice, h->st));
         if ( offsets[0] != 0 )
         {
@@ -593,12 +584,10 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
         h->qual_present = false;
         if ( quality && (h->prm.scores || h->ll.p) )
         {
-                dev_alloc(h, h->qual, total + 64);
+                dev_reserve(h, h->qual, total + 64);
                 if ( total ) RG_CUDA(cudaMemcpyAsync(h->qual.p, quality + offsets[0], total, cudaMemcpyHostToDevice, h->st));
                 h->qual_present = true;
         }
-        else
-                dev_free(h, h->qual);
         RG_CUDA(cudaEventRecord(h->ev[1], h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
@@ -615,19 +604,16 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
         if ( maxlen > 65535 ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: read longer than 65535 bases");
         h->have_reads = false;
         h->nreads = nreads; h->total_bases = total_bases; h->maxlen = maxlen;
-        dev_alloc(h, h->mapped, total_bases + 64);
-        dev_alloc(h, h->offs, (nreads + 1) * 8);
-        if ( total_bases ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, d_mapped, total_bases, cudaMemcpyDeviceToDevice, h->st));
+        dev_reserve(h, h->offs, (nreads + 1) * 8);
+        h->src_mapped = d_mapped;          // packed before this call returns; the caller's buffer is not referenced afterwards
         RG_CUDA(cudaMemcpyAsync(h->offs.p, d_offsets, (nreads + 1) * 8, cudaMemcpyDeviceToDevice, h->st));
         h->qual_present = false;
         if ( d_quality && (h->prm.scores || h->ll.p) )
         {
-                dev_alloc(h, h->qual, total_bases + 64);
+                dev_reserve(h, h->qual, total_bases + 64);
                 if ( total_bases ) RG_CUDA(cudaMemcpyAsync(h->qual.p, d_quality, total_bases, cudaMemcpyDeviceToDevice, h->st));
                 h->qual_present = true;
         }
-        else
-                dev_free(h, h->qual);
         h->stats.h2d_reads_ms = 0;
         return build_from_device(h);
         RG_API_END(h)
@@ -743,7 +729,7 @@ int real_gpu_reset_unique(real_gpu * h)
 {
         RG_API_BEGIN(h)
         if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
-        RG_CUDA(cudaMemsetAsync(h->info.p, 0, h->info.bytes, h->st));
+        RG_CUDA(cudaMemsetAsync(h->info.p, 0, (size_t)h->nreads * 8 + 16, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         return REAL_GPU_OK;
         RG_API_END(h)
