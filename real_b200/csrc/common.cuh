@@ -129,4 +129,28 @@ __host__ __device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t keyb
         return (top << low) | (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - low));
 }
 
+// Loads from the hot table slices (presence bits, entries).  Measured on B200
+// (tools/l2_resident_bench.cu): loads issued as ld.global.nc.L1::no_allocate are kept in L2 with low
+// priority -- a randomly probed 32 MB table already drops from ~278 to ~180 G probes/s, 64 MB to
+// ~105 -- while plain loads or loads carrying an evict_last policy hold ~275 G/s up to 64 MB, also with
+// a stream of touch-once data flowing through L2 at the same time.
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+        return pol;
+}
+__device__ __forceinline__ uint32_t ld_hot_u32(const uint32_t * p, uint64_t pol)
+{
+        uint32_t v;
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+        return v;
+}
+__device__ __forceinline__ uint4 ld_hot_v4(const void * p, uint64_t pol)
+{
+        uint4 v;
+        asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+        return v;
+}
+
 } // namespace realgpu

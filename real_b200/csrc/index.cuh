@@ -50,58 +50,83 @@ __device__ __forceinline__ uint64_t revcomp_word(uint64_t x, uint32_t len)
         return y >> (64 - 2*len);
 }
 
-// one warp per read: the lanes load 32 consecutive bases at a time (coalesced) and the packed word is
-// formed with two warp OR-reductions; both strands, usable flag, length and the two strand seeds.
-// seed word = seedl bases right aligned, fragment 0 in the top bits (what getTextWord(p,seedl) yields for
-// the text window the strand is laid over); the '-' seed is the LAST seedl bases of the reverse
-// complement strand (RestMatch.hpp:84-89) = the reverse complement of the first seedl bases of the read.
-__global__ void __launch_bounds__(256) k_pack_reads(const uint8_t * __restrict__ mapped, const uint64_t * __restrict__ offsets,
-                                                  uint64_t nreads, uint32_t W, uint32_t seedl, uint64_t * __restrict__ rpack,
-                                                  uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds, uint32_t * __restrict__ usable)
+// `len` (1..32) mapped bytes starting at p, packed 2 bit/base MSB first and left aligned; *bad is set when a
+// byte is not 0..3.  The bytes are fetched as aligned 32-bit words and realigned with funnel shifts; four
+// bases are packed at a time with one multiply: for x = b0 | b1<<8 | b2<<16 | b3<<24 (each 0..3) the top byte
+// of x * 0x40100401 is b0<<6 | b1<<4 | b2<<2 | b3 (the partial products land on disjoint bits).
+__device__ __forceinline__ uint64_t pack_bytes(const uint8_t * __restrict__ p, uint32_t len, uint32_t & bad)
 {
-        uint64_t const r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-        int const lane = threadIdx.x & 31;
-        if ( r >= nreads ) return;
+        uintptr_t const addr = reinterpret_cast<uintptr_t>(p);
+        const uint32_t * q = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        uint32_t const sh = (uint32_t)(addr & 3) * 8;
+        uint32_t const nq = (uint32_t)((addr & 3) + len + 3) >> 2;        // aligned words that hold the bytes
+        uint32_t w[9];
+        #pragma unroll
+        for ( uint32_t i = 0; i < 9; ++i )
+                w[i] = (i < nq) ? __ldg(q + i) : 0u;
+        uint64_t word = 0;
+        #pragma unroll
+        for ( uint32_t i = 0; i < 8; ++i )
+        {
+                uint32_t x = __funnelshift_r(w[i], w[i+1], sh);
+                int const rem = (int)len - 4 * (int)i;                      // bytes of this group that belong to the read
+                if ( rem < 4 ) x &= (rem <= 0) ? 0u : (0xFFFFFFFFu >> (8 * (4 - rem)));
+                bad |= x & 0xFCFCFCFCu;
+                uint32_t const packed = ((x & 0x03030303u) * 0x40100401u) >> 24;
+                word |= (uint64_t)packed << (56 - 8 * i);
+        }
+        return word;
+}
+
+// one thread per (read, strand, word): word w of the '+' strand is read[32w, 32w+32); word w of the '-' strand
+// is the reverse complement of read[L-32w-len, L-32w)
+__global__ void __launch_bounds__(256) k_pack_reads(const uint8_t * __restrict__ mapped, const uint64_t * __restrict__ offsets,
+                                                  uint64_t nreads, uint32_t W, uint64_t * __restrict__ rpack, uint32_t * __restrict__ bad)
+{
+        uint64_t const gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( gid >= nreads * 2 * W ) return;
+        uint32_t const w = (uint32_t)(gid % W);
+        uint64_t const rs = gid / W;
+        uint32_t const s = (uint32_t)(rs & 1);
+        uint64_t const r = rs >> 1;
         uint64_t const o = offsets[r];
         uint32_t const L = (uint32_t)(offsets[r+1] - o);
-        const uint8_t * p = mapped + o;
-        uint32_t anybad = 0;
-        uint64_t first_word = 0;
-        for ( uint32_t w = 0; w < W; ++w )
+        uint64_t word = 0;
+        if ( 32 * w < L )
         {
-                uint32_t const b = w * 32 + lane;
-                // '+' strand: base b; '-' strand: complement of base L-1-b
-                uint32_t cf = 0, cr = 0;
-                if ( b < L )
+                uint32_t const len = min(32u, L - 32 * w);
+                uint32_t anybad = 0;
+                if ( s == 0 )
                 {
-                        uint32_t const x = p[b], y = p[L - 1 - b];
-                        anybad |= (x > 3);
-                        cf = x & 3;
-                        cr = 3 - (y & 3);
+                        word = pack_bytes(mapped + o + 32 * w, len, anybad);
+                        if ( anybad ) bad[r] = 1;
                 }
-                uint32_t const sh = 30 - 2 * (lane & 15);
-                uint32_t const fhi = __reduce_or_sync(0xffffffffu, lane < 16 ? (cf << sh) : 0u);
-                uint32_t const flo = __reduce_or_sync(0xffffffffu, lane < 16 ? 0u : (cf << sh));
-                uint32_t const rhi = __reduce_or_sync(0xffffffffu, lane < 16 ? (cr << sh) : 0u);
-                uint32_t const rlo = __reduce_or_sync(0xffffffffu, lane < 16 ? 0u : (cr << sh));
-                uint64_t const fw = ((uint64_t)fhi << 32) | flo, rw = ((uint64_t)rhi << 32) | rlo;
-                if ( w == 0 ) first_word = fw;
-                if ( lane == 0 )
+                else
                 {
-                        rpack[(2*r) * W + w] = fw;
-                        rpack[(2*r+1) * W + w] = rw;
+                        uint64_t const fwd = pack_bytes(mapped + o + (L - 32 * w - len), len, anybad);
+                        word = revcomp_word(fwd >> (64 - 2 * len), len) << (64 - 2 * len);
                 }
         }
-        anybad = __any_sync(0xffffffffu, anybad);
-        if ( lane == 0 )
-        {
-                bool const ok = (L >= seedl) && ! anybad;
-                rlen[r] = ok ? L : 0;
-                usable[r] = ok ? 1 : 0;
-                uint64_t const sf = first_word >> (64 - 2*seedl);
-                seeds[2*r] = ok ? sf : 0;
-                seeds[2*r+1] = ok ? revcomp_word(sf, seedl) : 0;
-        }
+        rpack[gid] = word;
+}
+
+// one thread per read: usable length and the two strand seeds.
+// seed word = seedl bases right aligned, fragment 0 in the top bits (what getTextWord(p,seedl) yields for the
+// text window the strand is laid over); the '-' seed is the LAST seedl bases of the reverse complement strand
+// (RestMatch.hpp:84-89) = the reverse complement of the first seedl bases of the read.
+__global__ void __launch_bounds__(256) k_read_seeds(const uint64_t * __restrict__ offsets, uint64_t nreads, uint32_t W, uint32_t seedl,
+                                                  const uint64_t * __restrict__ rpack, const uint32_t * __restrict__ bad,
+                                                  uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds, uint32_t * __restrict__ usable)
+{
+        uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( r >= nreads ) return;
+        uint32_t const L = (uint32_t)(offsets[r+1] - offsets[r]);
+        bool const ok = (L >= seedl) && ! bad[r];
+        rlen[r] = ok ? L : 0;
+        usable[r] = ok ? 1 : 0;
+        uint64_t const sf = rpack[(2*r) * W] >> (64 - 2*seedl);
+        seeds[2*r] = ok ? sf : 0;
+        seeds[2*r+1] = ok ? revcomp_word(sf, seedl) : 0;
 }
 
 // ---- K2 --------------------------------------------------------------------------------------
@@ -299,7 +324,7 @@ __global__ void __launch_bounds__(256) k_build_bits(const uint64_t * __restrict_
         uint32_t const n = *total;
         for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
         {
-                uint32_t const h = entry_slot(ent_seed[i], G, ent_val[i] & 3);
+                uint32_t const h = entry_slot(__ldcs(ent_seed + i), G, __ldcs(ent_val + i) & 3);
                 uint32_t const sector = h / SECTOR_SLOTS, slot = h - sector * SECTOR_SLOTS;
                 atomicOr(&bitmap[(uint64_t)sector * SECTOR_WORDS + 1 + (slot >> 5)], 1u << (slot & 31));
         }
@@ -313,14 +338,15 @@ __global__ void __launch_bounds__(256) k_build_entries(const uint64_t * __restri
                                                      TableGeom G, const uint32_t * __restrict__ bitmap, uint32_t ovf_base, Entry * __restrict__ E)
 {
         uint32_t const n = *total;
+        uint64_t const pol = policy_evict_last();
         for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
         {
-                uint64_t const seed = ent_seed[i];
-                uint32_t const val = ent_val[i];
+                uint64_t const seed = __ldcs(ent_seed + i);
+                uint32_t const val = __ldcs(ent_val + i);
                 uint32_t const h = entry_slot(seed, G, val & 3);
                 uint32_t const sector = h / SECTOR_SLOTS, slot = h - sector * SECTOR_SLOTS;
                 const uint4 * sp = reinterpret_cast<const uint4 *>(bitmap + (uint64_t)sector * SECTOR_WORDS);
-                uint4 const a = sp[0], b = sp[1];
+                uint4 const a = ld_hot_v4(sp, pol), b = ld_hot_v4(sp + 1, pol);
                 uint32_t const wv[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
                 uint32_t rank = wv[0];
                 uint32_t const wi = slot >> 5;

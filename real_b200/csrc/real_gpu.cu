@@ -272,10 +272,15 @@ int build_from_device(real_gpu * h)
         dev_reserve(h, h->rlen, (size_t)nreads * 4 + 16);
         dev_reserve(h, h->seeds, (size_t)nreads * 2 * 8 + 16);
         dev_reserve(h, h->usable, (size_t)nreads * 4 + 16);
+        dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
+        RG_CUDA(cudaMemsetAsync(h->bad.p, 0, (size_t)nreads * 4 + 16, h->st));
         if ( nreads )
         {
-                k_pack_reads<<<blocks_for(nreads * 32, 256), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W, seedl,
-                                                                              ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
+                k_pack_reads<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W,
+                                                                                  ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->bad));
+                RG_KERNEL_CHECK(); launch_count(h);
+                k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
+                                                                       ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
                 RG_KERNEL_CHECK(); launch_count(h);
         }
         RG_CUDA(cudaEventRecord(h->ev[3], h->st));
@@ -384,31 +389,28 @@ uint64_t run_scan(real_gpu * h, int mode)
                 P.bucket_bits = bbits;
                 if ( const char * e = getenv("REAL_GPU_DEBUG") ) P.debug_flags = (uint32_t)atoi(e);
 
-                uint64_t const chunk_max = h->chunk_positions;
+                uint64_t const chunk_max = std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
                 uint64_t const x_begin = P.x_begin, x_end = P.x_end;
                 uint64_t const chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
-                dev_reserve(h, h->rec_win, chunk_cap * 8 + 64);
-                dev_reserve(h, h->rec_pos, chunk_cap * 4 + 64);
+                dev_reserve(h, h->rec_win, (chunk_cap + (uint64_t)SC_MAX_BUCKETS * SC_UNIT) * sizeof(uint4) + 64);
                 dev_reserve(h, h->part_meta, (1100 + 256 * SC_CURSOR_STRIDE) * 4);
                 uint32_t * meta = ptr<uint32_t>(h->part_meta);
-                P.rec_win = ptr<uint64_t>(h->rec_win);
-                P.rec_pos = ptr<uint32_t>(h->rec_pos);
+                P.recs = ptr<uint4>(h->rec_win);
                 P.bucket_count = meta;
                 P.bucket_start = meta + 256;
-                P.unit_start = meta + 256 + 260;
                 P.unit_counter = meta + 256 + 520;
                 P.bucket_cursor = meta + 1088;
 
-                size_t const psmem = sizeof(PartSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem);
-                RG_CUDA(cudaFuncSetAttribute(k_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem);
+                RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
                 RG_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
                 RG_CUDA(cudaFuncSetAttribute(k_bucket_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
                 int occ_p = 0, occ_b = 0, occ_s = 0;
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part<false>, SC_THREADS, psmem));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, psmem));
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_part_scatter, SC_THREADS, ssmem));
-                if ( occ_s < 1 ) occ_s = 1;
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bucket_probe, SC_THREADS, bsmem));
                 if ( occ_p < 1 ) occ_p = 1;
+                if ( occ_s < 1 ) occ_s = 1;
                 if ( occ_b < 1 ) occ_b = 1;
 
                 for ( uint64_t cb = x_begin; cb < x_end; cb += chunk_cap )
@@ -418,7 +420,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                         uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
                         unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * occ_p);
                         RG_CUDA(cudaMemsetAsync(meta, 0, 256 * 4, h->st));
-                        k_part<false><<<pgrid, SC_THREADS, psmem, h->st>>>(P);
+                        k_part_hist<<<pgrid, SC_THREADS, psmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
                         k_part_offsets<<<1, SC_MAX_BUCKETS, 0, h->st>>>(P);
                         RG_KERNEL_CHECK();

@@ -16,13 +16,15 @@
 // in L2.
 //
 //   k_part_hist     TMA-staged text tiles -> bucket histogram
-//   k_part_offsets  bucket starts + work-unit directory (one small block)
-//   k_part_scatter  TMA-staged text tiles -> (window word, position) records grouped by bucket
-//   k_bucket_probe  persistent CTAs pull 1024-record units in bucket order; every thread issues its
-//                   12 independent 4-byte probes; set slot bits are compacted into a shared-memory
-//                   queue (stage A: rank -> entry chain -> seed test -> canonical-list rule), the
-//                   survivors into a second queue (stage B: record / wildcard predicates, whole-read
-//                   XOR+popcount distance, report), so that each stage runs with full warps.
+//   k_part_offsets  bucket starts (padded to whole work units) + sentinel records in the padding
+//   k_part_scatter  TMA-staged text tiles -> 16-byte records {window word, the 16 bases in front of it,
+//                   position} grouped by bucket (staged in shared memory, written run by run)
+//   k_bucket_probe  CTAs pull 2048-record grabs in bucket order, every warp owns 256 of them and walks
+//                   them 64 at a time: 6 independent 4-byte probes per lane; set slot bits are compacted
+//                   into the warp's shared-memory queue (stage A: rank -> entry chain -> seed test ->
+//                   canonical-list rule), the survivors into a second queue (stage B: record / wildcard
+//                   predicates, whole-read XOR+popcount distance, report), so that each stage runs with
+//                   full warps and no block-wide barrier sits between them.
 #pragma once
 
 #include "common.cuh"
@@ -39,12 +41,13 @@ static const int SC_HALO = 2;                                // words of halo in
 static const int SC_SMEM_WORDS = SC_TILE_WORDS + 2 * SC_HALO; // 516 words = 4128 bytes (multiple of 16)
 static const int SC_MAX_BUCKETS = 256;
 static const int SC_CURSOR_STRIDE = 32;                      // u32 per bucket cursor: one 128-byte line each, so the global atomics spread over the L2 slices
-static const int SC_UNIT = 512;                              // records per work unit of the probe kernel
-static const int SC_RPT = SC_UNIT / SC_THREADS;              // records per thread and unit
-static const int SC_QA_DRAIN = 512;                          // stage A queue (set slot bits): drained at this fill
-static const int SC_QA_CAP = SC_QA_DRAIN + 3 * SC_UNIT;      //   one more unit always fits
-static const int SC_QB_CAP = 512;                            // stage B queue (seed test passed)
-static const int SC_QB_DRAIN = 256;
+static const int SC_UNIT = 2048;                             // records per grab of the probe kernel (one global atomic)
+static const int SC_WARP_RECS = SC_UNIT / (SC_THREADS / 32); // 256 records per warp and grab
+static const int SC_RPT = 2;                                 // records per lane and step
+static const int SC_QA_CAP = 256;                            // per-warp stage A queue (set slot bits): drained from 32 up, a step adds <= 192
+static const int SC_QB_CAP = 64;                             // per-warp stage B queue (seed test passed)
+static const uint32_t SC_POS_NONE = 0xFFFFFFFFu;             // position word of a padding record
+static const uint64_t SC_MAX_CHUNK = 1ull << 30;             // positions per chunk: position (30 bits) and table (2 bits) share a word
 
 struct TableDev
 {
@@ -73,11 +76,9 @@ struct ScanParams
         // partition of the chunk [x_begin, x_end): x0 = first position of the chunk
         uint32_t bucket_bits;
         uint32_t debug_flags;         // development only (REAL_GPU_DEBUG): 1 = count set slot bits but do not follow them
-        uint64_t * rec_win;           // window word of every record, grouped by bucket
-        uint32_t * rec_pos;           // position of every record relative to x_begin
+        uint4 * recs;                 // records grouped by bucket: {window lo, window hi, 16 bases in front of it, position - x_begin}
         uint32_t * bucket_count;      // [SC_MAX_BUCKETS]
         uint32_t * bucket_start;      // [SC_MAX_BUCKETS+1] record index
-        uint32_t * unit_start;        // [SC_MAX_BUCKETS+1] work unit index
         uint32_t * bucket_cursor;     // [SC_MAX_BUCKETS]
         uint32_t * unit_counter;      // work distribution of k_bucket_probe
         int mode;                     // 0 = report all hits, 1 = fold into the unique state, 2 = gapped seed candidates
@@ -87,30 +88,6 @@ struct ScanParams
         unsigned long long * info;
         unsigned long long * stats;   // [0] candidates  [1] seed-pass  [2] hits
 };
-
-// Loads from the hot table slices (presence bits, entries).  Measured on B200
-// (tools/l2_resident_bench.cu): loads issued as ld.global.nc.L1::no_allocate are kept in L2 with low
-// priority -- a randomly probed 32 MB table already drops from ~278 to ~180 G probes/s, 64 MB to
-// ~105 -- while plain loads or loads carrying an evict_last policy hold ~275 G/s up to 64 MB, also with
-// a stream of touch-once data flowing through L2 at the same time.
-__device__ __forceinline__ uint64_t policy_evict_last()
-{
-        uint64_t pol;
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-        return pol;
-}
-__device__ __forceinline__ uint32_t ld_hot_u32(const uint32_t * p, uint64_t pol)
-{
-        uint32_t v;
-        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-        return v;
-}
-__device__ __forceinline__ uint4 ld_hot_v4(const void * p, uint64_t pol)
-{
-        uint4 v;
-        asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-        return v;
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -218,13 +195,11 @@ __device__ __forceinline__ bool wildcard_free(const uint64_t * __restrict__ nmas
 
 // ---- partition ---------------------------------------------------------------------------------
 
-struct PartSmem
+struct HistSmem
 {
         uint64_t tile[2][SC_SMEM_WORDS];
         uint64_t bar[2];
-        uint32_t cnt[SC_MAX_BUCKETS];                      // histogram variant: whole-grid-stride counts
-        uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];    // scatter variant: per-warp counts, then output offsets
-        uint16_t rank[SC_TILE_POS];                        // scatter variant: rank of a position inside its (warp, bucket) group
+        uint32_t cnt[SC_MAX_BUCKETS];
 };
 
 // valid positions of the word that starts at local position lx0, as a 32-bit mask (bit j = base j)
@@ -237,24 +212,17 @@ __device__ __forceinline__ uint32_t clip_mask(uint64_t lx0, uint64_t x_begin, ui
         return m;
 }
 
-// SCATTER = false: bucket histogram of the chunk (shared-memory reductions, no ranks needed).
-// SCATTER = true : the records.  Ranks come from a warp-level multisplit (__match_any_sync on the bucket
-// id, one text position per lane and step) -- shared-memory atomics that return a value serialise far
-// too much for this (measured: 10 ms per 250 M positions, all stalls on the shared-memory pipe).
-template<bool SCATTER>
-__global__ void __launch_bounds__(SC_THREADS) k_part(ScanParams P)
+// bucket histogram of the chunk (shared-memory reductions, then one global reduction per CTA and bucket)
+__global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
-        PartSmem & S = *reinterpret_cast<PartSmem *>(sc_smem);
+        HistSmem & S = *reinterpret_cast<HistSmem *>(sc_smem);
 
         uint64_t const first_tile = P.x_begin / SC_TILE_POS;
         uint64_t const end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
         uint32_t const bbits = P.bucket_bits;
         uint32_t const bsh = 64 - (bbits ? bbits : 1);
         uint32_t const bmask = bbits ? 0xFFFFFFFFu : 0u;
-        uint32_t const fsh = 64 - 2 * P.seedl;
-        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        uint32_t const lt = (1u << lane) - 1;
 
         if ( threadIdx.x == 0 )
         {
@@ -263,8 +231,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_part(ScanParams P)
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         S.cnt[threadIdx.x] = 0;
-        #pragma unroll
-        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
         __syncthreads();
 
         uint64_t tile_id = first_tile + blockIdx.x;
@@ -286,118 +252,47 @@ __global__ void __launch_bounds__(SC_THREADS) k_part(ScanParams P)
                 mbar_wait(&S.bar[buf], (it >> 1) & 1);
                 const uint64_t * tw = &S.tile[buf][SC_HALO];
                 uint64_t const tile_x0 = tile_id * SC_TILE_POS;
-
-                if ( ! SCATTER )
+                #pragma unroll
+                for ( int k = 0; k < SC_WPT; ++k )
                 {
-                        #pragma unroll
-                        for ( int k = 0; k < SC_WPT; ++k )
+                        uint32_t const wi = threadIdx.x + k * SC_THREADS;
+                        uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
+                        uint32_t m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
+                        while ( m )
                         {
-                                uint32_t const wi = threadIdx.x + k * SC_THREADS;
-                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
-                                uint32_t m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
-                                while ( m )
-                                {
-                                        uint32_t const j = __ffs(m) - 1;
-                                        m &= m - 1;
-                                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                        atomicAdd(&S.cnt[(uint32_t)(v >> bsh) & bmask], 1u);
-                                }
+                                uint32_t const j = __ffs(m) - 1;
+                                m &= m - 1;
+                                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                atomicAdd(&S.cnt[(uint32_t)(v >> bsh) & bmask], 1u);
                         }
                 }
-                else
-                {
-                        // (1) rank of every position inside its (warp, bucket) group
-                        #pragma unroll
-                        for ( int k = 0; k < SC_WPT; ++k )
-                        {
-                                uint32_t const wi = threadIdx.x + k * SC_THREADS;
-                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
-                                uint32_t const m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
-                                #pragma unroll 4
-                                for ( uint32_t j = 0; j < 32; ++j )
-                                {
-                                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                        bool const ok = (m >> j) & 1;
-                                        uint32_t const b = (uint32_t)(v >> bsh) & bmask;
-                                        uint32_t const peers = __match_any_sync(0xffffffffu, ok ? b : 0x100u);
-                                        uint32_t const below = __popc(peers & lt);
-                                        uint32_t pre = 0;
-                                        if ( ok ) pre = S.wcnt[wid][b];
-                                        __syncwarp();
-                                        if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers);
-                                        __syncwarp();
-                                        S.rank[wi * 32 + j] = (uint16_t)(pre + below);
-                                }
-                        }
-                        __syncthreads();
-                        // (2) bucket b (thread b): reserve the tile's run in the bucket, turn the per-warp counts into offsets
-                        {
-                                uint32_t tot = 0;
-                                #pragma unroll
-                                for ( int w = 0; w < SC_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
-                                uint32_t run = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
-                                #pragma unroll
-                                for ( int w = 0; w < SC_THREADS / 32; ++w )
-                                {
-                                        uint32_t const c = S.wcnt[w][threadIdx.x];
-                                        S.wcnt[w][threadIdx.x] = run;
-                                        run += c;
-                                }
-                        }
-                        __syncthreads();
-                        // (3) write the records
-                        #pragma unroll
-                        for ( int k = 0; k < SC_WPT; ++k )
-                        {
-                                uint32_t const wi = threadIdx.x + k * SC_THREADS;
-                                uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
-                                uint64_t const lx0 = tile_x0 + (uint64_t)wi * 32;
-                                uint32_t const m = clip_mask(lx0, P.x_begin, P.x_end);
-                                #pragma unroll 4
-                                for ( uint32_t j = 0; j < 32; ++j )
-                                {
-                                        if ( (m >> j) & 1 )
-                                        {
-                                                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                                uint32_t const b = (uint32_t)(v >> bsh) & bmask;
-                                                uint32_t const o = S.wcnt[wid][b] + S.rank[wi * 32 + j];
-                                                P.rec_win[o] = v >> fsh;
-                                                P.rec_pos[o] = (uint32_t)(lx0 + j - P.x_begin);
-                                        }
-                                }
-                        }
-                        __syncthreads();
-                        #pragma unroll
-                        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
-                }
-                __syncthreads();   // tile[buf], rank and the counters are free again
+                __syncthreads();   // tile[buf] is free again
         }
-        if ( ! SCATTER )
-        {
-                uint32_t const c = S.cnt[threadIdx.x];
-                if ( c ) atomicAdd(P.bucket_count + threadIdx.x, c);
-        }
+        uint32_t const c = S.cnt[threadIdx.x];
+        if ( c ) atomicAdd(P.bucket_count + threadIdx.x, c);
 }
 
 // ---- partition, scatter pass ---------------------------------------------------------------------
-// Tiles of 8192 positions.  Records are first laid out bucket by bucket in shared memory and then copied
-// out run by run, so every global store instruction writes whole consecutive records of one bucket:
-// scattering 8-byte records straight from the threads that produce them leaves ~200 KB of half-written
-// lines open per CTA, more than L2 holds for a full grid (measured: 2 GB of DRAM reads and 5 GB of writes
-// for 3 GB of records, 10 ms per 250 M positions).
-static const int PS_TILE_WORDS = SC_THREADS;                  // one text word per thread
-static const int PS_TILE_POS = PS_TILE_WORDS * 32;            // 8192
-static const int PS_SMEM_WORDS = PS_TILE_WORDS + 2 * SC_HALO; // 260 words = 2080 bytes
+// Tiles of 4096 positions (half a text word per thread).  Records are first laid out bucket by bucket in
+// shared memory and then copied out run by run, so every global store instruction writes whole
+// consecutive records of one bucket: scattering records straight from the threads that produce them
+// leaves ~200 KB of half-written lines open per CTA, more than L2 holds for a full grid (measured: 2 GB
+// of DRAM reads and 5 GB of writes for 3 GB of records, 10 ms per 250 M positions).  Ranks come from a
+// warp-level multisplit (__match_any_sync on the bucket id): shared-memory atomics that return a value
+// serialise far too much for this.
+static const int PS_PPT = 16;                                 // positions per thread
+static const int PS_TILE_POS = SC_THREADS * PS_PPT;           // 4096
+static const int PS_TILE_WORDS = PS_TILE_POS / 32;            // 128
+static const int PS_SMEM_WORDS = PS_TILE_WORDS + 2 * SC_HALO; // 132 words = 1056 bytes
 
 struct ScatterSmem
 {
-        uint64_t stage_win[PS_TILE_POS];
+        uint4 stage[PS_TILE_POS];                          // record, position field relative to the tile
         uint64_t tile[2][PS_SMEM_WORDS];
         uint64_t bar[2];
         uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];    // per-warp counts, then running slots
         uint32_t loc[SC_MAX_BUCKETS + 1];                  // first staging slot of a bucket
         uint32_t base[SC_MAX_BUCKETS];                     // first global record of the tile's run in a bucket
-        uint16_t stage_pos[PS_TILE_POS];
         uint8_t stage_b[PS_TILE_POS];
 };
 
@@ -443,16 +338,16 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 }
                 mbar_wait(&S.bar[buf], (it >> 1) & 1);
                 uint64_t const tile_x0 = tile_id * PS_TILE_POS;
-                uint32_t const wi = threadIdx.x;
-                uint64_t const w0 = S.tile[buf][SC_HALO + wi], w1 = S.tile[buf][SC_HALO + wi + 1];
-                uint32_t const m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
+                uint32_t const wi = threadIdx.x >> 1, j0 = (threadIdx.x & 1) * PS_PPT;
+                uint64_t const wm = S.tile[buf][SC_HALO + wi - 1], w0 = S.tile[buf][SC_HALO + wi], w1 = S.tile[buf][SC_HALO + wi + 1];
+                uint32_t const m = (clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end) >> j0) & 0xFFFFu;
 
                 // (1) per-warp bucket counts (reductions without return value)
                 {
                         uint32_t mm = m;
                         while ( mm )
                         {
-                                uint32_t const j = __ffs(mm) - 1;
+                                uint32_t const j = j0 + __ffs(mm) - 1;
                                 mm &= mm - 1;
                                 uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
                                 atomicAdd(&S.wcnt[wid][(uint32_t)(v >> bsh) & bmask], 1u);
@@ -481,10 +376,11 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 __syncthreads();
                 // (3) warp multisplit: one position per lane and step; the group leader advances the warp's slot counter
                 #pragma unroll 4
-                for ( uint32_t j = 0; j < 32; ++j )
+                for ( uint32_t jj = 0; jj < PS_PPT; ++jj )
                 {
+                        uint32_t const j = j0 + jj;
                         uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                        bool const ok = (m >> j) & 1;
+                        bool const ok = (m >> jj) & 1;
                         uint32_t const b = (uint32_t)(v >> bsh) & bmask;
                         uint32_t const peers = __match_any_sync(0xffffffffu, ok ? b : 0x100u);
                         uint32_t const below = __popc(peers & lt);
@@ -496,8 +392,9 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                         if ( ok )
                         {
                                 uint32_t const slot = pre + below;
-                                S.stage_win[slot] = v >> fsh;
-                                S.stage_pos[slot] = (uint16_t)(wi * 32 + j);
+                                uint64_t const win = v >> fsh;
+                                uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;       // the 32 bases that end in front of the window
+                                S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, wi * 32 + j);
                                 S.stage_b[slot] = (uint8_t)b;
                         }
                 }
@@ -505,13 +402,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 // (4) copy out: consecutive threads write consecutive records of a bucket run
                 {
                         uint32_t const n = S.loc[SC_MAX_BUCKETS];
-                        uint32_t const pos0 = (uint32_t)(tile_x0 - P.x_begin);      // may wrap for the clipped first tile; offsets below are relative
+                        uint32_t const pos0 = (uint32_t)(tile_x0 - P.x_begin);      // may wrap for the clipped first tile; the sums below do not
                         for ( uint32_t i = threadIdx.x; i < n; i += SC_THREADS )
                         {
                                 uint32_t const b = S.stage_b[i];
-                                uint32_t const o = S.base[b] + (i - S.loc[b]);
-                                P.rec_win[o] = S.stage_win[i];
-                                P.rec_pos[o] = pos0 + S.stage_pos[i];
+                                uint4 r = S.stage[i];
+                                r.w += pos0;
+                                P.recs[S.base[b] + (i - S.loc[b])] = r;
                         }
                 }
                 __syncthreads();
@@ -521,39 +418,43 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
         }
 }
 
-// one block: bucket starts, unit directory, cursors
+// one block: bucket starts (every bucket padded to whole grabs), cursors, sentinel records in the padding
 __global__ void __launch_bounds__(SC_MAX_BUCKETS) k_part_offsets(ScanParams P)
 {
-        __shared__ uint32_t sc[SC_MAX_BUCKETS], su[SC_MAX_BUCKETS];
+        __shared__ uint32_t sc[SC_MAX_BUCKETS], st[SC_MAX_BUCKETS + 1];
         uint32_t const c = P.bucket_count[threadIdx.x];
         sc[threadIdx.x] = c;
-        su[threadIdx.x] = (c + SC_UNIT - 1) / SC_UNIT;
         __syncthreads();
         if ( threadIdx.x == 0 )
         {
-                uint32_t a = 0, u = 0;
+                uint32_t a = 0;
                 for ( int b = 0; b < SC_MAX_BUCKETS; ++b )
                 {
-                        P.bucket_start[b] = a; P.unit_start[b] = u;
-                        a += sc[b]; u += su[b];
+                        st[b] = a;
+                        a += ((sc[b] + SC_UNIT - 1) / SC_UNIT) * SC_UNIT;
                 }
-                P.bucket_start[SC_MAX_BUCKETS] = a; P.unit_start[SC_MAX_BUCKETS] = u;
+                st[SC_MAX_BUCKETS] = a;
                 *P.unit_counter = 0;
         }
+        __syncthreads();
+        P.bucket_start[threadIdx.x] = st[threadIdx.x];
+        if ( threadIdx.x == 0 ) P.bucket_start[SC_MAX_BUCKETS] = st[SC_MAX_BUCKETS];
         P.bucket_cursor[threadIdx.x * SC_CURSOR_STRIDE] = 0;
+        for ( uint32_t r = st[threadIdx.x] + c; r < st[threadIdx.x + 1]; ++r )
+                P.recs[r] = make_uint4(0, 0, 0, SC_POS_NONE);
 }
 
 // ---- probe -------------------------------------------------------------------------------------
 
-struct ItemA { uint64_t win; uint32_t pos; uint32_t table; };          // a set slot bit
+struct ItemA { uint64_t win; uint32_t before; uint32_t post; };      // a set slot bit: window, bases in front, position | table << 30
 struct ItemB { uint64_t lp; uint32_t id; uint32_t seedk; };           // an entry that passed the seed test
 
 struct ProbeSmem
 {
-        ItemA qa[SC_QA_CAP];
-        ItemB qb[SC_QB_CAP];
-        uint32_t ustart[SC_MAX_BUCKETS + 1];
-        uint32_t qan, qbn, unit[2];
+        ItemA qa[SC_THREADS / 32][SC_QA_CAP];
+        ItemB qb[SC_THREADS / 32][SC_QB_CAP];
+        uint32_t qan[SC_THREADS / 32], qbn[SC_THREADS / 32];
+        uint32_t grab[2];
 };
 
 // stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
@@ -607,9 +508,9 @@ __device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t
 // stage A: a set slot bit -> rank inside the sector -> entry chain; per entry the seed test
 // (match.hpp:386-388) and the canonical-list rule: of the up to six lists that reach a position,
 // only the pair made of the two LOWEST exact fragments reports it (replaces unifyMatches' dedup)
-__device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, ProbeSmem & S, unsigned long long * lstats, uint64_t pol)
+__device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, ItemB * qb, uint32_t * qbn, unsigned long long * lstats, uint64_t pol)
 {
-        int const table = (int)it.table;
+        int const table = (int)(it.post >> 30);
         uint32_t const F = P.F;
         uint64_t const fm = (1ULL << (2*F)) - 1;
         uint64_t const m0 = (it.win >> (6*F)) & fm;
@@ -627,7 +528,7 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
                 if ( w < wi ) rank += __popc(wv[1+w]);
                 else if ( w == wi ) rank += __popc(wv[1+w] & ((1u << (slot & 31)) - 1));
         }
-        uint64_t const lx = P.x_begin + it.pos;
+        uint64_t const lx = P.x_begin + (it.post & 0x3FFFFFFFu);
         uint32_t e = rank;
         while ( e != ENTRY_NONE )
         {
@@ -639,7 +540,10 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
                 uint64_t const lp = lx - (uint64_t)t * F;                      // seed window start (local)
                 if ( lp < P.win_begin || lp >= P.win_end ) continue;
                 lstats[0] += 1;
-                uint64_t const win = t ? text_word(P.text, lp, P.seedl) : it.win;
+                // the seed window starts t fragments in front of the probed position: its first t*F bases come
+                // from the record's "before" word, the rest from the window word
+                uint32_t const tb = 2 * t * F;
+                uint64_t const win = t ? ((((uint64_t)it.before & ((1ULL << tb) - 1)) << (2*P.seedl - tb)) | (it.win >> tb)) : it.win;
                 uint64_t x = eseed ^ win;
                 x = ((x >> 1) | x) & 0x5555555555555555ULL;
                 uint32_t const seedk = (uint32_t)__popcll(x);
@@ -653,60 +557,53 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
                 }
                 if ( first != (int)t || second != pair_second(table, (int)t) ) continue;
                 lstats[1] += 1;
-                uint32_t const o = atomicAdd(&S.qbn, 1u);
+                uint32_t const o = atomicAdd(qbn, 1u);
                 if ( o < SC_QB_CAP )
                 {
                         ItemB ib; ib.lp = lp; ib.id = id; ib.seedk = seedk;
-                        S.qb[o] = ib;
+                        qb[o] = ib;
                 }
                 else
                         verify_and_report(P, lp, id, lstats);          // queue full: handle it here
         }
 }
 
-__device__ __forceinline__ void drain_b(ScanParams const & P, ProbeSmem & S, unsigned long long * lstats)
+// the warp's stage B queue
+__device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, uint32_t * qbn, int lane, unsigned long long * lstats)
 {
-        uint32_t const n = min(S.qbn, (uint32_t)SC_QB_CAP);
-        for ( uint32_t i = threadIdx.x; i < n; i += SC_THREADS )
+        uint32_t const n = min(*qbn, (uint32_t)SC_QB_CAP);
+        __syncwarp();
+        for ( uint32_t i = lane; i < n; i += 32 )
         {
-                ItemB const ib = S.qb[i];
+                ItemB const ib = qb[i];
                 verify_and_report(P, ib.lp, ib.id, lstats);
         }
-        __syncthreads();
-        if ( threadIdx.x == 0 ) S.qbn = 0;
-        __syncthreads();
+        __syncwarp();
+        if ( lane == 0 ) *qbn = 0;
+        __syncwarp();
 }
 
-__device__ __forceinline__ void drain_a(ScanParams const & P, ProbeSmem & S, unsigned long long * lstats, bool flush, uint64_t pol)
+// the warp's stage A queue: full rounds of 32 from the top of the queue; with `flush` also the rest
+__device__ __forceinline__ void drain_a_warp(ScanParams const & P, ItemA * qa, uint32_t * qan, ItemB * qb, uint32_t * qbn, int lane,
+                                             unsigned long long * lstats, bool flush, uint64_t pol)
 {
-        uint32_t const n = S.qan;
-        for ( uint32_t i0 = 0; i0 < n; i0 += SC_THREADS )
+        uint32_t n = *qan;
+        __syncwarp();
+        while ( n >= 32 || (flush && n) )
         {
-                uint32_t const i = i0 + threadIdx.x;
-                if ( i < n )
-                        follow_item(P, S.qa[i], S, lstats, pol);
-                __syncthreads();
-                if ( S.qbn >= SC_QB_DRAIN )
-                        drain_b(P, S, lstats);
+                uint32_t const take = n >= 32 ? 32u : n;
+                if ( (uint32_t)lane < take )
+                        follow_item(P, qa[n - take + lane], qb, qbn, lstats, pol);
+                __syncwarp();
+                n -= take;
+                if ( *qbn >= 32 )
+                        drain_b_warp(P, qb, qbn, lane, lstats);
         }
-        __syncthreads();
-        if ( threadIdx.x == 0 ) S.qan = 0;
-        __syncthreads();
-        if ( flush && S.qbn )
-                drain_b(P, S, lstats);
-}
-
-__device__ __forceinline__ void locate_unit(ScanParams const & P, const uint32_t * ustart, uint32_t u, uint32_t & r0, uint32_t & r1)
-{
-        // bucket of the unit: last b with ustart[b] <= u
-        uint32_t lo = 0, hi = SC_MAX_BUCKETS;
-        while ( lo < hi )
-        {
-                uint32_t const mid = (lo + hi + 1) >> 1;
-                if ( ustart[mid] <= u ) lo = mid; else hi = mid - 1;
-        }
-        r0 = __ldg(P.bucket_start + lo) + (u - ustart[lo]) * SC_UNIT;
-        r1 = min(r0 + (uint32_t)SC_UNIT, __ldg(P.bucket_start + lo + 1));
+        __syncwarp();
+        if ( lane == 0 ) *qan = n;
+        __syncwarp();
+        if ( flush && *qbn )
+                drain_b_warp(P, qb, qbn, lane, lstats);
 }
 
 __global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
@@ -714,132 +611,114 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
         extern __shared__ __align__(128) unsigned char sc_smem[];
         ProbeSmem & S = *reinterpret_cast<ProbeSmem *>(sc_smem);
         unsigned long long lstats[3] = {0, 0, 0};
-        int const lane = threadIdx.x & 31;
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         uint64_t const pol = policy_evict_last();
+        ItemA * qa = S.qa[wid];
+        ItemB * qb = S.qb[wid];
+        uint32_t * qan = &S.qan[wid], * qbn = &S.qbn[wid];
 
-        for ( int i = threadIdx.x; i <= SC_MAX_BUCKETS; i += SC_THREADS )
-                S.ustart[i] = P.unit_start[i];
-        if ( threadIdx.x == 0 ) { S.qan = 0; S.qbn = 0; }
-        __syncthreads();
-        uint32_t const nunits = S.ustart[SC_MAX_BUCKETS];
+        if ( lane == 0 ) { *qan = 0; *qbn = 0; }
+        uint32_t const total = P.bucket_start[SC_MAX_BUCKETS];           // padded to whole grabs
+        uint32_t const ngrabs = total / SC_UNIT;
 
         uint32_t const F = P.F;
         uint32_t const kb = P.keybits;
         uint64_t const fm = (1ULL << (2*F)) - 1;
         bool const nlA = P.tab[0].nlists != 0, nlB = P.tab[1].nlists != 0, nlC = P.tab[2].nlists != 0;
 
-        // units are handed out in bucket order by a global counter, so all CTAs work on the same bucket (slice)
-        // at any time; unit ids are drawn two iterations ahead and the records of the next unit are requested
-        // before the current one is probed
+        // grabs are handed out in bucket order by a global counter, so all CTAs work on the same bucket (slice)
+        // at any time; grab ids are drawn two iterations ahead
         if ( threadIdx.x == 0 )
         {
-                S.unit[0] = atomicAdd(P.unit_counter, 1u);
-                S.unit[1] = atomicAdd(P.unit_counter, 1u);
+                S.grab[0] = atomicAdd(P.unit_counter, 1u);
+                S.grab[1] = atomicAdd(P.unit_counter, 1u);
         }
         __syncthreads();
-        uint32_t r0n = 0, r1n = 0;
-        uint64_t win_next[SC_RPT];
+        for ( uint32_t iter = 0; ; ++iter )
         {
-                uint32_t const u0 = S.unit[0];
-                if ( u0 < nunits )
-                {
-                        locate_unit(P, S.ustart, u0, r0n, r1n);
-                        #pragma unroll
-                        for ( int k = 0; k < SC_RPT; ++k )
-                        {
-                                uint32_t const r = r0n + k * SC_THREADS + threadIdx.x;
-                                win_next[k] = (r < r1n) ? __ldcs(P.rec_win + r) : 0;
-                        }
-                }
-        }
-        uint32_t u = S.unit[0];
-        __syncthreads();
-        for ( uint32_t iter = 0; u < nunits; ++iter )
-        {
-                uint32_t const r0 = r0n, r1 = r1n;
-                uint64_t win[SC_RPT];
-                #pragma unroll
-                for ( int k = 0; k < SC_RPT; ++k ) win[k] = win_next[k];
-                uint32_t const unext = S.unit[(iter + 1) & 1];
-                if ( unext < nunits )
-                {
-                        locate_unit(P, S.ustart, unext, r0n, r1n);
-                        #pragma unroll
-                        for ( int k = 0; k < SC_RPT; ++k )
-                        {
-                                uint32_t const r = r0n + k * SC_THREADS + threadIdx.x;
-                                win_next[k] = (r < r1n) ? __ldcs(P.rec_win + r) : 0;
-                        }
-                }
-                if ( threadIdx.x == 0 ) S.unit[iter & 1] = atomicAdd(P.unit_counter, 1u);      // for iteration iter+2
-                u = unext;
+                uint32_t const g = S.grab[iter & 1];
+                __syncthreads();
+                if ( g >= ngrabs ) break;
+                if ( threadIdx.x == 0 ) S.grab[iter & 1] = atomicAdd(P.unit_counter, 1u);      // for iteration iter+2
 
-                uint32_t v[SC_RPT][3], bit[SC_RPT][3];
+                const uint4 * rp = P.recs + (uint64_t)g * SC_UNIT + wid * SC_WARP_RECS + lane;
+                uint4 nxt[SC_RPT];
                 #pragma unroll
-                for ( int k = 0; k < SC_RPT; ++k )
+                for ( int k = 0; k < SC_RPT; ++k ) nxt[k] = __ldcs(rp + k * 32);
+                #pragma unroll 1
+                for ( int step = 0; step < SC_WARP_RECS / (32 * SC_RPT); ++step )
                 {
-                        uint32_t const r = r0 + k * SC_THREADS + threadIdx.x;
-                        bool const ok = r < r1;
-                        uint64_t const m0 = (win[k] >> (6*F)) & fm, m1 = (win[k] >> (4*F)) & fm, m2 = (win[k] >> (2*F)) & fm, m3 = win[k] & fm;
-                        v[k][0] = v[k][1] = v[k][2] = 0; bit[k][0] = bit[k][1] = bit[k][2] = 0;
-                        if ( ok && nlA )
-                        {
-                                uint32_t const h = slot_of((m0 << (2*F)) | m1, kb, P.tab[0].hb);
-                                uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][0] = rr & 31;
-                                v[k][0] = ld_hot_u32(P.tab[0].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
-                        }
-                        if ( ok && nlB )
-                        {
-                                uint32_t const h = slot_of((m0 << (2*F)) | m2, kb, P.tab[1].hb);
-                                uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][1] = rr & 31;
-                                v[k][1] = ld_hot_u32(P.tab[1].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
-                        }
-                        if ( ok && nlC )
-                        {
-                                uint32_t const h = slot_of((m0 << (2*F)) | m3, kb, P.tab[2].hb);
-                                uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][2] = rr & 31;
-                                v[k][2] = ld_hot_u32(P.tab[2].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
-                        }
-                }
-                // compact the set slot bits into the stage A queue
-                uint32_t cand = 0;
-                #pragma unroll
-                for ( int k = 0; k < SC_RPT; ++k )
+                        uint4 cur[SC_RPT];
                         #pragma unroll
-                        for ( int t = 0; t < 3; ++t )
-                                cand |= ((v[k][t] >> bit[k][t]) & 1u) << (k * 3 + t);
-                uint32_t const c = __popc(cand);
-                uint32_t const incl = warp_incl_scan(c, lane);
-                uint32_t base = 0;
-                if ( lane == 31 && incl ) base = atomicAdd(&S.qan, incl);
-                base = __shfl_sync(0xffffffffu, base, 31);
-                uint32_t o = base + incl - c;
-                #pragma unroll
-                for ( int k = 0; k < SC_RPT; ++k )
-                {
-                        if ( (cand >> (k * 3)) & 7u )
+                        for ( int k = 0; k < SC_RPT; ++k ) cur[k] = nxt[k];
+                        if ( step + 1 < SC_WARP_RECS / (32 * SC_RPT) )
                         {
-                                uint32_t const r = r0 + k * SC_THREADS + threadIdx.x;
-                                uint32_t const pos = __ldcs(P.rec_pos + r);
+                                #pragma unroll
+                                for ( int k = 0; k < SC_RPT; ++k ) nxt[k] = __ldcs(rp + (step + 1) * 32 * SC_RPT + k * 32);
+                        }
+                        uint32_t v[SC_RPT][3], bit[SC_RPT][3];
+                        #pragma unroll
+                        for ( int k = 0; k < SC_RPT; ++k )
+                        {
+                                bool const ok = cur[k].w != SC_POS_NONE;
+                                uint64_t const win = ((uint64_t)cur[k].y << 32) | cur[k].x;
+                                uint64_t const m0 = (win >> (6*F)) & fm, m1 = (win >> (4*F)) & fm, m2 = (win >> (2*F)) & fm, m3 = win & fm;
+                                v[k][0] = v[k][1] = v[k][2] = 0; bit[k][0] = bit[k][1] = bit[k][2] = 0;
+                                if ( ok && nlA )
+                                {
+                                        uint32_t const h = slot_of((m0 << (2*F)) | m1, kb, P.tab[0].hb);
+                                        uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][0] = rr & 31;
+                                        v[k][0] = ld_hot_u32(P.tab[0].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
+                                }
+                                if ( ok && nlB )
+                                {
+                                        uint32_t const h = slot_of((m0 << (2*F)) | m2, kb, P.tab[1].hb);
+                                        uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][1] = rr & 31;
+                                        v[k][1] = ld_hot_u32(P.tab[1].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
+                                }
+                                if ( ok && nlC )
+                                {
+                                        uint32_t const h = slot_of((m0 << (2*F)) | m3, kb, P.tab[2].hb);
+                                        uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][2] = rr & 31;
+                                        v[k][2] = ld_hot_u32(P.tab[2].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
+                                }
+                        }
+                        // compact the set slot bits into the warp's stage A queue
+                        uint32_t cand = 0;
+                        #pragma unroll
+                        for ( int k = 0; k < SC_RPT; ++k )
                                 #pragma unroll
                                 for ( int t = 0; t < 3; ++t )
-                                        if ( (cand >> (k * 3 + t)) & 1u )
-                                        {
-                                                ItemA ia; ia.win = win[k]; ia.pos = pos; ia.table = (uint32_t)t;
-                                                S.qa[o++] = ia;
-                                        }
+                                        cand |= ((v[k][t] >> bit[k][t]) & 1u) << (k * 3 + t);
+                        if ( __any_sync(0xffffffffu, cand != 0) )
+                        {
+                                uint32_t const c = __popc(cand);
+                                uint32_t const incl = warp_incl_scan(c, lane);
+                                uint32_t const n0 = *qan;
+                                __syncwarp();
+                                uint32_t o = n0 + incl - c;
+                                #pragma unroll
+                                for ( int k = 0; k < SC_RPT; ++k )
+                                        #pragma unroll
+                                        for ( int t = 0; t < 3; ++t )
+                                                if ( (cand >> (k * 3 + t)) & 1u )
+                                                {
+                                                        ItemA ia; ia.win = ((uint64_t)cur[k].y << 32) | cur[k].x; ia.before = cur[k].z; ia.post = cur[k].w | ((uint32_t)t << 30);
+                                                        qa[o++] = ia;
+                                                }
+                                if ( lane == 31 ) *qan = n0 + incl;
+                                __syncwarp();
+                                if ( P.debug_flags & 1 )
+                                {
+                                        if ( lane == 0 ) { lstats[0] += *qan; *qan = 0; }
+                                        __syncwarp();
+                                }
+                                else if ( n0 + __shfl_sync(0xffffffffu, incl, 31) >= 32 )
+                                        drain_a_warp(P, qa, qan, qb, qbn, lane, lstats, false, pol);
                         }
                 }
-                __syncthreads();
-                if ( P.debug_flags & 1 )
-                {
-                        if ( threadIdx.x == 0 ) { lstats[0] += S.qan; S.qan = 0; }
-                        __syncthreads();
-                }
-                else if ( S.qan >= SC_QA_DRAIN )
-                        drain_a(P, S, lstats, false, pol);
         }
-        drain_a(P, S, lstats, true, pol);
+        drain_a_warp(P, qa, qan, qb, qbn, lane, lstats, true, pol);
 
         // statistics: one atomic per warp and counter
         #pragma unroll
