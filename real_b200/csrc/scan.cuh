@@ -19,8 +19,8 @@
 //   k_part_offsets  bucket starts (padded to whole work units) + sentinel records in the padding
 //   k_part_scatter  TMA-staged text tiles -> 16-byte records {window word, the 16 bases in front of it,
 //                   position} grouped by bucket (staged in shared memory, written run by run)
-//   k_bucket_probe  CTAs pull 2048-record grabs in bucket order, every warp owns 256 of them and walks
-//                   them 64 at a time: 6 independent 4-byte probes per lane; set slot bits are compacted
+//   k_bucket_probe  warps pull 512-record grabs in bucket order and walk them 64 records at a time:
+//                   6 independent 4-byte probes per lane; set slot bits are compacted
 //                   into the warp's shared-memory queue (stage A: rank -> entry chain -> seed test ->
 //                   canonical-list rule), the survivors into a second queue (stage B: record / wildcard
 //                   predicates, whole-read XOR+popcount distance, report), so that each stage runs with
@@ -41,8 +41,7 @@ static const int SC_HALO = 2;                                // words of halo in
 static const int SC_SMEM_WORDS = SC_TILE_WORDS + 2 * SC_HALO; // 516 words = 4128 bytes (multiple of 16)
 static const int SC_MAX_BUCKETS = 256;
 static const int SC_CURSOR_STRIDE = 32;                      // u32 per bucket cursor: one 128-byte line each, so the global atomics spread over the L2 slices
-static const int SC_UNIT = 2048;                             // records per grab of the probe kernel (one global atomic)
-static const int SC_WARP_RECS = SC_UNIT / (SC_THREADS / 32); // 256 records per warp and grab
+static const int SC_UNIT = 512;                              // records per grab of the probe kernel (one global atomic per warp and grab)
 static const int SC_RPT = 2;                                 // records per lane and step
 static const int SC_QA_CAP = 256;                            // per-warp stage A queue (set slot bits): drained from 32 up, a step adds <= 192
 static const int SC_QB_CAP = 64;                             // per-warp stage B queue (seed test passed)
@@ -374,28 +373,39 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                         }
                 }
                 __syncthreads();
-                // (3) warp multisplit: one position per lane and step; the group leader advances the warp's slot counter
-                #pragma unroll 4
-                for ( uint32_t jj = 0; jj < PS_PPT; ++jj )
+                // (3) warp multisplit: one position per lane and step; the group leader advances the warp's slot counter.
+                // The matches of four steps are issued together: their result latency is what this phase waits for.
+                #pragma unroll 1
+                for ( uint32_t jb = 0; jb < PS_PPT; jb += 4 )
                 {
-                        uint32_t const j = j0 + jj;
-                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                        bool const ok = (m >> jj) & 1;
-                        uint32_t const b = (uint32_t)(v >> bsh) & bmask;
-                        uint32_t const peers = __match_any_sync(0xffffffffu, ok ? b : 0x100u);
-                        uint32_t const below = __popc(peers & lt);
-                        uint32_t pre = 0;
-                        if ( ok ) pre = S.wcnt[wid][b];
-                        __syncwarp();
-                        if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers);
-                        __syncwarp();
-                        if ( ok )
+                        uint64_t v[4]; uint32_t b[4], peers[4];
+                        #pragma unroll
+                        for ( uint32_t u = 0; u < 4; ++u )
                         {
-                                uint32_t const slot = pre + below;
-                                uint64_t const win = v >> fsh;
-                                uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;       // the 32 bases that end in front of the window
-                                S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, wi * 32 + j);
-                                S.stage_b[slot] = (uint8_t)b;
+                                uint32_t const j = j0 + jb + u;
+                                v[u] = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                b[u] = (uint32_t)(v[u] >> bsh) & bmask;
+                                peers[u] = __match_any_sync(0xffffffffu, ((m >> (jb + u)) & 1) ? b[u] : 0x100u);
+                        }
+                        #pragma unroll
+                        for ( uint32_t u = 0; u < 4; ++u )
+                        {
+                                uint32_t const j = j0 + jb + u;
+                                bool const ok = (m >> (jb + u)) & 1;
+                                uint32_t const below = __popc(peers[u] & lt);
+                                uint32_t pre = 0;
+                                if ( ok ) pre = S.wcnt[wid][b[u]];
+                                __syncwarp();
+                                if ( ok && below == 0 ) S.wcnt[wid][b[u]] = pre + __popc(peers[u]);
+                                __syncwarp();
+                                if ( ok )
+                                {
+                                        uint32_t const slot = pre + below;
+                                        uint64_t const win = v[u] >> fsh;
+                                        uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;       // the 32 bases that end in front of the window
+                                        S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, wi * 32 + j);
+                                        S.stage_b[slot] = (uint8_t)b[u];
+                                }
                         }
                 }
                 __syncthreads();
@@ -454,7 +464,6 @@ struct ProbeSmem
         ItemA qa[SC_THREADS / 32][SC_QA_CAP];
         ItemB qb[SC_THREADS / 32][SC_QB_CAP];
         uint32_t qan[SC_THREADS / 32], qbn[SC_THREADS / 32];
-        uint32_t grab[2];
 };
 
 // stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
@@ -618,6 +627,7 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
         uint32_t * qan = &S.qan[wid], * qbn = &S.qbn[wid];
 
         if ( lane == 0 ) { *qan = 0; *qbn = 0; }
+        __syncwarp();
         uint32_t const total = P.bucket_start[SC_MAX_BUCKETS];           // padded to whole grabs
         uint32_t const ngrabs = total / SC_UNIT;
 
@@ -626,32 +636,28 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
         uint64_t const fm = (1ULL << (2*F)) - 1;
         bool const nlA = P.tab[0].nlists != 0, nlB = P.tab[1].nlists != 0, nlC = P.tab[2].nlists != 0;
 
-        // grabs are handed out in bucket order by a global counter, so all CTAs work on the same bucket (slice)
-        // at any time; grab ids are drawn two iterations ahead
-        if ( threadIdx.x == 0 )
+        // grabs of 512 records are handed out in bucket order by a global counter, one per warp at a time, so all
+        // warps of the grid work on the same bucket (slice) at any time; a warp draws its next grab before it
+        // starts on the current one, and there is no block-wide barrier anywhere in the loop
+        uint32_t g = 0;
+        if ( lane == 0 ) g = atomicAdd(P.unit_counter, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        while ( g < ngrabs )
         {
-                S.grab[0] = atomicAdd(P.unit_counter, 1u);
-                S.grab[1] = atomicAdd(P.unit_counter, 1u);
-        }
-        __syncthreads();
-        for ( uint32_t iter = 0; ; ++iter )
-        {
-                uint32_t const g = S.grab[iter & 1];
-                __syncthreads();
-                if ( g >= ngrabs ) break;
-                if ( threadIdx.x == 0 ) S.grab[iter & 1] = atomicAdd(P.unit_counter, 1u);      // for iteration iter+2
+                uint32_t gn = 0;
+                if ( lane == 0 ) gn = atomicAdd(P.unit_counter, 1u);
 
-                const uint4 * rp = P.recs + (uint64_t)g * SC_UNIT + wid * SC_WARP_RECS + lane;
+                const uint4 * rp = P.recs + (uint64_t)g * SC_UNIT + lane;
                 uint4 nxt[SC_RPT];
                 #pragma unroll
                 for ( int k = 0; k < SC_RPT; ++k ) nxt[k] = __ldcs(rp + k * 32);
                 #pragma unroll 1
-                for ( int step = 0; step < SC_WARP_RECS / (32 * SC_RPT); ++step )
+                for ( int step = 0; step < SC_UNIT / (32 * SC_RPT); ++step )
                 {
                         uint4 cur[SC_RPT];
                         #pragma unroll
                         for ( int k = 0; k < SC_RPT; ++k ) cur[k] = nxt[k];
-                        if ( step + 1 < SC_WARP_RECS / (32 * SC_RPT) )
+                        if ( step + 1 < SC_UNIT / (32 * SC_RPT) )
                         {
                                 #pragma unroll
                                 for ( int k = 0; k < SC_RPT; ++k ) nxt[k] = __ldcs(rp + (step + 1) * 32 * SC_RPT + k * 32);
@@ -717,6 +723,7 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
                                         drain_a_warp(P, qa, qan, qb, qbn, lane, lstats, false, pol);
                         }
                 }
+                g = __shfl_sync(0xffffffffu, gn, 0);
         }
         drain_a_warp(P, qa, qan, qb, qbn, lane, lstats, true, pol);
 
