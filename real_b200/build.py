@@ -49,6 +49,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+BIN_DIR = os.path.join(HERE, "bin")
+HOST_BIN = os.path.join(BIN_DIR, "real")
+HOST_DUMP = os.path.join(BIN_DIR, "real_host_dump")
+
+
+def build_host(force: bool = False) -> str:
+    """Compiles the C++ host driver (the `real` command line on the C ABI) and its test helper."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("real_host.cpp", "real_host.hpp", "real_main.cpp", "real_host_dump.cpp")]
+    newest = max(os.path.getmtime(f) for f in srcs + [os.path.join(HERE, "..", "include", "real_gpu.h")])
+    if not force and all(os.path.exists(b) and os.path.getmtime(b) >= newest for b in (HOST_BIN, HOST_DUMP)) and os.path.getmtime(HOST_BIN) >= os.path.getmtime(LIB):
+        return HOST_BIN
+    os.makedirs(BIN_DIR, exist_ok=True)
+    gxx = shutil.which("g++") or "g++"
+    common = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra"]
+    subprocess.check_call(common + ["-o", HOST_BIN, os.path.join(HOST_DIR, "real_main.cpp"), os.path.join(HOST_DIR, "real_host.cpp"),
+                                    "-L" + HERE, "-lreal_gpu", "-Wl,-rpath,$ORIGIN/.."])
+    subprocess.check_call(common + ["-o", HOST_DUMP, os.path.join(HOST_DIR, "real_host_dump.cpp"), os.path.join(HOST_DIR, "real_host.cpp"),
+                                    "-L" + HERE, "-lreal_gpu", "-Wl,-rpath,$ORIGIN/.."])
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     build(force=True, verbose=True)
     print(LIB)
+    print(build_host(force=True))

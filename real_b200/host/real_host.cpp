@@ -1,0 +1,686 @@
+// See real_host.hpp.  Host C++ above the C ABI (include/real_gpu.h).
+#include "real_host.hpp"
+#include "../../include/real_gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+#include <dirent.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace realhost
+{
+
+// ---------------------------------------------------------------------------------------------
+// RealOptions (RealOptions.cpp:85-466)
+// ---------------------------------------------------------------------------------------------
+
+static double const DFLT_SIMILARITY = 0.995, DFLT_GC = 0.41, DFLT_TRANS = 0.71, DFLT_ERR = 0.00, DFLT_GCMUT_BIAS = 2.0;   // Scoring.cpp:204-208
+static double const default_fracmem = 0.75;
+
+void RealOptions::printHelp() const
+{
+        std::cerr << "Options:" << std::endl;
+        std::cerr << "-t <textfilename>" << std::endl;
+        std::cerr << "-p <patternfilename>" << std::endl;
+        std::cerr << "-o <outputfilename>" << std::endl;
+        std::cerr << "-s <maximum number of errors in seed, default=" << default_seedkmax << ">" << std::endl;
+        std::cerr << "-e <total maximum number of errors, default=" << default_totalkmax << ">" << std::endl;
+        std::cerr << "-l <length of seed, default=" << default_seedl << ">" << std::endl;
+        std::cerr << "-u <search for unique match, default=" << default_match_unique << ">" << std::endl;
+        std::cerr << "-f <fraction of physical memory to use, default=" << default_fracmem << ">" << std::endl;
+        std::cerr << "-q <use quality scores, default=" << default_scores << ">" << std::endl;
+        std::cerr << "-Q <offset for quality scores, default=autodetect>" << std::endl;
+        std::cerr << "-R <rewrite pattern file, default=" << default_rewritepatterns << ">" << std::endl;
+        std::cerr << "-T <number of matching threads, accepted for compatibility>" << std::endl;
+        std::cerr << "-similarity <sequence similarity, default=" << DFLT_SIMILARITY << ">" << std::endl;
+        std::cerr << "-trans <transitions fraction of mutations, default=" << DFLT_TRANS << ">" << std::endl;
+        std::cerr << "-gc <composition bias, default=" << DFLT_GC << ">" << std::endl;
+        std::cerr << "-gcmut_bias <mutability bias of G&C, default=" << DFLT_GCMUT_BIAS << ">" << std::endl;
+        std::cerr << "-filter_level <filtering level for equal hits 0-4, default=" << default_filter_level << ">" << std::endl;
+}
+
+bool RealOptions::isFastQ(std::string const & filename)
+{
+        std::ifstream istr(filename.c_str());
+        if ( ! istr.is_open() )
+                throw std::runtime_error("Unable to open pattern file.");
+        int const first = istr.get();
+        if ( first < 0 )
+                throw std::runtime_error("Failed to read first character from pattern file.");
+        if ( first == '>' ) return false;
+        if ( first == '@' ) return true;
+        throw std::runtime_error("Unable to determine type of pattern file.");
+}
+
+static double clampWarn(char const * name, double v, bool upper)
+{
+        if ( v < 0 ) { std::cerr << "Warning: setting " << name << " up to 0." << std::endl; v = 0; }
+        if ( upper && v > 1 ) { std::cerr << "Warning: setting " << name << " down to 1." << std::endl; v = 1; }
+        return v;
+}
+
+RealOptions::RealOptions(int argc, char * argv[])
+: seedkmax(default_seedkmax), totalkmax(default_totalkmax), seedl(default_seedl), match_unique(default_match_unique), fracmem(default_fracmem),
+  scores(default_scores), qualityOffset(0), rewritepatterns(default_rewritepatterns), filter_level(default_filter_level), filter_mult(0),
+  similarity(DFLT_SIMILARITY), err(DFLT_ERR), trans(DFLT_TRANS), gc(DFLT_GC), gcmut_bias(DFLT_GCMUT_BIAS), gaps(false), fastq(false), threads(0), device(0)
+{
+        std::vector<std::string> opts;
+        for ( int i = 1; i < argc; ++i )
+                opts.push_back(argv[i]);
+        unsigned int i = 0;
+        while ( i < opts.size() )
+        {
+                std::string const & a = opts[i];
+                bool const known2 = a == "-t" || a == "-p" || a == "-o" || a == "-s" || a == "-e" || a == "-l" || a == "-u" || a == "-g" || a == "-R" || a == "-m" ||
+                        a == "-q" || a == "-Q" || a == "-f" || a == "-T" || a == "-similarity" || a == "-err" || a == "-trans" || a == "-gc" || a == "-gcmut_bias" || a == "-filter_level";
+                if ( known2 )
+                {
+                        if ( i + 1 >= opts.size() )
+                                throw std::runtime_error("Parameter for argument " + a + " is missing.");
+                        char const * v = opts[i+1].c_str();
+                        if ( a == "-t" ) textfilename = v;
+                        else if ( a == "-p" ) patternfilename = v;
+                        else if ( a == "-o" ) outputfilename = v;
+                        else if ( a == "-s" ) seedkmax = atoi(v);
+                        else if ( a == "-e" )
+                        {
+                                totalkmax = atoi(v);
+                                if ( totalkmax > 15 )                   // UniqueMatchInfoBase::getMaxErrors()
+                                {
+                                        totalkmax = 15;
+                                        std::cerr << "Warning: reducing maximum amount of errors to " << totalkmax << std::endl;
+                                }
+                        }
+                        else if ( a == "-l" ) seedl = atoi(v);
+                        else if ( a == "-u" ) match_unique = atoi(v);
+                        else if ( a == "-g" ) gaps = atoi(v);
+                        else if ( a == "-R" ) rewritepatterns = atoi(v);
+                        else if ( a == "-m" || a == "-f" ) fracmem = atof(v);
+                        else if ( a == "-q" ) scores = atoi(v);
+                        else if ( a == "-Q" ) qualityOffset = atoi(v);
+                        else if ( a == "-T" )
+                        {
+                                threads = atoi(v);
+                                if ( threads < 1 )
+                                        throw std::runtime_error("Argument for -T parameter is invalid (<1)");
+                        }
+                        else if ( a == "-similarity" )
+                        {
+                                similarity = clampWarn("similarity", atof(v), true);
+                                if ( similarity == 0 ) std::cerr << "Warning: similarity value is " << similarity << std::endl;
+                        }
+                        else if ( a == "-err" )
+                        {
+                                err = clampWarn("err", atof(v), true);
+                                if ( err == 1 ) std::cerr << "Warning: err value is " << err << std::endl;
+                        }
+                        else if ( a == "-trans" )
+                        {
+                                trans = clampWarn("trans", atof(v), true);
+                                if ( trans == 0 || trans == 1 ) std::cerr << "Warning: trans value is " << trans << std::endl;
+                        }
+                        else if ( a == "-gc" )
+                        {
+                                gc = clampWarn("gc", atof(v), true);
+                                if ( gc == 0 || gc == 1 ) std::cerr << "Warning: gc value is " << gc << std::endl;
+                        }
+                        else if ( a == "-gcmut_bias" )
+                        {
+                                gcmut_bias = clampWarn("gcmut_bias", atof(v), false);
+                                if ( gcmut_bias == 0 ) std::cerr << "Warning: gcmut_bias value is " << gcmut_bias << std::endl;
+                        }
+                        else if ( a == "-filter_level" )
+                        {
+                                filter_level = atoi(v);
+                                if ( filter_level < 0 ) { std::cerr << "Warning: setting filter_level up to 0." << std::endl; filter_level = 0; }
+                                if ( filter_level > 4 ) { std::cerr << "Warning: setting filter_level down to 4." << std::endl; filter_level = 4; }
+                        }
+                        i += 2;
+                }
+                else if ( a == "-h" )
+                {
+                        printHelp();
+                        throw std::runtime_error("Help requested.");
+                }
+                else
+                {
+                        std::cerr << "Ignoring argument " << a << std::endl;
+                        i += 1;
+                }
+        }
+        if ( ! (textfilename.size() && patternfilename.size() && outputfilename.size()) )
+                printHelp();
+        if ( ! textfilename.size() )
+                throw std::runtime_error("Mandatory argument -t (text file name) is not given.");
+        if ( ! patternfilename.size() )
+                throw std::runtime_error("Mandatory argument -p (pattern file name) is not given.");
+        if ( ! outputfilename.size() )
+                throw std::runtime_error("Mandatory argument -o (output file name) is not given.");
+        fracmem = std::min(1.0, fracmem);
+        if ( patternfilename == "-" )
+                throw std::runtime_error("Reading patterns from standard input is not supported by the GPU driver.");
+        fastq = isFastQ(patternfilename);
+        std::cerr << "pattern file is " << (fastq ? "FASTQ" : "FASTA") << " rewrite is " << (rewritepatterns ? "on" : "off") << std::endl;
+        if ( seedl > 64 )
+        {
+                seedl = 64;
+                std::cerr << "reduced seed size to " << seedl << " to not exceed 64." << std::endl;
+        }
+        if ( seedl % 4 )
+        {
+                seedl -= (seedl % 4);
+                std::cerr << "reduced seed size to " << seedl << " to have a multiple of 4." << std::endl;
+        }
+        if ( seedl < static_cast<int>(nu) )
+                throw std::runtime_error("cannot handle seed length < 4");
+        if ( seedkmax > 2 )
+        {
+                seedkmax = 2;
+                std::cerr << "reduced number of mismatches in seed to " << seedkmax << " as we cannot handle more." << std::endl;
+        }
+        switch ( filter_level )
+        {
+                case 1: filter_mult = 0.5 * totalkmax; break;
+                case 2: filter_mult = 1 * totalkmax; break;
+                case 3: filter_mult = 2 * totalkmax; break;
+                case 4: filter_mult = 3 * totalkmax; break;
+                case 0: default: filter_mult = 0 * totalkmax; break;
+        }
+        filter_mult /= 70.0;
+        std::cerr << "filter_mult=" << filter_mult << std::endl;
+        if ( char const * e = getenv("REAL_GPU_DEVICE") ) device = atoi(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scoring table (Scoring.cpp:61-133 init, :155-171 getScore)
+// ---------------------------------------------------------------------------------------------
+
+static double const q_prb[65] = {
+        1.0000000, 0.7943282, 0.6309573, 0.5011872, 0.3981072, 0.3162278, 0.2511886, 0.1995262, 0.1584893, 0.1258925,
+        0.1000000, 0.0794328, 0.0630957, 0.0501187, 0.0398107, 0.0316228, 0.0251189, 0.0199526, 0.0158489, 0.0125893,
+        0.0100000, 0.0079433, 0.0063096, 0.0050119, 0.0039811, 0.0031623, 0.0025119, 0.0019953, 0.0015849, 0.0012589,
+        0.0010000, 0.0007943, 0.0006310, 0.0005012, 0.0003981, 0.0003162, 0.0002512, 0.0001995, 0.0001585, 0.0001259,
+        0.0001000, 0.0000794, 0.0000631, 0.0000501, 0.0000398, 0.0000316, 0.0000251, 0.0000200, 0.0000158, 0.0000126,
+        0.0000100, 0.0000079, 0.0000063, 0.0000050, 0.0000040, 0.0000032, 0.0000025, 0.0000020, 0.0000016, 0.0000013,
+        0.0000010, 0.0000008, 0.0000006, 0.0000005, 0.0000004 };
+
+void buildScoringTable(double similarity, double gc, double trans, double err, double gcmut_bias, double * ll)
+{
+        volatile double odds[4][4];     // volatile: every intermediate is rounded to double like the reference's -ffloat-store build
+        double const transit = trans * (1 - similarity);
+        double const transver = (1 - trans) * (1 - similarity);
+        double const bg[4] = { (1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2 };
+        double const bias = gcmut_bias * (1 - gc) / gc;
+        odds[0][2] = transit / (bias + 1) / (1 - gc);
+        odds[3][1] = transit / (bias + 1) / (1 - gc);
+        odds[2][0] = transit / (bias + 1) / gc * bias;
+        odds[1][3] = transit / (bias + 1) / gc * bias;
+        odds[0][1] = transver / 2 / (bias + 1) / (1 - gc);
+        odds[3][2] = transver / 2 / (bias + 1) / (1 - gc);
+        odds[0][3] = transver / 2 / (bias + 1) / (1 - gc);
+        odds[3][0] = transver / 2 / (bias + 1) / (1 - gc);
+        odds[1][0] = transver / 2 / (bias + 1) / gc * bias;
+        odds[2][3] = transver / 2 / (bias + 1) / gc * bias;
+        odds[1][2] = transver / 2 / (bias + 1) / gc * bias;
+        odds[2][1] = transver / 2 / (bias + 1) / gc * bias;
+        odds[0][0] = 1 - odds[0][1] - odds[0][2] - odds[0][3];
+        odds[3][3] = 1 - odds[3][0] - odds[3][1] - odds[3][2];
+        odds[2][2] = 1 - odds[2][0] - odds[2][1] - odds[2][3];
+        odds[1][1] = 1 - odds[1][0] - odds[1][2] - odds[1][3];
+        for ( int x = 0; x < 4; ++x )
+                for ( int y = 0; y < 4; ++y )
+                {
+                        odds[x][y] = odds[x][y] * (1 - err);
+                        odds[x][y] = odds[x][y] / bg[y];
+                }
+        double const log2 = std::log(2.0);
+        for ( unsigned int c0 = 0; c0 < 4; ++c0 )
+                for ( unsigned int c1 = 0; c1 < 4; ++c1 )
+                        for ( unsigned int q = 0; q < 64; ++q )
+                        {
+                                volatile double const l = std::log(odds[c0][c1]) / log2;
+                                ll[(c0 << 8) | (c1 << 6) | q] = l * (1 - q_prb[q]);
+                        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// text (countReads.cpp:28-125, AutoTextArray.hpp:27-61)
+// ---------------------------------------------------------------------------------------------
+
+static void slurp(std::string const & filename, std::vector<char> & buf)
+{
+        FILE * f = fopen(filename.c_str(), "rb");
+        if ( ! f )
+                throw std::runtime_error("Failed to open file " + filename);
+        fseek(f, 0, SEEK_END);
+        long const sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize(sz > 0 ? sz : 0);
+        if ( sz > 0 && fread(&buf[0], 1, sz, f) != (size_t)sz )
+        {
+                fclose(f);
+                throw std::runtime_error("Failed to read file " + filename);
+        }
+        fclose(f);
+}
+
+std::vector<uint64_t> TextFile::starts() const
+{
+        std::vector<uint64_t> s(ranges.size());
+        for ( size_t i = 0; i < ranges.size(); ++i ) s[i] = ranges[i].second;
+        return s;
+}
+
+void getText(std::string const & filename, TextFile & out)
+{
+        std::cerr << "Computing length of file " << filename << "...";
+        std::vector<char> buf;
+        slurp(filename, buf);
+        out.ranges.clear();
+        out.words.assign(buf.size() / 32 + 2, 0);
+        out.nmask.assign(buf.size() / 64 + 2, 0);
+        // one pass with the state machine of countLength/readFile: '>' starts a header that runs to the end of
+        // the line, everything but A C G T N outside headers is dropped (lower case included)
+        bool header = false;
+        uint64_t cnt = 0, idcnt = 0;
+        std::string id;
+        for ( size_t p = 0; p < buf.size(); ++p )
+        {
+                char const c = buf[p];
+                if ( c == '>' ) { header = true; idcnt = cnt; id.resize(0); }
+                else if ( c == '\n' )
+                {
+                        if ( header )
+                                out.ranges.push_back(std::pair<std::string, uint64_t>(id, idcnt));
+                        header = false;
+                }
+                else if ( header ) id += c;
+                else
+                {
+                        unsigned int code;
+                        switch ( c )
+                        {
+                                case 'A': code = 0; break;
+                                case 'C': code = 1; break;
+                                case 'G': code = 2; break;
+                                case 'T': code = 3; break;
+                                case 'N': code = 4; break;
+                                default: continue;
+                        }
+                        if ( code == 4 )
+                                out.nmask[cnt >> 6] |= 1ULL << (63 - (cnt & 63));
+                        else
+                                out.words[cnt >> 5] |= (uint64_t)code << (62 - 2 * (cnt & 31));
+                        ++cnt;
+                }
+        }
+        out.ranges.push_back(std::pair<std::string, uint64_t>("terminal", cnt));
+        out.n = cnt;
+        out.words.resize((cnt + 31) / 32 + 1);
+        out.nmask.resize((cnt + 63) / 64 + 1);
+        std::cerr << "done, length is " << cnt << std::endl;
+}
+
+static bool endsOn(std::string const & s, std::string const & suffix)
+{
+        return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0;
+}
+
+static void enumerateFilesInDirectory(std::string const & dirname, std::vector<std::string> & files, std::string const & suffix)
+{
+        DIR * d = opendir(dirname.c_str());
+        if ( ! d )
+                throw std::runtime_error("Could not open file/directory");
+        struct dirent * e = 0;
+        while ( (e = readdir(d)) )
+        {
+                std::string const filename = dirname + "/" + e->d_name;
+                struct stat st;
+                if ( stat(filename.c_str(), &st) == 0 )
+                {
+                        if ( S_ISREG(st.st_mode) )
+                        {
+                                if ( endsOn(filename, suffix) )
+                                        files.push_back(filename);
+                        }
+                        else if ( S_ISDIR(st.st_mode) && std::string(e->d_name) != "." && std::string(e->d_name) != ".." )
+                                enumerateFilesInDirectory(filename + "/", files, suffix);
+                }
+        }
+        closedir(d);
+}
+
+void getFileList(std::string const & name, std::vector<std::string> & files, std::string const & suffix)
+{
+        struct stat st;
+        if ( stat(name.c_str(), &st) != 0 )
+                return;
+        if ( S_ISREG(st.st_mode) && endsOn(name, suffix) )
+                files.push_back(name);
+        else if ( S_ISDIR(st.st_mode) )
+                enumerateFilesInDirectory(name, files, suffix);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reads (FastAReader.hpp:107-138, FastQReader.hpp:130-180)
+// ---------------------------------------------------------------------------------------------
+
+namespace
+{
+        struct Cursor
+        {
+                std::vector<char> const & b; size_t p;
+                Cursor(std::vector<char> const & rb) : b(rb), p(0) {}
+                int get() { return p < b.size() ? (unsigned char)b[p++] : -1; }
+        };
+        inline uint8_t mapChar(int c)
+        {
+                switch ( c ) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 4; }
+        }
+}
+
+// the reader state machines, one record at a time; quality == 0 for FASTA
+static bool nextPattern(Cursor & in, bool fastq, int qualityOffset, bool & foundnextmarker, std::string & id, std::string & pat, std::string * quality)
+{
+        char const marker = fastq ? '@' : '>';
+        if ( ! foundnextmarker )
+                return false;
+        foundnextmarker = false;
+        int c;
+        id.resize(0);
+        while ( (c = in.get()) >= 0 && c != '\n' ) id += (char)c;
+        if ( c < 0 ) return false;
+        pat.resize(0);
+        char const patterm = fastq ? '+' : '>';
+        while ( (c = in.get()) >= 0 && c != patterm )
+                if ( ! isspace(c) ) pat += (char)c;
+        if ( ! fastq )
+        {
+                foundnextmarker = (c == '>');
+                return true;
+        }
+        while ( (c = in.get()) >= 0 && c != '\n' ) {}           // rest of the '+' line
+        if ( c < 0 ) return false;
+        quality->resize(0);
+        // the reference's loop fetches one character beyond the last quality value (FastQReader.hpp:163-165)
+        while ( ((c = in.get()) >= 0) && (quality->size() < pat.size()) )
+                if ( ! isspace(c) ) *quality += (char)(c - qualityOffset);
+        if ( quality->size() < pat.size() )
+                return false;
+        while ( (c = in.get()) >= 0 && c != marker ) {}          // findNextMarker
+        foundnextmarker = (c == marker);
+        return true;
+}
+
+static bool findFirstMarker(Cursor & in, char marker)
+{
+        int c;
+        while ( (c = in.get()) >= 0 && c != marker ) {}
+        return c == marker;
+}
+
+int detectQualityOffset(std::string const & filename)
+{
+        std::vector<char> buf;
+        slurp(filename, buf);
+        Cursor in(buf);
+        bool found = findFirstMarker(in, '@');
+        std::string id, pat, q;
+        while ( nextPattern(in, true, 0, found, id, pat, &q) )
+                for ( size_t i = 0; i < q.size(); ++i )
+                {
+                        if ( q[i] <= 54 ) return 33;            // Sanger
+                        else if ( q[i] >= 94 ) return 64;       // Illumina
+                }
+        return 0;
+}
+
+void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out)
+{
+        std::vector<char> buf;
+        slurp(filename, buf);
+        Cursor in(buf);
+        bool found = findFirstMarker(in, fastq ? '@' : '>');
+        out.mapped.clear(); out.quality.clear(); out.ids.clear();
+        out.offsets.assign(1, 0);
+        out.mapped.reserve(buf.size());
+        if ( fastq ) out.quality.reserve(buf.size() / 2);
+        std::string id, pat, q;
+        while ( nextPattern(in, fastq, qualityOffset, found, id, pat, fastq ? &q : 0) )
+        {
+                for ( size_t i = 0; i < pat.size(); ++i ) out.mapped.push_back(mapChar(pat[i]));
+                if ( fastq )
+                        for ( size_t i = 0; i < pat.size(); ++i ) out.quality.push_back((uint8_t)q[i]);
+                out.offsets.push_back(out.mapped.size());
+                out.ids.push_back(id);
+        }
+}
+
+void reorderLikeRewrite(ReadSet & reads)
+{
+        uint64_t const n = reads.size();
+        std::vector< std::pair< std::pair<uint64_t,int>, uint64_t> > key(n);
+        for ( uint64_t r = 0; r < n; ++r )
+        {
+                uint64_t const L = reads.offsets[r+1] - reads.offsets[r];
+                int hasn = 0;
+                for ( uint64_t i = reads.offsets[r]; i < reads.offsets[r+1]; ++i ) if ( reads.mapped[i] > 3 ) { hasn = 1; break; }
+                key[r] = std::make_pair(std::make_pair(L, hasn), r);
+        }
+        std::sort(key.begin(), key.end());     // r is part of the key: file order inside a group
+        ReadSet o;
+        o.mapped.reserve(reads.mapped.size());
+        if ( reads.quality.size() ) o.quality.reserve(reads.quality.size());
+        o.offsets.assign(1, 0);
+        for ( uint64_t i = 0; i < n; ++i )
+        {
+                uint64_t const r = key[i].second;
+                o.mapped.insert(o.mapped.end(), reads.mapped.begin() + reads.offsets[r], reads.mapped.begin() + reads.offsets[r+1]);
+                if ( reads.quality.size() )
+                        o.quality.insert(o.quality.end(), reads.quality.begin() + reads.offsets[r], reads.quality.begin() + reads.offsets[r+1]);
+                o.offsets.push_back(o.mapped.size());
+                o.ids.push_back(reads.ids[r]);
+        }
+        reads.mapped.swap(o.mapped); reads.quality.swap(o.quality); reads.offsets.swap(o.offsets); reads.ids.swap(o.ids);
+}
+
+// ---------------------------------------------------------------------------------------------
+// drivers
+// ---------------------------------------------------------------------------------------------
+
+namespace
+{
+        struct Gpu
+        {
+                real_gpu * h;
+                Gpu() : h(0) {}
+                ~Gpu() { if ( h ) real_gpu_destroy(h); }
+                void check(int rc, char const * what) const
+                {
+                        if ( rc != REAL_GPU_OK )
+                                throw std::runtime_error(std::string(what) + ": " + (h ? real_gpu_last_error(h) : "library error"));
+                }
+        };
+
+        struct Output
+        {
+                FILE * f; bool own;
+                explicit Output(std::string const & name) : f(0), own(false)
+                {
+                        if ( name == "-" ) f = stdout;
+                        else { f = fopen(name.c_str(), "wb"); own = true; }
+                        if ( ! f ) throw std::runtime_error("Failed to open output file " + name);
+                }
+                ~Output() { if ( f ) { fflush(f); if ( own ) fclose(f); } }
+                void write(std::string const & s) { if ( fwrite(s.data(), 1, s.size(), f) != s.size() ) throw std::runtime_error("write failed"); }
+        };
+
+        // one result line (matchAllImplementation.cpp:485-510, matchUniqueImplementation.cpp:267-288)
+        void formatLine(std::ostringstream & o, ReadSet const & reads, uint64_t r, bool inverted, bool scores, float score,
+                        std::string const & recname, uint64_t pos_in_record, unsigned int k)
+        {
+                static char const remap[5] = { 'A', 'C', 'G', 'T', 'N' };
+                uint64_t const b = reads.offsets[r], e = reads.offsets[r+1];
+                o << reads.ids[r] << "\t";
+                if ( ! inverted )
+                        for ( uint64_t i = b; i < e; ++i ) o << remap[std::min<int>(reads.mapped[i], 4)];
+                else
+                        for ( uint64_t i = e; i > b; --i ) { int const c = reads.mapped[i-1]; o << remap[c < 4 ? 3 - c : 4]; }
+                o << "\t";
+                if ( scores ) o << score;
+                o << "\t" << 1 << "\t" << "a" << "\t" << (e - b) << "\t" << (inverted ? "-" : "+") << "\t" << recname << "\t" << pos_in_record << "\t" << "\t" << k << "\n";
+        }
+
+        void createHandle(Gpu & G, RealOptions const & opts, std::vector<double> & ll)
+        {
+                real_gpu_params P;
+                memset(&P, 0, sizeof(P));
+                P.struct_size = sizeof(P);
+                P.device = opts.device;
+                P.seedl = opts.seedl; P.seedkmax = opts.seedkmax; P.totalkmax = opts.totalkmax; P.scores = opts.scores ? 1 : 0;
+                P.filter_mult = opts.filter_mult;
+                if ( opts.scores || opts.gaps )
+                {
+                        ll.resize(1024);
+                        buildScoringTable(opts.similarity, opts.gc, opts.trans, opts.err, opts.gcmut_bias, &ll[0]);
+                        P.ll_table = &ll[0];
+                }
+                int const rc = real_gpu_create(&P, &G.h);
+                if ( rc != REAL_GPU_OK )
+                        throw std::runtime_error("real_gpu_create failed (no CUDA device or unsupported option); there is no CPU fallback");
+        }
+
+        void loadReads(RealOptions const & opts, ReadSet & reads)
+        {
+                int qualityOffset = 0;
+                if ( opts.fastq )
+                {
+                        qualityOffset = opts.qualityOffset ? opts.qualityOffset : detectQualityOffset(opts.patternfilename);
+                        if ( ! qualityOffset )
+                                throw std::runtime_error("Unable to automatically detect FastQ quality format.");
+                }
+                readPatterns(opts.patternfilename, opts.fastq, qualityOffset, reads);
+                std::cerr << "Number of patterns is " << reads.size() << std::endl;
+        }
+}
+
+int doMatchingAll(RealOptions const & opts)
+{
+        ReadSet reads;
+        loadReads(opts, reads);            // (the stock -u 0 path parses FASTQ files with the FASTA reader, real.cpp:325-328; here FASTQ is honoured)
+        std::vector<std::string> filenames;
+        getFileList(opts.textfilename, filenames, ".fa");
+        Gpu G; std::vector<double> ll;
+        createHandle(G, opts, ll);
+        G.check(real_gpu_set_reads(G.h, reads.mapped.empty() ? 0 : &reads.mapped[0], reads.quality.empty() ? 0 : &reads.quality[0], &reads.offsets[0], reads.size()), "set_reads");
+        Output out(opts.outputfilename);
+        for ( size_t fi = 0; fi < filenames.size(); ++fi )
+        {
+                TextFile T;
+                getText(filenames[fi], T);
+                if ( T.n < (uint64_t)opts.seedl )
+                {
+                        std::cerr << "file " << filenames[fi] << " is too short for seed length " << opts.seedl << std::endl;
+                        continue;
+                }
+                std::vector<uint64_t> const starts = T.starts();
+                G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
+                real_gpu_hit const * hits = 0; uint64_t nhits = 0;
+                G.check(real_gpu_match_all(G.h, &hits, &nhits), "match_all");
+                std::ostringstream o;
+                for ( uint64_t i = 0; i < nhits; ++i )
+                {
+                        real_gpu_hit const & H = hits[i];
+                        formatLine(o, reads, H.patid, H.inverted != 0, opts.scores, H.score, T.ranges[H.frag].first, H.pos - T.ranges[H.frag].second + 1, H.k);
+                        if ( o.tellp() > 16384 ) { out.write(o.str()); o.str(std::string()); }
+                }
+                out.write(o.str());         // (the stock driver never flushes this tail, matchAllImplementation.cpp:512-517)
+        }
+        return EXIT_SUCCESS;
+}
+
+int doMatchingUnique(RealOptions const & opts)
+{
+        ReadSet reads;
+        loadReads(opts, reads);
+        if ( opts.rewritepatterns )
+                reorderLikeRewrite(reads);
+        std::vector<std::string> filenames;
+        getFileList(opts.textfilename, filenames, ".fa");
+        Gpu G; std::vector<double> ll;
+        createHandle(G, opts, ll);
+        G.check(real_gpu_set_reads(G.h, reads.mapped.empty() ? 0 : &reads.mapped[0], reads.quality.empty() ? 0 : &reads.quality[0], &reads.offsets[0], reads.size()), "set_reads");
+        std::vector< std::vector< std::pair<std::string, uint64_t> > > rangeset(filenames.size());       // RangeSet
+        for ( size_t fi = 0; fi < filenames.size(); ++fi )
+        {
+                TextFile T;
+                getText(filenames[fi], T);
+                rangeset[fi] = T.ranges;
+                if ( fi >= 64 || T.n >= (1ULL << 35) || T.ranges.size() > 65536 )
+                {
+                        std::cerr << "Skipping file " << filenames[fi] << " as it exceeds the limits of UniqueMatchInfo." << std::endl;
+                        continue;
+                }
+                if ( T.n < (uint64_t)opts.seedl )
+                        continue;
+                std::vector<uint64_t> const starts = T.starts();
+                G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
+                G.check(real_gpu_match_unique(G.h), "match_unique");
+        }
+        if ( opts.gaps )
+                G.check(real_gpu_match_gaps(G.h, 0), "match_gaps");
+        std::vector<uint64_t> info(reads.size() + 1);
+        std::vector<float> score(reads.size() + 1);
+        G.check(real_gpu_get_unique(G.h, &info[0], opts.scores ? &score[0] : 0), "get_unique");
+
+        Output out(opts.outputfilename);
+        uint64_t unique = 0;
+        std::ostringstream o;
+        for ( uint64_t r = 0; r < reads.size(); ++r )
+        {
+                uint64_t const d = info[r];
+                unsigned int const state = (unsigned int)(d >> 61);
+                if ( state != 1 && state != 2 )
+                        continue;
+                unsigned int const file = (unsigned int)((d >> 35) & 63), frag = (unsigned int)((d >> 45) & 0xFFFF), k = (unsigned int)((d >> 41) & 15);
+                uint64_t const pos = d & ((1ULL << 35) - 1);
+                formatLine(o, reads, r, state == 2, opts.scores, score[r], rangeset[file][frag].first, pos - rangeset[file][frag].second + 1, k);
+                ++unique;
+                if ( o.tellp() > 16384 ) { out.write(o.str()); o.str(std::string()); }
+        }
+        out.write(o.str());
+        std::cerr << "unique: " << unique << std::endl;
+        return EXIT_SUCCESS;
+}
+
+int realMain(int argc, char * argv[])
+{
+        std::cerr << "This is REAL (B200 matching path) for the command line of REAL version 0.0.31" << std::endl;
+        std::cerr << "real is distributed under version 3.0 of the GNU GENERAL PUBLIC LICENSE." << std::endl;
+        try
+        {
+                RealOptions opts(argc, argv);
+                return opts.match_unique ? doMatchingUnique(opts) : doMatchingAll(opts);
+        }
+        catch ( std::exception const & ex )
+        {
+                std::cerr << ex.what() << std::endl;
+                return EXIT_FAILURE;
+        }
+        catch ( ... )
+        {
+                std::cerr << "Caught unexpected exception, terminating." << std::endl;
+                return EXIT_FAILURE;
+        }
+}
+
+}

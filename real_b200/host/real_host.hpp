@@ -1,0 +1,92 @@
+// Host side of the drop-in: the reference's run drivers re-hosted on the C ABI of libreal_gpu.so.
+//
+// Mirrors, with the same names and argument meaning,
+//   RealOptions                         RealOptions.hpp:24-79, RealOptions.cpp:122-466
+//   countLength / readFile / getText    countReads.cpp:28-125, getText.hpp:31-58
+//   getFileList                         getFileList.cpp:155-174
+//   FastAReader / FastQReader           FastAReader.hpp:107-138, FastQReader.hpp:130-180, 221-239
+//   reorderFastA / reorderFastQ order   ReorderFastA.hpp:31-70, TemporaryFile.hpp:194-295 (-R 1)
+//   EnumerateAllMatches::doMatching     matchAllImplementation.cpp:359-538
+//   EnumerateUniqueMatches::doMatching  matchUniqueImplementation.cpp:1082-1489
+//   Scoring                             Scoring.cpp:61-171
+// The block loop over text-side index blocks (matchAllImplementation.cpp:451-535,
+// matchUniqueImplementation.cpp:1253-1297) is what the library replaces: one real_gpu_set_reads
+// (read-side index), then per text file one real_gpu_set_text + real_gpu_match_all / _match_unique.
+// Nothing here matches on the CPU; library errors surface as std::runtime_error like the reference's.
+#ifndef REAL_HOST_HPP
+#define REAL_HOST_HPP
+
+#include <stdint.h>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace realhost
+{
+
+struct RealOptions
+{
+        static unsigned int const default_seedkmax = 2;
+        static unsigned int const default_totalkmax = 5;
+        static unsigned int const default_seedl = 32;
+        static bool const default_match_unique = true;
+        static bool const default_scores = true;
+        static bool const default_rewritepatterns = true;
+        static unsigned int const default_filter_level = 2;
+        static unsigned int const nu = 4;
+
+        std::string textfilename, patternfilename, outputfilename;
+        unsigned int seedkmax, totalkmax;
+        int seedl;
+        bool match_unique;
+        double fracmem;
+        bool scores;
+        unsigned int qualityOffset;
+        bool rewritepatterns;
+        int filter_level;
+        double filter_mult;
+        double similarity, err, trans, gc, gcmut_bias;
+        bool gaps;
+        bool fastq;
+        int threads;            // -T: accepted and ignored (the matching runs on the GPU)
+        int device;             // REAL_GPU_DEVICE, default 0
+
+        RealOptions(int argc, char * argv[]);
+        void printHelp() const;
+        static bool isFastQ(std::string const & filename);
+        double getFilterValue(unsigned int patl) const { return filter_mult * patl; }
+};
+
+// Scoring::LL, 4*4*64 doubles indexed (ref<<8)|(read<<6)|q
+void buildScoringTable(double similarity, double gc, double trans, double err, double gcmut_bias, double * ll);
+
+struct TextFile
+{
+        std::vector<uint64_t> words;     // 2 bit/base, MSB first (AutoTextArray.hpp:27-43), N stored as A
+        std::vector<uint64_t> nmask;     // 1 bit/base, MSB first (AutoTextArray.hpp:45-61)
+        uint64_t n;
+        std::vector< std::pair<std::string, uint64_t> > ranges;   // (header text, start) + ("terminal", n)
+        std::vector<uint64_t> starts() const;
+};
+void getText(std::string const & filename, TextFile & out);
+void getFileList(std::string const & name, std::vector<std::string> & files, std::string const & suffix);
+
+struct ReadSet
+{
+        std::vector<uint8_t> mapped;     // 0..3 = ACGT, 4 = anything else (Pattern.hpp:105-128)
+        std::vector<uint8_t> quality;    // char - offset (FastQReader.hpp:168); empty for FASTA
+        std::vector<uint64_t> offsets;   // nreads + 1
+        std::vector<std::string> ids;
+        uint64_t size() const { return offsets.size() - 1; }
+};
+int detectQualityOffset(std::string const & filename);                       // FastQReader::getOffset
+void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out);
+// the order the rewritten pattern file hands the reads out in (-R 1): by length, wildcard-free reads first
+void reorderLikeRewrite(ReadSet & reads);
+
+int doMatchingAll(RealOptions const & opts);
+int doMatchingUnique(RealOptions const & opts);
+int realMain(int argc, char * argv[]);
+
+}
+#endif

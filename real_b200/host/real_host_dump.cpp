@@ -1,0 +1,85 @@
+// Test helper: dumps what the host layer hands to the C ABI (packed text, parsed reads, scoring table, options)
+// as JSON, so the CPU test-suite can check the parsers without a GPU.
+#include "real_host.hpp"
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+
+using namespace realhost;
+
+static void jstr(std::string const & s)
+{
+        putchar('"');
+        for ( size_t i = 0; i < s.size(); ++i )
+        {
+                unsigned char const c = s[i];
+                if ( c == '"' || c == '\\' ) { putchar('\\'); putchar(c); }
+                else if ( c < 32 ) printf("\\u%04x", c);
+                else putchar(c);
+        }
+        putchar('"');
+}
+
+int main(int argc, char * argv[])
+{
+        try
+        {
+                if ( argc < 2 ) return 2;
+                std::string const mode = argv[1];
+                if ( mode == "text" )
+                {
+                        TextFile T; getText(argv[2], T);
+                        printf("{\"n\":%llu,\"ranges\":[", (unsigned long long)T.n);
+                        for ( size_t i = 0; i < T.ranges.size(); ++i ) { if ( i ) putchar(','); putchar('['); jstr(T.ranges[i].first); printf(",%llu]", (unsigned long long)T.ranges[i].second); }
+                        printf("],\"words\":[");
+                        for ( size_t i = 0; i < T.words.size(); ++i ) printf("%s%llu", i ? "," : "", (unsigned long long)T.words[i]);
+                        printf("],\"nmask\":[");
+                        for ( size_t i = 0; i < T.nmask.size(); ++i ) printf("%s%llu", i ? "," : "", (unsigned long long)T.nmask[i]);
+                        printf("]}\n");
+                }
+                else if ( mode == "reads" )
+                {
+                        bool const fastq = atoi(argv[3]); int qoff = atoi(argv[4]); bool const rewrite = atoi(argv[5]);
+                        if ( fastq && ! qoff ) qoff = detectQualityOffset(argv[2]);
+                        ReadSet R; readPatterns(argv[2], fastq, qoff, R);
+                        if ( rewrite ) reorderLikeRewrite(R);
+                        printf("{\"qoff\":%d,\"ids\":[", qoff);
+                        for ( size_t i = 0; i < R.ids.size(); ++i ) { if ( i ) putchar(','); jstr(R.ids[i]); }
+                        printf("],\"offsets\":[");
+                        for ( size_t i = 0; i < R.offsets.size(); ++i ) printf("%s%llu", i ? "," : "", (unsigned long long)R.offsets[i]);
+                        printf("],\"mapped\":[");
+                        for ( size_t i = 0; i < R.mapped.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)R.mapped[i]);
+                        printf("],\"quality\":[");
+                        for ( size_t i = 0; i < R.quality.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)R.quality[i]);
+                        printf("]}\n");
+                }
+                else if ( mode == "ll" )
+                {
+                        double ll[1024];
+                        buildScoringTable(atof(argv[2]), atof(argv[3]), atof(argv[4]), atof(argv[5]), atof(argv[6]), ll);
+                        printf("[");
+                        for ( int i = 0; i < 1024; ++i ) { unsigned long long u; memcpy(&u, &ll[i], 8); printf("%s%llu", i ? "," : "", u); }
+                        printf("]\n");
+                }
+                else if ( mode == "opts" )
+                {
+                        RealOptions o(argc - 1, argv + 1);
+                        unsigned long long fm; memcpy(&fm, &o.filter_mult, 8);
+                        printf("{\"seedkmax\":%u,\"totalkmax\":%u,\"seedl\":%d,\"match_unique\":%d,\"scores\":%d,\"qualityOffset\":%u,\"rewritepatterns\":%d,\"filter_level\":%d,"
+                               "\"filter_mult_bits\":%llu,\"gaps\":%d,\"fastq\":%d}\n", o.seedkmax, o.totalkmax, o.seedl, (int)o.match_unique, (int)o.scores, o.qualityOffset,
+                               (int)o.rewritepatterns, o.filter_level, fm, (int)o.gaps, (int)o.fastq);
+                }
+                else if ( mode == "files" )
+                {
+                        std::vector<std::string> f; getFileList(argv[2], f, ".fa");
+                        printf("[");
+                        for ( size_t i = 0; i < f.size(); ++i ) { if ( i ) putchar(','); jstr(f[i]); }
+                        printf("]\n");
+                }
+                else return 2;
+                return 0;
+        }
+        catch ( std::exception const & e ) { std::cerr << e.what() << std::endl; return 1; }
+}

@@ -1,0 +1,52 @@
+"""GPU: the `real` command line on the GPU path (real_b200/bin/real) against output files written by the
+STOCK reference binary (tests/golden/cli_*.txt, made by tests/golden/make_cli_golden.py)."""
+import os
+import subprocess
+
+import pytest
+
+from real_b200 import build as rbuild
+from cli_cases import CASES, make_case
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cli_output_identical_to_stock_real(name, tmp_path):
+    rbuild.build()
+    rbuild.build_host()
+    targ, rf, flags = make_case(name, str(tmp_path))
+    out = tmp_path / "out.txt"
+    p = subprocess.run([rbuild.HOST_BIN, "-t", targ, "-p", rf, "-o", str(out)] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, REAL_STRICT_EXIT="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    want = open(os.path.join(GOLDEN, "cli_%s.txt" % name)).read()
+    got = out.read_text()
+    assert len(want.splitlines()) > 100
+    assert got == want
+
+
+def test_cli_match_all_complete_output(tmp_path):
+    """matchAll through the CLI: every oracle hit is printed once (the stock CLI truncates)."""
+    import numpy as np
+    from oracle import oracle_py as O
+    from real_b200 import synth
+    rbuild.build()
+    rbuild.build_host()
+    text = synth.make_text(401, 50000, nrecords=2)
+    reads = synth.make_reads(text, 402, 500, 60, 0.02, True)
+    synth.write_fasta(str(tmp_path / "t.fa"), text)
+    synth.write_reads(str(tmp_path / "r.fq"), reads, True)
+    out = tmp_path / "o.txt"
+    p = subprocess.run([rbuild.HOST_BIN, "-t", str(tmp_path / "t.fa"), "-p", str(tmp_path / "r.fq"), "-o", str(out), "-u", "0", "-e", "4", "-q", "1", "-Q", "33"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, REAL_STRICT_EXIT="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = O.match_all(text, reads, totalkmax=4, scores=True)
+    rows = [l.split("\t") for l in out.read_text().splitlines()]
+    assert len(rows) == len(ref)
+    starts = text.record_starts
+    want = sorted((reads.ids[int(h["patid"])], "-" if h["inverted"] else "+", text.records[int(h["frag"])][0], int(h["pos"]) - int(starts[int(h["frag"])]) + 1,
+                   int(h["k"]), "%g" % np.float32(h["score"])) for h in ref)
+    got = sorted((r[0], r[6], r[7], int(r[8]), int(r[10]), r[2]) for r in rows)
+    assert got == want

@@ -1,0 +1,121 @@
+"""CPU: the C++ host layer (real_b200/host) -- FASTA/FASTQ parsing, text packing, record table, scoring table
+and option handling -- against the reference's own outputs in the KAT fixtures and against the layouts of
+real_b200/synth.py.  Uses real_b200/bin/real_host_dump (no GPU calls)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from real_b200 import build as rbuild
+from real_b200 import synth
+from util import load_kat
+
+
+@pytest.fixture(scope="module")
+def dump():
+    rbuild.build()
+    rbuild.build_host()
+
+    def run(*args, ok=True):
+        p = subprocess.run([rbuild.HOST_DUMP] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        if ok:
+            assert p.returncode == 0, p.stderr
+            return json.loads(p.stdout)
+        return p
+    return run
+
+
+def test_text_loader_matches_reference_layout(dump, tmp_path):
+    kat = load_kat("kat_l32")
+    tk = synth.make_text(107, 3000, nrecords=3, n_per_million=30000)
+    f = tmp_path / "t.fa"
+    synth.write_fasta(str(f), tk)
+    d = dump("text", f)
+    assert d["n"] == kat["n"]
+    assert [[a, b] for a, b in d["ranges"]] == kat["ranges"]
+    ref = kat["textwords"]
+    assert d["words"][:len(ref)] == ref
+    w, m = tk.packed()
+    assert d["nmask"][:m.size] == [int(x) for x in m]
+
+
+def test_text_loader_quirks(dump, tmp_path):
+    # lower case and IUPAC codes are dropped, '>' inside a line starts a header (countReads.cpp:44-76)
+    f = tmp_path / "q.fa"
+    f.write_bytes(b"> one two\nACGTacgtNNRYAC\nGT>mid line\nTTTT\n\nGG\n")
+    d = dump("text", f)
+    assert d["ranges"] == [[" one two", 0], ["mid line", 10], ["terminal", 16]]
+    sym = synth.unpack_text(np.asarray(d["words"], dtype=np.uint64), 16, np.asarray(d["nmask"], dtype=np.uint64))
+    assert "".join("ACGTN"[c] for c in sym) == "ACGTNNACGTTTTTGG"
+
+
+def test_scoring_table_bits(dump):
+    kat = load_kat("kat_l32")
+    p = kat["scoring_params"]
+    assert dump("ll", *["%.17g" % x for x in p]) == kat["ll_bits"]
+    assert dump("ll", 0.9, 0.5, 0.6, 0.01, 1.5) == [int(x) for x in __import__("oracle.oracle_py", fromlist=["x"]).build_ll(0.9, 0.5, 0.6, 0.01, 1.5).view(np.uint64)]
+
+
+@pytest.mark.parametrize("fastq", [False, True])
+def test_read_parsers(dump, tmp_path, fastq):
+    kat = load_kat("kat_l32")
+    tk = synth.make_text(107, 3000, nrecords=3, n_per_million=30000)
+    rk = synth.concat_reads([synth.make_reads(tk, 12, 12, L, 0.03, True) for L in (32, 33, 36, 64, 96, 100, 150, 250)])
+    f = tmp_path / ("r.fq" if fastq else "r.fa")
+    synth.write_reads(str(f), rk, fastq)
+    d = dump("reads", f, int(fastq), 0, 0)
+    assert d["ids"] == rk.ids
+    assert d["offsets"] == [int(x) for x in rk.offsets]
+    assert d["mapped"] == [int(x) for x in rk.mapped]
+    for r, ref in enumerate(kat["reads"]):
+        b, e = d["offsets"][r], d["offsets"][r + 1]
+        assert d["mapped"][b:e] == ref["mapped"]
+        if fastq:
+            assert d["quality"][b:e] == ref["quality"]
+    if fastq:
+        assert d["qoff"] == 33
+
+
+def test_fastq_multiline_and_offset_detection(dump, tmp_path):
+    f = tmp_path / "m.fq"
+    f.write_bytes(b"@r1 x\nACGT\nAC\n+r1\nhhhh\nhh\n@r2\nNNAC\n+\n~~~~\n")
+    d = dump("reads", f, 1, 0, 0)
+    assert d["qoff"] == 64 and d["ids"] == ["r1 x", "r2"]
+    assert d["mapped"] == [0, 1, 2, 3, 0, 1, 4, 4, 0, 1]
+    assert d["quality"] == [40] * 6 + [62] * 4
+
+
+def test_rewrite_order(dump, tmp_path):
+    # -R 1: grouped by length, wildcard-free reads first, file order inside a group (ReorderFastA.hpp, TemporaryFile.hpp)
+    f = tmp_path / "o.fa"
+    f.write_bytes(b">a\nACGTAC\n>b\nACG\n>c\nACNTAC\n>d\nAAA\n>e\nGGGGGG\n>f\nNNN\n")
+    d = dump("reads", f, 0, 0, 1)
+    assert d["ids"] == ["b", "d", "f", "a", "e", "c"]
+
+
+def test_options(dump, tmp_path):
+    r = tmp_path / "r.fa"
+    r.write_bytes(b">x\nACGT\n")
+    d = dump("opts", "-t", "t.fa", "-p", r, "-o", "o", "-e", "77", "-s", "9", "-l", "70", "-u", "0", "-bogus", "-filter_level", "3")
+    assert (d["totalkmax"], d["seedkmax"], d["seedl"], d["match_unique"], d["filter_level"], d["fastq"]) == (15, 2, 64, 0, 3, 0)
+    assert np.asarray([d["filter_mult_bits"]], dtype=np.uint64).view(np.float64)[0] == 2 * 15 / 70.0
+    p = dump("opts", "-p", r, "-o", "o", ok=False)
+    assert p.returncode == 1 and "Mandatory argument -t" in p.stderr
+    p = dump("opts", "-t", "t", "-p", r, "-o", ok=False)
+    assert p.returncode == 1 and "Parameter for argument -o is missing." in p.stderr
+    q = tmp_path / "r.fq"
+    q.write_bytes(b"@x\nACGT\n+\nIIII\n")
+    assert dump("opts", "-t", "t", "-p", q, "-o", "o")["fastq"] == 1
+
+
+def test_file_list(dump, tmp_path):
+    (tmp_path / "d").mkdir()
+    (tmp_path / "d" / "a.fa").write_bytes(b">a\nA\n")
+    (tmp_path / "d" / "b.txt").write_bytes(b">a\nA\n")
+    (tmp_path / "d" / "sub").mkdir()
+    (tmp_path / "d" / "sub" / "c.fa").write_bytes(b">a\nA\n")
+    got = sorted(os.path.basename(x) for x in dump("files", tmp_path / "d"))
+    assert got == ["a.fa", "c.fa"]
+    assert dump("files", tmp_path / "d" / "b.txt") == []
