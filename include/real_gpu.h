@@ -165,6 +165,11 @@ int real_gpu_match_unique(real_gpu * h);
 int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores);
 /* Clears the unique state (fresh UniqueMatchInfo objects). */
 int real_gpu_reset_unique(real_gpu * h);
+/* With scores the unique fold is order dependent (UpdateUniqueInfo<true>::update, matchUniqueImplementation.cpp:179-248):
+ * the reference visits the hits of a read text block by text block.  n_list = seed windows per reference text block
+ * as its memory planner would choose them (matchUniqueImplementation.cpp:1208-1244); 0 = one block per file.
+ * Also used by real_gpu_match_gaps.  In this mode the handle must hold the whole file (one shard). */
+int real_gpu_set_block_windows(real_gpu * h, uint64_t n_list);
 
 /* Cross-shard exchange for matchUnique without scores: the per-read state is
  * exported as an order-preserving u64 key so that a MIN all-reduce followed by a SUM all-reduce of

@@ -61,6 +61,8 @@ __host__ __device__ inline uint64_t rawhit_pack(uint64_t pos, uint32_t k, uint32
 {
         return pos | ((uint64_t)k << 35) | ((uint64_t)strand << 39) | ((uint64_t)frag << 40);
 }
+__host__ __device__ inline uint32_t rawhit_read(uint32_t r) { return r & 0x0FFFFFFFu; }      // RawHit::read = read | exact-fragment mask << 28
+__host__ __device__ inline uint32_t rawhit_exact(uint32_t r) { return r >> 28; }
 __host__ __device__ inline uint64_t rawhit_pos(uint64_t pm) { return pm & ((1ULL << 35) - 1); }
 __host__ __device__ inline uint32_t rawhit_k(uint64_t pm) { return (uint32_t)((pm >> 35) & 15); }
 __host__ __device__ inline uint32_t rawhit_strand(uint64_t pm) { return (uint32_t)((pm >> 39) & 1); }

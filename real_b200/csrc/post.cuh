@@ -44,9 +44,10 @@ __global__ void __launch_bounds__(256) k_score_hits(RawHit * __restrict__ hits, 
         if ( i >= nhits ) return;
         RawHit h = hits[i];
         uint32_t const strand = rawhit_strand(h.pm);
-        uint32_t const L = rlen[h.read];
-        const uint8_t * q = quality ? (quality + offsets[h.read]) : nullptr;
-        h.score = score_hit(sll, text, rawhit_pos(h.pm) - shard_begin, rpack + ((uint64_t)h.read * 2 + strand) * W, q, L, strand);
+        uint32_t const read = rawhit_read(h.read);
+        uint32_t const L = rlen[read];
+        const uint8_t * q = quality ? (quality + offsets[read]) : nullptr;
+        h.score = score_hit(sll, text, rawhit_pos(h.pm) - shard_begin, rpack + ((uint64_t)read * 2 + strand) * W, q, L, strand);
         hits[i] = h;
 }
 
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) k_score_hits(RawHit * __restrict__ hits, 
 __global__ void __launch_bounds__(256) k_hit_count(const RawHit * __restrict__ hits, uint64_t nhits, uint32_t * __restrict__ counts)
 {
         uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if ( i < nhits ) atomicAdd(&counts[hits[i].read], 1u);
+        if ( i < nhits ) atomicAdd(&counts[rawhit_read(hits[i].read)], 1u);
 }
 
 __global__ void __launch_bounds__(256) k_hit_scatter(const RawHit * __restrict__ hits, uint64_t nhits, const uint32_t * __restrict__ starts,
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) k_hit_scatter(const RawHit * __restrict__
         uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if ( i >= nhits ) return;
         RawHit const h = hits[i];
-        uint32_t const o = starts[h.read] + atomicAdd(&cursor[h.read], 1u);
+        uint32_t const o = starts[rawhit_read(h.read)] + atomicAdd(&cursor[rawhit_read(h.read)], 1u);
         out[o] = h;
 }
 
@@ -110,6 +111,162 @@ __global__ void __launch_bounds__(128) k_hit_order(RawHit * __restrict__ seg, co
                 H.reserved = 0;
                 o[i] = H;
         }
+}
+
+// ---- order-faithful matchUnique with scores ---------------------------------------------------
+// UpdateUniqueInfo<true>::update (matchUniqueImplementation.cpp:179-248) compares float scores with a
+// tolerance epsilon = (float)(filter_mult * patl); the comparisons are not transitive, so the result
+// depends on the order in which the reference visits the hits of a read: text block, strand ('+' first),
+// list 0..5, ascending seed-window position.  The scan reports every hit once together with
+// the set of exact seed fragments; the lists that see a hit are the fragment pairs that are both exact.
+
+// valid seed-window starts of one 64-position group: no wildcard in [i, i+seedl) and i + seedl <= n
+__global__ void __launch_bounds__(256) k_window_counts(const uint64_t * __restrict__ nmask, uint64_t n, uint32_t seedl, uint64_t ngroups,
+                                                     uint64_t * __restrict__ valid, uint32_t * __restrict__ counts)
+{
+        uint64_t const g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( g >= ngroups ) return;
+        // bad(i) = OR of the wildcard bits i .. i+seedl-1 ; positions are MSB first, so "later" is toward the low bits
+        uint64_t hi = nmask[g], lo = nmask[g + 1];
+        uint32_t covered = 1;
+        while ( covered < seedl )
+        {
+                uint32_t const step = min(covered, seedl - covered);
+                uint64_t const nhi = hi | ((hi << step) | (lo >> (64 - step)));
+                uint64_t const nlo = lo | (lo << step);
+                hi = nhi; lo = nlo;
+                covered += step;
+        }
+        uint64_t v = ~hi;
+        uint64_t const first = g * 64;
+        uint64_t const last_start = (n >= seedl) ? (n - seedl) : 0;              // inclusive
+        if ( n < seedl || first > last_start ) v = 0;
+        else if ( first + 63 > last_start ) v &= (~0ULL) << (63 - (last_start - first));
+        valid[g] = v;
+        counts[g] = (uint32_t)__popcll(v);
+}
+
+// position of the first window of block b (b >= 1): the (b * n_list)-th valid window start
+__global__ void __launch_bounds__(64) k_block_bounds(const uint64_t * __restrict__ valid, const uint32_t * __restrict__ prefix, uint64_t ngroups,
+                                                   uint64_t n_list, uint32_t nblocks, uint64_t * __restrict__ bounds)
+{
+        uint32_t const b = blockIdx.x * blockDim.x + threadIdx.x;
+        if ( b >= nblocks ) return;
+        if ( b == 0 ) { bounds[0] = 0; return; }
+        uint64_t const target = (uint64_t)b * n_list;
+        uint64_t lo = 0, hi = ngroups;           // last group with prefix[g] <= target
+        while ( hi - lo > 1 )
+        {
+                uint64_t const mid = (lo + hi) >> 1;
+                if ( prefix[mid] <= target ) lo = mid; else hi = mid;
+        }
+        uint64_t v = valid[lo];
+        uint32_t skip = (uint32_t)(target - prefix[lo]);
+        while ( skip-- ) v &= ~(1ULL << (63 - __clzll(v)));
+        bounds[b] = lo * 64 + __clzll(v);
+}
+
+struct ReplayParams
+{
+        RawHit * seg;                   // hits grouped by read
+        const uint32_t * starts;
+        const uint32_t * counts;
+        const uint32_t * rlen;
+        uint64_t nreads;
+        uint32_t seedl, fileid;
+        double filter_mult;
+        const uint64_t * bounds;        // first window of every block, or null for a single block
+        uint32_t nblocks;
+        unsigned long long * info;
+        float * score;
+};
+
+__device__ __forceinline__ uint32_t block_of(ReplayParams const & P, uint64_t rpos)
+{
+        if ( ! P.bounds ) return 0;
+        uint32_t lo = 0, hi = P.nblocks;
+        while ( hi - lo > 1 )
+        {
+                uint32_t const mid = (lo + hi) >> 1;
+                if ( P.bounds[mid] <= rpos ) lo = mid; else hi = mid;
+        }
+        return lo;
+}
+
+// one thread per read
+__global__ void __launch_bounds__(128) k_unique_replay(ReplayParams P)
+{
+        uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( r >= P.nreads ) return;
+        uint32_t const n = P.counts[r];
+        if ( ! n ) return;
+        RawHit * s = P.seg + P.starts[r];
+        uint32_t const L = P.rlen[r];
+        float const epsilon = (float)(P.filter_mult * (double)L);
+        uint32_t const moff = L - P.seedl;
+        // order by (block, strand, seed window position); the block is kept in the (now free) frag bits above bit 16 ...
+        // frag is < 65536 in unique mode, so pm bits 56..63 are free for nothing we need: compute the key on the fly instead
+        auto key_less = [&](RawHit const & a, RawHit const & b) -> bool
+        {
+                uint32_t const sa = rawhit_strand(a.pm), sb = rawhit_strand(b.pm);
+                uint64_t const ra = rawhit_pos(a.pm) + (sa ? moff : 0), rb = rawhit_pos(b.pm) + (sb ? moff : 0);
+                uint32_t const ba = block_of(P, ra), bb = block_of(P, rb);
+                if ( ba != bb ) return ba < bb;
+                if ( sa != sb ) return sa < sb;
+                return ra < rb;
+        };
+        for ( uint32_t i = 1; i < n; ++i )
+        {
+                RawHit const x = s[i];
+                uint32_t j = i;
+                while ( j > 0 && key_less(x, s[j-1]) ) { s[j] = s[j-1]; --j; }
+                s[j] = x;
+        }
+        unsigned long long d = P.info[r];
+        float sc = P.score[r];
+        uint32_t i = 0;
+        while ( i < n )
+        {
+                uint32_t const st = rawhit_strand(s[i].pm);
+                uint32_t const bl = block_of(P, rawhit_pos(s[i].pm) + (st ? moff : 0));
+                uint32_t j = i + 1;
+                while ( j < n && rawhit_strand(s[j].pm) == st && block_of(P, rawhit_pos(s[j].pm) + (st ? moff : 0)) == bl ) ++j;
+                for ( uint32_t l = 0; l < 6; ++l )
+                {
+                        // list l = fragment pair (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+                        uint32_t const fa = l < 3 ? 0u : (l < 5 ? 1u : 2u);
+                        uint32_t const fb = l < 3 ? l + 1 : (l < 5 ? l - 1 : 3u);
+                        uint32_t const need = (1u << fa) | (1u << fb);
+                        for ( uint32_t t = i; t < j; ++t )
+                        {
+                                if ( (rawhit_exact(s[t].read) & need) != need ) continue;
+                                uint64_t const pos = rawhit_pos(s[t].pm);
+                                uint32_t const k = rawhit_k(s[t].pm), frag = rawhit_frag(s[t].pm);
+                                float const score = s[t].score;
+                                uint32_t const state = umi_state(d);
+                                bool const same = (pos == umi_pos(d)) && (P.fileid == umi_file(d)) && (frag == umi_frag(d));
+                                if ( state == ST_NOMATCH || state == ST_GAPPED )
+                                {
+                                        d = umi_make(st ? ST_REVERSE : ST_STRAIGHT, P.fileid, pos, k, frag); sc = score;
+                                }
+                                else if ( score > sc + epsilon )
+                                {
+                                        d = umi_make(st ? ST_REVERSE : ST_STRAIGHT, P.fileid, pos, k, frag); sc = score;
+                                }
+                                else if ( state != ST_NONUNIQUE && (score > sc - epsilon) && ! same )
+                                        d = umi_with_state(d, ST_NONUNIQUE);
+                        }
+                }
+                i = j;
+        }
+        P.info[r] = d;
+        P.score[r] = sc;
+}
+
+__global__ void __launch_bounds__(256) k_fill_f32(float * __restrict__ p, uint64_t n, float v)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i < n ) p[i] = v;
 }
 
 // ---- K5 : cross-shard reduction keys --------------------------------------------

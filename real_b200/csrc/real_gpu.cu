@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <cfloat>
 #include <vector>
 
 using namespace realgpu;
@@ -64,6 +65,8 @@ struct real_gpu
 
         // results
         DevBuf rec_win, rec_pos, part_meta;
+        DevBuf win_valid, win_counts, bounds;   // reference text blocks (order-faithful replay)
+        uint64_t n_list;               // windows per reference text block, 0 = one block per file
         DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
         uint32_t table_counts[6];      // per table: entries, distinct slots (read back after the build)
         const uint8_t * src_mapped;    // device pointer the reads are packed from (caller's buffer or h->mapped)
@@ -77,7 +80,7 @@ struct real_gpu
         uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
 
-        real_gpu() : src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -313,6 +316,12 @@ int build_from_device(real_gpu * h)
         // fresh unique state (UniqueMatchInfo.hpp:172,190)
         dev_reserve(h, h->info, (size_t)nreads * 8 + 16);
         RG_CUDA(cudaMemsetAsync(h->info.p, 0, (size_t)nreads * 8 + 16, h->st));
+        if ( h->prm.scores )
+        {
+                dev_reserve(h, h->scores, (size_t)nreads * 4 + 16);
+                k_fill_f32<<<blocks_for(nreads + 1, 256), 256, 0, h->st>>>(ptr<float>(h->scores), nreads, -FLT_MAX);      // UniqueMatchInfo.hpp:190
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->have_reads = true;
         return REAL_GPU_OK;
@@ -523,7 +532,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
@@ -621,14 +630,10 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
         RG_API_END(h)
 }
 
-int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhits)
+// scan in hit-list mode (regrowing the buffer if it was too small), score the hits, group them by read:
+// afterwards hits_seg holds the hits of read r at [starts[r], starts[r] + counts[r])
+static uint64_t collect_hits_by_read(real_gpu * h)
 {
-        RG_API_BEGIN(h)
-        if ( ! hits || ! nhits ) return fail(h, REAL_GPU_E_ARG, "match_all: null pointer");
-        int const rc = check_ready(h);
-        if ( rc ) return rc;
-        *hits = nullptr; *nhits = 0;
-        h->stats.scan_launches = 0;
         if ( h->hit_cap == 0 )
         {
                 h->hit_cap = std::max<uint64_t>(1u << 16, 2 * h->nreads);
@@ -641,11 +646,14 @@ int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhit
                 h->hit_cap = found + found / 8 + 1024;
                 dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
                 found = run_scan(h, 0);
-                if ( found > h->hit_cap ) return fail(h, REAL_GPU_E_CUDA, "match_all: hit count changed between scans");
+                if ( found > h->hit_cap ) throw CudaError("hit count changed between scans");
         }
-        if ( found >= (1ULL << 32) ) return fail(h, REAL_GPU_E_LIMIT, "match_all: more than 2^32 hits in one call");
-
+        if ( found >= (1ULL << 32) ) throw CudaError("more than 2^32 hits in one call");
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        dev_reserve(h, h->counts, h->nreads * 4 + 16);
+        dev_reserve(h, h->starts, h->nreads * 4 + 16);
+        dev_reserve(h, h->cursor, h->nreads * 4 + 16);
+        RG_CUDA(cudaMemsetAsync(h->counts.p, 0, h->nreads * 4 + 16, h->st));
         if ( found )
         {
                 if ( h->prm.scores )
@@ -655,14 +663,9 @@ int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhit
                                 h->qual_present ? ptr<uint8_t>(h->qual) : nullptr, ptr<uint64_t>(h->offs));
                         RG_KERNEL_CHECK(); launch_count(h);
                 }
-                // counting sort by read, then per-read ordering
-                dev_reserve(h, h->counts, h->nreads * 4 + 16);
-                dev_reserve(h, h->starts, h->nreads * 4 + 16);
-                dev_reserve(h, h->cursor, h->nreads * 4 + 16);
+                // counting sort by read
                 dev_reserve(h, h->scantmp, scan_temp_elems(h->nreads) * 4 + 64);
                 dev_reserve(h, h->hits_seg, found * sizeof(RawHit));
-                dev_reserve(h, h->hits_out, found * sizeof(real_gpu_hit));
-                RG_CUDA(cudaMemsetAsync(h->counts.p, 0, h->nreads * 4, h->st));
                 RG_CUDA(cudaMemsetAsync(h->cursor.p, 0, h->nreads * 4, h->st));
                 k_hit_count<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<uint32_t>(h->counts));
                 RG_KERNEL_CHECK(); launch_count(h);
@@ -671,6 +674,22 @@ int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhit
                 launch_count(h, nl);
                 k_hit_scatter<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<uint32_t>(h->starts), ptr<uint32_t>(h->cursor), ptr<RawHit>(h->hits_seg));
                 RG_KERNEL_CHECK(); launch_count(h);
+        }
+        return found;
+}
+
+int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhits)
+{
+        RG_API_BEGIN(h)
+        if ( ! hits || ! nhits ) return fail(h, REAL_GPU_E_ARG, "match_all: null pointer");
+        int const rc = check_ready(h);
+        if ( rc ) return rc;
+        *hits = nullptr; *nhits = 0;
+        h->stats.scan_launches = 0;
+        uint64_t const found = collect_hits_by_read(h);
+        if ( found )
+        {
+                dev_reserve(h, h->hits_out, found * sizeof(real_gpu_hit));
                 k_hit_order<real_gpu_hit><<<blocks_for(h->nreads, 128), 128, 0, h->st>>>(ptr<RawHit>(h->hits_seg), ptr<uint32_t>(h->starts), ptr<uint32_t>(h->counts),
                                                                                         h->nreads, h->fileid, ptr<real_gpu_hit>(h->hits_out));
                 RG_KERNEL_CHECK(); launch_count(h);
@@ -696,18 +715,67 @@ int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhit
         RG_API_END(h)
 }
 
+// first window of every reference text block (matchUniqueImplementation.cpp:1208-1244: n_list windows per block)
+static uint32_t block_bounds(real_gpu * h)
+{
+        if ( ! h->n_list ) return 1;
+        uint32_t const seedl = h->prm.seedl;
+        uint64_t const ngroups = (h->n_total + 63) / 64;
+        dev_reserve(h, h->win_valid, ngroups * 8 + 64);
+        dev_reserve(h, h->win_counts, ngroups * 4 + 64);
+        dev_reserve(h, h->scantmp, scan_temp_elems(ngroups) * 4 + 64);
+        k_window_counts<<<blocks_for(ngroups, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, h->n_total, seedl, ngroups,
+                                                                     ptr<uint64_t>(h->win_valid), ptr<uint32_t>(h->win_counts));
+        RG_KERNEL_CHECK(); launch_count(h);
+        uint32_t lastc = 0, lastp = 0, nl = 0;
+        RG_CUDA(cudaMemcpyAsync(&lastc, ptr<uint32_t>(h->win_counts) + (ngroups - 1), 4, cudaMemcpyDeviceToHost, h->st));
+        exclusive_scan_u32(ptr<uint32_t>(h->win_counts), ptr<uint32_t>(h->win_counts), ngroups, ptr<uint32_t>(h->scantmp), h->st, &nl);
+        launch_count(h, nl);
+        RG_CUDA(cudaMemcpyAsync(&lastp, ptr<uint32_t>(h->win_counts) + (ngroups - 1), 4, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        uint64_t const nwin = (uint64_t)lastc + lastp;
+        uint64_t const nb = nwin ? (nwin + h->n_list - 1) / h->n_list : 1;
+        if ( nb <= 1 ) return 1;
+        if ( nb > (1u << 24) ) throw CudaError("more than 2^24 reference text blocks");
+        dev_reserve(h, h->bounds, nb * 8 + 64);
+        k_block_bounds<<<blocks_for(nb, 64), 64, 0, h->st>>>(ptr<uint64_t>(h->win_valid), ptr<uint32_t>(h->win_counts), ngroups, h->n_list, (uint32_t)nb, ptr<uint64_t>(h->bounds));
+        RG_KERNEL_CHECK(); launch_count(h);
+        return (uint32_t)nb;
+}
+
 int real_gpu_match_unique(real_gpu * h)
 {
         RG_API_BEGIN(h)
         int const rc = check_ready(h);
         if ( rc ) return rc;
-        if ( h->prm.scores )
-                return fail(h, REAL_GPU_E_ARG, "match_unique with scores (order-dependent epsilon rule, matchUniqueImplementation.cpp:179-248) is not built in this version");
         if ( h->nrec + 1 > 65536 )
                 return REAL_GPU_OK;   // the reference skips such files (matchUniqueImplementation.cpp:1139-1143)
         h->stats.scan_launches = 0;
-        run_scan(h, 1);
         h->stats.post_ms = 0; h->stats.d2h_ms = 0;
+        if ( ! h->prm.scores )
+        {
+                run_scan(h, 1);         // order independent: folded in the scan itself
+                return REAL_GPU_OK;
+        }
+        // with scores the fold depends on the reference's visiting order (matchUniqueImplementation.cpp:179-248):
+        // collect the hits of this file, then replay them per read in that order
+        if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
+                return fail(h, REAL_GPU_E_ARG, "match_unique with scores needs the whole file in one shard (the fold is order dependent)");
+        uint64_t const found = collect_hits_by_read(h);
+        if ( found )
+        {
+                uint32_t const nb = block_bounds(h);
+                ReplayParams R;
+                R.seg = ptr<RawHit>(h->hits_seg); R.starts = ptr<uint32_t>(h->starts); R.counts = ptr<uint32_t>(h->counts); R.rlen = ptr<uint32_t>(h->rlen);
+                R.nreads = h->nreads; R.seedl = h->prm.seedl; R.fileid = h->fileid; R.filter_mult = h->prm.filter_mult;
+                R.bounds = nb > 1 ? ptr<uint64_t>(h->bounds) : nullptr; R.nblocks = nb;
+                R.info = ptr<unsigned long long>(h->info); R.score = ptr<float>(h->scores);
+                k_unique_replay<<<blocks_for(h->nreads, 128), 128, 0, h->st>>>(R);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.post_ms = elapsed(h->ev[0], h->ev[1]);
         return REAL_GPU_OK;
         RG_API_END(h)
 }
@@ -722,7 +790,11 @@ int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores)
         RG_CUDA(cudaEventRecord(h->ev[1], h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.d2h_ms = elapsed(h->ev[0], h->ev[1]);
-        if ( scores ) for ( uint64_t i = 0; i < h->nreads; ++i ) scores[i] = 0.0f;
+        if ( scores )
+        {
+                if ( h->prm.scores && h->nreads ) RG_CUDA(cudaMemcpy(scores, h->scores.p, h->nreads * 4, cudaMemcpyDeviceToHost));
+                else for ( uint64_t i = 0; i < h->nreads; ++i ) scores[i] = 0.0f;
+        }
         return REAL_GPU_OK;
         RG_API_END(h)
 }
@@ -732,9 +804,21 @@ int real_gpu_reset_unique(real_gpu * h)
         RG_API_BEGIN(h)
         if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
         RG_CUDA(cudaMemsetAsync(h->info.p, 0, (size_t)h->nreads * 8 + 16, h->st));
+        if ( h->prm.scores )
+        {
+                k_fill_f32<<<blocks_for(h->nreads + 1, 256), 256, 0, h->st>>>(ptr<float>(h->scores), h->nreads, -FLT_MAX);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
         RG_CUDA(cudaStreamSynchronize(h->st));
         return REAL_GPU_OK;
         RG_API_END(h)
+}
+
+int real_gpu_set_block_windows(real_gpu * h, uint64_t n_list)
+{
+        if ( ! h ) return REAL_GPU_E_ARG;
+        h->n_list = n_list;
+        return REAL_GPU_OK;
 }
 
 int real_gpu_unique_export_keys(real_gpu * h, uint64_t * d_keys)

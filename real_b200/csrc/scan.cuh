@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(SC_MAX_BUCKETS) k_part_offsets(ScanParams P)
 // ---- probe -------------------------------------------------------------------------------------
 
 struct ItemA { uint64_t win; uint32_t before; uint32_t post; };      // a set slot bit: window, bases in front, position | table << 30
-struct ItemB { uint64_t lp; uint32_t id; uint32_t seedk; };           // an entry that passed the seed test
+struct ItemB { uint64_t lp; uint32_t id; uint32_t exact; };           // an entry that passed the seed test (exact: bit f = fragment f matches exactly)
 
 struct ProbeSmem
 {
@@ -468,7 +468,7 @@ struct ProbeSmem
 
 // stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
 // whole-read distance, report
-__device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, unsigned long long * lstats)
+__device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, uint32_t exact, unsigned long long * lstats)
 {
         uint32_t const strand = id & 1;
         uint32_t const read = id >> 1;
@@ -507,7 +507,7 @@ __device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t
                 {
                         RawHit h;
                         h.pm = rawhit_pack(gpos, k, strand, frag);
-                        h.read = read;
+                        h.read = read | (exact << 28);     // which fragments of the seed are exact: decides the lists that see the hit (order-faithful replay)
                         h.score = 1.0f;
                         P.hits[slot] = h;
                 }
@@ -558,22 +558,23 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
                 uint32_t const seedk = (uint32_t)__popcll(x);
                 if ( seedk > P.seedkmax ) continue;
                 int first = -1, second = -1;
+                uint32_t exact4 = 0;
                 #pragma unroll
                 for ( int f = 0; f < 4; ++f )
                 {
                         bool const exact = ((x >> (2*F*(3-f))) & fm) == 0;
-                        if ( exact ) { if ( first < 0 ) first = f; else if ( second < 0 ) second = f; }
+                        if ( exact ) { exact4 |= 1u << f; if ( first < 0 ) first = f; else if ( second < 0 ) second = f; }
                 }
                 if ( first != (int)t || second != pair_second(table, (int)t) ) continue;
                 lstats[1] += 1;
                 uint32_t const o = atomicAdd(qbn, 1u);
                 if ( o < SC_QB_CAP )
                 {
-                        ItemB ib; ib.lp = lp; ib.id = id; ib.seedk = seedk;
+                        ItemB ib; ib.lp = lp; ib.id = id; ib.exact = exact4;
                         qb[o] = ib;
                 }
                 else
-                        verify_and_report(P, lp, id, lstats);          // queue full: handle it here
+                        verify_and_report(P, lp, id, exact4, lstats);          // queue full: handle it here
         }
 }
 
@@ -585,7 +586,7 @@ __device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, u
         for ( uint32_t i = lane; i < n; i += 32 )
         {
                 ItemB const ib = qb[i];
-                verify_and_report(P, ib.lp, ib.id, lstats);
+                verify_and_report(P, ib.lp, ib.id, ib.exact, lstats);
         }
         __syncwarp();
         if ( lane == 0 ) *qbn = 0;

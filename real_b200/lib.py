@@ -92,6 +92,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_match_unique.argtypes = [vp]
     L.real_gpu_get_unique.argtypes = [vp, vp, vp]
     L.real_gpu_reset_unique.argtypes = [vp]
+    L.real_gpu_set_block_windows.argtypes = [vp, u64]
     L.real_gpu_unique_export_keys.argtypes = [vp, vp]
     L.real_gpu_unique_export_ties.argtypes = [vp, vp, vp]
     L.real_gpu_unique_import.argtypes = [vp, vp, vp]
@@ -217,6 +218,9 @@ class Handle:
 
     def reset_unique(self):
         self._check(self.L.real_gpu_reset_unique(self.h))
+
+    def set_block_windows(self, n_list: int):
+        self._check(self.L.real_gpu_set_block_windows(self.h, n_list))
 
     def unique_export_keys(self, d_keys: int):
         self._check(self.L.real_gpu_unique_export_keys(self.h, d_keys))

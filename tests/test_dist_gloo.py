@@ -1,0 +1,117 @@
+"""CPU, world_size 2, gloo: the cross-shard fold of the per-read unique state (real_b200.dist.unique_exchange)
+-- the one exchange step of the path.  Each rank holds the state a text shard would produce (built here from
+the oracle's complete hit set, cut by hit start position), the exchange runs over torch.distributed, and the
+merged state must equal the oracle's matchUnique over the whole text.  The three key transforms that the
+device kernels implement (k_unique_export / k_unique_ties / k_unique_import, csrc/post.cuh) are restated in
+numpy for the CPU participants."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle_py as O
+from real_b200 import dist as rdist
+from real_b200 import matcher, synth
+
+NONE = rdist.UNIQUE_KEY_NONE
+
+
+def fold_hits(nreads, hits):
+    """UpdateUniqueInfo<false>::update over a hit list (order independent form)."""
+    info = np.zeros(nreads, dtype=np.uint64)
+    best = {}
+    for h in hits:
+        r = int(h["patid"])
+        cur = best.get(r)
+        key = (int(h["k"]), int(h["file"]), int(h["pos"]), int(h["inverted"]), int(h["frag"]))
+        if cur is None or key[0] < cur[0][0]:
+            best[r] = [key, False]
+        elif key[0] == cur[0][0]:
+            if key[1:3] != cur[0][1:3]:
+                cur[1] = True
+                if key[1:3] < cur[0][1:3]:
+                    cur[0] = key
+            elif key[3] < cur[0][3]:
+                cur[0] = key
+    for r, (key, non) in best.items():
+        k, f, p, inv, frag = key
+        st = 4 if non else (2 if inv else 1)
+        info[r] = p | (f << 35) | (k << 41) | (frag << 45) | (st << 61)
+    return info
+
+
+def np_key(info):
+    st = matcher.umi_state(info)
+    key = (matcher.umi_err(info) << 59) | ((st != 4).astype(np.int64) << 58) | (matcher.umi_file(info) << 52) | (matcher.umi_pos(info) << 17) | \
+          ((st == 2).astype(np.int64) << 16) | matcher.umi_frag(info)
+    key[(st == 0) | (st == 3)] = NONE
+    return key.astype(np.int64)
+
+
+class NumpyShard:
+    def __init__(self, info):
+        self.info = info
+        self.nreads = info.size
+        self.device = torch.device("cpu")
+
+    def export_keys(self, keys):
+        keys.copy_(torch.from_numpy(np_key(self.info)))
+
+    def export_ties(self, min_keys, ties):
+        mine, win = np_key(self.info), min_keys.numpy()
+        samepos = (((mine ^ win) >> 17) & ((1 << 41) - 1)) == 0
+        ties.copy_(torch.from_numpy(((mine != NONE) & ((mine >> 59) == (win >> 59)) & ~samepos).astype(np.uint8)))
+
+    def import_merged(self, min_keys, tie_sums):
+        key, ts = min_keys.numpy(), tie_sums.numpy()
+        has = key != NONE
+        uniq = (((key >> 58) & 1) == 1) & (ts == 0)
+        strand = (key >> 16) & 1
+        st = np.where(uniq, np.where(strand == 1, 2, 1), 4)
+        merged = ((key >> 17) & ((1 << 35) - 1)) | (((key >> 52) & 63) << 35) | ((key >> 59) << 41) | ((key & 0xFFFF) << 45) | (st << 61)
+        self.info = np.where(has, merged.astype(np.uint64), self.info)
+
+    def sync(self):
+        pass
+
+
+def _worker(rank, world, port, shard_infos, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = NumpyShard(shard_infos[rank].copy())
+        rdist.unique_exchange(sh)
+        np.save(out_path % rank, sh.info)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unique_exchange_world2_gloo(tmp_path):
+    text = synth.make_text(77, 120_000, nrecords=3, n_per_million=1500)
+    sym = text.symbols.copy()
+    sym[70_000:76_000] = sym[10_000:16_000]          # repeats across the shard boundary => cross-shard ties
+    text = synth.Text(sym, text.records)
+    reads = synth.make_reads(text, 78, 1500, 64, 0.015, fastq=False)
+    kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    hits = O.match_all(text, reads, **kw)
+    want, _ = O.unique_init(reads.nreads, False)
+    O.match_unique(text, reads, want, None, **kw)
+    world = 2
+    shards = matcher.shard_ranges(text.n, world, 64)
+    infos = [fold_hits(reads.nreads, hits[(hits["pos"] >= ob) & (hits["pos"] < oe)]) for ob, oe, _, _ in shards]
+    assert np.array_equal(matcher.canonical_unique(fold_hits(reads.nreads, hits)), matcher.canonical_unique(want))   # the fold itself is right
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "rank%d.npy")
+    mp.spawn(_worker, args=(world, port, infos, out), nprocs=world, join=True)
+    st = matcher.umi_state(want)
+    assert (st == 4).sum() > 20 and (st == 1).sum() > 300 and (st == 2).sum() > 300
+    for r in range(world):
+        got = np.load(out % r)
+        assert np.array_equal(matcher.canonical_unique(got), matcher.canonical_unique(want))
