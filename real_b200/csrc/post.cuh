@@ -3,6 +3,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "../../include/real_gpu.h"
 
 namespace realgpu
 {
@@ -261,6 +262,243 @@ __global__ void __launch_bounds__(128) k_unique_replay(ReplayParams P)
         }
         P.info[r] = d;
         P.score[r] = sc;
+}
+
+// ---- gapped extension (K7): ::matchGaps, match.hpp:428-602 --------------------------------------
+// Per seed candidate of a read that is still NoMatch/Gapped: banded DP `agm` (match.hpp:267-332) of the
+// read rest (m = L - seedl bases) against up to n = min(record end - seedl - rpos, 2L) text bases behind the
+// seed, band |i-j| <= 3, fp64 scores from the LL table:
+//     G[i][j] = max( G[i-1][j-1] + LL[text_i][read_j][q_j] ,  G[d][d] with d = min(i,j) )      (off the main diagonal)
+//     H[i][j] = |i-j| when the second term is strictly larger, else 0
+// then `opt_solution` (:159-260) over the end cells of the seven diagonals and `backtracing` (:115-152) along the
+// winning diagonal.  Only seven running diagonal values, the last four main-diagonal values and the row of the
+// last gap per diagonal are needed; every addition happens in the reference's order, so the doubles are identical.
+struct GapRes { double complete; uint32_t mingap, where, start, gap_pos; };
+
+struct GapParams
+{
+        const RawHit * seg; uint64_t ncand;
+        const double * ll;
+        const uint64_t * text; const uint64_t * nmask; uint64_t shard_begin;
+        const uint64_t * rec; uint32_t nrec;
+        const uint64_t * rpack; uint32_t W; const uint32_t * rlen;
+        const uint8_t * quality; const uint64_t * offsets;
+        uint32_t seedl, scores;
+        GapRes * res;
+};
+
+__device__ __forceinline__ double gap_total_scoring(uint32_t gap, double cur)
+{
+        // total_scoring(gap, cur, open = -1, extend = -1, offset = -1), match.hpp:16-29
+        if ( gap % 3 == 0 ) return cur + ((double)gap * -1.0) + -1.0 + -1.0;
+        return cur + ((double)gap * -1.0) + -1.0;
+}
+
+__global__ void __launch_bounds__(128) k_gap_dp(GapParams P)
+{
+        __shared__ double sll[1024];
+        for ( int i = threadIdx.x; i < 1024; i += blockDim.x ) sll[i] = P.ll[i];
+        __syncthreads();
+        uint64_t const c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( c >= P.ncand ) return;
+        RawHit const h = P.seg[c];
+        uint32_t const read = rawhit_read(h.read);
+        uint64_t const rpos = rawhit_pos(h.pm);
+        uint32_t const frag = rawhit_frag(h.pm);
+        uint32_t const L = P.rlen[read];
+        uint32_t const seedl = P.seedl;
+        GapRes R; R.complete = 0; R.mingap = 0; R.where = 0; R.start = 0; R.gap_pos = 0;
+        uint64_t const phigh = P.rec[frag + 1];
+        uint64_t n64 = phigh - seedl - rpos;
+        if ( n64 > 2ULL * L ) n64 = 2ULL * L;
+        uint32_t const n = (uint32_t)n64, m = L - seedl;
+        uint64_t const lbase = rpos - P.shard_begin;
+        if ( ! (n && m && wildcard_free(P.nmask, lbase + seedl, n)) ) { P.res[c] = R; return; }
+
+        const uint64_t * rp = P.rpack + (uint64_t)read * 2 * P.W;            // '+' strand
+        const uint8_t * q = P.quality ? (P.quality + P.offsets[read]) : nullptr;
+        double const seedscore = P.scores ? (double)score_hit(sll, P.text, lbase, rp, q, seedl, 0) : (double)1.0f;
+
+        int const MAXgap = 3;
+        double const MINscore = -100.0;
+        double g[7];                 // running value of diagonal delta = i - j, index delta + 3
+        uint32_t lastgap[7];         // row of the last cell of the diagonal that took the gap branch (0 = none)
+        #pragma unroll
+        for ( int d = 0; d < 7; ++d ) { g[d] = 0.0; lastgap[d] = 0; }
+        double mainh[4] = {0.0, 0.0, 0.0, 0.0};    // G[i-1][i-1], G[i-2][i-2], G[i-3][i-3] at [1..3]; [0] = G[i][i]
+
+        for ( uint32_t i = 1; i <= n; ++i )
+        {
+                int const left = ((int)i - MAXgap > 0) ? ((int)i - MAXgap) : 1;
+                int const right = (i + MAXgap > m) ? (int)m : (int)(i + MAXgap);
+                if ( left > right ) break;                                   // the band has left the matrix: nothing below is ever read
+                uint64_t const tpos = lbase + seedl - 1 + i;
+                uint32_t const tb = (uint32_t)(__ldg(P.text + (tpos >> 5)) >> (62 - 2 * (tpos & 31))) & 3;
+                // main diagonal history: shift before the row is computed
+                mainh[3] = mainh[2]; mainh[2] = mainh[1]; mainh[1] = mainh[0];
+                #pragma unroll
+                for ( int dd = 3; dd >= -3; --dd )                            // j = i - dd ascending
+                {
+                        int const j = (int)i - dd;
+                        if ( j < left || j > right ) continue;
+                        uint32_t const rpos_read = (uint32_t)j + seedl - 1;
+                        uint32_t const rb = (uint32_t)(__ldg(rp + (rpos_read >> 5)) >> (62 - 2 * (rpos_read & 31))) & 3;
+                        uint32_t const qq = q ? (uint32_t)__ldg(q + rpos_read) : 30u;
+                        double const sub = sll[((tb << 8) | (rb << 6) | qq) & 1023];
+                        double const mis = __dadd_rn(g[dd + 3], sub);
+                        if ( dd == 0 )
+                        {
+                                g[3] = mis;
+                                mainh[0] = mis;
+                        }
+                        else
+                        {
+                                // G[d][d], d = min(i,j): for j < i the main diagonal value of dd rows ago, for j > i this row's
+                                double const gp = (dd > 0) ? mainh[dd] : mainh[0];
+                                g[dd + 3] = (mis < gp) ? gp : mis;
+                                if ( gp > mis ) lastgap[dd + 3] = i;
+                        }
+                }
+        }
+
+        // opt_solution: end cells (i, m) for i in [up, down], then (n, j) for j in [left, right)
+        double score = MINscore;
+        int const up = ((int)m - MAXgap < 0) ? 0 : ((int)m - MAXgap);
+        int const down = (m + MAXgap > n) ? (int)n : (int)(m + MAXgap);
+        double maxscore = 0;
+        for ( int i = up; i <= down; ++i )
+        {
+                int const dd = i - (int)m;
+                double const gv = (i >= 1) ? g[dd + 3] : 0.0;               // row 0 is never written: calloc'ed zero
+                if ( gv >= MINscore )
+                {
+                        uint32_t const gap = (uint32_t)(dd < 0 ? -dd : dd);
+                        double const t = gap_total_scoring(gap, gv);
+                        if ( t > score )
+                        {
+                                score = t; maxscore = t; R.mingap = gap;
+                                R.where = dd < 0 ? 1u : (dd > 0 ? 2u : 0u);
+                                R.start = dd == 0 ? m : (uint32_t)i;
+                        }
+                }
+        }
+        if ( m + MAXgap > n )
+        {
+                int const left = ((int)n - MAXgap > 0) ? ((int)n - MAXgap) : 1;
+                int const right = (n + MAXgap > m) ? (int)m : (int)(n + MAXgap);
+                for ( int j = left; j < right; ++j )
+                {
+                        int const dd = (int)n - j;
+                        double const gv = g[dd + 3];
+                        if ( gv >= MINscore && dd <= MAXgap )
+                        {
+                                double const t = gap_total_scoring((uint32_t)dd, gv);
+                                if ( t > score ) { score = t; maxscore = t; R.mingap = (uint32_t)dd; R.where = 3; R.start = (uint32_t)j; }
+                        }
+                }
+        }
+        // backtracing along the winning diagonal: first cell from the end whose H is set
+        {
+                int bi, bj;
+                if ( R.where == 1 || R.where == 2 ) { bi = (int)R.start; bj = (int)m; }
+                else { bi = (int)n; bj = (int)R.start; }
+                int const dd = bi - bj;
+                R.gap_pos = 0;
+                if ( dd >= -3 && dd <= 3 && dd != 0 )
+                {
+                        uint32_t const lg = lastgap[dd + 3];
+                        if ( lg && (int)lg <= bi )
+                        {
+                                int const gi = (int)lg, gj = gi - dd;
+                                R.gap_pos = (uint32_t)(gi > gj ? gj : gi);
+                        }
+                        // else the walk ends on the matrix border (H[i][0] = i, H[0][j] = j): min(i,j) = 0
+                }
+        }
+        R.complete = seedscore + maxscore;
+        P.res[c] = R;
+}
+
+struct GapReplayParams
+{
+        RawHit * seg; GapRes * res;
+        const uint32_t * starts; const uint32_t * counts;
+        uint64_t nreads;
+        uint32_t scores;
+        const uint64_t * bounds; uint32_t nblocks;
+        unsigned long long * info; float * score; real_gpu_gapinfo * gaps;
+};
+
+// one thread per read: the reference's visiting order (block, list 0..5, window position), '+' strand only
+__global__ void __launch_bounds__(128) k_gap_replay(GapReplayParams P)
+{
+        uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( r >= P.nreads ) return;
+        uint32_t const n = P.counts[r];
+        if ( ! n ) return;
+        RawHit * s = P.seg + P.starts[r];
+        GapRes * gr = P.res + P.starts[r];
+        auto blk = [&](uint64_t rpos) -> uint32_t
+        {
+                if ( ! P.bounds ) return 0;
+                uint32_t lo = 0, hi = P.nblocks;
+                while ( hi - lo > 1 ) { uint32_t const mid = (lo + hi) >> 1; if ( P.bounds[mid] <= rpos ) lo = mid; else hi = mid; }
+                return lo;
+        };
+        for ( uint32_t i = 1; i < n; ++i )                 // ascending window position (which also orders the blocks)
+        {
+                RawHit const x = s[i]; GapRes const y = gr[i];
+                uint32_t j = i;
+                while ( j > 0 && rawhit_pos(x.pm) < rawhit_pos(s[j-1].pm) ) { s[j] = s[j-1]; gr[j] = gr[j-1]; --j; }
+                s[j] = x; gr[j] = y;
+        }
+        unsigned long long d = P.info[r];
+        float sc = P.scores ? P.score[r] : 0.0f;
+        real_gpu_gapinfo gi = P.gaps[r];
+        uint32_t i = 0;
+        while ( i < n )
+        {
+                uint32_t const bl = blk(rawhit_pos(s[i].pm));
+                uint32_t j = i + 1;
+                while ( j < n && blk(rawhit_pos(s[j].pm)) == bl ) ++j;
+                for ( uint32_t l = 0; l < 6; ++l )
+                {
+                        uint32_t const fa = l < 3 ? 0u : (l < 5 ? 1u : 2u);
+                        uint32_t const fb = l < 3 ? l + 1 : (l < 5 ? l - 1 : 3u);
+                        uint32_t const need = (1u << fa) | (1u << fb);
+                        for ( uint32_t t = i; t < j; ++t )
+                        {
+                                if ( (rawhit_exact(s[t].read) & need) != need ) continue;
+                                GapRes const & G = gr[t];
+                                if ( ! G.mingap ) continue;                                  // match.hpp:540
+                                uint64_t const rpos = rawhit_pos(s[t].pm);
+                                float const stored = P.scores ? sc : 0.0f;                  // UniqueMatchInfo.hpp:178-185
+                                uint32_t const st = umi_state(d);
+                                bool take = false;
+                                if ( st == ST_NOMATCH )
+                                {
+                                        d = umi_with_state(d, ST_GAPPED);
+                                        take = true;
+                                }
+                                else if ( st == ST_GAPPED )
+                                {
+                                        if ( G.complete > (double)stored + 1e-6 ) take = true;
+                                        else if ( G.complete < (double)stored - 1e-6 ) {}
+                                        else gi.present = 0;
+                                }
+                                if ( take )
+                                {
+                                        if ( P.scores ) sc = (float)G.complete;
+                                        d = (d & ~UMI_POSMASK) | rpos;
+                                        gi.patid = (uint32_t)r; gi.mingap = G.mingap; gi.where = G.where; gi.start = G.start; gi.gap_pos = G.gap_pos; gi.present = 1;
+                                }
+                        }
+                }
+                i = j;
+        }
+        P.info[r] = d;
+        if ( P.scores ) P.score[r] = sc;
+        P.gaps[r] = gi;
 }
 
 __global__ void __launch_bounds__(256) k_fill_f32(float * __restrict__ p, uint64_t n, float v)

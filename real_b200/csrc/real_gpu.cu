@@ -65,7 +65,7 @@ struct real_gpu
 
         // results
         DevBuf rec_win, rec_pos, part_meta;
-        DevBuf win_valid, win_counts, bounds;   // reference text blocks (order-faithful replay)
+        DevBuf win_valid, win_counts, bounds, gapres, gaps;   // reference text blocks (order-faithful replay)
         uint64_t n_list;               // windows per reference text block, 0 = one block per file
         DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
         uint32_t table_counts[6];      // per table: entries, distinct slots (read back after the build)
@@ -316,6 +316,11 @@ int build_from_device(real_gpu * h)
         // fresh unique state (UniqueMatchInfo.hpp:172,190)
         dev_reserve(h, h->info, (size_t)nreads * 8 + 16);
         RG_CUDA(cudaMemsetAsync(h->info.p, 0, (size_t)nreads * 8 + 16, h->st));
+        if ( h->ll.p )
+        {
+                dev_reserve(h, h->gaps, (size_t)nreads * sizeof(real_gpu_gapinfo) + 16);
+                RG_CUDA(cudaMemsetAsync(h->gaps.p, 0, (size_t)nreads * sizeof(real_gpu_gapinfo) + 16, h->st));
+        }
         if ( h->prm.scores )
         {
                 dev_reserve(h, h->scores, (size_t)nreads * 4 + 16);
@@ -456,7 +461,7 @@ uint64_t run_scan(real_gpu * h, int mode)
         h->stats.n_candidates = c[1];
         h->stats.n_seedpass = c[2];
         h->stats.n_hits = c[3];
-        return (mode == 0) ? (uint64_t)c[0] : (uint64_t)c[3];
+        return (mode != 1) ? (uint64_t)c[0] : (uint64_t)c[3];
 }
 
 int check_ready(real_gpu * h)
@@ -532,7 +537,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
@@ -632,20 +637,20 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
 
 // scan in hit-list mode (regrowing the buffer if it was too small), score the hits, group them by read:
 // afterwards hits_seg holds the hits of read r at [starts[r], starts[r] + counts[r])
-static uint64_t collect_hits_by_read(real_gpu * h)
+static uint64_t collect_hits_by_read(real_gpu * h, int mode = 0)
 {
         if ( h->hit_cap == 0 )
         {
                 h->hit_cap = std::max<uint64_t>(1u << 16, 2 * h->nreads);
                 dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
         }
-        uint64_t found = run_scan(h, 0);
+        uint64_t found = run_scan(h, mode);
         if ( found > h->hit_cap )
         {
                 // the buffer was too small: the kernel counted everything, so size it exactly and rescan
                 h->hit_cap = found + found / 8 + 1024;
                 dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
-                found = run_scan(h, 0);
+                found = run_scan(h, mode);
                 if ( found > h->hit_cap ) throw CudaError("hit count changed between scans");
         }
         if ( found >= (1ULL << 32) ) throw CudaError("more than 2^32 hits in one call");
@@ -656,7 +661,7 @@ static uint64_t collect_hits_by_read(real_gpu * h)
         RG_CUDA(cudaMemsetAsync(h->counts.p, 0, h->nreads * 4 + 16, h->st));
         if ( found )
         {
-                if ( h->prm.scores )
+                if ( h->prm.scores && mode == 0 )
                 {
                         k_score_hits<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<double>(h->ll),
                                 ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, h->shard_begin, ptr<uint64_t>(h->rpack), h->W, ptr<uint32_t>(h->rlen),
@@ -804,6 +809,7 @@ int real_gpu_reset_unique(real_gpu * h)
         RG_API_BEGIN(h)
         if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
         RG_CUDA(cudaMemsetAsync(h->info.p, 0, (size_t)h->nreads * 8 + 16, h->st));
+        if ( h->gaps.p ) RG_CUDA(cudaMemsetAsync(h->gaps.p, 0, (size_t)h->nreads * sizeof(real_gpu_gapinfo) + 16, h->st));
         if ( h->prm.scores )
         {
                 k_fill_f32<<<blocks_for(h->nreads + 1, 256), 256, 0, h->st>>>(ptr<float>(h->scores), h->nreads, -FLT_MAX);
@@ -866,14 +872,57 @@ int real_gpu_unique_import(real_gpu * h, const uint64_t * d_min_keys, const uint
         RG_API_END(h)
 }
 
-int real_gpu_match_gaps(real_gpu * h, uint64_t)
+int real_gpu_match_gaps(real_gpu * h, uint64_t n_list_windows)
 {
-        return fail(h, REAL_GPU_E_ARG, "match_gaps: the gapped extension kernel is not built in this version");
+        RG_API_BEGIN(h)
+        int const rc = check_ready(h);
+        if ( rc ) return rc;
+        if ( ! h->ll.p )
+                return fail(h, REAL_GPU_E_ARG, "match_gaps needs the scoring table (real_gpu_params::ll_table)");
+        if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
+                return fail(h, REAL_GPU_E_ARG, "match_gaps needs the whole file in one shard (the fold is order dependent)");
+        if ( h->nrec + 1 > 65536 )
+                return REAL_GPU_OK;
+        if ( n_list_windows ) h->n_list = n_list_windows;
+        h->stats.scan_launches = 0;
+        uint64_t const found = collect_hits_by_read(h, 2);
+        if ( found )
+        {
+                dev_reserve(h, h->gapres, found * sizeof(GapRes) + 64);
+                GapParams G;
+                G.seg = ptr<RawHit>(h->hits_seg); G.ncand = found; G.ll = ptr<double>(h->ll);
+                G.text = ptr<uint64_t>(h->text) + TEXT_PAD_WORDS; G.nmask = ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS; G.shard_begin = h->shard_begin;
+                G.rec = ptr<uint64_t>(h->rec); G.nrec = h->nrec;
+                G.rpack = ptr<uint64_t>(h->rpack); G.W = h->W; G.rlen = ptr<uint32_t>(h->rlen);
+                G.quality = h->qual_present ? ptr<uint8_t>(h->qual) : nullptr; G.offsets = ptr<uint64_t>(h->offs);
+                G.seedl = h->prm.seedl; G.scores = h->prm.scores;
+                G.res = ptr<GapRes>(h->gapres);
+                k_gap_dp<<<blocks_for(found, 128), 128, 0, h->st>>>(G);
+                RG_KERNEL_CHECK(); launch_count(h);
+                uint32_t const nb = block_bounds(h);
+                GapReplayParams R;
+                R.seg = ptr<RawHit>(h->hits_seg); R.res = ptr<GapRes>(h->gapres); R.starts = ptr<uint32_t>(h->starts); R.counts = ptr<uint32_t>(h->counts);
+                R.nreads = h->nreads; R.scores = h->prm.scores;
+                R.bounds = nb > 1 ? ptr<uint64_t>(h->bounds) : nullptr; R.nblocks = nb;
+                R.info = ptr<unsigned long long>(h->info); R.score = ptr<float>(h->scores); R.gaps = ptr<real_gpu_gapinfo>(h->gaps);
+                k_gap_replay<<<blocks_for(h->nreads, 128), 128, 0, h->st>>>(R);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.post_ms = elapsed(h->ev[0], h->ev[1]);
+        return REAL_GPU_OK;
+        RG_API_END(h)
 }
 
-int real_gpu_get_gaps(real_gpu * h, real_gpu_gapinfo *)
+int real_gpu_get_gaps(real_gpu * h, real_gpu_gapinfo * gaps)
 {
-        return fail(h, REAL_GPU_E_ARG, "get_gaps: the gapped extension kernel is not built in this version");
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( ! gaps ) return fail(h, REAL_GPU_E_ARG, "get_gaps: null pointer");
+        if ( h->nreads ) RG_CUDA(cudaMemcpy(gaps, h->gaps.p, h->nreads * sizeof(real_gpu_gapinfo), cudaMemcpyDeviceToHost));
+        return REAL_GPU_OK;
+        RG_API_END(h)
 }
 
 int real_gpu_get_stats(real_gpu * h, real_gpu_stats * out)

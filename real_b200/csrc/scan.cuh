@@ -80,7 +80,7 @@ struct ScanParams
         uint32_t * bucket_start;      // [SC_MAX_BUCKETS+1] record index
         uint32_t * bucket_cursor;     // [SC_MAX_BUCKETS]
         uint32_t * unit_counter;      // work distribution of k_bucket_probe
-        int mode;                     // 0 = report all hits, 1 = fold into the unique state, 2 = gapped seed candidates
+        int mode;                     // 0 = report all hits, 1 = fold into the unique state, 2 = seed candidates of the gapped pass
         RawHit * hits;
         unsigned long long hit_cap;
         unsigned long long * hit_count;
@@ -472,6 +472,30 @@ __device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t
 {
         uint32_t const strand = id & 1;
         uint32_t const read = id >> 1;
+        if ( P.mode == 2 )
+        {
+                // gapped pass (match.hpp:477-499): only the seed is required to match; '+' strand only; reads still
+                // NoMatch/Gapped; the seed window must lie inside one record and be wildcard free
+                if ( strand ) return;
+                uint32_t const st = umi_state(P.info[read]);
+                if ( st != ST_NOMATCH && st != ST_GAPPED ) return;
+                uint64_t const grpos = P.shard_begin + lp;
+                if ( grpos < P.own_begin || grpos >= P.own_end ) return;
+                uint32_t const gfrag = record_of(P.rec, P.nrec, grpos);
+                if ( gfrag >= P.nrec || grpos + P.seedl > __ldg(P.rec + gfrag + 1) ) return;
+                if ( ! wildcard_free(P.nmask, lp, P.seedl) ) return;
+                lstats[2] += 1;
+                unsigned long long const slot = atomicAdd(P.hit_count, 1ULL);
+                if ( slot < P.hit_cap )
+                {
+                        RawHit h;
+                        h.pm = rawhit_pack(grpos, 0, 0, gfrag);
+                        h.read = read | (exact << 28);
+                        h.score = 0.0f;
+                        P.hits[slot] = h;
+                }
+                return;
+        }
         uint32_t const L = __ldg(P.rlen + read);
         uint32_t const matchoffset = strand ? (L - P.seedl) : 0;          // RestMatch.hpp:84-89
         uint64_t const gp = P.shard_begin + lp;

@@ -231,6 +231,14 @@ class Handle:
     def unique_import(self, d_min_keys: int, d_tie_sums: int):
         self._check(self.L.real_gpu_unique_import(self.h, d_min_keys, d_tie_sums))
 
+    def match_gaps(self, n_list: int = 0):
+        self._check(self.L.real_gpu_match_gaps(self.h, n_list))
+
+    def get_gaps(self) -> np.ndarray:
+        g = np.zeros(self.nreads, dtype=GAP_DTYPE)
+        self._check(self.L.real_gpu_get_gaps(self.h, g.ctypes.data))
+        return g
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self.L.real_gpu_get_stats(self.h, C.byref(s)))

@@ -265,6 +265,13 @@ class UniqueMatcher(MatcherBase):
     def reset(self):
         self.handle.reset_unique()
 
+    def matchGaps(self, n_list: int = 0):
+        """UniqueMatcher::matchGaps for every read still NoMatch/Gapped (matchUniqueImplementation.cpp:501-572)."""
+        self.handle.match_gaps(n_list)
+
+    def gaps(self):
+        return self.handle.get_gaps()
+
 
 # UniqueMatchInfo field access (UniqueMatchInfo.hpp:26-39) on numpy arrays
 def umi_state(d): return (np.asarray(d, dtype=np.uint64) >> np.uint64(61)).astype(np.int64)
