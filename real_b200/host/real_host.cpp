@@ -608,6 +608,34 @@ int doMatchingAll(RealOptions const & opts)
         return EXIT_SUCCESS;
 }
 
+// The reference's memory planner (matchUniqueImplementation.cpp:1208-1244): how many seed windows one text-side
+// index block holds.  Only the order-dependent folds (scores, gaps) depend on it.  The byte counts of the
+// reference's text and rank structures are restated approximately; REAL_NLIST pins the value.
+static uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, uint64_t nreads)
+{
+        if ( char const * e = getenv("REAL_NLIST") ) return strtoull(e, 0, 10);
+        long const pages = sysconf(_SC_PHYS_PAGES), pagesize = sysconf(_SC_PAGE_SIZE);
+        uint64_t const usemem = (uint64_t)((double)pages * (double)pagesize * opts.fracmem);
+        uint64_t const bits = ((T.n + 63) / 64) * 64;
+        uint64_t const rank = (bits / 65536 + 1) * 8 + (bits / 64) * 2;
+        uint64_t const textmemory = T.n / 4 + bits / 8 + rank + 16;
+        uint64_t const rangevectormemory = bits / 8 + rank + 8;
+        uint64_t const lookupmemory = 2ULL * 6 * (1ULL << 22) * sizeof(size_t);
+        uint64_t const uniqueinfomemory = nreads * (opts.scores ? 16 : 8);
+        uint64_t const nonlist = textmemory + rangevectormemory + lookupmemory + uniqueinfomemory;
+        if ( nonlist > usemem )
+                throw std::runtime_error("Insufficient memory.");
+        uint64_t const elementmemory = opts.seedl <= 32 ? 72 : 112;
+        uint64_t const n_list_max = (usemem - nonlist) / elementmemory;
+        if ( ! n_list_max )
+                throw std::runtime_error("Insufficient memory.");
+        uint64_t const expblocks = (T.n - opts.seedl + 1 + (n_list_max - 1)) / n_list_max;
+        std::cerr << "Expected number of blocks = " << expblocks << std::endl;
+        uint64_t const n_list = (T.n + (expblocks - 1)) / expblocks;
+        std::cerr << "Using n_list = " << n_list << std::endl;
+        return n_list;
+}
+
 int doMatchingUnique(RealOptions const & opts)
 {
         ReadSet reads;
@@ -634,10 +662,25 @@ int doMatchingUnique(RealOptions const & opts)
                         continue;
                 std::vector<uint64_t> const starts = T.starts();
                 G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
+                if ( opts.scores )
+                        G.check(real_gpu_set_block_windows(G.h, planBlockWindows(opts, T, reads.size())), "set_block_windows");
                 G.check(real_gpu_match_unique(G.h), "match_unique");
         }
         if ( opts.gaps )
-                G.check(real_gpu_match_gaps(G.h, 0), "match_gaps");
+        {
+                // second pass over all files for the reads still unmatched (matchUniqueImplementation.cpp:1302-1436);
+                // like the reference the results are computed but not printed (the stock CLI has no output for them)
+                for ( size_t fi = 0; fi < filenames.size(); ++fi )
+                {
+                        TextFile T;
+                        getText(filenames[fi], T);
+                        if ( fi >= 64 || T.n >= (1ULL << 35) || T.ranges.size() > 65536 || T.n < (uint64_t)opts.seedl )
+                                continue;
+                        std::vector<uint64_t> const starts = T.starts();
+                        G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
+                        G.check(real_gpu_match_gaps(G.h, planBlockWindows(opts, T, reads.size())), "match_gaps");
+                }
+        }
         std::vector<uint64_t> info(reads.size() + 1);
         std::vector<float> score(reads.size() + 1);
         G.check(real_gpu_get_unique(G.h, &info[0], opts.scores ? &score[0] : 0), "get_unique");

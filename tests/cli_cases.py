@@ -5,7 +5,7 @@ import numpy as np
 
 from real_b200 import synth
 
-CASES = ["unique_fa_R1", "unique_fq_R0", "unique_dir_ragged"]
+CASES = ["unique_fa_R1", "unique_fq_R0", "unique_dir_ragged", "unique_fq_scores_default"]
 
 
 def make_case(name, work):
@@ -51,4 +51,17 @@ def make_case(name, work):
         rf = os.path.join(work, "r.fa")
         synth.write_reads(rf, reads, False)
         return tdir, rf, ["-e", "2", "-q", "0"]
+    if name == "unique_fq_scores_default":
+        # the stock default mode: -u 1 -q 1 -R 1 (quality-aware scores, epsilon filter level 2)
+        text = synth.make_text(331, 90000, nrecords=2, n_per_million=1000)
+        sym = text.symbols.copy()
+        seg = sym[3000:9000].copy()
+        seg[::97] = (seg[::97] + 1) % 4
+        sym[50000:56000] = seg
+        text = synth.Text(sym, text.records)
+        reads = synth.concat_reads([synth.make_reads(text, 332, 700, 100, 0.015, True), synth.make_reads(text, 333, 300, 64, 0.02, True)])
+        synth.write_fasta(os.path.join(work, "t.fa"), text)
+        rf = os.path.join(work, "r.fq")
+        synth.write_reads(rf, reads, True)
+        return os.path.join(work, "t.fa"), rf, ["-e", "4", "-Q", "33"]
     raise KeyError(name)
