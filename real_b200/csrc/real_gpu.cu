@@ -242,7 +242,11 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         uint64_t const etiles = (EP.nids + EP_TILE_IDS - 1) / EP_TILE_IDS;
         k_ent_scatter<<<(unsigned)std::min<uint64_t>(etiles, (uint64_t)h->sm_count * occ), 256, esmem, h->st>>>(EP);
         RG_KERNEL_CHECK();
-        k_build_bits<<<grid, 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap));
+        int occ_bits = 0, occ_ent = 0;
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bits, k_build_bits, 256, 0));
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ent, k_build_entries, 256, 0));
+        // one resident wave each: the grid-stride sweep then passes over the buckets exactly once
+        k_build_bits<<<(unsigned)(h->sm_count * std::max(1, occ_bits)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap));
         RG_KERNEL_CHECK();
         launch_count(h, 4);
 
@@ -257,7 +261,7 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         RG_KERNEL_CHECK(); launch_count(h);
 
         RG_CUDA(cudaMemsetAsync(T.E.p, 0xFF, cap_entries * sizeof(Entry), h->st));
-        k_build_entries<<<grid, 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap), (uint32_t)cap_entries, ptr<Entry>(T.E));
+        k_build_entries<<<(unsigned)(h->sm_count * std::max(1, occ_ent)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap), (uint32_t)cap_entries, ptr<Entry>(T.E));
         RG_KERNEL_CHECK(); launch_count(h);
         RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
 }
