@@ -197,10 +197,10 @@ def main():
     ap.add_argument("--table-bits", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-text", type=int, default=16_000_000, help="reference arm: text bases of the sample")
-    ap.add_argument("--ref-reads", type=int, default=400_000, help="reference arm: reads of the sample")
-    ap.add_argument("--cpu-text", type=int, default=4_000_000)
-    ap.add_argument("--cpu-reads", type=int, default=100_000)
+    ap.add_argument("--ref-text", type=int, default=32_000_000, help="reference arm: text bases of the sample")
+    ap.add_argument("--ref-reads", type=int, default=500_000, help="reference arm: reads of the sample")
+    ap.add_argument("--cpu-text", type=int, default=16_000_000)
+    ap.add_argument("--cpu-reads", type=int, default=250_000)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.warmup < 3 and args.impl == "ours":
@@ -344,25 +344,38 @@ def main():
     # ---- e2e: host buffers through the host-pointer ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        h_mapped = torch.empty(R * L, dtype=torch.uint8).pin_memory()
-        h_mapped.copy_(mapped)
+        # reads cross PCIe 2 bit/base, the layout of the reference's own rewritten pattern file (-R 1, the default of
+        # matchUnique; TemporaryFile.hpp:231-268); qualities (only with scores) stay 1 byte/base
+        L4 = (L + 3) // 4
+        m2 = mapped.view(R, L)
+        if L % 4:
+            m2 = torch.nn.functional.pad(m2, (0, 4 * L4 - L))
+        m2 = (m2 & 3).view(R, L4, 4)
+        d_packed = ((m2[:, :, 0] << 6) | (m2[:, :, 1] << 4) | (m2[:, :, 2] << 2) | m2[:, :, 3]).contiguous().view(-1)
+        d_flags = (mapped.view(R, L) > 3).any(dim=1).to(torch.uint8)
+        h_mapped = torch.empty(R * L4, dtype=torch.uint8).pin_memory()
+        h_mapped.copy_(d_packed)
+        h_flags = torch.empty(R, dtype=torch.uint8).pin_memory()
+        h_flags.copy_(d_flags)
+        del m2, d_packed, d_flags
+        torch.cuda.empty_cache()
         h_qual = None
         if qual is not None:
             h_qual = torch.empty(R * L, dtype=torch.uint8).pin_memory()
             h_qual.copy_(qual)
-        h_offs = (np.arange(R + 1, dtype=np.uint64) * np.uint64(L))
         h_w = sh_w.cpu().pin_memory()
         h_m = sh_m.cpu().pin_memory()
         h_info = torch.empty(R, dtype=torch.int64).pin_memory()
         np_w = h_w.numpy().view(np.uint64)
         np_m = h_m.numpy().view(np.uint64)
         np_mapped = h_mapped.numpy()
+        np_flags = h_flags.numpy()
         np_qual = h_qual.numpy() if h_qual is not None else None
         np_info = h_info.numpy().view(np.uint64)
         d2h = [0]
 
         def step_host():
-            h.set_reads(np_mapped, h_offs, np_qual)
+            h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
             h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
             if unique:
                 h.match_unique()
@@ -378,10 +391,12 @@ def main():
 
         e_steps = max(1, min(args.steps, 3))
         e_ms, _ = timed(step_host, e_steps, 1)
-        h2d = R * L * (2 if qual is not None else 1) + (R + 1) * 8 + np_w.nbytes + np_m.nbytes + rs.nbytes
+        h2d = R * L4 + R + (R * L if qual is not None else 0) + np_w.nbytes + np_m.nbytes + rs.nbytes
         e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-               "ms_per_step": e_ms / e_steps, "steps": e_steps}
-        del h_mapped, h_qual, h_w, h_m
+               "ms_per_step": e_ms / e_steps, "steps": e_steps,
+               "input": "host buffers: text 2 bit/base + N mask, reads 2 bit/base (the reference's rewritten pattern file layout), "
+                        "qualities 1 byte/base when scoring; result read back to pinned host memory"}
+        del h_mapped, h_qual, h_w, h_m, h_flags
 
     dev_bytes = h.device_bytes()
     h.close()

@@ -148,6 +148,16 @@ int real_gpu_set_text_device(real_gpu * h, uint32_t fileid,
  * Limits: nreads < 2^28, read length <= 65535. */
 int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * quality,
                        const uint64_t * offsets, uint64_t nreads);
+/* Same as real_gpu_set_reads for reads that are already packed 2 bit/base the way the reference's rewritten pattern
+ * file stores them (-R 1, TemporaryFile.hpp:231-268 writePatternDontCareFree): 4 bases per byte, first base in bits 7..6,
+ * every read starting on a byte boundary.  A quarter of the host-to-device traffic of the byte-per-base form.
+ *   byte_offsets   nreads+1 offsets into packed, lengths nreads base counts; both may be NULL when uniform_length != 0
+ *                  (all reads have that many bases and are stored back to back, ceil(L/4) bytes each)
+ *   wildcard_flags nreads bytes, non-zero = the read contains a wildcard (such reads never match; the reference
+ *                  keeps them in a separate 4 bit/base section) or NULL
+ *   quality        one byte per BASE, reads back to back (as in real_gpu_set_reads), or NULL */
+int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64_t * byte_offsets, const uint32_t * lengths,
+                              uint32_t uniform_length, const uint8_t * wildcard_flags, const uint8_t * quality, uint64_t nreads);
 int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint8_t * d_quality,
                               const uint64_t * d_offsets, uint64_t nreads, uint64_t total_bases, uint32_t maxlen);
 

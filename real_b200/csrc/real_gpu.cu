@@ -65,10 +65,11 @@ struct real_gpu
 
         // results
         DevBuf rec_win, rec_pos, part_meta;
-        DevBuf win_valid, win_counts, bounds, gapres, gaps;   // reference text blocks (order-faithful replay)
+        DevBuf win_valid, win_counts, bounds, gapres, gaps, boffs, flags8;   // reference text blocks (order-faithful replay)
         uint64_t n_list;               // windows per reference text block, 0 = one block per file
         DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
         uint32_t table_counts[6];      // per table: entries, distinct slots (read back after the build)
+        const uint8_t * src_packed; const uint64_t * src_byte_offsets; uint32_t src_packed_uniform;   // 2-bit input (set_reads_packed)
         const uint8_t * src_mapped;    // device pointer the reads are packed from (caller's buffer or h->mapped)
         DevBuf ll, hits_raw, hits_seg, hits_out, counters, counts, starts, cursor, scantmp, info, scores;
         uint64_t hit_cap;
@@ -80,7 +81,7 @@ struct real_gpu
         uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
 
-        real_gpu() : n_list(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -280,11 +281,16 @@ int build_from_device(real_gpu * h)
         dev_reserve(h, h->seeds, (size_t)nreads * 2 * 8 + 16);
         dev_reserve(h, h->usable, (size_t)nreads * 4 + 16);
         dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
-        RG_CUDA(cudaMemsetAsync(h->bad.p, 0, (size_t)nreads * 4 + 16, h->st));
+        if ( ! h->src_packed )
+                RG_CUDA(cudaMemsetAsync(h->bad.p, 0, (size_t)nreads * 4 + 16, h->st));
         if ( nreads )
         {
-                k_pack_reads<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W,
-                                                                                  ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->bad));
+                if ( h->src_packed )
+                        k_pack_reads_packed<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_packed, h->src_byte_offsets, h->src_packed_uniform ? nullptr : ptr<uint64_t>(h->offs),
+                                                                                                 h->src_packed_uniform, nreads, h->W, ptr<uint64_t>(h->rpack));
+                else
+                        k_pack_reads<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W,
+                                                                                          ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->bad));
                 RG_KERNEL_CHECK(); launch_count(h);
                 k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
                                                                        ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
@@ -541,7 +547,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
@@ -590,7 +596,7 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
         dev_reserve(h, h->mapped, total + 64);
         dev_reserve(h, h->offs, (nreads + 1) * 8);
-        h->src_mapped = ptr<uint8_t>(h->mapped);
+        h->src_mapped = ptr<uint8_t>(h->mapped); h->src_packed = nullptr;
         if ( total ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, mapped + offsets[0], total, cudaMemcpyHostToDevice, h->st));
         if ( offsets[0] != 0 )
         {
@@ -625,6 +631,7 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
         h->have_reads = false;
         h->nreads = nreads; h->total_bases = total_bases; h->maxlen = maxlen;
         dev_reserve(h, h->offs, (nreads + 1) * 8);
+        h->src_packed = nullptr;
         h->src_mapped = d_mapped;          // packed before this call returns; the caller's buffer is not referenced afterwards
         RG_CUDA(cudaMemcpyAsync(h->offs.p, d_offsets, (nreads + 1) * 8, cudaMemcpyDeviceToDevice, h->st));
         h->qual_present = false;
@@ -635,6 +642,74 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
                 h->qual_present = true;
         }
         h->stats.h2d_reads_ms = 0;
+        return build_from_device(h);
+        RG_API_END(h)
+}
+
+int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64_t * byte_offsets, const uint32_t * lengths, uint32_t uniform_length,
+                              const uint8_t * wildcard_flags, const uint8_t * quality, uint64_t nreads)
+{
+        RG_API_BEGIN(h)
+        if ( nreads && ! packed ) return fail(h, REAL_GPU_E_ARG, "set_reads_packed: null pointer");
+        if ( ! uniform_length && (! byte_offsets || ! lengths) ) return fail(h, REAL_GPU_E_ARG, "set_reads_packed: offsets and lengths are needed unless uniform_length is given");
+        if ( nreads >= (1ULL << 28) ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: more than 2^28 reads in one set");
+        std::vector<uint64_t> boffs, offs;
+        uint32_t maxlen = uniform_length;
+        uint64_t total = (uint64_t)uniform_length * nreads, total_bytes = (uint64_t)((uniform_length + 3) / 4) * nreads;
+        if ( ! uniform_length )
+        {
+                offs.resize(nreads + 1); offs[0] = 0;
+                for ( uint64_t i = 0; i < nreads; ++i )
+                {
+                        if ( lengths[i] > 65535 ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: read longer than 65535 bases");
+                        maxlen = std::max(maxlen, lengths[i]);
+                        offs[i+1] = offs[i] + lengths[i];
+                }
+                total = offs[nreads];
+                total_bytes = byte_offsets[nreads] - byte_offsets[0];
+                boffs.resize(nreads + 1);
+                for ( uint64_t i = 0; i <= nreads; ++i ) boffs[i] = byte_offsets[i] - byte_offsets[0];
+        }
+        else if ( uniform_length > 65535 ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: read longer than 65535 bases");
+        h->have_reads = false;
+        h->nreads = nreads; h->total_bases = total; h->maxlen = maxlen;
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        dev_reserve(h, h->mapped, total_bytes + 64);
+        dev_reserve(h, h->offs, (nreads + 1) * 8);
+        dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
+        if ( total_bytes ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, packed + (uniform_length ? 0 : byte_offsets[0]), total_bytes, cudaMemcpyHostToDevice, h->st));
+        h->src_packed = ptr<uint8_t>(h->mapped); h->src_mapped = nullptr; h->src_packed_uniform = uniform_length; h->src_byte_offsets = nullptr;
+        if ( uniform_length )
+        {
+                k_uniform_offsets<<<blocks_for(nreads + 1, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, uniform_length);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        else
+        {
+                dev_reserve(h, h->boffs, (nreads + 1) * 8);
+                RG_CUDA(cudaMemcpyAsync(h->offs.p, offs.data(), (nreads + 1) * 8, cudaMemcpyHostToDevice, h->st));
+                RG_CUDA(cudaMemcpyAsync(h->boffs.p, boffs.data(), (nreads + 1) * 8, cudaMemcpyHostToDevice, h->st));
+                h->src_byte_offsets = ptr<uint64_t>(h->boffs);
+        }
+        if ( wildcard_flags && nreads )
+        {
+                dev_reserve(h, h->flags8, nreads + 64);
+                RG_CUDA(cudaMemcpyAsync(h->flags8.p, wildcard_flags, nreads, cudaMemcpyHostToDevice, h->st));
+                k_flags_to_bad<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint8_t>(h->flags8), nreads, ptr<uint32_t>(h->bad));
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        else
+                RG_CUDA(cudaMemsetAsync(h->bad.p, 0, (size_t)nreads * 4 + 16, h->st));
+        h->qual_present = false;
+        if ( quality && (h->prm.scores || h->ll.p) )
+        {
+                dev_reserve(h, h->qual, total + 64);
+                if ( total ) RG_CUDA(cudaMemcpyAsync(h->qual.p, quality, total, cudaMemcpyHostToDevice, h->st));
+                h->qual_present = true;
+        }
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));      // the staging vectors above must outlive the copies
+        h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
         return build_from_device(h);
         RG_API_END(h)
 }

@@ -88,6 +88,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_set_text_device.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_reads.argtypes = [vp, vp, vp, vp, u64]
     L.real_gpu_set_reads_device.argtypes = [vp, vp, vp, vp, u64, u64, u32]
+    L.real_gpu_set_reads_packed.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64]
     L.real_gpu_match_all.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.real_gpu_match_unique.argtypes = [vp]
     L.real_gpu_get_unique.argtypes = [vp, vp, vp]
@@ -185,6 +186,15 @@ class Handle:
             q = quality.ctypes.data
         self.nreads = int(offsets.size - 1)
         self._check(self.L.real_gpu_set_reads(self.h, mapped.ctypes.data if mapped.size else None, q, offsets.ctypes.data, self.nreads))
+
+    def set_reads_packed(self, packed: np.ndarray, nreads: int, uniform_length: int = 0, byte_offsets: np.ndarray | None = None,
+                         lengths: np.ndarray | None = None, wildcard_flags: np.ndarray | None = None, quality: np.ndarray | None = None):
+        self.nreads = nreads
+        p = lambda a, dt: (None if a is None else _np_ptr(np.ascontiguousarray(a, dtype=dt), dt))
+        keep = [np.ascontiguousarray(a, dtype=dt) if a is not None else None
+                for a, dt in ((packed, np.uint8), (byte_offsets, np.uint64), (lengths, np.uint32), (wildcard_flags, np.uint8), (quality, np.uint8))]
+        ptrs = [a.ctypes.data if a is not None else None for a in keep]
+        self._check(self.L.real_gpu_set_reads_packed(self.h, ptrs[0], ptrs[1], ptrs[2], uniform_length, ptrs[3], ptrs[4], nreads))
 
     def set_reads_device(self, d_mapped: int, d_offsets: int, nreads: int, total_bases: int, maxlen: int, d_quality: int | None = None):
         self.nreads = nreads

@@ -276,3 +276,25 @@ def write_reads(path: str, reads: Reads, fastq: bool, qoffset: int = 33) -> None
 def tmp_path(dirname: str, name: str) -> str:
     os.makedirs(dirname, exist_ok=True)
     return os.path.join(dirname, name)
+
+
+def pack_reads_2bit(reads: Reads):
+    """Reads in the layout of the reference's rewritten pattern file (TemporaryFile.hpp:231-268): 4 bases per byte,
+    first base in bits 7..6, every read on a byte boundary.  Returns (packed, byte_offsets, lengths, wildcard_flags);
+    reads with a wildcard are flagged and their bases stored as A."""
+    n = reads.nreads
+    lens = np.diff(reads.offsets.astype(np.int64)).astype(np.int64)
+    nbytes = (lens + 3) // 4
+    boffs = np.concatenate([np.zeros(1, np.int64), np.cumsum(nbytes)]).astype(np.uint64)
+    packed = np.zeros(int(boffs[-1]), dtype=np.uint8)
+    flags = np.zeros(n, dtype=np.uint8)
+    for r in range(n):
+        s = reads.read(r)
+        if (s > 3).any():
+            flags[r] = 1
+            s = np.where(s > 3, 0, s)
+        pad = np.zeros(int(nbytes[r]) * 4, dtype=np.uint8)
+        pad[:len(s)] = s
+        q = pad.reshape(-1, 4)
+        packed[int(boffs[r]):int(boffs[r + 1])] = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
+    return packed, boffs, lens.astype(np.uint32), flags
