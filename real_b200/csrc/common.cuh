@@ -35,9 +35,14 @@ struct CudaError : public std::runtime_error
 // extracts and tile halos never leave the allocation
 static const uint32_t TEXT_PAD_WORDS = 64;
 
-// presence-table sector: 32 bytes = rank header + 224 slot bits
-static const uint32_t SECTOR_SLOTS = 224;
-static const uint32_t SECTOR_WORDS = 8;
+// presence table: one 8-byte word per 32 slots = {presence bits, rank of the word's first slot}; a probe is ONE
+// 8-byte load that yields both the bit and, if it is set, the index of the slot's entry
+struct __align__(8) SlotWord
+{
+        uint32_t bits;
+        uint32_t rank;
+};
+static const uint32_t RANK_BLOCK_WORDS = 2048;      // slot words per block of the ranking kernels (tables are padded to it)
 
 static const uint32_t ENTRY_NONE = 0xFFFFFFFFu;
 
@@ -142,10 +147,30 @@ __device__ __forceinline__ uint64_t policy_evict_last()
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
         return pol;
 }
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        return pol;
+}
 __device__ __forceinline__ uint32_t ld_hot_u32(const uint32_t * p, uint64_t pol)
 {
         uint32_t v;
         asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+        return v;
+}
+// probe of the presence table: a plain load (normal L2 priority).  The touch-once streams that pass through L2 at
+// the same time (text records, entries) are loaded evict_first, which is what keeps the probed slice resident.
+__device__ __forceinline__ SlotWord ld_slotword(const SlotWord * p)
+{
+        SlotWord v;
+        asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.bits), "=r"(v.rank) : "l"(p));
+        return v;
+}
+__device__ __forceinline__ SlotWord ld_hot_slotword(const SlotWord * p, uint64_t pol)
+{
+        SlotWord v;
+        asm volatile("ld.global.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.bits), "=r"(v.rank) : "l"(p), "l"(pol));
         return v;
 }
 __device__ __forceinline__ uint4 ld_hot_v4(const void * p, uint64_t pol)

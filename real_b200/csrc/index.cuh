@@ -12,8 +12,9 @@
 //   table A (adjacent fragments)  key(x) = bases [x,x+2F)               lists 0,3,5 at window x, x-F, x-2F
 //   table B (one fragment apart)  key(x) = [x,x+F) ++ [x+2F,x+3F)       lists 1,4   at window x, x-F
 //   table C (two apart)           key(x) = [x,x+F) ++ [x+3F,x+4F)       list  2     at window x
-// Each table is a presence bitmap over signature slots, cut into 32-byte sectors of
-// {u32 rank of the first slot, 224 slot bits}, plus an entry array addressed by rank.
+// Each table is a presence array over signature slots -- one 8-byte SlotWord {32 presence bits, rank of the
+// word's first slot} per 32 slots, so that one 8-byte probe yields the bit and the entry index -- plus an
+// entry array addressed by rank.
 #pragma once
 
 #include "common.cuh"
@@ -383,14 +384,13 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
 
 // presence bits of the grouped entries (reductions into the L2-resident slice)
 __global__ void __launch_bounds__(256) k_build_bits(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ total,
-                                                  TableGeom G, uint32_t * __restrict__ bitmap)
+                                                  TableGeom G, SlotWord * __restrict__ slots)
 {
         uint32_t const n = *total;
         for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
         {
                 uint32_t const h = entry_slot(__ldcs(ent_seed + i), G, __ldcs(ent_val + i) & 3);
-                uint32_t const sector = h / SECTOR_SLOTS, slot = h - sector * SECTOR_SLOTS;
-                atomicOr(&bitmap[(uint64_t)sector * SECTOR_WORDS + 1 + (slot >> 5)], 1u << (slot & 31));
+                atomicOr(&slots[h >> 5].bits, 1u << (h & 31));
         }
 }
 
@@ -398,9 +398,29 @@ __global__ void __launch_bounds__(256) k_build_bits(const uint64_t * __restrict_
 // at E[ovf_base + i] (i = its index in the grouped array: no allocation counter, and still inside the
 // bucket's address range) and linked in front of the head's chain.  A single global overflow counter was
 // measured at ~4 ns per (same-address) atomic: 75 ms for the 19 M warps of a 600 M entry build.
+//
+// The claims of a bucket land all over its slice of E, and each one first pulls its (freshly memset) sector out
+// of DRAM -- at the random-sector rate that was most of this kernel's time.  So while the grid sweeps bucket b it
+// also streams bucket b+1's slice of E into L2 with line prefetches, one 128-byte line per 8 entries processed
+// (the grid walks the grouped entries front to back, so "the entry at fraction f of bucket b" prefetches "the line
+// at fraction f of bucket b+1's slice").  bucket_start = the partition's 257 bucket offsets; bucket_shift =
+// hb - log2(buckets), 0 = no prefetching.
 __global__ void __launch_bounds__(256) k_build_entries(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ total,
-                                                     TableGeom G, const uint32_t * __restrict__ bitmap, uint32_t ovf_base, Entry * __restrict__ E)
+                                                     TableGeom G, const SlotWord * __restrict__ slots, uint32_t ovf_base, Entry * __restrict__ E,
+                                                     const uint32_t * __restrict__ bucket_start, uint32_t nbuckets, uint32_t bucket_shift)
 {
+        __shared__ uint32_t bs[EP_MAX_BUCKETS + 1];       // first grouped entry of a bucket
+        __shared__ uint32_t rs[EP_MAX_BUCKETS + 1];       // first rank (= index into E) of a bucket
+        bool const pf = bucket_shift >= 5 && nbuckets > 1;
+        if ( pf )
+        {
+                for ( uint32_t b = threadIdx.x; b <= nbuckets; b += blockDim.x )
+                {
+                        bs[b] = bucket_start[b];
+                        rs[b] = (b < nbuckets) ? slots[((uint64_t)b << bucket_shift) >> 5].rank : 0xFFFFFFFFu;
+                }
+                __syncthreads();
+        }
         uint32_t const n = *total;
         uint64_t const pol = policy_evict_last();
         for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
@@ -408,18 +428,21 @@ __global__ void __launch_bounds__(256) k_build_entries(const uint64_t * __restri
                 uint64_t const seed = __ldcs(ent_seed + i);
                 uint32_t const val = __ldcs(ent_val + i);
                 uint32_t const h = entry_slot(seed, G, val & 3);
-                uint32_t const sector = h / SECTOR_SLOTS, slot = h - sector * SECTOR_SLOTS;
-                const uint4 * sp = reinterpret_cast<const uint4 *>(bitmap + (uint64_t)sector * SECTOR_WORDS);
-                uint4 const a = ld_hot_v4(sp, pol), b = ld_hot_v4(sp + 1, pol);
-                uint32_t const wv[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-                uint32_t rank = wv[0];
-                uint32_t const wi = slot >> 5;
-                #pragma unroll
-                for ( uint32_t w = 0; w < 7; ++w )
+                if ( pf && (threadIdx.x & 7) == 0 )
                 {
-                        if ( w < wi ) rank += __popc(wv[1+w]);
-                        else if ( w == wi ) rank += __popc(wv[1+w] & ((1u << (slot & 31)) - 1));
+                        uint32_t const b = h >> bucket_shift;
+                        if ( b + 1 < nbuckets )
+                        {
+                                uint32_t const cnt = bs[b+1] - bs[b], f = i - bs[b];
+                                uint32_t const r0 = rs[b+1], r1 = (b + 2 < nbuckets) ? rs[b+2] : r0 + (bs[b+2] - bs[b+1]);
+                                uint32_t const lines = (r1 - r0 + 7) / 8 + 1;
+                                uint32_t const line = (uint32_t)(((uint64_t)(f >> 3) * lines) / ((cnt >> 3) + 1));
+                                if ( line < lines )
+                                        asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(reinterpret_cast<const char *>(E + r0) + (uint64_t)line * 128));
+                        }
                 }
+                SlotWord const sw = ld_hot_slotword(slots + (h >> 5), pol);
+                uint32_t const rank = sw.rank + __popc(sw.bits & ((1u << (h & 31)) - 1));
                 uint32_t const old = atomicCAS(&E[rank].val, ENTRY_NONE, val);
                 if ( old == ENTRY_NONE )
                         E[rank].seed = seed;                    // .next stays ENTRY_NONE until somebody links behind it
@@ -433,28 +456,46 @@ __global__ void __launch_bounds__(256) k_build_entries(const uint64_t * __restri
         }
 }
 
-__global__ void __launch_bounds__(256) k_sector_counts(const uint32_t * __restrict__ bitmap, uint32_t nsectors, uint32_t * __restrict__ counts)
+// Ranks: every block owns RANK_BLOCK_WORDS consecutive slot words (8 per thread).  First pass: presence bits per
+// block; after an exclusive scan of the block sums the second pass writes the rank of every word's first slot.
+__device__ __forceinline__ uint32_t load_block_words(const SlotWord * __restrict__ slots, SlotWord (&w)[8])
 {
-        uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
-        if ( s >= nsectors ) return;
-        const uint4 * p = reinterpret_cast<const uint4 *>(bitmap + (uint64_t)s * SECTOR_WORDS);
-        uint4 const a = p[0], b = p[1];
-        counts[s] = __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+        const uint4 * p = reinterpret_cast<const uint4 *>(slots + ((uint64_t)blockIdx.x * RANK_BLOCK_WORDS + (uint64_t)threadIdx.x * 8));
+        uint32_t c = 0;
+        #pragma unroll
+        for ( int i = 0; i < 4; ++i )
+        {
+                uint4 const v = p[i];
+                w[2*i].bits = v.x; w[2*i].rank = v.y; w[2*i+1].bits = v.z; w[2*i+1].rank = v.w;
+                c += __popc(v.x) + __popc(v.z);
+        }
+        return c;
 }
 
-// rank header of every sector; the last sector also publishes the number of distinct slots
-__global__ void __launch_bounds__(256) k_sector_headers(uint32_t * __restrict__ bitmap, uint32_t nsectors, const uint32_t * __restrict__ ranks,
-                                                      uint32_t * __restrict__ ndistinct)
+__global__ void __launch_bounds__(256) k_word_sums(const SlotWord * __restrict__ slots, uint32_t * __restrict__ block_sums)
 {
-        uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
-        if ( s >= nsectors ) return;
-        uint32_t const r = ranks[s];
-        bitmap[(uint64_t)s * SECTOR_WORDS] = r;
-        if ( s == nsectors - 1 )
+        SlotWord w[8];
+        uint32_t const c = load_block_words(slots, w);
+        uint32_t total;
+        block_excl_scan(c, &total);
+        if ( threadIdx.x == 0 ) block_sums[blockIdx.x] = total;
+}
+
+// the last block also publishes the number of distinct slots
+__global__ void __launch_bounds__(256) k_word_ranks(SlotWord * __restrict__ slots, const uint32_t * __restrict__ block_offsets, uint32_t * __restrict__ ndistinct)
+{
+        SlotWord w[8];
+        uint32_t const c = load_block_words(slots, w);
+        uint32_t total;
+        uint32_t run = block_excl_scan(c, &total) + block_offsets[blockIdx.x];
+        if ( blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 ) *ndistinct = block_offsets[blockIdx.x] + total;
+        uint4 * p = reinterpret_cast<uint4 *>(slots + ((uint64_t)blockIdx.x * RANK_BLOCK_WORDS + (uint64_t)threadIdx.x * 8));
+        #pragma unroll
+        for ( int i = 0; i < 4; ++i )
         {
-                uint32_t c = 0;
-                for ( int w = 1; w < (int)SECTOR_WORDS; ++w ) c += __popc(bitmap[(uint64_t)s * SECTOR_WORDS + w]);
-                *ndistinct = r + c;
+                uint32_t const r0 = run, r1 = run + __popc(w[2*i].bits);
+                run = r1 + __popc(w[2*i+1].bits);
+                p[i] = make_uint4(w[2*i].bits, r0, w[2*i+1].bits, r1);
         }
 }
 

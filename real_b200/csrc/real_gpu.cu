@@ -29,10 +29,10 @@ struct DevBuf
 struct Table
 {
         DevBuf bitmap, E;
-        uint32_t hb, nlists, nsectors;
+        uint32_t hb, nlists, nblocks;
         uint64_t nentries, ndistinct;
         size_t bitmap_bytes;
-        Table() : hb(0), nlists(0), nsectors(0), nentries(0), ndistinct(0), bitmap_bytes(0) {}
+        Table() : hb(0), nlists(0), nblocks(0), nentries(0), ndistinct(0), bitmap_bytes(0) {}
 };
 
 } // namespace
@@ -210,8 +210,9 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         }
         T.ndistinct = 0;
         uint64_t const nslots = 1ULL << T.hb;
-        T.nsectors = (uint32_t)((nslots + SECTOR_SLOTS - 1) / SECTOR_SLOTS);
-        T.bitmap_bytes = (size_t)T.nsectors * SECTOR_WORDS * 4;
+        uint64_t const nwords = (nslots + 31) / 32;
+        T.nblocks = (uint32_t)((nwords + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS);          // padded to whole ranking blocks
+        T.bitmap_bytes = (size_t)T.nblocks * RANK_BLOCK_WORDS * sizeof(SlotWord);
         dev_reserve(h, T.bitmap, T.bitmap_bytes);
         dev_reserve(h, T.E, std::max<size_t>(16, 2 * cap_entries * sizeof(Entry)));   // [0,cap): by rank; [cap,2cap): same-slot overflow, by grouped index
         RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap_bytes, h->st));
@@ -247,22 +248,23 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bits, k_build_bits, 256, 0));
         RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ent, k_build_entries, 256, 0));
         // one resident wave each: the grid-stride sweep then passes over the buckets exactly once
-        k_build_bits<<<(unsigned)(h->sm_count * std::max(1, occ_bits)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap));
+        k_build_bits<<<(unsigned)(h->sm_count * std::max(1, occ_bits)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<SlotWord>(T.bitmap));
         RG_KERNEL_CHECK();
         launch_count(h, 4);
 
-        // rank headers: per-sector popcount -> exclusive scan -> header word (+ number of distinct slots)
+        // ranks: presence bits per block of slot words -> exclusive scan -> rank of every word (+ number of distinct slots)
         uint32_t * cnt = ptr<uint32_t>(h->ws_flags);
-        k_sector_counts<<<blocks_for(T.nsectors, 256), 256, 0, h->st>>>(ptr<uint32_t>(T.bitmap), T.nsectors, cnt);
+        k_word_sums<<<T.nblocks, 256, 0, h->st>>>(ptr<SlotWord>(T.bitmap), cnt);
         RG_KERNEL_CHECK(); launch_count(h);
         uint32_t nl = 0;
-        exclusive_scan_u32(cnt, cnt, T.nsectors, ptr<uint32_t>(h->ws_stmp), h->st, &nl);
+        exclusive_scan_u32(cnt, cnt, T.nblocks, ptr<uint32_t>(h->ws_stmp), h->st, &nl);
         launch_count(h, nl);
-        k_sector_headers<<<blocks_for(T.nsectors, 256), 256, 0, h->st>>>(ptr<uint32_t>(T.bitmap), T.nsectors, cnt, d_ndist);
+        k_word_ranks<<<T.nblocks, 256, 0, h->st>>>(ptr<SlotWord>(T.bitmap), cnt, d_ndist);
         RG_KERNEL_CHECK(); launch_count(h);
 
         RG_CUDA(cudaMemsetAsync(T.E.p, 0xFF, cap_entries * sizeof(Entry), h->st));
-        k_build_entries<<<(unsigned)(h->sm_count * std::max(1, occ_ent)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<uint32_t>(T.bitmap), (uint32_t)cap_entries, ptr<Entry>(T.E));
+        k_build_entries<<<(unsigned)(h->sm_count * std::max(1, occ_ent)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<SlotWord>(T.bitmap), (uint32_t)cap_entries, ptr<Entry>(T.E),
+                                                                                          EP.bucket_start, 1u << EP.ebits, T.hb - EP.ebits);
         RG_KERNEL_CHECK(); launch_count(h);
         RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
 }
@@ -301,7 +303,7 @@ int build_from_device(real_gpu * h)
         // workspace sized for the largest table (A: up to 3 entries per read strand)
         uint64_t const maxent = std::max<uint64_t>(1, nreads * 2 * table_lists(0, h->prm.seedkmax));
         uint32_t const hbmax = std::min<uint32_t>(h->keybits, 32);
-        uint64_t const maxsectors = ((1ULL << hbmax) + SECTOR_SLOTS - 1) / SECTOR_SLOTS;
+        uint64_t const maxsectors = (((1ULL << hbmax) + 31) / 32 + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS;      // ranking blocks
         dev_reserve(h, h->ws_k0, maxent * 8 + 16);           // grouped entry seeds
         dev_reserve(h, h->ws_v0, maxent * 4 + 16);           // grouped entry values
         dev_reserve(h, h->ws_flags, maxsectors * 4 + 16);    // sector counts / ranks
@@ -371,7 +373,7 @@ void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
         P.own_end = h->own_end;
         for ( int t = 0; t < 3; ++t )
         {
-                P.tab[t].bitmap = ptr<uint32_t>(h->tab[t].bitmap);
+                P.tab[t].slots = ptr<SlotWord>(h->tab[t].bitmap);
                 P.tab[t].E = ptr<Entry>(h->tab[t].E);
                 P.tab[t].hb = h->tab[t].hb;
                 P.tab[t].nlists = h->tab[t].nentries ? h->tab[t].nlists : 0;

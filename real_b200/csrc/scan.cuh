@@ -42,15 +42,21 @@ static const int SC_SMEM_WORDS = SC_TILE_WORDS + 2 * SC_HALO; // 516 words = 412
 static const int SC_MAX_BUCKETS = 256;
 static const int SC_CURSOR_STRIDE = 32;                      // u32 per bucket cursor: one 128-byte line each, so the global atomics spread over the L2 slices
 static const int SC_UNIT = 512;                              // records per grab of the probe kernel (one global atomic per warp and grab)
-static const int SC_RPT = 2;                                 // records per lane and step
-static const int SC_QA_CAP = 256;                            // per-warp stage A queue (set slot bits): drained from 32 up, a step adds <= 192
+#ifndef REAL_SC_RPT
+#define REAL_SC_RPT 2
+#endif
+#ifndef REAL_PROBE_MINB
+#define REAL_PROBE_MINB 3
+#endif
+static const int SC_RPT = REAL_SC_RPT;                       // records per lane and step
+static const int SC_QA_CAP = 32 + 96 * SC_RPT;               // per-warp stage A queue (set slot bits): drained from 32 up, a step adds <= 96 per record and lane
 static const int SC_QB_CAP = 64;                             // per-warp stage B queue (seed test passed)
 static const uint32_t SC_POS_NONE = 0xFFFFFFFFu;             // position word of a padding record
 static const uint64_t SC_MAX_CHUNK = 1ull << 30;             // positions per chunk: position (30 bits) and table (2 bits) share a word
 
 struct TableDev
 {
-        const uint32_t * bitmap;
+        const SlotWord * slots;
         const Entry * E;
         uint32_t hb;
         uint32_t nlists;
@@ -279,7 +285,11 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
 // of DRAM reads and 5 GB of writes for 3 GB of records, 10 ms per 250 M positions).  Ranks come from a
 // warp-level multisplit (__match_any_sync on the bucket id): shared-memory atomics that return a value
 // serialise far too much for this.
-static const int PS_PPT = 16;                                 // positions per thread
+#ifndef REAL_PS_PPT
+#define REAL_PS_PPT 8
+#endif
+static const int PS_PPT = REAL_PS_PPT;                        // positions per thread (4, 8, 16 or 32)
+static const int PS_TPW = 32 / PS_PPT;                            // threads per text word
 static const int PS_TILE_POS = SC_THREADS * PS_PPT;           // 4096
 static const int PS_TILE_WORDS = PS_TILE_POS / 32;            // 128
 static const int PS_SMEM_WORDS = PS_TILE_WORDS + 2 * SC_HALO; // 132 words = 1056 bytes
@@ -337,9 +347,9 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 }
                 mbar_wait(&S.bar[buf], (it >> 1) & 1);
                 uint64_t const tile_x0 = tile_id * PS_TILE_POS;
-                uint32_t const wi = threadIdx.x >> 1, j0 = (threadIdx.x & 1) * PS_PPT;
+                uint32_t const wi = threadIdx.x / PS_TPW, j0 = (threadIdx.x % PS_TPW) * PS_PPT;
                 uint64_t const wm = S.tile[buf][SC_HALO + wi - 1], w0 = S.tile[buf][SC_HALO + wi], w1 = S.tile[buf][SC_HALO + wi + 1];
-                uint32_t const m = (clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end) >> j0) & 0xFFFFu;
+                uint32_t const m = (clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end) >> j0) & (uint32_t)((1ull << PS_PPT) - 1);
 
                 // (1) per-warp bucket counts (reductions without return value)
                 {
@@ -456,19 +466,21 @@ __global__ void __launch_bounds__(SC_MAX_BUCKETS) k_part_offsets(ScanParams P)
 
 // ---- probe -------------------------------------------------------------------------------------
 
-struct ItemA { uint64_t win; uint32_t before; uint32_t post; };      // a set slot bit: window, bases in front, position | table << 30
+struct ItemA { uint64_t win; uint32_t before; uint32_t post; };      // a set slot bit: window, bases in front, position | table << 30 (entry index: ProbeSmem::qe)
 struct ItemB { uint64_t lp; uint32_t id; uint32_t exact; };           // an entry that passed the seed test (exact: bit f = fragment f matches exactly)
 
 struct ProbeSmem
 {
         ItemA qa[SC_THREADS / 32][SC_QA_CAP];
         ItemB qb[SC_THREADS / 32][SC_QB_CAP];
-        uint32_t qan[SC_THREADS / 32], qbn[SC_THREADS / 32];
+        uint32_t qe[SC_THREADS / 32][SC_QA_CAP];        // entry index (rank of the slot) of the stage A items
+        uint32_t qbn[SC_THREADS / 32];
+        uint32_t stat[3][SC_THREADS];                   // per thread: candidates, seed passes, hits (far below 2^32 per launch)
 };
 
 // stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
 // whole-read distance, report
-__device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, uint32_t exact, unsigned long long * lstats)
+__device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, uint32_t exact)
 {
         uint32_t const strand = id & 1;
         uint32_t const read = id >> 1;
@@ -476,15 +488,14 @@ __device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t
         {
                 // gapped pass (match.hpp:477-499): only the seed is required to match; '+' strand only; reads still
                 // NoMatch/Gapped; the seed window must lie inside one record and be wildcard free
-                if ( strand ) return;
+                if ( strand ) return 0;
                 uint32_t const st = umi_state(P.info[read]);
-                if ( st != ST_NOMATCH && st != ST_GAPPED ) return;
+                if ( st != ST_NOMATCH && st != ST_GAPPED ) return 0;
                 uint64_t const grpos = P.shard_begin + lp;
-                if ( grpos < P.own_begin || grpos >= P.own_end ) return;
+                if ( grpos < P.own_begin || grpos >= P.own_end ) return 0;
                 uint32_t const gfrag = record_of(P.rec, P.nrec, grpos);
-                if ( gfrag >= P.nrec || grpos + P.seedl > __ldg(P.rec + gfrag + 1) ) return;
-                if ( ! wildcard_free(P.nmask, lp, P.seedl) ) return;
-                lstats[2] += 1;
+                if ( gfrag >= P.nrec || grpos + P.seedl > __ldg(P.rec + gfrag + 1) ) return 0;
+                if ( ! wildcard_free(P.nmask, lp, P.seedl) ) return 0;
                 unsigned long long const slot = atomicAdd(P.hit_count, 1ULL);
                 if ( slot < P.hit_cap )
                 {
@@ -494,34 +505,55 @@ __device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t
                         h.score = 0.0f;
                         P.hits[slot] = h;
                 }
-                return;
+                return 1;
         }
         uint32_t const L = __ldg(P.rlen + read);
         uint32_t const matchoffset = strand ? (L - P.seedl) : 0;          // RestMatch.hpp:84-89
         uint64_t const gp = P.shard_begin + lp;
-        if ( gp < matchoffset ) return;                                   // match.hpp:393
+        if ( gp < matchoffset ) return 0;                                   // match.hpp:393
         uint64_t const gpos = gp - matchoffset;
-        if ( gpos < P.own_begin || gpos >= P.own_end ) return;
+        if ( gpos < P.own_begin || gpos >= P.own_end ) return 0;
         uint64_t const lpos = gpos - P.shard_begin;
+
+        // whole-read Hamming distance = seedk + restk (match.hpp:400-405); the words of the read and of the text under
+        // it are fetched four at a time so that their latencies overlap (and overlap the predicates' loads below)
+        const uint64_t * rp = P.rpack + (uint64_t)id * P.W;
+        const uint64_t * tp = P.text + (lpos >> 5);
+        uint32_t const sh = (uint32_t)(lpos & 31) << 1;
+        uint32_t const nw = (L + 31) >> 5;
+        uint64_t prev = __ldg(tp);
+        uint64_t rw[4], tw[4];
+        #pragma unroll
+        for ( uint32_t u = 0; u < 4; ++u )
+                if ( u < nw ) { rw[u] = __ldg(rp + u); tw[u] = __ldg(tp + u + 1); }
 
         // RangeVector::isPositionValid && AutoTextArray::isDontCareFree (match.hpp:398)
         uint32_t const frag = record_of(P.rec, P.nrec, gpos);
-        if ( frag >= P.nrec || gpos + L > __ldg(P.rec + frag + 1) ) return;
-        if ( ! wildcard_free(P.nmask, lpos, L) ) return;
+        if ( frag >= P.nrec || gpos + L > __ldg(P.rec + frag + 1) ) return 0;
+        if ( ! wildcard_free(P.nmask, lpos, L) ) return 0;
 
-        // whole-read Hamming distance = seedk + restk (match.hpp:400-405)
-        const uint64_t * rp = P.rpack + (uint64_t)id * P.W;
         uint32_t k = 0;
-        uint32_t const nw = (L + 31) >> 5;
-        for ( uint32_t w = 0; w < nw; ++w )
+        for ( uint32_t w0 = 0; w0 < nw; w0 += 4 )
         {
-                uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
-                uint64_t const rw = __ldg(rp + w) >> (64 - 2*len);
-                k += diffcount64(rw, text_word(P.text, lpos + 32*w, len));
-                if ( k > P.totalkmax ) return;
+                if ( w0 )
+                {
+                        #pragma unroll
+                        for ( uint32_t u = 0; u < 4; ++u )
+                                if ( w0 + u < nw ) { rw[u] = __ldg(rp + w0 + u); tw[u] = __ldg(tp + w0 + u + 1); }
+                }
+                #pragma unroll
+                for ( uint32_t u = 0; u < 4; ++u )
+                        if ( w0 + u < nw )
+                        {
+                                uint32_t const w = w0 + u;
+                                uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
+                                uint64_t const tv = sh ? ((prev << sh) | (tw[u] >> (64 - sh))) : prev;      // = text_word(P.text, lpos + 32*w, .) before the final shift
+                                prev = tw[u];
+                                k += diffcount64(rw[u] >> (64 - 2*len), tv >> (64 - 2*len));
+                        }
+                if ( k > P.totalkmax ) return 0;
         }
 
-        lstats[2] += 1;
         if ( P.mode == 1 )
                 unique_update(P.info + read, strand, P.fileid, gpos, k, frag);
         else
@@ -536,36 +568,21 @@ __device__ __forceinline__ void verify_and_report(ScanParams const & P, uint64_t
                         P.hits[slot] = h;
                 }
         }
+        return 1;
 }
 
-// stage A: a set slot bit -> rank inside the sector -> entry chain; per entry the seed test
+// stage A: a set slot bit with the index e of its first entry -> entry chain; per entry the seed test
 // (match.hpp:386-388) and the canonical-list rule: of the up to six lists that reach a position,
 // only the pair made of the two LOWEST exact fragments reports it (replaces unifyMatches' dedup)
-__device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, ItemB * qb, uint32_t * qbn, unsigned long long * lstats, uint64_t pol)
+__device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, uint32_t e, ItemB * qb, uint32_t * qbn, uint32_t * lstats, uint64_t pol_e)
 {
         int const table = (int)(it.post >> 30);
         uint32_t const F = P.F;
         uint64_t const fm = (1ULL << (2*F)) - 1;
-        uint64_t const m0 = (it.win >> (6*F)) & fm;
-        uint64_t const mo = (it.win >> (2*F*(2 - table))) & fm;
-        uint32_t const h = slot_of((m0 << (2*F)) | mo, P.keybits, P.tab[table].hb);
-        uint32_t const sector = h / SECTOR_SLOTS, slot = h - sector * SECTOR_SLOTS;
-        const uint4 * sp = reinterpret_cast<const uint4 *>(P.tab[table].bitmap + (uint64_t)sector * SECTOR_WORDS);
-        uint4 const a = ld_hot_v4(sp, pol), b = ld_hot_v4(sp + 1, pol);
-        uint32_t const wv[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-        uint32_t rank = wv[0];
-        uint32_t const wi = slot >> 5;
-        #pragma unroll
-        for ( uint32_t w = 0; w < 7; ++w )
-        {
-                if ( w < wi ) rank += __popc(wv[1+w]);
-                else if ( w == wi ) rank += __popc(wv[1+w] & ((1u << (slot & 31)) - 1));
-        }
         uint64_t const lx = P.x_begin + (it.post & 0x3FFFFFFFu);
-        uint32_t e = rank;
         while ( e != ENTRY_NONE )
         {
-                uint4 const raw = ld_hot_v4(P.tab[table].E + e, pol);
+                uint4 const raw = ld_hot_v4(P.tab[table].E + e, pol_e);
                 uint64_t const eseed = ((uint64_t)raw.y << 32) | raw.x;
                 uint32_t const t = raw.z & 3, id = raw.z >> 2;
                 e = raw.w;
@@ -598,60 +615,70 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
                         qb[o] = ib;
                 }
                 else
-                        verify_and_report(P, lp, id, exact4, lstats);          // queue full: handle it here
+                        lstats[2] += verify_and_report(P, lp, id, exact4);          // queue full: handle it here
         }
 }
 
 // the warp's stage B queue
-__device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, uint32_t * qbn, int lane, unsigned long long * lstats)
+__device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, uint32_t * qbn, int lane, uint32_t * lstats)
 {
         uint32_t const n = min(*qbn, (uint32_t)SC_QB_CAP);
         __syncwarp();
         for ( uint32_t i = lane; i < n; i += 32 )
         {
                 ItemB const ib = qb[i];
-                verify_and_report(P, ib.lp, ib.id, ib.exact, lstats);
+                lstats[2] += verify_and_report(P, ib.lp, ib.id, ib.exact);
         }
         __syncwarp();
         if ( lane == 0 ) *qbn = 0;
         __syncwarp();
 }
 
-// the warp's stage A queue: full rounds of 32 from the top of the queue; with `flush` also the rest
-__device__ __forceinline__ void drain_a_warp(ScanParams const & P, ItemA * qa, uint32_t * qan, ItemB * qb, uint32_t * qbn, int lane,
-                                             unsigned long long * lstats, bool flush, uint64_t pol)
+// the warp's stage A queue (n items, the same value in every lane): full rounds of 32 from the top of the queue;
+// with `flush` also the rest.  Returns the number of items left.  The statistics go to per-thread shared-memory
+// counters so that the probe loop carries no state for this path.
+__device__ __forceinline__ uint32_t drain_a_warp(ScanParams const & P, ProbeSmem & S, uint32_t n, bool flush)
 {
-        uint32_t n = *qan;
-        __syncwarp();
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const ItemA * qa = S.qa[wid];
+        const uint32_t * qe = S.qe[wid];
+        ItemB * qb = S.qb[wid];
+        uint32_t * qbn = &S.qbn[wid];
+        uint32_t lstats[3] = {0, 0, 0};
+        // entries are touched about once per bucket pass: by default they go through L2 with evict_first priority so
+        // that they do not push the presence words (probed several times per line) out of the protected set
+        uint64_t const pol_e = (P.debug_flags & 2) ? policy_evict_last() : policy_evict_first();
         while ( n >= 32 || (flush && n) )
         {
                 uint32_t const take = n >= 32 ? 32u : n;
                 if ( (uint32_t)lane < take )
-                        follow_item(P, qa[n - take + lane], qb, qbn, lstats, pol);
+                        follow_item(P, qa[n - take + lane], qe[n - take + lane], qb, qbn, lstats, pol_e);
                 __syncwarp();
                 n -= take;
                 if ( *qbn >= 32 )
                         drain_b_warp(P, qb, qbn, lane, lstats);
         }
-        __syncwarp();
-        if ( lane == 0 ) *qan = n;
-        __syncwarp();
         if ( flush && *qbn )
                 drain_b_warp(P, qb, qbn, lane, lstats);
+        #pragma unroll
+        for ( int s = 0; s < 3; ++s )
+                if ( lstats[s] ) S.stat[s][threadIdx.x] += lstats[s];
+        return n;
 }
 
-__global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
+__global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(const __grid_constant__ ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
         ProbeSmem & S = *reinterpret_cast<ProbeSmem *>(sc_smem);
-        unsigned long long lstats[3] = {0, 0, 0};
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        uint64_t const pol = policy_evict_last();
+        uint32_t const lt = (1u << lane) - 1;
         ItemA * qa = S.qa[wid];
-        ItemB * qb = S.qb[wid];
-        uint32_t * qan = &S.qan[wid], * qbn = &S.qbn[wid];
+        uint32_t * qe = S.qe[wid];
+        uint32_t qn = 0;                 // items in the stage A queue; warp uniform, kept in a register
 
-        if ( lane == 0 ) { *qan = 0; *qbn = 0; }
+        if ( lane == 0 ) S.qbn[wid] = 0;
+        #pragma unroll
+        for ( int s = 0; s < 3; ++s ) S.stat[s][threadIdx.x] = 0;
         __syncwarp();
         uint32_t const total = P.bucket_start[SC_MAX_BUCKETS];           // padded to whole grabs
         uint32_t const ngrabs = total / SC_UNIT;
@@ -667,96 +694,100 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_bucket_probe(ScanParams P)
         uint32_t g = 0;
         if ( lane == 0 ) g = atomicAdd(P.unit_counter, 1u);
         g = __shfl_sync(0xffffffffu, g, 0);
+        int const NSTEP = SC_UNIT / (32 * SC_RPT);
+        int const STEP_LINES = 32 * SC_RPT * (int)sizeof(uint4) / 128;          // 128-byte lines of records per step
         while ( g < ngrabs )
         {
                 uint32_t gn = 0;
                 if ( lane == 0 ) gn = atomicAdd(P.unit_counter, 1u);
 
-                const uint4 * rp = P.recs + (uint64_t)g * SC_UNIT + lane;
-                uint4 nxt[SC_RPT];
-                #pragma unroll
-                for ( int k = 0; k < SC_RPT; ++k ) nxt[k] = __ldcs(rp + k * 32);
+                // The records of a step are not held in registers ahead of time (the candidate path below needs the
+                // registers): they are pulled into L2 two steps ahead with prefetches -- across the grab boundary too --
+                // and loaded when the step starts.
+                const uint4 * rp = P.recs + (uint64_t)g * SC_UNIT;
                 #pragma unroll 1
-                for ( int step = 0; step < SC_UNIT / (32 * SC_RPT); ++step )
+                for ( int step = 0; step < NSTEP; ++step )
                 {
+                        if ( step == NSTEP - 2 )
+                                gn = __shfl_sync(0xffffffffu, gn, 0);
+                        {
+                                int const ps = step + 2;
+                                const uint4 * pb = (ps < NSTEP) ? (rp + ps * 32 * SC_RPT) : (P.recs + (uint64_t)gn * SC_UNIT + (ps - NSTEP) * 32 * SC_RPT);
+                                if ( lane < STEP_LINES && (ps < NSTEP || gn < ngrabs) )
+                                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pb + lane * 8));
+                        }
                         uint4 cur[SC_RPT];
                         #pragma unroll
-                        for ( int k = 0; k < SC_RPT; ++k ) cur[k] = nxt[k];
-                        if ( step + 1 < SC_UNIT / (32 * SC_RPT) )
-                        {
-                                #pragma unroll
-                                for ( int k = 0; k < SC_RPT; ++k ) nxt[k] = __ldcs(rp + (step + 1) * 32 * SC_RPT + k * 32);
-                        }
-                        uint32_t v[SC_RPT][3], bit[SC_RPT][3];
+                        for ( int k = 0; k < SC_RPT; ++k ) cur[k] = __ldcs(rp + step * 32 * SC_RPT + k * 32 + lane);
+                        // one 8-byte probe per record and table: presence bits of the slot's word + rank of its first slot
+                        SlotWord sw[SC_RPT][3];
+                        uint32_t bits5[SC_RPT];          // bit index inside the word, 5 bits per table
                         #pragma unroll
                         for ( int k = 0; k < SC_RPT; ++k )
                         {
-                                bool const ok = cur[k].w != SC_POS_NONE;
+                                // padding records probe slot 0 of every table like anybody else (no divergent branch around the
+                                // loads); their candidates are masked out below
                                 uint64_t const win = ((uint64_t)cur[k].y << 32) | cur[k].x;
-                                uint64_t const m0 = (win >> (6*F)) & fm, m1 = (win >> (4*F)) & fm, m2 = (win >> (2*F)) & fm, m3 = win & fm;
-                                v[k][0] = v[k][1] = v[k][2] = 0; bit[k][0] = bit[k][1] = bit[k][2] = 0;
-                                if ( ok && nlA )
+                                uint64_t const m0 = (win >> (6*F)) & fm;
+                                bits5[k] = 0;
+                                #pragma unroll
+                                for ( int t = 0; t < 3; ++t )
                                 {
-                                        uint32_t const h = slot_of((m0 << (2*F)) | m1, kb, P.tab[0].hb);
-                                        uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][0] = rr & 31;
-                                        v[k][0] = ld_hot_u32(P.tab[0].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
-                                }
-                                if ( ok && nlB )
-                                {
-                                        uint32_t const h = slot_of((m0 << (2*F)) | m2, kb, P.tab[1].hb);
-                                        uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][1] = rr & 31;
-                                        v[k][1] = ld_hot_u32(P.tab[1].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
-                                }
-                                if ( ok && nlC )
-                                {
-                                        uint32_t const h = slot_of((m0 << (2*F)) | m3, kb, P.tab[2].hb);
-                                        uint32_t const sc = h / SECTOR_SLOTS, rr = h - sc * SECTOR_SLOTS; bit[k][2] = rr & 31;
-                                        v[k][2] = ld_hot_u32(P.tab[2].bitmap + (uint64_t)sc * SECTOR_WORDS + 1 + (rr >> 5), pol);
+                                        sw[k][t].bits = 0; sw[k][t].rank = 0;
+                                        if ( t == 0 ? nlA : (t == 1 ? nlB : nlC) )           // warp uniform
+                                        {
+                                                uint64_t const mo = (win >> (2*F*(2 - t))) & fm;
+                                                uint32_t const h = slot_of((m0 << (2*F)) | mo, kb, P.tab[t].hb);
+                                                bits5[k] |= (h & 31) << (5 * t);
+                                                sw[k][t] = ld_slotword(P.tab[t].slots + (h >> 5));
+                                        }
                                 }
                         }
-                        // compact the set slot bits into the warp's stage A queue
+                        // compact the set slot bits into the warp's stage A queue: one ballot per (record, table)
                         uint32_t cand = 0;
                         #pragma unroll
                         for ( int k = 0; k < SC_RPT; ++k )
                                 #pragma unroll
                                 for ( int t = 0; t < 3; ++t )
-                                        cand |= ((v[k][t] >> bit[k][t]) & 1u) << (k * 3 + t);
+                                        cand |= ((cur[k].w != SC_POS_NONE) ? ((sw[k][t].bits >> ((bits5[k] >> (5 * t)) & 31)) & 1u) : 0u) << (k * 3 + t);
                         if ( __any_sync(0xffffffffu, cand != 0) )
                         {
-                                uint32_t const c = __popc(cand);
-                                uint32_t const incl = warp_incl_scan(c, lane);
-                                uint32_t const n0 = *qan;
-                                __syncwarp();
-                                uint32_t o = n0 + incl - c;
+                                uint32_t const n0 = qn;
                                 #pragma unroll
                                 for ( int k = 0; k < SC_RPT; ++k )
                                         #pragma unroll
                                         for ( int t = 0; t < 3; ++t )
-                                                if ( (cand >> (k * 3 + t)) & 1u )
+                                        {
+                                                bool const set = (cand >> (k * 3 + t)) & 1u;
+                                                uint32_t const bal = __ballot_sync(0xffffffffu, set);
+                                                if ( set )
                                                 {
+                                                        uint32_t const o = qn + __popc(bal & lt);
                                                         ItemA ia; ia.win = ((uint64_t)cur[k].y << 32) | cur[k].x; ia.before = cur[k].z; ia.post = cur[k].w | ((uint32_t)t << 30);
-                                                        qa[o++] = ia;
+                                                        qa[o] = ia;
+                                                        qe[o] = sw[k][t].rank + __popc(sw[k][t].bits & ((1u << ((bits5[k] >> (5 * t)) & 31)) - 1));
                                                 }
-                                if ( lane == 31 ) *qan = n0 + incl;
+                                                qn += __popc(bal);
+                                        }
                                 __syncwarp();
                                 if ( P.debug_flags & 1 )
                                 {
-                                        if ( lane == 0 ) { lstats[0] += *qan; *qan = 0; }
-                                        __syncwarp();
+                                        if ( lane == 0 ) S.stat[0][threadIdx.x] += qn - n0;
+                                        qn = 0;
                                 }
-                                else if ( n0 + __shfl_sync(0xffffffffu, incl, 31) >= 32 )
-                                        drain_a_warp(P, qa, qan, qb, qbn, lane, lstats, false, pol);
+                                else if ( qn >= 32 )
+                                        qn = drain_a_warp(P, S, qn, false);
                         }
                 }
-                g = __shfl_sync(0xffffffffu, gn, 0);
+                g = gn;
         }
-        drain_a_warp(P, qa, qan, qb, qbn, lane, lstats, true, pol);
+        drain_a_warp(P, S, qn, true);
 
         // statistics: one atomic per warp and counter
         #pragma unroll
         for ( int s = 0; s < 3; ++s )
         {
-                unsigned long long v2 = lstats[s];
+                unsigned long long v2 = S.stat[s][threadIdx.x];      // widened for the sum over the warp
                 #pragma unroll
                 for ( int o = 16; o > 0; o >>= 1 )
                         v2 += __shfl_xor_sync(0xffffffffu, v2, o);

@@ -13,7 +13,7 @@ from typing import List
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libreal_gpu.so")
+LIB_PATH = os.environ.get("REAL_GPU_LIB") or os.path.join(HERE, "libreal_gpu.so")      # REAL_GPU_LIB: a differently tuned build (development)
 HEADER_PATH = os.path.join(HERE, "..", "include", "real_gpu.h")
 
 REAL_GPU_OK = 0

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Top source lines by stall samples from `ncu -i rep --page source --csv --print-source cuda,sass --kernel-name regex:<k>`."""
+"""Top source lines by stall samples.
+   ncu -i rep --page source --csv --print-source cuda,sass --kernel-name regex:<k> > src.csv ; ncu_hot_lines.py src.csv [n]
+Source rows (first column = line number) carry the per-line aggregates; SASS rows (empty first column) are skipped."""
 import csv
 import sys
 
@@ -9,7 +11,7 @@ fname = ""
 hdr = None
 out = []
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
         continue
     if len(r) > 8 and r[0] == "Line No":
