@@ -213,19 +213,26 @@ __device__ __forceinline__ uint64_t pair_key(uint64_t seed, uint32_t F, int a, i
         return (ma << (2*F)) | mb;
 }
 
-// The table build does not sort.  (1) The entries of a table -- (strand seed, strand id, fragment offset),
-// nlists per usable read strand -- are grouped by the top bits of their slot with one staged 256-way
-// partition pass (histogram, then a scatter that lays the records out bucket by bucket in shared memory
-// and writes whole runs).  (2..4) Walking the grouped entries in order then only ever touches one
-// 1/256 slice of the table at a time, which stays in L2, so the table can be built with plain L2
-// atomics: set the presence bits, rank them (sector popcounts + scan), and claim E[rank] with a
-// compare-and-swap; entries that lose the claim (same slot) go to an overflow area behind the distinct
-// entries and are pushed on the head's chain with an exchange.
+// The table build does not sort and uses no global atomics on the table itself.
+//  (1) The entries of a table -- (strand seed, strand id, fragment offset), nlists per usable read strand -- are
+//      grouped by the top e1 <= 8 bits of their slot with one staged partition pass (histogram, then a scatter
+//      that lays the records out bucket by bucket in shared memory and writes whole runs),
+//  (2) and each of those buckets again by the next e2 <= 8 bits, which leaves sub-buckets of a few thousand
+//      entries whose slots span at most 2^16 slots = 2048 slot words.
+//  (3) One CTA per sub-bucket then builds that piece of the table in shared memory: presence bits, ranks
+//      (popcount scan), and the claim of E[rank] by the first entry of a slot; same-slot entries go behind the
+//      distinct ones of the same sub-bucket and are chained through `next`.  E is addressed by "first grouped
+//      entry of the sub-bucket + rank inside it", so no device-wide rank scan is needed, E holds exactly one
+//      element per entry, and every global store of the build is part of a dense range.
+// Measured before this layout (entries claimed with global CAS into bucket-sized slices of a 2x over-allocated,
+// memset E): 45 of the 55 ms of the C3 index build were the bit / claim kernels waiting on random DRAM sectors.
 static const int EP_IDS_PER_THREAD = 4;
 static const int EP_TILE_IDS = 256 * EP_IDS_PER_THREAD;       // strand ids per tile
 static const int EP_TILE_ENTRIES = EP_TILE_IDS * 3;
 static const int EP_MAX_BUCKETS = 256;
 static const int EP_CURSOR_STRIDE = 32;
+static const uint32_t SUB_MAX_WORDS = 2048;                   // slot words of one sub-bucket (shared-memory arrays of k_build_sub)
+static const uint32_t SUB_TARGET_ENTRIES = 4096;
 
 struct EntryPartParams
 {
@@ -233,12 +240,19 @@ struct EntryPartParams
         const uint32_t * usable;      // nreads
         uint64_t nids;                // 2*nreads
         TableGeom G;
-        uint32_t ebits;               // bucket = slot >> (hb - ebits)
-        uint64_t * ent_seed;          // grouped output
+        uint32_t ebits;               // level 1: bucket = slot >> (hb - ebits)
+        uint32_t e2bits;              // level 2: sub-bucket = (slot >> (hb - ebits - e2bits)) & (2^e2bits - 1)
+        uint64_t * ent_seed;          // level 1 output
         uint32_t * ent_val;
+        uint64_t * ent2_seed;         // level 2 output
+        uint32_t * ent2_val;
         uint32_t * bucket_count;      // [256]
         uint32_t * bucket_start;      // [257]
         uint32_t * bucket_cursor;     // [256 * EP_CURSOR_STRIDE]
+        uint32_t * tile_start;        // [257] level 2: first tile of a level-1 bucket
+        uint32_t * sub_count;         // [2^(ebits+e2bits)]
+        uint32_t * sub_start;         // [2^(ebits+e2bits) + 1]
+        uint32_t * sub_cursor;        // [2^(ebits+e2bits)]
 };
 
 __device__ __forceinline__ uint32_t entry_slot(uint64_t seed, TableGeom const & G, uint32_t t)
@@ -263,6 +277,7 @@ __global__ void __launch_bounds__(256) k_ent_hist(EntryPartParams P)
         if ( cnt[threadIdx.x] ) atomicAdd(P.bucket_count + threadIdx.x, cnt[threadIdx.x]);
 }
 
+// bucket starts, cursors, and the level-2 tiling (tiles never straddle a level-1 bucket)
 __global__ void __launch_bounds__(EP_MAX_BUCKETS) k_ent_offsets(EntryPartParams P, uint32_t * total)
 {
         __shared__ uint32_t sc[EP_MAX_BUCKETS];
@@ -270,9 +285,14 @@ __global__ void __launch_bounds__(EP_MAX_BUCKETS) k_ent_offsets(EntryPartParams 
         __syncthreads();
         if ( threadIdx.x == 0 )
         {
-                uint32_t a = 0;
-                for ( int b = 0; b < EP_MAX_BUCKETS; ++b ) { P.bucket_start[b] = a; a += sc[b]; }
+                uint32_t a = 0, tl = 0;
+                for ( int b = 0; b < EP_MAX_BUCKETS; ++b )
+                {
+                        P.bucket_start[b] = a; a += sc[b];
+                        P.tile_start[b] = tl; tl += (sc[b] + EP_TILE_ENTRIES - 1) / EP_TILE_ENTRIES;
+                }
                 P.bucket_start[EP_MAX_BUCKETS] = a;
+                P.tile_start[EP_MAX_BUCKETS] = tl;
                 *total = a;
         }
         P.bucket_cursor[threadIdx.x * EP_CURSOR_STRIDE] = 0;
@@ -288,6 +308,58 @@ struct EntryPartSmem
         uint8_t stage_b[EP_TILE_ENTRIES];
 };
 
+// steps (2) and (4) of a staged 256-way scatter tile, shared by both levels: turn the per-warp counts into the
+// staging layout, reserve the tile's run in every bucket (cursor stride cs), and after the multisplit copy the
+// staged entries out run by run
+__device__ __forceinline__ void ep_layout(EntryPartSmem & S, const uint32_t * __restrict__ start, uint32_t * __restrict__ cursor, uint32_t cs)
+{
+        uint32_t tot = 0;
+        #pragma unroll
+        for ( int w = 0; w < 8; ++w ) tot += S.wcnt[w][threadIdx.x];
+        uint32_t blocktot;
+        uint32_t const ex = block_excl_scan(tot, &blocktot);
+        S.loc[threadIdx.x] = ex;
+        if ( threadIdx.x == EP_MAX_BUCKETS - 1 ) S.loc[EP_MAX_BUCKETS] = blocktot;
+        S.base[threadIdx.x] = tot ? (start[threadIdx.x] + atomicAdd(cursor + threadIdx.x * cs, tot)) : 0;
+        uint32_t run = ex;
+        #pragma unroll
+        for ( int w = 0; w < 8; ++w )
+        {
+                uint32_t const c = S.wcnt[w][threadIdx.x];
+                S.wcnt[w][threadIdx.x] = run;
+                run += c;
+        }
+}
+__device__ __forceinline__ void ep_place(EntryPartSmem & S, int wid, uint32_t lt, bool ok, uint32_t b, uint64_t seed, uint32_t val)
+{
+        uint32_t const peers = __match_any_sync(0xffffffffu, ok ? b : 0x100u);
+        uint32_t const below = __popc(peers & lt);
+        uint32_t pre = 0;
+        if ( ok ) pre = S.wcnt[wid][b];
+        __syncwarp();
+        if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers);
+        __syncwarp();
+        if ( ok )
+        {
+                uint32_t const slot = pre + below;
+                S.stage_seed[slot] = seed;
+                S.stage_val[slot] = val;
+                S.stage_b[slot] = (uint8_t)b;
+        }
+}
+__device__ __forceinline__ void ep_copy_out(EntryPartSmem & S, uint64_t * __restrict__ out_seed, uint32_t * __restrict__ out_val)
+{
+        uint32_t const n = S.loc[EP_MAX_BUCKETS];
+        for ( uint32_t i = threadIdx.x; i < n; i += 256 )
+        {
+                uint32_t const b = S.stage_b[i];
+                uint32_t const o = S.base[b] + (i - S.loc[b]);
+                out_seed[o] = S.stage_seed[i];
+                out_val[o] = S.stage_val[i];
+        }
+}
+
+// level 1: strand seeds -> entries grouped by the top ebits of their slot
 __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
 {
         extern __shared__ __align__(16) unsigned char ep_smem[];
@@ -320,24 +392,7 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                                         atomicAdd(&S.wcnt[wid][P.ebits ? (entry_slot(seed[k], P.G, t) >> sh) : 0u], 1u);
                 __syncthreads();
                 // (2) staging layout, global run reservation, per-warp running slots
-                {
-                        uint32_t tot = 0;
-                        #pragma unroll
-                        for ( int w = 0; w < 8; ++w ) tot += S.wcnt[w][threadIdx.x];
-                        uint32_t blocktot;
-                        uint32_t const ex = block_excl_scan(tot, &blocktot);
-                        S.loc[threadIdx.x] = ex;
-                        if ( threadIdx.x == EP_MAX_BUCKETS - 1 ) S.loc[EP_MAX_BUCKETS] = blocktot;
-                        S.base[threadIdx.x] = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * EP_CURSOR_STRIDE, tot)) : 0;
-                        uint32_t run = ex;
-                        #pragma unroll
-                        for ( int w = 0; w < 8; ++w )
-                        {
-                                uint32_t const c = S.wcnt[w][threadIdx.x];
-                                S.wcnt[w][threadIdx.x] = run;
-                                run += c;
-                        }
-                }
+                ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
                 __syncthreads();
                 // (3) warp multisplit into the staging area
                 #pragma unroll
@@ -347,34 +402,12 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                         for ( uint32_t t = 0; t < nl; ++t )
                         {
                                 uint32_t const b = (ok[k] && P.ebits) ? (entry_slot(seed[k], P.G, t) >> sh) : 0u;
-                                uint32_t const peers = __match_any_sync(0xffffffffu, ok[k] ? b : 0x100u);
-                                uint32_t const below = __popc(peers & lt);
-                                uint32_t pre = 0;
-                                if ( ok[k] ) pre = S.wcnt[wid][b];
-                                __syncwarp();
-                                if ( ok[k] && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers);
-                                __syncwarp();
-                                if ( ok[k] )
-                                {
-                                        uint32_t const slot = pre + below;
-                                        S.stage_seed[slot] = seed[k];
-                                        S.stage_val[slot] = (uint32_t)(id << 2) | t;
-                                        S.stage_b[slot] = (uint8_t)b;
-                                }
+                                ep_place(S, wid, lt, ok[k], b, seed[k], (uint32_t)(id << 2) | t);
                         }
                 }
                 __syncthreads();
                 // (4) copy out run by run
-                {
-                        uint32_t const n = S.loc[EP_MAX_BUCKETS];
-                        for ( uint32_t i = threadIdx.x; i < n; i += 256 )
-                        {
-                                uint32_t const b = S.stage_b[i];
-                                uint32_t const o = S.base[b] + (i - S.loc[b]);
-                                P.ent_seed[o] = S.stage_seed[i];
-                                P.ent_val[o] = S.stage_val[i];
-                        }
-                }
+                ep_copy_out(S, P.ent_seed, P.ent_val);
                 __syncthreads();
                 #pragma unroll
                 for ( int w = 0; w < 8; ++w ) S.wcnt[w][threadIdx.x] = 0;
@@ -382,120 +415,144 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
         }
 }
 
-// presence bits of the grouped entries (reductions into the L2-resident slice)
-__global__ void __launch_bounds__(256) k_build_bits(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ total,
-                                                  TableGeom G, SlotWord * __restrict__ slots)
+// level 2 tiling: tile -> (level-1 bucket, first entry, entries)
+__device__ __forceinline__ void ep2_tile(EntryPartParams const & P, uint32_t tile, uint32_t & b, uint32_t & first, uint32_t & n)
 {
-        uint32_t const n = *total;
-        for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+        uint32_t lo = 0, hi = 1u << P.ebits;                 // last bucket with tile_start <= tile
+        while ( hi - lo > 1 )
         {
-                uint32_t const h = entry_slot(__ldcs(ent_seed + i), G, __ldcs(ent_val + i) & 3);
-                atomicOr(&slots[h >> 5].bits, 1u << (h & 31));
+                uint32_t const mid = (lo + hi) >> 1;
+                if ( P.tile_start[mid] <= tile ) lo = mid; else hi = mid;
         }
+        b = lo;
+        first = P.bucket_start[b] + (tile - P.tile_start[b]) * EP_TILE_ENTRIES;
+        n = min((uint32_t)EP_TILE_ENTRIES, P.bucket_start[b+1] - first);
 }
 
-// E[rank(slot)] is claimed by the first entry that gets there; an entry that finds its slot taken is stored
-// at E[ovf_base + i] (i = its index in the grouped array: no allocation counter, and still inside the
-// bucket's address range) and linked in front of the head's chain.  A single global overflow counter was
-// measured at ~4 ns per (same-address) atomic: 75 ms for the 19 M warps of a 600 M entry build.
-//
-// The claims of a bucket land all over its slice of E, and each one first pulls its (freshly memset) sector out
-// of DRAM -- at the random-sector rate that was most of this kernel's time.  So while the grid sweeps bucket b it
-// also streams bucket b+1's slice of E into L2 with line prefetches, one 128-byte line per 8 entries processed
-// (the grid walks the grouped entries front to back, so "the entry at fraction f of bucket b" prefetches "the line
-// at fraction f of bucket b+1's slice").  bucket_start = the partition's 257 bucket offsets; bucket_shift =
-// hb - log2(buckets), 0 = no prefetching.
-__global__ void __launch_bounds__(256) k_build_entries(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ total,
-                                                     TableGeom G, const SlotWord * __restrict__ slots, uint32_t ovf_base, Entry * __restrict__ E,
-                                                     const uint32_t * __restrict__ bucket_start, uint32_t nbuckets, uint32_t bucket_shift)
+__global__ void __launch_bounds__(256) k_ent2_hist(EntryPartParams P)
 {
-        __shared__ uint32_t bs[EP_MAX_BUCKETS + 1];       // first grouped entry of a bucket
-        __shared__ uint32_t rs[EP_MAX_BUCKETS + 1];       // first rank (= index into E) of a bucket
-        bool const pf = bucket_shift >= 5 && nbuckets > 1;
-        if ( pf )
+        __shared__ uint32_t cnt[EP_MAX_BUCKETS];
+        uint32_t const ntiles = P.tile_start[1u << P.ebits];
+        uint32_t const sh = P.G.hb - P.ebits - P.e2bits, smask = (1u << P.e2bits) - 1;
+        for ( uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x )
         {
-                for ( uint32_t b = threadIdx.x; b <= nbuckets; b += blockDim.x )
-                {
-                        bs[b] = bucket_start[b];
-                        rs[b] = (b < nbuckets) ? slots[((uint64_t)b << bucket_shift) >> 5].rank : 0xFFFFFFFFu;
-                }
+                uint32_t b, first, n;
+                ep2_tile(P, tile, b, first, n);
+                cnt[threadIdx.x] = 0;
+                __syncthreads();
+                for ( uint32_t i = threadIdx.x; i < n; i += 256 )
+                        atomicAdd(&cnt[(entry_slot(__ldcs(P.ent_seed + first + i), P.G, __ldcs(P.ent_val + first + i) & 3) >> sh) & smask], 1u);
+                __syncthreads();
+                if ( threadIdx.x <= smask && cnt[threadIdx.x] ) atomicAdd(P.sub_count + ((b << P.e2bits) | threadIdx.x), cnt[threadIdx.x]);
                 __syncthreads();
         }
-        uint32_t const n = *total;
-        uint64_t const pol = policy_evict_last();
-        for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+}
+
+// level 2: the entries of every level-1 bucket grouped again by the next e2bits of their slot
+__global__ void __launch_bounds__(256) k_ent2_scatter(EntryPartParams P)
+{
+        extern __shared__ __align__(16) unsigned char ep_smem[];
+        EntryPartSmem & S = *reinterpret_cast<EntryPartSmem *>(ep_smem);
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        uint32_t const lt = (1u << lane) - 1;
+        uint32_t const ntiles = P.tile_start[1u << P.ebits];
+        uint32_t const sh = P.G.hb - P.ebits - P.e2bits, smask = (1u << P.e2bits) - 1;
+        #pragma unroll
+        for ( int w = 0; w < 8; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        for ( uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x )
         {
-                uint64_t const seed = __ldcs(ent_seed + i);
-                uint32_t const val = __ldcs(ent_val + i);
-                uint32_t const h = entry_slot(seed, G, val & 3);
-                if ( pf && (threadIdx.x & 7) == 0 )
+                uint32_t b, first, n;
+                ep2_tile(P, tile, b, first, n);
+                uint64_t seed[EP_TILE_ENTRIES / 256];
+                uint32_t val[EP_TILE_ENTRIES / 256];
+                #pragma unroll
+                for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
                 {
-                        uint32_t const b = h >> bucket_shift;
-                        if ( b + 1 < nbuckets )
-                        {
-                                uint32_t const cnt = bs[b+1] - bs[b], f = i - bs[b];
-                                uint32_t const r0 = rs[b+1], r1 = (b + 2 < nbuckets) ? rs[b+2] : r0 + (bs[b+2] - bs[b+1]);
-                                uint32_t const lines = (r1 - r0 + 7) / 8 + 1;
-                                uint32_t const line = (uint32_t)(((uint64_t)(f >> 3) * lines) / ((cnt >> 3) + 1));
-                                if ( line < lines )
-                                        asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(reinterpret_cast<const char *>(E + r0) + (uint64_t)line * 128));
-                        }
+                        uint32_t const i = (uint32_t)k * 256 + threadIdx.x;
+                        seed[k] = (i < n) ? __ldcs(P.ent_seed + first + i) : 0;
+                        val[k] = (i < n) ? __ldcs(P.ent_val + first + i) : 0;
                 }
-                SlotWord const sw = ld_hot_slotword(slots + (h >> 5), pol);
-                uint32_t const rank = sw.rank + __popc(sw.bits & ((1u << (h & 31)) - 1));
-                uint32_t const old = atomicCAS(&E[rank].val, ENTRY_NONE, val);
-                if ( old == ENTRY_NONE )
-                        E[rank].seed = seed;                    // .next stays ENTRY_NONE until somebody links behind it
+                #pragma unroll
+                for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
+                        if ( (uint32_t)k * 256 + threadIdx.x < n )
+                                atomicAdd(&S.wcnt[wid][(entry_slot(seed[k], P.G, val[k] & 3) >> sh) & smask], 1u);
+                __syncthreads();
+                ep_layout(S, P.sub_start + (b << P.e2bits), P.sub_cursor + (b << P.e2bits), 1);
+                __syncthreads();
+                #pragma unroll
+                for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
+                {
+                        bool const ok = (uint32_t)k * 256 + threadIdx.x < n;
+                        ep_place(S, wid, lt, ok, (entry_slot(seed[k], P.G, val[k] & 3) >> sh) & smask, seed[k], val[k]);
+                }
+                __syncthreads();
+                ep_copy_out(S, P.ent2_seed, P.ent2_val);
+                __syncthreads();
+                #pragma unroll
+                for ( int w = 0; w < 8; ++w ) S.wcnt[w][threadIdx.x] = 0;
+                __syncthreads();
+        }
+}
+
+// One CTA per sub-bucket: the grouped entries [sub_start[sb], sub_start[sb+1]) all have slots in
+// [sb << sub_shift, (sb+1) << sub_shift), i.e. `words` = max(1, 2^sub_shift / 32) slot words.  Dynamic shared
+// memory: 3 * words u32 (presence bits, rank of the word's first slot, claimed bits).
+__global__ void __launch_bounds__(256) k_build_sub(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ sub_start,
+                                                 TableGeom G, uint32_t sub_shift, uint32_t words, SlotWord * __restrict__ slots, Entry * __restrict__ E,
+                                                 uint32_t * __restrict__ ndistinct)
+{
+        extern __shared__ __align__(16) uint32_t sub_smem[];
+        uint32_t * bits = sub_smem, * rank = sub_smem + words, * claimed = sub_smem + 2 * words;
+        __shared__ uint32_t ovf;
+        uint32_t const sb = blockIdx.x;
+        uint32_t const s0 = sub_start[sb], s1 = sub_start[sb+1];
+        uint32_t const slot0 = sb << sub_shift;                    // sub_shift == hb when there is a single sub-bucket (sb == 0)
+        for ( uint32_t w = threadIdx.x; w < words; w += 256 ) { bits[w] = 0; claimed[w] = 0; }
+        if ( threadIdx.x == 0 ) ovf = 0;
+        __syncthreads();
+        for ( uint32_t i = s0 + threadIdx.x; i < s1; i += 256 )
+        {
+                uint32_t const l = entry_slot(__ldg(ent_seed + i), G, __ldg(ent_val + i) & 3) - slot0;
+                atomicOr(&bits[l >> 5], 1u << (l & 31));
+        }
+        __syncthreads();
+        // ranks: every thread owns a run of consecutive words
+        uint32_t const wpt = (words + 255) / 256;
+        uint32_t const w0 = threadIdx.x * wpt;
+        uint32_t c = 0;
+        for ( uint32_t w = w0; w < min(words, w0 + wpt); ++w ) c += __popc(bits[w]);
+        uint32_t d;
+        uint32_t run = s0 + block_excl_scan(c, &d);
+        for ( uint32_t w = w0; w < min(words, w0 + wpt); ++w ) { rank[w] = run; run += __popc(bits[w]); }
+        __syncthreads();
+        for ( uint32_t w = threadIdx.x; w < words; w += 256 )
+        {
+                SlotWord sw; sw.bits = bits[w]; sw.rank = rank[w];
+                slots[(uint64_t)sb * words + w] = sw;
+        }
+        for ( uint32_t r = threadIdx.x; r < d; r += 256 ) E[s0 + r].next = ENTRY_NONE;
+        if ( threadIdx.x == 0 && d ) atomicAdd(ndistinct, d);
+        __syncthreads();
+        for ( uint32_t i = s0 + threadIdx.x; i < s1; i += 256 )
+        {
+                uint64_t const seed = __ldg(ent_seed + i);
+                uint32_t const val = __ldg(ent_val + i);
+                uint32_t const l = entry_slot(seed, G, val & 3) - slot0;
+                uint32_t const bit = 1u << (l & 31);
+                uint32_t const r = rank[l >> 5] + __popc(bits[l >> 5] & (bit - 1));
+                if ( ! (atomicOr(&claimed[l >> 5], bit) & bit) )
+                {
+                        E[r].seed = seed;
+                        E[r].val = val;
+                }
                 else
                 {
-                        uint32_t const idx = ovf_base + i;
+                        uint32_t const o = s0 + d + atomicAdd(&ovf, 1u);        // behind the distinct entries of this sub-bucket
                         Entry en; en.seed = seed; en.val = val;
-                        en.next = atomicExch(&E[rank].next, idx);
-                        E[idx] = en;
+                        en.next = atomicExch(&E[r].next, o);
+                        E[o] = en;
                 }
-        }
-}
-
-// Ranks: every block owns RANK_BLOCK_WORDS consecutive slot words (8 per thread).  First pass: presence bits per
-// block; after an exclusive scan of the block sums the second pass writes the rank of every word's first slot.
-__device__ __forceinline__ uint32_t load_block_words(const SlotWord * __restrict__ slots, SlotWord (&w)[8])
-{
-        const uint4 * p = reinterpret_cast<const uint4 *>(slots + ((uint64_t)blockIdx.x * RANK_BLOCK_WORDS + (uint64_t)threadIdx.x * 8));
-        uint32_t c = 0;
-        #pragma unroll
-        for ( int i = 0; i < 4; ++i )
-        {
-                uint4 const v = p[i];
-                w[2*i].bits = v.x; w[2*i].rank = v.y; w[2*i+1].bits = v.z; w[2*i+1].rank = v.w;
-                c += __popc(v.x) + __popc(v.z);
-        }
-        return c;
-}
-
-__global__ void __launch_bounds__(256) k_word_sums(const SlotWord * __restrict__ slots, uint32_t * __restrict__ block_sums)
-{
-        SlotWord w[8];
-        uint32_t const c = load_block_words(slots, w);
-        uint32_t total;
-        block_excl_scan(c, &total);
-        if ( threadIdx.x == 0 ) block_sums[blockIdx.x] = total;
-}
-
-// the last block also publishes the number of distinct slots
-__global__ void __launch_bounds__(256) k_word_ranks(SlotWord * __restrict__ slots, const uint32_t * __restrict__ block_offsets, uint32_t * __restrict__ ndistinct)
-{
-        SlotWord w[8];
-        uint32_t const c = load_block_words(slots, w);
-        uint32_t total;
-        uint32_t run = block_excl_scan(c, &total) + block_offsets[blockIdx.x];
-        if ( blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 ) *ndistinct = block_offsets[blockIdx.x] + total;
-        uint4 * p = reinterpret_cast<uint4 *>(slots + ((uint64_t)blockIdx.x * RANK_BLOCK_WORDS + (uint64_t)threadIdx.x * 8));
-        #pragma unroll
-        for ( int i = 0; i < 4; ++i )
-        {
-                uint32_t const r0 = run, r1 = run + __popc(w[2*i].bits);
-                run = r1 + __popc(w[2*i+1].bits);
-                p[i] = make_uint4(w[2*i].bits, r0, w[2*i+1].bits, r1);
         }
 }
 

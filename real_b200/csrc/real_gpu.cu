@@ -192,7 +192,7 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
 // reads + index
 // ---------------------------------------------------------------------------------------------
 
-// one table: partition the entries by slot prefix, set the presence bits, rank them, place the entries
+// one table: group the entries by slot prefix (two levels), then build every sub-bucket in shared memory
 void build_table(real_gpu * h, int t, uint32_t * meta)
 {
         Table & T = h->tab[t];
@@ -209,25 +209,36 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
                 if ( T.hb < h->keybits && T.hb < SLOT_PREFIX_BITS + 4 ) T.hb = std::min<uint32_t>(cap, SLOT_PREFIX_BITS + 4);
         }
         T.ndistinct = 0;
-        uint64_t const nslots = 1ULL << T.hb;
-        uint64_t const nwords = (nslots + 31) / 32;
-        T.nblocks = (uint32_t)((nwords + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS);          // padded to whole ranking blocks
-        T.bitmap_bytes = (size_t)T.nblocks * RANK_BLOCK_WORDS * sizeof(SlotWord);
+        // partition depth: sub-buckets of about SUB_TARGET_ENTRIES entries, of at most 2^16 slots, of whole slot words
+        uint32_t const pbmin = T.hb > 16 ? T.hb - 16 : 0, pbmax = std::min<uint32_t>(16, T.hb > 5 ? T.hb - 5 : 0);
+        uint32_t pb = 0;
+        while ( (cap_entries >> pb) > SUB_TARGET_ENTRIES ) ++pb;
+        pb = std::min(std::max(pb, pbmin), pbmax);
+        uint32_t const e1 = std::min<uint32_t>(8, pb), e2 = pb - e1;
+        uint32_t const nsub = 1u << pb, sub_shift = T.hb - pb;
+        uint32_t const words = sub_shift >= 5 ? (1u << (sub_shift - 5)) : 1u;
+        T.nblocks = nsub;
+        T.bitmap_bytes = (size_t)nsub * words * sizeof(SlotWord);
         dev_reserve(h, T.bitmap, T.bitmap_bytes);
-        dev_reserve(h, T.E, std::max<size_t>(16, 2 * cap_entries * sizeof(Entry)));   // [0,cap): by rank; [cap,2cap): same-slot overflow, by grouped index
-        RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap_bytes, h->st));
+        dev_reserve(h, T.E, std::max<size_t>(16, cap_entries * sizeof(Entry)) + 256);
         if ( T.nlists == 0 || h->nreads == 0 )
+        {
+                RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap_bytes, h->st));
                 return;
-        if ( 2 * cap_entries >= 0xFFFFFFFFULL )
+        }
+        if ( cap_entries >= 0xFFFFFFFFULL )
                 throw CudaError("index: more than 2^32 entries in one table");
 
-        // meta layout (u32): [0,256) bucket counts, [256,513) bucket starts, 520 total, 521 ndistinct, 522 overflow counter, [1024, ...) cursors
+        // meta layout (u32): [0,256) bucket counts, [256,513) bucket starts, 520 total, 521 ndistinct, [600,857) level-2 tile starts, [1024, ...) cursors
         EntryPartParams EP;
         EP.seeds = ptr<uint64_t>(h->seeds); EP.usable = ptr<uint32_t>(h->usable); EP.nids = 2 * h->nreads;
         EP.G.F = h->F; EP.G.keybits = h->keybits; EP.G.hb = T.hb; EP.G.nlists = T.nlists; EP.G.table = t;
-        EP.ebits = std::min<uint32_t>(8, T.hb);
+        EP.ebits = e1; EP.e2bits = e2;
         EP.ent_seed = ptr<uint64_t>(h->ws_k0); EP.ent_val = ptr<uint32_t>(h->ws_v0);
-        EP.bucket_count = meta; EP.bucket_start = meta + 256; EP.bucket_cursor = meta + 1024;
+        EP.ent2_seed = ptr<uint64_t>(h->ws_k1); EP.ent2_val = ptr<uint32_t>(h->ws_v1);
+        EP.bucket_count = meta; EP.bucket_start = meta + 256; EP.tile_start = meta + 600; EP.bucket_cursor = meta + 1024;
+        uint32_t * sub = ptr<uint32_t>(h->ws_flags);
+        EP.sub_count = sub; EP.sub_start = sub + 65600; EP.sub_cursor = sub + 2 * 65600;
         uint32_t * d_total = meta + 520, * d_ndist = meta + 521;
         RG_CUDA(cudaMemsetAsync(meta, 0, 1024 * 4, h->st));
 
@@ -238,33 +249,31 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         RG_KERNEL_CHECK();
         size_t const esmem = sizeof(EntryPartSmem);
         RG_CUDA(cudaFuncSetAttribute(k_ent_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-        int occ = 0;
+        RG_CUDA(cudaFuncSetAttribute(k_ent2_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+        int occ = 0, occ2 = 0, occh = 0;
         RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ent_scatter, 256, esmem));
-        if ( occ < 1 ) occ = 1;
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_ent2_scatter, 256, esmem));
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occh, k_ent2_hist, 256, 0));
         uint64_t const etiles = (EP.nids + EP_TILE_IDS - 1) / EP_TILE_IDS;
-        k_ent_scatter<<<(unsigned)std::min<uint64_t>(etiles, (uint64_t)h->sm_count * occ), 256, esmem, h->st>>>(EP);
+        k_ent_scatter<<<(unsigned)std::min<uint64_t>(etiles, (uint64_t)h->sm_count * std::max(1, occ)), 256, esmem, h->st>>>(EP);
         RG_KERNEL_CHECK();
-        int occ_bits = 0, occ_ent = 0;
-        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bits, k_build_bits, 256, 0));
-        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ent, k_build_entries, 256, 0));
-        // one resident wave each: the grid-stride sweep then passes over the buckets exactly once
-        k_build_bits<<<(unsigned)(h->sm_count * std::max(1, occ_bits)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<SlotWord>(T.bitmap));
-        RG_KERNEL_CHECK();
-        launch_count(h, 4);
+        launch_count(h, 3);
 
-        // ranks: presence bits per block of slot words -> exclusive scan -> rank of every word (+ number of distinct slots)
-        uint32_t * cnt = ptr<uint32_t>(h->ws_flags);
-        k_word_sums<<<T.nblocks, 256, 0, h->st>>>(ptr<SlotWord>(T.bitmap), cnt);
-        RG_KERNEL_CHECK(); launch_count(h);
-        uint32_t nl = 0;
-        exclusive_scan_u32(cnt, cnt, T.nblocks, ptr<uint32_t>(h->ws_stmp), h->st, &nl);
-        launch_count(h, nl);
-        k_word_ranks<<<T.nblocks, 256, 0, h->st>>>(ptr<SlotWord>(T.bitmap), cnt, d_ndist);
-        RG_KERNEL_CHECK(); launch_count(h);
-
-        RG_CUDA(cudaMemsetAsync(T.E.p, 0xFF, cap_entries * sizeof(Entry), h->st));
-        k_build_entries<<<(unsigned)(h->sm_count * std::max(1, occ_ent)), 256, 0, h->st>>>(EP.ent_seed, EP.ent_val, d_total, EP.G, ptr<SlotWord>(T.bitmap), (uint32_t)cap_entries, ptr<Entry>(T.E),
-                                                                                          EP.bucket_start, 1u << EP.ebits, T.hb - EP.ebits);
+        const uint64_t * fin_seed = EP.ent_seed; const uint32_t * fin_val = EP.ent_val; const uint32_t * fin_start = EP.bucket_start;
+        if ( e2 )
+        {
+                // one resident wave each: the grid-stride sweeps then pass over the level-1 buckets in order
+                RG_CUDA(cudaMemsetAsync(sub, 0, (size_t)3 * 65600 * 4, h->st));
+                k_ent2_hist<<<(unsigned)(h->sm_count * std::max(1, occh)), 256, 0, h->st>>>(EP);
+                RG_KERNEL_CHECK(); launch_count(h);
+                uint32_t nl = 0;
+                exclusive_scan_u32(EP.sub_count, EP.sub_start, (uint64_t)nsub + 1, ptr<uint32_t>(h->ws_stmp), h->st, &nl);
+                launch_count(h, nl);
+                k_ent2_scatter<<<(unsigned)(h->sm_count * std::max(1, occ2)), 256, esmem, h->st>>>(EP);
+                RG_KERNEL_CHECK(); launch_count(h);
+                fin_seed = EP.ent2_seed; fin_val = EP.ent2_val; fin_start = EP.sub_start;
+        }
+        k_build_sub<<<nsub, 256, (size_t)3 * words * 4, h->st>>>(fin_seed, fin_val, fin_start, EP.G, sub_shift, words, ptr<SlotWord>(T.bitmap), ptr<Entry>(T.E), d_ndist);
         RG_KERNEL_CHECK(); launch_count(h);
         RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
 }
@@ -303,11 +312,12 @@ int build_from_device(real_gpu * h)
         // workspace sized for the largest table (A: up to 3 entries per read strand)
         uint64_t const maxent = std::max<uint64_t>(1, nreads * 2 * table_lists(0, h->prm.seedkmax));
         uint32_t const hbmax = std::min<uint32_t>(h->keybits, 32);
-        uint64_t const maxsectors = (((1ULL << hbmax) + 31) / 32 + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS;      // ranking blocks
-        dev_reserve(h, h->ws_k0, maxent * 8 + 16);           // grouped entry seeds
-        dev_reserve(h, h->ws_v0, maxent * 4 + 16);           // grouped entry values
-        dev_reserve(h, h->ws_flags, maxsectors * 4 + 16);    // sector counts / ranks
-        dev_reserve(h, h->ws_stmp, scan_temp_elems(maxsectors) * 4 + 64);
+        dev_reserve(h, h->ws_k0, maxent * 8 + 16);           // entries grouped by the first level: seeds
+        dev_reserve(h, h->ws_v0, maxent * 4 + 16);           //                                     values
+        dev_reserve(h, h->ws_k1, maxent * 8 + 16);           // entries grouped by both levels
+        dev_reserve(h, h->ws_v1, maxent * 4 + 16);
+        dev_reserve(h, h->ws_flags, (size_t)3 * 65600 * 4);  // sub-bucket counts, starts, cursors
+        dev_reserve(h, h->ws_stmp, scan_temp_elems(65600) * 4 + 64);
         dev_reserve(h, h->ws_hist, (1024 + 256 * EP_CURSOR_STRIDE) * 4);
         memset(h->table_counts, 0, sizeof(h->table_counts));
         for ( int t = 0; t < 3; ++t )
@@ -406,7 +416,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                 uint32_t const maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
                 for ( int t = 0; t < 3; ++t )
                         if ( P.tab[t].nlists )
-                                table_bytes += h->tab[t].bitmap_bytes + 2 * h->tab[t].nentries * sizeof(Entry);
+                                table_bytes += h->tab[t].bitmap_bytes + h->tab[t].nentries * sizeof(Entry);
                 uint32_t bbits = 0;
                 if ( h->pass_bits_override >= 0 )
                         bbits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
