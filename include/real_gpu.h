@@ -193,6 +193,26 @@ int real_gpu_unique_export_keys(real_gpu * h, uint64_t * d_keys);
 int real_gpu_unique_export_ties(real_gpu * h, const uint64_t * d_min_keys, uint8_t * d_ties);
 int real_gpu_unique_import(real_gpu * h, const uint64_t * d_min_keys, const uint8_t * d_tie_sums);
 
+/* Sharded tables: the multi-GPU form of the scan (BASELINE.json north_star asks for the text to be
+ * split over the GPUs of one box).  One handle = one rank = one GPU, at most 8.  Every rank is given the whole read
+ * set and the whole text, but builds and keeps the index tables of its own 1/nranks of the signature space only
+ * (scan buckets = the first 4 bases of a seed window).  In every round of the scan (round_positions text positions,
+ * 0 = 2^30) each rank forms the window records of ITS slice of the positions and its partition kernel stores the
+ * records of a bucket straight into the record area of the bucket's owner -- peer memory over NVLink, no staging
+ * copy, no collective -- after which each owner probes what it was sent.  Ranks hand over with release/acquire
+ * flags in each other's windows.  Every hit is found by exactly one rank; matchAll results are the union of the
+ * ranks' results, matchUnique states are merged with the real_gpu_unique_export_* exchange below.
+ *   real_gpu_comm_init           allocates this rank's window; call it BEFORE real_gpu_set_reads.  handle_out
+ *                                receives REAL_GPU_COMM_HANDLE_BYTES bytes (a CUDA IPC handle) to pass to the others
+ *   real_gpu_comm_connect        all_handles = the nranks handles in rank order (one process per GPU)
+ *   real_gpu_comm_connect_local  the same for ranks that live in one process (peers = the nranks handles)
+ * All ranks must use the same round_positions and make the same sequence of match calls.  Order dependent folds
+ * (matchUnique with scores, real_gpu_match_gaps) are not available in this mode. */
+#define REAL_GPU_COMM_HANDLE_BYTES 64
+int real_gpu_comm_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t round_positions, void * handle_out);
+int real_gpu_comm_connect(real_gpu * h, const void * all_handles);
+int real_gpu_comm_connect_local(real_gpu * h, real_gpu * const * peers);
+
 /* Gapped extension pass (UniqueMatcher::matchGaps) for reads still NoMatch/Gapped; updates the
  * unique state (state Gapped, score, seed position).  gaps[nreads], present==1 where a GapInfo
  * entry exists. */

@@ -253,7 +253,15 @@ struct EntryPartParams
         uint32_t * sub_count;         // [2^(ebits+e2bits)]
         uint32_t * sub_start;         // [2^(ebits+e2bits) + 1]
         uint32_t * sub_cursor;        // [2^(ebits+e2bits)]
+        // sharded tables: this rank indexes only the entries with own_lo <= slot >> own_shift <= own_last
+        uint32_t own_shift, own_lo, own_last;
 };
+
+__device__ __forceinline__ bool entry_owned(EntryPartParams const & P, uint32_t slot)
+{
+        uint32_t const p = slot >> P.own_shift;
+        return p >= P.own_lo && p <= P.own_last;
+}
 
 __device__ __forceinline__ uint32_t entry_slot(uint64_t seed, TableGeom const & G, uint32_t t)
 {
@@ -271,7 +279,10 @@ __global__ void __launch_bounds__(256) k_ent_hist(EntryPartParams P)
                 if ( ! P.usable[id >> 1] ) continue;
                 uint64_t const seed = P.seeds[id];
                 for ( uint32_t t = 0; t < P.G.nlists; ++t )
-                        atomicAdd(&cnt[P.ebits ? (entry_slot(seed, P.G, t) >> sh) : 0u], 1u);
+                {
+                        uint32_t const slot = entry_slot(seed, P.G, t);
+                        if ( entry_owned(P, slot) ) atomicAdd(&cnt[P.ebits ? (slot >> sh) : 0u], 1u);
+                }
         }
         __syncthreads();
         if ( cnt[threadIdx.x] ) atomicAdd(P.bucket_count + threadIdx.x, cnt[threadIdx.x]);
@@ -389,7 +400,10 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                 for ( int k = 0; k < EP_IDS_PER_THREAD; ++k )
                         if ( ok[k] )
                                 for ( uint32_t t = 0; t < nl; ++t )
-                                        atomicAdd(&S.wcnt[wid][P.ebits ? (entry_slot(seed[k], P.G, t) >> sh) : 0u], 1u);
+                                {
+                                        uint32_t const slot = entry_slot(seed[k], P.G, t);
+                                        if ( entry_owned(P, slot) ) atomicAdd(&S.wcnt[wid][P.ebits ? (slot >> sh) : 0u], 1u);
+                                }
                 __syncthreads();
                 // (2) staging layout, global run reservation, per-warp running slots
                 ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
@@ -401,8 +415,9 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                         uint64_t const id = tile * EP_TILE_IDS + (uint64_t)k * 256 + threadIdx.x;
                         for ( uint32_t t = 0; t < nl; ++t )
                         {
-                                uint32_t const b = (ok[k] && P.ebits) ? (entry_slot(seed[k], P.G, t) >> sh) : 0u;
-                                ep_place(S, wid, lt, ok[k], b, seed[k], (uint32_t)(id << 2) | t);
+                                uint32_t const slot = ok[k] ? entry_slot(seed[k], P.G, t) : 0u;
+                                uint32_t const b = (ok[k] && P.ebits) ? (slot >> sh) : 0u;
+                                ep_place(S, wid, lt, ok[k] && entry_owned(P, slot), b, seed[k], (uint32_t)(id << 2) | t);
                         }
                 }
                 __syncthreads();
@@ -500,12 +515,12 @@ __global__ void __launch_bounds__(256) k_ent2_scatter(EntryPartParams P)
 // memory: 3 * words u32 (presence bits, rank of the word's first slot, claimed bits).
 __global__ void __launch_bounds__(256) k_build_sub(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ sub_start,
                                                  TableGeom G, uint32_t sub_shift, uint32_t words, SlotWord * __restrict__ slots, Entry * __restrict__ E,
-                                                 uint32_t * __restrict__ ndistinct)
+                                                 uint32_t * __restrict__ ndistinct, uint32_t first_sub)
 {
         extern __shared__ __align__(16) uint32_t sub_smem[];
         uint32_t * bits = sub_smem, * rank = sub_smem + words, * claimed = sub_smem + 2 * words;
         __shared__ uint32_t ovf;
-        uint32_t const sb = blockIdx.x;
+        uint32_t const sb = first_sub + blockIdx.x;
         uint32_t const s0 = sub_start[sb], s1 = sub_start[sb+1];
         uint32_t const slot0 = sb << sub_shift;                    // sub_shift == hb when there is a single sub-bucket (sb == 0)
         for ( uint32_t w = threadIdx.x; w < words; w += 256 ) { bits[w] = 0; claimed[w] = 0; }

@@ -9,6 +9,9 @@
 #include "post.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstring>
 #include <cstdlib>
 #include <cfloat>
@@ -75,6 +78,28 @@ struct real_gpu
         uint64_t hit_cap;
         real_gpu_hit * host_hits;
         uint64_t host_hits_cap;
+
+        // sharded tables (real_gpu_comm_*): one window per rank = {flags, bucket counts per source, record area}
+        struct Comm
+        {
+                uint32_t nranks, rank, epoch, seg_cap;
+                uint64_t round_positions;
+                DevBuf window, ptrs, pairs, error;
+                size_t meta_off, recs_off;
+                char * base[SC_MAX_RANKS];      // window of every rank as mapped into this process
+                bool ipc_opened[SC_MAX_RANKS];
+                bool connected;
+                // ranks that live in one process (real_gpu_comm_connect_local) hand over with CUDA events instead of
+                // spinning on the device: kernels of different streams of ONE context may share a hardware queue, and
+                // a kernel that spins at the head of such a queue would hold back the very kernels it waits for
+                real_gpu * local[SC_MAX_RANKS];
+                cudaEvent_t ev[2];
+                std::atomic<uint32_t> enqueued[2];      // last round whose signal of slot 0/1 has been recorded on this rank's stream
+                uint32_t bucket_lo[SC_MAX_RANKS + 1];
+                Comm() : nranks(1), rank(0), epoch(0), seg_cap(0), round_positions(0), meta_off(0), recs_off(0), connected(false)
+                { for ( int i = 0; i < SC_MAX_RANKS; ++i ) { base[i] = nullptr; ipc_opened[i] = false; local[i] = nullptr; } for ( int i = 0; i <= SC_MAX_RANKS; ++i ) bucket_lo[i] = 0;
+                  ev[0] = ev[1] = nullptr; enqueued[0] = 0; enqueued[1] = 0; }
+        } comm;
 
         real_gpu_stats stats;
         int pass_bits_override;        // REAL_GPU_PASS_BITS (tuning), -1 = automatic
@@ -234,6 +259,19 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         EP.seeds = ptr<uint64_t>(h->seeds); EP.usable = ptr<uint32_t>(h->usable); EP.nids = 2 * h->nreads;
         EP.G.F = h->F; EP.G.keybits = h->keybits; EP.G.hb = T.hb; EP.G.nlists = T.nlists; EP.G.table = t;
         EP.ebits = e1; EP.e2bits = e2;
+        EP.own_shift = 0; EP.own_lo = 0; EP.own_last = 0xFFFFFFFFu;
+        uint32_t first_sub = 0, own_subs = nsub;
+        if ( h->comm.nranks > 1 )
+        {
+                // this rank owns the slots whose top 8 bits (= top 8 bits of the key = scan bucket) fall into its bucket range
+                if ( T.hb < 8 ) throw CudaError("sharded tables need presence tables of at least 2^8 slots");
+                EP.own_shift = T.hb - 8; EP.own_lo = h->comm.bucket_lo[h->comm.rank]; EP.own_last = h->comm.bucket_lo[h->comm.rank + 1] - 1;
+                if ( pb >= 8 )
+                {
+                        first_sub = EP.own_lo << (pb - 8);
+                        own_subs = (EP.own_last + 1 - EP.own_lo) << (pb - 8);
+                }
+        }
         EP.ent_seed = ptr<uint64_t>(h->ws_k0); EP.ent_val = ptr<uint32_t>(h->ws_v0);
         EP.ent2_seed = ptr<uint64_t>(h->ws_k1); EP.ent2_val = ptr<uint32_t>(h->ws_v1);
         EP.bucket_count = meta; EP.bucket_start = meta + 256; EP.tile_start = meta + 600; EP.bucket_cursor = meta + 1024;
@@ -273,7 +311,7 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
                 RG_KERNEL_CHECK(); launch_count(h);
                 fin_seed = EP.ent2_seed; fin_val = EP.ent2_val; fin_start = EP.sub_start;
         }
-        k_build_sub<<<nsub, 256, (size_t)3 * words * 4, h->st>>>(fin_seed, fin_val, fin_start, EP.G, sub_shift, words, ptr<SlotWord>(T.bitmap), ptr<Entry>(T.E), d_ndist);
+        k_build_sub<<<own_subs, 256, (size_t)3 * words * 4, h->st>>>(fin_seed, fin_val, fin_start, EP.G, sub_shift, words, ptr<SlotWord>(T.bitmap), ptr<Entry>(T.E), d_ndist, first_sub);
         RG_KERNEL_CHECK(); launch_count(h);
         RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
 }
@@ -349,6 +387,12 @@ int build_from_device(real_gpu * h)
                 k_fill_f32<<<blocks_for(nreads + 1, 256), 256, 0, h->st>>>(ptr<float>(h->scores), nreads, -FLT_MAX);      // UniqueMatchInfo.hpp:190
                 RG_KERNEL_CHECK(); launch_count(h);
         }
+        if ( h->comm.nranks > 1 && h->hit_cap == 0 )
+        {
+                // sharded tables: nothing may be allocated or freed between the hand-over kernels of a scan
+                h->hit_cap = std::max<uint64_t>(1u << 16, 4 * h->nreads);
+                dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
+        }
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->have_reads = true;
         return REAL_GPU_OK;
@@ -391,12 +435,53 @@ void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
         P.seedl = seedl; P.F = h->F; P.keybits = h->keybits; P.seedkmax = h->prm.seedkmax; P.totalkmax = h->prm.totalkmax;
         P.rpack = ptr<uint64_t>(h->rpack); P.W = h->W; P.rlen = ptr<uint32_t>(h->rlen);
         P.rec = ptr<uint64_t>(h->rec); P.nrec = h->nrec; P.fileid = h->fileid;
+        P.nranks = 1; P.rank = 0; P.bucket_lo[0] = 0; P.bucket_lo[1] = SC_MAX_BUCKETS; P.seg_cap = 0; P.npairs = 0;
         P.mode = mode;
         P.hits = ptr<RawHit>(h->hits_raw);
         P.hit_cap = h->hit_cap;
         P.hit_count = ptr<unsigned long long>(h->counters);
         P.stats = ptr<unsigned long long>(h->counters) + 1;
         P.info = ptr<unsigned long long>(h->info);
+}
+
+// hand-over between the ranks of a sharded scan: "slot 0 of round e" = my records of round e are delivered,
+// "slot 1" = I have consumed what I was sent in round e
+void comm_signal(real_gpu * h, uint32_t slot)
+{
+        real_gpu::Comm & CM = h->comm;
+        if ( CM.local[CM.rank] )
+        {
+                RG_CUDA(cudaEventRecord(CM.ev[slot], h->st));
+                CM.enqueued[slot].store(CM.epoch, std::memory_order_release);
+                return;
+        }
+        k_comm_signal<<<1, 32, 0, h->st>>>(ptr<uint32_t *>(CM.ptrs), CM.nranks, CM.rank, slot, CM.epoch);
+        RG_KERNEL_CHECK(); launch_count(h);
+}
+
+void comm_wait(real_gpu * h, uint32_t slot, uint32_t epoch, long long wait_ms)
+{
+        real_gpu::Comm & CM = h->comm;
+        if ( CM.local[CM.rank] )
+        {
+                if ( epoch == 0 ) return;
+                auto const t0 = std::chrono::steady_clock::now();
+                for ( uint32_t r = 0; r < CM.nranks; ++r )
+                {
+                        if ( r == CM.rank ) continue;
+                        real_gpu::Comm & Q = CM.local[r]->comm;
+                        while ( (int32_t)(Q.enqueued[slot].load(std::memory_order_acquire) - epoch) < 0 )
+                        {
+                                if ( std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > wait_ms )
+                                        throw CudaError("sharded tables: timed out waiting for rank " + std::to_string(r));
+                                std::this_thread::yield();
+                        }
+                        RG_CUDA(cudaStreamWaitEvent(h->st, Q.ev[slot], 0));
+                }
+                return;
+        }
+        k_comm_wait<<<1, 32, 0, h->st>>>(reinterpret_cast<uint32_t *>(CM.base[CM.rank]), CM.nranks, slot, epoch, wait_ms * 2000000LL, ptr<uint32_t>(CM.error));
+        RG_KERNEL_CHECK(); launch_count(h);
 }
 
 // launches K3 once; returns the number of hits the kernel counted
@@ -425,13 +510,43 @@ uint64_t run_scan(real_gpu * h, int mode)
                 P.bucket_bits = bbits;
                 if ( const char * e = getenv("REAL_GPU_DEBUG") ) P.debug_flags = (uint32_t)atoi(e);
 
-                uint64_t const chunk_max = std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
+                real_gpu::Comm & CM = h->comm;
+                bool const sharded = CM.nranks > 1;
+                if ( sharded )
+                {
+                        if ( ! CM.connected ) throw CudaError("sharded tables: real_gpu_comm_connect has not been called");
+                        if ( maxbits < 8 ) throw CudaError("sharded tables need seeds of at least 16 bases");
+                        if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
+                                throw CudaError("sharded tables: every rank must be given the whole text (the ranks split the positions among themselves)");
+                        P.bucket_bits = 8;
+                }
+                uint64_t const chunk_max = sharded ? CM.round_positions : std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
                 uint64_t const x_begin = P.x_begin, x_end = P.x_end;
                 uint64_t const chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
-                dev_reserve(h, h->rec_win, (chunk_cap + (uint64_t)SC_MAX_BUCKETS * SC_UNIT) * sizeof(uint4) + 64);
-                dev_reserve(h, h->part_meta, (1100 + 256 * SC_CURSOR_STRIDE) * 4);
-                uint32_t * meta = ptr<uint32_t>(h->part_meta);
-                P.recs = ptr<uint4>(h->rec_win);
+                uint32_t * meta = nullptr;
+                if ( sharded )
+                {
+                        // everything was allocated by real_gpu_comm_init: no allocation may happen between the hand-over kernels
+                        meta = ptr<uint32_t>(h->part_meta);
+                        P.recs = reinterpret_cast<uint4 *>(CM.base[CM.rank] + CM.recs_off);
+                        P.nranks = CM.nranks; P.rank = CM.rank; P.seg_cap = CM.seg_cap;
+                        for ( uint32_t r = 0; r <= CM.nranks; ++r ) P.bucket_lo[r] = CM.bucket_lo[r];
+                        for ( uint32_t r = 0; r < CM.nranks; ++r )
+                        {
+                                P.peer_recs[r] = reinterpret_cast<uint4 *>(CM.base[r] + CM.recs_off);
+                                P.peer_meta[r] = reinterpret_cast<uint32_t *>(CM.base[r] + CM.meta_off);
+                        }
+                        P.pair_grab = ptr<uint32_t>(CM.pairs); P.pair_rec = ptr<uint32_t>(CM.pairs) + 1024;
+                        P.npairs = (CM.bucket_lo[CM.rank + 1] - CM.bucket_lo[CM.rank]) * CM.nranks;
+                }
+                else
+                {
+                        dev_reserve(h, h->rec_win, (chunk_cap + (uint64_t)SC_MAX_BUCKETS * SC_UNIT) * sizeof(uint4) + 64);
+                        dev_reserve(h, h->part_meta, (1100 + 256 * SC_CURSOR_STRIDE) * 4);
+                        meta = ptr<uint32_t>(h->part_meta);
+                        P.recs = ptr<uint4>(h->rec_win);
+                        P.peer_recs[0] = P.recs;
+                }
                 P.bucket_count = meta;
                 P.bucket_start = meta + 256;
                 P.unit_counter = meta + 256 + 520;
@@ -448,26 +563,62 @@ uint64_t run_scan(real_gpu * h, int mode)
                 if ( occ_p < 1 ) occ_p = 1;
                 if ( occ_s < 1 ) occ_s = 1;
                 if ( occ_b < 1 ) occ_b = 1;
+                long long wait_ms = 30000;             // a peer that never arrives is reported, not waited for forever
+                if ( const char * e = getenv("REAL_GPU_COMM_TIMEOUT_MS") ) wait_ms = atoll(e);
 
+                h->stats.n_windows = 0;
                 for ( uint64_t cb = x_begin; cb < x_end; cb += chunk_cap )
                 {
-                        P.x_begin = cb;
-                        P.x_end = std::min<uint64_t>(x_end, cb + chunk_cap);
+                        uint64_t const ce = std::min<uint64_t>(x_end, cb + chunk_cap);
+                        P.pos_base = cb;
+                        P.x_begin = cb; P.x_end = ce;
+                        if ( sharded )
+                        {
+                                // this rank's slice of the round
+                                uint64_t const per = (chunk_cap + CM.nranks - 1) / CM.nranks;
+                                P.x_begin = std::min<uint64_t>(ce, cb + (uint64_t)CM.rank * per);
+                                P.x_end = std::min<uint64_t>(ce, P.x_begin + per);
+                                ++CM.epoch;
+                        }
+                        h->stats.n_windows += P.x_end - P.x_begin;
+                        bool const any = P.x_end > P.x_begin;
                         uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
                         unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * occ_p);
                         RG_CUDA(cudaMemsetAsync(meta, 0, 256 * 4, h->st));
-                        k_part_hist<<<pgrid, SC_THREADS, psmem, h->st>>>(P);
-                        RG_KERNEL_CHECK();
+                        if ( any )
+                        {
+                                k_part_hist<<<pgrid, SC_THREADS, psmem, h->st>>>(P);
+                                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
+                        }
+                        if ( sharded )
+                        {
+                                // the owners must have consumed the previous round before their record areas are written again
+                                comm_wait(h, 1, CM.epoch - 1, wait_ms);
+                        }
                         k_part_offsets<<<1, SC_MAX_BUCKETS, 0, h->st>>>(P);
                         RG_KERNEL_CHECK();
-                        uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
-                        unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
-                        k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
-                        RG_KERNEL_CHECK();
+                        if ( any )
+                        {
+                                uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
+                                unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
+                                k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
+                                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
+                        }
+                        if ( sharded )
+                        {
+                                comm_signal(h, 0);
+                                comm_wait(h, 0, CM.epoch, wait_ms);
+                                k_comm_pairs<<<1, SC_PAIR_THREADS, 0, h->st>>>(P, reinterpret_cast<uint32_t *>(CM.base[CM.rank] + CM.meta_off));
+                                RG_KERNEL_CHECK(); launch_count(h);
+                        }
                         k_bucket_probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
-                        launch_count(h, 4);
-                        h->stats.scan_launches += 4;
+                        if ( sharded )
+                        {
+                                comm_signal(h, 1);
+                        }
+                        launch_count(h, 2);
+                        h->stats.scan_launches += 2;
                 }
                 P.x_begin = x_begin; P.x_end = x_end;
         }
@@ -476,7 +627,13 @@ uint64_t run_scan(real_gpu * h, int mode)
         RG_CUDA(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.scan_ms = elapsed(h->ev[5], h->ev[6]);
-        h->stats.n_windows = P.x_end - P.x_begin;
+        if ( ! ntiles ) h->stats.n_windows = 0;
+        if ( h->comm.nranks > 1 )
+        {
+                uint32_t cerr = 0;
+                RG_CUDA(cudaMemcpy(&cerr, h->comm.error.p, 4, cudaMemcpyDeviceToHost));
+                if ( cerr ) throw CudaError("sharded tables: timed out waiting for rank " + std::to_string(cerr - 1));
+        }
         uint32_t nt = 0;
         for ( int t = 0; t < 3; ++t ) if ( P.tab[t].nlists ) ++nt;
         h->stats.n_probes = h->stats.n_windows * nt;
@@ -484,6 +641,27 @@ uint64_t run_scan(real_gpu * h, int mode)
         h->stats.n_seedpass = c[2];
         h->stats.n_hits = c[3];
         return (mode != 1) ? (uint64_t)c[0] : (uint64_t)c[3];
+}
+
+// CUDA loads kernels lazily, and loading one may wait for the device to drain.  With sharded tables a rank's
+// kernels wait (on the device) for kernels another rank has yet to launch, so a first-time load in the middle of a
+// scan could wait forever: every kernel of this library is loaded when the first handle is created.
+void preload_kernels(int device)
+{
+        static bool done[64] = { false };
+        if ( device < 0 || device >= 64 || done[device] ) return;
+        cudaFuncAttributes a;
+#define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
+        RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_reads_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
+        RG_PRELOAD(k_ent_hist); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
+        RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
+        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_bucket_probe);
+        RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
+        RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
+        RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay);
+        RG_PRELOAD(k_window_counts); RG_PRELOAD(k_block_bounds); RG_PRELOAD(k_gap_dp); RG_PRELOAD(k_gap_replay);
+#undef RG_PRELOAD
+        done[device] = true;
 }
 
 int check_ready(real_gpu * h)
@@ -530,6 +708,7 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 RG_CUDA(cudaGetDeviceProperties(&prop, params->device));
                 if ( prop.major < 10 ) throw CudaError("device is not sm_100 class; this library only carries sm_100a code");
                 h->sm_count = prop.multiProcessorCount;
+                preload_kernels(params->device);
                 if ( const char * e = getenv("REAL_GPU_PASS_BITS") ) h->pass_bits_override = atoi(e);
                 if ( const char * e = getenv("REAL_GPU_L2_SLICE_MB") ) h->l2_slice_bytes = (uint64_t)atoi(e) << 20;
                 if ( const char * e = getenv("REAL_GPU_CHUNK_MPOS") ) h->chunk_positions = std::max<uint64_t>(SC_TILE_POS, ((uint64_t)atoi(e) << 20) / SC_TILE_POS * SC_TILE_POS);
@@ -562,6 +741,10 @@ int real_gpu_destroy(real_gpu * h)
                            &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
+        for ( int r = 0; r < SC_MAX_RANKS; ++r )
+                if ( h->comm.ipc_opened[r] ) { cudaIpcCloseMemHandle(h->comm.base[r]); h->comm.ipc_opened[r] = false; }
+        for ( int i = 0; i < 2; ++i ) if ( h->comm.ev[i] ) cudaEventDestroy(h->comm.ev[i]);
+        dev_free(h, h->comm.window); dev_free(h, h->comm.ptrs); dev_free(h, h->comm.pairs); dev_free(h, h->comm.error);
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
         for ( int i = 0; i < 8; ++i ) if ( h->ev[i] ) cudaEventDestroy(h->ev[i]);
         if ( h->st ) cudaStreamDestroy(h->st);
@@ -855,6 +1038,8 @@ int real_gpu_match_unique(real_gpu * h)
         }
         // with scores the fold depends on the reference's visiting order (matchUniqueImplementation.cpp:179-248):
         // collect the hits of this file, then replay them per read in that order
+        if ( h->comm.nranks > 1 )
+                return fail(h, REAL_GPU_E_ARG, "match_unique with scores is order dependent: not available with sharded tables");
         if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
                 return fail(h, REAL_GPU_E_ARG, "match_unique with scores needs the whole file in one shard (the fold is order dependent)");
         uint64_t const found = collect_hits_by_read(h);
@@ -970,6 +1155,8 @@ int real_gpu_match_gaps(real_gpu * h, uint64_t n_list_windows)
         if ( rc ) return rc;
         if ( ! h->ll.p )
                 return fail(h, REAL_GPU_E_ARG, "match_gaps needs the scoring table (real_gpu_params::ll_table)");
+        if ( h->comm.nranks > 1 )
+                return fail(h, REAL_GPU_E_ARG, "match_gaps is order dependent: not available with sharded tables");
         if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
                 return fail(h, REAL_GPU_E_ARG, "match_gaps needs the whole file in one shard (the fold is order dependent)");
         if ( h->nrec + 1 > 65536 )
@@ -1013,6 +1200,102 @@ int real_gpu_get_gaps(real_gpu * h, real_gpu_gapinfo * gaps)
         if ( ! gaps ) return fail(h, REAL_GPU_E_ARG, "get_gaps: null pointer");
         if ( h->nreads ) RG_CUDA(cudaMemcpy(gaps, h->gaps.p, h->nreads * sizeof(real_gpu_gapinfo), cudaMemcpyDeviceToHost));
         return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+
+// ---- sharded tables ----------------------------------------------------------------------------
+
+static int comm_finish_connect(real_gpu * h)
+{
+        real_gpu::Comm & CM = h->comm;
+        uint32_t * fl[SC_MAX_RANKS];
+        for ( int r = 0; r < SC_MAX_RANKS; ++r ) fl[r] = reinterpret_cast<uint32_t *>(CM.base[(uint32_t)r < CM.nranks ? r : 0]);
+        RG_CUDA(cudaMemcpy(CM.ptrs.p, fl, sizeof(fl), cudaMemcpyHostToDevice));
+        CM.connected = true;
+        return REAL_GPU_OK;
+}
+
+int real_gpu_comm_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t round_positions, void * handle_out)
+{
+        RG_API_BEGIN(h)
+        if ( nranks < 1 || nranks > (uint32_t)SC_MAX_RANKS || rank >= nranks ) return fail(h, REAL_GPU_E_ARG, "comm_init: rank/nranks out of range (at most 8 ranks)");
+        real_gpu::Comm & CM = h->comm;
+        if ( CM.window.p ) return fail(h, REAL_GPU_E_STATE, "comm_init: already initialised");
+        if ( round_positions == 0 ) round_positions = SC_MAX_CHUNK;
+        round_positions = std::min<uint64_t>(SC_MAX_CHUNK, ((round_positions + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
+        CM.nranks = nranks; CM.rank = rank; CM.epoch = 0; CM.round_positions = round_positions; CM.connected = false;
+        for ( uint32_t r = 0; r <= nranks; ++r ) CM.bucket_lo[r] = (uint32_t)(((uint64_t)r * SC_MAX_BUCKETS) / nranks);
+        uint64_t const per = (round_positions + nranks - 1) / nranks;
+        CM.seg_cap = (uint32_t)(((per + SC_UNIT - 1) / SC_UNIT) * SC_UNIT + (uint64_t)SC_MAX_BUCKETS * SC_UNIT);
+        CM.meta_off = 256;
+        CM.recs_off = 16384;
+        size_t const bytes = CM.recs_off + (size_t)nranks * CM.seg_cap * sizeof(uint4);
+        dev_alloc(h, CM.window, bytes);
+        dev_alloc(h, CM.ptrs, SC_MAX_RANKS * sizeof(void *));
+        dev_alloc(h, CM.pairs, 2048 * 4);
+        dev_alloc(h, CM.error, 16);
+        dev_reserve(h, h->part_meta, (1100 + 256 * SC_CURSOR_STRIDE) * 4);
+        dev_reserve(h, h->counters, 8 * 8);
+        RG_CUDA(cudaMemset(CM.window.p, 0, CM.recs_off));
+        RG_CUDA(cudaMemset(CM.error.p, 0, 16));
+        for ( int i = 0; i < 2; ++i ) RG_CUDA(cudaEventCreateWithFlags(&CM.ev[i], cudaEventDisableTiming));
+        RG_CUDA(cudaDeviceSynchronize());
+        CM.base[rank] = reinterpret_cast<char *>(CM.window.p);
+        h->have_reads = false;            // the index has to be (re)built for this rank's buckets
+        if ( handle_out )
+        {
+                cudaIpcMemHandle_t ih;
+                RG_CUDA(cudaIpcGetMemHandle(&ih, CM.window.p));
+                static_assert(sizeof(ih) == REAL_GPU_COMM_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+                memcpy(handle_out, &ih, sizeof(ih));
+        }
+        if ( nranks == 1 ) return comm_finish_connect(h);
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_comm_connect(real_gpu * h, const void * all_handles)
+{
+        RG_API_BEGIN(h)
+        real_gpu::Comm & CM = h->comm;
+        if ( ! CM.window.p ) return fail(h, REAL_GPU_E_STATE, "comm_connect: call real_gpu_comm_init first");
+        if ( ! all_handles ) return fail(h, REAL_GPU_E_ARG, "comm_connect: null pointer");
+        for ( uint32_t r = 0; r < CM.nranks; ++r )
+        {
+                if ( r == CM.rank || CM.ipc_opened[r] ) continue;
+                cudaIpcMemHandle_t ih;
+                memcpy(&ih, static_cast<const char *>(all_handles) + (size_t)r * REAL_GPU_COMM_HANDLE_BYTES, sizeof(ih));
+                void * p = nullptr;
+                RG_CUDA(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+                CM.base[r] = reinterpret_cast<char *>(p);
+                CM.ipc_opened[r] = true;
+        }
+        return comm_finish_connect(h);
+        RG_API_END(h)
+}
+
+int real_gpu_comm_connect_local(real_gpu * h, real_gpu * const * peers)
+{
+        RG_API_BEGIN(h)
+        real_gpu::Comm & CM = h->comm;
+        if ( ! CM.window.p ) return fail(h, REAL_GPU_E_STATE, "comm_connect_local: call real_gpu_comm_init first");
+        if ( ! peers ) return fail(h, REAL_GPU_E_ARG, "comm_connect_local: null pointer");
+        for ( uint32_t r = 0; r < CM.nranks; ++r )
+        {
+                real_gpu * q = peers[r];
+                if ( ! q || ! q->comm.window.p || q->comm.nranks != CM.nranks || q->comm.rank != r || q->comm.seg_cap != CM.seg_cap )
+                        return fail(h, REAL_GPU_E_ARG, "comm_connect_local: peer handle is not an initialised rank of the same group");
+                if ( q->prm.device != h->prm.device )
+                {
+                        cudaError_t const e = cudaDeviceEnablePeerAccess(q->prm.device, 0);
+                        if ( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled ) RG_CUDA(e);
+                        (void)cudaGetLastError();
+                }
+                CM.base[r] = reinterpret_cast<char *>(q->comm.window.p);
+                CM.local[r] = q;
+        }
+        return comm_finish_connect(h);
         RG_API_END(h)
 }
 

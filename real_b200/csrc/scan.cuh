@@ -54,6 +54,9 @@ static const int SC_QB_CAP = 64;                             // per-warp stage B
 static const uint32_t SC_POS_NONE = 0xFFFFFFFFu;             // position word of a padding record
 static const uint64_t SC_MAX_CHUNK = 1ull << 30;             // positions per chunk: position (30 bits) and table (2 bits) share a word
 
+static const int SC_MAX_RANKS = 8;                           // GPUs of one NVSwitch box that can share a scan (sharded tables)
+static const int SC_META_STRIDE = SC_MAX_BUCKETS + 8;        // u32 per source in a rank's bucket-count area
+
 struct TableDev
 {
         const SlotWord * slots;
@@ -67,7 +70,8 @@ struct ScanParams
         const uint64_t * text;        // local word 0; valid from -TEXT_PAD_WORDS
         const uint64_t * nmask;       // local mask word 0
         uint64_t shard_begin;         // global position of local base 0
-        uint64_t x_begin, x_end;      // local text positions whose keys are probed
+        uint64_t x_begin, x_end;      // local text positions whose keys are probed (by this rank, this round)
+        uint64_t pos_base;            // local text position the record positions are relative to (first position of the round)
         uint64_t win_begin, win_end;  // local seed-window starts this shard evaluates
         uint64_t own_begin, own_end;  // GLOBAL hit start positions this shard reports
         TableDev tab[3];
@@ -81,7 +85,7 @@ struct ScanParams
         // partition of the chunk [x_begin, x_end): x0 = first position of the chunk
         uint32_t bucket_bits;
         uint32_t debug_flags;         // development only (REAL_GPU_DEBUG): 1 = count set slot bits but do not follow them
-        uint4 * recs;                 // records grouped by bucket: {window lo, window hi, 16 bases in front of it, position - x_begin}
+        uint4 * recs;                 // records grouped by bucket: {window lo, window hi, 16 bases in front of it, position - pos_base}
         uint32_t * bucket_count;      // [SC_MAX_BUCKETS]
         uint32_t * bucket_start;      // [SC_MAX_BUCKETS+1] record index
         uint32_t * bucket_cursor;     // [SC_MAX_BUCKETS]
@@ -92,7 +96,27 @@ struct ScanParams
         unsigned long long * hit_count;
         unsigned long long * info;
         unsigned long long * stats;   // [0] candidates  [1] seed-pass  [2] hits
+        // Sharded tables (nranks > 1, one rank per GPU): rank r holds the tables of the buckets [bucket_lo[r], bucket_lo[r+1])
+        // only.  Every rank partitions its slice of the round's positions and writes the records of a bucket straight
+        // into the record area of the bucket's owner (peer memory over NVLink); the owner probes what arrived.
+        uint32_t nranks, rank;
+        uint32_t bucket_lo[SC_MAX_RANKS + 1];
+        uint4 * peer_recs[SC_MAX_RANKS];        // record area of every rank (own included); source s writes from record s * seg_cap
+        uint32_t * peer_meta[SC_MAX_RANKS];     // bucket-count area of every rank: [source][SC_META_STRIDE] padded record counts
+        uint32_t seg_cap;                       // records a source may deliver to one rank in a round
+        uint32_t * pair_grab;                   // probe side: first grab of every (own bucket, source) pair, bucket-major, + total
+        uint32_t * pair_rec;                    //             first record of the pair in the local record area
+        uint32_t npairs;
 };
+
+__device__ __forceinline__ uint32_t bucket_owner(ScanParams const & P, uint32_t b)
+{
+        uint32_t r = 0;
+        #pragma unroll
+        for ( int i = 1; i < SC_MAX_RANKS; ++i )
+                if ( (uint32_t)i < P.nranks && b >= P.bucket_lo[i] ) r = i;
+        return r;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -301,7 +325,8 @@ struct ScatterSmem
         uint64_t bar[2];
         uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];    // per-warp counts, then running slots
         uint32_t loc[SC_MAX_BUCKETS + 1];                  // first staging slot of a bucket
-        uint32_t base[SC_MAX_BUCKETS];                     // first global record of the tile's run in a bucket
+        uint32_t base[SC_MAX_BUCKETS];                     // first record of the tile's run in a bucket (index into the owner's record area)
+        uint4 * area[SC_MAX_BUCKETS];                      // record area of the bucket's owner
         uint8_t stage_b[PS_TILE_POS];
 };
 
@@ -327,6 +352,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
         }
         #pragma unroll
         for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        S.area[threadIdx.x] = P.peer_recs[bucket_owner(P, threadIdx.x)];
         __syncthreads();
 
         uint64_t tile_id = first_tile + blockIdx.x;
@@ -422,13 +448,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 // (4) copy out: consecutive threads write consecutive records of a bucket run
                 {
                         uint32_t const n = S.loc[SC_MAX_BUCKETS];
-                        uint32_t const pos0 = (uint32_t)(tile_x0 - P.x_begin);      // may wrap for the clipped first tile; the sums below do not
+                        uint32_t const pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums below do not
                         for ( uint32_t i = threadIdx.x; i < n; i += SC_THREADS )
                         {
                                 uint32_t const b = S.stage_b[i];
                                 uint4 r = S.stage[i];
                                 r.w += pos0;
-                                P.recs[S.base[b] + (i - S.loc[b])] = r;
+                                S.area[b][S.base[b] + (i - S.loc[b])] = r;
                         }
                 }
                 __syncthreads();
@@ -438,30 +464,92 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
         }
 }
 
-// one block: bucket starts (every bucket padded to whole grabs), cursors, sentinel records in the padding
+// one block: bucket starts (every bucket padded to whole grabs), cursors, sentinel records in the padding.
+// The records of bucket b go to the record area of b's owner, into this rank's segment of it (from record
+// rank * seg_cap), bucket after bucket; the owner is told the padded size of every bucket it is sent.
 __global__ void __launch_bounds__(SC_MAX_BUCKETS) k_part_offsets(ScanParams P)
 {
         __shared__ uint32_t sc[SC_MAX_BUCKETS], st[SC_MAX_BUCKETS + 1];
         uint32_t const c = P.bucket_count[threadIdx.x];
-        sc[threadIdx.x] = c;
+        uint32_t const padded = ((c + SC_UNIT - 1) / SC_UNIT) * SC_UNIT;
+        sc[threadIdx.x] = padded;
         __syncthreads();
         if ( threadIdx.x == 0 )
         {
                 uint32_t a = 0;
-                for ( int b = 0; b < SC_MAX_BUCKETS; ++b )
+                for ( uint32_t d = 0; d < P.nranks; ++d )
                 {
-                        st[b] = a;
-                        a += ((sc[b] + SC_UNIT - 1) / SC_UNIT) * SC_UNIT;
+                        a = P.rank * P.seg_cap;
+                        for ( uint32_t b = P.bucket_lo[d]; b < P.bucket_lo[d+1]; ++b ) { st[b] = a; a += sc[b]; }
                 }
-                st[SC_MAX_BUCKETS] = a;
+                st[SC_MAX_BUCKETS] = a;            // single rank: the total (all buckets are in one area)
                 *P.unit_counter = 0;
         }
         __syncthreads();
+        uint32_t const owner = bucket_owner(P, threadIdx.x);
         P.bucket_start[threadIdx.x] = st[threadIdx.x];
         if ( threadIdx.x == 0 ) P.bucket_start[SC_MAX_BUCKETS] = st[SC_MAX_BUCKETS];
         P.bucket_cursor[threadIdx.x * SC_CURSOR_STRIDE] = 0;
-        for ( uint32_t r = st[threadIdx.x] + c; r < st[threadIdx.x + 1]; ++r )
-                P.recs[r] = make_uint4(0, 0, 0, SC_POS_NONE);
+        uint4 * area = P.peer_recs[owner];
+        for ( uint32_t r = st[threadIdx.x] + c; r < st[threadIdx.x] + padded; ++r )
+                area[r] = make_uint4(0, 0, 0, SC_POS_NONE);
+        if ( P.nranks > 1 )
+                P.peer_meta[owner][P.rank * SC_META_STRIDE + threadIdx.x] = padded;
+}
+
+// ---- cross-rank hand-over (sharded tables) ----------------------------------------------------------
+// flags[slot * SC_MAX_RANKS + source] in every rank's window holds the last round `source` has completed for
+// that slot (0: its records of the round are delivered, 1: it has consumed the records it was sent).  Kernel
+// boundaries order the data stores before the signal; the signal is a system-scope release store into peer
+// memory, the wait an acquire load of local memory.
+__global__ void k_comm_signal(uint32_t * const * peer_flags, uint32_t nranks, uint32_t rank, uint32_t slot, uint32_t epoch)
+{
+        if ( threadIdx.x < nranks )
+        {
+                __threadfence_system();
+                uint32_t * f = peer_flags[threadIdx.x] + slot * SC_MAX_RANKS + rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(f), "r"(epoch) : "memory");
+        }
+}
+
+// spins until every rank has signalled `epoch` (or later) in `slot`; gives up after timeout_cycles and raises *error
+__global__ void k_comm_wait(const uint32_t * flags, uint32_t nranks, uint32_t slot, uint32_t epoch, long long timeout_cycles, uint32_t * error)
+{
+        if ( threadIdx.x < nranks )
+        {
+                const uint32_t * f = flags + slot * SC_MAX_RANKS + threadIdx.x;
+                long long const t0 = clock64();
+                uint32_t v;
+                while ( true )
+                {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                        if ( (int32_t)(v - epoch) >= 0 ) break;
+                        if ( clock64() - t0 > timeout_cycles ) { *error = 1 + threadIdx.x; break; }
+                        __nanosleep(200);
+                }
+        }
+}
+
+// owner side: the (bucket, source) pairs of the round in bucket-major order -> first grab / first record of each
+static const int SC_PAIR_THREADS = 512;                      // >= own buckets * ranks for any rank count up to SC_MAX_RANKS
+__global__ void __launch_bounds__(SC_PAIR_THREADS) k_comm_pairs(ScanParams P, const uint32_t * meta)
+{
+        __shared__ uint32_t roff[SC_MAX_RANKS][SC_MAX_BUCKETS];
+        uint32_t const lo = P.bucket_lo[P.rank], nb = P.bucket_lo[P.rank + 1] - lo;
+        if ( threadIdx.x < P.nranks )
+        {
+                uint32_t a = threadIdx.x * P.seg_cap;
+                for ( uint32_t b = 0; b < nb; ++b ) { roff[threadIdx.x][b] = a; a += meta[threadIdx.x * SC_META_STRIDE + lo + b]; }
+        }
+        __syncthreads();
+        uint32_t const npairs = nb * P.nranks;                // < SC_PAIR_THREADS
+        uint32_t const p = threadIdx.x;
+        uint32_t const b = p / P.nranks, src = p - b * P.nranks;
+        uint32_t const g = (p < npairs) ? meta[src * SC_META_STRIDE + lo + b] / SC_UNIT : 0;
+        uint32_t total;
+        uint32_t const ex = block_excl_scan(g, &total);
+        if ( p < npairs ) { P.pair_grab[p] = ex; P.pair_rec[p] = roff[src][b]; }
+        if ( p == 0 ) { P.pair_grab[npairs] = total; *P.unit_counter = 0; }
 }
 
 // ---- probe -------------------------------------------------------------------------------------
@@ -579,7 +667,7 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
         int const table = (int)(it.post >> 30);
         uint32_t const F = P.F;
         uint64_t const fm = (1ULL << (2*F)) - 1;
-        uint64_t const lx = P.x_begin + (it.post & 0x3FFFFFFFu);
+        uint64_t const lx = P.pos_base + (it.post & 0x3FFFFFFFu);
         while ( e != ENTRY_NONE )
         {
                 uint4 const raw = ld_hot_v4(P.tab[table].E + e, pol_e);
@@ -666,6 +754,20 @@ __device__ __forceinline__ uint32_t drain_a_warp(ScanParams const & P, ProbeSmem
         return n;
 }
 
+// the 512 records of grab g
+__device__ __forceinline__ const uint4 * grab_records(ScanParams const & P, uint32_t g)
+{
+        if ( ! P.npairs )
+                return P.recs + (uint64_t)g * SC_UNIT;
+        uint32_t lo = 0, hi = P.npairs;                 // last pair with pair_grab <= g
+        while ( hi - lo > 1 )
+        {
+                uint32_t const mid = (lo + hi) >> 1;
+                if ( __ldg(P.pair_grab + mid) <= g ) lo = mid; else hi = mid;
+        }
+        return P.recs + (uint64_t)__ldg(P.pair_rec + lo) + (uint64_t)(g - __ldg(P.pair_grab + lo)) * SC_UNIT;
+}
+
 __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(const __grid_constant__ ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
@@ -680,8 +782,9 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
         #pragma unroll
         for ( int s = 0; s < 3; ++s ) S.stat[s][threadIdx.x] = 0;
         __syncwarp();
-        uint32_t const total = P.bucket_start[SC_MAX_BUCKETS];           // padded to whole grabs
-        uint32_t const ngrabs = total / SC_UNIT;
+        // single rank: the record area holds the buckets back to back, padded to whole grabs; sharded: the grabs are
+        // numbered pair by pair (own bucket, source), see k_comm_pairs
+        uint32_t const ngrabs = P.npairs ? P.pair_grab[P.npairs] : P.bucket_start[SC_MAX_BUCKETS] / SC_UNIT;
 
         uint32_t const F = P.F;
         uint32_t const kb = P.keybits;
@@ -704,7 +807,7 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
                 // The records of a step are not held in registers ahead of time (the candidate path below needs the
                 // registers): they are pulled into L2 two steps ahead with prefetches -- across the grab boundary too --
                 // and loaded when the step starts.
-                const uint4 * rp = P.recs + (uint64_t)g * SC_UNIT;
+                const uint4 * rp = grab_records(P, g);
                 #pragma unroll 1
                 for ( int step = 0; step < NSTEP; ++step )
                 {
@@ -712,8 +815,9 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
                                 gn = __shfl_sync(0xffffffffu, gn, 0);
                         {
                                 int const ps = step + 2;
-                                const uint4 * pb = (ps < NSTEP) ? (rp + ps * 32 * SC_RPT) : (P.recs + (uint64_t)gn * SC_UNIT + (ps - NSTEP) * 32 * SC_RPT);
-                                if ( lane < STEP_LINES && (ps < NSTEP || gn < ngrabs) )
+                                bool const pv = ps < NSTEP || gn < ngrabs;
+                                const uint4 * pb = (ps < NSTEP) ? (rp + ps * 32 * SC_RPT) : (pv ? grab_records(P, gn) + (ps - NSTEP) * 32 * SC_RPT : rp);
+                                if ( lane < STEP_LINES && pv )
                                         asm volatile("prefetch.global.L2 [%0];" :: "l"(pb + lane * 8));
                         }
                         uint4 cur[SC_RPT];

@@ -99,6 +99,9 @@ def load(build_if_missing: bool = True):
     L.real_gpu_unique_import.argtypes = [vp, vp, vp]
     L.real_gpu_match_gaps.argtypes = [vp, u64]
     L.real_gpu_get_gaps.argtypes = [vp, vp]
+    L.real_gpu_comm_init.argtypes = [vp, u32, u32, u64, vp]
+    L.real_gpu_comm_connect.argtypes = [vp, vp]
+    L.real_gpu_comm_connect_local.argtypes = [vp, vp]
     L.real_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.real_gpu_stream.argtypes = [vp]
     L.real_gpu_stream.restype = vp
@@ -240,6 +243,20 @@ class Handle:
 
     def unique_import(self, d_min_keys: int, d_tie_sums: int):
         self._check(self.L.real_gpu_unique_import(self.h, d_min_keys, d_tie_sums))
+
+    # ---- sharded tables (one handle per rank)
+    def comm_init(self, rank: int, nranks: int, round_positions: int = 0) -> bytes:
+        """Allocates this rank's window; returns the 64-byte handle the other ranks connect with."""
+        buf = C.create_string_buffer(64)
+        self._check(self.L.real_gpu_comm_init(self.h, rank, nranks, round_positions, buf))
+        return buf.raw
+
+    def comm_connect(self, all_handles: bytes):
+        self._check(self.L.real_gpu_comm_connect(self.h, all_handles))
+
+    def comm_connect_local(self, peers):
+        arr = (C.c_void_p * len(peers))(*[p.h for p in peers])
+        self._check(self.L.real_gpu_comm_connect_local(self.h, arr))
 
     def match_gaps(self, n_list: int = 0):
         self._check(self.L.real_gpu_match_gaps(self.h, n_list))

@@ -1,0 +1,196 @@
+"""GPU: the sharded-table form of the scan (include/real_gpu.h, real_gpu_comm_*), the multi-GPU path of SURVEY.md 8(e).
+
+One GPU is enough to exercise it: the ranks are handles of this process on the same device, connected with
+real_gpu_comm_connect_local and driven from one host thread each -- exactly what one process per GPU does, except
+that the peer windows are reached through plain device pointers instead of CUDA IPC mappings.  Every rank builds the
+tables of its own buckets only, partitions its slice of every round's text positions and writes the window records
+into the owners' windows; the results (union of the hits / merged unique states) must equal the oracle's."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from real_b200 import matcher, synth
+from util import canon_hits
+
+pytestmark = pytest.mark.gpu
+
+
+def _fresh(seed, n=900_000, nreads=20_000, L=100, nrec=5, npm=1500, sub=0.012):
+    text = synth.make_text(seed, n, nrecords=nrec, n_per_million=npm)
+    sym = text.symbols.copy()
+    sym[n // 2:n // 2 + 20000] = sym[1000:21000]          # a repeat => multi-hit reads
+    text = synth.Text(sym, text.records)
+    reads = synth.make_reads(text, seed + 1, nreads, L, sub, fastq=False)
+    return text, reads
+
+
+def _ranks(cls, opts, nranks, round_positions, table_bits=0):
+    ms = [cls(opts, table_bits=table_bits) for _ in range(nranks)]
+    for r, m in enumerate(ms):
+        m.handle.comm_init(r, nranks, round_positions)
+    for m in ms:
+        m.handle.comm_connect_local([x.handle for x in ms])
+    return ms
+
+
+def _run_threads(fns):
+    """One host thread per rank (the ranks wait for each other on the device)."""
+    errs, outs = [], [None] * len(fns)
+
+    def run(i):
+        try:
+            outs[i] = fns[i]()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(len(fns))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ts), "a rank is stuck"
+    if errs:
+        raise errs[0]
+    return outs
+
+
+@pytest.mark.parametrize("nranks,round_positions,e,table_bits", [(2, 1 << 18, 4, 0), (4, 1 << 19, 3, 0), (3, 1 << 30, 4, 24), (8, 1 << 17, 4, 0)])
+def test_sharded_match_all_vs_oracle(nranks, round_positions, e, table_bits):
+    text, reads = _fresh(100 + nranks)
+    kw = dict(seedl=32, seedkmax=2, totalkmax=e, scores=False)
+    ref = O.match_all(text, reads, **kw)
+    ms = _ranks(matcher.AllMatcher, matcher.RealOptions(**kw), nranks, round_positions, table_bits)
+    try:
+        words, nmask = text.packed()
+        for m in ms:
+            m.set_reads(reads.mapped, reads.offsets, None)
+            m.set_text(words, nmask, text.n, text.record_starts)
+        parts = _run_threads([m.match for m in ms])
+        entries = [m.stats()["n_candidates"] for m in ms]
+    finally:
+        for m in ms:
+            m.close()
+    got = np.concatenate(parts)
+    a, b = canon_hits(got), canon_hits(ref)
+    assert len(b) > reads.nreads // 2
+    assert a.shape == b.shape and np.array_equal(a, b)       # every hit found by exactly one rank
+    assert sum(1 for p in parts if len(p)) == nranks and min(entries) > 0
+
+
+@pytest.mark.parametrize("nranks,round_positions", [(2, 1 << 19), (4, 1 << 18)])
+def test_sharded_match_unique_two_files_vs_oracle(nranks, round_positions):
+    import torch
+    t0, reads0 = _fresh(31, n=500_000, nreads=8000)
+    t1, reads1 = _fresh(33, n=300_000, nreads=4000, nrec=2)
+    sym = t1.symbols.copy()
+    sym[5000:45000] = t0.symbols[30000:70000]            # cross-file repeats
+    t1 = synth.Text(sym, t1.records)
+    reads = synth.concat_reads([reads0, reads1])
+    kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    info_ref, _ = O.unique_init(reads.nreads, False)
+    for fi, t in enumerate((t0, t1)):
+        O.match_unique(t, reads, info_ref, None, fileid=fi, **kw)
+
+    ms = _ranks(matcher.UniqueMatcher, matcher.RealOptions(**kw), nranks, round_positions)
+    try:
+        dev = torch.device("cuda", 0)
+        for m in ms:
+            m.set_reads(reads.mapped, reads.offsets, None)
+        for fi, t in enumerate((t0, t1)):
+            words, nmask = t.packed()
+            for m in ms:
+                m.set_text(words, nmask, t.n, t.record_starts, fileid=fi)
+            _run_threads([m.match for m in ms])
+            # the exchange of real_b200.dist.unique_exchange (MIN of the keys, SUM of the ties), emulated on one device
+            keys = [torch.empty(reads.nreads, dtype=torch.int64, device=dev) for _ in ms]
+            ties = [torch.empty(reads.nreads, dtype=torch.uint8, device=dev) for _ in ms]
+            for g, m in enumerate(ms):
+                m.handle.unique_export_keys(keys[g].data_ptr())
+            kmin = torch.stack(keys).min(dim=0).values.contiguous()
+            for g, m in enumerate(ms):
+                m.handle.unique_export_ties(kmin.data_ptr(), ties[g].data_ptr())
+            tsum = torch.stack(ties).sum(dim=0).to(torch.uint8).contiguous()
+            torch.cuda.synchronize()
+            for m in ms:
+                m.handle.unique_import(kmin.data_ptr(), tsum.data_ptr())
+        infos = [m.info()[0] for m in ms]
+    finally:
+        for m in ms:
+            m.close()
+    want = matcher.canonical_unique(info_ref)
+    states = matcher.umi_state(info_ref)
+    assert (states == 4).sum() > 50 and (states == 1).sum() > 1000 and (states == 2).sum() > 1000
+    for info in infos:
+        assert np.array_equal(matcher.canonical_unique(info), want)
+
+
+def test_sharded_mode_refusals():
+    """Order dependent folds need the whole table set in one handle; a rank that was never connected must not scan."""
+    from real_b200 import lib as rlib
+    text, reads = _fresh(77, n=200_000, nreads=1000)
+    words, nmask = text.packed()
+    m = matcher.UniqueMatcher(matcher.RealOptions(seedl=32, seedkmax=2, totalkmax=4, scores=False))
+    try:
+        m.handle.comm_init(0, 2, 1 << 18)
+        m.set_reads(reads.mapped, reads.offsets, None)
+        m.set_text(words, nmask, text.n, text.record_starts)
+        with pytest.raises(rlib.RealGpuError):
+            m.match()
+    finally:
+        m.close()
+
+
+def _ipc_rank(rank, nranks, conn, seed):
+    """One rank in its own process (what one process per GPU does); the windows are mapped with CUDA IPC."""
+    import os
+    os.environ["REAL_GPU_COMM_TIMEOUT_MS"] = "20000"
+    from real_b200 import matcher as M
+    text, reads = _fresh(seed, n=400_000, nreads=6000)
+    m = M.AllMatcher(M.RealOptions(seedl=32, seedkmax=2, totalkmax=4, scores=False))
+    try:
+        conn.send(m.handle.comm_init(rank, nranks, 1 << 18))
+        m.handle.comm_connect(conn.recv())
+        m.set_reads(reads.mapped, reads.offsets, None)
+        words, nmask = text.packed()
+        m.set_text(words, nmask, text.n, text.record_starts)
+        conn.send("ready")
+        conn.recv()
+        conn.send(m.match())
+        conn.recv()                 # keep the window mapped until every rank is done
+    finally:
+        m.close()
+
+
+def test_sharded_two_processes_ipc():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    nranks, seed = 2, 55
+    pipes = [ctx.Pipe() for _ in range(nranks)]
+    procs = [ctx.Process(target=_ipc_rank, args=(r, nranks, pipes[r][1], seed)) for r in range(nranks)]
+    for p in procs:
+        p.start()
+    try:
+        def get(c):
+            assert c.poll(180), "a rank process did not answer"
+            return c.recv()
+        handles = b"".join(get(pipes[r][0]) for r in range(nranks))
+        for r in range(nranks):
+            pipes[r][0].send(handles)
+        for r in range(nranks):
+            assert get(pipes[r][0]) == "ready"
+        for r in range(nranks):
+            pipes[r][0].send("go")
+        parts = [get(pipes[r][0]) for r in range(nranks)]
+        for r in range(nranks):
+            pipes[r][0].send("done")
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.terminate()
+    text, reads = _fresh(seed, n=400_000, nreads=6000)
+    ref = O.match_all(text, reads, seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    a, b = canon_hits(np.concatenate(parts)), canon_hits(ref)
+    assert len(b) > 3000 and a.shape == b.shape and np.array_equal(a, b)
+    assert all(len(p) for p in parts)
