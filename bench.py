@@ -195,6 +195,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--table-bits", type=int, default=0)
+    ap.add_argument("--parallel", default="tables", choices=["tables", "text"],
+                    help="N>1: 'tables' = signature tables sharded, window records exchanged through peer memory (default); "
+                         "'text' = text sharded with a read-length halo, index replicated on every rank")
+    ap.add_argument("--round-mpos", type=int, default=0, help="sharded tables: text positions per round in units of 2^20 (0 = 2^30 positions)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-text", type=int, default=32_000_000, help="reference arm: text bases of the sample")
@@ -232,7 +236,8 @@ def main():
     n, R, L = wl["n"], wl["reads"], wl["L"]
     unique = wl["mode"] == "unique"
     rs = record_starts(n, wl["nrec"])
-    ob, oe, sb, sl = matcher.shard_ranges(n, world, L)[rank]
+    tables_mode = world > 1 and args.parallel == "tables"
+    ob, oe, sb, sl = (0, n, 0, n) if (tables_mode or world == 1) else matcher.shard_ranges(n, world, L)[rank]
 
     # ---- synthetic inputs, generated on the device: this rank's text shard and the whole read set.
     # Reads are cut from the whole text, so they are generated from a transient full copy.
@@ -248,6 +253,8 @@ def main():
 
     ll = matcher.scoring_table() if wl["scores"] else None
     h = rlib.Handle(seedl=32, seedkmax=2, totalkmax=wl["e"], scores=wl["scores"], ll_table=ll, device=local, table_bits=args.table_bits)
+    if tables_mode:
+        rdist.connect_sharded_tables(h, dev, round_positions=args.round_mpos << 20)
     shard = rdist.HandleShard(h, R)
     keys = torch.empty(R, dtype=torch.int64, device=dev) if unique else None
     ties = torch.empty(R, dtype=torch.uint8, device=dev) if unique else None
@@ -411,7 +418,10 @@ def main():
             "metric": "matching-path reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["desc"], "text_bases": n, "reads": R, "read_len": L, "mode": wl["mode"], "scores": wl["scores"],
-                       "parallelism": "text sharded x%d with %d-base halo, read index replicated" % (world, L),
+                       "parallelism": ("signature tables sharded x%d: every rank indexes 1/%d of the buckets, partitions 1/%d of the text positions of a round "
+                                       "and stores the window records into the owners' windows (peer memory over NVLink); reads and text replicated"
+                                       % (world, world, world)) if tables_mode else
+                                      ("text sharded x%d with %d-base halo, read index replicated" % (world, L)),
                        "l2": "inputs larger than L2 (text %.0f MB/GPU, index tables > 1.8 GB): no flush needed" % (sl / 4 / 1e6),
                        "table_bits": args.table_bits or 32},
             "text_gbp_per_s": n / (ms_per_step * 1e-3) / 1e9,

@@ -343,7 +343,7 @@ __device__ __forceinline__ void ep_layout(EntryPartSmem & S, const uint32_t * __
 }
 __device__ __forceinline__ void ep_place(EntryPartSmem & S, int wid, uint32_t lt, bool ok, uint32_t b, uint64_t seed, uint32_t val)
 {
-        uint32_t const peers = __match_any_sync(0xffffffffu, ok ? b : 0x100u);
+        uint32_t const peers = peers_u8(b, ok);
         uint32_t const below = __popc(peers & lt);
         uint32_t pre = 0;
         if ( ok ) pre = S.wcnt[wid][b];

@@ -27,6 +27,23 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
         return v;
 }
 
+// Lanes of the warp that hold the same 8-bit value as this lane (among the lanes with ok set; lanes without ok get
+// an unspecified mask).  One ballot per bit: measured on B200 (tools/match_bench.cu) MATCH.ANY costs ~2 cycles per
+// DISTINCT value on a unit shared by the whole SM -- 58 cycles per warp for random bytes, which made the multisplit
+// ranking the bottleneck of every partition kernel -- against ~32 cycles for the eight ballots.
+__device__ __forceinline__ uint32_t peers_u8(uint32_t v, bool ok)
+{
+        uint32_t peers = __ballot_sync(0xffffffffu, ok);
+        #pragma unroll
+        for ( int b = 0; b < 8; ++b )
+        {
+                bool const bit = (v >> b) & 1u;
+                uint32_t const bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+        }
+        return peers;
+}
+
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = block sum
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t * total)
 {

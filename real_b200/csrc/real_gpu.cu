@@ -567,8 +567,13 @@ uint64_t run_scan(real_gpu * h, int mode)
                 if ( const char * e = getenv("REAL_GPU_COMM_TIMEOUT_MS") ) wait_ms = atoll(e);
 
                 h->stats.n_windows = 0;
+                // REAL_GPU_TRACE=1: per-round phase times on stderr (development)
+                bool const trace = getenv("REAL_GPU_TRACE") != nullptr;
+                std::vector<cudaEvent_t> tev;
+                auto mark = [&]() { if ( trace ) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->st); tev.push_back(e); } };
                 for ( uint64_t cb = x_begin; cb < x_end; cb += chunk_cap )
                 {
+                        mark();
                         uint64_t const ce = std::min<uint64_t>(x_end, cb + chunk_cap);
                         P.pos_base = cb;
                         P.x_begin = cb; P.x_end = ce;
@@ -590,11 +595,13 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 k_part_hist<<<pgrid, SC_THREADS, psmem, h->st>>>(P);
                                 RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
                         }
+                        mark();
                         if ( sharded )
                         {
                                 // the owners must have consumed the previous round before their record areas are written again
                                 comm_wait(h, 1, CM.epoch - 1, wait_ms);
                         }
+                        mark();
                         k_part_offsets<<<1, SC_MAX_BUCKETS, 0, h->st>>>(P);
                         RG_KERNEL_CHECK();
                         if ( any )
@@ -604,6 +611,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
                                 RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
                         }
+                        mark();
                         if ( sharded )
                         {
                                 comm_signal(h, 0);
@@ -611,8 +619,10 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 k_comm_pairs<<<1, SC_PAIR_THREADS, 0, h->st>>>(P, reinterpret_cast<uint32_t *>(CM.base[CM.rank] + CM.meta_off));
                                 RG_KERNEL_CHECK(); launch_count(h);
                         }
+                        mark();
                         k_bucket_probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
+                        mark();
                         if ( sharded )
                         {
                                 comm_signal(h, 1);
@@ -621,6 +631,17 @@ uint64_t run_scan(real_gpu * h, int mode)
                         h->stats.scan_launches += 2;
                 }
                 P.x_begin = x_begin; P.x_end = x_end;
+                if ( trace )
+                {
+                        RG_CUDA(cudaStreamSynchronize(h->st));
+                        static const char * names[6] = { "hist", "wait_consumed", "offsets+scatter", "handover", "probe", "" };
+                        for ( size_t i = 0; i + 1 < tev.size(); ++i )
+                        {
+                                if ( i % 6 == 5 ) continue;
+                                fprintf(stderr, "[trace rank %u round %zu] %-16s %8.3f ms\n", CM.rank, i / 6, names[i % 6], elapsed(tev[i], tev[i+1]));
+                        }
+                        for ( cudaEvent_t e : tev ) cudaEventDestroy(e);
+                }
         }
         RG_CUDA(cudaEventRecord(h->ev[6], h->st));
         unsigned long long c[4] = {0, 0, 0, 0};

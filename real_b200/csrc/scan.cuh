@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
 // consecutive records of one bucket: scattering records straight from the threads that produce them
 // leaves ~200 KB of half-written lines open per CTA, more than L2 holds for a full grid (measured: 2 GB
 // of DRAM reads and 5 GB of writes for 3 GB of records, 10 ms per 250 M positions).  Ranks come from a
-// warp-level multisplit (__match_any_sync on the bucket id): shared-memory atomics that return a value
+// warp-level multisplit (peers_u8 on the bucket id: one ballot per bit): shared-memory atomics that return a value
 // serialise far too much for this.
 #ifndef REAL_PS_PPT
 #define REAL_PS_PPT 8
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                                 uint32_t const j = j0 + jb + u;
                                 v[u] = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
                                 b[u] = (uint32_t)(v[u] >> bsh) & bmask;
-                                peers[u] = __match_any_sync(0xffffffffu, ((m >> (jb + u)) & 1) ? b[u] : 0x100u);
+                                peers[u] = peers_u8(b[u], (m >> (jb + u)) & 1);
                         }
                         #pragma unroll
                         for ( uint32_t u = 0; u < 4; ++u )
@@ -806,13 +806,14 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
 
                 // The records of a step are not held in registers ahead of time (the candidate path below needs the
                 // registers): they are pulled into L2 two steps ahead with prefetches -- across the grab boundary too --
-                // and loaded when the step starts.
+                // and loaded when the step starts (holding the next step's records in registers instead: 83 vs 76 ms scan on C3).
                 const uint4 * rp = grab_records(P, g);
                 #pragma unroll 1
                 for ( int step = 0; step < NSTEP; ++step )
                 {
                         if ( step == NSTEP - 2 )
                                 gn = __shfl_sync(0xffffffffu, gn, 0);
+                        uint4 cur[SC_RPT];
                         {
                                 int const ps = step + 2;
                                 bool const pv = ps < NSTEP || gn < ngrabs;
@@ -820,7 +821,6 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
                                 if ( lane < STEP_LINES && pv )
                                         asm volatile("prefetch.global.L2 [%0];" :: "l"(pb + lane * 8));
                         }
-                        uint4 cur[SC_RPT];
                         #pragma unroll
                         for ( int k = 0; k < SC_RPT; ++k ) cur[k] = __ldcs(rp + step * 32 * SC_RPT + k * 32 + lane);
                         // one 8-byte probe per record and table: presence bits of the slot's word + rank of its first slot

@@ -1,4 +1,10 @@
-"""Multi-GPU layer of the matching path: one process per GPU, text sharded, read index replicated.
+"""Multi-GPU layer of the matching path: one process per GPU.
+
+Default form (connect_sharded_tables): the signature tables are sharded -- every rank indexes 1/N of the scan
+buckets, partitions 1/N of the text positions of every round, and its partition kernel stores the window records
+straight into the windows of the bucket owners (peer memory over NVLink, include/real_gpu.h "sharded tables").
+torch.distributed only carries the 64-byte window handles at set-up and the matchUnique fold below.  The older
+form (text sharded with a read-length halo, read index replicated on every rank) needs no set-up at all.
 
 matchAll needs no exchange (every shard reports the hits that START in its own range).  matchUnique
 has exactly one exchange step per text file, the cross-shard fold of the per-read UniqueMatchInfo
@@ -58,3 +64,17 @@ def unique_exchange(shard, group: Optional[dist.ProcessGroup] = None, keys: Opti
         dist.all_reduce(ties, op=dist.ReduceOp.SUM, group=group)
         shard.sync()
     shard.import_merged(keys, ties)
+
+
+def connect_sharded_tables(handle, device: torch.device, round_positions: int = 0, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Puts `handle` (this rank's real_gpu handle) into sharded-table mode with all ranks of `group`: allocates the
+    rank's window, exchanges the CUDA IPC handles (64 bytes per rank) and maps the peers' windows.  Call before
+    set_reads; afterwards every rank is given the whole text and the whole read set."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = handle.comm_init(rank, world, round_positions)
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    handle.comm_connect(b"".join(bytes(p.cpu().tolist()) for p in parts))
+    dist.barrier(group=group)

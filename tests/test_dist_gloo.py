@@ -79,11 +79,29 @@ class NumpyShard:
         pass
 
 
+class FakeHandle:
+    """Stands in for real_b200.lib.Handle in the window set-up (no GPU here): records what it is given."""
+
+    def __init__(self):
+        self.got = None
+
+    def comm_init(self, rank, nranks, round_positions):
+        self.args = (rank, nranks, round_positions)
+        return bytes([rank + 1]) * 64
+
+    def comm_connect(self, all_handles):
+        self.got = all_handles
+
+
 def _worker(rank, world, port, shard_infos, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        fh = FakeHandle()
+        rdist.connect_sharded_tables(fh, torch.device("cpu"), round_positions=1 << 20)
+        assert fh.args == (rank, world, 1 << 20)
+        assert fh.got == b"".join(bytes([r + 1]) * 64 for r in range(world))       # the handles of all ranks, in rank order
         sh = NumpyShard(shard_infos[rank].copy())
         rdist.unique_exchange(sh)
         np.save(out_path % rank, sh.info)
@@ -91,7 +109,8 @@ def _worker(rank, world, port, shard_infos, out_path):
         dist.destroy_process_group()
 
 
-def test_unique_exchange_world2_gloo(tmp_path):
+@pytest.mark.parametrize("split", ["text", "tables"])
+def test_unique_exchange_world2_gloo(tmp_path, split):
     text = synth.make_text(77, 120_000, nrecords=3, n_per_million=1500)
     sym = text.symbols.copy()
     sym[70_000:76_000] = sym[10_000:16_000]          # repeats across the shard boundary => cross-shard ties
@@ -103,7 +122,14 @@ def test_unique_exchange_world2_gloo(tmp_path):
     O.match_unique(text, reads, want, None, **kw)
     world = 2
     shards = matcher.shard_ranges(text.n, world, 64)
-    infos = [fold_hits(reads.nreads, hits[(hits["pos"] >= ob) & (hits["pos"] < oe)]) for ob, oe, _, _ in shards]
+    if split == "text":
+        # text sharded: a rank holds the hits that start in its range
+        infos = [fold_hits(reads.nreads, hits[(hits["pos"] >= ob) & (hits["pos"] < oe)]) for ob, oe, _, _ in shards]
+    else:
+        # tables sharded: a hit is found by the rank that owns the bucket of the seed window it is reported through, which
+        # scatters the hits of a read -- even the two strands at one position -- over the ranks
+        owner = (hits["pos"].astype(np.int64) * 2654435761 + hits["inverted"].astype(np.int64) * 40503 + hits["patid"].astype(np.int64)) >> 7
+        infos = [fold_hits(reads.nreads, hits[(owner % world) == r]) for r in range(world)]
     assert np.array_equal(matcher.canonical_unique(fold_hits(reads.nreads, hits)), matcher.canonical_unique(want))   # the fold itself is right
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

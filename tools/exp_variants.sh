@@ -8,5 +8,4 @@ run() { # name, env...
   echo "$name rc=$? $(tail -1 gpurun_out/var_$name.log | python -c 'import sys,json; d=json.loads(sys.stdin.readline()); print(d["ms_per_step"], d["phases_ms"]["pack_ms"], d["phases_ms"]["index_ms"], d["phases_ms"]["scan_ms"], d["counts"]["hits"])' 2>&1)"
 }
 run default A=1
-run default_elast REAL_GPU_DEBUG=2
 for v in real_b200/variants/*.so; do run $(basename $v .so) REAL_GPU_LIB=$PWD/$v; done
