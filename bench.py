@@ -195,9 +195,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--table-bits", type=int, default=0)
-    ap.add_argument("--parallel", default="tables", choices=["tables", "text"],
-                    help="N>1: 'tables' = signature tables sharded, window records exchanged through peer memory (default); "
-                         "'text' = text sharded with a read-length halo, index replicated on every rank")
+    ap.add_argument("--parallel", default="buckets", choices=["buckets", "tables", "text"],
+                    help="N>1: 'buckets' = signature tables sharded by scan bucket, every rank reads the whole text and keeps the positions "
+                         "of its own buckets, no record exchange (default); 'tables' = the same sharding with the window records exchanged "
+                         "through peer memory; 'text' = text sharded with a read-length halo, index replicated on every rank")
     ap.add_argument("--round-mpos", type=int, default=0, help="sharded tables: text positions per round in units of 2^20 (0 = 2^30 positions)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -237,7 +238,8 @@ def main():
     unique = wl["mode"] == "unique"
     rs = record_starts(n, wl["nrec"])
     tables_mode = world > 1 and args.parallel == "tables"
-    ob, oe, sb, sl = (0, n, 0, n) if (tables_mode or world == 1) else matcher.shard_ranges(n, world, L)[rank]
+    buckets_mode = world > 1 and args.parallel == "buckets"
+    ob, oe, sb, sl = (0, n, 0, n) if (tables_mode or buckets_mode or world == 1) else matcher.shard_ranges(n, world, L)[rank]
 
     # ---- synthetic inputs, generated on the device: this rank's text shard and the whole read set.
     # Reads are cut from the whole text, so they are generated from a transient full copy.
@@ -255,6 +257,8 @@ def main():
     h = rlib.Handle(seedl=32, seedkmax=2, totalkmax=wl["e"], scores=wl["scores"], ll_table=ll, device=local, table_bits=args.table_bits)
     if tables_mode:
         rdist.connect_sharded_tables(h, dev, round_positions=args.round_mpos << 20)
+    if buckets_mode:
+        h.set_bucket_shard(rank, world)
     shard = rdist.HandleShard(h, R)
     keys = torch.empty(R, dtype=torch.int64, device=dev) if unique else None
     ties = torch.empty(R, dtype=torch.uint8, device=dev) if unique else None
@@ -418,7 +422,10 @@ def main():
             "metric": "matching-path reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["desc"], "text_bases": n, "reads": R, "read_len": L, "mode": wl["mode"], "scores": wl["scores"],
-                       "parallelism": ("signature tables sharded x%d: every rank indexes 1/%d of the buckets, partitions 1/%d of the text positions of a round "
+                       "parallelism": ("signature tables sharded by scan bucket x%d: every rank indexes 1/%d of the signature space, reads the whole text and "
+                                       "keeps the positions of its own buckets (no record exchange); reads and text replicated; one NCCL fold of the "
+                                       "per-read results" % (world, world)) if buckets_mode else
+                                      ("signature tables sharded x%d: every rank indexes 1/%d of the buckets, partitions 1/%d of the text positions of a round "
                                        "and stores the window records into the owners' windows (peer memory over NVLink); reads and text replicated"
                                        % (world, world, world)) if tables_mode else
                                       ("text sharded x%d with %d-base halo, read index replicated" % (world, L)),

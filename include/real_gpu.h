@@ -213,6 +213,16 @@ int real_gpu_comm_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t ro
 int real_gpu_comm_connect(real_gpu * h, const void * all_handles);
 int real_gpu_comm_connect_local(real_gpu * h, real_gpu * const * peers);
 
+/* Bucket shards: the multi-GPU form of the scan without any record exchange.  Every rank is given the whole read set
+ * and the whole text (the text is 2 bit/base: 0.78 GB for 3.1 Gbp); rank r builds and keeps the index tables of its
+ * own 1/nranks of the signature space (the scan buckets [256 r / nranks, 256 (r+1) / nranks) = first 4 bases of a
+ * seed window) and its partition kernel keeps only the text positions whose bucket it owns, so a rank does 1/nranks
+ * of the index build, of the record traffic and of the probes.  Every hit is found by exactly one rank; matchAll
+ * results are the union of the ranks' results, matchUnique states are merged with the real_gpu_unique_export_*
+ * exchange above -- the only cross-GPU traffic of the path.  Call before real_gpu_set_reads.  Order dependent folds
+ * (matchUnique with scores, real_gpu_match_gaps) are not available in this mode. */
+int real_gpu_set_bucket_shard(real_gpu * h, uint32_t rank, uint32_t nranks);
+
 /* Gapped extension pass (UniqueMatcher::matchGaps) for reads still NoMatch/Gapped; updates the
  * unique state (state Gapped, score, seed position).  gaps[nreads], present==1 where a GapInfo
  * entry exists. */

@@ -111,6 +111,62 @@ __global__ void __launch_bounds__(256) k_pack_reads(const uint8_t * __restrict__
         rpack[gid] = word;
 }
 
+// The same for reads of at most PB_MAX_W words, both strands and the seeds in one pass: one thread per (read, word)
+// packs the forward word once; the words of a read are exchanged through shared memory, and word w of the '-' strand
+// is cut out of the (at most two) forward words that hold its bases.  Halves the byte loads and the packing work of
+// k_pack_reads and replaces k_read_seeds (and the wildcard-flag array in between).
+static const uint32_t PB_MAX_W = 64;
+__global__ void __launch_bounds__(256) k_pack_both(const uint8_t * __restrict__ mapped, const uint64_t * __restrict__ offsets, uint64_t nreads, uint32_t W,
+                                                 uint32_t seedl, uint64_t * __restrict__ rpack, uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds,
+                                                 uint32_t * __restrict__ usable)
+{
+        __shared__ uint64_t fw[256];
+        __shared__ uint32_t sbad[256];
+        uint32_t const rpb = 256 / W;                                 // reads per block
+        uint32_t const rl = threadIdx.x / W, w = threadIdx.x - rl * W;
+        uint64_t const r = (uint64_t)blockIdx.x * rpb + rl;
+        bool const active = rl < rpb && r < nreads;
+        sbad[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t L = 0;
+        uint64_t word = 0;
+        if ( active )
+        {
+                uint64_t const o = offsets[r];
+                L = (uint32_t)(offsets[r+1] - o);
+                if ( 32 * w < L )
+                {
+                        uint32_t anybad = 0;
+                        word = pack_bytes(mapped + o + 32 * w, min(32u, L - 32 * w), anybad);
+                        if ( anybad ) sbad[rl] = 1;
+                }
+                __stcs(rpack + (2 * r) * W + w, word);
+        }
+        fw[threadIdx.x] = word;
+        __syncthreads();
+        if ( ! active ) return;
+        uint64_t rc = 0;
+        if ( 32 * w < L )
+        {
+                uint32_t const len = min(32u, L - 32 * w);
+                uint32_t const b0 = L - 32 * w - len;                  // first base of the stretch whose reverse complement this word is
+                uint32_t const a = b0 >> 5, o2 = 2 * (b0 & 31);
+                uint64_t const x0 = fw[rl * W + a], x1 = (a + 1 < W) ? fw[rl * W + a + 1] : 0ULL;
+                uint64_t const fwd = (o2 ? ((x0 << o2) | (x1 >> (64 - o2))) : x0) >> (64 - 2 * len);
+                rc = revcomp_word(fwd, len) << (64 - 2 * len);
+        }
+        __stcs(rpack + (2 * r + 1) * W + w, rc);
+        if ( w == 0 )
+        {
+                bool const ok = (L >= seedl) && ! sbad[rl];
+                rlen[r] = ok ? L : 0;
+                usable[r] = ok ? 1 : 0;
+                uint64_t const sf = fw[rl * W] >> (64 - 2 * seedl);
+                seeds[2*r] = ok ? sf : 0;
+                seeds[2*r+1] = ok ? revcomp_word(sf, seedl) : 0;
+        }
+}
+
 // Reads that arrive 2 bit/base, 4 bases per byte MSB first, every read starting on a byte boundary -- the layout
 // of the reference's rewritten pattern file (TemporaryFile.hpp:231-268, writePatternDontCareFree).  `len` bases
 // starting at base `first` (a multiple of 32) of the read whose packed bytes start at p, left aligned in a word.

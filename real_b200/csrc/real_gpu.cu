@@ -190,7 +190,7 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
                 return fail(h, REAL_GPU_E_ARG, "set_text: record_starts[nrecords] must equal n_total");
 
         uint64_t const nw = (shard_len + 31) / 32, nmw = (shard_len + 63) / 64;
-        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS;
+        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + PF_SMEM_WORDS;     // the last tile of every kernel stays inside the allocation
         size_t const tbytes = (TEXT_PAD_WORDS + nw + tail) * 8, mbytes = (TEXT_PAD_WORDS + nmw + tail) * 8;
 
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
@@ -330,10 +330,19 @@ int build_from_device(real_gpu * h)
         dev_reserve(h, h->seeds, (size_t)nreads * 2 * 8 + 16);
         dev_reserve(h, h->usable, (size_t)nreads * 4 + 16);
         dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
-        if ( ! h->src_packed )
+        if ( ! h->src_packed && h->W > PB_MAX_W )
                 RG_CUDA(cudaMemsetAsync(h->bad.p, 0, (size_t)nreads * 4 + 16, h->st));
         if ( nreads )
         {
+                if ( ! h->src_packed && h->W <= PB_MAX_W )
+                {
+                        uint32_t const rpb = 256 / h->W;
+                        k_pack_both<<<blocks_for(nreads, rpb), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
+                                                                                ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
+                        RG_KERNEL_CHECK(); launch_count(h);
+                }
+                else
+                {
                 if ( h->src_packed )
                         k_pack_reads_packed<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_packed, h->src_byte_offsets, h->src_packed_uniform ? nullptr : ptr<uint64_t>(h->offs),
                                                                                                  h->src_packed_uniform, nreads, h->W, ptr<uint64_t>(h->rpack));
@@ -344,6 +353,7 @@ int build_from_device(real_gpu * h)
                 k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
                                                                        ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
                 RG_KERNEL_CHECK(); launch_count(h);
+                }
         }
         RG_CUDA(cudaEventRecord(h->ev[3], h->st));
 
@@ -436,6 +446,8 @@ void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
         P.rpack = ptr<uint64_t>(h->rpack); P.W = h->W; P.rlen = ptr<uint32_t>(h->rlen);
         P.rec = ptr<uint64_t>(h->rec); P.nrec = h->nrec; P.fileid = h->fileid;
         P.nranks = 1; P.rank = 0; P.bucket_lo[0] = 0; P.bucket_lo[1] = SC_MAX_BUCKETS; P.seg_cap = 0; P.npairs = 0;
+        P.own_b_lo = 0; P.own_b_cnt = SC_MAX_BUCKETS;
+        P.nprobed = ptr<unsigned long long>(h->counters) + 4;
         P.mode = mode;
         P.hits = ptr<RawHit>(h->hits_raw);
         P.hit_cap = h->hit_cap;
@@ -511,7 +523,17 @@ uint64_t run_scan(real_gpu * h, int mode)
                 if ( const char * e = getenv("REAL_GPU_DEBUG") ) P.debug_flags = (uint32_t)atoi(e);
 
                 real_gpu::Comm & CM = h->comm;
-                bool const sharded = CM.nranks > 1;
+                bool const sharded = CM.nranks > 1 && CM.window.p;          // records exchanged through peer memory
+                bool const own_only = CM.nranks > 1 && ! CM.window.p;       // bucket shard: this handle keeps the positions of its own buckets
+                if ( own_only )
+                {
+                        if ( maxbits < 8 ) throw CudaError("bucket shards need seeds of at least 16 bases");
+                        if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
+                                throw CudaError("bucket shards: every rank must be given the whole text (the ranks split the signature space, not the text)");
+                        P.bucket_bits = 8;
+                        P.own_b_lo = CM.bucket_lo[CM.rank];
+                        P.own_b_cnt = CM.bucket_lo[CM.rank + 1] - CM.bucket_lo[CM.rank];
+                }
                 if ( sharded )
                 {
                         if ( ! CM.connected ) throw CudaError("sharded tables: real_gpu_comm_connect has not been called");
@@ -552,7 +574,14 @@ uint64_t run_scan(real_gpu * h, int mode)
                 P.unit_counter = meta + 256 + 520;
                 P.bucket_cursor = meta + 1088;
 
-                size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem);
+                size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem), osmem = sizeof(OwnScatterSmem);
+                int occ_o = 0;
+                if ( own_only )
+                {
+                        RG_CUDA(cudaFuncSetAttribute(k_part_scatter_own, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
+                        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_o, k_part_scatter_own, SC_THREADS, osmem));
+                        if ( occ_o < 1 ) occ_o = 1;
+                }
                 RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
                 RG_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
                 RG_CUDA(cudaFuncSetAttribute(k_bucket_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
@@ -585,7 +614,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 P.x_end = std::min<uint64_t>(ce, P.x_begin + per);
                                 ++CM.epoch;
                         }
-                        h->stats.n_windows += P.x_end - P.x_begin;
+                        if ( ! own_only ) h->stats.n_windows += P.x_end - P.x_begin;
                         bool const any = P.x_end > P.x_begin;
                         uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
                         unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * occ_p);
@@ -608,7 +637,13 @@ uint64_t run_scan(real_gpu * h, int mode)
                         {
                                 uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
                                 unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
-                                k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
+                                if ( own_only )
+                                {
+                                        uint64_t const oft = P.x_begin / PF_SUPER_POS, oet = (P.x_end + PF_SUPER_POS - 1) / PF_SUPER_POS;
+                                        k_part_scatter_own<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * occ_o), SC_THREADS, osmem, h->st>>>(P);
+                                }
+                                else
+                                        k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
                                 RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
                         }
                         mark();
@@ -644,12 +679,13 @@ uint64_t run_scan(real_gpu * h, int mode)
                 }
         }
         RG_CUDA(cudaEventRecord(h->ev[6], h->st));
-        unsigned long long c[4] = {0, 0, 0, 0};
+        unsigned long long c[5] = {0, 0, 0, 0, 0};
         RG_CUDA(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.scan_ms = elapsed(h->ev[5], h->ev[6]);
         if ( ! ntiles ) h->stats.n_windows = 0;
-        if ( h->comm.nranks > 1 )
+        else if ( h->comm.nranks > 1 && ! h->comm.window.p ) h->stats.n_windows = c[4];     // bucket shard: the positions this handle kept
+        if ( h->comm.nranks > 1 && h->comm.window.p )
         {
                 uint32_t cerr = 0;
                 RG_CUDA(cudaMemcpy(&cerr, h->comm.error.p, 4, cudaMemcpyDeviceToHost));
@@ -673,10 +709,10 @@ void preload_kernels(int device)
         if ( device < 0 || device >= 64 || done[device] ) return;
         cudaFuncAttributes a;
 #define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
-        RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_reads_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
+        RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_pack_reads_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
         RG_PRELOAD(k_ent_hist); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
-        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_bucket_probe);
+        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD(k_bucket_probe);
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
         RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay);
@@ -1272,6 +1308,19 @@ int real_gpu_comm_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t ro
                 memcpy(handle_out, &ih, sizeof(ih));
         }
         if ( nranks == 1 ) return comm_finish_connect(h);
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_set_bucket_shard(real_gpu * h, uint32_t rank, uint32_t nranks)
+{
+        RG_API_BEGIN(h)
+        if ( nranks < 1 || nranks > (uint32_t)SC_MAX_RANKS || rank >= nranks ) return fail(h, REAL_GPU_E_ARG, "set_bucket_shard: rank/nranks out of range (at most 8 ranks)");
+        real_gpu::Comm & CM = h->comm;
+        if ( CM.window.p ) return fail(h, REAL_GPU_E_STATE, "set_bucket_shard: the handle is already a rank of a peer-memory group (real_gpu_comm_init)");
+        CM.nranks = nranks; CM.rank = rank; CM.connected = false;
+        for ( uint32_t r = 0; r <= nranks; ++r ) CM.bucket_lo[r] = (uint32_t)(((uint64_t)r * SC_MAX_BUCKETS) / nranks);
+        h->have_reads = false;            // the index has to be (re)built for this rank's buckets
         return REAL_GPU_OK;
         RG_API_END(h)
 }

@@ -107,6 +107,11 @@ struct ScanParams
         uint32_t * pair_grab;                   // probe side: first grab of every (own bucket, source) pair, bucket-major, + total
         uint32_t * pair_rec;                    //             first record of the pair in the local record area
         uint32_t npairs;
+        // Bucket shards (real_gpu_set_bucket_shard): this handle indexes and probes the buckets [own_b_lo, own_b_lo + own_b_cnt)
+        // only; it reads every text position of the chunk but forms records only of the positions whose bucket it owns.
+        // own_b_cnt = SC_MAX_BUCKETS: no filter.
+        uint32_t own_b_lo, own_b_cnt;
+        unsigned long long * nprobed; // positions this handle has formed records of (statistics)
 };
 
 __device__ __forceinline__ uint32_t bucket_owner(ScanParams const & P, uint32_t b)
@@ -241,6 +246,20 @@ __device__ __forceinline__ uint32_t clip_mask(uint64_t lx0, uint64_t x_begin, ui
         return m;
 }
 
+// The positions j0 .. j0+7 (j0 a multiple of 8) of the text word w0 (w1 = the word behind it): bit u of the result is
+// set when the 8-bit bucket (first 4 bases) of position j0+u lies in [lo, lo+cnt); top = the 16 bases from j0 on,
+// bucket of position j0+u = (top >> (24 - 2u)) & 0xFF
+__device__ __forceinline__ uint32_t own_mask8(uint64_t w0, uint64_t w1, uint32_t j0, uint32_t lo, uint32_t cnt, uint32_t & top)
+{
+        uint64_t const v = j0 ? ((w0 << (2*j0)) | (w1 >> (64 - 2*j0))) : w0;
+        top = (uint32_t)(v >> 32);
+        uint32_t m = 0;
+        #pragma unroll
+        for ( uint32_t u = 0; u < 8; ++u )
+                m |= ((((top >> (24 - 2*u)) & 0xFFu) - lo < cnt) ? 1u : 0u) << u;
+        return m;
+}
+
 // bucket histogram of the chunk (shared-memory reductions, then one global reduction per CTA and bucket)
 __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
 {
@@ -287,12 +306,30 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                         uint32_t const wi = threadIdx.x + k * SC_THREADS;
                         uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
                         uint32_t m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
+                        if ( P.own_b_cnt < SC_MAX_BUCKETS )
+                        {
+                                // bucket shard: only the positions of the own buckets are counted (8-bit buckets)
+                                #pragma unroll
+                                for ( uint32_t j0 = 0; j0 < 32; j0 += 8 )
+                                {
+                                        uint32_t top;
+                                        uint32_t mm = own_mask8(w0, w1, j0, P.own_b_lo, P.own_b_cnt, top) & (m >> j0);
+                                        while ( mm )
+                                        {
+                                                uint32_t const u = __ffs(mm) - 1;
+                                                mm &= mm - 1;
+                                                atomicAdd(&S.cnt[(top >> (24 - 2*u)) & 0xFFu], 1u);
+                                        }
+                                }
+                                continue;
+                        }
                         while ( m )
                         {
                                 uint32_t const j = __ffs(m) - 1;
                                 m &= m - 1;
                                 uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                atomicAdd(&S.cnt[(uint32_t)(v >> bsh) & bmask], 1u);
+                                uint32_t const b = (uint32_t)(v >> bsh) & bmask;
+                                if ( b - P.own_b_lo < P.own_b_cnt ) atomicAdd(&S.cnt[b], 1u);
                         }
                 }
                 __syncthreads();   // tile[buf] is free again
@@ -462,6 +499,203 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
                 __syncthreads();   // tile[buf], staging and the counters are free again
         }
+}
+
+// ---- partition of a bucket shard -------------------------------------------------------------------
+// The multi-GPU form of the scatter pass when the tables are sharded by bucket and every GPU holds the whole text
+// (real_gpu_set_bucket_shard): the CTA reads EVERY position of its text tiles but keeps only those whose bucket
+// belongs to this handle, 1/nranks of them.  Testing a position costs a handful of instructions; what is expensive is
+// the ranking and the staged copy-out, so the kept positions are first compacted into a shared-memory list of
+// descriptors (bucket << 24 | position inside the super tile) and the list is ranked and written out 2048 descriptors at
+// a time with full warps, exactly like a tile of k_part_scatter.  No record crosses NVLink: the only exchange of a
+// bucket-sharded scan is the fold of the per-read results at its end.
+static const int PF_SUBS = 32;                                // sub-tiles of PS_TILE_POS positions per super tile
+static const int PF_SUPER_POS = PS_TILE_POS * PF_SUBS;        // 65536 positions: 16 bits of a descriptor
+static const int PF_SUPER_WORDS = PF_SUPER_POS / 32;
+static const int PF_SMEM_WORDS = PF_SUPER_WORDS + 2 * SC_HALO;
+static const int PF_LIST_CAP = 2 * PS_TILE_POS;
+static const int PF_FLUSH = PS_TILE_POS - 256;                // the list is flushed when it holds at least this many descriptors
+
+struct OwnScatterSmem
+{
+        uint4 stage[PS_TILE_POS];
+        uint64_t tile[2][PF_SMEM_WORDS];
+        uint64_t bar[2];
+        uint32_t list[PF_LIST_CAP];
+        uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];
+        uint32_t loc[SC_MAX_BUCKETS + 1];
+        uint32_t base[SC_MAX_BUCKETS];
+        uint32_t add[4];
+        uint8_t stage_b[PS_TILE_POS];
+};
+
+// ranks the descriptors list[first, first+n), n <= PS_TILE_POS, and writes their records; all threads of the CTA
+__device__ __forceinline__ void own_flush(ScanParams const & P, OwnScatterSmem & S, const uint64_t * __restrict__ tw, uint32_t first, uint32_t n,
+                                          uint32_t pos0, uint32_t fsh)
+{
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        uint32_t const lt = (1u << lane) - 1;
+        uint32_t d[PS_PPT];
+        #pragma unroll
+        for ( int k = 0; k < PS_PPT; ++k )
+        {
+                uint32_t const i = (uint32_t)k * SC_THREADS + threadIdx.x;
+                d[k] = (i < n) ? S.list[first + i] : 0xFFFFFFFFu;
+                if ( i < n ) atomicAdd(&S.wcnt[wid][d[k] >> 24], 1u);
+        }
+        __syncthreads();
+        {
+                uint32_t tot = 0;
+                #pragma unroll
+                for ( int w = 0; w < SC_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                uint32_t blocktot;
+                uint32_t const ex = block_excl_scan(tot, &blocktot);
+                S.loc[threadIdx.x] = ex;
+                if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
+                S.base[threadIdx.x] = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
+                uint32_t run = ex;
+                #pragma unroll
+                for ( int w = 0; w < SC_THREADS / 32; ++w )
+                {
+                        uint32_t const c = S.wcnt[w][threadIdx.x];
+                        S.wcnt[w][threadIdx.x] = run;
+                        run += c;
+                }
+        }
+        __syncthreads();
+        #pragma unroll
+        for ( uint32_t kb = 0; kb < PS_PPT; kb += 4 )
+        {
+                uint32_t peers[4];
+                #pragma unroll
+                for ( uint32_t u = 0; u < 4; ++u )
+                        peers[u] = peers_u8(d[kb + u] >> 24, d[kb + u] != 0xFFFFFFFFu);
+                #pragma unroll
+                for ( uint32_t u = 0; u < 4; ++u )
+                {
+                        uint32_t const dd = d[kb + u];
+                        bool const ok = dd != 0xFFFFFFFFu;
+                        uint32_t const b = dd >> 24;
+                        uint32_t const below = __popc(peers[u] & lt);
+                        uint32_t pre = 0;
+                        if ( ok ) pre = S.wcnt[wid][b];
+                        __syncwarp();
+                        if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers[u]);
+                        __syncwarp();
+                        if ( ok )
+                        {
+                                uint32_t const slot = pre + below;
+                                uint32_t const p = dd & 0xFFFFFFu, wi = p >> 5, j = p & 31;
+                                uint64_t const wm = tw[wi - 1], w0 = tw[wi], w1 = tw[wi + 1];
+                                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                uint64_t const win = v >> fsh;
+                                uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;
+                                S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, p + pos0);
+                                S.stage_b[slot] = (uint8_t)b;
+                        }
+                }
+        }
+        __syncthreads();
+        {
+                uint32_t const m = S.loc[SC_MAX_BUCKETS];
+                for ( uint32_t i = threadIdx.x; i < m; i += SC_THREADS )
+                {
+                        uint32_t const b = S.stage_b[i];
+                        P.recs[S.base[b] + (i - S.loc[b])] = S.stage[i];
+                }
+        }
+        __syncthreads();
+        #pragma unroll
+        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_part_scatter_own(ScanParams P)
+{
+        extern __shared__ __align__(128) unsigned char sc_smem[];
+        OwnScatterSmem & S = *reinterpret_cast<OwnScatterSmem *>(sc_smem);
+
+        uint64_t const first_tile = P.x_begin / PF_SUPER_POS;
+        uint64_t const end_tile = (P.x_end + PF_SUPER_POS - 1) / PF_SUPER_POS;
+        uint32_t const fsh = 64 - 2 * P.seedl;
+        int const lane = threadIdx.x & 31;
+
+        if ( threadIdx.x == 0 )
+        {
+                mbar_init(&S.bar[0], 1);
+                mbar_init(&S.bar[1], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                S.add[0] = S.add[1] = S.add[2] = 0;
+        }
+        #pragma unroll
+        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t n = 0;          // descriptors in the list (CTA uniform)
+        uint32_t gsub = 0;       // sub-tiles handled so far
+
+        uint64_t tile_id = first_tile + blockIdx.x;
+        if ( threadIdx.x == 0 && tile_id < end_tile )
+        {
+                mbar_expect_tx(&S.bar[0], PF_SMEM_WORDS * 8);
+                bulk_load(&S.tile[0][0], P.text + (int64_t)tile_id * PF_SUPER_WORDS - SC_HALO, PF_SMEM_WORDS * 8, &S.bar[0]);
+        }
+        unsigned long long kept = 0;
+        for ( uint32_t it = 0; tile_id < end_tile; tile_id += gridDim.x, ++it )
+        {
+                uint32_t const buf = it & 1;
+                uint64_t const next_tile = tile_id + gridDim.x;
+                if ( threadIdx.x == 0 && next_tile < end_tile )
+                {
+                        mbar_expect_tx(&S.bar[buf ^ 1], PF_SMEM_WORDS * 8);
+                        bulk_load(&S.tile[buf ^ 1][0], P.text + (int64_t)next_tile * PF_SUPER_WORDS - SC_HALO, PF_SMEM_WORDS * 8, &S.bar[buf ^ 1]);
+                }
+                mbar_wait(&S.bar[buf], (it >> 1) & 1);
+                const uint64_t * tw = &S.tile[buf][SC_HALO];
+                uint64_t const tile_x0 = tile_id * PF_SUPER_POS;
+                uint32_t const pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums do not
+
+                for ( uint32_t sub = 0; sub < PF_SUBS; ++sub )
+                {
+                        uint32_t const wi = sub * PS_TILE_WORDS + threadIdx.x / PS_TPW, j0 = (threadIdx.x % PS_TPW) * PS_PPT;
+                        uint64_t const lx0 = tile_x0 + (uint64_t)wi * 32;
+                        uint32_t m = 0, top = 0;
+                        if ( lx0 + 32 > P.x_begin && lx0 < P.x_end )
+                        {
+                                static_assert(PS_PPT == 8, "own_mask8 tests 8 positions");
+                                m = own_mask8(tw[wi], tw[wi + 1], j0, P.own_b_lo, P.own_b_cnt, top);
+                                m &= (clip_mask(lx0, P.x_begin, P.x_end) >> j0) & 0xFFu;
+                        }
+                        // append the kept positions to the list: one shared-memory atomic per warp.  The additions of a
+                        // sub-tile are summed in one of three rotating counters (the one two steps ahead is cleared), so one
+                        // barrier per sub-tile is enough; the list length n itself is CTA uniform and lives in a register
+                        uint32_t const c = __popc(m);
+                        uint32_t const incl = warp_incl_scan(c, lane);
+                        uint32_t wbase = 0;
+                        if ( lane == 31 && incl ) wbase = atomicAdd(&S.add[gsub % 3], incl);
+                        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                        uint32_t o = n + wbase + incl - c;
+                        while ( m )
+                        {
+                                uint32_t const u = __ffs(m) - 1;
+                                m &= m - 1;
+                                S.list[o++] = (((top >> (24 - 2*u)) & 0xFFu) << 24) | (wi * 32 + j0 + u);
+                        }
+                        if ( threadIdx.x == 0 ) S.add[(gsub + 1) % 3] = 0;
+                        __syncthreads();
+                        n += S.add[gsub % 3];
+                        ++gsub;
+                        bool const last = sub + 1 == PF_SUBS;
+                        // the list never holds more than PF_FLUSH - 1 + PS_TILE_POS descriptors: at most two flushes empty it
+                        while ( n >= (uint32_t)PF_FLUSH || (last && n) )
+                        {
+                                uint32_t const take = min(n, (uint32_t)PS_TILE_POS);
+                                own_flush(P, S, tw, n - take, take, pos0, fsh);
+                                kept += (threadIdx.x == 0) ? take : 0;
+                                n -= take;
+                        }
+                }
+        }
+        if ( threadIdx.x == 0 && kept ) atomicAdd(P.nprobed, kept);
 }
 
 // one block: bucket starts (every bucket padded to whole grabs), cursors, sentinel records in the padding.

@@ -102,6 +102,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_comm_init.argtypes = [vp, u32, u32, u64, vp]
     L.real_gpu_comm_connect.argtypes = [vp, vp]
     L.real_gpu_comm_connect_local.argtypes = [vp, vp]
+    L.real_gpu_set_bucket_shard.argtypes = [vp, u32, u32]
     L.real_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.real_gpu_stream.argtypes = [vp]
     L.real_gpu_stream.restype = vp
@@ -250,6 +251,10 @@ class Handle:
         buf = C.create_string_buffer(64)
         self._check(self.L.real_gpu_comm_init(self.h, rank, nranks, round_positions, buf))
         return buf.raw
+
+    def set_bucket_shard(self, rank: int, nranks: int):
+        """This handle indexes and probes 1/nranks of the signature space (no peer memory); call before set_reads."""
+        self._check(self.L.real_gpu_set_bucket_shard(self.h, rank, nranks))
 
     def comm_connect(self, all_handles: bytes):
         self._check(self.L.real_gpu_comm_connect(self.h, all_handles))

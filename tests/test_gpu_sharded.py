@@ -125,6 +125,82 @@ def test_sharded_match_unique_two_files_vs_oracle(nranks, round_positions):
         assert np.array_equal(matcher.canonical_unique(info), want)
 
 
+def _bucket_ranks(cls, opts, nranks, table_bits=0):
+    ms = [cls(opts, table_bits=table_bits) for _ in range(nranks)]
+    for r, m in enumerate(ms):
+        m.handle.set_bucket_shard(r, nranks)
+    return ms
+
+
+@pytest.mark.parametrize("nranks,e,table_bits,n", [(2, 4, 0, 900_000), (8, 4, 0, 900_000), (3, 3, 24, 700_000), (5, 4, 0, 2_300_000)])
+def test_bucket_shards_match_all_vs_oracle(nranks, e, table_bits, n):
+    """Bucket shards (real_gpu_set_bucket_shard): every rank reads the whole text but keeps the positions of its own
+    buckets; no exchange.  The union of the ranks' hits must be the oracle's hit set, every hit found exactly once."""
+    text, reads = _fresh(200 + nranks, n=n)
+    kw = dict(seedl=32, seedkmax=2, totalkmax=e, scores=False)
+    ref = O.match_all(text, reads, **kw)
+    ms = _bucket_ranks(matcher.AllMatcher, matcher.RealOptions(**kw), nranks, table_bits)
+    try:
+        words, nmask = text.packed()
+        parts, kept = [], []
+        for m in ms:
+            m.set_reads(reads.mapped, reads.offsets, None)
+            m.set_text(words, nmask, text.n, text.record_starts)
+            parts.append(m.match())
+            kept.append(m.stats()["n_windows"])
+    finally:
+        for m in ms:
+            m.close()
+    a, b = canon_hits(np.concatenate(parts)), canon_hits(ref)
+    assert len(b) > reads.nreads // 2
+    assert a.shape == b.shape and np.array_equal(a, b)
+    assert sum(kept) == text.n - 32 + 1 + 2 * 8          # every probed position (seed windows + two fragments) is kept by exactly one rank
+    assert min(kept) > 0
+
+
+def test_bucket_shards_low_complexity_text():
+    """A text whose positions all fall into few buckets (long single-base and dinucleotide runs): one rank keeps nearly
+    everything, the list of kept positions is flushed every sub-tile, others keep next to nothing."""
+    text, reads = _fresh(77, n=400_000, nreads=6000)
+    sym = text.symbols.copy()
+    sym[50_000:150_000] = 0                       # poly-A
+    sym[200_000:260_000:2] = 1                    # CGCG...
+    sym[200_001:260_000:2] = 2
+    text = synth.Text(sym, text.records)
+    reads = synth.make_reads(text, 78, 6000, 100, 0.01, fastq=False)
+    kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    info_ref, _ = O.unique_init(reads.nreads, False)
+    O.match_unique(text, reads, info_ref, None, **kw)
+    import torch
+    nranks = 4
+    ms = _bucket_ranks(matcher.UniqueMatcher, matcher.RealOptions(**kw), nranks)
+    try:
+        dev = torch.device("cuda", 0)
+        words, nmask = text.packed()
+        for m in ms:
+            m.set_reads(reads.mapped, reads.offsets, None)
+            m.set_text(words, nmask, text.n, text.record_starts)
+            m.match()
+        keys = [torch.empty(reads.nreads, dtype=torch.int64, device=dev) for _ in ms]
+        ties = [torch.empty(reads.nreads, dtype=torch.uint8, device=dev) for _ in ms]
+        for g, m in enumerate(ms):
+            m.handle.unique_export_keys(keys[g].data_ptr())
+        kmin = torch.stack(keys).min(dim=0).values.contiguous()
+        for g, m in enumerate(ms):
+            m.handle.unique_export_ties(kmin.data_ptr(), ties[g].data_ptr())
+        tsum = torch.stack(ties).sum(dim=0).to(torch.uint8).contiguous()
+        torch.cuda.synchronize()
+        for m in ms:
+            m.handle.unique_import(kmin.data_ptr(), tsum.data_ptr())
+        infos = [m.info()[0] for m in ms]
+    finally:
+        for m in ms:
+            m.close()
+    want = matcher.canonical_unique(info_ref)
+    for info in infos:
+        assert np.array_equal(matcher.canonical_unique(info), want)
+
+
 def test_sharded_mode_refusals():
     """Order dependent folds need the whole table set in one handle; a rank that was never connected must not scan."""
     from real_b200 import lib as rlib
