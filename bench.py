@@ -200,6 +200,8 @@ def main():
                          "of its own buckets, no record exchange (default); 'tables' = the same sharding with the window records exchanged "
                          "through peer memory; 'text' = text sharded with a read-length halo, index replicated on every rank")
     ap.add_argument("--round-mpos", type=int, default=0, help="sharded tables: text positions per round in units of 2^20 (0 = 2^30 positions)")
+    ap.add_argument("--as-rank", default="", help="development: R/N = run on ONE GPU the work rank R of an N-rank bucket-sharded job does "
+                                                  "(no exchange; for profiling a rank's kernels under ncu; not a reportable number)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-text", type=int, default=32_000_000, help="reference arm: text bases of the sample")
@@ -259,6 +261,10 @@ def main():
         rdist.connect_sharded_tables(h, dev, round_positions=args.round_mpos << 20)
     if buckets_mode:
         h.set_bucket_shard(rank, world)
+    if args.as_rank:
+        er, en = (int(x) for x in args.as_rank.split("/"))
+        h.set_bucket_shard(er, en)
+        print("note: --as-rank %d/%d: one rank's share of a bucket-sharded job; not a reportable number" % (er, en), file=sys.stderr)
     shard = rdist.HandleShard(h, R)
     keys = torch.empty(R, dtype=torch.int64, device=dev) if unique else None
     ties = torch.empty(R, dtype=torch.uint8, device=dev) if unique else None

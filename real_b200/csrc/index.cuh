@@ -330,15 +330,28 @@ __global__ void __launch_bounds__(256) k_ent_hist(EntryPartParams P)
         cnt[threadIdx.x] = 0;
         __syncthreads();
         uint32_t const sh = P.G.hb - P.ebits;
-        for ( uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < P.nids; id += (uint64_t)gridDim.x * blockDim.x )
+        // four ids per thread and step, their loads issued together (the loop is bound by load latency otherwise)
+        uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+        for ( uint64_t id0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id0 < P.nids; id0 += 4 * stride )
         {
-                if ( ! P.usable[id >> 1] ) continue;
-                uint64_t const seed = P.seeds[id];
-                for ( uint32_t t = 0; t < P.G.nlists; ++t )
+                uint64_t seed[4];
+                bool ok[4];
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
                 {
-                        uint32_t const slot = entry_slot(seed, P.G, t);
-                        if ( entry_owned(P, slot) ) atomicAdd(&cnt[P.ebits ? (slot >> sh) : 0u], 1u);
+                        uint64_t const id = id0 + (uint64_t)k * stride;
+                        ok[k] = id < P.nids;
+                        seed[k] = ok[k] ? __ldcs(P.seeds + id) : 0;
+                        ok[k] = ok[k] && __ldg(P.usable + (id >> 1));
                 }
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                        if ( ok[k] )
+                                for ( uint32_t t = 0; t < P.G.nlists; ++t )
+                                {
+                                        uint32_t const slot = entry_slot(seed[k], P.G, t);
+                                        if ( entry_owned(P, slot) ) atomicAdd(&cnt[P.ebits ? (slot >> sh) : 0u], 1u);
+                                }
         }
         __syncthreads();
         if ( cnt[threadIdx.x] ) atomicAdd(P.bucket_count + threadIdx.x, cnt[threadIdx.x]);
@@ -378,7 +391,9 @@ struct EntryPartSmem
 // steps (2) and (4) of a staged 256-way scatter tile, shared by both levels: turn the per-warp counts into the
 // staging layout, reserve the tile's run in every bucket (cursor stride cs), and after the multisplit copy the
 // staged entries out run by run
-__device__ __forceinline__ void ep_layout(EntryPartSmem & S, const uint32_t * __restrict__ start, uint32_t * __restrict__ cursor, uint32_t cs)
+// returns the first output index of the tile's run in bucket threadIdx.x: the caller stores it to S.base after the
+// multisplit, so that the global atomic behind it is in flight while the tile is ranked
+__device__ __forceinline__ uint32_t ep_layout(EntryPartSmem & S, const uint32_t * __restrict__ start, uint32_t * __restrict__ cursor, uint32_t cs)
 {
         uint32_t tot = 0;
         #pragma unroll
@@ -387,7 +402,7 @@ __device__ __forceinline__ void ep_layout(EntryPartSmem & S, const uint32_t * __
         uint32_t const ex = block_excl_scan(tot, &blocktot);
         S.loc[threadIdx.x] = ex;
         if ( threadIdx.x == EP_MAX_BUCKETS - 1 ) S.loc[EP_MAX_BUCKETS] = blocktot;
-        S.base[threadIdx.x] = tot ? (start[threadIdx.x] + atomicAdd(cursor + threadIdx.x * cs, tot)) : 0;
+        uint32_t const basev = tot ? (start[threadIdx.x] + atomicAdd(cursor + threadIdx.x * cs, tot)) : 0;
         uint32_t run = ex;
         #pragma unroll
         for ( int w = 0; w < 8; ++w )
@@ -396,6 +411,7 @@ __device__ __forceinline__ void ep_layout(EntryPartSmem & S, const uint32_t * __
                 S.wcnt[w][threadIdx.x] = run;
                 run += c;
         }
+        return basev;
 }
 __device__ __forceinline__ void ep_place(EntryPartSmem & S, int wid, uint32_t lt, bool ok, uint32_t b, uint64_t seed, uint32_t val)
 {
@@ -462,7 +478,7 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                                 }
                 __syncthreads();
                 // (2) staging layout, global run reservation, per-warp running slots
-                ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
+                uint32_t const basev = ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
                 __syncthreads();
                 // (3) warp multisplit into the staging area
                 #pragma unroll
@@ -476,6 +492,7 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                                 ep_place(S, wid, lt, ok[k] && entry_owned(P, slot), b, seed[k], (uint32_t)(id << 2) | t);
                         }
                 }
+                S.base[threadIdx.x] = basev;
                 __syncthreads();
                 // (4) copy out run by run
                 ep_copy_out(S, P.ent_seed, P.ent_val);
@@ -483,6 +500,139 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                 #pragma unroll
                 for ( int w = 0; w < 8; ++w ) S.wcnt[w][threadIdx.x] = 0;
                 __syncthreads();
+        }
+}
+
+// level 1 of a bucket shard (real_gpu_set_bucket_shard / sharded tables): only the entries whose slot belongs to this
+// rank are kept, 1/nranks of them.  Computing and testing a slot is cheap, ranking and staging an entry is not, so the
+// kept entries are first compacted into a shared-memory list, which is ranked and written out EP_TILE_ENTRIES at a
+// time with full warps (the same scheme as k_part_scatter_own in scan.cuh).
+static const int EO_IDS_PER_THREAD = 2;
+static const int EO_TILE_IDS = 256 * EO_IDS_PER_THREAD;
+static const int EO_FLUSH = EP_TILE_ENTRIES - 256;
+static const int EO_LIST_CAP = EO_FLUSH + EO_TILE_IDS * 3;
+
+struct EntryOwnSmem
+{
+        EntryPartSmem P;
+        uint64_t list_seed[EO_LIST_CAP];
+        uint32_t list_val[EO_LIST_CAP];
+        uint32_t add[4];
+        uint8_t list_b[EO_LIST_CAP];
+};
+
+__device__ __forceinline__ void eo_flush(EntryPartParams const & P, EntryOwnSmem & SO, uint32_t first, uint32_t n)
+{
+        EntryPartSmem & S = SO.P;
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        uint32_t const lt = (1u << lane) - 1;
+        uint64_t seed[EP_TILE_ENTRIES / 256];
+        uint32_t val[EP_TILE_ENTRIES / 256], b[EP_TILE_ENTRIES / 256];
+        #pragma unroll
+        for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
+        {
+                uint32_t const i = (uint32_t)k * 256 + threadIdx.x;
+                bool const ok = i < n;
+                seed[k] = ok ? SO.list_seed[first + i] : 0;
+                val[k] = ok ? SO.list_val[first + i] : 0;
+                b[k] = ok ? SO.list_b[first + i] : 0;
+                if ( ok ) atomicAdd(&S.wcnt[wid][b[k]], 1u);
+        }
+        __syncthreads();
+        uint32_t const basev = ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
+        __syncthreads();
+        #pragma unroll
+        for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
+                ep_place(S, wid, lt, (uint32_t)k * 256 + threadIdx.x < n, b[k], seed[k], val[k]);
+        S.base[threadIdx.x] = basev;
+        __syncthreads();
+        ep_copy_out(S, P.ent_seed, P.ent_val);
+        __syncthreads();
+        #pragma unroll
+        for ( int w = 0; w < 8; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 2) k_ent_scatter_own(EntryPartParams P)
+{
+        extern __shared__ __align__(16) unsigned char ep_smem[];
+        EntryOwnSmem & SO = *reinterpret_cast<EntryOwnSmem *>(ep_smem);
+        int const lane = threadIdx.x & 31;
+        uint32_t const sh = P.G.hb - P.ebits;
+        uint32_t const nl = P.G.nlists;
+        #pragma unroll
+        for ( int w = 0; w < 8; ++w ) SO.P.wcnt[w][threadIdx.x] = 0;
+        if ( threadIdx.x < 4 ) SO.add[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t n = 0, step = 0;
+
+        uint64_t const ntiles = (P.nids + EO_TILE_IDS - 1) / EO_TILE_IDS;
+        // the seeds of the next tile are fetched while the current one is worked on (two CTAs per SM do not hide the latency)
+        uint64_t seedn[EO_IDS_PER_THREAD];
+        uint32_t usen[EO_IDS_PER_THREAD];
+        #pragma unroll
+        for ( int k = 0; k < EO_IDS_PER_THREAD; ++k )
+        {
+                uint64_t const id = (uint64_t)blockIdx.x * EO_TILE_IDS + (uint64_t)k * 256 + threadIdx.x;
+                seedn[k] = (id < P.nids) ? __ldcs(P.seeds + id) : 0;
+                usen[k] = (id < P.nids) ? __ldg(P.usable + (id >> 1)) : 0u;
+        }
+        for ( uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++step )
+        {
+                uint64_t seed[EO_IDS_PER_THREAD];
+                uint32_t slot[EO_IDS_PER_THREAD][3];
+                bool okk[EO_IDS_PER_THREAD];
+                uint32_t own = 0;                      // bit k*3+t: entry t of id k is kept
+                #pragma unroll
+                for ( int k = 0; k < EO_IDS_PER_THREAD; ++k )
+                {
+                        seed[k] = seedn[k];
+                        okk[k] = usen[k] != 0;
+                        uint64_t const idn = (tile + gridDim.x) * EO_TILE_IDS + (uint64_t)k * 256 + threadIdx.x;
+                        seedn[k] = (idn < P.nids) ? __ldcs(P.seeds + idn) : 0;
+                        usen[k] = (idn < P.nids) ? __ldg(P.usable + (idn >> 1)) : 0u;
+                }
+                #pragma unroll
+                for ( int k = 0; k < EO_IDS_PER_THREAD; ++k )
+                {
+                        bool const ok = okk[k];
+                        #pragma unroll
+                        for ( uint32_t t = 0; t < 3; ++t )
+                        {
+                                slot[k][t] = (ok && t < nl) ? entry_slot(seed[k], P.G, t) : 0u;
+                                if ( ok && t < nl && entry_owned(P, slot[k][t]) ) own |= 1u << (k * 3 + t);
+                        }
+                }
+                uint32_t const c = __popc(own);
+                uint32_t const incl = warp_incl_scan(c, lane);
+                uint32_t wbase = 0;
+                if ( lane == 31 && incl ) wbase = atomicAdd(&SO.add[step % 3], incl);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                uint32_t o = n + wbase + incl - c;
+                #pragma unroll
+                for ( int k = 0; k < EO_IDS_PER_THREAD; ++k )
+                {
+                        uint64_t const id = tile * EO_TILE_IDS + (uint64_t)k * 256 + threadIdx.x;
+                        #pragma unroll
+                        for ( uint32_t t = 0; t < 3; ++t )
+                                if ( (own >> (k * 3 + t)) & 1u )
+                                {
+                                        SO.list_seed[o] = seed[k];
+                                        SO.list_val[o] = (uint32_t)(id << 2) | t;
+                                        SO.list_b[o] = (uint8_t)(P.ebits ? (slot[k][t] >> sh) : 0u);
+                                        ++o;
+                                }
+                }
+                if ( threadIdx.x == 0 ) SO.add[(step + 1) % 3] = 0;
+                __syncthreads();
+                n += SO.add[step % 3];
+                bool const last = tile + gridDim.x >= ntiles;
+                while ( n >= (uint32_t)EO_FLUSH || (last && n) )
+                {
+                        uint32_t const take = min(n, (uint32_t)EP_TILE_ENTRIES);
+                        eo_flush(P, SO, n - take, take);
+                        n -= take;
+                }
         }
 }
 
@@ -549,7 +699,7 @@ __global__ void __launch_bounds__(256) k_ent2_scatter(EntryPartParams P)
                         if ( (uint32_t)k * 256 + threadIdx.x < n )
                                 atomicAdd(&S.wcnt[wid][(entry_slot(seed[k], P.G, val[k] & 3) >> sh) & smask], 1u);
                 __syncthreads();
-                ep_layout(S, P.sub_start + (b << P.e2bits), P.sub_cursor + (b << P.e2bits), 1);
+                uint32_t const basev = ep_layout(S, P.sub_start + (b << P.e2bits), P.sub_cursor + (b << P.e2bits), 1);
                 __syncthreads();
                 #pragma unroll
                 for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
@@ -557,6 +707,7 @@ __global__ void __launch_bounds__(256) k_ent2_scatter(EntryPartParams P)
                         bool const ok = (uint32_t)k * 256 + threadIdx.x < n;
                         ep_place(S, wid, lt, ok, (entry_slot(seed[k], P.G, val[k] & 3) >> sh) & smask, seed[k], val[k]);
                 }
+                S.base[threadIdx.x] = basev;
                 __syncthreads();
                 ep_copy_out(S, P.ent2_seed, P.ent2_val);
                 __syncthreads();

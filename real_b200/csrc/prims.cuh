@@ -44,6 +44,21 @@ __device__ __forceinline__ uint32_t peers_u8(uint32_t v, bool ok)
         return peers;
 }
 
+// the same when only the low nbits bits of v differ between the lanes (warp uniform nbits)
+__device__ __forceinline__ uint32_t peers_low(uint32_t v, bool ok, uint32_t nbits)
+{
+        uint32_t peers = __ballot_sync(0xffffffffu, ok);
+        #pragma unroll
+        for ( int b = 0; b < 8; ++b )
+                if ( (uint32_t)b < nbits )
+                {
+                        bool const bit = (v >> b) & 1u;
+                        uint32_t const bal = __ballot_sync(0xffffffffu, bit);
+                        peers &= bit ? bal : ~bal;
+                }
+        return peers;
+}
+
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = block sum
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t * total)
 {

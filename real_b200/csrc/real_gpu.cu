@@ -293,7 +293,17 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_ent2_scatter, 256, esmem));
         RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occh, k_ent2_hist, 256, 0));
         uint64_t const etiles = (EP.nids + EP_TILE_IDS - 1) / EP_TILE_IDS;
-        k_ent_scatter<<<(unsigned)std::min<uint64_t>(etiles, (uint64_t)h->sm_count * std::max(1, occ)), 256, esmem, h->st>>>(EP);
+        if ( h->comm.nranks > 1 )
+        {
+                size_t const osmem = sizeof(EntryOwnSmem);
+                int occ_o = 0;
+                RG_CUDA(cudaFuncSetAttribute(k_ent_scatter_own, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_o, k_ent_scatter_own, 256, osmem));
+                uint64_t const otiles = (EP.nids + EO_TILE_IDS - 1) / EO_TILE_IDS;
+                k_ent_scatter_own<<<(unsigned)std::min<uint64_t>(otiles, (uint64_t)h->sm_count * std::max(1, occ_o)), 256, osmem, h->st>>>(EP);
+        }
+        else
+                k_ent_scatter<<<(unsigned)std::min<uint64_t>(etiles, (uint64_t)h->sm_count * std::max(1, occ)), 256, esmem, h->st>>>(EP);
         RG_KERNEL_CHECK();
         launch_count(h, 3);
 
@@ -576,10 +586,13 @@ uint64_t run_scan(real_gpu * h, int mode)
 
                 size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem), osmem = sizeof(OwnScatterSmem);
                 int occ_o = 0;
+                // text words per step of k_part_scatter_own: about PF_BATCH kept positions expected per step
+                uint32_t own_step_words = PF_THREADS;
+                while ( own_step_words > (uint32_t)PF_PIECE_WORDS && (uint64_t)own_step_words * 32 * P.own_b_cnt > (uint64_t)PF_BATCH * SC_MAX_BUCKETS + 256 * P.own_b_cnt ) own_step_words >>= 1;
                 if ( own_only )
                 {
                         RG_CUDA(cudaFuncSetAttribute(k_part_scatter_own, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
-                        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_o, k_part_scatter_own, SC_THREADS, osmem));
+                        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_o, k_part_scatter_own, PF_THREADS, osmem));
                         if ( occ_o < 1 ) occ_o = 1;
                 }
                 RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
@@ -640,7 +653,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 if ( own_only )
                                 {
                                         uint64_t const oft = P.x_begin / PF_SUPER_POS, oet = (P.x_end + PF_SUPER_POS - 1) / PF_SUPER_POS;
-                                        k_part_scatter_own<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * occ_o), SC_THREADS, osmem, h->st>>>(P);
+                                        k_part_scatter_own<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * occ_o), PF_THREADS, osmem, h->st>>>(P, own_step_words);
                                 }
                                 else
                                         k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
@@ -710,7 +723,7 @@ void preload_kernels(int device)
         cudaFuncAttributes a;
 #define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
         RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_pack_reads_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
-        RG_PRELOAD(k_ent_hist); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
+        RG_PRELOAD(k_ent_hist); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
         RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD(k_bucket_probe);
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);

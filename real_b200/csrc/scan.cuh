@@ -260,6 +260,45 @@ __device__ __forceinline__ uint32_t own_mask8(uint64_t w0, uint64_t w1, uint32_t
         return m;
 }
 
+// The positions of the text word w0 (w1 = the word behind it) whose 8-bit bucket (their first 4 bases) lies in
+// [lo, lo+cnt): bit 63-2j of the result is set for position j.  When the range is an aligned power of two -- the case
+// for 2, 4 or 8 ranks -- only the top bits of the bucket decide, and they are compared for all 32 positions at once.
+__device__ __forceinline__ uint64_t kept_positions(uint64_t w0, uint64_t w1, uint32_t lo, uint32_t cnt)
+{
+        if ( (cnt & (cnt - 1)) == 0 && (lo & (cnt - 1)) == 0 )
+        {
+                uint32_t const nb = 8 - (31 - __clz(cnt));            // deciding bits
+                uint32_t const want = lo >> (8 - nb);
+                uint64_t eq = 0xAAAAAAAAAAAAAAAAULL;
+                for ( uint32_t k = 0; k < nb; ++k )
+                {
+                        uint64_t const y = k ? ((w0 << k) | (w1 >> (64 - k))) : w0;
+                        eq &= ((want >> (nb - 1 - k)) & 1u) ? y : ~y;
+                }
+                return eq;
+        }
+        uint64_t eq = 0;
+        #pragma unroll
+        for ( uint32_t j0 = 0; j0 < 32; j0 += 8 )
+        {
+                uint32_t top;
+                uint32_t const m = own_mask8(w0, w1, j0, lo, cnt, top);
+                #pragma unroll
+                for ( uint32_t u = 0; u < 8; ++u )
+                        eq |= (uint64_t)((m >> u) & 1u) << (63 - 2 * (j0 + u));
+        }
+        return eq;
+}
+// the same restricted to the positions [x_begin, x_end); lx0 = position of base 0 of w0
+__device__ __forceinline__ uint64_t kept_positions_clipped(uint64_t w0, uint64_t w1, uint32_t lo, uint32_t cnt, uint64_t lx0, uint64_t x_begin, uint64_t x_end)
+{
+        if ( lx0 + 32 <= x_begin || lx0 >= x_end ) return 0;
+        uint64_t eq = kept_positions(w0, w1, lo, cnt);
+        if ( lx0 < x_begin ) eq &= (~0ULL) >> (2 * (uint32_t)(x_begin - lx0));
+        if ( lx0 + 32 > x_end ) eq &= (~0ULL) << (2 * (uint32_t)(lx0 + 32 - x_end));
+        return eq;
+}
+
 // bucket histogram of the chunk (shared-memory reductions, then one global reduction per CTA and bucket)
 __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
 {
@@ -309,17 +348,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                         if ( P.own_b_cnt < SC_MAX_BUCKETS )
                         {
                                 // bucket shard: only the positions of the own buckets are counted (8-bit buckets)
-                                #pragma unroll
-                                for ( uint32_t j0 = 0; j0 < 32; j0 += 8 )
+                                uint64_t eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
+                                while ( eq )
                                 {
-                                        uint32_t top;
-                                        uint32_t mm = own_mask8(w0, w1, j0, P.own_b_lo, P.own_b_cnt, top) & (m >> j0);
-                                        while ( mm )
-                                        {
-                                                uint32_t const u = __ffs(mm) - 1;
-                                                mm &= mm - 1;
-                                                atomicAdd(&S.cnt[(top >> (24 - 2*u)) & 0xFFu], 1u);
-                                        }
+                                        uint32_t const j = (uint32_t)__clzll(eq) >> 1;
+                                        eq &= ~(0x8000000000000000ULL >> (2 * j));
+                                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                        atomicAdd(&S.cnt[(uint32_t)(v >> 56)], 1u);
                                 }
                                 continue;
                         }
@@ -427,6 +462,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 }
                 __syncthreads();
                 // (2) bucket b (thread b): totals -> staging layout, global run reservation, per-warp running slots
+                uint32_t basev;
                 {
                         uint32_t tot = 0;
                         #pragma unroll
@@ -435,7 +471,9 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                         uint32_t const ex = block_excl_scan(tot, &blocktot);
                         S.loc[threadIdx.x] = ex;
                         if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
-                        S.base[threadIdx.x] = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
+                        // the run's first record is needed at the copy-out only: the global atomic that reserves it stays in
+                        // flight while the tile is ranked
+                        basev = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
                         uint32_t run = ex;
                         #pragma unroll
                         for ( int w = 0; w < SC_THREADS / 32; ++w )
@@ -481,6 +519,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                                 }
                         }
                 }
+                S.base[threadIdx.x] = basev;
                 __syncthreads();
                 // (4) copy out: consecutive threads write consecutive records of a bucket run
                 {
@@ -504,113 +543,136 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
 // ---- partition of a bucket shard -------------------------------------------------------------------
 // The multi-GPU form of the scatter pass when the tables are sharded by bucket and every GPU holds the whole text
 // (real_gpu_set_bucket_shard): the CTA reads EVERY position of its text tiles but keeps only those whose bucket
-// belongs to this handle, 1/nranks of them.  Testing a position costs a handful of instructions; what is expensive is
-// the ranking and the staged copy-out, so the kept positions are first compacted into a shared-memory list of
-// descriptors (bucket << 24 | position inside the super tile) and the list is ranked and written out 2048 descriptors at
-// a time with full warps, exactly like a tile of k_part_scatter.  No record crosses NVLink: the only exchange of a
-// bucket-sharded scan is the fold of the per-read results at its end.
-static const int PF_SUBS = 32;                                // sub-tiles of PS_TILE_POS positions per super tile
-static const int PF_SUPER_POS = PS_TILE_POS * PF_SUBS;        // 65536 positions: 16 bits of a descriptor
-static const int PF_SUPER_WORDS = PF_SUPER_POS / 32;
+// belongs to this handle, 1/nranks of them.  Testing a position costs about one instruction (kept_positions: bit
+// sliced over the 32 positions of a text word); what is expensive is the ranking and the staged copy-out, so the
+// kept positions are first compacted into a shared-memory list of descriptors (bucket << 24 | position inside the
+// super tile) and the list is ranked and written out 2048 descriptors at a time with full warps, like a tile of
+// k_part_scatter.  No record crosses NVLink: the only exchange of a bucket-sharded scan is the fold of the per-read
+// results at its end.
+static const int PF_THREADS = 512;
+static const int PF_SUPER_WORDS = 2048;                       // text words per super tile
+static const int PF_SUPER_POS = PF_SUPER_WORDS * 32;          // 65536 positions: 16 bits of a descriptor
 static const int PF_SMEM_WORDS = PF_SUPER_WORDS + 2 * SC_HALO;
-static const int PF_LIST_CAP = 2 * PS_TILE_POS;
-static const int PF_FLUSH = PS_TILE_POS - 256;                // the list is flushed when it holds at least this many descriptors
+static const int PF_BATCH = 2048;                             // descriptors ranked and written out at a time
+static const int PF_DPT = PF_BATCH / PF_THREADS;              // per thread
+static const int PF_LIST_CAP = 3 * PF_BATCH;
+static const int PF_PIECE_WORDS = PF_BATCH / 32;              // a piece of a step whose kept positions always fit into the list
 
 struct OwnScatterSmem
 {
-        uint4 stage[PS_TILE_POS];
-        uint64_t tile[2][PF_SMEM_WORDS];
-        uint64_t bar[2];
+        uint4 stage[PF_BATCH];
+        uint64_t tile[PF_SMEM_WORDS];
+        uint64_t bar;
         uint32_t list[PF_LIST_CAP];
-        uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];
+        uint32_t wcnt[PF_THREADS / 32][SC_MAX_BUCKETS];
         uint32_t loc[SC_MAX_BUCKETS + 1];
         uint32_t base[SC_MAX_BUCKETS];
         uint32_t add[4];
-        uint8_t stage_b[PS_TILE_POS];
+        uint8_t stage_b[PF_BATCH];
 };
 
-// ranks the descriptors list[first, first+n), n <= PS_TILE_POS, and writes their records; all threads of the CTA
+// ranks the descriptors list[first, first+n), n <= PF_BATCH, and writes their records; all threads of the CTA
 __device__ __forceinline__ void own_flush(ScanParams const & P, OwnScatterSmem & S, const uint64_t * __restrict__ tw, uint32_t first, uint32_t n,
                                           uint32_t pos0, uint32_t fsh)
 {
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         uint32_t const lt = (1u << lane) - 1;
-        uint32_t d[PS_PPT];
+        uint32_t d[PF_DPT];
         #pragma unroll
-        for ( int k = 0; k < PS_PPT; ++k )
+        for ( int k = 0; k < PF_DPT; ++k )
         {
-                uint32_t const i = (uint32_t)k * SC_THREADS + threadIdx.x;
+                uint32_t const i = (uint32_t)k * PF_THREADS + threadIdx.x;
                 d[k] = (i < n) ? S.list[first + i] : 0xFFFFFFFFu;
                 if ( i < n ) atomicAdd(&S.wcnt[wid][d[k] >> 24], 1u);
         }
         __syncthreads();
+        uint32_t basev = 0;       // first record of the batch's run in bucket threadIdx.x: needed at the copy-out only, so the
+                                  // global atomic that reserves the run is in flight while the batch is ranked
         {
                 uint32_t tot = 0;
-                #pragma unroll
-                for ( int w = 0; w < SC_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                if ( threadIdx.x < SC_MAX_BUCKETS )
+                {
+                        #pragma unroll
+                        for ( int w = 0; w < PF_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                }
                 uint32_t blocktot;
                 uint32_t const ex = block_excl_scan(tot, &blocktot);
-                S.loc[threadIdx.x] = ex;
-                if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
-                S.base[threadIdx.x] = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
-                uint32_t run = ex;
-                #pragma unroll
-                for ( int w = 0; w < SC_THREADS / 32; ++w )
+                if ( threadIdx.x < SC_MAX_BUCKETS )
                 {
-                        uint32_t const c = S.wcnt[w][threadIdx.x];
-                        S.wcnt[w][threadIdx.x] = run;
-                        run += c;
-                }
-        }
-        __syncthreads();
-        #pragma unroll
-        for ( uint32_t kb = 0; kb < PS_PPT; kb += 4 )
-        {
-                uint32_t peers[4];
-                #pragma unroll
-                for ( uint32_t u = 0; u < 4; ++u )
-                        peers[u] = peers_u8(d[kb + u] >> 24, d[kb + u] != 0xFFFFFFFFu);
-                #pragma unroll
-                for ( uint32_t u = 0; u < 4; ++u )
-                {
-                        uint32_t const dd = d[kb + u];
-                        bool const ok = dd != 0xFFFFFFFFu;
-                        uint32_t const b = dd >> 24;
-                        uint32_t const below = __popc(peers[u] & lt);
-                        uint32_t pre = 0;
-                        if ( ok ) pre = S.wcnt[wid][b];
-                        __syncwarp();
-                        if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers[u]);
-                        __syncwarp();
-                        if ( ok )
+                        S.loc[threadIdx.x] = ex;
+                        if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
+                        if ( tot ) basev = P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot);
+                        uint32_t run = ex;
+                        #pragma unroll
+                        for ( int w = 0; w < PF_THREADS / 32; ++w )
                         {
-                                uint32_t const slot = pre + below;
-                                uint32_t const p = dd & 0xFFFFFFu, wi = p >> 5, j = p & 31;
-                                uint64_t const wm = tw[wi - 1], w0 = tw[wi], w1 = tw[wi + 1];
-                                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                uint64_t const win = v >> fsh;
-                                uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;
-                                S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, p + pos0);
-                                S.stage_b[slot] = (uint8_t)b;
+                                uint32_t const c = S.wcnt[w][threadIdx.x];
+                                S.wcnt[w][threadIdx.x] = run;
+                                run += c;
                         }
                 }
         }
         __syncthreads();
+        // buckets of an aligned power-of-two range differ in their low bits only
+        uint32_t const vbits = ((P.own_b_cnt & (P.own_b_cnt - 1)) == 0 && (P.own_b_lo & (P.own_b_cnt - 1)) == 0) ? (uint32_t)(31 - __clz(P.own_b_cnt)) : 8u;
+        uint32_t peers[PF_DPT];
+        #pragma unroll
+        for ( uint32_t u = 0; u < PF_DPT; ++u )
+                peers[u] = peers_low(d[u] >> 24, d[u] != 0xFFFFFFFFu, vbits);
+        #pragma unroll
+        for ( uint32_t u = 0; u < PF_DPT; ++u )
+        {
+                uint32_t const dd = d[u];
+                bool const ok = dd != 0xFFFFFFFFu;
+                uint32_t const b = dd >> 24;
+                uint32_t const below = __popc(peers[u] & lt);
+                uint32_t pre = 0;
+                if ( ok ) pre = S.wcnt[wid][b];
+                __syncwarp();
+                if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers[u]);
+                __syncwarp();
+                if ( ok )
+                {
+                        uint32_t const slot = pre + below;
+                        uint32_t const p = dd & 0xFFFFFFu, wi = p >> 5, j = p & 31;
+                        uint64_t const wm = tw[(int)wi - 1], w0 = tw[wi], w1 = tw[wi + 1];
+                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                        uint64_t const win = v >> fsh;
+                        uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;
+                        S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, p + pos0);
+                        S.stage_b[slot] = (uint8_t)b;
+                }
+        }
+        if ( threadIdx.x < SC_MAX_BUCKETS ) S.base[threadIdx.x] = basev;
+        __syncthreads();
         {
                 uint32_t const m = S.loc[SC_MAX_BUCKETS];
-                for ( uint32_t i = threadIdx.x; i < m; i += SC_THREADS )
+                for ( uint32_t i = threadIdx.x; i < m; i += PF_THREADS )
                 {
                         uint32_t const b = S.stage_b[i];
                         P.recs[S.base[b] + (i - S.loc[b])] = S.stage[i];
                 }
         }
-        __syncthreads();
         #pragma unroll
-        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        for ( int w = threadIdx.x >> 8; w < PF_THREADS / 32; w += PF_THREADS / 256 ) S.wcnt[w][threadIdx.x & 255] = 0;     // read last before the barrier above
         __syncthreads();
 }
 
-__global__ void __launch_bounds__(SC_THREADS) k_part_scatter_own(ScanParams P)
+// appends the kept positions eq of text word wi to the list from slot o on
+__device__ __forceinline__ void own_append(OwnScatterSmem & S, uint64_t eq, uint64_t w0, uint64_t w1, uint32_t wi, uint32_t o)
+{
+        while ( eq )
+        {
+                uint32_t const j = (uint32_t)__clzll(eq) >> 1;
+                eq &= ~(0x8000000000000000ULL >> (2 * j));
+                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                S.list[o++] = ((uint32_t)(v >> 56) << 24) | (wi * 32 + j);
+        }
+}
+
+// step_words = text words handled between two barriers, one per thread (<= PF_THREADS, a multiple of PF_PIECE_WORDS
+// that divides PF_SUPER_WORDS): chosen by the host so that a step is expected to keep about PF_BATCH positions
+__global__ void __launch_bounds__(PF_THREADS) k_part_scatter_own(ScanParams P, uint32_t step_words)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
         OwnScatterSmem & S = *reinterpret_cast<OwnScatterSmem *>(sc_smem);
@@ -622,78 +684,97 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter_own(ScanParams P)
 
         if ( threadIdx.x == 0 )
         {
-                mbar_init(&S.bar[0], 1);
-                mbar_init(&S.bar[1], 1);
+                mbar_init(&S.bar, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                S.add[0] = S.add[1] = S.add[2] = 0;
+                S.add[0] = S.add[1] = S.add[2] = S.add[3] = 0;
         }
-        #pragma unroll
-        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+        for ( int w = threadIdx.x >> 8; w < PF_THREADS / 32; w += PF_THREADS / 256 ) S.wcnt[w][threadIdx.x & 255] = 0;
         __syncthreads();
         uint32_t n = 0;          // descriptors in the list (CTA uniform)
-        uint32_t gsub = 0;       // sub-tiles handled so far
-
-        uint64_t tile_id = first_tile + blockIdx.x;
-        if ( threadIdx.x == 0 && tile_id < end_tile )
-        {
-                mbar_expect_tx(&S.bar[0], PF_SMEM_WORDS * 8);
-                bulk_load(&S.tile[0][0], P.text + (int64_t)tile_id * PF_SUPER_WORDS - SC_HALO, PF_SMEM_WORDS * 8, &S.bar[0]);
-        }
+        uint32_t gstep = 0;      // steps so far
         unsigned long long kept = 0;
-        for ( uint32_t it = 0; tile_id < end_tile; tile_id += gridDim.x, ++it )
+        const uint64_t * tw = &S.tile[SC_HALO];
+        uint32_t const nsteps = PF_SUPER_WORDS / step_words;
+
+        uint32_t it = 0;
+        for ( uint64_t tile_id = first_tile + blockIdx.x; tile_id < end_tile; tile_id += gridDim.x, ++it )
         {
-                uint32_t const buf = it & 1;
-                uint64_t const next_tile = tile_id + gridDim.x;
-                if ( threadIdx.x == 0 && next_tile < end_tile )
+                // one text buffer: a super tile is 16 KB and is worked on for tens of microseconds, the load is not worth hiding
+                if ( threadIdx.x == 0 )
                 {
-                        mbar_expect_tx(&S.bar[buf ^ 1], PF_SMEM_WORDS * 8);
-                        bulk_load(&S.tile[buf ^ 1][0], P.text + (int64_t)next_tile * PF_SUPER_WORDS - SC_HALO, PF_SMEM_WORDS * 8, &S.bar[buf ^ 1]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_expect_tx(&S.bar, PF_SMEM_WORDS * 8);
+                        bulk_load(&S.tile[0], P.text + (int64_t)tile_id * PF_SUPER_WORDS - SC_HALO, PF_SMEM_WORDS * 8, &S.bar);
                 }
-                mbar_wait(&S.bar[buf], (it >> 1) & 1);
-                const uint64_t * tw = &S.tile[buf][SC_HALO];
+                mbar_wait(&S.bar, it & 1);
                 uint64_t const tile_x0 = tile_id * PF_SUPER_POS;
                 uint32_t const pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums do not
 
-                for ( uint32_t sub = 0; sub < PF_SUBS; ++sub )
+                for ( uint32_t step = 0; step < nsteps; ++step, ++gstep )
                 {
-                        uint32_t const wi = sub * PS_TILE_WORDS + threadIdx.x / PS_TPW, j0 = (threadIdx.x % PS_TPW) * PS_PPT;
-                        uint64_t const lx0 = tile_x0 + (uint64_t)wi * 32;
-                        uint32_t m = 0, top = 0;
-                        if ( lx0 + 32 > P.x_begin && lx0 < P.x_end )
+                        // one text word = 32 positions per thread; the kept ones are appended to the list with one shared-memory
+                        // atomic per warp.  The additions of a step are summed in one of three rotating counters (the one of the
+                        // next step is cleared here), so a step costs one barrier; the list length n is CTA uniform.
+                        bool const active = threadIdx.x < step_words;
+                        uint32_t const wi = step * step_words + threadIdx.x;
+                        uint64_t w0 = 0, w1 = 0, eq = 0;
+                        if ( active )
                         {
-                                static_assert(PS_PPT == 8, "own_mask8 tests 8 positions");
-                                m = own_mask8(tw[wi], tw[wi + 1], j0, P.own_b_lo, P.own_b_cnt, top);
-                                m &= (clip_mask(lx0, P.x_begin, P.x_end) >> j0) & 0xFFu;
+                                w0 = tw[wi]; w1 = tw[wi + 1];
+                                eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
                         }
-                        // append the kept positions to the list: one shared-memory atomic per warp.  The additions of a
-                        // sub-tile are summed in one of three rotating counters (the one two steps ahead is cleared), so one
-                        // barrier per sub-tile is enough; the list length n itself is CTA uniform and lives in a register
-                        uint32_t const c = __popc(m);
+                        uint32_t const c = (uint32_t)__popcll(eq);
                         uint32_t const incl = warp_incl_scan(c, lane);
                         uint32_t wbase = 0;
-                        if ( lane == 31 && incl ) wbase = atomicAdd(&S.add[gsub % 3], incl);
+                        if ( lane == 31 && incl ) wbase = atomicAdd(&S.add[gstep % 3], incl);
                         wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                        uint32_t o = n + wbase + incl - c;
-                        while ( m )
-                        {
-                                uint32_t const u = __ffs(m) - 1;
-                                m &= m - 1;
-                                S.list[o++] = (((top >> (24 - 2*u)) & 0xFFu) << 24) | (wi * 32 + j0 + u);
-                        }
-                        if ( threadIdx.x == 0 ) S.add[(gsub + 1) % 3] = 0;
+                        if ( threadIdx.x == 0 ) S.add[(gstep + 1) % 3] = 0;
                         __syncthreads();
-                        n += S.add[gsub % 3];
-                        ++gsub;
-                        bool const last = sub + 1 == PF_SUBS;
-                        // the list never holds more than PF_FLUSH - 1 + PS_TILE_POS descriptors: at most two flushes empty it
-                        while ( n >= (uint32_t)PF_FLUSH || (last && n) )
+                        uint32_t const T = S.add[gstep % 3];
+                        if ( n + T <= (uint32_t)PF_LIST_CAP )
                         {
-                                uint32_t const take = min(n, (uint32_t)PS_TILE_POS);
-                                own_flush(P, S, tw, n - take, take, pos0, fsh);
-                                kept += (threadIdx.x == 0) ? take : 0;
-                                n -= take;
+                                own_append(S, eq, w0, w1, wi, n + wbase + incl - c);
+                                n += T;
+                        }
+                        else
+                        {
+                                // far more positions kept than expected (a text that falls into few buckets): piece by piece
+                                for ( uint32_t piece = 0; piece < step_words / PF_PIECE_WORDS; ++piece )
+                                {
+                                        __syncthreads();
+                                        if ( threadIdx.x == 0 ) S.add[3] = 0;
+                                        __syncthreads();
+                                        bool const mine = active && threadIdx.x / PF_PIECE_WORDS == piece;
+                                        uint32_t const c2 = mine ? c : 0;
+                                        uint32_t const incl2 = warp_incl_scan(c2, lane);
+                                        uint32_t wb2 = 0;
+                                        if ( lane == 31 && incl2 ) wb2 = atomicAdd(&S.add[3], incl2);
+                                        wb2 = __shfl_sync(0xffffffffu, wb2, 31);
+                                        if ( mine ) own_append(S, eq, w0, w1, wi, n + wb2 + incl2 - c2);
+                                        __syncthreads();
+                                        n += S.add[3];
+                                        while ( n >= (uint32_t)PF_BATCH )
+                                        {
+                                                own_flush(P, S, tw, n - PF_BATCH, PF_BATCH, pos0, fsh);
+                                                kept += (threadIdx.x == 0) ? PF_BATCH : 0;
+                                                n -= PF_BATCH;
+                                        }
+                                }
+                        }
+                        bool const last = step + 1 == nsteps;
+                        if ( n >= (uint32_t)PF_BATCH || (last && n) )
+                        {
+                                __syncthreads();
+                                while ( n >= (uint32_t)PF_BATCH || (last && n) )
+                                {
+                                        uint32_t const take = min(n, (uint32_t)PF_BATCH);
+                                        own_flush(P, S, tw, n - take, take, pos0, fsh);
+                                        kept += (threadIdx.x == 0) ? take : 0;
+                                        n -= take;
+                                }
                         }
                 }
+                __syncthreads();         // everybody is done with the text buffer
         }
         if ( threadIdx.x == 0 && kept ) atomicAdd(P.nprobed, kept);
 }
