@@ -391,9 +391,26 @@ def main():
         np_info = h_info.numpy().view(np.uint64)
         d2h = [0]
 
+        # N > 1 with replicated inputs (bucket shards): every rank uploads 1/N of the input bytes from its pinned host copy and
+        # the ranks all-gather them over NVLink, instead of every rank pulling everything through its own PCIe link
+        gather = None
+        if world > 1 and (buckets_mode or tables_mode):
+            sections = [("reads", h_mapped), ("flags", h_flags)]
+            if h_qual is not None:
+                sections.append(("qual", h_qual))
+            gather = rdist.ShardedUpload(sections, dev)
+            gather_text = rdist.ShardedUpload([("words", h_w.view(torch.uint8)), ("nmask", h_m.view(torch.uint8))], dev)
+
         def step_host():
-            h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
-            h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+            if gather is not None:
+                d = gather.run()
+                h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
+                                          d_quality=d["qual"].data_ptr() if "qual" in d else None)
+                d = gather_text.run()             # upload + all-gather of the text while the index build runs
+                h.set_text_device(d["words"].data_ptr(), d["nmask"].data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+            else:
+                h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
+                h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
             if unique:
                 h.match_unique()
                 if world > 1:
@@ -409,10 +426,14 @@ def main():
         e_steps = max(1, min(args.steps, 3))
         e_ms, _ = timed(step_host, e_steps, 1)
         h2d = R * L4 + R + (R * L if qual is not None else 0) + np_w.nbytes + np_m.nbytes + rs.nbytes
+        if gather is not None:
+            h2d = gather.chunk + gather_text.chunk + rs.nbytes          # per rank; the rest arrives over NVLink
         e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
                "ms_per_step": e_ms / e_steps, "steps": e_steps,
                "input": "host buffers: text 2 bit/base + N mask, reads 2 bit/base (the reference's rewritten pattern file layout), "
-                        "qualities 1 byte/base when scoring; result read back to pinned host memory"}
+                        "qualities 1 byte/base when scoring; result read back to pinned host memory"
+                        + ("; every rank uploads 1/%d of the bytes, NCCL all-gather over NVLink for the rest (h2d_bytes_per_step is per rank)" % world
+                           if gather is not None else "")}
         del h_mapped, h_qual, h_w, h_m, h_flags
 
     dev_bytes = h.device_bytes()

@@ -160,6 +160,15 @@ int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64
                               uint32_t uniform_length, const uint8_t * wildcard_flags, const uint8_t * quality, uint64_t nreads);
 int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint8_t * d_quality,
                               const uint64_t * d_offsets, uint64_t nreads, uint64_t total_bases, uint32_t maxlen);
+/* real_gpu_set_reads_packed for a read set of uniform length that is already in device memory (all pointers are
+ * device pointers): the multi-GPU drivers upload 1/nranks of the reads per GPU and all-gather them over NVLink. */
+int real_gpu_set_reads_packed_device(real_gpu * h, const uint8_t * d_packed, uint32_t uniform_length,
+                                     const uint8_t * d_wildcard_flags, const uint8_t * d_quality, uint64_t nreads);
+/* Asynchrony: the real_gpu_set_reads* calls return as soon as the caller's buffers have been consumed (copied, or for
+ * device buffers packed); the index build they started keeps running on the handle's stream and is waited for by the
+ * next call that needs it.  real_gpu_set_text* does not wait for it -- the text goes over a second stream -- so calling
+ * set_reads, then set_text, then match overlaps the text transfer with the index build.  Every call still returns
+ * only when the caller's buffers may be reused; errors of the deferred build are reported by the call that waits. */
 
 /* All matches of every read against the current text: what AllMatcher::match + unifyMatches
  * accumulate over the file, sorted by (patid, k, pos, file, frag, score, inverted)

@@ -44,8 +44,11 @@ struct real_gpu
 {
         real_gpu_params prm;
         std::string err;
-        cudaStream_t st;
+        cudaStream_t st;               // every kernel of the path
+        cudaStream_t st2;              // host<->device copies of the text, so that they overlap the index build on st
         cudaEvent_t ev[8];
+        cudaEvent_t evc[2];
+        bool build_pending;            // the index build of the current read set has been enqueued but not yet waited for
         uint64_t held;
         int sm_count;
 
@@ -71,7 +74,7 @@ struct real_gpu
         DevBuf win_valid, win_counts, bounds, gapres, gaps, boffs, flags8;   // reference text blocks (order-faithful replay)
         uint64_t n_list;               // windows per reference text block, 0 = one block per file
         DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
-        uint32_t table_counts[6];      // per table: entries, distinct slots (read back after the build)
+        uint32_t * table_counts;       // [6] pinned host memory; per table: entries, distinct slots (copied back asynchronously by the build)
         const uint8_t * src_packed; const uint64_t * src_byte_offsets; uint32_t src_packed_uniform;   // 2-bit input (set_reads_packed)
         const uint8_t * src_mapped;    // device pointer the reads are packed from (caller's buffer or h->mapped)
         DevBuf ll, hits_raw, hits_seg, hits_out, counters, counts, starts, cursor, scantmp, info, scores;
@@ -106,13 +109,14 @@ struct real_gpu
         uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
 
-        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
                 memset(&prm, 0, sizeof(prm));
                 memset(&stats, 0, sizeof(stats));
                 for ( int i = 0; i < 8; ++i ) ev[i] = nullptr;
+                evc[0] = evc[1] = nullptr;
         }
 };
 
@@ -164,7 +168,11 @@ int fail(real_gpu * h, int code, std::string const & msg)
         return code;
 }
 
-#define RG_API_BEGIN(h)  if ( ! (h) ) return REAL_GPU_E_ARG; try { RG_CUDA(cudaSetDevice((h)->prm.device));
+void finish_build(real_gpu * h);
+// every entry point first waits for an index build that is still in flight -- except the ones that set the text,
+// whose transfer is meant to overlap it
+#define RG_API_BEGIN(h)  if ( ! (h) ) return REAL_GPU_E_ARG; try { RG_CUDA(cudaSetDevice((h)->prm.device)); finish_build(h);
+#define RG_API_BEGIN_ASYNC(h)  if ( ! (h) ) return REAL_GPU_E_ARG; try { RG_CUDA(cudaSetDevice((h)->prm.device));
 #define RG_API_END(h)    } catch ( realgpu::CudaError const & e ) { return fail((h), REAL_GPU_E_CUDA, e.what()); } \
                            catch ( std::exception const & e ) { return fail((h), REAL_GPU_E_CUDA, e.what()); }
 
@@ -193,19 +201,25 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
         size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + PF_SMEM_WORDS;     // the last tile of every kernel stays inside the allocation
         size_t const tbytes = (TEXT_PAD_WORDS + nw + tail) * 8, mbytes = (TEXT_PAD_WORDS + nmw + tail) * 8;
 
-        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        // The text goes over the copy stream: an index build that real_gpu_set_reads* has left running on the kernel
+        // stream (it does not touch the text) overlaps the transfer.  Scans are over when their call returns, so
+        // nothing on the kernel stream still reads the old text.
         dev_reserve(h, h->text, tbytes);
         dev_reserve(h, h->nmask, mbytes);
         dev_reserve(h, h->rec, (size_t)(nrecords + 1) * 8);
-        RG_CUDA(cudaMemsetAsync(h->text.p, 0, tbytes, h->st));
-        RG_CUDA(cudaMemsetAsync(h->nmask.p, 0, mbytes, h->st));
+        RG_CUDA(cudaEventRecord(h->evc[0], h->st2));
+        // the padding in front and behind (the words in between are overwritten by the copy)
+        RG_CUDA(cudaMemsetAsync(h->text.p, 0, TEXT_PAD_WORDS * 8, h->st2));
+        RG_CUDA(cudaMemsetAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS + nw, 0, tail * 8, h->st2));
+        RG_CUDA(cudaMemsetAsync(h->nmask.p, 0, TEXT_PAD_WORDS * 8, h->st2));
+        RG_CUDA(cudaMemsetAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS + nmw, 0, tail * 8, h->st2));
         cudaMemcpyKind const kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, words, nw * 8, kind, h->st));
-        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, nmask, nmw * 8, kind, h->st));
-        RG_CUDA(cudaMemcpyAsync(h->rec.p, record_starts, (size_t)(nrecords + 1) * 8, cudaMemcpyHostToDevice, h->st));
-        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
-        RG_CUDA(cudaStreamSynchronize(h->st));
-        h->stats.h2d_text_ms = elapsed(h->ev[0], h->ev[1]);
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, words, nw * 8, kind, h->st2));
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, nmask, nmw * 8, kind, h->st2));
+        RG_CUDA(cudaMemcpyAsync(h->rec.p, record_starts, (size_t)(nrecords + 1) * 8, cudaMemcpyHostToDevice, h->st2));
+        RG_CUDA(cudaEventRecord(h->evc[1], h->st2));
+        RG_CUDA(cudaEventSynchronize(h->evc[1]));       // the caller's buffers are free again; later launches on the kernel stream come after
+        h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);
 
         h->fileid = fileid; h->n_total = n_total; h->shard_begin = shard_begin; h->shard_len = shard_len;
         h->own_begin = own_begin; h->own_end = own_end; h->nrec = nrecords;
@@ -377,21 +391,10 @@ int build_from_device(real_gpu * h)
         dev_reserve(h, h->ws_flags, (size_t)3 * 65600 * 4);  // sub-bucket counts, starts, cursors
         dev_reserve(h, h->ws_stmp, scan_temp_elems(65600) * 4 + 64);
         dev_reserve(h, h->ws_hist, (1024 + 256 * EP_CURSOR_STRIDE) * 4);
-        memset(h->table_counts, 0, sizeof(h->table_counts));
+        memset(h->table_counts, 0, 6 * sizeof(uint32_t));
         for ( int t = 0; t < 3; ++t )
                 build_table(h, t, ptr<uint32_t>(h->ws_hist));
         RG_CUDA(cudaEventRecord(h->ev[4], h->st));
-        RG_CUDA(cudaStreamSynchronize(h->st));
-        h->n_usable = 0;
-        for ( int t = 0; t < 3; ++t )
-        {
-                h->tab[t].nentries = h->table_counts[2*t];
-                h->tab[t].ndistinct = h->table_counts[2*t+1];
-        }
-        if ( h->tab[0].nlists ) h->n_usable = h->tab[0].nentries / (2 * h->tab[0].nlists);
-
-        h->stats.pack_ms = elapsed(h->ev[2], h->ev[3]);
-        h->stats.index_ms = elapsed(h->ev[3], h->ev[4]);
 
         // fresh unique state (UniqueMatchInfo.hpp:172,190)
         dev_reserve(h, h->info, (size_t)nreads * 8 + 16);
@@ -413,9 +416,28 @@ int build_from_device(real_gpu * h)
                 h->hit_cap = std::max<uint64_t>(1u << 16, 4 * h->nreads);
                 dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
         }
-        RG_CUDA(cudaStreamSynchronize(h->st));
-        h->have_reads = true;
+        // Everything above is enqueued; the build is waited for by the next call that needs the index (finish_build),
+        // so that a text transfer issued in between overlaps it.
+        h->build_pending = true;
         return REAL_GPU_OK;
+}
+
+// waits for the index build real_gpu_set_reads* has enqueued and takes over its counts
+void finish_build(real_gpu * h)
+{
+        if ( ! h->build_pending ) return;
+        h->build_pending = false;
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->n_usable = 0;
+        for ( int t = 0; t < 3; ++t )
+        {
+                h->tab[t].nentries = h->table_counts[2*t];
+                h->tab[t].ndistinct = h->table_counts[2*t+1];
+        }
+        if ( h->tab[0].nlists ) h->n_usable = h->tab[0].nentries / (2 * h->tab[0].nlists);
+        h->stats.pack_ms = elapsed(h->ev[2], h->ev[3]);
+        h->stats.index_ms = elapsed(h->ev[3], h->ev[4]);
+        h->have_reads = true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -783,7 +805,10 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 if ( const char * e = getenv("REAL_GPU_L2_SLICE_MB") ) h->l2_slice_bytes = (uint64_t)atoi(e) << 20;
                 if ( const char * e = getenv("REAL_GPU_CHUNK_MPOS") ) h->chunk_positions = std::max<uint64_t>(SC_TILE_POS, ((uint64_t)atoi(e) << 20) / SC_TILE_POS * SC_TILE_POS);
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+                RG_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+                RG_CUDA(cudaMallocHost(&h->table_counts, 6 * sizeof(uint32_t)));
                 for ( int i = 0; i < 8; ++i ) RG_CUDA(cudaEventCreate(&h->ev[i]));
+                for ( int i = 0; i < 2; ++i ) RG_CUDA(cudaEventCreate(&h->evc[i]));
                 if ( params->ll_table )
                 {
                         dev_alloc(h, h->ll, 1024 * 8);
@@ -817,6 +842,9 @@ int real_gpu_destroy(real_gpu * h)
         dev_free(h, h->comm.window); dev_free(h, h->comm.ptrs); dev_free(h, h->comm.pairs); dev_free(h, h->comm.error);
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
         for ( int i = 0; i < 8; ++i ) if ( h->ev[i] ) cudaEventDestroy(h->ev[i]);
+        for ( int i = 0; i < 2; ++i ) if ( h->evc[i] ) cudaEventDestroy(h->evc[i]);
+        if ( h->st2 ) cudaStreamDestroy(h->st2);
+        if ( h->table_counts ) cudaFreeHost(h->table_counts);
         if ( h->st ) cudaStreamDestroy(h->st);
         delete h;
         return REAL_GPU_OK;
@@ -828,7 +856,7 @@ int real_gpu_set_text(real_gpu * h, uint32_t fileid, const uint64_t * words, con
                       uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
                       const uint64_t * record_starts, uint32_t nrecords)
 {
-        RG_API_BEGIN(h)
+        RG_API_BEGIN_ASYNC(h)
         return set_text_common(h, fileid, words, nmask, false, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords);
         RG_API_END(h)
 }
@@ -837,7 +865,7 @@ int real_gpu_set_text_device(real_gpu * h, uint32_t fileid, const uint64_t * d_w
                              uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
                              const uint64_t * record_starts, uint32_t nrecords)
 {
-        RG_API_BEGIN(h)
+        RG_API_BEGIN_ASYNC(h)
         return set_text_common(h, fileid, d_words, d_nmask, true, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords);
         RG_API_END(h)
 }
@@ -880,9 +908,10 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
                 h->qual_present = true;
         }
         RG_CUDA(cudaEventRecord(h->ev[1], h->st));
-        RG_CUDA(cudaStreamSynchronize(h->st));
+        int const brc = build_from_device(h);           // enqueued; waited for by the next call that needs the index
+        RG_CUDA(cudaEventSynchronize(h->ev[1]));        // the caller's buffers have been copied
         h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
-        return build_from_device(h);
+        return brc;
         RG_API_END(h)
 }
 
@@ -907,7 +936,9 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
                 h->qual_present = true;
         }
         h->stats.h2d_reads_ms = 0;
-        return build_from_device(h);
+        int const brc = build_from_device(h);
+        RG_CUDA(cudaEventSynchronize(h->ev[3]));        // the reads are packed: the caller's buffers are not referenced any more
+        return brc;
         RG_API_END(h)
 }
 
@@ -973,9 +1004,45 @@ int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64
                 h->qual_present = true;
         }
         RG_CUDA(cudaEventRecord(h->ev[1], h->st));
-        RG_CUDA(cudaStreamSynchronize(h->st));      // the staging vectors above must outlive the copies
+        int const brc = build_from_device(h);           // enqueued; waited for by the next call that needs the index
+        RG_CUDA(cudaEventSynchronize(h->ev[1]));        // the caller's buffers (and the staging vectors above) have been copied
         h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
-        return build_from_device(h);
+        return brc;
+        RG_API_END(h)
+}
+
+int real_gpu_set_reads_packed_device(real_gpu * h, const uint8_t * d_packed, uint32_t uniform_length, const uint8_t * d_wildcard_flags,
+                                     const uint8_t * d_quality, uint64_t nreads)
+{
+        RG_API_BEGIN(h)
+        if ( nreads && ! d_packed ) return fail(h, REAL_GPU_E_ARG, "set_reads_packed_device: null pointer");
+        if ( ! uniform_length || uniform_length > 65535 ) return fail(h, REAL_GPU_E_ARG, "set_reads_packed_device: uniform_length must be 1..65535");
+        if ( nreads >= (1ULL << 28) ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: more than 2^28 reads in one set");
+        h->have_reads = false;
+        h->nreads = nreads; h->total_bases = (uint64_t)uniform_length * nreads; h->maxlen = uniform_length;
+        dev_reserve(h, h->offs, (nreads + 1) * 8);
+        dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
+        h->src_packed = d_packed; h->src_mapped = nullptr; h->src_packed_uniform = uniform_length; h->src_byte_offsets = nullptr;
+        k_uniform_offsets<<<blocks_for(nreads + 1, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, uniform_length);
+        RG_KERNEL_CHECK(); launch_count(h);
+        if ( d_wildcard_flags && nreads )
+        {
+                k_flags_to_bad<<<blocks_for(nreads, 256), 256, 0, h->st>>>(d_wildcard_flags, nreads, ptr<uint32_t>(h->bad));
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        else
+                RG_CUDA(cudaMemsetAsync(h->bad.p, 0, (size_t)nreads * 4 + 16, h->st));
+        h->qual_present = false;
+        if ( d_quality && (h->prm.scores || h->ll.p) )
+        {
+                dev_reserve(h, h->qual, h->total_bases + 64);
+                if ( h->total_bases ) RG_CUDA(cudaMemcpyAsync(h->qual.p, d_quality, h->total_bases, cudaMemcpyDeviceToDevice, h->st));
+                h->qual_present = true;
+        }
+        h->stats.h2d_reads_ms = 0;
+        int const brc = build_from_device(h);
+        RG_CUDA(cudaEventSynchronize(h->ev[3]));        // the reads are packed: the caller's buffers are not referenced any more
+        return brc;
         RG_API_END(h)
 }
 
@@ -1384,9 +1451,11 @@ int real_gpu_comm_connect_local(real_gpu * h, real_gpu * const * peers)
 
 int real_gpu_get_stats(real_gpu * h, real_gpu_stats * out)
 {
-        if ( ! h || ! out ) return REAL_GPU_E_ARG;
+        if ( ! out ) return REAL_GPU_E_ARG;
+        RG_API_BEGIN(h)
         *out = h->stats;
         return REAL_GPU_OK;
+        RG_API_END(h)
 }
 
 void * real_gpu_stream(real_gpu * h) { return h ? (void *)h->st : nullptr; }

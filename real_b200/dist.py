@@ -78,3 +78,41 @@ def connect_sharded_tables(handle, device: torch.device, round_positions: int = 
     dist.all_gather(parts, t, group=group)
     handle.comm_connect(b"".join(bytes(p.cpu().tolist()) for p in parts))
     dist.barrier(group=group)
+
+
+class ShardedUpload:
+    """Host -> all GPUs for inputs that every rank needs in full (bucket shards: the whole read set and the whole text).
+    The byte sections are laid out back to back in one pinned host blob; every step each rank copies ITS 1/N slice of the
+    blob to its GPU and one NCCL all-gather over NVLink completes the blob on every GPU -- N times less PCIe traffic per
+    GPU than N full uploads.  run() returns device views of the sections (valid until the next run())."""
+
+    ALIGN = 256
+
+    def __init__(self, sections, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.offsets = {}
+        total = 0
+        for name, t in sections:
+            self.offsets[name] = (total, t.numel())
+            total += (t.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        unit = self.world * self.ALIGN
+        total = (total + unit - 1) // unit * unit
+        self.chunk = total // self.world
+        self.blob = torch.zeros(total, dtype=torch.uint8)
+        if device.type == "cuda":
+            self.blob = self.blob.pin_memory()
+        for name, t in sections:
+            o, n = self.offsets[name]
+            self.blob[o:o + n].copy_(t.reshape(-1).view(torch.uint8))
+        self.d_in = torch.empty(self.chunk, dtype=torch.uint8, device=device)
+        self.d_all = torch.empty(total, dtype=torch.uint8, device=device)
+
+    def run(self):
+        lo = self.rank * self.chunk
+        self.d_in.copy_(self.blob[lo:lo + self.chunk], non_blocking=True)
+        dist.all_gather_into_tensor(self.d_all, self.d_in, group=self.group)
+        if self.d_all.device.type == "cuda":
+            torch.cuda.current_stream(self.d_all.device).synchronize()
+        return {name: self.d_all[o:o + n] for name, (o, n) in self.offsets.items()}

@@ -102,6 +102,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_comm_init.argtypes = [vp, u32, u32, u64, vp]
     L.real_gpu_comm_connect.argtypes = [vp, vp]
     L.real_gpu_comm_connect_local.argtypes = [vp, vp]
+    L.real_gpu_set_reads_packed_device.argtypes = [vp, vp, u32, vp, vp, u64]
     L.real_gpu_set_bucket_shard.argtypes = [vp, u32, u32]
     L.real_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.real_gpu_stream.argtypes = [vp]
@@ -199,6 +200,10 @@ class Handle:
                 for a, dt in ((packed, np.uint8), (byte_offsets, np.uint64), (lengths, np.uint32), (wildcard_flags, np.uint8), (quality, np.uint8))]
         ptrs = [a.ctypes.data if a is not None else None for a in keep]
         self._check(self.L.real_gpu_set_reads_packed(self.h, ptrs[0], ptrs[1], ptrs[2], uniform_length, ptrs[3], ptrs[4], nreads))
+
+    def set_reads_packed_device(self, d_packed: int, nreads: int, uniform_length: int, d_wildcard_flags: int | None = None, d_quality: int | None = None):
+        self.nreads = nreads
+        self._check(self.L.real_gpu_set_reads_packed_device(self.h, d_packed, uniform_length, d_wildcard_flags, d_quality, nreads))
 
     def set_reads_device(self, d_mapped: int, d_offsets: int, nreads: int, total_bases: int, maxlen: int, d_quality: int | None = None):
         self.nreads = nreads

@@ -141,3 +141,36 @@ def test_unique_exchange_world2_gloo(tmp_path, split):
     for r in range(world):
         got = np.load(out % r)
         assert np.array_equal(matcher.canonical_unique(got), matcher.canonical_unique(want))
+
+
+def _upload_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)           # every rank holds the same host inputs
+        a = torch.randint(0, 256, (100_003,), dtype=torch.uint8, generator=g)
+        b = torch.randint(-2**62, 2**62, (777,), dtype=torch.int64, generator=g)
+        c = torch.randint(0, 256, (5,), dtype=torch.uint8, generator=g)
+        up = rdist.ShardedUpload([("a", a), ("b", b.view(torch.uint8)), ("c", c)], torch.device("cpu"))
+        assert up.chunk * world >= a.numel() + b.numel() * 8 + c.numel() and up.chunk % rdist.ShardedUpload.ALIGN == 0
+        # a rank only ever reads its own slice of the blob: wipe the rest to prove it
+        lo = rank * up.chunk
+        keep = up.blob[lo:lo + up.chunk].clone()
+        up.blob.zero_()
+        up.blob[lo:lo + up.chunk] = keep
+        d = up.run()
+        ok = torch.equal(d["a"], a) and torch.equal(d["b"].view(torch.int64), b) and torch.equal(d["c"], c)
+        np.save(out_path % rank, np.asarray([int(ok)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_upload_world2_gloo(tmp_path):
+    """real_b200.dist.ShardedUpload: every rank contributes 1/N of the input bytes, the all-gather completes them everywhere."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "up%d.npy")
+    mp.spawn(_upload_worker, args=(2, port, out), nprocs=2, join=True)
+    assert all(int(np.load(out % r)[0]) == 1 for r in range(2))
