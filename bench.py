@@ -183,6 +183,18 @@ def run_reference_arm(args, wl):
     return 0
 
 
+def scan_traffic(workload: str, world: int, as_rank: str):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) the scan kernels of ONE step moved in the committed
+    `ncu --set full` capture of this workload (profiles/r01_traffic_<workload>.json), or None when no capture matches."""
+    if world != 1 or as_rank:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % workload)) as f:
+            return float(json.load(f)["scan_dram_bytes_per_step"])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -351,7 +363,7 @@ def main():
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_bucket_probe (+k_part): text scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                "traffic": None, "alg_bytes_per_launch": alg_bytes, "scan_ms": scan_ms,
+                "traffic": scan_traffic(args.workload, world, args.as_rank), "alg_bytes_per_launch": alg_bytes, "scan_ms": scan_ms,
                 "design_bytes_per_launch": design_bytes, "design_frac": design_bytes / (scan_ms * 1e-3) / 1e9 / peak,
                 "note": "alg bytes = 0.375*N_text + 6*32*N_win + 64*N_cand + 16*N_hit (SURVEY 8d, six lists); the kernel probes 3 merged "
                         "tables per window (design bytes = 3*32*N_win + ...), so frac can exceed the sector-traffic fraction"}

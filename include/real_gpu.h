@@ -164,7 +164,10 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
  * device pointers): the multi-GPU drivers upload 1/nranks of the reads per GPU and all-gather them over NVLink. */
 int real_gpu_set_reads_packed_device(real_gpu * h, const uint8_t * d_packed, uint32_t uniform_length,
                                      const uint8_t * d_wildcard_flags, const uint8_t * d_quality, uint64_t nreads);
-/* Asynchrony: the real_gpu_set_reads* calls return as soon as the caller's buffers have been consumed (copied, or for
+/* Device-pointer entry points (real_gpu_set_*_device, real_gpu_unique_export_*, real_gpu_unique_import) read and write
+ * the caller's device buffers on the handle's own stream (real_gpu_stream): whatever produced the buffers on another
+ * stream must have finished before the call (the caller synchronizes).
+ * Asynchrony: the real_gpu_set_reads* calls return as soon as the caller's buffers have been consumed (copied, or for
  * device buffers packed); the index build they started keeps running on the handle's stream and is waited for by the
  * next call that needs it.  real_gpu_set_text* does not wait for it -- the text goes over a second stream -- so calling
  * set_reads, then set_text, then match overlaps the text transfer with the index build.  Every call still returns

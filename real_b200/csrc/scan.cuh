@@ -363,8 +363,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                                 uint32_t const j = __ffs(m) - 1;
                                 m &= m - 1;
                                 uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                uint32_t const b = (uint32_t)(v >> bsh) & bmask;
-                                if ( b - P.own_b_lo < P.own_b_cnt ) atomicAdd(&S.cnt[b], 1u);
+                                atomicAdd(&S.cnt[(uint32_t)(v >> bsh) & bmask], 1u);
                         }
                 }
                 __syncthreads();   // tile[buf] is free again

@@ -330,6 +330,7 @@ def test_c4_full_size_gapped_pass():
         b = sym[ppos[r0:r1, None] + src_col]
         new = torch.where(from_read, a, b)
         m2[r0:r1] = torch.where(sel[:, None], new, m2[r0:r1])
+    torch.cuda.synchronize()      # the library reads the device buffers on its own stream (include/real_gpu.h: the caller synchronizes)
 
     def run():
         h = rlib.Handle(seedl=32, seedkmax=2, totalkmax=e, scores=True, ll_table=matcher.scoring_table())
