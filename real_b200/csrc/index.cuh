@@ -456,6 +456,16 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
         __syncthreads();
 
         uint64_t const ntiles = (P.nids + EP_TILE_IDS - 1) / EP_TILE_IDS;
+        // the seeds of the next tile are fetched while the current one is ranked
+        uint64_t seedn[EP_IDS_PER_THREAD];
+        uint32_t usen[EP_IDS_PER_THREAD];
+        #pragma unroll
+        for ( int k = 0; k < EP_IDS_PER_THREAD; ++k )
+        {
+                uint64_t const id = (uint64_t)blockIdx.x * EP_TILE_IDS + (uint64_t)k * 256 + threadIdx.x;
+                seedn[k] = (id < P.nids) ? __ldcs(P.seeds + id) : 0;
+                usen[k] = (id < P.nids) ? __ldg(P.usable + (id >> 1)) : 0u;
+        }
         for ( uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x )
         {
                 uint64_t seed[EP_IDS_PER_THREAD];
@@ -463,9 +473,11 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                 #pragma unroll
                 for ( int k = 0; k < EP_IDS_PER_THREAD; ++k )
                 {
-                        uint64_t const id = tile * EP_TILE_IDS + (uint64_t)k * 256 + threadIdx.x;
-                        ok[k] = (id < P.nids) && P.usable[id >> 1];
-                        seed[k] = ok[k] ? P.seeds[id] : 0;
+                        seed[k] = seedn[k];
+                        ok[k] = usen[k] != 0;
+                        uint64_t const idn = (tile + gridDim.x) * EP_TILE_IDS + (uint64_t)k * 256 + threadIdx.x;
+                        seedn[k] = (idn < P.nids) ? __ldcs(P.seeds + idn) : 0;
+                        usen[k] = (idn < P.nids) ? __ldg(P.usable + (idn >> 1)) : 0u;
                 }
                 // (1) per-warp bucket counts
                 #pragma unroll
@@ -720,23 +732,41 @@ __global__ void __launch_bounds__(256) k_ent2_scatter(EntryPartParams P)
 // One CTA per sub-bucket: the grouped entries [sub_start[sb], sub_start[sb+1]) all have slots in
 // [sb << sub_shift, (sb+1) << sub_shift), i.e. `words` = max(1, 2^sub_shift / 32) slot words.  Dynamic shared
 // memory: 3 * words u32 (presence bits, rank of the word's first slot, claimed bits).
-__global__ void __launch_bounds__(256) k_build_sub(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ sub_start,
+static const uint32_t SUB_DUP_CAP = 512;       // same-slot entries of a sub-bucket that are chained in one go (more are chained one by one)
+struct SubDup { uint64_t seed; uint32_t val; uint32_t r; };
+
+__global__ void __launch_bounds__(256, 7) k_build_sub(const uint64_t * __restrict__ ent_seed, const uint32_t * __restrict__ ent_val, const uint32_t * __restrict__ sub_start,
                                                  TableGeom G, uint32_t sub_shift, uint32_t words, SlotWord * __restrict__ slots, Entry * __restrict__ E,
                                                  uint32_t * __restrict__ ndistinct, uint32_t first_sub)
 {
         extern __shared__ __align__(16) uint32_t sub_smem[];
         uint32_t * bits = sub_smem, * rank = sub_smem + words, * claimed = sub_smem + 2 * words;
-        __shared__ uint32_t ovf;
+        __shared__ SubDup dup[SUB_DUP_CAP];
+        __shared__ uint32_t ovf, ndup;
         uint32_t const sb = first_sub + blockIdx.x;
         uint32_t const s0 = sub_start[sb], s1 = sub_start[sb+1];
         uint32_t const slot0 = sb << sub_shift;                    // sub_shift == hb when there is a single sub-bucket (sb == 0)
         for ( uint32_t w = threadIdx.x; w < words; w += 256 ) { bits[w] = 0; claimed[w] = 0; }
-        if ( threadIdx.x == 0 ) ovf = 0;
+        if ( threadIdx.x == 0 ) { ovf = 0; ndup = 0; }
         __syncthreads();
-        for ( uint32_t i = s0 + threadIdx.x; i < s1; i += 256 )
+        // presence bits; four entries per thread and step, their loads issued together
+        for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
         {
-                uint32_t const l = entry_slot(__ldg(ent_seed + i), G, __ldg(ent_val + i) & 3) - slot0;
-                atomicOr(&bits[l >> 5], 1u << (l & 31));
+                uint64_t seed[4]; uint32_t val[4];
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                {
+                        uint32_t const i = i0 + (uint32_t)k * 256;
+                        seed[k] = (i < s1) ? __ldg(ent_seed + i) : 0;
+                        val[k] = (i < s1) ? __ldg(ent_val + i) : 0;
+                }
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                        if ( i0 + (uint32_t)k * 256 < s1 )
+                        {
+                                uint32_t const l = entry_slot(seed[k], G, val[k] & 3) - slot0;
+                                atomicOr(&bits[l >> 5], 1u << (l & 31));
+                        }
         }
         __syncthreads();
         // ranks: every thread owns a run of consecutive words
@@ -756,25 +786,59 @@ __global__ void __launch_bounds__(256) k_build_sub(const uint64_t * __restrict__
         for ( uint32_t r = threadIdx.x; r < d; r += 256 ) E[s0 + r].next = ENTRY_NONE;
         if ( threadIdx.x == 0 && d ) atomicAdd(ndistinct, d);
         __syncthreads();
-        for ( uint32_t i = s0 + threadIdx.x; i < s1; i += 256 )
+        // entries: the first one of a slot claims E[rank]; the others (few: the tables are sparse) are set aside and chained
+        // below by full warps -- chaining them where they are found leaves two or three lanes of a warp waiting for a
+        // global atomic each time
+        for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
         {
-                uint64_t const seed = __ldg(ent_seed + i);
-                uint32_t const val = __ldg(ent_val + i);
-                uint32_t const l = entry_slot(seed, G, val & 3) - slot0;
-                uint32_t const bit = 1u << (l & 31);
-                uint32_t const r = rank[l >> 5] + __popc(bits[l >> 5] & (bit - 1));
-                if ( ! (atomicOr(&claimed[l >> 5], bit) & bit) )
+                uint64_t seed[4]; uint32_t val[4];
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
                 {
-                        E[r].seed = seed;
-                        E[r].val = val;
+                        uint32_t const i = i0 + (uint32_t)k * 256;
+                        seed[k] = (i < s1) ? __ldg(ent_seed + i) : 0;
+                        val[k] = (i < s1) ? __ldg(ent_val + i) : 0;
                 }
-                else
-                {
-                        uint32_t const o = s0 + d + atomicAdd(&ovf, 1u);        // behind the distinct entries of this sub-bucket
-                        Entry en; en.seed = seed; en.val = val;
-                        en.next = atomicExch(&E[r].next, o);
-                        E[o] = en;
-                }
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                        if ( i0 + (uint32_t)k * 256 < s1 )
+                        {
+                                uint32_t const l = entry_slot(seed[k], G, val[k] & 3) - slot0;
+                                uint32_t const bit = 1u << (l & 31);
+                                uint32_t const r = rank[l >> 5] + __popc(bits[l >> 5] & (bit - 1));
+                                if ( ! (atomicOr(&claimed[l >> 5], bit) & bit) )
+                                {
+                                        E[r].seed = seed[k];
+                                        E[r].val = val[k];
+                                }
+                                else
+                                {
+                                        uint32_t const j = atomicAdd(&ndup, 1u);
+                                        if ( j < SUB_DUP_CAP )
+                                        {
+                                                SubDup dd; dd.seed = seed[k]; dd.val = val[k]; dd.r = r;
+                                                dup[j] = dd;
+                                        }
+                                        else
+                                        {
+                                                uint32_t const o = s0 + d + SUB_DUP_CAP + atomicAdd(&ovf, 1u);
+                                                Entry en; en.seed = seed[k]; en.val = val[k];
+                                                en.next = atomicExch(&E[r].next, o);
+                                                E[o] = en;
+                                        }
+                                }
+                        }
+        }
+        __syncthreads();
+        // the set-aside entries go behind the distinct ones of this sub-bucket, in list order
+        uint32_t const nd = min(ndup, SUB_DUP_CAP);
+        for ( uint32_t j = threadIdx.x; j < nd; j += 256 )
+        {
+                SubDup const dd = dup[j];
+                uint32_t const o = s0 + d + j;
+                Entry en; en.seed = dd.seed; en.val = dd.val;
+                en.next = atomicExch(&E[dd.r].next, o);
+                E[o] = en;
         }
 }
 

@@ -27,6 +27,21 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
         return v;
 }
 
+// one bit of the multisplit: the ballot of bit `mask` of v and the word that turns it into "lanes that agree with me"
+// (0 where the bit is set, ~0 where it is clear).  Written in PTX: the compiler's own rendering of the C version
+// spends six instructions per bit (shift, and, compare, vote, select, combine), this one four.
+__device__ __forceinline__ void ballot_bit(uint32_t v, uint32_t mask, uint32_t & bal, uint32_t & flip)
+{
+        asm volatile("{\n\t"
+                     ".reg .pred p;\n\t"
+                     ".reg .b32 t;\n\t"
+                     "and.b32 t, %2, %3;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                     "selp.b32 %1, 0, 0xffffffff, p;\n\t"
+                     "}" : "=r"(bal), "=r"(flip) : "r"(v), "r"(mask));
+}
+
 // Lanes of the warp that hold the same 8-bit value as this lane (among the lanes with ok set; lanes without ok get
 // an unspecified mask).  One ballot per bit: measured on B200 (tools/match_bench.cu) MATCH.ANY costs ~2 cycles per
 // DISTINCT value on a unit shared by the whole SM -- 58 cycles per warp for random bytes, which made the multisplit
@@ -37,9 +52,9 @@ __device__ __forceinline__ uint32_t peers_u8(uint32_t v, bool ok)
         #pragma unroll
         for ( int b = 0; b < 8; ++b )
         {
-                bool const bit = (v >> b) & 1u;
-                uint32_t const bal = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? bal : ~bal;
+                uint32_t bal, flip;
+                ballot_bit(v, 1u << b, bal, flip);
+                peers &= bal ^ flip;
         }
         return peers;
 }
@@ -52,9 +67,9 @@ __device__ __forceinline__ uint32_t peers_low(uint32_t v, bool ok, uint32_t nbit
         for ( int b = 0; b < 8; ++b )
                 if ( (uint32_t)b < nbits )
                 {
-                        bool const bit = (v >> b) & 1u;
-                        uint32_t const bal = __ballot_sync(0xffffffffu, bit);
-                        peers &= bit ? bal : ~bal;
+                        uint32_t bal, flip;
+                        ballot_bit(v, 1u << b, bal, flip);
+                        peers &= bal ^ flip;
                 }
         return peers;
 }
