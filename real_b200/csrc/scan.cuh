@@ -358,6 +358,18 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                                 }
                                 continue;
                         }
+                        if ( m == 0xFFFFFFFFu && bbits == 8 )
+                        {
+                                // a whole word of 8-bit buckets: 32-bit funnel shifts over the three halves that hold them
+                                uint32_t const hi = (uint32_t)(w0 >> 32), lo = (uint32_t)w0, nx = (uint32_t)(w1 >> 32);
+                                #pragma unroll
+                                for ( int j = 0; j < 16; ++j )
+                                {
+                                        atomicAdd(&S.cnt[__funnelshift_l(lo, hi, 2*j) >> 24], 1u);
+                                        atomicAdd(&S.cnt[__funnelshift_l(nx, lo, 2*j) >> 24], 1u);
+                                }
+                                continue;
+                        }
                         while ( m )
                         {
                                 uint32_t const j = __ffs(m) - 1;
