@@ -263,6 +263,13 @@ struct TableGeom
 
 __device__ __forceinline__ uint64_t pair_key(uint64_t seed, uint32_t F, int a, int b)
 {
+        if ( F == 8 )
+        {
+                // -l 32: the four fragments are the four 16-bit fields of the seed; one byte permute puts fragment a over
+                // fragment b (bytes 0-3 = low half f2:f3, bytes 4-7 = high half f0:f1; fragment f sits in bytes 7-2f, 6-2f)
+                uint32_t const sel = ((7u - 2u * (uint32_t)a) << 12) | ((6u - 2u * (uint32_t)a) << 8) | ((7u - 2u * (uint32_t)b) << 4) | (6u - 2u * (uint32_t)b);
+                return __byte_perm((uint32_t)seed, (uint32_t)(seed >> 32), sel);
+        }
         uint64_t const fm = (F == 32) ? ~0ULL : ((1ULL << (2*F)) - 1);
         uint64_t const ma = (seed >> (2*F*(3-a))) & fm;
         uint64_t const mb = (seed >> (2*F*(3-b))) & fm;

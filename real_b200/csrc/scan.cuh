@@ -310,7 +310,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
         uint32_t const bbits = P.bucket_bits;
         uint32_t const bsh = 64 - (bbits ? bbits : 1);
         uint32_t const bmask = bbits ? 0xFFFFFFFFu : 0u;
-        uint32_t const own_copies = SC_MAX_BUCKETS / max(1u, P.own_b_cnt);      // bucket shard: replicas of the own counters
 
         if ( threadIdx.x == 0 )
         {
@@ -349,16 +348,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                         if ( P.own_b_cnt < SC_MAX_BUCKETS )
                         {
                                 // bucket shard: only the positions of the own buckets are counted (8-bit buckets)
-                                // the few own buckets would make every shared-memory atomic of a warp collide: the counters are
-                                // replicated own_copies times (lane l counts in copy l % own_copies) and summed at the end
                                 uint64_t eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
-                                uint32_t const cbase = (threadIdx.x % own_copies) * P.own_b_cnt - P.own_b_lo;
                                 while ( eq )
                                 {
                                         uint32_t const j = (uint32_t)__clzll(eq) >> 1;
                                         eq &= ~(0x8000000000000000ULL >> (2 * j));
                                         uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                        atomicAdd(&S.cnt[cbase + (uint32_t)(v >> 56)], 1u);
+                                        atomicAdd(&S.cnt[(uint32_t)(v >> 56)], 1u);
                                 }
                                 continue;
                         }
@@ -383,16 +379,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                         }
                 }
                 __syncthreads();   // tile[buf] is free again
-        }
-        if ( P.own_b_cnt < SC_MAX_BUCKETS )
-        {
-                if ( threadIdx.x < P.own_b_cnt )
-                {
-                        uint32_t c = 0;
-                        for ( uint32_t k = 0; k < own_copies; ++k ) c += S.cnt[k * P.own_b_cnt + threadIdx.x];
-                        if ( c ) atomicAdd(P.bucket_count + P.own_b_lo + threadIdx.x, c);
-                }
-                return;
         }
         uint32_t const c = S.cnt[threadIdx.x];
         if ( c ) atomicAdd(P.bucket_count + threadIdx.x, c);
