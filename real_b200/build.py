@@ -63,7 +63,7 @@ def build_host(force: bool = False) -> str:
         return HOST_BIN
     os.makedirs(BIN_DIR, exist_ok=True)
     gxx = shutil.which("g++") or "g++"
-    common = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra"]
+    common = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread"]
     subprocess.check_call(common + ["-o", HOST_BIN, os.path.join(HOST_DIR, "real_main.cpp"), os.path.join(HOST_DIR, "real_host.cpp"),
                                     "-L" + HERE, "-lreal_gpu", "-Wl,-rpath,$ORIGIN/.."])
     subprocess.check_call(common + ["-o", HOST_DUMP, os.path.join(HOST_DIR, "real_host_dump.cpp"), os.path.join(HOST_DIR, "real_host.cpp"),

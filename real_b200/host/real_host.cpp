@@ -11,6 +11,8 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
+#include <chrono>
 
 #include <dirent.h>
 #include <sys/stat.h>
@@ -40,7 +42,7 @@ void RealOptions::printHelp() const
         std::cerr << "-q <use quality scores, default=" << default_scores << ">" << std::endl;
         std::cerr << "-Q <offset for quality scores, default=autodetect>" << std::endl;
         std::cerr << "-R <rewrite pattern file, default=" << default_rewritepatterns << ">" << std::endl;
-        std::cerr << "-T <number of matching threads, accepted for compatibility>" << std::endl;
+        std::cerr << "-T <number of host threads (output formatting); the matching runs on the GPU>" << std::endl;
         std::cerr << "-similarity <sequence similarity, default=" << DFLT_SIMILARITY << ">" << std::endl;
         std::cerr << "-trans <transitions fraction of mutations, default=" << DFLT_TRANS << ">" << std::endl;
         std::cerr << "-gc <composition bias, default=" << DFLT_GC << ">" << std::endl;
@@ -540,6 +542,62 @@ namespace
                 o << "\t" << 1 << "\t" << "a" << "\t" << (e - b) << "\t" << (inverted ? "-" : "+") << "\t" << recname << "\t" << pos_in_record << "\t" << "\t" << k << "\n";
         }
 
+        // Formats the items [0,n) with `threads` host threads and writes the pieces in item order, wave by wave (the
+        // reference formats and prints serially: matchUniqueImplementation.cpp:1455-1486).  fmt(o, i) appends the lines
+        // of item i to o and returns how many it wrote.  The bytes written are those of the serial loop.
+        template<typename F>
+        uint64_t formatParallel(uint64_t n, unsigned int threads, Output & out, F fmt)
+        {
+                if ( threads < 1 ) threads = 1;
+                uint64_t per = 1u << 16;                         // items per thread and wave (REAL_FORMAT_CHUNK: tests)
+                if ( char const * e = getenv("REAL_FORMAT_CHUNK") ) per = std::max<uint64_t>(1, strtoull(e, 0, 10));
+                uint64_t total = 0;
+                std::vector<std::string> piece(threads);
+                std::vector<uint64_t> lines(threads);
+                for ( uint64_t w0 = 0; w0 < n; w0 += per * threads )
+                {
+                        uint64_t const w1 = std::min<uint64_t>(n, w0 + per * threads);
+                        unsigned int const used = (unsigned int)((w1 - w0 + per - 1) / per);
+                        std::vector<std::thread> team;
+                        for ( unsigned int t = 0; t < used; ++t )
+                        {
+                                uint64_t const a = w0 + t * per, b = std::min<uint64_t>(w1, a + per);
+                                auto work = [&piece, &lines, &fmt, t, a, b]()
+                                {
+                                        std::ostringstream o;
+                                        uint64_t c = 0;
+                                        for ( uint64_t i = a; i < b; ++i ) c += fmt(o, i);
+                                        piece[t] = o.str();
+                                        lines[t] = c;
+                                };
+                                if ( used == 1 ) work(); else team.push_back(std::thread(work));
+                        }
+                        for ( size_t t = 0; t < team.size(); ++t ) team[t].join();
+                        for ( unsigned int t = 0; t < used; ++t ) { out.write(piece[t]); total += lines[t]; }
+                }
+                return total;
+        }
+
+        unsigned int hostThreads(RealOptions const & opts)
+        {
+                if ( opts.threads > 0 ) return (unsigned int)opts.threads;
+                unsigned int const hc = std::thread::hardware_concurrency();
+                return hc ? hc : 1;
+        }
+
+        struct PhaseTimer
+        {
+                std::chrono::steady_clock::time_point t0;
+                PhaseTimer() : t0(std::chrono::steady_clock::now()) {}
+                void lap(char const * what)
+                {
+                        std::chrono::steady_clock::time_point const t1 = std::chrono::steady_clock::now();
+                        if ( getenv("REAL_TIMING") )
+                                std::cerr << "[timing] " << what << " " << std::chrono::duration<double>(t1 - t0).count() << " s" << std::endl;
+                        t0 = t1;
+                }
+        };
+
         void createHandle(Gpu & G, RealOptions const & opts, std::vector<double> & ll)
         {
                 real_gpu_params P;
@@ -575,13 +633,16 @@ namespace
 
 int doMatchingAll(RealOptions const & opts)
 {
+        PhaseTimer PT;
         ReadSet reads;
-        loadReads(opts, reads);            // (the stock -u 0 path parses FASTQ files with the FASTA reader, real.cpp:325-328; here FASTQ is honoured)
+        loadReads(opts, reads);
+        PT.lap("read patterns");            // (the stock -u 0 path parses FASTQ files with the FASTA reader, real.cpp:325-328; here FASTQ is honoured)
         std::vector<std::string> filenames;
         getFileList(opts.textfilename, filenames, ".fa");
         Gpu G; std::vector<double> ll;
         createHandle(G, opts, ll);
         G.check(real_gpu_set_reads(G.h, reads.mapped.empty() ? 0 : &reads.mapped[0], reads.quality.empty() ? 0 : &reads.quality[0], &reads.offsets[0], reads.size()), "set_reads");
+        PT.lap("create + set_reads");
         Output out(opts.outputfilename);
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
         {
@@ -596,14 +657,15 @@ int doMatchingAll(RealOptions const & opts)
                 G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
                 real_gpu_hit const * hits = 0; uint64_t nhits = 0;
                 G.check(real_gpu_match_all(G.h, &hits, &nhits), "match_all");
-                std::ostringstream o;
-                for ( uint64_t i = 0; i < nhits; ++i )
+                PT.lap("text + match_all");
+                bool const scores = opts.scores;
+                formatParallel(nhits, hostThreads(opts), out, [&reads, &T, hits, scores](std::ostringstream & o, uint64_t i) -> uint64_t
                 {
                         real_gpu_hit const & H = hits[i];
-                        formatLine(o, reads, H.patid, H.inverted != 0, opts.scores, H.score, T.ranges[H.frag].first, H.pos - T.ranges[H.frag].second + 1, H.k);
-                        if ( o.tellp() > 16384 ) { out.write(o.str()); o.str(std::string()); }
-                }
-                out.write(o.str());         // (the stock driver never flushes this tail, matchAllImplementation.cpp:512-517)
+                        formatLine(o, reads, H.patid, H.inverted != 0, scores, H.score, T.ranges[H.frag].first, H.pos - T.ranges[H.frag].second + 1, H.k);
+                        return 1;
+                });                         // (complete: the stock driver never flushes the tail of a block, matchAllImplementation.cpp:512-517)
+                PT.lap("format + write");
         }
         return EXIT_SUCCESS;
 }
@@ -638,8 +700,10 @@ static uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, u
 
 int doMatchingUnique(RealOptions const & opts)
 {
+        PhaseTimer PT;
         ReadSet reads;
         loadReads(opts, reads);
+        PT.lap("read patterns");
         if ( opts.rewritepatterns )
                 reorderLikeRewrite(reads);
         std::vector<std::string> filenames;
@@ -685,22 +749,22 @@ int doMatchingUnique(RealOptions const & opts)
         std::vector<float> score(reads.size() + 1);
         G.check(real_gpu_get_unique(G.h, &info[0], opts.scores ? &score[0] : 0), "get_unique");
 
+        PT.lap("texts + matching");
         Output out(opts.outputfilename);
-        uint64_t unique = 0;
-        std::ostringstream o;
-        for ( uint64_t r = 0; r < reads.size(); ++r )
+        bool const scores = opts.scores;
+        uint64_t const unique = formatParallel(reads.size(), hostThreads(opts), out,
+                [&reads, &info, &score, &rangeset, scores](std::ostringstream & o, uint64_t r) -> uint64_t
         {
                 uint64_t const d = info[r];
                 unsigned int const state = (unsigned int)(d >> 61);
                 if ( state != 1 && state != 2 )
-                        continue;
+                        return 0;
                 unsigned int const file = (unsigned int)((d >> 35) & 63), frag = (unsigned int)((d >> 45) & 0xFFFF), k = (unsigned int)((d >> 41) & 15);
                 uint64_t const pos = d & ((1ULL << 35) - 1);
-                formatLine(o, reads, r, state == 2, opts.scores, score[r], rangeset[file][frag].first, pos - rangeset[file][frag].second + 1, k);
-                ++unique;
-                if ( o.tellp() > 16384 ) { out.write(o.str()); o.str(std::string()); }
-        }
-        out.write(o.str());
+                formatLine(o, reads, r, state == 2, scores, score[r], rangeset[file][frag].first, pos - rangeset[file][frag].second + 1, k);
+                return 1;
+        });
+        PT.lap("format + write");
         std::cerr << "unique: " << unique << std::endl;
         return EXIT_SUCCESS;
 }

@@ -48,7 +48,7 @@ struct RealOptions
         double similarity, err, trans, gc, gcmut_bias;
         bool gaps;
         bool fastq;
-        int threads;            // -T: accepted and ignored (the matching runs on the GPU)
+        int threads;            // -T: host threads that format the output (0 = all); the matching runs on the GPU
         int device;             // REAL_GPU_DEVICE, default 0
 
         RealOptions(int argc, char * argv[]);

@@ -27,6 +27,20 @@ def test_cli_output_identical_to_stock_real(name, tmp_path):
     assert got == want
 
 
+@pytest.mark.parametrize("name", CASES[:2])
+def test_cli_output_identical_with_threaded_formatter(name, tmp_path):
+    """The output is formatted by several host threads, wave by wave, and written in order: tiny waves and 5 threads
+    must give the stock binary's bytes too."""
+    rbuild.build()
+    rbuild.build_host()
+    targ, rf, flags = make_case(name, str(tmp_path))
+    out = tmp_path / "out.txt"
+    p = subprocess.run([rbuild.HOST_BIN, "-t", targ, "-p", rf, "-o", str(out)] + flags + ["-T", "5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, REAL_STRICT_EXIT="1", REAL_FORMAT_CHUNK="7"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert out.read_text() == open(os.path.join(GOLDEN, "cli_%s.txt" % name)).read()
+
+
 def test_cli_match_all_complete_output(tmp_path):
     """matchAll through the CLI: every oracle hit is printed once (the stock CLI truncates)."""
     import numpy as np
