@@ -331,15 +331,17 @@ __device__ __forceinline__ uint32_t entry_slot(uint64_t seed, TableGeom const & 
         return slot_of(pair_key(seed, G.F, (int)t, pair_second(G.table, (int)t)), G.keybits, G.hb);
 }
 
-__global__ void __launch_bounds__(256) k_ent_hist(EntryPartParams P)
+// level-1 histograms of all three tables in one pass over the seeds (P[t].G.nlists == 0: table not built)
+struct EntryPartParams3 { EntryPartParams P[3]; };
+__global__ void __launch_bounds__(256) k_ent_hist3(const __grid_constant__ EntryPartParams3 Q)
 {
-        __shared__ uint32_t cnt[EP_MAX_BUCKETS];
-        cnt[threadIdx.x] = 0;
+        __shared__ uint32_t cnt[3][EP_MAX_BUCKETS];
+        #pragma unroll
+        for ( int t = 0; t < 3; ++t ) cnt[t][threadIdx.x] = 0;
         __syncthreads();
-        uint32_t const sh = P.G.hb - P.ebits;
-        // four ids per thread and step, their loads issued together (the loop is bound by load latency otherwise)
+        EntryPartParams const & P0 = Q.P[0];
         uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
-        for ( uint64_t id0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id0 < P.nids; id0 += 4 * stride )
+        for ( uint64_t id0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id0 < P0.nids; id0 += 4 * stride )
         {
                 uint64_t seed[4];
                 bool ok[4];
@@ -347,21 +349,31 @@ __global__ void __launch_bounds__(256) k_ent_hist(EntryPartParams P)
                 for ( int k = 0; k < 4; ++k )
                 {
                         uint64_t const id = id0 + (uint64_t)k * stride;
-                        ok[k] = id < P.nids;
-                        seed[k] = ok[k] ? __ldcs(P.seeds + id) : 0;
-                        ok[k] = ok[k] && __ldg(P.usable + (id >> 1));
+                        ok[k] = id < P0.nids;
+                        seed[k] = ok[k] ? __ldcs(P0.seeds + id) : 0;
+                        ok[k] = ok[k] && __ldg(P0.usable + (id >> 1));
                 }
                 #pragma unroll
                 for ( int k = 0; k < 4; ++k )
                         if ( ok[k] )
-                                for ( uint32_t t = 0; t < P.G.nlists; ++t )
+                        {
+                                #pragma unroll
+                                for ( int tb = 0; tb < 3; ++tb )
                                 {
-                                        uint32_t const slot = entry_slot(seed[k], P.G, t);
-                                        if ( entry_owned(P, slot) ) atomicAdd(&cnt[P.ebits ? (slot >> sh) : 0u], 1u);
+                                        EntryPartParams const & P = Q.P[tb];
+                                        uint32_t const sh = P.G.hb - P.ebits;
+                                        for ( uint32_t t = 0; t < P.G.nlists; ++t )
+                                        {
+                                                uint32_t const slot = entry_slot(seed[k], P.G, t);
+                                                if ( entry_owned(P, slot) ) atomicAdd(&cnt[tb][P.ebits ? (slot >> sh) : 0u], 1u);
+                                        }
                                 }
+                        }
         }
         __syncthreads();
-        if ( cnt[threadIdx.x] ) atomicAdd(P.bucket_count + threadIdx.x, cnt[threadIdx.x]);
+        #pragma unroll
+        for ( int tb = 0; tb < 3; ++tb )
+                if ( Q.P[tb].G.nlists && cnt[tb][threadIdx.x] ) atomicAdd(Q.P[tb].bucket_count + threadIdx.x, cnt[tb][threadIdx.x]);
 }
 
 // bucket starts, cursors, and the level-2 tiling (tiles never straddle a level-1 bucket)

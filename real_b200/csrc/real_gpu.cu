@@ -231,9 +231,21 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
 // reads + index
 // ---------------------------------------------------------------------------------------------
 
-// one table: group the entries by slot prefix (two levels), then build every sub-bucket in shared memory
-void build_table(real_gpu * h, int t, uint32_t * meta)
+// geometry and partition parameters of one table
+struct TablePlan
 {
+        EntryPartParams EP;
+        uint32_t e2, nsub, sub_shift, words, first_sub, own_subs;
+        uint32_t * d_total, * d_ndist;
+        bool empty;
+};
+static const size_t TABLE_META_WORDS = 1024 + 256 * EP_CURSOR_STRIDE;
+
+// sizes, buffers and the level-1 parameters of table t; meta = its bookkeeping words, cleared here
+TablePlan plan_table(real_gpu * h, int t, uint32_t * meta)
+{
+        TablePlan TP;
+        memset(&TP, 0, sizeof(TP));
         Table & T = h->tab[t];
         T.nlists = table_lists(t, h->prm.seedkmax);
         uint64_t const cap_entries = h->nreads * 2 * T.nlists;        // upper bound (unusable reads produce none)
@@ -253,28 +265,31 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         uint32_t pb = 0;
         while ( (cap_entries >> pb) > SUB_TARGET_ENTRIES ) ++pb;
         pb = std::min(std::max(pb, pbmin), pbmax);
-        uint32_t const e1 = std::min<uint32_t>(8, pb), e2 = pb - e1;
-        uint32_t const nsub = 1u << pb, sub_shift = T.hb - pb;
-        uint32_t const words = sub_shift >= 5 ? (1u << (sub_shift - 5)) : 1u;
-        T.nblocks = nsub;
-        T.bitmap_bytes = (size_t)nsub * words * sizeof(SlotWord);
+        uint32_t const e1 = std::min<uint32_t>(8, pb);
+        TP.e2 = pb - e1;
+        TP.nsub = 1u << pb; TP.sub_shift = T.hb - pb;
+        TP.words = TP.sub_shift >= 5 ? (1u << (TP.sub_shift - 5)) : 1u;
+        T.nblocks = TP.nsub;
+        T.bitmap_bytes = (size_t)TP.nsub * TP.words * sizeof(SlotWord);
         dev_reserve(h, T.bitmap, T.bitmap_bytes);
         dev_reserve(h, T.E, std::max<size_t>(16, cap_entries * sizeof(Entry)) + 256);
+        EntryPartParams & EP = TP.EP;
+        EP.G.F = h->F; EP.G.keybits = h->keybits; EP.G.hb = T.hb; EP.G.nlists = 0; EP.G.table = t;
         if ( T.nlists == 0 || h->nreads == 0 )
         {
                 RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap_bytes, h->st));
-                return;
+                TP.empty = true;
+                return TP;
         }
         if ( cap_entries >= 0xFFFFFFFFULL )
                 throw CudaError("index: more than 2^32 entries in one table");
 
         // meta layout (u32): [0,256) bucket counts, [256,513) bucket starts, 520 total, 521 ndistinct, [600,857) level-2 tile starts, [1024, ...) cursors
-        EntryPartParams EP;
         EP.seeds = ptr<uint64_t>(h->seeds); EP.usable = ptr<uint32_t>(h->usable); EP.nids = 2 * h->nreads;
-        EP.G.F = h->F; EP.G.keybits = h->keybits; EP.G.hb = T.hb; EP.G.nlists = T.nlists; EP.G.table = t;
-        EP.ebits = e1; EP.e2bits = e2;
+        EP.G.nlists = T.nlists;
+        EP.ebits = e1; EP.e2bits = TP.e2;
         EP.own_shift = 0; EP.own_lo = 0; EP.own_last = 0xFFFFFFFFu;
-        uint32_t first_sub = 0, own_subs = nsub;
+        TP.first_sub = 0; TP.own_subs = TP.nsub;
         if ( h->comm.nranks > 1 )
         {
                 // this rank owns the slots whose top 8 bits (= top 8 bits of the key = scan bucket) fall into its bucket range
@@ -282,8 +297,8 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
                 EP.own_shift = T.hb - 8; EP.own_lo = h->comm.bucket_lo[h->comm.rank]; EP.own_last = h->comm.bucket_lo[h->comm.rank + 1] - 1;
                 if ( pb >= 8 )
                 {
-                        first_sub = EP.own_lo << (pb - 8);
-                        own_subs = (EP.own_last + 1 - EP.own_lo) << (pb - 8);
+                        TP.first_sub = EP.own_lo << (pb - 8);
+                        TP.own_subs = (EP.own_last + 1 - EP.own_lo) << (pb - 8);
                 }
         }
         EP.ent_seed = ptr<uint64_t>(h->ws_k0); EP.ent_val = ptr<uint32_t>(h->ws_v0);
@@ -291,13 +306,20 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         EP.bucket_count = meta; EP.bucket_start = meta + 256; EP.tile_start = meta + 600; EP.bucket_cursor = meta + 1024;
         uint32_t * sub = ptr<uint32_t>(h->ws_flags);
         EP.sub_count = sub; EP.sub_start = sub + 65600; EP.sub_cursor = sub + 2 * 65600;
-        uint32_t * d_total = meta + 520, * d_ndist = meta + 521;
+        TP.d_total = meta + 520; TP.d_ndist = meta + 521;
         RG_CUDA(cudaMemsetAsync(meta, 0, 1024 * 4, h->st));
+        return TP;
+}
 
-        unsigned const grid = (unsigned)(h->sm_count * 8);
-        k_ent_hist<<<grid, 256, 0, h->st>>>(EP);
-        RG_KERNEL_CHECK();
-        k_ent_offsets<<<1, EP_MAX_BUCKETS, 0, h->st>>>(EP, d_total);
+// one table, its level-1 histogram already counted: group the entries by slot prefix (two levels; the grouped
+// entries of the tables share one workspace, so the tables are built one after the other), then build every
+// sub-bucket in shared memory
+void build_table(real_gpu * h, int t, TablePlan const & TP)
+{
+        if ( TP.empty ) return;
+        Table & T = h->tab[t];
+        EntryPartParams const & EP = TP.EP;
+        k_ent_offsets<<<1, EP_MAX_BUCKETS, 0, h->st>>>(EP, TP.d_total);
         RG_KERNEL_CHECK();
         size_t const esmem = sizeof(EntryPartSmem);
         RG_CUDA(cudaFuncSetAttribute(k_ent_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
@@ -319,25 +341,25 @@ void build_table(real_gpu * h, int t, uint32_t * meta)
         else
                 k_ent_scatter<<<(unsigned)std::min<uint64_t>(etiles, (uint64_t)h->sm_count * std::max(1, occ)), 256, esmem, h->st>>>(EP);
         RG_KERNEL_CHECK();
-        launch_count(h, 3);
+        launch_count(h, 2);
 
         const uint64_t * fin_seed = EP.ent_seed; const uint32_t * fin_val = EP.ent_val; const uint32_t * fin_start = EP.bucket_start;
-        if ( e2 )
+        if ( TP.e2 )
         {
                 // one resident wave each: the grid-stride sweeps then pass over the level-1 buckets in order
-                RG_CUDA(cudaMemsetAsync(sub, 0, (size_t)3 * 65600 * 4, h->st));
+                RG_CUDA(cudaMemsetAsync(EP.sub_count, 0, (size_t)3 * 65600 * 4, h->st));
                 k_ent2_hist<<<(unsigned)(h->sm_count * std::max(1, occh)), 256, 0, h->st>>>(EP);
                 RG_KERNEL_CHECK(); launch_count(h);
                 uint32_t nl = 0;
-                exclusive_scan_u32(EP.sub_count, EP.sub_start, (uint64_t)nsub + 1, ptr<uint32_t>(h->ws_stmp), h->st, &nl);
+                exclusive_scan_u32(EP.sub_count, EP.sub_start, (uint64_t)TP.nsub + 1, ptr<uint32_t>(h->ws_stmp), h->st, &nl);
                 launch_count(h, nl);
                 k_ent2_scatter<<<(unsigned)(h->sm_count * std::max(1, occ2)), 256, esmem, h->st>>>(EP);
                 RG_KERNEL_CHECK(); launch_count(h);
                 fin_seed = EP.ent2_seed; fin_val = EP.ent2_val; fin_start = EP.sub_start;
         }
-        k_build_sub<<<own_subs, 256, (size_t)3 * words * 4, h->st>>>(fin_seed, fin_val, fin_start, EP.G, sub_shift, words, ptr<SlotWord>(T.bitmap), ptr<Entry>(T.E), d_ndist, first_sub);
+        k_build_sub<<<TP.own_subs, 256, (size_t)3 * TP.words * 4, h->st>>>(fin_seed, fin_val, fin_start, EP.G, TP.sub_shift, TP.words, ptr<SlotWord>(T.bitmap), ptr<Entry>(T.E), TP.d_ndist, TP.first_sub);
         RG_KERNEL_CHECK(); launch_count(h);
-        RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
+        RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], TP.d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
 }
 
 int build_from_device(real_gpu * h)
@@ -390,10 +412,29 @@ int build_from_device(real_gpu * h)
         dev_reserve(h, h->ws_v1, maxent * 4 + 16);
         dev_reserve(h, h->ws_flags, (size_t)3 * 65600 * 4);  // sub-bucket counts, starts, cursors
         dev_reserve(h, h->ws_stmp, scan_temp_elems(65600) * 4 + 64);
-        dev_reserve(h, h->ws_hist, (1024 + 256 * EP_CURSOR_STRIDE) * 4);
+        dev_reserve(h, h->ws_hist, 3 * TABLE_META_WORDS * 4);
         memset(h->table_counts, 0, 6 * sizeof(uint32_t));
+        TablePlan plan[3];
+        EntryPartParams3 Q;
+        bool any_table = false;
         for ( int t = 0; t < 3; ++t )
-                build_table(h, t, ptr<uint32_t>(h->ws_hist));
+        {
+                plan[t] = plan_table(h, t, ptr<uint32_t>(h->ws_hist) + (size_t)t * TABLE_META_WORDS);
+                Q.P[t] = plan[t].EP;
+                any_table = any_table || ! plan[t].empty;
+        }
+        if ( any_table )
+        {
+                // the level-1 histograms of the three tables in one pass over the seeds
+                for ( int t = 0; t < 3; ++t )
+                        if ( plan[t].empty ) { Q.P[t].nids = 2 * nreads; Q.P[t].seeds = ptr<uint64_t>(h->seeds); Q.P[t].usable = ptr<uint32_t>(h->usable); }
+                if ( plan[0].empty )
+                        for ( int t = 1; t < 3; ++t ) if ( ! plan[t].empty ) { std::swap(Q.P[0], Q.P[t]); break; }       // slot 0 carries the seed pointers
+                k_ent_hist3<<<(unsigned)(h->sm_count * 8), 256, 0, h->st>>>(Q);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        for ( int t = 0; t < 3; ++t )
+                build_table(h, t, plan[t]);
         RG_CUDA(cudaEventRecord(h->ev[4], h->st));
 
         // fresh unique state (UniqueMatchInfo.hpp:172,190)
@@ -745,7 +786,7 @@ void preload_kernels(int device)
         cudaFuncAttributes a;
 #define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
         RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_pack_reads_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
-        RG_PRELOAD(k_ent_hist); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
+        RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
         RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD(k_bucket_probe);
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
