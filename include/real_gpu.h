@@ -50,7 +50,8 @@ typedef struct
 {
         uint32_t struct_size;   /* sizeof(real_gpu_params), for ABI evolution */
         int32_t device;         /* CUDA device ordinal */
-        uint32_t seedl;         /* -l  seed length, multiple of 4, 4..64 (RealOptions.cpp:434-447) */
+        uint32_t seedl;         /* -l  seed length, multiple of 4, 4..64 (RealOptions.cpp:434-447); above 32 the first 32 bases are
+                                   indexed and the whole seed is tested at verification (same match sets) */
         uint32_t seedkmax;      /* -s  mismatches allowed in the seed, 0..2 (RealOptions.cpp:449-453) */
         uint32_t totalkmax;     /* -e  mismatches allowed in the read, 0..15 (RealOptions.cpp:176-180) */
         uint32_t scores;        /* -q  quality-aware scores on/off */

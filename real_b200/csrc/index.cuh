@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) k_pack_reads(const uint8_t * __restrict__
 // k_pack_reads and replaces k_read_seeds (and the wildcard-flag array in between).
 static const uint32_t PB_MAX_W = 64;
 __global__ void __launch_bounds__(256) k_pack_both(const uint8_t * __restrict__ mapped, const uint64_t * __restrict__ offsets, uint64_t nreads, uint32_t W,
-                                                 uint32_t seedl, uint64_t * __restrict__ rpack, uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds,
+                                                 uint32_t seedl, uint32_t minlen, uint64_t * __restrict__ rpack, uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds,
                                                  uint32_t * __restrict__ usable)
 {
         __shared__ uint64_t fw[256];
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) k_pack_both(const uint8_t * __restrict__ 
         __stcs(rpack + (2 * r + 1) * W + w, rc);
         if ( w == 0 )
         {
-                bool const ok = (L >= seedl) && ! sbad[rl];
+                bool const ok = (L >= minlen) && ! sbad[rl];          // minlen = the seed length of the options (>= the indexed seed length)
                 rlen[r] = ok ? L : 0;
                 usable[r] = ok ? 1 : 0;
                 uint64_t const sf = fw[rl * W] >> (64 - 2 * seedl);
@@ -235,14 +235,14 @@ __global__ void __launch_bounds__(256) k_flags_to_bad(const uint8_t * __restrict
 // seed word = seedl bases right aligned, fragment 0 in the top bits (what getTextWord(p,seedl) yields for the
 // text window the strand is laid over); the '-' seed is the LAST seedl bases of the reverse complement strand
 // (RestMatch.hpp:84-89) = the reverse complement of the first seedl bases of the read.
-__global__ void __launch_bounds__(256) k_read_seeds(const uint64_t * __restrict__ offsets, uint64_t nreads, uint32_t W, uint32_t seedl,
+__global__ void __launch_bounds__(256) k_read_seeds(const uint64_t * __restrict__ offsets, uint64_t nreads, uint32_t W, uint32_t seedl, uint32_t minlen,
                                                   const uint64_t * __restrict__ rpack, const uint32_t * __restrict__ bad,
                                                   uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds, uint32_t * __restrict__ usable)
 {
         uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if ( r >= nreads ) return;
         uint32_t const L = (uint32_t)(offsets[r+1] - offsets[r]);
-        bool const ok = (L >= seedl) && ! bad[r];
+        bool const ok = (L >= minlen) && ! bad[r];
         rlen[r] = ok ? L : 0;
         usable[r] = ok ? 1 : 0;
         uint64_t const sf = rpack[(2*r) * W] >> (64 - 2*seedl);

@@ -364,7 +364,11 @@ void build_table(real_gpu * h, int t, TablePlan const & TP)
 
 int build_from_device(real_gpu * h)
 {
-        uint32_t const seedl = h->prm.seedl;
+        // Seeds of more than 32 bases (64-bit signatures in the reference): the index and the scan work on the first 32
+        // bases of the seed ('-': the last 32 of the strand, which lie inside the seed too) -- a seed with at most
+        // seedkmax <= 2 mismatches has at most that many in any part of it, so this finds a superset of the reference's
+        // candidates -- and the verification applies the test to the whole seed (verify_and_report, scan.cuh).
+        uint32_t const seedl = std::min<uint32_t>(h->prm.seedl, 32);
         h->F = seedl / 4;
         h->keybits = seedl;                    // two fragments of F bases = 4F bits
         h->W = std::max<uint32_t>(1, (h->maxlen + 31) / 32);
@@ -383,7 +387,7 @@ int build_from_device(real_gpu * h)
                 if ( ! h->src_packed && h->W <= PB_MAX_W )
                 {
                         uint32_t const rpb = 256 / h->W;
-                        k_pack_both<<<blocks_for(nreads, rpb), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
+                        k_pack_both<<<blocks_for(nreads, rpb), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W, seedl, h->prm.seedl, ptr<uint64_t>(h->rpack),
                                                                                 ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
                         RG_KERNEL_CHECK(); launch_count(h);
                 }
@@ -396,7 +400,7 @@ int build_from_device(real_gpu * h)
                         k_pack_reads<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W,
                                                                                           ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->bad));
                 RG_KERNEL_CHECK(); launch_count(h);
-                k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, ptr<uint64_t>(h->rpack),
+                k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, h->prm.seedl, ptr<uint64_t>(h->rpack),
                                                                        ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
                 RG_KERNEL_CHECK(); launch_count(h);
                 }
@@ -491,7 +495,7 @@ void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
         P.text = ptr<uint64_t>(h->text) + TEXT_PAD_WORDS;
         P.nmask = ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS;
         P.shard_begin = h->shard_begin;
-        uint32_t const seedl = h->prm.seedl;
+        uint32_t const seedl = std::min<uint32_t>(h->prm.seedl, 32);       // the indexed part of the seed
         // seed windows this shard evaluates: every window whose hit start (p for '+', p-(L-seedl) for '-')
         // may fall into [own_begin, own_end)
         uint64_t gwin_b = h->own_begin;
@@ -515,7 +519,7 @@ void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
                 P.tab[t].hb = h->tab[t].hb;
                 P.tab[t].nlists = h->tab[t].nentries ? h->tab[t].nlists : 0;
         }
-        P.seedl = seedl; P.F = h->F; P.keybits = h->keybits; P.seedkmax = h->prm.seedkmax; P.totalkmax = h->prm.totalkmax;
+        P.seedl = seedl; P.vseedl = h->prm.seedl; P.F = h->F; P.keybits = h->keybits; P.seedkmax = h->prm.seedkmax; P.totalkmax = h->prm.totalkmax;
         P.rpack = ptr<uint64_t>(h->rpack); P.W = h->W; P.rlen = ptr<uint32_t>(h->rlen);
         P.rec = ptr<uint64_t>(h->rec); P.nrec = h->nrec; P.fileid = h->fileid;
         P.nranks = 1; P.rank = 0; P.bucket_lo[0] = 0; P.bucket_lo[1] = SC_MAX_BUCKETS; P.seg_cap = 0; P.npairs = 0;
@@ -828,8 +832,6 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 // option domain = what RealOptions lets through (RealOptions.cpp:434-453,176-180)
                 if ( params->seedl < 4 || params->seedl > 64 || params->seedl % 4 )
                         throw std::invalid_argument("seed length must be a multiple of 4 in 4..64");
-                if ( params->seedl > 32 )
-                        throw std::invalid_argument("seed lengths above 32 (64-bit signatures) are not built in this version");
                 if ( params->seedkmax > 2 ) throw std::invalid_argument("seedkmax > 2");
                 if ( params->totalkmax > 15 ) throw std::invalid_argument("totalkmax > 15");
                 if ( params->scores && ! params->ll_table ) throw std::invalid_argument("scores requested without ll_table");

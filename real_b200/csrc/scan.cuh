@@ -75,7 +75,8 @@ struct ScanParams
         uint64_t win_begin, win_end;  // local seed-window starts this shard evaluates
         uint64_t own_begin, own_end;  // GLOBAL hit start positions this shard reports
         TableDev tab[3];
-        uint32_t seedl, F, keybits, seedkmax, totalkmax;
+        uint32_t seedl, F, keybits, seedkmax, totalkmax;        // seedl = the indexed seed bases (<= 32)
+        uint32_t vseedl;              // seed length of the options; > seedl: the rest of the seed is tested at verification
         const uint64_t * rpack;
         uint32_t W;
         const uint32_t * rlen;
@@ -892,6 +893,27 @@ struct ProbeSmem
         uint32_t stat[3][SC_THREADS];                   // per thread: candidates, seed passes, hits (far below 2^32 per launch)
 };
 
+// Seeds longer than the indexed 32 bases: the seed test of ::match (match.hpp:386-388) over the WHOLE seed of strand
+// `id` laid over the text at local position lstart (read start); a0 = first seed base in strand coordinates.  Returns
+// false when the seed has more than seedkmax mismatches; exact = which of its four fragments match exactly.
+__device__ __forceinline__ bool wide_seed_test(ScanParams const & P, uint32_t id, uint64_t lstart, uint32_t a0, uint32_t & exact)
+{
+        const uint64_t * rp = P.rpack + (uint64_t)id * P.W;
+        uint32_t const Ft = P.vseedl >> 2;
+        uint32_t seedk = 0;
+        exact = 0;
+        #pragma unroll
+        for ( uint32_t f = 0; f < 4; ++f )
+        {
+                uint64_t const rf = text_word(rp, (uint64_t)a0 + f * Ft, Ft);
+                uint64_t const tf = text_word(P.text, lstart + a0 + f * Ft, Ft);
+                uint32_t const kf = diffcount64(rf, tf);
+                seedk += kf;
+                if ( kf == 0 ) exact |= 1u << f;
+        }
+        return seedk <= P.seedkmax;
+}
+
 // stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
 // whole-read distance, report
 __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, uint32_t exact)
@@ -908,8 +930,9 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
                 uint64_t const grpos = P.shard_begin + lp;
                 if ( grpos < P.own_begin || grpos >= P.own_end ) return 0;
                 uint32_t const gfrag = record_of(P.rec, P.nrec, grpos);
-                if ( gfrag >= P.nrec || grpos + P.seedl > __ldg(P.rec + gfrag + 1) ) return 0;
-                if ( ! wildcard_free(P.nmask, lp, P.seedl) ) return 0;
+                if ( gfrag >= P.nrec || grpos + P.vseedl > __ldg(P.rec + gfrag + 1) ) return 0;
+                if ( ! wildcard_free(P.nmask, lp, P.vseedl) ) return 0;
+                if ( P.vseedl > P.seedl && ! wide_seed_test(P, id, lp, 0, exact) ) return 0;
                 unsigned long long const slot = atomicAdd(P.hit_count, 1ULL);
                 if ( slot < P.hit_cap )
                 {
@@ -928,6 +951,7 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
         uint64_t const gpos = gp - matchoffset;
         if ( gpos < P.own_begin || gpos >= P.own_end ) return 0;
         uint64_t const lpos = gpos - P.shard_begin;
+        if ( P.vseedl > P.seedl && ! wide_seed_test(P, id, lpos, strand ? (L - P.vseedl) : 0u, exact) ) return 0;
 
         // whole-read Hamming distance = seedk + restk (match.hpp:400-405); the words of the read and of the text under
         // it are fetched four at a time so that their latencies overlap (and overlap the predicates' loads below)
