@@ -5,7 +5,7 @@ import numpy as np
 
 from real_b200 import synth
 
-CASES = ["unique_fa_R1", "unique_fq_R0", "unique_dir_ragged", "unique_fq_scores_default"]
+CASES = ["unique_fa_R1", "unique_fq_R0", "unique_dir_ragged", "unique_fq_scores_default", "unique_fq_l64_scores"]
 
 
 def make_case(name, work):
@@ -64,4 +64,18 @@ def make_case(name, work):
         rf = os.path.join(work, "r.fq")
         synth.write_reads(rf, reads, True)
         return os.path.join(work, "t.fa"), rf, ["-e", "4", "-Q", "33"]
+    if name == "unique_fq_l64_scores":
+        # 64-base seeds (the reference's u_int64_t signatures), scores, repeats within epsilon
+        text = synth.make_text(341, 90000, nrecords=3, n_per_million=1000)
+        sym = text.symbols.copy()
+        seg = sym[4000:9000].copy()
+        seg[::83] = (seg[::83] + 2) % 4
+        sym[60000:65000] = seg
+        text = synth.Text(sym, text.records)
+        reads = synth.concat_reads([synth.make_reads(text, 342, 700, 100, 0.015, True), synth.make_reads(text, 343, 300, 70, 0.02, True),
+                                    synth.make_reads(text, 344, 100, 50, 0.01, True)])      # the 50-base reads are shorter than the seed
+        synth.write_fasta(os.path.join(work, "t.fa"), text)
+        rf = os.path.join(work, "r.fq")
+        synth.write_reads(rf, reads, True)
+        return os.path.join(work, "t.fa"), rf, ["-e", "4", "-Q", "33", "-l", "64"]
     raise KeyError(name)
