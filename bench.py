@@ -5,13 +5,16 @@
 
 A step = one pass of the hot path over the synthetic workload: read packing + read-side signature
 index build (K1+K2), text scan with probe/verify (K3), result reduction (and, for N>1, the one
-cross-shard exchange of matchUnique).  The text is sharded across ranks with a read-length halo,
-the read index is replicated; total work is fixed as N grows ("strong").
+cross-shard exchange of matchUnique).  N>1 (default --parallel buckets): the signature space is
+sharded -- every rank indexes and probes 1/N of the scan buckets against the whole text, no record
+exchange; total work is fixed as N grows ("strong").
 
 `value`  : whole-job reads/s with inputs resident in HBM (device pointers through the C ABI).
-`e2e`    : the same through the host-pointer C ABI (pinned host buffers; H2D of text + reads and
-           D2H of the per-read results inside the timed region).
-`roofline`: the text-scan kernel against the measured HBM peak, algorithmic bytes per SURVEY 8(d).
+`e2e`    : the same from pinned host buffers (H2D of text + 2-bit reads and D2H of the per-read
+           results inside the timed region); N=1 through the host-pointer C ABI, N>1 every rank
+           uploads 1/N of the bytes and NCCL all-gathers the rest over NVLink.
+`roofline`: the text-scan kernels against the measured HBM peak, algorithmic bytes per SURVEY 8(d),
+           `traffic` = DRAM bytes of the committed ncu capture (profiles/r01_traffic_c3.json).
 `cpu_baseline` / --impl reference: the reference's own CPU code (oracle/_ref/ref_harness, compiled
 from the reference sources) on a bounded sample, extrapolated linearly to the workload.
 """
