@@ -430,9 +430,10 @@ def main():
                 h.match_unique()
                 if world > 1:
                     rdist.unique_exchange(shard, keys=keys, ties=ties)
-                if rank == 0 or world == 1:
-                    h.get_unique(out=np_info)
-                    d2h[0] = R * 8
+                # after the exchange every rank holds the merged state: each reads back its own 1/N of the reads
+                r_lo, r_hi = (R * rank) // world, (R * (rank + 1)) // world
+                h.get_unique(out=np_info[r_lo:r_hi], first=r_lo, count=r_hi - r_lo)
+                d2h[0] = (r_hi - r_lo) * 8
             else:
                 nh = h.match_all_count()          # records land in the library's pinned host buffer
                 d2h[0] = nh * 40
@@ -448,7 +449,8 @@ def main():
                "input": "host buffers: text 2 bit/base + N mask, reads 2 bit/base (the reference's rewritten pattern file layout), "
                         "qualities 1 byte/base when scoring; result read back to pinned host memory"
                         + ("; every rank uploads 1/%d of the bytes, NCCL all-gather over NVLink for the rest (h2d_bytes_per_step is per rank)" % world
-                           if gather is not None else "")}
+                           if gather is not None else "")
+                        + ("; every rank reads back the merged result of its own 1/%d of the reads (d2h_bytes_per_step is per rank)" % world if world > 1 and unique else "")}
         del h_mapped, h_qual, h_w, h_m, h_flags
 
     dev_bytes = h.device_bytes()

@@ -186,6 +186,9 @@ int real_gpu_match_unique(real_gpu * h);
 /* Copies out the state: info[nreads] in UniqueMatchInfo bit layout (UniqueMatchInfo.hpp:26-39:
  * pos 35 | file 6 | err 4 | frag 16 | state 3, low to high), scores[nreads] or NULL. */
 int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores);
+/* The same for the reads [first, first+count) only: after the cross-shard exchange every rank of a multi-GPU job holds
+ * the merged state, and each reads back (formats, writes) its own 1/nranks of the reads. */
+int real_gpu_get_unique_range(real_gpu * h, uint64_t first, uint64_t count, uint64_t * info, float * scores);
 /* Clears the unique state (fresh UniqueMatchInfo objects). */
 int real_gpu_reset_unique(real_gpu * h);
 /* With scores the unique fold is order dependent (UpdateUniqueInfo<true>::update, matchUniqueImplementation.cpp:179-248):

@@ -1241,23 +1241,30 @@ int real_gpu_match_unique(real_gpu * h)
         RG_API_END(h)
 }
 
-int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores)
+int real_gpu_get_unique_range(real_gpu * h, uint64_t first, uint64_t count, uint64_t * info, float * scores)
 {
         RG_API_BEGIN(h)
         if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
         if ( ! info ) return fail(h, REAL_GPU_E_ARG, "get_unique: null pointer");
+        if ( first > h->nreads || count > h->nreads - first ) return fail(h, REAL_GPU_E_ARG, "get_unique: range outside the read set");
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
-        if ( h->nreads ) RG_CUDA(cudaMemcpyAsync(info, h->info.p, h->nreads * 8, cudaMemcpyDeviceToHost, h->st));
+        if ( count ) RG_CUDA(cudaMemcpyAsync(info, ptr<uint64_t>(h->info) + first, count * 8, cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaEventRecord(h->ev[1], h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.d2h_ms = elapsed(h->ev[0], h->ev[1]);
         if ( scores )
         {
-                if ( h->prm.scores && h->nreads ) RG_CUDA(cudaMemcpy(scores, h->scores.p, h->nreads * 4, cudaMemcpyDeviceToHost));
-                else for ( uint64_t i = 0; i < h->nreads; ++i ) scores[i] = 0.0f;
+                if ( h->prm.scores && count ) RG_CUDA(cudaMemcpy(scores, ptr<float>(h->scores) + first, count * 4, cudaMemcpyDeviceToHost));
+                else for ( uint64_t i = 0; i < count; ++i ) scores[i] = 0.0f;
         }
         return REAL_GPU_OK;
         RG_API_END(h)
+}
+
+int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores)
+{
+        if ( ! h ) return REAL_GPU_E_ARG;
+        return real_gpu_get_unique_range(h, 0, h->nreads, info, scores);
 }
 
 int real_gpu_reset_unique(real_gpu * h)

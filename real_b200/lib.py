@@ -92,6 +92,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_match_all.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.real_gpu_match_unique.argtypes = [vp]
     L.real_gpu_get_unique.argtypes = [vp, vp, vp]
+    L.real_gpu_get_unique_range.argtypes = [vp, u64, u64, vp, vp]
     L.real_gpu_reset_unique.argtypes = [vp]
     L.real_gpu_set_block_windows.argtypes = [vp, u64]
     L.real_gpu_unique_export_keys.argtypes = [vp, vp]
@@ -229,10 +230,12 @@ class Handle:
     def match_unique(self):
         self._check(self.L.real_gpu_match_unique(self.h))
 
-    def get_unique(self, out: np.ndarray | None = None):
-        info = out if out is not None else np.zeros(self.nreads, dtype=np.uint64)
-        sc = np.zeros(self.nreads, dtype=np.float32) if self.scores else None
-        self._check(self.L.real_gpu_get_unique(self.h, info.ctypes.data, sc.ctypes.data if sc is not None else None))
+    def get_unique(self, out: np.ndarray | None = None, first: int = 0, count: int | None = None):
+        """UniqueMatchInfo words (and scores) of the reads [first, first+count); default: all reads."""
+        count = self.nreads - first if count is None else count
+        info = out if out is not None else np.zeros(count, dtype=np.uint64)
+        sc = np.zeros(count, dtype=np.float32) if self.scores else None
+        self._check(self.L.real_gpu_get_unique_range(self.h, first, count, info.ctypes.data, sc.ctypes.data if sc is not None else None))
         return info, sc
 
     def reset_unique(self):
