@@ -664,11 +664,14 @@ uint64_t run_scan(real_gpu * h, int mode)
                 }
                 RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
                 RG_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-                RG_CUDA(cudaFuncSetAttribute(k_bucket_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+                bool const wide = h->prm.seedl > 32;
+                RG_CUDA(cudaFuncSetAttribute(k_bucket_probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+                RG_CUDA(cudaFuncSetAttribute(k_bucket_probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
                 int occ_p = 0, occ_b = 0, occ_s = 0;
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, psmem));
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_part_scatter, SC_THREADS, ssmem));
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bucket_probe, SC_THREADS, bsmem));
+                if ( wide ) RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bucket_probe<true>, SC_THREADS, bsmem));
+                else RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bucket_probe<false>, SC_THREADS, bsmem));
                 if ( occ_p < 1 ) occ_p = 1;
                 if ( occ_s < 1 ) occ_s = 1;
                 if ( occ_b < 1 ) occ_b = 1;
@@ -735,7 +738,8 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 RG_KERNEL_CHECK(); launch_count(h);
                         }
                         mark();
-                        k_bucket_probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
+                        if ( wide ) k_bucket_probe<true><<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
+                        else k_bucket_probe<false><<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
                         mark();
                         if ( sharded )
@@ -792,7 +796,7 @@ void preload_kernels(int device)
         RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_pack_reads_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
         RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
-        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD(k_bucket_probe);
+        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD(k_bucket_probe<false>); RG_PRELOAD(k_bucket_probe<true>);
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
         RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay);

@@ -916,6 +916,7 @@ __device__ __forceinline__ bool wide_seed_test(ScanParams const & P, uint32_t id
 
 // stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
 // whole-read distance, report
+template<bool WIDE>
 __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, uint32_t exact)
 {
         uint32_t const strand = id & 1;
@@ -932,7 +933,7 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
                 uint32_t const gfrag = record_of(P.rec, P.nrec, grpos);
                 if ( gfrag >= P.nrec || grpos + P.vseedl > __ldg(P.rec + gfrag + 1) ) return 0;
                 if ( ! wildcard_free(P.nmask, lp, P.vseedl) ) return 0;
-                if ( P.vseedl > P.seedl && ! wide_seed_test(P, id, lp, 0, exact) ) return 0;
+                if ( WIDE && ! wide_seed_test(P, id, lp, 0, exact) ) return 0;
                 unsigned long long const slot = atomicAdd(P.hit_count, 1ULL);
                 if ( slot < P.hit_cap )
                 {
@@ -951,7 +952,7 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
         uint64_t const gpos = gp - matchoffset;
         if ( gpos < P.own_begin || gpos >= P.own_end ) return 0;
         uint64_t const lpos = gpos - P.shard_begin;
-        if ( P.vseedl > P.seedl && ! wide_seed_test(P, id, lpos, strand ? (L - P.vseedl) : 0u, exact) ) return 0;
+        if ( WIDE && ! wide_seed_test(P, id, lpos, strand ? (L - P.vseedl) : 0u, exact) ) return 0;
 
         // whole-read Hamming distance = seedk + restk (match.hpp:400-405); the words of the read and of the text under
         // it are fetched four at a time so that their latencies overlap (and overlap the predicates' loads below)
@@ -1012,6 +1013,7 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
 // stage A: a set slot bit with the index e of its first entry -> entry chain; per entry the seed test
 // (match.hpp:386-388) and the canonical-list rule: of the up to six lists that reach a position,
 // only the pair made of the two LOWEST exact fragments reports it (replaces unifyMatches' dedup)
+template<bool WIDE>
 __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, uint32_t e, ItemB * qb, uint32_t * qbn, uint32_t * lstats, uint64_t pol_e)
 {
         int const table = (int)(it.post >> 30);
@@ -1053,11 +1055,12 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
                         qb[o] = ib;
                 }
                 else
-                        lstats[2] += verify_and_report(P, lp, id, exact4);          // queue full: handle it here
+                        lstats[2] += verify_and_report<WIDE>(P, lp, id, exact4);          // queue full: handle it here
         }
 }
 
 // the warp's stage B queue
+template<bool WIDE>
 __device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, uint32_t * qbn, int lane, uint32_t * lstats)
 {
         uint32_t const n = min(*qbn, (uint32_t)SC_QB_CAP);
@@ -1065,7 +1068,7 @@ __device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, u
         for ( uint32_t i = lane; i < n; i += 32 )
         {
                 ItemB const ib = qb[i];
-                lstats[2] += verify_and_report(P, ib.lp, ib.id, ib.exact);
+                lstats[2] += verify_and_report<WIDE>(P, ib.lp, ib.id, ib.exact);
         }
         __syncwarp();
         if ( lane == 0 ) *qbn = 0;
@@ -1075,6 +1078,7 @@ __device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, u
 // the warp's stage A queue (n items, the same value in every lane): full rounds of 32 from the top of the queue;
 // with `flush` also the rest.  Returns the number of items left.  The statistics go to per-thread shared-memory
 // counters so that the probe loop carries no state for this path.
+template<bool WIDE>
 __device__ __forceinline__ uint32_t drain_a_warp(ScanParams const & P, ProbeSmem & S, uint32_t n, bool flush)
 {
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1090,14 +1094,14 @@ __device__ __forceinline__ uint32_t drain_a_warp(ScanParams const & P, ProbeSmem
         {
                 uint32_t const take = n >= 32 ? 32u : n;
                 if ( (uint32_t)lane < take )
-                        follow_item(P, qa[n - take + lane], qe[n - take + lane], qb, qbn, lstats, pol_e);
+                        follow_item<WIDE>(P, qa[n - take + lane], qe[n - take + lane], qb, qbn, lstats, pol_e);
                 __syncwarp();
                 n -= take;
                 if ( *qbn >= 32 )
-                        drain_b_warp(P, qb, qbn, lane, lstats);
+                        drain_b_warp<WIDE>(P, qb, qbn, lane, lstats);
         }
         if ( flush && *qbn )
-                drain_b_warp(P, qb, qbn, lane, lstats);
+                drain_b_warp<WIDE>(P, qb, qbn, lane, lstats);
         #pragma unroll
         for ( int s = 0; s < 3; ++s )
                 if ( lstats[s] ) S.stat[s][threadIdx.x] += lstats[s];
@@ -1118,6 +1122,8 @@ __device__ __forceinline__ const uint4 * grab_records(ScanParams const & P, uint
         return P.recs + (uint64_t)__ldg(P.pair_rec + lo) + (uint64_t)(g - __ldg(P.pair_grab + lo)) * SC_UNIT;
 }
 
+// WIDE: seeds longer than the indexed 32 bases (the whole-seed test costs registers the common case must not pay for)
+template<bool WIDE>
 __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(const __grid_constant__ ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
@@ -1230,12 +1236,12 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
                                         qn = 0;
                                 }
                                 else if ( qn >= 32 )
-                                        qn = drain_a_warp(P, S, qn, false);
+                                        qn = drain_a_warp<WIDE>(P, S, qn, false);
                         }
                 }
                 g = gn;
         }
-        drain_a_warp(P, S, qn, true);
+        drain_a_warp<WIDE>(P, S, qn, true);
 
         // statistics: one atomic per warp and counter
         #pragma unroll

@@ -1,10 +1,9 @@
 #!/bin/bash
-# development experiment: gpu parity tests on the default build, then the C3 scan with differently tuned builds
+# development experiment: the C3 step with differently tuned builds (real_b200/variants/*.so, built with -D flags)
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
 run() { # name, env...
   name=$1; shift
-  env "$@" python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/var_$name.log 2>&1
+  env "$@" python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/var_$name.log 2>&1
   echo "$name rc=$? $(tail -1 gpurun_out/var_$name.log | python -c 'import sys,json; d=json.loads(sys.stdin.readline()); print(d["ms_per_step"], d["phases_ms"]["pack_ms"], d["phases_ms"]["index_ms"], d["phases_ms"]["scan_ms"], d["counts"]["hits"])' 2>&1)"
 }
 run default A=1
