@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(256) k_ent2_hist(EntryPartParams P)
 }
 
 // level 2: the entries of every level-1 bucket grouped again by the next e2bits of their slot
-__global__ void __launch_bounds__(256) k_ent2_scatter(EntryPartParams P)
+__global__ void __launch_bounds__(256, 4) k_ent2_scatter(EntryPartParams P)
 {
         extern __shared__ __align__(16) unsigned char ep_smem[];
         EntryPartSmem & S = *reinterpret_cast<EntryPartSmem *>(ep_smem);
