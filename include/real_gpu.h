@@ -138,6 +138,26 @@ int real_gpu_set_text_device(real_gpu * h, uint32_t fileid,
                              uint64_t own_begin, uint64_t own_end,
                              const uint64_t * record_starts, uint32_t nrecords);
 
+/* Text of one whole file straight from the BYTES of its FASTA file: the library runs the reference's text loader on
+ * the device (K0, csrc/ingest.cuh) -- countLength + readFile (countReads.cpp:28-125: '>' opens a header up to the
+ * next '\n', wherever it stands; outside headers A C G T N are kept, every other byte is dropped) and the packing of
+ * AutoTextArray (AutoTextArray.hpp:27-61) -- and sets the result as the current text, as real_gpu_set_text would with
+ * shard = own range = the whole file.  *n_bases = bases kept, *nrecords = headers closed by a '\n'
+ * (ranges.size() - 1 of countLength).  When either is 0 the call succeeds but no text is set.
+ * Limits as for real_gpu_set_text.  The caller's buffer is free again when the call returns. */
+int real_gpu_set_text_fasta(real_gpu * h, uint32_t fileid, const void * fasta_bytes, uint64_t nbytes,
+                            uint64_t * n_bases, uint64_t * nrecords);
+/* Same, with the file bytes already in device memory (16-byte aligned; not modified, not kept). */
+int real_gpu_set_text_fasta_device(real_gpu * h, uint32_t fileid, const void * d_fasta_bytes, uint64_t nbytes,
+                                   uint64_t * n_bases, uint64_t * nrecords);
+/* Record table of the text set by real_gpu_set_text_fasta*: record_starts[nrecords+1] (last == n_bases) and, per
+ * record, the file offset of the '\n' that closed its header -- the record's name is the bytes between the last '>'
+ * in front of that offset and the offset itself (countReads.cpp:44-58).  Either pointer may be NULL. */
+int real_gpu_get_text_records(real_gpu * h, uint64_t * record_starts, uint64_t * header_ends);
+/* Copies the current text (shard) back in the layout real_gpu_set_text takes: (shard_len+31)/32 words and
+ * (shard_len+63)/64 mask words.  Either pointer may be NULL. */
+int real_gpu_get_text_packed(real_gpu * h, uint64_t * words, uint64_t * nmask);
+
 /* Read set (replaces reader_type::fillPatternBlock + Pattern::computeMapped + RestWordBuffer::setup*
  * + SignatureConstruction::signatureMapped/reverseMappedSignature per read, and the index build
  * ListSet::sort + getLookupTable, here on the read side).

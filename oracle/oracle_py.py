@@ -211,3 +211,35 @@ def run_ref(mode: str, workdir: str, real_args, gap_dump: bool = False, env=None
             order.append(name)
     timing["file_order"] = order
     return timing, dump, gpath
+
+
+# ------------------------------------------------------------------ text loader (restatement)
+
+def fasta_text(data: bytes):
+    """The reference's text loader restated: countLength + readFile (countReads.cpp:28-125).
+    Returns (symbols uint8 0..4, record names (bytes), record starts incl. the terminal entry).
+    '>' opens a header wherever it stands and clears the name; '\\n' closes a header (filing the record at the base count of
+    the '>') ; inside a header every other byte joins the name; outside, A C G T N are kept and everything else is dropped.
+    Pinned against the reference's own getText by tests/golden/text_quirks.npz (tests/test_oracle_golden.py)."""
+    code = {65: 0, 67: 1, 71: 2, 84: 3, 78: 4}
+    syms = bytearray()
+    names, starts = [], []
+    header = False
+    name = bytearray()
+    idcnt = 0
+    for c in data:
+        if c == 62:            # '>'
+            header = True
+            idcnt = len(syms)
+            name = bytearray()
+        elif c == 10:          # '\n'
+            if header:
+                names.append(bytes(name))
+                starts.append(idcnt)
+            header = False
+        elif header:
+            name.append(c)
+        elif c in code:
+            syms.append(code[c])
+    starts.append(len(syms))
+    return np.frombuffer(bytes(syms), dtype=np.uint8), names, np.asarray(starts, dtype=np.uint64)

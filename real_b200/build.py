@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libreal_gpu.so")
 SOURCES = ["real_gpu.cu"]
-HEADERS = ["common.cuh", "prims.cuh", "index.cuh", "scan.cuh", "post.cuh"]
+HEADERS = ["common.cuh", "prims.cuh", "index.cuh", "scan.cuh", "post.cuh", "ingest.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

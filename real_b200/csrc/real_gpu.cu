@@ -7,6 +7,7 @@
 #include "index.cuh"
 #include "scan.cuh"
 #include "post.cuh"
+#include "ingest.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -57,6 +58,10 @@ struct real_gpu
         DevBuf text, nmask, rec;
         uint64_t n_total, shard_begin, shard_len, own_begin, own_end;
         uint32_t nrec, fileid;
+        // text ingest (real_gpu_set_text_fasta*): file bytes, tile summaries and offsets, record table of the last file
+        DevBuf fa_raw, fa_sums, fa_tbase, fa_trec, fa_recnl, fa_tot;
+        uint64_t * fa_totals;          // [2] pinned host memory: kept bases, records
+        std::vector<uint64_t> fa_rec_starts, fa_rec_nl;
 
         // reads
         bool have_reads;
@@ -109,7 +114,7 @@ struct real_gpu
         uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
 
-        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -223,6 +228,80 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
 
         h->fileid = fileid; h->n_total = n_total; h->shard_begin = shard_begin; h->shard_len = shard_len;
         h->own_begin = own_begin; h->own_end = own_end; h->nrec = nrecords;
+        h->fa_rec_starts.clear(); h->fa_rec_nl.clear();
+        h->have_text = true;
+        return REAL_GPU_OK;
+}
+
+// K0: the text straight from the bytes of its FASTA file (ingest.cuh).  Everything runs on the copy stream, like the
+// transfer of a packed text, so an index build in flight on the kernel stream overlaps it.
+int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uint64_t nbytes, bool on_device, uint64_t * n_bases, uint64_t * nrecords)
+{
+        if ( (! bytes && nbytes) || ! n_bases || ! nrecords )
+                return fail(h, REAL_GPU_E_ARG, "set_text_fasta: null pointer");
+        if ( on_device && ((uintptr_t)bytes & 15) )
+                return fail(h, REAL_GPU_E_ARG, "set_text_fasta_device: the buffer must be 16-byte aligned");
+        if ( fileid >= 64 )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text: fileid >= 64 (UniqueMatchInfo.hpp:31)");
+        uint64_t const ntiles = (nbytes + FA_TILE - 1) / FA_TILE;
+        if ( ntiles >= (1ULL << 31) )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text_fasta: file longer than 2^43 bytes");
+        h->have_text = false;
+        h->fa_rec_starts.clear(); h->fa_rec_nl.clear();
+        *n_bases = 0; *nrecords = 0;
+
+        RG_CUDA(cudaEventRecord(h->evc[0], h->st2));
+        const uint8_t * d_raw = static_cast<const uint8_t *>(bytes);
+        if ( ! on_device )
+        {
+                dev_reserve(h, h->fa_raw, nbytes);
+                RG_CUDA(cudaMemcpyAsync(h->fa_raw.p, bytes, nbytes, cudaMemcpyHostToDevice, h->st2));
+                d_raw = ptr<uint8_t>(h->fa_raw);
+        }
+        dev_reserve(h, h->fa_sums, ntiles * sizeof(FaSum32));
+        dev_reserve(h, h->fa_tbase, ntiles * 8);
+        dev_reserve(h, h->fa_trec, ntiles * 8);
+        dev_reserve(h, h->fa_tot, 16);
+        if ( ntiles )
+                k_fa_summary<<<(unsigned)ntiles, FA_THREADS, 0, h->st2>>>(d_raw, nbytes, ptr<FaSum32>(h->fa_sums));
+        k_fa_scan<<<1, FA_SCAN_THREADS, 0, h->st2>>>(ptr<FaSum32>(h->fa_sums), ntiles, ptr<uint64_t>(h->fa_tbase), ptr<uint64_t>(h->fa_trec), ptr<uint64_t>(h->fa_tot));
+        RG_CUDA(cudaGetLastError());
+        launch_count(h, ntiles ? 2 : 1);
+        RG_CUDA(cudaMemcpyAsync(h->fa_totals, h->fa_tot.p, 16, cudaMemcpyDeviceToHost, h->st2));
+        RG_CUDA(cudaStreamSynchronize(h->st2));                 // the caller's bytes are on the device; the sizes are known
+        uint64_t const n = h->fa_totals[0], nrec = h->fa_totals[1];
+        *n_bases = n; *nrecords = nrec;
+        if ( n >= (1ULL << 35) )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text: text longer than 2^35 bases (UniqueMatchInfo.hpp:29-33)");
+        if ( nrec >= (1ULL << 32) )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text_fasta: more than 2^32 records");
+        if ( n == 0 || nrec == 0 )
+                return REAL_GPU_OK;                             // nothing to match against; no text is set
+
+        uint64_t const nw = (n + 31) / 32, nmw = (n + 63) / 64;
+        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + PF_SMEM_WORDS;
+        size_t const tbytes = (TEXT_PAD_WORDS + nw + tail) * 8, mbytes = (TEXT_PAD_WORDS + nmw + tail) * 8;
+        dev_reserve(h, h->text, tbytes);
+        dev_reserve(h, h->nmask, mbytes);
+        dev_reserve(h, h->rec, (size_t)(nrec + 1) * 8);
+        dev_reserve(h, h->fa_recnl, (size_t)nrec * 8);
+        RG_CUDA(cudaMemsetAsync(h->text.p, 0, tbytes, h->st2));
+        RG_CUDA(cudaMemsetAsync(h->nmask.p, 0, mbytes, h->st2));
+        k_fa_pack<<<(unsigned)ntiles, FA_THREADS, 0, h->st2>>>(d_raw, nbytes, ptr<uint64_t>(h->fa_tbase), ptr<uint64_t>(h->fa_trec),
+                                                               ptr<unsigned long long>(h->text) + TEXT_PAD_WORDS, ptr<unsigned long long>(h->nmask) + TEXT_PAD_WORDS,
+                                                               ptr<uint64_t>(h->rec), ptr<uint64_t>(h->fa_recnl));
+        RG_CUDA(cudaGetLastError());
+        launch_count(h);
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->rec) + nrec, h->fa_totals, 8, cudaMemcpyHostToDevice, h->st2));
+        RG_CUDA(cudaEventRecord(h->evc[1], h->st2));
+        h->fa_rec_starts.resize(nrec + 1); h->fa_rec_nl.resize(nrec);
+        RG_CUDA(cudaMemcpyAsync(&h->fa_rec_starts[0], h->rec.p, (size_t)(nrec + 1) * 8, cudaMemcpyDeviceToHost, h->st2));
+        RG_CUDA(cudaMemcpyAsync(&h->fa_rec_nl[0], h->fa_recnl.p, (size_t)nrec * 8, cudaMemcpyDeviceToHost, h->st2));
+        RG_CUDA(cudaStreamSynchronize(h->st2));
+        h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);   // transfer of the file bytes + the three ingest kernels
+
+        h->fileid = fileid; h->n_total = n; h->shard_begin = 0; h->shard_len = n;
+        h->own_begin = 0; h->own_end = n; h->nrec = (uint32_t)nrec;
         h->have_text = true;
         return REAL_GPU_OK;
 }
@@ -800,6 +879,7 @@ void preload_kernels(int device)
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
         RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay);
+        RG_PRELOAD(k_fa_summary); RG_PRELOAD(k_fa_scan); RG_PRELOAD(k_fa_pack);
         RG_PRELOAD(k_window_counts); RG_PRELOAD(k_block_bounds); RG_PRELOAD(k_gap_dp); RG_PRELOAD(k_gap_replay);
 #undef RG_PRELOAD
         done[device] = true;
@@ -854,6 +934,7 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
                 RG_CUDA(cudaMallocHost(&h->table_counts, 6 * sizeof(uint32_t)));
+                RG_CUDA(cudaMallocHost(&h->fa_totals, 2 * sizeof(uint64_t)));
                 for ( int i = 0; i < 8; ++i ) RG_CUDA(cudaEventCreate(&h->ev[i]));
                 for ( int i = 0; i < 2; ++i ) RG_CUDA(cudaEventCreate(&h->evc[i]));
                 if ( params->ll_table )
@@ -880,7 +961,8 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores };
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
+                           &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
         for ( int r = 0; r < SC_MAX_RANKS; ++r )
@@ -892,6 +974,7 @@ int real_gpu_destroy(real_gpu * h)
         for ( int i = 0; i < 2; ++i ) if ( h->evc[i] ) cudaEventDestroy(h->evc[i]);
         if ( h->st2 ) cudaStreamDestroy(h->st2);
         if ( h->table_counts ) cudaFreeHost(h->table_counts);
+        if ( h->fa_totals ) cudaFreeHost(h->fa_totals);
         if ( h->st ) cudaStreamDestroy(h->st);
         delete h;
         return REAL_GPU_OK;
@@ -914,6 +997,42 @@ int real_gpu_set_text_device(real_gpu * h, uint32_t fileid, const uint64_t * d_w
 {
         RG_API_BEGIN_ASYNC(h)
         return set_text_common(h, fileid, d_words, d_nmask, true, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords);
+        RG_API_END(h)
+}
+
+int real_gpu_set_text_fasta(real_gpu * h, uint32_t fileid, const void * fasta_bytes, uint64_t nbytes, uint64_t * n_bases, uint64_t * nrecords)
+{
+        RG_API_BEGIN_ASYNC(h)
+        return set_text_fasta_common(h, fileid, fasta_bytes, nbytes, false, n_bases, nrecords);
+        RG_API_END(h)
+}
+
+int real_gpu_set_text_fasta_device(real_gpu * h, uint32_t fileid, const void * d_fasta_bytes, uint64_t nbytes, uint64_t * n_bases, uint64_t * nrecords)
+{
+        RG_API_BEGIN_ASYNC(h)
+        return set_text_fasta_common(h, fileid, d_fasta_bytes, nbytes, true, n_bases, nrecords);
+        RG_API_END(h)
+}
+
+int real_gpu_get_text_records(real_gpu * h, uint64_t * record_starts, uint64_t * header_ends)
+{
+        RG_API_BEGIN_ASYNC(h)
+        if ( ! h->have_text || h->fa_rec_starts.size() != (size_t)h->nrec + 1 )
+                return fail(h, REAL_GPU_E_STATE, "get_text_records: the current text was not set by real_gpu_set_text_fasta");
+        if ( record_starts ) memcpy(record_starts, &h->fa_rec_starts[0], h->fa_rec_starts.size() * 8);
+        if ( header_ends && h->nrec ) memcpy(header_ends, &h->fa_rec_nl[0], h->fa_rec_nl.size() * 8);
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_get_text_packed(real_gpu * h, uint64_t * words, uint64_t * nmask)
+{
+        RG_API_BEGIN_ASYNC(h)
+        if ( ! h->have_text ) return fail(h, REAL_GPU_E_STATE, "no text set");
+        if ( words ) RG_CUDA(cudaMemcpyAsync(words, ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, (h->shard_len + 31) / 32 * 8, cudaMemcpyDeviceToHost, h->st2));
+        if ( nmask ) RG_CUDA(cudaMemcpyAsync(nmask, ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, (h->shard_len + 63) / 64 * 8, cudaMemcpyDeviceToHost, h->st2));
+        RG_CUDA(cudaStreamSynchronize(h->st2));
+        return REAL_GPU_OK;
         RG_API_END(h)
 }
 

@@ -617,6 +617,61 @@ namespace
                         throw std::runtime_error("real_gpu_create failed (no CUDA device or unsupported option); there is no CPU fallback");
         }
 
+        // getText (getText.hpp:31-58) for the device: the bytes of the file go to real_gpu_set_text_fasta, which parses and
+        // packs them there and sets the text; the record table comes back for the output lines.  T.words / T.nmask stay empty.
+        // REAL_TEXT_LOADER=host selects the host parser + real_gpu_set_text instead (timing comparisons, tests).
+        // Returns false when the file holds nothing to match against (too short for the seed, or over the library's limits
+        // when skip_over_limits is set).
+        bool setText(Gpu & G, RealOptions const & opts, uint32_t fileid, std::string const & filename, TextFile & T, bool skip_over_limits)
+        {
+                char const * const loader = getenv("REAL_TEXT_LOADER");
+                if ( loader && std::string(loader) == "host" )
+                {
+                        getText(filename, T);
+                        if ( skip_over_limits && (fileid >= 64 || T.n >= (1ULL << 35)) )
+                                return false;
+                        if ( T.n < (uint64_t)opts.seedl )
+                                return false;
+                        std::vector<uint64_t> const starts = T.starts();
+                        G.check(real_gpu_set_text(G.h, fileid, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
+                        return true;
+                }
+                std::cerr << "Computing length of file " << filename << "...";
+                std::vector<char> buf;
+                slurp(filename, buf);
+                T.ranges.clear(); T.words.clear(); T.nmask.clear(); T.n = 0;
+                if ( skip_over_limits && fileid >= 64 )
+                        return false;
+                uint64_t n = 0, nrec = 0;
+                int const rc = real_gpu_set_text_fasta(G.h, fileid, buf.empty() ? 0 : &buf[0], buf.size(), &n, &nrec);
+                T.n = n;
+                std::cerr << "done, length is " << n << std::endl;
+                if ( rc == REAL_GPU_E_LIMIT && skip_over_limits )
+                {
+                        T.ranges.push_back(std::pair<std::string, uint64_t>("terminal", n));
+                        return false;
+                }
+                G.check(rc, "set_text_fasta");
+                if ( n && nrec )
+                {
+                        std::vector<uint64_t> starts(nrec + 1), ends(nrec);
+                        G.check(real_gpu_get_text_records(G.h, &starts[0], &ends[0]), "get_text_records");
+                        T.ranges.reserve(nrec + 1);
+                        for ( uint64_t r = 0; r < nrec; ++r )
+                        {
+                                uint64_t b = ends[r];
+                                while ( b > 0 && buf[b-1] != '>' ) --b;         // the name starts behind the line's last '>' (countReads.cpp:47-51)
+                                T.ranges.push_back(std::pair<std::string, uint64_t>(std::string(&buf[0] + b, &buf[0] + ends[r]), starts[r]));
+                        }
+                }
+                T.ranges.push_back(std::pair<std::string, uint64_t>("terminal", n));
+                if ( n < (uint64_t)opts.seedl )
+                        return false;
+                if ( ! nrec )
+                        throw std::runtime_error("set_text: null pointer or no records");
+                return true;
+        }
+
         void loadReads(RealOptions const & opts, ReadSet & reads)
         {
                 int qualityOffset = 0;
@@ -647,14 +702,11 @@ int doMatchingAll(RealOptions const & opts)
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
         {
                 TextFile T;
-                getText(filenames[fi], T);
-                if ( T.n < (uint64_t)opts.seedl )
+                if ( ! setText(G, opts, (uint32_t)fi, filenames[fi], T, false) )
                 {
                         std::cerr << "file " << filenames[fi] << " is too short for seed length " << opts.seedl << std::endl;
                         continue;
                 }
-                std::vector<uint64_t> const starts = T.starts();
-                G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
                 real_gpu_hit const * hits = 0; uint64_t nhits = 0;
                 G.check(real_gpu_match_all(G.h, &hits, &nhits), "match_all");
                 PT.lap("text + match_all");
@@ -715,17 +767,15 @@ int doMatchingUnique(RealOptions const & opts)
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
         {
                 TextFile T;
-                getText(filenames[fi], T);
+                bool const usable = setText(G, opts, (uint32_t)fi, filenames[fi], T, true);
                 rangeset[fi] = T.ranges;
                 if ( fi >= 64 || T.n >= (1ULL << 35) || T.ranges.size() > 65536 )
                 {
                         std::cerr << "Skipping file " << filenames[fi] << " as it exceeds the limits of UniqueMatchInfo." << std::endl;
                         continue;
                 }
-                if ( T.n < (uint64_t)opts.seedl )
+                if ( ! usable )
                         continue;
-                std::vector<uint64_t> const starts = T.starts();
-                G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
                 if ( opts.scores )
                         G.check(real_gpu_set_block_windows(G.h, planBlockWindows(opts, T, reads.size())), "set_block_windows");
                 G.check(real_gpu_match_unique(G.h), "match_unique");
@@ -737,11 +787,8 @@ int doMatchingUnique(RealOptions const & opts)
                 for ( size_t fi = 0; fi < filenames.size(); ++fi )
                 {
                         TextFile T;
-                        getText(filenames[fi], T);
-                        if ( fi >= 64 || T.n >= (1ULL << 35) || T.ranges.size() > 65536 || T.n < (uint64_t)opts.seedl )
+                        if ( ! setText(G, opts, (uint32_t)fi, filenames[fi], T, true) || T.ranges.size() > 65536 )
                                 continue;
-                        std::vector<uint64_t> const starts = T.starts();
-                        G.check(real_gpu_set_text(G.h, (uint32_t)fi, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
                         G.check(real_gpu_match_gaps(G.h, planBlockWindows(opts, T, reads.size())), "match_gaps");
                 }
         }

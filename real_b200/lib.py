@@ -86,6 +86,10 @@ def load(build_if_missing: bool = True):
     L.real_gpu_last_error.restype = C.c_char_p
     L.real_gpu_set_text.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_text_device.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
+    L.real_gpu_set_text_fasta.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.real_gpu_set_text_fasta_device.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.real_gpu_get_text_records.argtypes = [vp, vp, vp]
+    L.real_gpu_get_text_packed.argtypes = [vp, vp, vp]
     L.real_gpu_set_reads.argtypes = [vp, vp, vp, vp, u64]
     L.real_gpu_set_reads_device.argtypes = [vp, vp, vp, vp, u64, u64, u32]
     L.real_gpu_set_reads_packed.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64]
@@ -181,6 +185,32 @@ class Handle:
         rs = np.ascontiguousarray(record_starts, dtype=np.uint64)
         self._check(self.L.real_gpu_set_text_device(self.h, fileid, d_words, d_nmask, n_total, shard_begin, shard_len,
                                                     own_begin, own_end, rs.ctypes.data, rs.size - 1))
+
+    def set_text_fasta(self, data, fileid: int = 0, device_ptr: int | None = None, nbytes: int | None = None):
+        """Text straight from the bytes of a FASTA file (K0, on the device).  data = bytes / uint8 array, or device_ptr + nbytes.
+        Returns (n_bases, nrecords); no text is set when either is 0."""
+        n, r = C.c_uint64(), C.c_uint64()
+        if device_ptr is not None:
+            self._check(self.L.real_gpu_set_text_fasta_device(self.h, fileid, device_ptr, nbytes, C.byref(n), C.byref(r)))
+        else:
+            a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
+            self._check(self.L.real_gpu_set_text_fasta(self.h, fileid, a.ctypes.data if a.size else None, a.size, C.byref(n), C.byref(r)))
+        self._text_n, self._text_nrec = int(n.value), int(r.value)
+        return self._text_n, self._text_nrec
+
+    def get_text_records(self):
+        """(record_starts[nrecords+1], header_ends[nrecords]) of the text set by set_text_fasta."""
+        starts = np.zeros(self._text_nrec + 1, dtype=np.uint64)
+        ends = np.zeros(max(self._text_nrec, 1), dtype=np.uint64)
+        self._check(self.L.real_gpu_get_text_records(self.h, starts.ctypes.data, ends.ctypes.data))
+        return starts, ends[:self._text_nrec]
+
+    def get_text_packed(self, n: int):
+        """The current text as (words, nmask) in the layout set_text takes; n = its length in bases."""
+        words = np.zeros((n + 31) // 32, dtype=np.uint64)
+        nmask = np.zeros((n + 63) // 64, dtype=np.uint64)
+        self._check(self.L.real_gpu_get_text_packed(self.h, words.ctypes.data, nmask.ctypes.data))
+        return words, nmask
 
     # ---- reads
     def set_reads(self, mapped: np.ndarray, offsets: np.ndarray, quality: np.ndarray | None = None):

@@ -241,6 +241,17 @@ class MatcherBase:
             self.handle.set_text(np.ascontiguousarray(words[w0:w1]), np.ascontiguousarray(nmask[m0:m1]), n_total, record_starts,
                                  fileid, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
 
+    def set_text_fasta(self, data, fileid: int = 0):
+        """Text of file `fileid` from the bytes of its FASTA file, parsed and packed on the device (getText, getText.hpp:31-58).
+        Returns (n_bases, [(record name, start)] + [("terminal", n)]) like countLength's `ranges` (countReads.cpp:28-85)."""
+        n, nrec = self.handle.set_text_fasta(data, fileid)
+        if not n or not nrec:
+            return n, [(b"terminal", n)]
+        starts, ends = self.handle.get_text_records()
+        buf = bytes(data)
+        ranges = [(buf[buf.rfind(b">", 0, int(e)) + 1:int(e)], int(s)) for s, e in zip(starts[:-1], ends)]
+        return n, ranges + [(b"terminal", n)]
+
     def stats(self) -> dict:
         return self.handle.stats()
 

@@ -136,15 +136,25 @@ def make_text(seed: int, n: int, nrecords: int = 1, n_per_million: int = 0) -> T
     return Text(symbols=sym, records=recs)
 
 
-def write_fasta(path: str, text: Text, line: int = 60) -> None:
-    """FASTA writer in `randstr.cpp` style (60 columns)."""
+def write_fasta_file(f, text: Text, line: int = 60) -> None:
+    """FASTA writer in `randstr.cpp` style (60 columns) onto an open binary file."""
     starts = [s for _, s in text.records] + [text.n]
+    for (name, s), e in zip(text.records, starts[1:]):
+        f.write(b">" + name.encode() + b"\n")
+        chunk = BASES[text.symbols[s:e]]
+        full = (chunk.size // line) * line
+        if full:
+            rows = np.empty((full // line, line + 1), dtype=np.uint8)
+            rows[:, :line] = chunk[:full].reshape(-1, line)
+            rows[:, line] = 10
+            f.write(rows.tobytes())
+        if chunk.size > full:
+            f.write(chunk[full:].tobytes() + b"\n")
+
+
+def write_fasta(path: str, text: Text, line: int = 60) -> None:
     with open(path, "wb") as f:
-        for (name, s), e in zip(text.records, starts[1:]):
-            f.write(b">" + name.encode() + b"\n")
-            chunk = BASES[text.symbols[s:e]]
-            for o in range(0, chunk.size, line):
-                f.write(chunk[o:o + line].tobytes() + b"\n")
+        write_fasta_file(f, text, line)
 
 
 # ------------------------------------------------------------------ reads

@@ -119,3 +119,17 @@ def test_file_list(dump, tmp_path):
     got = sorted(os.path.basename(x) for x in dump("files", tmp_path / "d"))
     assert got == ["a.fa", "c.fa"]
     assert dump("files", tmp_path / "d" / "b.txt") == []
+
+
+def test_text_loader_reference_quirk_fixture(dump, tmp_path):
+    """host getText against the reference's own getText on the awkward files of tests/golden/text_quirks.npz"""
+    from util import text_quirk_cases
+    for name, data, symbols, starts, names in text_quirk_cases():
+        f = tmp_path / (name + ".fa")
+        f.write_bytes(data)
+        d = dump("text", f)
+        assert d["n"] == symbols.size, name
+        assert [r[1] for r in d["ranges"]] == [int(x) for x in starts], name
+        assert [r[0].encode("latin-1") for r in d["ranges"][:-1]] == names, name
+        sym = synth.unpack_text(np.asarray(d["words"], dtype=np.uint64), symbols.size, np.asarray(d["nmask"], dtype=np.uint64))
+        assert np.array_equal(sym, symbols), name

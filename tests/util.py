@@ -72,3 +72,15 @@ def unify_order_ok(h) -> bool:
         if a > b:
             return False
     return True
+
+
+def text_quirk_cases():
+    """[(name, fasta bytes, symbols, starts incl. terminal, [names])] of tests/golden/text_quirks.npz (the reference's own getText)."""
+    z = np.load(os.path.join(GOLDEN, "text_quirks.npz"))
+    out = []
+    for name in bytes(z["cases"]).decode().split("\n"):
+        nrec = int(z[name + "_nrecords"])
+        names = bytes(z[name + "_names"]).split(b"\n") if nrec else []
+        assert len(names) == nrec
+        out.append((name, bytes(z[name + "_fasta"]), z[name + "_symbols"], z[name + "_starts"], names))
+    return out
