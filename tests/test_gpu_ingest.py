@@ -18,9 +18,10 @@ pytestmark = pytest.mark.gpu
 def _check(m, data, symbols, starts, names):
     n, ranges = m.set_text_fasta(data)
     assert n == symbols.size
-    assert [r[1] for r in ranges] == [int(x) for x in starts]
-    assert [r[0] for r in ranges[:-1]] == list(names)
+    assert m.handle._text_nrec == len(names)
     if n and len(names):
+        assert [r[1] for r in ranges] == [int(x) for x in starts]
+        assert [r[0] for r in ranges[:-1]] == list(names)
         words, nmask = m.handle.get_text_packed(n)
         ew, em = synth.pack_text(symbols)
         assert np.array_equal(words, ew)
