@@ -15,7 +15,11 @@
 //                 wildcard bits in shared memory and write whole words (the two words a tile shares with its
 //                 neighbours are merged with atomicOr into the zeroed arrays); record starts and the file offsets
 //                 of the header ends go to the record arrays
-// Inside a thread (16 bytes = one 128-bit load) the state is a 17-bit Kogge-Stone carry chain.
+// A thread owns 64 consecutive bytes (four 128-bit loads) as two pieces of 32; a byte is classified by ONE 8-byte
+// shared-memory lookup whose words are accumulated with one multiply-add each (four flag masks in the byte lanes of one
+// register, the 2-bit codes most significant first in another); inside a piece the state is a 32-bit carry chain
+// (skipped when the piece holds no '>').  The first version (one table lookup and five shift/mask/or steps per byte,
+// 16 bytes per thread, ranking every kept byte one by one) was instruction bound at 280 GB/s of file bytes.
 // Algorithmic bytes per file byte: 1 read + (2 + 1)/8 written per kept base; the input is read twice (summary, pack).
 #pragma once
 #include "common.cuh"
@@ -25,16 +29,18 @@ namespace realgpu
 {
 
 static const uint32_t FA_THREADS = 256;
-static const uint32_t FA_TILE = FA_THREADS * 16;               // bytes of one tile
+static const uint32_t FA_PIECE = 32;                           // bytes of one piece (one bit per byte in a 32-bit mask)
+static const uint32_t FA_PER_THREAD = 2 * FA_PIECE;
+static const uint32_t FA_TILE = FA_THREADS * FA_PER_THREAD;    // bytes of one tile
 
-// what a piece of the file does to the scan state; counts are split at its first '>' or '\n' (the first "setter"):
-// in front of it the entry state decides, behind it the piece decides by itself
+// what a stretch of the file does to the scan state; counts are split at its first '>' or '\n' (the first "setter"):
+// in front of it the entry state decides, behind it the stretch decides by itself
 template<typename C>
 struct FaSum
 {
         uint32_t f;             // 0 = no setter (state passes through), 1 = leaves "no header", 2 = leaves "header"
-        uint32_t pre_hdr;       // 1 = the first setter is a '\n': it files a record if the piece is entered inside a header
-        C pre_cnt;              // A C G T N in front of the first setter: kept if the piece is entered outside a header
+        uint32_t pre_hdr;       // 1 = the first setter is a '\n': it files a record if the stretch is entered inside a header
+        C pre_cnt;              // A C G T N in front of the first setter: kept if the stretch is entered outside a header
         C post_cnt;             // bases kept behind the first setter
         C post_hdr;             // records filed behind the first setter
 };
@@ -60,42 +66,73 @@ __device__ __forceinline__ A fa_combine(A const & a, B const & b)         // a, 
         return r;
 }
 
-// byte classes: bits 0-1 = 2-bit code, bit 2 = kept outside headers, bit 3 = N, bit 4 = '>', bit 5 = '\n'
-__host__ __device__ __forceinline__ uint32_t fa_class(uint32_t c)
+template<typename S> __device__ __forceinline__ S fa_shfl_down(S const & a, int o)
 {
-        return c == 'A' ? 4u : c == 'C' ? 5u : c == 'G' ? 6u : c == 'T' ? 7u : c == 'N' ? 12u : c == '>' ? 16u : c == '\n' ? 32u : 0u;
+        S r;
+        r.f = __shfl_down_sync(0xffffffffu, a.f, o); r.pre_hdr = __shfl_down_sync(0xffffffffu, a.pre_hdr, o);
+        r.pre_cnt = __shfl_down_sync(0xffffffffu, a.pre_cnt, o); r.post_cnt = __shfl_down_sync(0xffffffffu, a.post_cnt, o);
+        r.post_hdr = __shfl_down_sync(0xffffffffu, a.post_hdr, o);
+        return r;
+}
+template<typename S> __device__ __forceinline__ S fa_shfl_up(S const & a, int o)
+{
+        S r;
+        r.f = __shfl_up_sync(0xffffffffu, a.f, o); r.pre_hdr = __shfl_up_sync(0xffffffffu, a.pre_hdr, o);
+        r.pre_cnt = __shfl_up_sync(0xffffffffu, a.pre_cnt, o); r.post_cnt = __shfl_up_sync(0xffffffffu, a.post_cnt, o);
+        r.post_hdr = __shfl_up_sync(0xffffffffu, a.post_hdr, o);
+        return r;
 }
 
-struct FaMasks { uint32_t base, nb, gt, nl, codes; };           // one bit (codes: two) per byte of the 16-byte piece, byte i = bit i
-
-__device__ __forceinline__ FaMasks fa_classify(uint4 const v, const uint8_t * lut)
+// table entry of a byte: x = flags in the low bit of the four byte lanes (kept outside headers, N, '>', '\n'), y = 2-bit code
+__device__ __forceinline__ uint2 fa_entry(uint32_t c)
 {
-        uint32_t const w[4] = { v.x, v.y, v.z, v.w };
-        FaMasks M; M.base = M.nb = M.gt = M.nl = M.codes = 0;
+        uint32_t const base = (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N') ? 1u : 0u;
+        uint32_t const code = c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u;
+        return make_uint2(base | ((c == 'N' ? 1u : 0u) << 8) | ((c == '>' ? 1u : 0u) << 16) | ((c == '\n' ? 1u : 0u) << 24), code);
+}
+
+// one bit per byte of a 32-byte piece (byte i = bit i); codes of the bytes 0..15 / 16..31, byte 0 (16) in the two top bits
+struct FaMasks { uint32_t base, nb, gt, nl, c0, c1; };
+
+__device__ __forceinline__ FaMasks fa_classify(uint4 const v0, uint4 const v1, const uint2 * lut)
+{
+        uint32_t const w[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+        uint32_t acc[4] = { 0, 0, 0, 0 }, c[2] = { 0, 0 };
         #pragma unroll
-        for ( int i = 0; i < 16; ++i )
+        for ( int i = 0; i < 32; ++i )
         {
-                uint32_t const t = lut[(w[i >> 2] >> (8 * (i & 3))) & 0xFF];
-                M.base |= ((t >> 2) & 1) << i;
-                M.nb |= ((t >> 3) & 1) << i;
-                M.gt |= ((t >> 4) & 1) << i;
-                M.nl |= ((t >> 5) & 1) << i;
-                M.codes |= (t & 3) << (2 * i);
+                uint2 const e = lut[(w[i >> 2] >> (8 * (i & 3))) & 0xFF];
+                acc[i >> 3] += e.x << (i & 7);
+                c[i >> 4] += e.y << (30 - 2 * (i & 15));
         }
+        FaMasks M;
+        M.base = __byte_perm(__byte_perm(acc[0], acc[1], 0x0040), __byte_perm(acc[2], acc[3], 0x0040), 0x5410);
+        M.nb   = __byte_perm(__byte_perm(acc[0], acc[1], 0x0051), __byte_perm(acc[2], acc[3], 0x0051), 0x5410);
+        M.gt   = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+        M.nl   = __byte_perm(__byte_perm(acc[0], acc[1], 0x0073), __byte_perm(acc[2], acc[3], 0x0073), 0x5410);
+        M.c0 = c[0]; M.c1 = c[1];
         return M;
 }
 
-// bit 0 = the state the piece is entered in, bit i+1 = the state behind byte i (1 = inside a header)
-__device__ __forceinline__ uint32_t fa_states(uint32_t gt, uint32_t nl, uint32_t in)
+// bit i = the state in front of byte i (1 = inside a header) of a piece entered in state `in`; *out = the state behind it
+__device__ __forceinline__ uint32_t fa_states(uint32_t gt, uint32_t nl, uint32_t in, uint32_t * out)
 {
-        uint32_t G = (gt << 1) | in;
-        uint32_t P = ~((gt | nl) << 1);
+        if ( gt == 0 )
+        {
+                // no '>': the entry state lasts up to and including the first '\n'
+                *out = nl ? 0u : in;
+                return in ? (((nl & (0u - nl)) << 1) - 1u) : 0u;
+        }
+        uint32_t const set = gt | nl;
+        uint32_t G = gt, P = ~set;
         G |= (G << 1) & P; P &= P << 1;
         G |= (G << 2) & P; P &= P << 2;
         G |= (G << 4) & P; P &= P << 4;
         G |= (G << 8) & P; P &= P << 8;
         G |= (G << 16) & P;
-        return G;
+        uint32_t const after = G | (in ? ((set & (0u - set)) - 1u) : 0u);       // bit i = state behind byte i
+        *out = after >> 31;
+        return (after << 1) | in;
 }
 
 __device__ __forceinline__ FaSum32 fa_piece_summary(FaMasks const & M)
@@ -108,22 +145,14 @@ __device__ __forceinline__ FaSum32 fa_piece_summary(FaMasks const & M)
                 return s;
         }
         uint32_t const first = set & (0u - set), front = first - 1, behind = ~(front | first);
-        uint32_t const st = fa_states(M.gt, M.nl, 0);
+        uint32_t o;
+        uint32_t const st = fa_states(M.gt, M.nl, 0, &o);
         s.f = ((M.gt >> (31 - __clz(set))) & 1) ? 2 : 1;
         s.pre_hdr = (M.nl & first) ? 1 : 0;
         s.pre_cnt = __popc(M.base & front);
         s.post_cnt = __popc(M.base & ~st & behind);
         s.post_hdr = __popc(M.nl & st & behind);
         return s;
-}
-
-__device__ __forceinline__ FaSum32 fa_shfl_down(FaSum32 const & a, int o)
-{
-        FaSum32 r;
-        r.f = __shfl_down_sync(0xffffffffu, a.f, o); r.pre_hdr = __shfl_down_sync(0xffffffffu, a.pre_hdr, o);
-        r.pre_cnt = __shfl_down_sync(0xffffffffu, a.pre_cnt, o); r.post_cnt = __shfl_down_sync(0xffffffffu, a.post_cnt, o);
-        r.post_hdr = __shfl_down_sync(0xffffffffu, a.post_hdr, o);
-        return r;
 }
 
 // 16 bytes at file offset off (a multiple of 16; the buffer is 16-byte aligned); bytes behind the end of the file read as 0,
@@ -140,12 +169,16 @@ __device__ __forceinline__ uint4 fa_load(const uint8_t * bytes, uint64_t nbytes,
 
 __global__ void __launch_bounds__(FA_THREADS) k_fa_summary(const uint8_t * __restrict__ bytes, uint64_t nbytes, FaSum32 * __restrict__ sums)
 {
-        __shared__ uint8_t lut[256];
+        __shared__ uint2 lut[256];
         __shared__ FaSum32 wsum[FA_THREADS / 32];
-        lut[threadIdx.x] = (uint8_t)fa_class(threadIdx.x);
-        uint4 const v = fa_load(bytes, nbytes, (uint64_t)blockIdx.x * FA_TILE + threadIdx.x * 16);
+        lut[threadIdx.x] = fa_entry(threadIdx.x);
+        uint64_t const byte0 = (uint64_t)blockIdx.x * FA_TILE + threadIdx.x * FA_PER_THREAD;
+        uint4 v[4];
+        #pragma unroll
+        for ( int j = 0; j < 4; ++j ) v[j] = fa_load(bytes, nbytes, byte0 + 16 * j);
         __syncthreads();
-        FaSum32 s = fa_piece_summary(fa_classify(v, lut));
+        FaSum32 s = fa_piece_summary(fa_classify(v[0], v[1], lut));
+        s = fa_combine(s, fa_piece_summary(fa_classify(v[2], v[3], lut)));
         #pragma unroll
         for ( int o = 1; o < 32; o <<= 1 )
         {
@@ -163,77 +196,112 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_summary(const uint8_t * __res
         }
 }
 
-// one CTA; tile_base[t] = (index of the tile's first kept base << 1) | entry state, tile_rec[t] = index of its first record;
-// totals[0] = kept bases, totals[1] = records of the whole file
+// one CTA, FA_SCAN_THREADS tiles at a time; tile_base[t] = (index of the tile's first kept base << 1) | entry state,
+// tile_rec[t] = index of its first record; totals[0] = kept bases, totals[1] = records of the whole file
 static const uint32_t FA_SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(FA_SCAN_THREADS) k_fa_scan(const FaSum32 * __restrict__ sums, uint64_t ntiles, uint64_t * __restrict__ tile_base,
                                                              uint64_t * __restrict__ tile_rec, uint64_t * __restrict__ totals)
 {
-        __shared__ FaSum64 wtot[FA_SCAN_THREADS / 32];
-        uint64_t const per = (ntiles + FA_SCAN_THREADS - 1) / FA_SCAN_THREADS;
-        uint64_t const t0 = min(ntiles, threadIdx.x * per), t1 = min(ntiles, t0 + per);
-        FaSum64 acc; acc.f = 0; acc.pre_hdr = 0; acc.pre_cnt = 0; acc.post_cnt = 0; acc.post_hdr = 0;
-        FaSum64 const ident = acc;
-        for ( uint64_t t = t0; t < t1; ++t ) acc = fa_combine(acc, sums[t]);
-        // inclusive scan over the threads of a warp, then over the warps
+        __shared__ FaSum64 wtot[FA_SCAN_THREADS / 32];          // per warp: its total, then everything in front of it in the chunk
+        __shared__ FaSum64 carry_s;
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        FaSum64 inc = acc;
-        #pragma unroll
-        for ( int o = 1; o < 32; o <<= 1 )
+        FaSum64 ident; ident.f = 0; ident.pre_hdr = 0; ident.pre_cnt = 0; ident.post_cnt = 0; ident.post_hdr = 0;
+        FaSum64 carry = ident;                                  // everything in front of the chunk
+        for ( uint64_t c0 = 0; c0 < ntiles; c0 += FA_SCAN_THREADS )
         {
-                FaSum64 p;
-                p.f = __shfl_up_sync(0xffffffffu, inc.f, o); p.pre_hdr = __shfl_up_sync(0xffffffffu, inc.pre_hdr, o);
-                p.pre_cnt = __shfl_up_sync(0xffffffffu, inc.pre_cnt, o); p.post_cnt = __shfl_up_sync(0xffffffffu, inc.post_cnt, o);
-                p.post_hdr = __shfl_up_sync(0xffffffffu, inc.post_hdr, o);
-                if ( lane >= o ) inc = fa_combine(p, inc);
+                uint64_t const t = c0 + threadIdx.x;
+                FaSum64 own = ident;
+                if ( t < ntiles ) own = fa_combine(ident, sums[t]);
+                FaSum64 inc = own;
+                #pragma unroll
+                for ( int o = 1; o < 32; o <<= 1 )
+                {
+                        FaSum64 const p = fa_shfl_up(inc, o);
+                        if ( lane >= o ) inc = fa_combine(p, inc);
+                }
+                FaSum64 exc = fa_shfl_up(inc, 1);               // everything in front of this thread inside its warp
+                if ( lane == 0 ) exc = ident;
+                if ( lane == 31 ) wtot[wid] = inc;
+                __syncthreads();
+                if ( wid == 0 )
+                {
+                        FaSum64 const mine = wtot[lane];
+                        FaSum64 winc = mine;
+                        #pragma unroll
+                        for ( int o = 1; o < 32; o <<= 1 )
+                        {
+                                FaSum64 const p = fa_shfl_up(winc, o);
+                                if ( lane >= o ) winc = fa_combine(p, winc);
+                        }
+                        FaSum64 wexc = fa_shfl_up(winc, 1);
+                        if ( lane == 0 ) wexc = ident;
+                        wtot[lane] = wexc;
+                        if ( lane == 31 ) carry_s = fa_combine(carry, winc);
+                }
+                __syncthreads();
+                FaSum64 const pre = fa_combine(carry, fa_combine(wtot[wid], exc));
+                if ( t < ntiles )
+                {
+                        // the file is entered outside a header: the "pre" parts count as kept bases and file no record
+                        tile_base[t] = ((pre.pre_cnt + pre.post_cnt) << 1) | (pre.f == 2 ? 1u : 0u);
+                        tile_rec[t] = pre.post_hdr;
+                }
+                carry = carry_s;
+                __syncthreads();
         }
-        if ( lane == 31 ) wtot[wid] = inc;
-        FaSum64 exc;                                            // everything in front of this thread inside its warp
-        exc.f = __shfl_up_sync(0xffffffffu, inc.f, 1); exc.pre_hdr = __shfl_up_sync(0xffffffffu, inc.pre_hdr, 1);
-        exc.pre_cnt = __shfl_up_sync(0xffffffffu, inc.pre_cnt, 1); exc.post_cnt = __shfl_up_sync(0xffffffffu, inc.post_cnt, 1);
-        exc.post_hdr = __shfl_up_sync(0xffffffffu, inc.post_hdr, 1);
-        if ( lane == 0 ) exc = ident;
-        __syncthreads();
-        FaSum64 pre = ident;
-        for ( int w = 0; w < wid; ++w ) pre = fa_combine(pre, wtot[w]);
-        pre = fa_combine(pre, exc);
-        // the file is entered outside a header: the "pre" parts count as kept bases and file no record
-        for ( uint64_t t = t0; t < t1; ++t )
+        if ( threadIdx.x == 0 )
         {
-                tile_base[t] = ((pre.pre_cnt + pre.post_cnt) << 1) | (pre.f == 2 ? 1u : 0u);
-                tile_rec[t] = pre.post_hdr;
-                pre = fa_combine(pre, sums[t]);
+                totals[0] = carry.pre_cnt + carry.post_cnt;
+                totals[1] = carry.post_hdr;
         }
-        if ( t1 == ntiles && t0 < t1 )
-        {
-                totals[0] = pre.pre_cnt + pre.post_cnt;
-                totals[1] = pre.post_hdr;
-        }
-        if ( ntiles == 0 && threadIdx.x == 0 ) { totals[0] = 0; totals[1] = 0; }
 }
+
+// removes the 2-bit fields of the bytes whose bit is set in drop (16 bytes, byte j = bits 31-2j..30-2j); the rest closes up towards the top
+__device__ __forceinline__ uint32_t fa_squeeze(uint32_t c, uint32_t drop)
+{
+        while ( drop )
+        {
+                int const p = 31 - __clz(drop);                 // highest byte first: the fields in front of it stay where they are
+                drop ^= 1u << p;
+                uint32_t const below = (1u << (30 - 2 * p)) - 1u;
+                c = (c & ~(below * 4u + 3u)) | ((c & below) << 2);
+        }
+        return c;
+}
+
+static const uint32_t FA_CU = FA_TILE / 16 + 4, FA_NU = FA_TILE / 32 + 4;
 
 // text / nmask: word 0 of the (zeroed) arrays; rec_start / rec_nl: one entry per record (rec_nl = file offset of the '\n' that filed it)
 __global__ void __launch_bounds__(FA_THREADS) k_fa_pack(const uint8_t * __restrict__ bytes, uint64_t nbytes, const uint64_t * __restrict__ tile_base,
                                                         const uint64_t * __restrict__ tile_rec, unsigned long long * __restrict__ text,
                                                         unsigned long long * __restrict__ nmask, uint64_t * __restrict__ rec_start, uint64_t * __restrict__ rec_nl)
 {
-        __shared__ uint8_t lut[256];
+        __shared__ uint2 lut[256];
         __shared__ uint32_t wf[FA_THREADS / 32];
-        __shared__ uint32_t cu[FA_TILE / 16 + 4];               // 2-bit codes, 16 bases per unit, most significant first; unit pairs = text words
-        __shared__ uint32_t nu[FA_TILE / 32 + 4];               // wildcard bits, 32 bases per unit; unit pairs = mask words
+        __shared__ uint32_t cu[FA_CU];                          // 2-bit codes, 16 bases per unit, most significant first; unit pairs = text words
+        __shared__ uint32_t nu[FA_NU];                          // wildcard bits, 32 bases per unit; unit pairs = mask words
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        lut[threadIdx.x] = (uint8_t)fa_class(threadIdx.x);
-        for ( uint32_t i = threadIdx.x; i < FA_TILE / 16 + 4; i += FA_THREADS ) cu[i] = 0;
-        for ( uint32_t i = threadIdx.x; i < FA_TILE / 32 + 4; i += FA_THREADS ) nu[i] = 0;
-        uint64_t const byte0 = (uint64_t)blockIdx.x * FA_TILE + threadIdx.x * 16;
-        uint4 const v = fa_load(bytes, nbytes, byte0);
+        lut[threadIdx.x] = fa_entry(threadIdx.x);
+        for ( uint32_t i = threadIdx.x; i < FA_CU; i += FA_THREADS ) cu[i] = 0;
+        for ( uint32_t i = threadIdx.x; i < FA_NU; i += FA_THREADS ) nu[i] = 0;
+        uint64_t const byte0 = (uint64_t)blockIdx.x * FA_TILE + threadIdx.x * FA_PER_THREAD;
+        uint4 v[4];
+        #pragma unroll
+        for ( int j = 0; j < 4; ++j ) v[j] = fa_load(bytes, nbytes, byte0 + 16 * j);
         uint64_t const tb = tile_base[blockIdx.x];
         uint64_t const B0 = tb >> 1;
         __syncthreads();
-        FaMasks const M = fa_classify(v, lut);
+        FaMasks M[2];
+        M[0] = fa_classify(v[0], v[1], lut);
+        M[1] = fa_classify(v[2], v[3], lut);
         // entry state of this thread: the last setter in front of it -- in its warp, else in an earlier warp, else the tile's
-        uint32_t const set = M.gt | M.nl;
-        uint32_t const mine = set ? (((M.gt >> (31 - __clz(set))) & 1) ? 2u : 1u) : 0u;
+        uint32_t mine = 0;
+        #pragma unroll
+        for ( int s = 0; s < 2; ++s )
+        {
+                uint32_t const set = M[s].gt | M[s].nl;
+                if ( set ) mine = ((M[s].gt >> (31 - __clz(set))) & 1) ? 2u : 1u;
+        }
         uint32_t const m_set = __ballot_sync(0xffffffffu, mine != 0), m_one = __ballot_sync(0xffffffffu, mine == 2);
         if ( lane == 0 ) wf[wid] = m_set ? (((m_one >> (31 - __clz(m_set))) & 1) ? 2u : 1u) : 0u;
         __syncthreads();
@@ -241,45 +309,50 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_pack(const uint8_t * __restri
         for ( int w = 0; w < wid; ++w ) if ( wf[w] ) in = wf[w] == 2;
         uint32_t const lower = m_set & ((1u << lane) - 1);
         if ( lower ) in = (m_one >> (31 - __clz(lower))) & 1;
-        uint32_t const st = fa_states(M.gt, M.nl, in);           // bit i = state in front of byte i
-        uint32_t const kept = M.base & ~st & 0xFFFFu, ends = M.nl & st & 0xFFFFu;
-        uint32_t const k = __popc(kept), nh = __popc(ends);
+        uint32_t kept[2], ends[2];
+        #pragma unroll
+        for ( int s = 0; s < 2; ++s )
+        {
+                uint32_t out;
+                uint32_t const st = fa_states(M[s].gt, M[s].nl, in, &out);
+                kept[s] = M[s].base & ~st; ends[s] = M[s].nl & st;
+                in = out;
+        }
+        uint32_t const k = __popc(kept[0]) + __popc(kept[1]), nh = __popc(ends[0]) + __popc(ends[1]);
         uint32_t tot;
         uint32_t const ex = block_excl_scan((nh << 16) | k, &tot);
         uint32_t const K = tot & 0xFFFFu;
-        uint64_t const g = B0 + (ex & 0xFFFFu);                  // index of this thread's first kept base
-        if ( k )
+        uint64_t g = B0 + (ex & 0xFFFFu);                        // index of this thread's next kept base
+        uint64_t r = nh ? tile_rec[blockIdx.x] + (ex >> 16) : 0;
+        #pragma unroll
+        for ( int s = 0; s < 2; ++s )
         {
-                // compact the codes and the wildcard bits of the kept bytes, first byte most significant
-                uint32_t cc = 0, nn = 0;
-                for ( uint32_t m = kept; m; m &= m - 1 )
+                if ( ends[s] )
+                        for ( uint32_t m = ends[s]; m; m &= m - 1, ++r )
+                        {
+                                int const i = __ffs(m) - 1;
+                                rec_start[r] = g + __popc(kept[s] & ((1u << i) - 1));
+                                rec_nl[r] = byte0 + 32 * s + i;
+                        }
+                uint32_t const nk = M[s].nb & kept[s];
+                if ( nk )
+                        for ( uint32_t m = nk; m; m &= m - 1 )
+                        {
+                                uint64_t const x = g + __popc(kept[s] & ((1u << (__ffs(m) - 1)) - 1));
+                                atomicOr(&nu[(uint32_t)((x >> 5) - 2 * (B0 >> 6))], 0x80000000u >> (x & 31));
+                        }
+                #pragma unroll
+                for ( int hh = 0; hh < 2; ++hh )
                 {
-                        int const i = __ffs(m) - 1;
-                        cc = (cc << 2) | ((M.codes >> (2 * i)) & 3);
-                        nn = (nn << 1) | ((M.nb >> i) & 1);
-                }
-                {
-                        uint32_t const val = cc << (32 - 2 * k), sh = 2 * (uint32_t)(g & 15);
+                        uint32_t const k16 = (kept[s] >> (16 * hh)) & 0xFFFFu;
+                        if ( ! k16 ) continue;
+                        uint32_t const kk = __popc(k16);
+                        uint32_t const val = fa_squeeze(hh ? M[s].c1 : M[s].c0, k16 ^ 0xFFFFu);
+                        uint32_t const sh = 2 * (uint32_t)(g & 15);
                         uint32_t const u = (uint32_t)((g >> 4) - 2 * (B0 >> 5));
                         atomicOr(&cu[u], val >> sh);
-                        if ( sh + 2 * k > 32 ) atomicOr(&cu[u + 1], val << (32 - sh));
-                }
-                if ( nn )
-                {
-                        uint32_t const val = nn << (32 - k), sh = (uint32_t)(g & 31);
-                        uint32_t const u = (uint32_t)((g >> 5) - 2 * (B0 >> 6));
-                        atomicOr(&nu[u], val >> sh);
-                        if ( sh + k > 32 ) atomicOr(&nu[u + 1], val << (32 - sh));
-                }
-        }
-        if ( nh )
-        {
-                uint64_t r = tile_rec[blockIdx.x] + (ex >> 16);
-                for ( uint32_t m = ends; m; m &= m - 1, ++r )
-                {
-                        int const i = __ffs(m) - 1;
-                        rec_start[r] = g + __popc(kept & ((1u << i) - 1));
-                        rec_nl[r] = byte0 + i;
+                        if ( sh + 2 * kk > 32 ) atomicOr(&cu[u + 1], val << (32 - sh));
+                        g += kk;
                 }
         }
         __syncthreads();

@@ -3,6 +3,7 @@
 #include "../../include/real_gpu.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -430,10 +431,8 @@ static bool findFirstMarker(Cursor & in, char marker)
         return c == marker;
 }
 
-int detectQualityOffset(std::string const & filename)
+static int detectQualityOffsetBuffer(std::vector<char> const & buf)
 {
-        std::vector<char> buf;
-        slurp(filename, buf);
         Cursor in(buf);
         bool found = findFirstMarker(in, '@');
         std::string id, pat, q;
@@ -446,25 +445,153 @@ int detectQualityOffset(std::string const & filename)
         return 0;
 }
 
-void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out)
+int detectQualityOffset(std::string const & filename)
 {
         std::vector<char> buf;
         slurp(filename, buf);
-        Cursor in(buf);
-        bool found = findFirstMarker(in, fastq ? '@' : '>');
+        return detectQualityOffsetBuffer(buf);
+}
+
+namespace
+{
+        static size_t const NO_MARKER = ~(size_t)0;
+
+        // Runs the reader's state machine from the marker at `start` (NO_MARKER = nothing to read) and appends the records
+        // whose marker lies in front of `limit`.  Returns the position of the marker the next record starts at, or
+        // NO_MARKER when the reader's loop is over (end of file, or a record it rejects: the reference stops there too).
+        size_t parseRange(std::vector<char> const & buf, size_t start, size_t limit, bool fastq, int qualityOffset, ReadSet & out)
+        {
+                if ( start == NO_MARKER )
+                        return NO_MARKER;
+                Cursor in(buf);
+                in.p = start + 1;
+                bool found = true;
+                size_t at = start;
+                std::string id, pat, q;
+                while ( at < limit )
+                {
+                        if ( ! nextPattern(in, fastq, qualityOffset, found, id, pat, fastq ? &q : 0) )
+                                return NO_MARKER;
+                        for ( size_t i = 0; i < pat.size(); ++i ) out.mapped.push_back(mapChar(pat[i]));
+                        if ( fastq )
+                                for ( size_t i = 0; i < pat.size(); ++i ) out.quality.push_back((uint8_t)q[i]);
+                        out.offsets.push_back(out.mapped.size());
+                        out.ids.push_back(id);
+                        if ( ! found )
+                                return NO_MARKER;
+                        at = in.p - 1;
+                }
+                return at;
+        }
+
+        // where a record probably starts at or behind `from`: a marker at the start of a line (FASTQ: with a '+' line two
+        // lines on).  Only a guess -- readPatternsBuffer checks it against the state machine's own position.
+        size_t guessRecordStart(std::vector<char> const & buf, size_t from, bool fastq)
+        {
+                char const marker = fastq ? '@' : '>';
+                for ( size_t p = from; p < buf.size(); ++p )
+                {
+                        if ( buf[p] != marker || (p && buf[p-1] != '\n') )
+                                continue;
+                        if ( ! fastq )
+                                return p;
+                        size_t a = p;
+                        while ( a < buf.size() && buf[a] != '\n' ) ++a;          // end of the id line
+                        size_t b = a + 1;
+                        while ( b < buf.size() && buf[b] != '\n' ) ++b;          // end of the sequence line
+                        if ( b + 1 < buf.size() && buf[b+1] == '+' )
+                                return p;
+                }
+                return NO_MARKER;
+        }
+
+        void appendReads(ReadSet & to, ReadSet const & from)
+        {
+                uint64_t const base = to.mapped.size();
+                to.mapped.insert(to.mapped.end(), from.mapped.begin(), from.mapped.end());
+                to.quality.insert(to.quality.end(), from.quality.begin(), from.quality.end());
+                for ( size_t i = 1; i < from.offsets.size(); ++i ) to.offsets.push_back(base + from.offsets[i]);
+                to.ids.insert(to.ids.end(), from.ids.begin(), from.ids.end());
+        }
+}
+
+// FastAReader / FastQReader::getNextPatternUnlocked over the whole file (FastAReader.hpp:107-138, FastQReader.hpp:130-180),
+// with a team of host threads: the file is cut into byte ranges, every thread guesses where the first record of its
+// range starts and runs the reader's state machine from there; a range is accepted only if its guess is exactly the
+// position the state machine reached at the end of the range in front of it -- otherwise that range is parsed again
+// from the right position.  The result is the serial reader's, whatever the file looks like.
+void readPatternsBuffer(std::vector<char> const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads)
+{
         out.mapped.clear(); out.quality.clear(); out.ids.clear();
         out.offsets.assign(1, 0);
-        out.mapped.reserve(buf.size());
-        if ( fastq ) out.quality.reserve(buf.size() / 2);
-        std::string id, pat, q;
-        while ( nextPattern(in, fastq, qualityOffset, found, id, pat, fastq ? &q : 0) )
+        size_t chunk = std::max<size_t>(size_t(1) << 22, (buf.size() + (threads ? threads : 1) - 1) / (threads ? threads : 1));
+        if ( char const * e = getenv("REAL_PARSE_CHUNK") ) chunk = std::max<size_t>(1, strtoull(e, 0, 10));       // tests
+        size_t const nchunks = std::max<size_t>(1, (buf.size() + chunk - 1) / chunk);
+        size_t first = NO_MARKER;
         {
-                for ( size_t i = 0; i < pat.size(); ++i ) out.mapped.push_back(mapChar(pat[i]));
-                if ( fastq )
-                        for ( size_t i = 0; i < pat.size(); ++i ) out.quality.push_back((uint8_t)q[i]);
-                out.offsets.push_back(out.mapped.size());
-                out.ids.push_back(id);
+                Cursor in(buf);
+                if ( findFirstMarker(in, fastq ? '@' : '>') ) first = in.p - 1;
         }
+        if ( nchunks == 1 || threads <= 1 )
+        {
+                out.mapped.reserve(buf.size());
+                if ( fastq ) out.quality.reserve(buf.size() / 2);
+                parseRange(buf, first, buf.size(), fastq, qualityOffset, out);
+                return;
+        }
+        std::vector<ReadSet> part(nchunks);
+        std::vector<size_t> guess(nchunks, NO_MARKER), reached(nchunks, NO_MARKER);
+        std::atomic<size_t> next(0);
+        auto work = [&]()
+        {
+                for ( size_t c = next++; c < nchunks; c = next++ )
+                {
+                        size_t const lo = c * chunk, hi = std::min(buf.size(), lo + chunk);
+                        guess[c] = c ? guessRecordStart(buf, lo, fastq) : first;
+                        part[c].offsets.assign(1, 0);
+                        if ( guess[c] != NO_MARKER && guess[c] < hi )
+                                reached[c] = parseRange(buf, guess[c], hi, fastq, qualityOffset, part[c]);
+                        else
+                                reached[c] = guess[c];          // no record starts in this range
+                }
+        };
+        {
+                std::vector<std::thread> team;
+                for ( unsigned int t = 0; t < std::min<size_t>(threads, nchunks); ++t ) team.push_back(std::thread(work));
+                for ( size_t t = 0; t < team.size(); ++t ) team[t].join();
+        }
+        size_t total = 0;
+        for ( size_t c = 0; c < nchunks; ++c ) total += part[c].mapped.size();
+        out.mapped.reserve(total);
+        if ( fastq ) out.quality.reserve(total);
+        size_t pos = first;                                     // the marker the serial reader's next record starts at
+        for ( size_t c = 0; c < nchunks && pos != NO_MARKER; ++c )
+        {
+                size_t const hi = std::min(buf.size(), c * chunk + chunk);
+                if ( pos >= hi )
+                        continue;                               // the record in front runs across this whole range
+                if ( guess[c] == pos )
+                {
+                        appendReads(out, part[c]);
+                        pos = reached[c];
+                }
+                else
+                {
+                        ReadSet again;
+                        again.offsets.assign(1, 0);
+                        pos = parseRange(buf, pos, hi, fastq, qualityOffset, again);
+                        appendReads(out, again);
+                }
+                ReadSet().mapped.swap(part[c].mapped); ReadSet().quality.swap(part[c].quality);
+        }
+}
+
+void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads)
+{
+        std::vector<char> buf;
+        slurp(filename, buf);
+        if ( ! threads ) threads = std::max(1u, std::thread::hardware_concurrency());
+        readPatternsBuffer(buf, fastq, qualityOffset, out, threads);
 }
 
 void reorderLikeRewrite(ReadSet & reads)
@@ -674,14 +801,16 @@ namespace
 
         void loadReads(RealOptions const & opts, ReadSet & reads)
         {
+                std::vector<char> buf;
+                slurp(opts.patternfilename, buf);
                 int qualityOffset = 0;
                 if ( opts.fastq )
                 {
-                        qualityOffset = opts.qualityOffset ? opts.qualityOffset : detectQualityOffset(opts.patternfilename);
+                        qualityOffset = opts.qualityOffset ? opts.qualityOffset : detectQualityOffsetBuffer(buf);
                         if ( ! qualityOffset )
                                 throw std::runtime_error("Unable to automatically detect FastQ quality format.");
                 }
-                readPatterns(opts.patternfilename, opts.fastq, qualityOffset, reads);
+                readPatternsBuffer(buf, opts.fastq, qualityOffset, reads, hostThreads(opts));
                 std::cerr << "Number of patterns is " << reads.size() << std::endl;
         }
 }

@@ -80,7 +80,8 @@ struct ReadSet
         uint64_t size() const { return offsets.size() - 1; }
 };
 int detectQualityOffset(std::string const & filename);                       // FastQReader::getOffset
-void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out);
+void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads = 0);   // 0 = all host threads
+void readPatternsBuffer(std::vector<char> const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads);
 // the order the rewritten pattern file hands the reads out in (-R 1): by length, wildcard-free reads first
 void reorderLikeRewrite(ReadSet & reads);
 

@@ -18,8 +18,9 @@ def dump():
     rbuild.build()
     rbuild.build_host()
 
-    def run(*args, ok=True):
-        p = subprocess.run([rbuild.HOST_DUMP] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    def run(*args, ok=True, env=None):
+        p = subprocess.run([rbuild.HOST_DUMP] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           env=dict(os.environ, **env) if env else None)
         if ok:
             assert p.returncode == 0, p.stderr
             return json.loads(p.stdout)
@@ -133,3 +134,46 @@ def test_text_loader_reference_quirk_fixture(dump, tmp_path):
         assert [r[0].encode("latin-1") for r in d["ranges"][:-1]] == names, name
         sym = synth.unpack_text(np.asarray(d["words"], dtype=np.uint64), symbols.size, np.asarray(d["nmask"], dtype=np.uint64))
         assert np.array_equal(sym, symbols), name
+
+
+def _awkward_read_files():
+    """(name, fastq, bytes): files on which a guessed record start is wrong somewhere"""
+    rng = np.random.RandomState(99)
+    acgt = np.frombuffer(b"ACGTN", dtype=np.uint8)
+
+    def seq(n):
+        return acgt[rng.randint(0, 5 if rng.rand() < 0.2 else 4, n)].tobytes()
+
+    fa = b"junk in front\n"
+    for i in range(120):
+        s = seq(rng.randint(1, 90))
+        cut = rng.randint(0, len(s) + 1)
+        fa += b">id%d >not a marker\n" % i + s[:cut] + (b"\n" if i % 3 else b"\r\n") + s[cut:] + (b"" if i % 7 == 0 else b"\n")
+    fa += b">last without newline"
+    fq = b""
+    for i in range(150):
+        n = rng.randint(1, 80)
+        s = seq(n)
+        q = bytes(rng.randint(33, 74, n).astype(np.uint8))
+        if i % 5 == 0:
+            q = b"@" + q[1:]                      # a quality line that starts like a record
+        if i % 11 == 0 and n > 3:
+            q = q[:1] + b"+" + q[2:]
+        if i % 4 == 0 and n > 10:                  # sequence and qualities over two lines
+            fq += b"@r%d\n" % i + s[:5] + b"\n" + s[5:] + b"\n+r%d\n" % i + q[:7] + b"\n" + q[7:] + b"\n"
+        else:
+            fq += b"@r%d\n" % i + s + b"\n+\n" + q + b"\n"
+    fq_trunc = fq + b"@cut\nACGTACGT\n+\nIII"      # the reader rejects the last record
+    return [("fa", 0, fa), ("fq", 1, fq), ("fq_trunc", 1, fq_trunc)]
+
+
+@pytest.mark.parametrize("chunk", [1, 37, 256, 1000])
+def test_parallel_read_parser_equals_serial(dump, tmp_path, chunk):
+    """the team parser (ranges of REAL_PARSE_CHUNK bytes, guessed record starts, checked hand-over) against the one-range parse"""
+    for name, fastq, data in _awkward_read_files():
+        f = tmp_path / (name + (".fq" if fastq else ".fa"))
+        f.write_bytes(data)
+        serial = dump("reads", f, fastq, 33 if fastq else 0, 0, env={"REAL_PARSE_CHUNK": str(1 << 40)})
+        team = dump("reads", f, fastq, 33 if fastq else 0, 0, env={"REAL_PARSE_CHUNK": str(chunk)})
+        assert len(serial["ids"]) > 100, name
+        assert team == serial, name

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_ingest.py tests/test_cli_gpu.py -x -q > gpurun_out/pytest_ingest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_ingest.log
 timeout 900 python tools/ingest_bench.py > gpurun_out/ingest_bench.log 2>&1; rc=$?; echo "ingest bench rc=$rc"; tail -c 1800 gpurun_out/ingest_bench.log
-timeout 600 python tools/cli_timing.py > gpurun_out/cli_timing.log 2>&1; echo "cli timing rc=$?"; tail -20 gpurun_out/cli_timing.log
+true
 if [ $rc -eq 0 ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_fa_" -s 3 -c 3 -o gpurun_out/prof_ingest_r1 -f python tools/ingest_bench.py --bases 1000000000 --reps 1 --no-cpu --no-e2e > gpurun_out/ncu_ingest.log 2>&1
   echo "ncu rc=$?"

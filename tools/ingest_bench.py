@@ -156,7 +156,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6538.0)) if isinstance(peaks, dict) else 6538.0
     alg = nbytes + n * 3 / 8.0                          # file bytes read once + 2-bit text and 1-bit mask written
-    design = 2 * nbytes + 2 * n * 3 / 8.0 + 36 * ((nbytes + 4095) // 4096) * 2   # two passes over the file, arrays cleared then written, tile summaries
+    design = 2 * nbytes + 2 * n * 3 / 8.0                # two passes over the file, arrays cleared then written (tile summaries: 36 B per 16 KB)
     out = {"kernel": "K0 k_fa_summary + k_fa_scan + k_fa_pack (+ clearing the arrays)", "file_bytes": nbytes, "bases": n, "records": nrec,
            "device_ms": dev_ms, "device_ms_all": [round(x, 3) for x in ms], "file_GBps": nbytes / dev_ms / 1e6, "gbp_per_s": n / dev_ms / 1e6,
            "roofline": {"bound": "hbm", "achieved": alg / dev_ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / dev_ms / 1e6 / peak,
