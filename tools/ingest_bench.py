@@ -62,11 +62,6 @@ def make_fasta_on_device(torch, n, nrecords, seed):
     return data, sym, np.asarray(starts, dtype=np.uint64)
 
 
-def word_checksum(torch, words):
-    w = words.view(torch.int64)
-    i = torch.arange(w.numel(), device=w.device, dtype=torch.int64)
-    return int(((w ^ (i * -7046029254386353131)).sum()).item()) & 0xFFFFFFFFFFFFFFFF
-
 
 def expected_words(torch, sym):
     """packed 2-bit words and N-mask words of the symbols, on the device, in pieces"""
