@@ -94,16 +94,23 @@ __device__ __forceinline__ uint2 fa_entry(uint32_t c)
 // one bit per byte of a 32-byte piece (byte i = bit i); codes of the bytes 0..15 / 16..31, byte 0 (16) in the two top bits
 struct FaMasks { uint32_t base, nb, gt, nl, c0, c1; };
 
-__device__ __forceinline__ FaMasks fa_classify(uint4 const v0, uint4 const v1, const uint2 * lut)
+__device__ __forceinline__ uint32_t fa_lut_flags(uint2 const & e) { return e.x; }
+__device__ __forceinline__ uint32_t fa_lut_flags(uint32_t const & e) { return e; }
+__device__ __forceinline__ uint32_t fa_lut_code(uint2 const & e) { return e.y; }
+__device__ __forceinline__ uint32_t fa_lut_code(uint32_t const &) { return 0; }
+
+// LUT = uint2 (flags + code) or uint32_t (flags only: the summary pass needs no codes)
+template<typename LUT>
+__device__ __forceinline__ FaMasks fa_classify(uint4 const v0, uint4 const v1, const LUT * lut)
 {
         uint32_t const w[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
         uint32_t acc[4] = { 0, 0, 0, 0 }, c[2] = { 0, 0 };
         #pragma unroll
         for ( int i = 0; i < 32; ++i )
         {
-                uint2 const e = lut[(w[i >> 2] >> (8 * (i & 3))) & 0xFF];
-                acc[i >> 3] += e.x << (i & 7);
-                c[i >> 4] += e.y << (30 - 2 * (i & 15));
+                LUT const e = lut[(w[i >> 2] >> (8 * (i & 3))) & 0xFF];
+                acc[i >> 3] += fa_lut_flags(e) << (i & 7);
+                c[i >> 4] += fa_lut_code(e) << (30 - 2 * (i & 15));
         }
         FaMasks M;
         M.base = __byte_perm(__byte_perm(acc[0], acc[1], 0x0040), __byte_perm(acc[2], acc[3], 0x0040), 0x5410);
@@ -169,9 +176,9 @@ __device__ __forceinline__ uint4 fa_load(const uint8_t * bytes, uint64_t nbytes,
 
 __global__ void __launch_bounds__(FA_THREADS) k_fa_summary(const uint8_t * __restrict__ bytes, uint64_t nbytes, FaSum32 * __restrict__ sums)
 {
-        __shared__ uint2 lut[256];
+        __shared__ uint32_t lut[256];
         __shared__ FaSum32 wsum[FA_THREADS / 32];
-        lut[threadIdx.x] = fa_entry(threadIdx.x);
+        lut[threadIdx.x] = fa_entry(threadIdx.x).x;
         uint64_t const byte0 = (uint64_t)blockIdx.x * FA_TILE + threadIdx.x * FA_PER_THREAD;
         uint4 v[4];
         #pragma unroll

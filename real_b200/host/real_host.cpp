@@ -653,20 +653,42 @@ namespace
                 void write(std::string const & s) { if ( fwrite(s.data(), 1, s.size(), f) != s.size() ) throw std::runtime_error("write failed"); }
         };
 
-        // one result line (matchAllImplementation.cpp:485-510, matchUniqueImplementation.cpp:267-288)
-        void formatLine(std::ostringstream & o, ReadSet const & reads, uint64_t r, bool inverted, bool scores, float score,
+        inline void appendUnsigned(std::string & o, uint64_t v)
+        {
+                char tmp[24]; int n = 0;
+                do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while ( v );
+                while ( n ) o.push_back(tmp[--n]);
+        }
+
+        // one result line (matchAllImplementation.cpp:485-510, matchUniqueImplementation.cpp:267-288); the reference prints
+        // through an ostream with default flags: integers in decimal, the float score like printf's %g
+        void formatLine(std::string & o, ReadSet const & reads, uint64_t r, bool inverted, bool scores, float score,
                         std::string const & recname, uint64_t pos_in_record, unsigned int k)
         {
                 static char const remap[5] = { 'A', 'C', 'G', 'T', 'N' };
                 uint64_t const b = reads.offsets[r], e = reads.offsets[r+1];
-                o << reads.ids[r] << "\t";
+                o += reads.ids[r]; o.push_back('\t');
+                size_t const at = o.size();
+                o.resize(at + (e - b));
                 if ( ! inverted )
-                        for ( uint64_t i = b; i < e; ++i ) o << remap[std::min<int>(reads.mapped[i], 4)];
+                        for ( uint64_t i = b; i < e; ++i ) o[at + (i - b)] = remap[std::min<int>(reads.mapped[i], 4)];
                 else
-                        for ( uint64_t i = e; i > b; --i ) { int const c = reads.mapped[i-1]; o << remap[c < 4 ? 3 - c : 4]; }
-                o << "\t";
-                if ( scores ) o << score;
-                o << "\t" << 1 << "\t" << "a" << "\t" << (e - b) << "\t" << (inverted ? "-" : "+") << "\t" << recname << "\t" << pos_in_record << "\t" << "\t" << k << "\n";
+                        for ( uint64_t i = e; i > b; --i ) { int const c = reads.mapped[i-1]; o[at + (e - i)] = remap[c < 4 ? 3 - c : 4]; }
+                o.push_back('\t');
+                if ( scores )
+                {
+                        char tmp[32];
+                        int const n = snprintf(tmp, sizeof(tmp), "%g", (double)score);
+                        o.append(tmp, n);
+                }
+                o += "\t1\ta\t";
+                appendUnsigned(o, e - b);
+                o += inverted ? "\t-\t" : "\t+\t";
+                o += recname; o.push_back('\t');
+                appendUnsigned(o, pos_in_record);
+                o += "\t\t";
+                appendUnsigned(o, k);
+                o.push_back('\n');
         }
 
         // Formats the items [0,n) with `threads` host threads and writes the pieces in item order, wave by wave (the
@@ -691,10 +713,11 @@ namespace
                                 uint64_t const a = w0 + t * per, b = std::min<uint64_t>(w1, a + per);
                                 auto work = [&piece, &lines, &fmt, t, a, b]()
                                 {
-                                        std::ostringstream o;
+                                        std::string o;
+                                        o.reserve((b - a) * 192);
                                         uint64_t c = 0;
                                         for ( uint64_t i = a; i < b; ++i ) c += fmt(o, i);
-                                        piece[t] = o.str();
+                                        piece[t].swap(o);
                                         lines[t] = c;
                                 };
                                 if ( used == 1 ) work(); else team.push_back(std::thread(work));
@@ -840,7 +863,7 @@ int doMatchingAll(RealOptions const & opts)
                 G.check(real_gpu_match_all(G.h, &hits, &nhits), "match_all");
                 PT.lap("text + match_all");
                 bool const scores = opts.scores;
-                formatParallel(nhits, hostThreads(opts), out, [&reads, &T, hits, scores](std::ostringstream & o, uint64_t i) -> uint64_t
+                formatParallel(nhits, hostThreads(opts), out, [&reads, &T, hits, scores](std::string & o, uint64_t i) -> uint64_t
                 {
                         real_gpu_hit const & H = hits[i];
                         formatLine(o, reads, H.patid, H.inverted != 0, scores, H.score, T.ranges[H.frag].first, H.pos - T.ranges[H.frag].second + 1, H.k);
@@ -929,7 +952,7 @@ int doMatchingUnique(RealOptions const & opts)
         Output out(opts.outputfilename);
         bool const scores = opts.scores;
         uint64_t const unique = formatParallel(reads.size(), hostThreads(opts), out,
-                [&reads, &info, &score, &rangeset, scores](std::ostringstream & o, uint64_t r) -> uint64_t
+                [&reads, &info, &score, &rangeset, scores](std::string & o, uint64_t r) -> uint64_t
         {
                 uint64_t const d = info[r];
                 unsigned int const state = (unsigned int)(d >> 61);
