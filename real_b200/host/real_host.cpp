@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 #include <stdexcept>
 #include <thread>
@@ -505,13 +506,13 @@ namespace
                 return NO_MARKER;
         }
 
-        void appendReads(ReadSet & to, ReadSet const & from)
+        void appendReads(ReadSet & to, ReadSet & from)          // from's ids are moved out
         {
                 uint64_t const base = to.mapped.size();
                 to.mapped.insert(to.mapped.end(), from.mapped.begin(), from.mapped.end());
                 to.quality.insert(to.quality.end(), from.quality.begin(), from.quality.end());
                 for ( size_t i = 1; i < from.offsets.size(); ++i ) to.offsets.push_back(base + from.offsets[i]);
-                to.ids.insert(to.ids.end(), from.ids.begin(), from.ids.end());
+                to.ids.insert(to.ids.end(), std::make_move_iterator(from.ids.begin()), std::make_move_iterator(from.ids.end()));
         }
 }
 
@@ -767,6 +768,19 @@ namespace
                         throw std::runtime_error("real_gpu_create failed (no CUDA device or unsupported option); there is no CPU fallback");
         }
 
+        // real_gpu_create on a thread of its own (context creation and module load take a few hundred milliseconds);
+        // wait() joins it and rethrows its error.  The destructor joins too, so G outlives the thread on every path.
+        struct HandleStarter
+        {
+                std::thread th; std::exception_ptr err;
+                HandleStarter(Gpu & G, RealOptions const & opts, std::vector<double> & ll)
+                {
+                        th = std::thread([this, &G, &opts, &ll]() { try { createHandle(G, opts, ll); } catch ( ... ) { err = std::current_exception(); } });
+                }
+                void wait() { if ( th.joinable() ) th.join(); if ( err ) { std::exception_ptr e = err; err = nullptr; std::rethrow_exception(e); } }
+                ~HandleStarter() { if ( th.joinable() ) th.join(); }
+        };
+
         // getText (getText.hpp:31-58) for the device: the bytes of the file go to real_gpu_set_text_fasta, which parses and
         // packs them there and sets the text; the record table comes back for the output lines.  T.words / T.nmask stay empty.
         // REAL_TEXT_LOADER=host selects the host parser + real_gpu_set_text instead (timing comparisons, tests).
@@ -841,13 +855,14 @@ namespace
 int doMatchingAll(RealOptions const & opts)
 {
         PhaseTimer PT;
+        Gpu G; std::vector<double> ll;
+        HandleStarter starter(G, opts, ll);  // the CUDA context comes up while the pattern file is read
         ReadSet reads;
         loadReads(opts, reads);
         PT.lap("read patterns");            // (the stock -u 0 path parses FASTQ files with the FASTA reader, real.cpp:325-328; here FASTQ is honoured)
         std::vector<std::string> filenames;
         getFileList(opts.textfilename, filenames, ".fa");
-        Gpu G; std::vector<double> ll;
-        createHandle(G, opts, ll);
+        starter.wait();
         G.check(real_gpu_set_reads(G.h, reads.mapped.empty() ? 0 : &reads.mapped[0], reads.quality.empty() ? 0 : &reads.quality[0], &reads.offsets[0], reads.size()), "set_reads");
         PT.lap("create + set_reads");
         Output out(opts.outputfilename);
@@ -905,6 +920,8 @@ static uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, u
 int doMatchingUnique(RealOptions const & opts)
 {
         PhaseTimer PT;
+        Gpu G; std::vector<double> ll;
+        HandleStarter starter(G, opts, ll);  // the CUDA context comes up while the pattern file is read
         ReadSet reads;
         loadReads(opts, reads);
         PT.lap("read patterns");
@@ -912,8 +929,7 @@ int doMatchingUnique(RealOptions const & opts)
                 reorderLikeRewrite(reads);
         std::vector<std::string> filenames;
         getFileList(opts.textfilename, filenames, ".fa");
-        Gpu G; std::vector<double> ll;
-        createHandle(G, opts, ll);
+        starter.wait();
         G.check(real_gpu_set_reads(G.h, reads.mapped.empty() ? 0 : &reads.mapped[0], reads.quality.empty() ? 0 : &reads.quality[0], &reads.offsets[0], reads.size()), "set_reads");
         std::vector< std::vector< std::pair<std::string, uint64_t> > > rangeset(filenames.size());       // RangeSet
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
