@@ -19,6 +19,8 @@
 #include <dirent.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 
 namespace realhost
 {
@@ -260,22 +262,45 @@ void buildScoringTable(double similarity, double gc, double trans, double err, d
 // text (countReads.cpp:28-125, AutoTextArray.hpp:27-61)
 // ---------------------------------------------------------------------------------------------
 
-static void slurp(std::string const & filename, std::vector<char> & buf)
+// the bytes of a file: mapped read-only (no copy, the page cache is the buffer), or read into memory where mapping fails
+FileBytes::~FileBytes() { close(); }
+
+void FileBytes::close()
 {
-        FILE * f = fopen(filename.c_str(), "rb");
-        if ( ! f )
-                throw std::runtime_error("Failed to open file " + filename);
-        fseek(f, 0, SEEK_END);
-        long const sz = ftell(f);
-        fseek(f, 0, SEEK_SET);
-        buf.resize(sz > 0 ? sz : 0);
-        if ( sz > 0 && fread(&buf[0], 1, sz, f) != (size_t)sz )
-        {
-                fclose(f);
-                throw std::runtime_error("Failed to read file " + filename);
-        }
-        fclose(f);
+        if ( mapped && p ) munmap(const_cast<char *>(p), n);
+        p = 0; n = 0; mapped = false;
+        std::vector<char>().swap(owned);
 }
+
+void FileBytes::open(std::string const & filename)
+{
+        close();
+        int const fd = ::open(filename.c_str(), O_RDONLY);
+        if ( fd < 0 )
+                throw std::runtime_error("Failed to open file " + filename);
+        struct stat st;
+        if ( fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 )
+        {
+                void * m = mmap(0, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if ( m != MAP_FAILED )
+                {
+                        madvise(m, (size_t)st.st_size, MADV_WILLNEED);
+                        p = static_cast<char const *>(m); n = (size_t)st.st_size; mapped = true;
+                        ::close(fd);
+                        return;
+                }
+        }
+        // not mappable (or empty): read it
+        char tmp[1 << 16];
+        ssize_t got;
+        while ( (got = ::read(fd, tmp, sizeof(tmp))) > 0 ) owned.insert(owned.end(), tmp, tmp + got);
+        ::close(fd);
+        if ( got < 0 )
+                throw std::runtime_error("Failed to read file " + filename);
+        p = owned.empty() ? 0 : &owned[0]; n = owned.size();
+}
+
+static void slurp(std::string const & filename, FileBytes & buf) { buf.open(filename); }
 
 std::vector<uint64_t> TextFile::starts() const
 {
@@ -287,7 +312,7 @@ std::vector<uint64_t> TextFile::starts() const
 void getText(std::string const & filename, TextFile & out)
 {
         std::cerr << "Computing length of file " << filename << "...";
-        std::vector<char> buf;
+        FileBytes buf;
         slurp(filename, buf);
         out.ranges.clear();
         out.words.assign(buf.size() / 32 + 2, 0);
@@ -382,8 +407,8 @@ namespace
 {
         struct Cursor
         {
-                std::vector<char> const & b; size_t p;
-                Cursor(std::vector<char> const & rb) : b(rb), p(0) {}
+                FileBytes const & b; size_t p;
+                Cursor(FileBytes const & rb) : b(rb), p(0) {}
                 int get() { return p < b.size() ? (unsigned char)b[p++] : -1; }
         };
         inline uint8_t mapChar(int c)
@@ -392,36 +417,70 @@ namespace
         }
 }
 
-// the reader state machines, one record at a time; quality == 0 for FASTA
+// the reader state machines, one record at a time; quality == 0 for FASTA.  Same transitions as the reference's
+// character-at-a-time loops (FastAReader.hpp:107-138, FastQReader.hpp:130-180), taken a run of bytes at a time.
+static inline bool isSpaceByte(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }      // isspace in the "C" locale
+
 static bool nextPattern(Cursor & in, bool fastq, int qualityOffset, bool & foundnextmarker, std::string & id, std::string & pat, std::string * quality)
 {
         char const marker = fastq ? '@' : '>';
         if ( ! foundnextmarker )
                 return false;
         foundnextmarker = false;
-        int c;
-        id.resize(0);
-        while ( (c = in.get()) >= 0 && c != '\n' ) id += (char)c;
-        if ( c < 0 ) return false;
+        char const * const B = in.b.data();
+        size_t const N = in.b.size();
+        size_t p = in.p;
+        {
+                // id: the rest of the marker's line
+                void const * e = p < N ? memchr(B + p, '\n', N - p) : 0;
+                if ( ! e ) { in.p = N; return false; }
+                size_t const q = static_cast<char const *>(e) - B;
+                id.assign(B + p, q - p);
+                p = q + 1;
+        }
         pat.resize(0);
-        char const patterm = fastq ? '+' : '>';
-        while ( (c = in.get()) >= 0 && c != patterm )
-                if ( ! isspace(c) ) pat += (char)c;
+        unsigned char const patterm = fastq ? '+' : '>';
+        int c = -1;
+        while ( p < N )
+        {
+                unsigned char const ch = B[p];
+                if ( ch == patterm ) { c = ch; ++p; break; }
+                if ( isSpaceByte(ch) ) { ++p; continue; }
+                size_t q = p + 1;
+                while ( q < N && (unsigned char)B[q] != patterm && ! isSpaceByte(B[q]) ) ++q;
+                pat.append(B + p, q - p);
+                p = q;
+        }
         if ( ! fastq )
         {
+                in.p = p;
                 foundnextmarker = (c == '>');
                 return true;
         }
-        while ( (c = in.get()) >= 0 && c != '\n' ) {}           // rest of the '+' line
-        if ( c < 0 ) return false;
+        {
+                // rest of the '+' line
+                void const * e = p < N ? memchr(B + p, '\n', N - p) : 0;
+                if ( ! e ) { in.p = N; return false; }
+                p = static_cast<char const *>(e) - B + 1;
+        }
         quality->resize(0);
         // the reference's loop fetches one character beyond the last quality value (FastQReader.hpp:163-165)
-        while ( ((c = in.get()) >= 0) && (quality->size() < pat.size()) )
-                if ( ! isspace(c) ) *quality += (char)(c - qualityOffset);
+        for ( ;; )
+        {
+                if ( p >= N ) break;
+                unsigned char const ch = B[p++];
+                if ( quality->size() >= pat.size() ) break;
+                if ( ! isSpaceByte(ch) ) quality->push_back((char)(ch - qualityOffset));
+        }
+        in.p = p;
         if ( quality->size() < pat.size() )
                 return false;
-        while ( (c = in.get()) >= 0 && c != marker ) {}          // findNextMarker
-        foundnextmarker = (c == marker);
+        {
+                // findNextMarker
+                void const * e = p < N ? memchr(B + p, marker, N - p) : 0;
+                if ( e ) { in.p = static_cast<char const *>(e) - B + 1; foundnextmarker = true; }
+                else in.p = N;
+        }
         return true;
 }
 
@@ -432,7 +491,7 @@ static bool findFirstMarker(Cursor & in, char marker)
         return c == marker;
 }
 
-static int detectQualityOffsetBuffer(std::vector<char> const & buf)
+static int detectQualityOffsetBuffer(FileBytes const & buf)
 {
         Cursor in(buf);
         bool found = findFirstMarker(in, '@');
@@ -448,7 +507,7 @@ static int detectQualityOffsetBuffer(std::vector<char> const & buf)
 
 int detectQualityOffset(std::string const & filename)
 {
-        std::vector<char> buf;
+        FileBytes buf;
         slurp(filename, buf);
         return detectQualityOffsetBuffer(buf);
 }
@@ -460,7 +519,7 @@ namespace
         // Runs the reader's state machine from the marker at `start` (NO_MARKER = nothing to read) and appends the records
         // whose marker lies in front of `limit`.  Returns the position of the marker the next record starts at, or
         // NO_MARKER when the reader's loop is over (end of file, or a record it rejects: the reference stops there too).
-        size_t parseRange(std::vector<char> const & buf, size_t start, size_t limit, bool fastq, int qualityOffset, ReadSet & out)
+        size_t parseRange(FileBytes const & buf, size_t start, size_t limit, bool fastq, int qualityOffset, ReadSet & out)
         {
                 if ( start == NO_MARKER )
                         return NO_MARKER;
@@ -473,9 +532,11 @@ namespace
                 {
                         if ( ! nextPattern(in, fastq, qualityOffset, found, id, pat, fastq ? &q : 0) )
                                 return NO_MARKER;
-                        for ( size_t i = 0; i < pat.size(); ++i ) out.mapped.push_back(mapChar(pat[i]));
+                        size_t const m0 = out.mapped.size();
+                        out.mapped.resize(m0 + pat.size());
+                        for ( size_t i = 0; i < pat.size(); ++i ) out.mapped[m0 + i] = mapChar((unsigned char)pat[i]);
                         if ( fastq )
-                                for ( size_t i = 0; i < pat.size(); ++i ) out.quality.push_back((uint8_t)q[i]);
+                                out.quality.insert(out.quality.end(), q.begin(), q.begin() + pat.size());
                         out.offsets.push_back(out.mapped.size());
                         out.ids.push_back(id);
                         if ( ! found )
@@ -487,7 +548,7 @@ namespace
 
         // where a record probably starts at or behind `from`: a marker at the start of a line (FASTQ: with a '+' line two
         // lines on).  Only a guess -- readPatternsBuffer checks it against the state machine's own position.
-        size_t guessRecordStart(std::vector<char> const & buf, size_t from, bool fastq)
+        size_t guessRecordStart(FileBytes const & buf, size_t from, bool fastq)
         {
                 char const marker = fastq ? '@' : '>';
                 for ( size_t p = from; p < buf.size(); ++p )
@@ -506,14 +567,6 @@ namespace
                 return NO_MARKER;
         }
 
-        void appendReads(ReadSet & to, ReadSet & from)          // from's ids are moved out
-        {
-                uint64_t const base = to.mapped.size();
-                to.mapped.insert(to.mapped.end(), from.mapped.begin(), from.mapped.end());
-                to.quality.insert(to.quality.end(), from.quality.begin(), from.quality.end());
-                for ( size_t i = 1; i < from.offsets.size(); ++i ) to.offsets.push_back(base + from.offsets[i]);
-                to.ids.insert(to.ids.end(), std::make_move_iterator(from.ids.begin()), std::make_move_iterator(from.ids.end()));
-        }
 }
 
 // FastAReader / FastQReader::getNextPatternUnlocked over the whole file (FastAReader.hpp:107-138, FastQReader.hpp:130-180),
@@ -521,7 +574,7 @@ namespace
 // range starts and runs the reader's state machine from there; a range is accepted only if its guess is exactly the
 // position the state machine reached at the end of the range in front of it -- otherwise that range is parsed again
 // from the right position.  The result is the serial reader's, whatever the file looks like.
-void readPatternsBuffer(std::vector<char> const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads)
+void readPatternsBuffer(FileBytes const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads)
 {
         out.mapped.clear(); out.quality.clear(); out.ids.clear();
         out.offsets.assign(1, 0);
@@ -540,6 +593,7 @@ void readPatternsBuffer(std::vector<char> const & buf, bool fastq, int qualityOf
                 parseRange(buf, first, buf.size(), fastq, qualityOffset, out);
                 return;
         }
+        std::chrono::steady_clock::time_point const tp0 = std::chrono::steady_clock::now();
         std::vector<ReadSet> part(nchunks);
         std::vector<size_t> guess(nchunks, NO_MARKER), reached(nchunks, NO_MARKER);
         std::atomic<size_t> next(0);
@@ -561,35 +615,67 @@ void readPatternsBuffer(std::vector<char> const & buf, bool fastq, int qualityOf
                 for ( unsigned int t = 0; t < std::min<size_t>(threads, nchunks); ++t ) team.push_back(std::thread(work));
                 for ( size_t t = 0; t < team.size(); ++t ) team[t].join();
         }
-        size_t total = 0;
-        for ( size_t c = 0; c < nchunks; ++c ) total += part[c].mapped.size();
-        out.mapped.reserve(total);
-        if ( fastq ) out.quality.reserve(total);
+        std::chrono::steady_clock::time_point const tp1 = std::chrono::steady_clock::now();
+        // hand-over check, range by range (a range whose guess was wrong is parsed again here), then the pieces are
+        // copied into place by the team
+        std::vector<char> use(nchunks, 0);
         size_t pos = first;                                     // the marker the serial reader's next record starts at
         for ( size_t c = 0; c < nchunks && pos != NO_MARKER; ++c )
         {
                 size_t const hi = std::min(buf.size(), c * chunk + chunk);
                 if ( pos >= hi )
                         continue;                               // the record in front runs across this whole range
-                if ( guess[c] == pos )
-                {
-                        appendReads(out, part[c]);
-                        pos = reached[c];
-                }
-                else
+                if ( guess[c] != pos )
                 {
                         ReadSet again;
                         again.offsets.assign(1, 0);
-                        pos = parseRange(buf, pos, hi, fastq, qualityOffset, again);
-                        appendReads(out, again);
+                        reached[c] = parseRange(buf, pos, hi, fastq, qualityOffset, again);
+                        part[c].mapped.swap(again.mapped); part[c].quality.swap(again.quality); part[c].offsets.swap(again.offsets); part[c].ids.swap(again.ids);
                 }
-                ReadSet().mapped.swap(part[c].mapped); ReadSet().quality.swap(part[c].quality);
+                use[c] = 1;
+                pos = reached[c];
         }
+        std::vector<size_t> mbase(nchunks + 1, 0), rbase(nchunks + 1, 0);
+        for ( size_t c = 0; c < nchunks; ++c )
+        {
+                mbase[c+1] = mbase[c] + (use[c] ? part[c].mapped.size() : 0);
+                rbase[c+1] = rbase[c] + (use[c] ? part[c].ids.size() : 0);
+        }
+        out.mapped.resize(mbase[nchunks]);
+        if ( fastq ) out.quality.resize(mbase[nchunks]);
+        out.offsets.resize(rbase[nchunks] + 1);
+        out.ids.resize(rbase[nchunks]);
+        next = 0;
+        auto place = [&]()
+        {
+                for ( size_t c = next++; c < nchunks; c = next++ )
+                {
+                        if ( ! use[c] ) continue;
+                        ReadSet & P = part[c];
+                        if ( ! P.mapped.empty() ) memcpy(&out.mapped[mbase[c]], &P.mapped[0], P.mapped.size());
+                        if ( fastq && ! P.quality.empty() ) memcpy(&out.quality[mbase[c]], &P.quality[0], P.quality.size());
+                        for ( size_t i = 0; i < P.ids.size(); ++i )
+                        {
+                                out.offsets[rbase[c] + i + 1] = mbase[c] + P.offsets[i+1];
+                                out.ids[rbase[c] + i].swap(P.ids[i]);
+                        }
+                        ReadSet().mapped.swap(P.mapped); ReadSet().quality.swap(P.quality);
+                }
+        };
+        {
+                std::vector<std::thread> team;
+                for ( unsigned int t = 0; t < std::min<size_t>(threads, nchunks); ++t ) team.push_back(std::thread(place));
+                for ( size_t t = 0; t < team.size(); ++t ) team[t].join();
+        }
+        if ( getenv("REAL_TIMING") )
+                std::cerr << "[timing]   parse (" << nchunks << " ranges, " << threads << " threads) "
+                          << std::chrono::duration<double>(tp1 - tp0).count() << " s, hand-over check + merge "
+                          << std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count() << " s" << std::endl;
 }
 
 void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads)
 {
-        std::vector<char> buf;
+        FileBytes buf;
         slurp(filename, buf);
         if ( ! threads ) threads = std::max(1u, std::thread::hardware_concurrency());
         readPatternsBuffer(buf, fastq, qualityOffset, out, threads);
@@ -801,7 +887,7 @@ namespace
                         return true;
                 }
                 std::cerr << "Computing length of file " << filename << "...";
-                std::vector<char> buf;
+                FileBytes buf;
                 slurp(filename, buf);
                 T.ranges.clear(); T.words.clear(); T.nmask.clear(); T.n = 0;
                 if ( skip_over_limits && fileid >= 64 )
@@ -838,8 +924,10 @@ namespace
 
         void loadReads(RealOptions const & opts, ReadSet & reads)
         {
-                std::vector<char> buf;
+                FileBytes buf;
+                PhaseTimer PT;
                 slurp(opts.patternfilename, buf);
+                PT.lap("  read pattern file");
                 int qualityOffset = 0;
                 if ( opts.fastq )
                 {

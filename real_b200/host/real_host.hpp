@@ -71,6 +71,22 @@ struct TextFile
 void getText(std::string const & filename, TextFile & out);
 void getFileList(std::string const & name, std::vector<std::string> & files, std::string const & suffix);
 
+// the bytes of an input file, mapped read-only (or read into memory where the file cannot be mapped)
+class FileBytes
+{
+        char const * p; size_t n; bool mapped; std::vector<char> owned;
+        FileBytes(FileBytes const &); FileBytes & operator=(FileBytes const &);
+        public:
+        FileBytes() : p(0), n(0), mapped(false) {}
+        ~FileBytes();
+        void open(std::string const & filename);
+        void close();
+        size_t size() const { return n; }
+        char const * data() const { return p; }
+        bool empty() const { return n == 0; }
+        char const & operator[](size_t i) const { return p[i]; }
+};
+
 struct ReadSet
 {
         std::vector<uint8_t> mapped;     // 0..3 = ACGT, 4 = anything else (Pattern.hpp:105-128)
@@ -81,7 +97,7 @@ struct ReadSet
 };
 int detectQualityOffset(std::string const & filename);                       // FastQReader::getOffset
 void readPatterns(std::string const & filename, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads = 0);   // 0 = all host threads
-void readPatternsBuffer(std::vector<char> const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads);
+void readPatternsBuffer(FileBytes const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads);
 // the order the rewritten pattern file hands the reads out in (-R 1): by length, wildcard-free reads first
 void reorderLikeRewrite(ReadSet & reads);
 
