@@ -299,6 +299,8 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
         RG_CUDA(cudaMemcpyAsync(&h->fa_rec_nl[0], h->fa_recnl.p, (size_t)nrec * 8, cudaMemcpyDeviceToHost, h->st2));
         RG_CUDA(cudaStreamSynchronize(h->st2));
         h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);   // transfer of the file bytes + the three ingest kernels
+        if ( ! on_device && h->fa_raw.bytes > (64u << 20) )
+                dev_free(h, h->fa_raw);                         // the file bytes are ~2.7x the packed text: not kept between files
 
         h->fileid = fileid; h->n_total = n; h->shard_begin = 0; h->shard_len = n;
         h->own_begin = 0; h->own_end = n; h->nrec = (uint32_t)nrec;
