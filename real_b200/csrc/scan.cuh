@@ -682,8 +682,8 @@ __device__ __forceinline__ void own_append(OwnScatterSmem & S, uint64_t eq, uint
         }
 }
 
-// step_words = text words handled between two barriers, one per thread (<= PF_THREADS, a multiple of PF_PIECE_WORDS
-// that divides PF_SUPER_WORDS): chosen by the host so that a step is expected to keep about PF_BATCH positions
+// step_words = text words handled between two barriers (PF_THREADS / 1, 2, 4 or 8, a multiple of PF_PIECE_WORDS that
+// divides PF_SUPER_WORDS): chosen by the host so that a step is expected to keep about PF_BATCH positions
 __global__ void __launch_bounds__(PF_THREADS) k_part_scatter_own(ScanParams P, uint32_t step_words)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
@@ -707,6 +707,8 @@ __global__ void __launch_bounds__(PF_THREADS) k_part_scatter_own(ScanParams P, u
         unsigned long long kept = 0;
         const uint64_t * tw = &S.tile[SC_HALO];
         uint32_t const nsteps = PF_SUPER_WORDS / step_words;
+        uint32_t const lanes_per_word = PF_THREADS / step_words, ppt = 32 / lanes_per_word;
+        uint64_t const sub_mask = ppt == 32 ? ~0ULL : ~(~0ULL >> (2 * ppt));         // the first ppt positions of a word (two bits each, first position on top)
 
         uint32_t it = 0;
         for ( uint64_t tile_id = first_tile + blockIdx.x; tile_id < end_tile; tile_id += gridDim.x, ++it )
@@ -727,14 +729,13 @@ __global__ void __launch_bounds__(PF_THREADS) k_part_scatter_own(ScanParams P, u
                         // one text word = 32 positions per thread; the kept ones are appended to the list with one shared-memory
                         // atomic per warp.  The additions of a step are summed in one of three rotating counters (the one of the
                         // next step is cleared here), so a step costs one barrier; the list length n is CTA uniform.
-                        bool const active = threadIdx.x < step_words;
-                        uint32_t const wi = step * step_words + threadIdx.x;
-                        uint64_t w0 = 0, w1 = 0, eq = 0;
-                        if ( active )
-                        {
-                                w0 = tw[wi]; w1 = tw[wi + 1];
-                                eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
-                        }
+                        // G = PF_THREADS / step_words threads share a text word, each takes 32 / G of its positions: whatever
+                        // fraction of the positions a rank keeps, the whole CTA tests and appends
+                        bool const active = true;
+                        uint32_t const wi = step * step_words + threadIdx.x / lanes_per_word;
+                        uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
+                        uint64_t const eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end)
+                                            & (sub_mask >> (2 * ppt * (threadIdx.x % lanes_per_word)));
                         uint32_t const c = (uint32_t)__popcll(eq);
                         uint32_t const incl = warp_incl_scan(c, lane);
                         uint32_t wbase = 0;
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_part_scatter_own(ScanParams P, u
                                         __syncthreads();
                                         if ( threadIdx.x == 0 ) S.add[3] = 0;
                                         __syncthreads();
-                                        bool const mine = active && threadIdx.x / PF_PIECE_WORDS == piece;
+                                        bool const mine = active && (threadIdx.x / lanes_per_word) / PF_PIECE_WORDS == piece;
                                         uint32_t const c2 = mine ? c : 0;
                                         uint32_t const incl2 = warp_incl_scan(c2, lane);
                                         uint32_t wb2 = 0;
