@@ -561,11 +561,17 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
 // super tile) and the list is ranked and written out 2048 descriptors at a time with full warps, like a tile of
 // k_part_scatter.  No record crosses NVLink: the only exchange of a bucket-sharded scan is the fold of the per-read
 // results at its end.
-static const int PF_THREADS = 512;
+#ifndef REAL_PF_THREADS
+#define REAL_PF_THREADS 256
+#endif
+#ifndef REAL_PF_BATCH
+#define REAL_PF_BATCH 2048
+#endif
+static const int PF_THREADS = REAL_PF_THREADS;
 static const int PF_SUPER_WORDS = 2048;                       // text words per super tile
 static const int PF_SUPER_POS = PF_SUPER_WORDS * 32;          // 65536 positions: 16 bits of a descriptor
 static const int PF_SMEM_WORDS = PF_SUPER_WORDS + 2 * SC_HALO;
-static const int PF_BATCH = 2048;                             // descriptors ranked and written out at a time
+static const int PF_BATCH = REAL_PF_BATCH;                    // descriptors ranked and written out at a time
 static const int PF_DPT = PF_BATCH / PF_THREADS;              // per thread
 static const int PF_LIST_CAP = 3 * PF_BATCH;
 static const int PF_PIECE_WORDS = PF_BATCH / 32;              // a piece of a step whose kept positions always fit into the list
