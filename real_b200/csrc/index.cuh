@@ -412,7 +412,8 @@ struct EntryPartSmem
 // staged entries out run by run
 // returns the first output index of the tile's run in bucket threadIdx.x: the caller stores it to S.base after the
 // multisplit, so that the global atomic behind it is in flight while the tile is ranked
-__device__ __forceinline__ uint32_t ep_layout(EntryPartSmem & S, const uint32_t * __restrict__ start, uint32_t * __restrict__ cursor, uint32_t cs)
+// (as two addends: adding them here would make the thread wait for the atomic's round trip on the spot)
+__device__ __forceinline__ uint2 ep_layout(EntryPartSmem & S, const uint32_t * __restrict__ start, uint32_t * __restrict__ cursor, uint32_t cs)
 {
         uint32_t tot = 0;
         #pragma unroll
@@ -421,7 +422,12 @@ __device__ __forceinline__ uint32_t ep_layout(EntryPartSmem & S, const uint32_t 
         uint32_t const ex = block_excl_scan(tot, &blocktot);
         S.loc[threadIdx.x] = ex;
         if ( threadIdx.x == EP_MAX_BUCKETS - 1 ) S.loc[EP_MAX_BUCKETS] = blocktot;
-        uint32_t const basev = tot ? (start[threadIdx.x] + atomicAdd(cursor + threadIdx.x * cs, tot)) : 0;
+        uint2 basev = make_uint2(0u, 0u);
+        if ( tot )
+        {
+                basev.x = start[threadIdx.x];
+                basev.y = atomicAdd(cursor + threadIdx.x * cs, tot);
+        }
         uint32_t run = ex;
         #pragma unroll
         for ( int w = 0; w < 8; ++w )
@@ -451,11 +457,23 @@ __device__ __forceinline__ void ep_place(EntryPartSmem & S, int wid, uint32_t lt
 }
 __device__ __forceinline__ void ep_copy_out(EntryPartSmem & S, uint64_t * __restrict__ out_seed, uint32_t * __restrict__ out_val)
 {
+        // S.base[b] holds "first output index of the run - first staging slot of the bucket" (mod 2^32), so an entry costs one
+        // dependent shared-memory load; four entries are in flight per thread
         uint32_t const n = S.loc[EP_MAX_BUCKETS];
-        for ( uint32_t i = threadIdx.x; i < n; i += 256 )
+        uint32_t i = threadIdx.x;
+        for ( ; i + 3 * 256 < n; i += 4 * 256 )
         {
-                uint32_t const b = S.stage_b[i];
-                uint32_t const o = S.base[b] + (i - S.loc[b]);
+                uint32_t o[4]; uint64_t sd[4]; uint32_t vl[4];
+                #pragma unroll
+                for ( int u = 0; u < 4; ++u ) { o[u] = S.stage_b[i + u * 256]; sd[u] = S.stage_seed[i + u * 256]; vl[u] = S.stage_val[i + u * 256]; }
+                #pragma unroll
+                for ( int u = 0; u < 4; ++u ) o[u] = S.base[o[u]] + (i + u * 256);
+                #pragma unroll
+                for ( int u = 0; u < 4; ++u ) { out_seed[o[u]] = sd[u]; out_val[o[u]] = vl[u]; }
+        }
+        for ( ; i < n; i += 256 )
+        {
+                uint32_t const o = S.base[S.stage_b[i]] + i;
                 out_seed[o] = S.stage_seed[i];
                 out_val[o] = S.stage_val[i];
         }
@@ -509,7 +527,7 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                                 }
                 __syncthreads();
                 // (2) staging layout, global run reservation, per-warp running slots
-                uint32_t const basev = ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
+                uint2 const basev = ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
                 __syncthreads();
                 // (3) warp multisplit into the staging area
                 #pragma unroll
@@ -523,7 +541,7 @@ __global__ void __launch_bounds__(256) k_ent_scatter(EntryPartParams P)
                                 ep_place(S, wid, lt, ok[k] && entry_owned(P, slot), b, seed[k], (uint32_t)(id << 2) | t);
                         }
                 }
-                S.base[threadIdx.x] = basev;
+                S.base[threadIdx.x] = basev.x + basev.y - S.loc[threadIdx.x];
                 __syncthreads();
                 // (4) copy out run by run
                 ep_copy_out(S, P.ent_seed, P.ent_val);
@@ -570,12 +588,12 @@ __device__ __forceinline__ void eo_flush(EntryPartParams const & P, EntryOwnSmem
                 if ( ok ) atomicAdd(&S.wcnt[wid][b[k]], 1u);
         }
         __syncthreads();
-        uint32_t const basev = ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
+        uint2 const basev = ep_layout(S, P.bucket_start, P.bucket_cursor, EP_CURSOR_STRIDE);
         __syncthreads();
         #pragma unroll
         for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
                 ep_place(S, wid, lt, (uint32_t)k * 256 + threadIdx.x < n, b[k], seed[k], val[k]);
-        S.base[threadIdx.x] = basev;
+        S.base[threadIdx.x] = basev.x + basev.y - S.loc[threadIdx.x];
         __syncthreads();
         ep_copy_out(S, P.ent_seed, P.ent_val);
         __syncthreads();
@@ -730,7 +748,7 @@ __global__ void __launch_bounds__(256, 4) k_ent2_scatter(EntryPartParams P)
                         if ( (uint32_t)k * 256 + threadIdx.x < n )
                                 atomicAdd(&S.wcnt[wid][(entry_slot(seed[k], P.G, val[k] & 3) >> sh) & smask], 1u);
                 __syncthreads();
-                uint32_t const basev = ep_layout(S, P.sub_start + (b << P.e2bits), P.sub_cursor + (b << P.e2bits), 1);
+                uint2 const basev = ep_layout(S, P.sub_start + (b << P.e2bits), P.sub_cursor + (b << P.e2bits), 1);
                 __syncthreads();
                 #pragma unroll
                 for ( int k = 0; k < EP_TILE_ENTRIES / 256; ++k )
@@ -738,7 +756,7 @@ __global__ void __launch_bounds__(256, 4) k_ent2_scatter(EntryPartParams P)
                         bool const ok = (uint32_t)k * 256 + threadIdx.x < n;
                         ep_place(S, wid, lt, ok, (entry_slot(seed[k], P.G, val[k] & 3) >> sh) & smask, seed[k], val[k]);
                 }
-                S.base[threadIdx.x] = basev;
+                S.base[threadIdx.x] = basev.x + basev.y - S.loc[threadIdx.x];
                 __syncthreads();
                 ep_copy_out(S, P.ent2_seed, P.ent2_val);
                 __syncthreads();

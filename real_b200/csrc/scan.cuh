@@ -346,9 +346,11 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                         uint32_t const wi = threadIdx.x + k * SC_THREADS;
                         uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
                         uint32_t m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
-                        if ( P.own_b_cnt < SC_MAX_BUCKETS )
+                        if ( P.own_b_cnt < SC_MAX_BUCKETS && ! (m == 0xFFFFFFFFu && bbits == 8) )
                         {
-                                // bucket shard: only the positions of the own buckets are counted (8-bit buckets)
+                                // bucket shard, clipped word: only the positions of the own buckets are counted (8-bit buckets).  Whole
+                                // words take the path below and count every position -- 32 cheap reductions beat picking the kept
+                                // positions out one by one -- and the counts of foreign buckets are dropped at the end
                                 uint64_t eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
                                 while ( eq )
                                 {
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                 __syncthreads();   // tile[buf] is free again
         }
         uint32_t const c = S.cnt[threadIdx.x];
-        if ( c ) atomicAdd(P.bucket_count + threadIdx.x, c);
+        if ( c && (P.own_b_cnt >= SC_MAX_BUCKETS || threadIdx.x - P.own_b_lo < P.own_b_cnt) ) atomicAdd(P.bucket_count + threadIdx.x, c);
 }
 
 // ---- partition, scatter pass ---------------------------------------------------------------------
@@ -409,7 +411,7 @@ struct ScatterSmem
         uint64_t bar[2];
         uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];    // per-warp counts, then running slots
         uint32_t loc[SC_MAX_BUCKETS + 1];                  // first staging slot of a bucket
-        uint32_t base[SC_MAX_BUCKETS];                     // first record of the tile's run in a bucket (index into the owner's record area)
+        uint4 * dst[SC_MAX_BUCKETS];                       // per tile: record area of the bucket's owner + first record of the tile's run - first staging slot
         uint4 * area[SC_MAX_BUCKETS];                      // record area of the bucket's owner
         uint8_t stage_b[PS_TILE_POS];
 };
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 }
                 __syncthreads();
                 // (2) bucket b (thread b): totals -> staging layout, global run reservation, per-warp running slots
-                uint32_t basev;
+                uint32_t bstart = 0, reserved = 0;       // basev = bstart + reserved, summed only where it is needed (see below)
                 {
                         uint32_t tot = 0;
                         #pragma unroll
@@ -484,8 +486,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                         S.loc[threadIdx.x] = ex;
                         if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
                         // the run's first record is needed at the copy-out only: the global atomic that reserves it stays in
-                        // flight while the tile is ranked
-                        basev = tot ? (P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot)) : 0;
+                        // flight while the tile is ranked -- its result must not be touched before (an addition right here
+                        // made every thread wait for the round trip: 12 % of the kernel's stall samples)
+                        if ( tot )
+                        {
+                                bstart = P.bucket_start[threadIdx.x];
+                                reserved = atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot);
+                        }
                         uint32_t run = ex;
                         #pragma unroll
                         for ( int w = 0; w < SC_THREADS / 32; ++w )
@@ -531,18 +538,30 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                                 }
                         }
                 }
-                S.base[threadIdx.x] = basev;
+                // where staging slot 0 would go if it belonged to this bucket: the copy-out adds the slot number
+                S.dst[threadIdx.x] = S.area[threadIdx.x] + ((int64_t)(bstart + reserved) - (int64_t)S.loc[threadIdx.x]);
                 __syncthreads();
-                // (4) copy out: consecutive threads write consecutive records of a bucket run
+                // (4) copy out: consecutive threads write consecutive records of a bucket run; four records in flight per thread,
+                // one dependent shared-memory load each
                 {
                         uint32_t const n = S.loc[SC_MAX_BUCKETS];
                         uint32_t const pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums below do not
-                        for ( uint32_t i = threadIdx.x; i < n; i += SC_THREADS )
+                        uint32_t i = threadIdx.x;
+                        for ( ; i + 3 * SC_THREADS < n; i += 4 * SC_THREADS )
                         {
-                                uint32_t const b = S.stage_b[i];
+                                uint32_t b[4]; uint4 r[4]; uint4 * d[4];
+                                #pragma unroll
+                                for ( int u = 0; u < 4; ++u ) { b[u] = S.stage_b[i + u * SC_THREADS]; r[u] = S.stage[i + u * SC_THREADS]; }
+                                #pragma unroll
+                                for ( int u = 0; u < 4; ++u ) d[u] = S.dst[b[u]];
+                                #pragma unroll
+                                for ( int u = 0; u < 4; ++u ) { r[u].w += pos0; d[u][i + u * SC_THREADS] = r[u]; }
+                        }
+                        for ( ; i < n; i += SC_THREADS )
+                        {
                                 uint4 r = S.stage[i];
                                 r.w += pos0;
-                                S.area[b][S.base[b] + (i - S.loc[b])] = r;
+                                S.dst[S.stage_b[i]][i] = r;
                         }
                 }
                 __syncthreads();
@@ -604,8 +623,8 @@ __device__ __forceinline__ void own_flush(ScanParams const & P, OwnScatterSmem &
                 if ( i < n ) atomicAdd(&S.wcnt[wid][d[k] >> 24], 1u);
         }
         __syncthreads();
-        uint32_t basev = 0;       // first record of the batch's run in bucket threadIdx.x: needed at the copy-out only, so the
-                                  // global atomic that reserves the run is in flight while the batch is ranked
+        uint32_t bstart = 0, reserved = 0;   // their sum = first record of the batch's run in bucket threadIdx.x: needed at the copy-out
+                                             // only, so the global atomic that reserves the run is in flight while the batch is ranked
         {
                 uint32_t tot = 0;
                 if ( threadIdx.x < SC_MAX_BUCKETS )
@@ -619,7 +638,11 @@ __device__ __forceinline__ void own_flush(ScanParams const & P, OwnScatterSmem &
                 {
                         S.loc[threadIdx.x] = ex;
                         if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
-                        if ( tot ) basev = P.bucket_start[threadIdx.x] + atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot);
+                        if ( tot )
+                        {
+                                bstart = P.bucket_start[threadIdx.x];
+                                reserved = atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot);
+                        }
                         uint32_t run = ex;
                         #pragma unroll
                         for ( int w = 0; w < PF_THREADS / 32; ++w )
@@ -661,15 +684,23 @@ __device__ __forceinline__ void own_flush(ScanParams const & P, OwnScatterSmem &
                         S.stage_b[slot] = (uint8_t)b;
                 }
         }
-        if ( threadIdx.x < SC_MAX_BUCKETS ) S.base[threadIdx.x] = basev;
+        if ( threadIdx.x < SC_MAX_BUCKETS ) S.base[threadIdx.x] = bstart + reserved - S.loc[threadIdx.x];     // + staging slot = record index (mod 2^32)
         __syncthreads();
         {
                 uint32_t const m = S.loc[SC_MAX_BUCKETS];
-                for ( uint32_t i = threadIdx.x; i < m; i += PF_THREADS )
+                uint32_t i = threadIdx.x;
+                for ( ; i + 3 * PF_THREADS < m; i += 4 * PF_THREADS )
                 {
-                        uint32_t const b = S.stage_b[i];
-                        P.recs[S.base[b] + (i - S.loc[b])] = S.stage[i];
+                        uint32_t o[4]; uint4 r[4];
+                        #pragma unroll
+                        for ( int u = 0; u < 4; ++u ) { o[u] = S.stage_b[i + u * PF_THREADS]; r[u] = S.stage[i + u * PF_THREADS]; }
+                        #pragma unroll
+                        for ( int u = 0; u < 4; ++u ) o[u] = S.base[o[u]] + (i + u * PF_THREADS);
+                        #pragma unroll
+                        for ( int u = 0; u < 4; ++u ) P.recs[o[u]] = r[u];
                 }
+                for ( ; i < m; i += PF_THREADS )
+                        P.recs[S.base[S.stage_b[i]] + i] = S.stage[i];
         }
         #pragma unroll
         for ( int w = threadIdx.x >> 8; w < PF_THREADS / 32; w += PF_THREADS / 256 ) S.wcnt[w][threadIdx.x & 255] = 0;     // read last before the barrier above
