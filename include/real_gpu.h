@@ -154,9 +154,10 @@ int real_gpu_set_text_fasta_device(real_gpu * h, uint32_t fileid, const void * d
  * record, the file offset of the '\n' that closed its header -- the record's name is the bytes between the last '>'
  * in front of that offset and the offset itself (countReads.cpp:44-58).  Either pointer may be NULL. */
 int real_gpu_get_text_records(real_gpu * h, uint64_t * record_starts, uint64_t * header_ends);
-/* Copies the current text (shard) back in the layout real_gpu_set_text takes: (shard_len+31)/32 words and
- * (shard_len+63)/64 mask words.  Either pointer may be NULL. */
-int real_gpu_get_text_packed(real_gpu * h, uint64_t * words, uint64_t * nmask);
+/* Copies the current text (shard) back in the layout real_gpu_set_text takes: (n_bases+31)/32 words and
+ * (n_bases+63)/64 mask words.  n_bases must be the length of the current text (shard), REAL_GPU_E_ARG otherwise:
+ * it is what the caller sized its buffers for.  Either pointer may be NULL. */
+int real_gpu_get_text_packed(real_gpu * h, uint64_t n_bases, uint64_t * words, uint64_t * nmask);
 
 /* Read set (replaces reader_type::fillPatternBlock + Pattern::computeMapped + RestWordBuffer::setup*
  * + SignatureConstruction::signatureMapped/reverseMappedSignature per read, and the index build

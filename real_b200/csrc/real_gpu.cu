@@ -1027,10 +1027,11 @@ int real_gpu_get_text_records(real_gpu * h, uint64_t * record_starts, uint64_t *
         RG_API_END(h)
 }
 
-int real_gpu_get_text_packed(real_gpu * h, uint64_t * words, uint64_t * nmask)
+int real_gpu_get_text_packed(real_gpu * h, uint64_t n_bases, uint64_t * words, uint64_t * nmask)
 {
         RG_API_BEGIN_ASYNC(h)
         if ( ! h->have_text ) return fail(h, REAL_GPU_E_STATE, "no text set");
+        if ( n_bases != h->shard_len ) return fail(h, REAL_GPU_E_ARG, "get_text_packed: n_bases is not the length of the current text (shard)");
         if ( words ) RG_CUDA(cudaMemcpyAsync(words, ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, (h->shard_len + 31) / 32 * 8, cudaMemcpyDeviceToHost, h->st2));
         if ( nmask ) RG_CUDA(cudaMemcpyAsync(nmask, ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, (h->shard_len + 63) / 64 * 8, cudaMemcpyDeviceToHost, h->st2));
         RG_CUDA(cudaStreamSynchronize(h->st2));

@@ -89,7 +89,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_set_text_fasta.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.real_gpu_set_text_fasta_device.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.real_gpu_get_text_records.argtypes = [vp, vp, vp]
-    L.real_gpu_get_text_packed.argtypes = [vp, vp, vp]
+    L.real_gpu_get_text_packed.argtypes = [vp, u64, vp, vp]
     L.real_gpu_set_reads.argtypes = [vp, vp, vp, vp, u64]
     L.real_gpu_set_reads_device.argtypes = [vp, vp, vp, vp, u64, u64, u32]
     L.real_gpu_set_reads_packed.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64]
@@ -209,7 +209,7 @@ class Handle:
         """The current text as (words, nmask) in the layout set_text takes; n = its length in bases."""
         words = np.zeros((n + 31) // 32, dtype=np.uint64)
         nmask = np.zeros((n + 63) // 64, dtype=np.uint64)
-        self._check(self.L.real_gpu_get_text_packed(self.h, words.ctypes.data, nmask.ctypes.data))
+        self._check(self.L.real_gpu_get_text_packed(self.h, n, words.ctypes.data, nmask.ctypes.data))
         return words, nmask
 
     # ---- reads

@@ -103,22 +103,23 @@ def test_matching_after_fasta_ingest_equals_packed_path():
 
 
 def test_argument_errors(m):
+    import ctypes as C
     import torch
     L = m.handle.L
-    import ctypes as C
     n, r = C.c_uint64(), C.c_uint64()
     data = np.frombuffer(b">a\nACGT\n", dtype=np.uint8)
     assert L.real_gpu_set_text_fasta(m.handle.h, 0, None, 8, C.byref(n), C.byref(r)) == -1                 # REAL_GPU_E_ARG: null pointer
     assert L.real_gpu_set_text_fasta(m.handle.h, 0, data.ctypes.data, 8, None, C.byref(r)) == -1
-    assert L.real_gpu_set_text_fasta(m.handle.h, 64, data.ctypes.data, 8, C.byref(n), C.byref(r)) != 0     # fileid over UniqueMatchInfo's 6 bits
+    assert L.real_gpu_set_text_fasta(m.handle.h, 64, data.ctypes.data, 8, C.byref(n), C.byref(r)) == -4    # REAL_GPU_E_LIMIT: fileid over UniqueMatchInfo's 6 bits
     d = torch.zeros(64, dtype=torch.uint8, device="cuda")
     assert L.real_gpu_set_text_fasta_device(m.handle.h, 0, d.data_ptr() + 1, 8, C.byref(n), C.byref(r)) == -1   # unaligned device buffer
-    # a failed call leaves no text behind
-    with pytest.raises(rlib.RealGpuError):
-        m.handle.get_text_packed(4)
     assert m.set_text_fasta(b">a\nACGT\n")[0] == 4
     starts, ends = m.handle.get_text_records()
     assert list(starts) == [0, 4] and list(ends) == [2]
+    words, nmask = m.handle.get_text_packed(4)
+    assert int(words[0]) == 0x1B << 56 and int(nmask[0]) == 0
+    with pytest.raises(rlib.RealGpuError):          # buffers sized for another length are refused, not overrun
+        m.handle.get_text_packed(5)
     # the record table belongs to the fasta loader: a packed text replaces it
     w, k = synth.pack_text(np.asarray([0, 1, 2, 3], dtype=np.uint8))
     m.set_text(w, k, 4, np.asarray([0, 4], dtype=np.uint64))

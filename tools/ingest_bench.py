@@ -140,7 +140,7 @@ def main():
     ew, em = expected_words(torch, sym)
     hw = np.zeros((n + 31) // 32, dtype=np.uint64)
     hm = np.zeros((n + 63) // 64, dtype=np.uint64)
-    h.L.real_gpu_get_text_packed(h.h, hw.ctypes.data, hm.ctypes.data)
+    assert h.L.real_gpu_get_text_packed(h.h, n, hw.ctypes.data, hm.ctypes.data) == 0
     ok_words = bool(np.array_equal(hw.view(np.int64), ew.cpu().numpy())) and bool(np.array_equal(hm.view(np.int64), em.cpu().numpy()))
     del ew, em, hw, hm
     peaks = {}
