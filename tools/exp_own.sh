@@ -1,5 +1,6 @@
 #!/bin/bash
 # development experiment: one rank's share of a bucket-sharded C3 step (ranks of 2 and of 8) with differently tuned own-partition kernels
+# (variants = real_b200/variants/v_<name>.so, built from csrc/real_gpu.cu with -DREAL_PF_THREADS=... -DREAL_PF_BATCH=...; the directory is scratch)
 mkdir -p gpurun_out
 run() { # name, rank spec, env...
   name=$1; rn=$2; shift; shift
