@@ -119,6 +119,9 @@ class ClockSampler:
 # CPU reference leg
 # ------------------------------------------------------------------------------------------------
 
+_REF_SAMPLE = {}     # the sample's input files, written once per process and reused by every step of the reference arm
+
+
 def cpu_reference(wl: dict, sample_text: int, sample_reads: int, threads: int) -> dict:
     """Times the reference's own CPU path (oracle/_ref/ref_harness: its index build per text block and its
     OpenMP matching region) on a bounded sample of the workload, and extrapolates linearly: index time
@@ -129,22 +132,27 @@ def cpu_reference(wl: dict, sample_text: int, sample_reads: int, threads: int) -
     from oracle import oracle_py as O
     n_s = min(sample_text, wl["n"])
     r_s = min(sample_reads, wl["reads"])
-    text = synth.make_text(SEED, n_s, nrecords=min(wl["nrec"], 4), n_per_million=wl["npm"])
     fastq = bool(wl["scores"])
-    reads = synth.make_reads(text, SEED + 1, r_s, wl["L"], wl["sub"], fastq=fastq)
-    if O.have_ref():
-        work = tempfile.mkdtemp(prefix="bench_ref_")
-        try:
+    key = (wl["desc"], n_s, r_s)
+    if key not in _REF_SAMPLE:
+        text = synth.make_text(SEED, n_s, nrecords=min(wl["nrec"], 4), n_per_million=wl["npm"])
+        reads = synth.make_reads(text, SEED + 1, r_s, wl["L"], wl["sub"], fastq=fastq)
+        work = None
+        if O.have_ref():
+            import atexit
+            work = tempfile.mkdtemp(prefix="bench_ref_")
+            atexit.register(shutil.rmtree, work, ignore_errors=True)
             synth.write_fasta(os.path.join(work, "t.fa"), text)
-            rf = os.path.join(work, "r.fq" if fastq else "r.fa")
-            synth.write_reads(rf, reads, fastq)
-            args = ["-t", os.path.join(work, "t.fa"), "-p", rf, "-o", "x", "-u", "1" if wl["mode"] == "unique" else "0", "-R", "0",
-                    "-s", "2", "-e", str(wl["e"]), "-l", "32", "-q", "1" if wl["scores"] else "0", "-T", str(threads)]
-            if fastq:
-                args += ["-Q", "33"]
-            timing, _, _ = O.run_ref(wl["mode"], work, args, threads=threads)
-        finally:
-            shutil.rmtree(work, ignore_errors=True)
+            synth.write_reads(os.path.join(work, "r.fq" if fastq else "r.fa"), reads, fastq)
+        _REF_SAMPLE[key] = (text, reads, work)
+    text, reads, work = _REF_SAMPLE[key]
+    if work is not None:
+        rf = os.path.join(work, "r.fq" if fastq else "r.fa")
+        args = ["-t", os.path.join(work, "t.fa"), "-p", rf, "-o", "x", "-u", "1" if wl["mode"] == "unique" else "0", "-R", "0",
+                "-s", "2", "-e", str(wl["e"]), "-l", "32", "-q", "1" if wl["scores"] else "0", "-T", str(threads)]
+        if fastq:
+            args += ["-Q", "33"]
+        timing, _, _ = O.run_ref(wl["mode"], work, args, threads=threads)
         index_s, match_s, kind = timing["index_s"], timing["match_s"], "reference"
     else:
         O.lib()
