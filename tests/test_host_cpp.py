@@ -177,3 +177,33 @@ def test_parallel_read_parser_equals_serial(dump, tmp_path, chunk):
         team = dump("reads", f, fastq, 33 if fastq else 0, 0, env={"REAL_PARSE_CHUNK": str(chunk)})
         assert len(serial["ids"]) > 100, name
         assert team == serial, name
+
+
+def test_host_text_loader_fuzz_against_restatement(dump, tmp_path):
+    """host getText (REAL_TEXT_LOADER=host path of the command line) against the restated loader on random byte strings"""
+    from oracle import oracle_py as O
+    rng = np.random.RandomState(4242)
+    for k, alphabet in enumerate([b"ACGTN" * 8 + b"acgtn>\n\r x", b"ACGT" * 30 + b">\n\n", b">\nA"]):
+        a = np.frombuffer(alphabet, dtype=np.uint8)
+        data = a[rng.randint(0, a.size, 3000 + 517 * k)].tobytes()
+        f = tmp_path / ("fz%d.fa" % k)
+        f.write_bytes(data)
+        symbols, names, starts = O.fasta_text(data)
+        d = dump("text", f)
+        assert d["n"] == symbols.size
+        assert [r[1] for r in d["ranges"]] == [int(x) for x in starts]
+        assert [r[0].encode("latin-1") for r in d["ranges"][:-1]] == names
+        sym = synth.unpack_text(np.asarray(d["words"], dtype=np.uint64), symbols.size, np.asarray(d["nmask"], dtype=np.uint64))
+        assert np.array_equal(sym, symbols)
+
+
+def test_fasta_writer_roundtrip():
+    """synth.write_fasta_file (the generator of the GPU ingest tests) read back by the restated loader"""
+    import io
+    from oracle import oracle_py as O
+    t = synth.make_text(31, 30007, nrecords=5, n_per_million=2000)
+    f = io.BytesIO()
+    synth.write_fasta_file(f, t)
+    s, names, st = O.fasta_text(f.getvalue())
+    assert np.array_equal(s, t.symbols) and np.array_equal(st, t.record_starts)
+    assert [x.decode() for x in names] == [a for a, _ in t.records]
