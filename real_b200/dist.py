@@ -116,3 +116,30 @@ class ShardedUpload:
         if self.d_all.device.type == "cuda":
             torch.cuda.current_stream(self.d_all.device).synchronize()
         return {name: self.d_all[o:o + n] for name, (o, n) in self.offsets.items()}
+
+
+def gather_match_all(hits, dst: int = 0, group: Optional[dist.ProcessGroup] = None):
+    """matchAll of a job sharded over the ranks of `group`: every rank passes the rows its handle returned, rank `dst`
+    gets them merged in single-handle order (matcher.merge_match_all), the others None.  The rows travel as bytes over
+    the group's backend (NCCL: through device memory; gloo: host) -- an all-gather of variable-length pieces, no reduction."""
+    import numpy as np
+    from . import lib as _lib
+    from . import matcher as _matcher
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    raw = np.ascontiguousarray(np.asarray(hits, dtype=_lib.HIT_DTYPE)).view(np.uint8).reshape(-1)
+    n = torch.tensor([raw.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    if raw.size:
+        buf[:raw.size] = torch.from_numpy(raw.copy()).to(dev)
+    pieces = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(pieces, buf, group=group)
+    if rank != dst:
+        return None
+    parts = [p[:sz].cpu().numpy().view(_lib.HIT_DTYPE) for p, sz in zip(pieces, sizes) if sz]
+    return _matcher.merge_match_all(parts)

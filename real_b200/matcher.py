@@ -284,6 +284,27 @@ class UniqueMatcher(MatcherBase):
         return self.handle.get_gaps()
 
 
+def merge_match_all(parts) -> np.ndarray:
+    """matchAll rows of several shards of one job (text shards or bucket shards: every hit is found by exactly one of them)
+    -> one array in the order a single handle returns them: by read, and inside a read by (k, pos, file, frag, score,
+    inverted), the order of MatchPosAndError::operator< that unifyMatches sorts with (matchAllImplementation.cpp:122-161);
+    rows equal in all of these are dropped like its std::unique does.  No collective is needed for matchAll: each
+    rank's rows go to the host and are merged here."""
+    parts = [np.asarray(p, dtype=_lib.HIT_DTYPE) for p in parts if len(p)]
+    if not parts:
+        return np.zeros(0, dtype=_lib.HIT_DTYPE)
+    h = np.concatenate(parts)
+    order = np.lexsort((h["inverted"], h["score"], h["frag"], h["file"], h["pos"], h["k"], h["patid"]))
+    h = h[order]
+    if len(h) > 1:
+        same = np.ones(len(h) - 1, dtype=bool)
+        for f in ("patid", "k", "pos", "file", "frag", "inverted"):
+            same &= h[f][1:] == h[f][:-1]
+        same &= h["score"][1:] == h["score"][:-1]
+        h = h[np.concatenate(([True], ~same))]
+    return h
+
+
 # UniqueMatchInfo field access (UniqueMatchInfo.hpp:26-39) on numpy arrays
 def umi_state(d): return (np.asarray(d, dtype=np.uint64) >> np.uint64(61)).astype(np.int64)
 def umi_pos(d): return (np.asarray(d, dtype=np.uint64) & np.uint64((1 << 35) - 1)).astype(np.int64)

@@ -174,3 +174,63 @@ def test_sharded_upload_world2_gloo(tmp_path):
     out = str(tmp_path / "up%d.npy")
     mp.spawn(_upload_worker, args=(2, port, out), nprocs=2, join=True)
     assert all(int(np.load(out % r)[0]) == 1 for r in range(2))
+
+
+def _lib_hits(h):
+    """oracle rows (one text block) in the row type the library returns"""
+    from real_b200 import lib as rlib
+    out = np.zeros(len(h), dtype=rlib.HIT_DTYPE)
+    for f in ("patid", "pos", "file", "frag", "k", "inverted", "score"):
+        out[f] = h[f]
+    return out
+
+
+def _all_case():
+    text = synth.make_text(91, 90_000, nrecords=2, n_per_million=1000)
+    sym = text.symbols.copy()
+    sym[50_000:54_000] = sym[5_000:9_000]            # repeats => reads with several rows
+    text = synth.Text(sym, text.records)
+    reads = synth.make_reads(text, 92, 1200, 64, 0.015, fastq=True)
+    ll = O.build_ll()
+    hits = _lib_hits(O.match_all(text, reads, seedl=32, seedkmax=2, totalkmax=4, scores=True, ll=ll))
+    owner = (hits["pos"].astype(np.int64) * 2654435761 + hits["inverted"].astype(np.int64) * 40503 + hits["patid"].astype(np.int64)) >> 7
+    return hits, owner
+
+
+def test_merge_match_all_restores_single_handle_order():
+    """matcher.merge_match_all: rows scattered over shards come back in the order one handle returns them"""
+    hits, owner = _all_case()
+    assert len(hits) > 1200 and (np.bincount(hits["patid"].astype(np.int64)) > 1).sum() > 30
+    parts = [hits[(owner % 3) == r] for r in (2, 0, 1)]
+    parts.append(hits[5:9])                           # rows reported twice are dropped like unifyMatches' std::unique does
+    got = matcher.merge_match_all(parts)
+    assert got.dtype == hits.dtype and got.tobytes() == hits.tobytes()
+    assert len(matcher.merge_match_all([hits[:0], hits[:0]])) == 0
+
+
+def _gather_worker(rank, world, port, parts, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = rdist.gather_match_all(parts[rank], dst=0)
+        if rank == 0:
+            np.save(out_path, got)
+        else:
+            assert got is None
+        empty = rdist.gather_match_all(parts[rank][:0], dst=1)         # nobody found anything
+        assert (empty is None) if rank != 1 else (len(empty) == 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_match_all_world2_gloo(tmp_path):
+    """real_b200.dist.gather_match_all: the rows of two ranks (one of them may hold none) merged on rank 0"""
+    hits, owner = _all_case()
+    for parts in ([hits[(owner % 2) == 0], hits[(owner % 2) == 1]], [hits[:0], hits]):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        out = str(tmp_path / "merged.npy")
+        mp.spawn(_gather_worker, args=(2, port, parts, out), nprocs=2, join=True)
+        assert np.load(out).tobytes() == hits.tobytes()
