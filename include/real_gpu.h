@@ -144,7 +144,8 @@ int real_gpu_set_text_device(real_gpu * h, uint32_t fileid,
  * AutoTextArray (AutoTextArray.hpp:27-61) -- and sets the result as the current text, as real_gpu_set_text would with
  * shard = own range = the whole file.  *n_bases = bases kept, *nrecords = headers closed by a '\n'
  * (ranges.size() - 1 of countLength).  When either is 0 the call succeeds but no text is set.
- * Limits as for real_gpu_set_text.  The caller's buffer is free again when the call returns. */
+ * Limits as for real_gpu_set_text.  The caller's buffer is free again when the call returns.  A call refused with
+ * REAL_GPU_E_ARG changes nothing; after any other failure the handle has no text. */
 int real_gpu_set_text_fasta(real_gpu * h, uint32_t fileid, const void * fasta_bytes, uint64_t nbytes,
                             uint64_t * n_bases, uint64_t * nrecords);
 /* Same, with the file bytes already in device memory (16-byte aligned; not modified, not kept). */
