@@ -90,7 +90,7 @@ typedef struct
  * handle's stream. */
 typedef struct
 {
-        float h2d_text_ms;
+        float h2d_text_ms;      /* text transfer; after real_gpu_set_text_fasta*: transfer of the file bytes + the K0 kernels */
         float h2d_reads_ms;
         float pack_ms;          /* K1: read packing + seed extraction */
         float index_ms;         /* K2: entry generation + radix sorts + table build */
