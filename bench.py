@@ -17,6 +17,8 @@ exchange; total work is fixed as N grows ("strong").
            `traffic` = DRAM bytes of the committed ncu capture (profiles/r01_traffic_c3.json).
 `cpu_baseline` / --impl reference: the reference's own CPU code (oracle/_ref/ref_harness, compiled
 from the reference sources) on a bounded sample, extrapolated linearly to the workload.
+`ingest` : (N=1, an extra outside the timed step) K0, the FASTA text loader on the device, on a 260 MB
+           file held in HBM: device time, file GB/s, HBM fraction, parity of the packed words.
 """
 from __future__ import annotations
 
@@ -206,6 +208,43 @@ def scan_traffic(workload: str, world: int, as_rank: str):
         return None
 
 
+def ingest_probe(torch, rlib, peak_gbs: float) -> dict:
+    """K0, the FASTA text loader on the device (csrc/ingest.cuh), on a bounded synthetic file held in HBM: 256 Mbp in one record,
+    60-column lines.  Device time of real_gpu_set_text_fasta_device (summary + scan + clear + pack, CUDA events on the library's
+    stream), and the packed words it produced against the symbols the file was written from.  An extra of the bench line,
+    not part of the timed step; tools/ingest_bench.py is the full-size measurement (profiles/r01_ingest_bench.txt)."""
+    import numpy as np
+    n = 480 * 533_333                                   # a multiple of the 60-column lines and of the 32-base words
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED)
+    sym = torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
+    rows = torch.empty((n // 60, 61), dtype=torch.uint8, device="cuda")
+    rows[:, :60] = lut[sym.long()].reshape(-1, 60)
+    rows[:, 60] = 10
+    data = torch.cat([torch.frombuffer(bytearray(b"> bench_ingest\n"), dtype=torch.uint8).cuda(), rows.reshape(-1)])
+    del rows
+    h = rlib.Handle(seedl=32, seedkmax=2, totalkmax=4)
+    try:
+        ms = []
+        for _ in range(5):
+            nb, nrec = h.set_text_fasta(None, device_ptr=data.data_ptr(), nbytes=data.numel())
+            ms.append(h.stats()["h2d_text_ms"])
+        words, _ = h.get_text_packed(nb)
+        starts, _ = h.get_text_records()
+    finally:
+        h.close()
+    sh = 62 - 2 * torch.arange(32, device="cuda", dtype=torch.int64)
+    want = (sym.long().reshape(-1, 32) << sh).sum(1).cpu().numpy()
+    t = float(np.median(ms[2:]))
+    alg = data.numel() + n * 3 / 8.0
+    return {"kernel": "K0 text ingest: k_fa_summary + k_fa_scan + k_fa_pack", "file_bytes": int(data.numel()), "bases": int(nb), "records": int(nrec),
+            "device_ms": t, "file_GBps": data.numel() / t / 1e6, "gbp_per_s": n / t / 1e6,
+            "roofline": {"bound": "hbm", "achieved": alg / t / 1e6, "peak": peak_gbs, "unit": "GB/s", "frac": alg / t / 1e6 / peak_gbs,
+                         "note": "algorithmic bytes = file bytes read once + 3/8 byte written per kept base; the kernels read the file twice"},
+            "parity": bool(nb == n and nrec == 1 and list(starts) == [0, n] and np.array_equal(words.view(np.int64), want))}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -227,6 +266,7 @@ def main():
                                                   "(no exchange; for profiling a rank's kernels under ncu; not a reportable number)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the K0 (device text loader) extra of the bench line")
     ap.add_argument("--ref-text", type=int, default=32_000_000, help="reference arm: text bases of the sample")
     ap.add_argument("--ref-reads", type=int, default=500_000, help="reference arm: reads of the sample")
     ap.add_argument("--cpu-text", type=int, default=16_000_000)
@@ -464,6 +504,13 @@ def main():
     dev_bytes = h.device_bytes()
     h.close()
 
+    ingest = None
+    if rank == 0 and world == 1 and not args.no_ingest and not args.as_rank:
+        try:
+            ingest = ingest_probe(torch, rlib, float(roofline["peak"]))
+        except Exception as e:                          # an extra: never in the way of the bench line
+            ingest = {"error": "%s: %s" % (type(e).__name__, e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(wl, args.cpu_text, args.cpu_reads, os.cpu_count() or 1)
@@ -489,7 +536,7 @@ def main():
             "phases_ms": {k: statistics.mean(v) for k, v in phase.items()},
             "counts": {"windows": tot[0], "candidates": tot[1], "hits": tot[2], "seedpass": tot[3], "matchall_hits": nhits_holder[0]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
-            "device_bytes": dev_bytes,
+            "device_bytes": dev_bytes, "ingest": ingest,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
