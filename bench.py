@@ -264,6 +264,10 @@ def main():
     ap.add_argument("--round-mpos", type=int, default=0, help="sharded tables: text positions per round in units of 2^20 (0 = 2^30 positions)")
     ap.add_argument("--as-rank", default="", help="development: R/N = run on ONE GPU the work rank R of an N-rank bucket-sharded job does "
                                                   "(no exchange; for profiling a rank's kernels under ncu; not a reportable number)")
+    ap.add_argument("--reads-format", default="packed", choices=["packed", "bytes"],
+                    help="layout of the HBM-resident read set of the timed step: 'packed' = 2 bit/base, the reference's rewritten pattern file "
+                         "(TemporaryFile.hpp:231-268; verified in place, only the seeds are extracted); 'bytes' = one mapped byte per base "
+                         "(Pattern::mapped; packed into both strands by K1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ingest", action="store_true", help="skip the K0 (device text loader) extra of the bench line")
@@ -338,9 +342,28 @@ def main():
     last_stats = {}
     nhits_holder = [0]
 
+    def pack_2bit():
+        """The read set 2 bit/base on the device (4 bases per byte, first base in bits 7..6) + per-read wildcard flags."""
+        L4 = (L + 3) // 4
+        m2 = mapped.view(R, L)
+        if L % 4:
+            m2 = torch.nn.functional.pad(m2, (0, 4 * L4 - L))
+        m2 = (m2 & 3).view(R, L4, 4)
+        d_packed = ((m2[:, :, 0] << 6) | (m2[:, :, 1] << 4) | (m2[:, :, 2] << 2) | m2[:, :, 3]).contiguous().view(-1)
+        d_flags = (mapped.view(R, L) > 3).any(dim=1).to(torch.uint8)
+        return d_packed, d_flags
+
+    d_packed = d_flags = None
+    if args.reads_format == "packed" or not args.no_e2e:
+        d_packed, d_flags = pack_2bit()
+        torch.cuda.synchronize()
+
     def step_device():
         t0 = time.perf_counter()
-        h.set_reads_device(mapped.data_ptr(), offs.data_ptr(), R, R * L, L, d_quality=qual.data_ptr() if qual is not None else None)
+        if args.reads_format == "packed":
+            h.set_reads_packed_device(d_packed.data_ptr(), R, L, d_wildcard_flags=d_flags.data_ptr(), d_quality=qual.data_ptr() if qual is not None else None)
+        else:
+            h.set_reads_device(mapped.data_ptr(), offs.data_ptr(), R, R * L, L, d_quality=qual.data_ptr() if qual is not None else None)
         t1 = time.perf_counter()
         h.set_text_device(sh_w.data_ptr(), sh_m.data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
         t2 = time.perf_counter()
@@ -427,17 +450,11 @@ def main():
         # reads cross PCIe 2 bit/base, the layout of the reference's own rewritten pattern file (-R 1, the default of
         # matchUnique; TemporaryFile.hpp:231-268); qualities (only with scores) stay 1 byte/base
         L4 = (L + 3) // 4
-        m2 = mapped.view(R, L)
-        if L % 4:
-            m2 = torch.nn.functional.pad(m2, (0, 4 * L4 - L))
-        m2 = (m2 & 3).view(R, L4, 4)
-        d_packed = ((m2[:, :, 0] << 6) | (m2[:, :, 1] << 4) | (m2[:, :, 2] << 2) | m2[:, :, 3]).contiguous().view(-1)
-        d_flags = (mapped.view(R, L) > 3).any(dim=1).to(torch.uint8)
         h_mapped = torch.empty(R * L4, dtype=torch.uint8).pin_memory()
         h_mapped.copy_(d_packed)
         h_flags = torch.empty(R, dtype=torch.uint8).pin_memory()
         h_flags.copy_(d_flags)
-        del m2, d_packed, d_flags
+        del d_packed, d_flags
         torch.cuda.empty_cache()
         h_qual = None
         if qual is not None:
@@ -529,7 +546,9 @@ def main():
                                        % (world, world, world)) if tables_mode else
                                       ("text sharded x%d with %d-base halo, read index replicated" % (world, L)),
                        "l2": "inputs larger than L2 (text %.0f MB/GPU, index tables > 1.8 GB): no flush needed" % (sl / 4 / 1e6),
-                       "table_bits": args.table_bits or 32},
+                       "table_bits": args.table_bits or 32,
+                       "reads_format": "2 bit/base (the reference's rewritten pattern layout), verified in place" if args.reads_format == "packed"
+                                       else "1 byte/base (Pattern::mapped)"},
             "text_gbp_per_s": n / (ms_per_step * 1e-3) / 1e9,
             "scan_only": {"ms": scan_ms, "text_gbp_per_s_per_gpu": last_stats["n_windows"] / (scan_ms * 1e-3) / 1e9,
                           "reads_per_s": R / (scan_ms * 1e-3)},

@@ -114,6 +114,80 @@ __device__ __forceinline__ uint64_t text_word(const uint64_t * __restrict__ word
         return v >> (64 - 2*l);
 }
 
+// reverse complement of the `len` bases held right aligned in x
+__device__ __forceinline__ uint64_t revcomp_word(uint64_t x, uint32_t len)
+{
+        uint64_t y = __brevll(~x);                                                     // complement, reverse all bits
+        y = ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);   // put the two bits of every base back in order
+        return y >> (64 - 2*len);
+}
+
+// ---- where the bases of the reads live ---------------------------------------------------------
+// Byte-per-base input (real_gpu_set_reads*) is packed once into `rpack`: both strands of every read, W words each,
+// 32 bases per word MSB first, left aligned (RestWordBuffer.hpp:33-78 for all reads at once).  Input that already is
+// 2 bit/base (real_gpu_set_reads_packed*: 4 bases per byte, first base in bits 7..6, every read on a byte boundary --
+// the reference's rewritten pattern file, TemporaryFile.hpp:231-268) is NOT repacked: the few candidates that reach
+// the verification cut their words straight out of the packed bytes, the '-' strand by reverse complement.
+struct ReadSrc
+{
+        const uint64_t * rpack;       // strand id s = 2*read + strand at rpack + s * W, or null
+        uint32_t W;
+        uint32_t ubytes;              // packed input of uniform length: bytes per read (0: boffs)
+        const uint8_t * packed;
+        const uint64_t * boffs;       // nreads+1 byte offsets into packed
+};
+
+// `len` (1..32) bases from base `first` on of the packed read that starts at byte p, LEFT aligned.  Reads aligned 32-bit
+// words only, and none that does not hold a wanted byte.
+__device__ __forceinline__ uint64_t packed_bases(const uint8_t * __restrict__ p, uint32_t first, uint32_t len)
+{
+        uintptr_t const addr = reinterpret_cast<uintptr_t>(p) + (first >> 2);
+        const uint32_t * q = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        uint32_t const sh = (uint32_t)(addr & 3) * 8;
+        uint32_t const bo = 2 * (first & 3);
+        uint32_t const nbytes = (bo + 2 * len + 7) >> 3;                        // <= 9
+        uint32_t const nq = (uint32_t)((addr & 3) + nbytes + 3) >> 2;          // <= 3
+        uint32_t const w0 = __ldg(q), w1 = nq > 1 ? __ldg(q + 1) : 0u, w2 = nq > 2 ? __ldg(q + 2) : 0u;
+        // bytes in memory order -> most significant byte first
+        uint32_t const hi = __byte_perm(__funnelshift_r(w0, w1, sh), 0, 0x0123);
+        uint32_t const lo = __byte_perm(__funnelshift_r(w1, w2, sh), 0, 0x0123);
+        uint64_t v = ((uint64_t)hi << 32) | lo;
+        if ( bo )
+        {
+                uint32_t const b8 = (w2 >> sh) & 0xFFu;                           // the ninth byte
+                v = (v << bo) | (uint64_t)(b8 >> (8 - bo));
+        }
+        return len == 32 ? v : (v & (~0ULL << (64 - 2 * len)));
+}
+
+__device__ __forceinline__ const uint8_t * packed_read(ReadSrc const & S, uint32_t read)
+{
+        return S.packed + (S.ubytes ? (uint64_t)read * S.ubytes : __ldg(S.boffs + read));
+}
+
+// `len` (1..32) bases from base `first` on of strand id (= 2*read + strand) of a read of L bases, LEFT aligned.
+// '-' strand = reverse complement of the read: its bases [first, first+len) are read[L-first-len, L-first) mirrored.
+__device__ __forceinline__ uint64_t strand_bases(ReadSrc const & S, uint32_t id, uint32_t L, uint32_t first, uint32_t len)
+{
+        if ( S.rpack )
+        {
+                const uint64_t * rp = S.rpack + (uint64_t)id * S.W;
+                uint32_t const w = first >> 5, o = 2 * (first & 31);
+                uint64_t v = __ldg(rp + w);
+                if ( o )
+                {
+                        v <<= o;
+                        if ( o + 2 * len > 64 ) v |= __ldg(rp + w + 1) >> (64 - o);
+                }
+                return len == 32 ? v : (v & (~0ULL << (64 - 2 * len)));
+        }
+        const uint8_t * p = packed_read(S, id >> 1);
+        if ( ! (id & 1) )
+                return packed_bases(p, first, len);
+        uint64_t const fwd = packed_bases(p, L - first - len, len) >> (64 - 2 * len);
+        return revcomp_word(fwd, len) << (64 - 2 * len);
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 {
         uint64_t z = x + 0x9E3779B97F4A7C15ULL;

@@ -43,14 +43,6 @@ __host__ __device__ __forceinline__ int table_lists(int table, uint32_t seedkmax
 
 // ---- K1 --------------------------------------------------------------------------------------
 
-// reverse complement of the `len` bases held right aligned in x
-__device__ __forceinline__ uint64_t revcomp_word(uint64_t x, uint32_t len)
-{
-        uint64_t y = __brevll(~x);                                                     // complement, reverse all bits
-        y = ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);   // put the two bits of every base back in order
-        return y >> (64 - 2*len);
-}
-
 // `len` (1..32) mapped bytes starting at p, packed 2 bit/base MSB first and left aligned; *bad is set when a
 // byte is not 0..3.  The bytes are fetched as aligned 32-bit words and realigned with funnel shifts; four
 // bases are packed at a time with one multiply: for x = b0 | b1<<8 | b2<<16 | b3<<24 (each 0..3) the top byte
@@ -167,58 +159,6 @@ __global__ void __launch_bounds__(256) k_pack_both(const uint8_t * __restrict__ 
         }
 }
 
-// Reads that arrive 2 bit/base, 4 bases per byte MSB first, every read starting on a byte boundary -- the layout
-// of the reference's rewritten pattern file (TemporaryFile.hpp:231-268, writePatternDontCareFree).  `len` bases
-// starting at base `first` (a multiple of 32) of the read whose packed bytes start at p, left aligned in a word.
-__device__ __forceinline__ uint64_t load_packed_word(const uint8_t * __restrict__ p, uint32_t first, uint32_t len)
-{
-        uintptr_t const addr = reinterpret_cast<uintptr_t>(p) + (first >> 2);
-        const uint32_t * q = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-        uint32_t const sh = (uint32_t)(addr & 3) * 8;
-        uint32_t const nbytes = (len + 3) >> 2;
-        uint32_t const nq = (uint32_t)((addr & 3) + nbytes + 3) >> 2;
-        uint32_t const w0 = __ldg(q), w1 = nq > 1 ? __ldg(q + 1) : 0u, w2 = nq > 2 ? __ldg(q + 2) : 0u;
-        // bytes in memory order -> most significant byte first
-        uint32_t const hi = __byte_perm(__funnelshift_r(w0, w1, sh), 0, 0x0123);
-        uint32_t const lo = __byte_perm(__funnelshift_r(w1, w2, sh), 0, 0x0123);
-        uint64_t const v = ((uint64_t)hi << 32) | lo;
-        return len == 32 ? v : (v & (~0ULL << (64 - 2 * len)));
-}
-
-// one thread per (read, strand, word), packed input; offsets/lengths null = all reads have `uniform` bases
-__global__ void __launch_bounds__(256) k_pack_reads_packed(const uint8_t * __restrict__ packed, const uint64_t * __restrict__ byte_offsets,
-                                                         const uint64_t * __restrict__ offsets, uint32_t uniform, uint64_t nreads, uint32_t W,
-                                                         uint64_t * __restrict__ rpack)
-{
-        uint64_t const gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if ( gid >= nreads * 2 * W ) return;
-        uint32_t const w = (uint32_t)(gid % W);
-        uint64_t const rs = gid / W;
-        uint32_t const s = (uint32_t)(rs & 1);
-        uint64_t const r = rs >> 1;
-        uint32_t const L = offsets ? (uint32_t)(offsets[r+1] - offsets[r]) : uniform;
-        const uint8_t * p = packed + (byte_offsets ? byte_offsets[r] : r * (uint64_t)((uniform + 3) >> 2));
-        uint64_t word = 0;
-        if ( 32 * w < L )
-        {
-                uint32_t const len = min(32u, L - 32 * w);
-                if ( s == 0 )
-                        word = load_packed_word(p, 32 * w, len);
-                else
-                {
-                        // reverse complement of read[L-32w-len, L-32w): fetch the 64 bases around it and cut them out
-                        uint32_t const b0 = L - 32 * w - len;                     // first base of the stretch
-                        uint32_t const a0 = b0 & ~31u;                            // word-aligned base in front of it
-                        uint64_t const x0 = load_packed_word(p, a0, min(32u, L - a0));
-                        uint64_t const x1 = (a0 + 32 < L) ? load_packed_word(p, a0 + 32, min(32u, L - a0 - 32)) : 0ULL;
-                        uint32_t const o = 2 * (b0 - a0);
-                        uint64_t const fwd = (o ? ((x0 << o) | (x1 >> (64 - o))) : x0) >> (64 - 2 * len);
-                        word = revcomp_word(fwd, len) << (64 - 2 * len);
-                }
-        }
-        rpack[gid] = word;
-}
-
 __global__ void __launch_bounds__(256) k_uniform_offsets(uint64_t * __restrict__ offsets, uint64_t nreads, uint32_t L)
 {
         uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,6 +188,30 @@ __global__ void __launch_bounds__(256) k_read_seeds(const uint64_t * __restrict_
         uint64_t const sf = rpack[(2*r) * W] >> (64 - 2*seedl);
         seeds[2*r] = ok ? sf : 0;
         seeds[2*r+1] = ok ? revcomp_word(sf, seedl) : 0;
+}
+
+// 2 bit/base input (real_gpu_set_reads_packed*): nothing is repacked -- the scan verifies its candidates against the
+// caller's bytes (ReadSrc, common.cuh) -- so K1 shrinks to the usable length and the two strand seeds of every read.
+// One thread per read; lengths null = all reads have `uniform` bases.
+__global__ void __launch_bounds__(256) k_seeds_packed(const uint8_t * __restrict__ packed, const uint64_t * __restrict__ byte_offsets,
+                                                    const uint64_t * __restrict__ offsets, uint32_t uniform, uint64_t nreads, uint32_t seedl, uint32_t minlen,
+                                                    const uint32_t * __restrict__ bad, uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds,
+                                                    uint32_t * __restrict__ usable)
+{
+        uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( r >= nreads ) return;
+        uint32_t const L = offsets ? (uint32_t)(offsets[r+1] - offsets[r]) : uniform;
+        bool const ok = (L >= minlen) && ! bad[r];
+        uint64_t sf = 0;
+        if ( ok )
+        {
+                const uint8_t * p = packed + (byte_offsets ? byte_offsets[r] : r * (uint64_t)((uniform + 3) >> 2));
+                sf = packed_bases(p, 0, seedl) >> (64 - 2*seedl);
+        }
+        rlen[r] = ok ? L : 0;
+        usable[r] = ok ? 1 : 0;
+        __stcs(seeds + 2*r, sf);
+        __stcs(seeds + 2*r + 1, ok ? revcomp_word(sf, seedl) : 0);
 }
 
 // ---- K2 --------------------------------------------------------------------------------------

@@ -12,15 +12,16 @@ namespace realgpu
 // float(1.0 + sum_i LL[ref_i][read_i][q_i]), double accumulation in index order; the '-' strand is
 // scored with the reverse complement and the qualities back to front (ComputeScore.hpp:79).
 // One thread per hit: the additions are a dependent chain by definition of the result.
+// n = bases scored (the whole read, or its seed for the gapped pass), Lr = length of the read
 __device__ __forceinline__ float score_hit(const double * __restrict__ sll, const uint64_t * __restrict__ text, uint64_t lpos,
-                                           const uint64_t * __restrict__ rp, const uint8_t * __restrict__ q, uint32_t L, uint32_t strand)
+                                           ReadSrc const & rs, uint32_t id, uint32_t Lr, const uint8_t * __restrict__ q, uint32_t L, uint32_t strand)
 {
         double raw = 1.0;
         for ( uint32_t w = 0; w * 32 < L; ++w )
         {
                 uint32_t const len = (L - 32*w < 32) ? (L - 32*w) : 32;
                 uint64_t const tw = text_word(text, lpos + 32*w, len) << (64 - 2*len);   // left aligned
-                uint64_t const rw = __ldg(rp + w);
+                uint64_t const rw = strand_bases(rs, id, Lr, 32*w, len);
                 for ( uint32_t j = 0; j < len; ++j )
                 {
                         uint32_t const i = 32*w + j;
@@ -35,7 +36,7 @@ __device__ __forceinline__ float score_hit(const double * __restrict__ sll, cons
 
 __global__ void __launch_bounds__(256) k_score_hits(RawHit * __restrict__ hits, uint64_t nhits, const double * __restrict__ ll,
                                                   const uint64_t * __restrict__ text, uint64_t shard_begin,
-                                                  const uint64_t * __restrict__ rpack, uint32_t W, const uint32_t * __restrict__ rlen,
+                                                  ReadSrc rs, const uint32_t * __restrict__ rlen,
                                                   const uint8_t * __restrict__ quality, const uint64_t * __restrict__ offsets)
 {
         __shared__ double sll[1024];
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(256) k_score_hits(RawHit * __restrict__ hits, 
         uint32_t const read = rawhit_read(h.read);
         uint32_t const L = rlen[read];
         const uint8_t * q = quality ? (quality + offsets[read]) : nullptr;
-        h.score = score_hit(sll, text, rawhit_pos(h.pm) - shard_begin, rpack + ((uint64_t)read * 2 + strand) * W, q, L, strand);
+        h.score = score_hit(sll, text, rawhit_pos(h.pm) - shard_begin, rs, read * 2 + strand, L, q, L, strand);
         hits[i] = h;
 }
 
@@ -281,7 +282,7 @@ struct GapParams
         const double * ll;
         const uint64_t * text; const uint64_t * nmask; uint64_t shard_begin;
         const uint64_t * rec; uint32_t nrec;
-        const uint64_t * rpack; uint32_t W; const uint32_t * rlen;
+        ReadSrc rs; const uint32_t * rlen;
         const uint8_t * quality; const uint64_t * offsets;
         uint32_t seedl, scores;
         GapRes * res;
@@ -315,9 +316,11 @@ __global__ void __launch_bounds__(128) k_gap_dp(GapParams P)
         uint64_t const lbase = rpos - P.shard_begin;
         if ( ! (n && m && wildcard_free(P.nmask, lbase + seedl, n)) ) { P.res[c] = R; return; }
 
-        const uint64_t * rp = P.rpack + (uint64_t)read * 2 * P.W;            // '+' strand
+        // '+' strand: packed words, or the caller's 2 bit/base bytes (4 bases per byte, first base in bits 7..6)
+        const uint64_t * rp = P.rs.rpack ? P.rs.rpack + (uint64_t)read * 2 * P.rs.W : nullptr;
+        const uint8_t * pp = P.rs.rpack ? nullptr : packed_read(P.rs, read);
         const uint8_t * q = P.quality ? (P.quality + P.offsets[read]) : nullptr;
-        double const seedscore = P.scores ? (double)score_hit(sll, P.text, lbase, rp, q, seedl, 0) : (double)1.0f;
+        double const seedscore = P.scores ? (double)score_hit(sll, P.text, lbase, P.rs, read * 2, L, q, seedl, 0) : (double)1.0f;
 
         int const MAXgap = 3;
         double const MINscore = -100.0;
@@ -342,7 +345,8 @@ __global__ void __launch_bounds__(128) k_gap_dp(GapParams P)
                         int const j = (int)i - dd;
                         if ( j < left || j > right ) continue;
                         uint32_t const rpos_read = (uint32_t)j + seedl - 1;
-                        uint32_t const rb = (uint32_t)(__ldg(rp + (rpos_read >> 5)) >> (62 - 2 * (rpos_read & 31))) & 3;
+                        uint32_t const rb = rp ? ((uint32_t)(__ldg(rp + (rpos_read >> 5)) >> (62 - 2 * (rpos_read & 31))) & 3)
+                                               : (((uint32_t)__ldg(pp + (rpos_read >> 2)) >> (6 - 2 * (rpos_read & 3))) & 3);
                         uint32_t const qq = q ? (uint32_t)__ldg(q + rpos_read) : 30u;
                         double const sub = sll[((tb << 8) | (rb << 6) | qq) & 1023];
                         double const mis = __dadd_rn(g[dd + 3], sub);

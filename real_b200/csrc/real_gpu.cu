@@ -456,7 +456,8 @@ int build_from_device(real_gpu * h)
         uint64_t const nreads = h->nreads;
 
         RG_CUDA(cudaEventRecord(h->ev[2], h->st));
-        dev_reserve(h, h->rpack, (size_t)nreads * 2 * h->W * 8 + 16);
+        if ( ! h->src_packed )
+                dev_reserve(h, h->rpack, (size_t)nreads * 2 * h->W * 8 + 16);
         dev_reserve(h, h->rlen, (size_t)nreads * 4 + 16);
         dev_reserve(h, h->seeds, (size_t)nreads * 2 * 8 + 16);
         dev_reserve(h, h->usable, (size_t)nreads * 4 + 16);
@@ -472,18 +473,22 @@ int build_from_device(real_gpu * h)
                                                                                 ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
                         RG_KERNEL_CHECK(); launch_count(h);
                 }
+                else if ( h->src_packed )
+                {
+                        // 2 bit/base input stays as it is (the verification reads it in place): only lengths and seeds
+                        k_seeds_packed<<<blocks_for(nreads, 256), 256, 0, h->st>>>(h->src_packed, h->src_byte_offsets, h->src_packed_uniform ? nullptr : ptr<uint64_t>(h->offs),
+                                                                                 h->src_packed_uniform, nreads, seedl, h->prm.seedl, ptr<uint32_t>(h->bad),
+                                                                                 ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
+                        RG_KERNEL_CHECK(); launch_count(h);
+                }
                 else
                 {
-                if ( h->src_packed )
-                        k_pack_reads_packed<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_packed, h->src_byte_offsets, h->src_packed_uniform ? nullptr : ptr<uint64_t>(h->offs),
-                                                                                                 h->src_packed_uniform, nreads, h->W, ptr<uint64_t>(h->rpack));
-                else
                         k_pack_reads<<<blocks_for(nreads * 2 * h->W, 256), 256, 0, h->st>>>(h->src_mapped, ptr<uint64_t>(h->offs), nreads, h->W,
                                                                                           ptr<uint64_t>(h->rpack), ptr<uint32_t>(h->bad));
-                RG_KERNEL_CHECK(); launch_count(h);
-                k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, h->prm.seedl, ptr<uint64_t>(h->rpack),
-                                                                       ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
-                RG_KERNEL_CHECK(); launch_count(h);
+                        RG_KERNEL_CHECK(); launch_count(h);
+                        k_read_seeds<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, h->W, seedl, h->prm.seedl, ptr<uint64_t>(h->rpack),
+                                                                               ptr<uint32_t>(h->bad), ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
+                        RG_KERNEL_CHECK(); launch_count(h);
                 }
         }
         RG_CUDA(cudaEventRecord(h->ev[3], h->st));
@@ -570,6 +575,25 @@ void finish_build(real_gpu * h)
 // scan
 // ---------------------------------------------------------------------------------------------
 
+// where the kernels find the bases of the reads (ReadSrc, common.cuh)
+ReadSrc read_src(real_gpu * h)
+{
+        ReadSrc S;
+        memset(&S, 0, sizeof(S));
+        if ( h->src_packed )
+        {
+                S.packed = h->src_packed;
+                S.ubytes = h->src_packed_uniform ? (h->src_packed_uniform + 3) / 4 : 0;
+                S.boffs = h->src_byte_offsets;
+        }
+        else
+        {
+                S.rpack = ptr<uint64_t>(h->rpack);
+                S.W = h->W;
+        }
+        return S;
+}
+
 void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
 {
         memset(&P, 0, sizeof(P));
@@ -601,10 +625,12 @@ void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
                 P.tab[t].nlists = h->tab[t].nentries ? h->tab[t].nlists : 0;
         }
         P.seedl = seedl; P.vseedl = h->prm.seedl; P.F = h->F; P.keybits = h->keybits; P.seedkmax = h->prm.seedkmax; P.totalkmax = h->prm.totalkmax;
-        P.rpack = ptr<uint64_t>(h->rpack); P.W = h->W; P.rlen = ptr<uint32_t>(h->rlen);
+        P.rs = read_src(h); P.rlen = ptr<uint32_t>(h->rlen);
         P.rec = ptr<uint64_t>(h->rec); P.nrec = h->nrec; P.fileid = h->fileid;
         P.nranks = 1; P.rank = 0; P.bucket_lo[0] = 0; P.bucket_lo[1] = SC_MAX_BUCKETS; P.seg_cap = 0; P.npairs = 0;
         P.own_b_lo = 0; P.own_b_cnt = SC_MAX_BUCKETS;
+        P.hist_pick_max = 32;
+        if ( const char * e = getenv("REAL_GPU_HIST_PICK") ) P.hist_pick_max = (uint32_t)atoi(e);
         P.nprobed = ptr<unsigned long long>(h->counters) + 4;
         P.mode = mode;
         P.hits = ptr<RawHit>(h->hits_raw);
@@ -746,13 +772,15 @@ uint64_t run_scan(real_gpu * h, int mode)
                 RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
                 RG_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
                 bool const wide = h->prm.seedl > 32;
-                RG_CUDA(cudaFuncSetAttribute(k_bucket_probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-                RG_CUDA(cudaFuncSetAttribute(k_bucket_probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+                typedef void (*probe_fn)(const ScanParams);
+                bool const packed_src = h->src_packed != nullptr;
+                probe_fn const probe = wide ? (packed_src ? (probe_fn)k_bucket_probe<true, true> : (probe_fn)k_bucket_probe<true, false>)
+                                            : (packed_src ? (probe_fn)k_bucket_probe<false, true> : (probe_fn)k_bucket_probe<false, false>);
+                RG_CUDA(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
                 int occ_p = 0, occ_b = 0, occ_s = 0;
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, psmem));
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_part_scatter, SC_THREADS, ssmem));
-                if ( wide ) RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bucket_probe<true>, SC_THREADS, bsmem));
-                else RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bucket_probe<false>, SC_THREADS, bsmem));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, probe, SC_THREADS, bsmem));
                 if ( occ_p < 1 ) occ_p = 1;
                 if ( occ_s < 1 ) occ_s = 1;
                 if ( occ_b < 1 ) occ_b = 1;
@@ -819,8 +847,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 RG_KERNEL_CHECK(); launch_count(h);
                         }
                         mark();
-                        if ( wide ) k_bucket_probe<true><<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
-                        else k_bucket_probe<false><<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
+                        probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
                         mark();
                         if ( sharded )
@@ -874,10 +901,10 @@ void preload_kernels(int device)
         if ( device < 0 || device >= 64 || done[device] ) return;
         cudaFuncAttributes a;
 #define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
-        RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_pack_reads_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
+        RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_seeds_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
         RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
-        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD(k_bucket_probe<false>); RG_PRELOAD(k_bucket_probe<true>);
+        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD((k_bucket_probe<false, false>)); RG_PRELOAD((k_bucket_probe<true, false>)); RG_PRELOAD((k_bucket_probe<false, true>)); RG_PRELOAD((k_bucket_probe<true, true>));
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
         RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay);
@@ -1244,7 +1271,7 @@ static uint64_t collect_hits_by_read(real_gpu * h, int mode = 0)
                 if ( h->prm.scores && mode == 0 )
                 {
                         k_score_hits<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<double>(h->ll),
-                                ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, h->shard_begin, ptr<uint64_t>(h->rpack), h->W, ptr<uint32_t>(h->rlen),
+                                ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, h->shard_begin, read_src(h), ptr<uint32_t>(h->rlen),
                                 h->qual_present ? ptr<uint8_t>(h->qual) : nullptr, ptr<uint64_t>(h->offs));
                         RG_KERNEL_CHECK(); launch_count(h);
                 }
@@ -1484,7 +1511,7 @@ int real_gpu_match_gaps(real_gpu * h, uint64_t n_list_windows)
                 G.seg = ptr<RawHit>(h->hits_seg); G.ncand = found; G.ll = ptr<double>(h->ll);
                 G.text = ptr<uint64_t>(h->text) + TEXT_PAD_WORDS; G.nmask = ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS; G.shard_begin = h->shard_begin;
                 G.rec = ptr<uint64_t>(h->rec); G.nrec = h->nrec;
-                G.rpack = ptr<uint64_t>(h->rpack); G.W = h->W; G.rlen = ptr<uint32_t>(h->rlen);
+                G.rs = read_src(h); G.rlen = ptr<uint32_t>(h->rlen);
                 G.quality = h->qual_present ? ptr<uint8_t>(h->qual) : nullptr; G.offsets = ptr<uint64_t>(h->offs);
                 G.seedl = h->prm.seedl; G.scores = h->prm.scores;
                 G.res = ptr<GapRes>(h->gapres);

@@ -77,8 +77,7 @@ struct ScanParams
         TableDev tab[3];
         uint32_t seedl, F, keybits, seedkmax, totalkmax;        // seedl = the indexed seed bases (<= 32)
         uint32_t vseedl;              // seed length of the options; > seedl: the rest of the seed is tested at verification
-        const uint64_t * rpack;
-        uint32_t W;
+        ReadSrc rs;                   // the bases of the reads: packed strands, or the caller's 2 bit/base input
         const uint32_t * rlen;
         const uint64_t * rec;         // nrec+1 global record starts
         uint32_t nrec;
@@ -112,6 +111,7 @@ struct ScanParams
         // only; it reads every text position of the chunk but forms records only of the positions whose bucket it owns.
         // own_b_cnt = SC_MAX_BUCKETS: no filter.
         uint32_t own_b_lo, own_b_cnt;
+        uint32_t hist_pick_max;       // k_part_hist picks the kept positions out one by one when own_b_cnt <= this
         unsigned long long * nprobed; // positions this handle has formed records of (statistics)
 };
 
@@ -346,11 +346,11 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
                         uint32_t const wi = threadIdx.x + k * SC_THREADS;
                         uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
                         uint32_t m = clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
-                        if ( P.own_b_cnt < SC_MAX_BUCKETS && ! (m == 0xFFFFFFFFu && bbits == 8) )
+                        if ( P.own_b_cnt < SC_MAX_BUCKETS && (P.own_b_cnt <= P.hist_pick_max || ! (m == 0xFFFFFFFFu && bbits == 8)) )
                         {
-                                // bucket shard, clipped word: only the positions of the own buckets are counted (8-bit buckets).  Whole
-                                // words take the path below and count every position -- 32 cheap reductions beat picking the kept
-                                // positions out one by one -- and the counts of foreign buckets are dropped at the end
+                                // bucket shard: only the positions of the own buckets are counted (8-bit buckets).  With many own buckets
+                                // (few ranks) whole words take the path below and count every position -- 32 cheap reductions beat
+                                // picking the kept positions out one by one -- and the counts of foreign buckets are dropped at the end
                                 uint64_t eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end);
                                 while ( eq )
                                 {
@@ -934,16 +934,15 @@ struct ProbeSmem
 // Seeds longer than the indexed 32 bases: the seed test of ::match (match.hpp:386-388) over the WHOLE seed of strand
 // `id` laid over the text at local position lstart (read start); a0 = first seed base in strand coordinates.  Returns
 // false when the seed has more than seedkmax mismatches; exact = which of its four fragments match exactly.
-__device__ __forceinline__ bool wide_seed_test(ScanParams const & P, uint32_t id, uint64_t lstart, uint32_t a0, uint32_t & exact)
+__device__ __forceinline__ bool wide_seed_test(ScanParams const & P, uint32_t id, uint32_t L, uint64_t lstart, uint32_t a0, uint32_t & exact)
 {
-        const uint64_t * rp = P.rpack + (uint64_t)id * P.W;
         uint32_t const Ft = P.vseedl >> 2;
         uint32_t seedk = 0;
         exact = 0;
         #pragma unroll
         for ( uint32_t f = 0; f < 4; ++f )
         {
-                uint64_t const rf = text_word(rp, (uint64_t)a0 + f * Ft, Ft);
+                uint64_t const rf = strand_bases(P.rs, id, L, a0 + f * Ft, Ft) >> (64 - 2 * Ft);
                 uint64_t const tf = text_word(P.text, lstart + a0 + f * Ft, Ft);
                 uint32_t const kf = diffcount64(rf, tf);
                 seedk += kf;
@@ -952,9 +951,28 @@ __device__ __forceinline__ bool wide_seed_test(ScanParams const & P, uint32_t id
         return seedk <= P.seedkmax;
 }
 
+// whole-read Hamming distance of strand id of a 2 bit/base input read against the text at word tp, bit offset sh; gives up
+// (returns more than kmax) as soon as the count exceeds kmax.  (PACKED instantiations of the probe kernel only.)
+__device__ __forceinline__ uint32_t distance_packed(ReadSrc const & rs, uint32_t id, uint32_t L, const uint64_t * __restrict__ tp, uint32_t sh, uint32_t kmax)
+{
+        uint32_t const nw = (L + 31) >> 5;
+        uint64_t prev = __ldg(tp);
+        uint32_t k = 0;
+        for ( uint32_t w = 0; w < nw; ++w )
+        {
+                uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
+                uint64_t const nx = __ldg(tp + w + 1);
+                uint64_t const tv = sh ? ((prev << sh) | (nx >> (64 - sh))) : prev;
+                prev = nx;
+                k += diffcount64(strand_bases(rs, id, L, 32*w, len) >> (64 - 2*len), tv >> (64 - 2*len));
+                if ( k > kmax ) break;
+        }
+        return k;
+}
+
 // stage B: one read strand laid over seed window lp -- position / record / wildcard predicates,
 // whole-read distance, report
-template<bool WIDE>
+template<bool WIDE, bool PACKED>
 __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint64_t lp, uint32_t id, uint32_t exact)
 {
         uint32_t const strand = id & 1;
@@ -971,7 +989,7 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
                 uint32_t const gfrag = record_of(P.rec, P.nrec, grpos);
                 if ( gfrag >= P.nrec || grpos + P.vseedl > __ldg(P.rec + gfrag + 1) ) return 0;
                 if ( ! wildcard_free(P.nmask, lp, P.vseedl) ) return 0;
-                if ( WIDE && ! wide_seed_test(P, id, lp, 0, exact) ) return 0;
+                if ( WIDE && ! wide_seed_test(P, id, __ldg(P.rlen + read), lp, 0, exact) ) return 0;
                 unsigned long long const slot = atomicAdd(P.hit_count, 1ULL);
                 if ( slot < P.hit_cap )
                 {
@@ -990,47 +1008,58 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
         uint64_t const gpos = gp - matchoffset;
         if ( gpos < P.own_begin || gpos >= P.own_end ) return 0;
         uint64_t const lpos = gpos - P.shard_begin;
-        if ( WIDE && ! wide_seed_test(P, id, lpos, strand ? (L - P.vseedl) : 0u, exact) ) return 0;
+        if ( WIDE && ! wide_seed_test(P, id, L, lpos, strand ? (L - P.vseedl) : 0u, exact) ) return 0;
 
         // whole-read Hamming distance = seedk + restk (match.hpp:400-405); the words of the read and of the text under
         // it are fetched four at a time so that their latencies overlap (and overlap the predicates' loads below)
-        const uint64_t * rp = P.rpack + (uint64_t)id * P.W;
         const uint64_t * tp = P.text + (lpos >> 5);
         uint32_t const sh = (uint32_t)(lpos & 31) << 1;
         uint32_t const nw = (L + 31) >> 5;
         uint64_t prev = __ldg(tp);
-        uint64_t rw[4], tw[4];
-        #pragma unroll
-        for ( uint32_t u = 0; u < 4; ++u )
-                if ( u < nw ) { rw[u] = __ldg(rp + u); tw[u] = __ldg(tp + u + 1); }
-
-        // RangeVector::isPositionValid && AutoTextArray::isDontCareFree (match.hpp:398)
-        uint32_t const frag = record_of(P.rec, P.nrec, gpos);
-        if ( frag >= P.nrec || gpos + L > __ldg(P.rec + frag + 1) ) return 0;
-        if ( ! wildcard_free(P.nmask, lpos, L) ) return 0;
-
-        uint32_t k = 0;
-        for ( uint32_t w0 = 0; w0 < nw; w0 += 4 )
+        uint32_t k = 0, frag;
+        if ( ! PACKED )
         {
-                if ( w0 )
-                {
-                        #pragma unroll
-                        for ( uint32_t u = 0; u < 4; ++u )
-                                if ( w0 + u < nw ) { rw[u] = __ldg(rp + w0 + u); tw[u] = __ldg(tp + w0 + u + 1); }
-                }
+                const uint64_t * rp = P.rs.rpack + (uint64_t)id * P.rs.W;
+                uint64_t rw[4], tw[4];
                 #pragma unroll
                 for ( uint32_t u = 0; u < 4; ++u )
-                        if ( w0 + u < nw )
+                        if ( u < nw ) { rw[u] = __ldg(rp + u); tw[u] = __ldg(tp + u + 1); }
+
+                // RangeVector::isPositionValid && AutoTextArray::isDontCareFree (match.hpp:398)
+                frag = record_of(P.rec, P.nrec, gpos);
+                if ( frag >= P.nrec || gpos + L > __ldg(P.rec + frag + 1) ) return 0;
+                if ( ! wildcard_free(P.nmask, lpos, L) ) return 0;
+
+                for ( uint32_t w0 = 0; w0 < nw; w0 += 4 )
+                {
+                        if ( w0 )
                         {
-                                uint32_t const w = w0 + u;
-                                uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
-                                uint64_t const tv = sh ? ((prev << sh) | (tw[u] >> (64 - sh))) : prev;      // = text_word(P.text, lpos + 32*w, .) before the final shift
-                                prev = tw[u];
-                                k += diffcount64(rw[u] >> (64 - 2*len), tv >> (64 - 2*len));
+                                #pragma unroll
+                                for ( uint32_t u = 0; u < 4; ++u )
+                                        if ( w0 + u < nw ) { rw[u] = __ldg(rp + w0 + u); tw[u] = __ldg(tp + w0 + u + 1); }
                         }
+                        #pragma unroll
+                        for ( uint32_t u = 0; u < 4; ++u )
+                                if ( w0 + u < nw )
+                                {
+                                        uint32_t const w = w0 + u;
+                                        uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
+                                        uint64_t const tv = sh ? ((prev << sh) | (tw[u] >> (64 - sh))) : prev;      // = text_word(P.text, lpos + 32*w, .) before the final shift
+                                        prev = tw[u];
+                                        k += diffcount64(rw[u] >> (64 - 2*len), tv >> (64 - 2*len));
+                                }
+                        if ( k > P.totalkmax ) return 0;
+                }
+        }
+        else
+        {
+                // 2 bit/base input: the strand's words are cut out of the caller's packed bytes
+                frag = record_of(P.rec, P.nrec, gpos);
+                if ( frag >= P.nrec || gpos + L > __ldg(P.rec + frag + 1) ) return 0;
+                if ( ! wildcard_free(P.nmask, lpos, L) ) return 0;
+                k = distance_packed(P.rs, id, L, tp, sh, P.totalkmax);
                 if ( k > P.totalkmax ) return 0;
         }
-
         if ( P.mode == 1 )
                 unique_update(P.info + read, strand, P.fileid, gpos, k, frag);
         else
@@ -1051,7 +1080,7 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
 // stage A: a set slot bit with the index e of its first entry -> entry chain; per entry the seed test
 // (match.hpp:386-388) and the canonical-list rule: of the up to six lists that reach a position,
 // only the pair made of the two LOWEST exact fragments reports it (replaces unifyMatches' dedup)
-template<bool WIDE>
+template<bool WIDE, bool PACKED>
 __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, uint32_t e, ItemB * qb, uint32_t * qbn, uint32_t * lstats, uint64_t pol_e)
 {
         int const table = (int)(it.post >> 30);
@@ -1093,12 +1122,12 @@ __device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & 
                         qb[o] = ib;
                 }
                 else
-                        lstats[2] += verify_and_report<WIDE>(P, lp, id, exact4);          // queue full: handle it here
+                        lstats[2] += verify_and_report<WIDE, PACKED>(P, lp, id, exact4);          // queue full: handle it here
         }
 }
 
 // the warp's stage B queue
-template<bool WIDE>
+template<bool WIDE, bool PACKED>
 __device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, uint32_t * qbn, int lane, uint32_t * lstats)
 {
         uint32_t const n = min(*qbn, (uint32_t)SC_QB_CAP);
@@ -1106,7 +1135,7 @@ __device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, u
         for ( uint32_t i = lane; i < n; i += 32 )
         {
                 ItemB const ib = qb[i];
-                lstats[2] += verify_and_report<WIDE>(P, ib.lp, ib.id, ib.exact);
+                lstats[2] += verify_and_report<WIDE, PACKED>(P, ib.lp, ib.id, ib.exact);
         }
         __syncwarp();
         if ( lane == 0 ) *qbn = 0;
@@ -1116,7 +1145,7 @@ __device__ __forceinline__ void drain_b_warp(ScanParams const & P, ItemB * qb, u
 // the warp's stage A queue (n items, the same value in every lane): full rounds of 32 from the top of the queue;
 // with `flush` also the rest.  Returns the number of items left.  The statistics go to per-thread shared-memory
 // counters so that the probe loop carries no state for this path.
-template<bool WIDE>
+template<bool WIDE, bool PACKED>
 __device__ __forceinline__ uint32_t drain_a_warp(ScanParams const & P, ProbeSmem & S, uint32_t n, bool flush)
 {
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1132,14 +1161,14 @@ __device__ __forceinline__ uint32_t drain_a_warp(ScanParams const & P, ProbeSmem
         {
                 uint32_t const take = n >= 32 ? 32u : n;
                 if ( (uint32_t)lane < take )
-                        follow_item<WIDE>(P, qa[n - take + lane], qe[n - take + lane], qb, qbn, lstats, pol_e);
+                        follow_item<WIDE, PACKED>(P, qa[n - take + lane], qe[n - take + lane], qb, qbn, lstats, pol_e);
                 __syncwarp();
                 n -= take;
                 if ( *qbn >= 32 )
-                        drain_b_warp<WIDE>(P, qb, qbn, lane, lstats);
+                        drain_b_warp<WIDE, PACKED>(P, qb, qbn, lane, lstats);
         }
         if ( flush && *qbn )
-                drain_b_warp<WIDE>(P, qb, qbn, lane, lstats);
+                drain_b_warp<WIDE, PACKED>(P, qb, qbn, lane, lstats);
         #pragma unroll
         for ( int s = 0; s < 3; ++s )
                 if ( lstats[s] ) S.stat[s][threadIdx.x] += lstats[s];
@@ -1161,7 +1190,7 @@ __device__ __forceinline__ const uint4 * grab_records(ScanParams const & P, uint
 }
 
 // WIDE: seeds longer than the indexed 32 bases (the whole-seed test costs registers the common case must not pay for)
-template<bool WIDE>
+template<bool WIDE, bool PACKED>
 __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(const __grid_constant__ ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
@@ -1274,12 +1303,12 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
                                         qn = 0;
                                 }
                                 else if ( qn >= 32 )
-                                        qn = drain_a_warp<WIDE>(P, S, qn, false);
+                                        qn = drain_a_warp<WIDE, PACKED>(P, S, qn, false);
                         }
                 }
                 g = gn;
         }
-        drain_a_warp<WIDE>(P, S, qn, true);
+        drain_a_warp<WIDE, PACKED>(P, S, qn, true);
 
         // statistics: one atomic per warp and counter
         #pragma unroll
