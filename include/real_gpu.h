@@ -104,6 +104,8 @@ typedef struct
         uint64_t n_candidates;  /* signature-equal (window, entry) pairs examined */
         uint64_t n_seedpass;    /* candidates that passed the seed test and the canonical-list rule */
         uint64_t n_hits;        /* hits emitted */
+        float fold_ms;          /* real_gpu_fold_unique*: push + hand-over + merge */
+        float reserved;
 } real_gpu_stats;
 
 int real_gpu_abi_version(void);
@@ -211,6 +213,12 @@ int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores);
 /* The same for the reads [first, first+count) only: after the cross-shard exchange every rank of a multi-GPU job holds
  * the merged state, and each reads back (formats, writes) its own 1/nranks of the reads. */
 int real_gpu_get_unique_range(real_gpu * h, uint64_t first, uint64_t count, uint64_t * info, float * scores);
+/* Order independent digest of the unique state of the reads [first, first+count), computed on the device: the sum over
+ * the reads of splitmix64(canonical word ^ splitmix64(read ordinal)) mod 2^64 -- canonical = what the reference defines
+ * independently of its visiting order (the whole word for Straight/Reverse, state and error count for NonUnique, the
+ * state alone for NoMatch).  Digests of disjoint ranges add up: the ranks of a multi-GPU job digest their own reads.
+ * Benchmarks and tests compare it with the digest of the single-GPU run / of the reference's dump. */
+int real_gpu_unique_checksum(real_gpu * h, uint64_t first, uint64_t count, uint64_t * checksum);
 /* Clears the unique state (fresh UniqueMatchInfo objects). */
 int real_gpu_reset_unique(real_gpu * h);
 /* With scores the unique fold is order dependent (UpdateUniqueInfo<true>::update, matchUniqueImplementation.cpp:179-248):
@@ -230,6 +238,26 @@ int real_gpu_set_block_windows(real_gpu * h, uint64_t n_list);
 int real_gpu_unique_export_keys(real_gpu * h, uint64_t * d_keys);
 int real_gpu_unique_export_ties(real_gpu * h, const uint64_t * d_min_keys, uint8_t * d_ties);
 int real_gpu_unique_import(real_gpu * h, const uint64_t * d_min_keys, const uint8_t * d_tie_sums);
+
+/* The same exchange over peer memory, as ONE step (reduce-scatter form; no collective library on the path): rank r of
+ * nranks owns the reads [nreads r / nranks, nreads (r+1) / nranks).  Every rank stores the state words of each owner's
+ * reads straight into the owner's staging area (NVLink peer stores, 8 bytes per read and peer), the ranks hand over with
+ * release/acquire flags, and each owner folds the nranks words of its reads by the rule above.  Afterwards rank r holds
+ * the merged UniqueMatchInfo words of ITS reads (real_gpu_get_unique_range); the words of the other reads keep the
+ * rank's own contribution, so further files can be matched and folded again (the fold is idempotent and order
+ * independent).  Without scores only.
+ *   real_gpu_fold_init           allocates this rank's window for read sets of up to max_reads reads; handle_out receives
+ *                                REAL_GPU_COMM_HANDLE_BYTES bytes (a CUDA IPC handle) to pass to the other ranks
+ *   real_gpu_fold_connect        all_handles = the nranks handles in rank order (one process per GPU)
+ *   real_gpu_fold_connect_local  the same for ranks that live in one process (peers = the nranks handles)
+ *   real_gpu_fold_unique         collective over the ranks of a one-process-per-GPU job: call it on every rank after
+ *                                real_gpu_match_unique; returns when this rank's reads are merged
+ *   real_gpu_fold_unique_group   the ranks of ONE process (handles[r] = rank r), driven by one host thread */
+int real_gpu_fold_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t max_reads, void * handle_out);
+int real_gpu_fold_connect(real_gpu * h, const void * all_handles);
+int real_gpu_fold_connect_local(real_gpu * h, real_gpu * const * peers);
+int real_gpu_fold_unique(real_gpu * h);
+int real_gpu_fold_unique_group(real_gpu * const * handles, uint32_t n);
 
 /* Sharded tables: the multi-GPU form of the scan (BASELINE.json north_star asks for the text to be
  * split over the GPUs of one box).  One handle = one rank = one GPU, at most 8.  Every rank is given the whole read

@@ -560,6 +560,78 @@ __global__ void __launch_bounds__(256) k_unique_import(unsigned long long * __re
         info[i] = umi_make(uniq ? (strand ? ST_REVERSE : ST_STRAIGHT) : ST_NONUNIQUE, file, pos, err, frag);
 }
 
+// ---- K5 over peer memory: the fold as ONE exchange (real_gpu_fold_*) ---------------------------------
+// Reduce-scatter form of the reduction above, without a collective library: rank r owns the reads
+// [R r / N, R (r+1) / N).  k_fold_push stores this rank's state words of every owner's reads straight into the owner's
+// staging area (peer memory over NVLink; 8 bytes per read and peer, plain coalesced stores), the ranks hand over with
+// the release/acquire flags of scan.cuh, and k_fold_merge folds the N words of each own read -- lowest error count,
+// NonUnique when a second distinct position holds it, smallest (file, position), '+' before '-': the rule of
+// unique_key / k_unique_ties / k_unique_import in one pass.  UpdateUniqueInfo<false>::update,
+// matchUniqueImplementation.cpp:97-159, folded over disjoint sets of hits.
+struct FoldPeers { unsigned long long * stage[8]; };       // staging area of every rank for this exchange (own included)
+
+// grid.y = destination rank
+__global__ void __launch_bounds__(256) k_fold_push(const unsigned long long * __restrict__ info, uint64_t nreads, uint32_t nranks, uint32_t rank,
+                                                 uint64_t seg, FoldPeers peers)
+{
+        uint32_t const j = blockIdx.y;
+        uint64_t const b = (nreads * j) / nranks, e = (nreads * (j + 1)) / nranks;
+        unsigned long long * dst = peers.stage[j] + (uint64_t)rank * seg;
+        for ( uint64_t i = b + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (uint64_t)gridDim.x * blockDim.x )
+                dst[i - b] = info[i];
+}
+
+// stage = this rank's staging area: the words of source s at stage + s * seg; info_own = &info[first own read]
+__global__ void __launch_bounds__(256) k_fold_merge(const unsigned long long * __restrict__ stage, uint32_t nranks, uint64_t seg, uint64_t n,
+                                                  unsigned long long * __restrict__ info_own)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= n ) return;
+        uint64_t key[8];
+        uint64_t win = UNIQUE_KEY_NONE;
+        #pragma unroll
+        for ( uint32_t s = 0; s < 8; ++s )
+        {
+                key[s] = (s < nranks) ? unique_key(__ldcs(stage + (uint64_t)s * seg + i)) : UNIQUE_KEY_NONE;
+                win = key[s] < win ? key[s] : win;
+        }
+        if ( win == UNIQUE_KEY_NONE )
+                return;            // no rank has a hit: the local NoMatch/Gapped word stays
+        uint32_t ties = 0;
+        #pragma unroll
+        for ( uint32_t s = 0; s < 8; ++s )
+        {
+                bool const samepos = (((key[s] ^ win) >> 17) & ((1ULL << 41) - 1)) == 0;
+                ties += (key[s] != UNIQUE_KEY_NONE && (key[s] >> 59) == (win >> 59) && ! samepos) ? 1u : 0u;
+        }
+        uint32_t const err = (uint32_t)(win >> 59);
+        bool const uniq = ((win >> 58) & 1) && ties == 0;
+        uint32_t const strand = (uint32_t)((win >> 16) & 1);
+        info_own[i] = umi_make(uniq ? (strand ? ST_REVERSE : ST_STRAIGHT) : ST_NONUNIQUE, (uint32_t)((win >> 52) & 63), (win >> 17) & UMI_POSMASK, err, (uint32_t)(win & 0xFFFF));
+}
+
+// ---- state checksum (bench / tests) -----------------------------------------------------------------
+// Order independent digest of the unique state of the reads [first, first + n): sum over the reads of
+// splitmix64(canonical word ^ splitmix64(read ordinal)) mod 2^64, where the canonical word keeps what the reference
+// defines about a read independently of its visiting order (matcher.canonical_unique: everything for Straight / Reverse,
+// state and error count for NonUnique, nothing but the state for NoMatch).  Sums of disjoint ranges add up, so the
+// ranks of a multi-GPU job digest their own reads and the digests are added.
+__global__ void __launch_bounds__(256) k_unique_checksum(const unsigned long long * __restrict__ info, uint64_t first, uint64_t n, unsigned long long * __restrict__ out)
+{
+        unsigned long long acc = 0;
+        for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x )
+        {
+                unsigned long long d = info[first + i];
+                uint32_t const st = umi_state(d);
+                if ( st == ST_NONUNIQUE ) d &= (7ULL << UMI_STATESHIFT) | (15ULL << UMI_ERRSHIFT);
+                else if ( st == ST_NOMATCH ) d = 0;
+                acc += splitmix64(d ^ splitmix64(first + i));
+        }
+        #pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 ) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ( (threadIdx.x & 31) == 0 && acc ) atomicAdd(out, acc);
+}
+
 // ---- synthetic inputs (same formulas as real_b200/synth.py) -------------------------------------
 
 __device__ __forceinline__ uint64_t synth_stream(uint64_t seed, uint64_t tag) { return splitmix64(splitmix64(seed) + tag); }

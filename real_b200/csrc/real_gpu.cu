@@ -75,7 +75,7 @@ struct real_gpu
         uint32_t F, keybits;
 
         // results
-        DevBuf rec_win, rec_pos, part_meta;
+        DevBuf rec_win, rec_pos, part_meta, own_list;
         DevBuf win_valid, win_counts, bounds, gapres, gaps, boffs, flags8;   // reference text blocks (order-faithful replay)
         uint64_t n_list;               // windows per reference text block, 0 = one block per file
         DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
@@ -108,6 +108,22 @@ struct real_gpu
                 { for ( int i = 0; i < SC_MAX_RANKS; ++i ) { base[i] = nullptr; ipc_opened[i] = false; local[i] = nullptr; } for ( int i = 0; i <= SC_MAX_RANKS; ++i ) bucket_lo[i] = 0;
                   ev[0] = ev[1] = nullptr; enqueued[0] = 0; enqueued[1] = 0; }
         } comm;
+
+        // peer-memory fold of the unique state (real_gpu_fold_*): one window per rank = {flags, two staging areas}
+        struct Fold
+        {
+                uint32_t nranks, rank, epoch;
+                uint64_t cap, seg;              // reads the window was sized for; words per source in a staging area
+                DevBuf window, ptrs, error;
+                size_t stage_off;
+                char * base[SC_MAX_RANKS];
+                bool ipc_opened[SC_MAX_RANKS];
+                real_gpu * local[SC_MAX_RANKS];
+                bool connected;
+                cudaEvent_t ev;                 // ranks of one process: "my words are pushed"
+                Fold() : nranks(1), rank(0), epoch(0), cap(0), seg(0), stage_off(4096), connected(false), ev(nullptr)
+                { for ( int i = 0; i < SC_MAX_RANKS; ++i ) { base[i] = nullptr; ipc_opened[i] = false; local[i] = nullptr; } }
+        } fold;
 
         real_gpu_stats stats;
         int pass_bits_override;        // REAL_GPU_PASS_BITS (tuning), -1 = automatic
@@ -203,7 +219,7 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
                 return fail(h, REAL_GPU_E_ARG, "set_text: record_starts[nrecords] must equal n_total");
 
         uint64_t const nw = (shard_len + 31) / 32, nmw = (shard_len + 63) / 64;
-        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + PF_SMEM_WORDS;     // the last tile of every kernel stays inside the allocation
+        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + 2 * OL_TILE_WORDS;     // the last tile of every kernel stays inside the allocation
         size_t const tbytes = (TEXT_PAD_WORDS + nw + tail) * 8, mbytes = (TEXT_PAD_WORDS + nmw + tail) * 8;
 
         // The text goes over the copy stream: an index build that real_gpu_set_reads* has left running on the kernel
@@ -279,7 +295,7 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
                 return REAL_GPU_OK;                             // nothing to match against; no text is set
 
         uint64_t const nw = (n + 31) / 32, nmw = (n + 63) / 64;
-        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + PF_SMEM_WORDS;
+        size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + 2 * OL_TILE_WORDS;
         size_t const tbytes = (TEXT_PAD_WORDS + nw + tail) * 8, mbytes = (TEXT_PAD_WORDS + nmw + tail) * 8;
         dev_reserve(h, h->text, tbytes);
         dev_reserve(h, h->nmask, mbytes);
@@ -629,7 +645,7 @@ void fill_scan_params(real_gpu * h, ScanParams & P, int mode)
         P.rec = ptr<uint64_t>(h->rec); P.nrec = h->nrec; P.fileid = h->fileid;
         P.nranks = 1; P.rank = 0; P.bucket_lo[0] = 0; P.bucket_lo[1] = SC_MAX_BUCKETS; P.seg_cap = 0; P.npairs = 0;
         P.own_b_lo = 0; P.own_b_cnt = SC_MAX_BUCKETS;
-        P.hist_pick_max = 32;
+        P.hist_pick_max = 0;          // measured: picking is slower than counting whole words at every rank count (r02)
         if ( const char * e = getenv("REAL_GPU_HIST_PICK") ) P.hist_pick_max = (uint32_t)atoi(e);
         P.nprobed = ptr<unsigned long long>(h->counters) + 4;
         P.mode = mode;
@@ -758,19 +774,17 @@ uint64_t run_scan(real_gpu * h, int mode)
                 P.unit_counter = meta + 256 + 520;
                 P.bucket_cursor = meta + 1088;
 
-                size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem), osmem = sizeof(OwnScatterSmem);
-                int occ_o = 0;
-                // text words per step of k_part_scatter_own: about PF_BATCH kept positions expected per step
-                uint32_t own_step_words = PF_THREADS;
-                while ( own_step_words > (uint32_t)PF_PIECE_WORDS && (uint64_t)own_step_words * 32 * P.own_b_cnt > (uint64_t)PF_BATCH * SC_MAX_BUCKETS + 256 * P.own_b_cnt ) own_step_words >>= 1;
+                size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem);
                 if ( own_only )
                 {
-                        RG_CUDA(cudaFuncSetAttribute(k_part_scatter_own, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
-                        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_o, k_part_scatter_own, PF_THREADS, osmem));
-                        if ( occ_o < 1 ) occ_o = 1;
+                        // the positions of a chunk this rank keeps, 4 bytes each (all of them if the text falls into its buckets only)
+                        dev_reserve(h, h->own_list, chunk_cap * 4 + 64);
+                        P.list = ptr<uint32_t>(h->own_list);
+                        P.list_count = reinterpret_cast<unsigned long long *>(meta + 780);
                 }
                 RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-                RG_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+                RG_CUDA(cudaFuncSetAttribute(k_part_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+                RG_CUDA(cudaFuncSetAttribute(k_part_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
                 bool const wide = h->prm.seedl > 32;
                 typedef void (*probe_fn)(const ScanParams);
                 bool const packed_src = h->src_packed != nullptr;
@@ -779,11 +793,15 @@ uint64_t run_scan(real_gpu * h, int mode)
                 RG_CUDA(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
                 int occ_p = 0, occ_b = 0, occ_s = 0;
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, psmem));
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_part_scatter, SC_THREADS, ssmem));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, own_only ? k_part_scatter<true> : k_part_scatter<false>, SC_THREADS, ssmem));
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, probe, SC_THREADS, bsmem));
                 if ( occ_p < 1 ) occ_p = 1;
                 if ( occ_s < 1 ) occ_s = 1;
                 if ( occ_b < 1 ) occ_b = 1;
+                // more than REAL_PROBE_MINB CTAs per SM make the probe slower (measured: 87 vs 74 ms scan on C3 with four): the grabs
+                // of more warps spread over more of the bucket order and the probed slices lose their place in L2
+                if ( occ_b > REAL_PROBE_MINB ) occ_b = REAL_PROBE_MINB;
+                if ( const char * e = getenv("REAL_GPU_PROBE_OCC") ) occ_b = std::max(1, atoi(e));
                 long long wait_ms = 30000;             // a peer that never arrives is reported, not waited for forever
                 if ( const char * e = getenv("REAL_GPU_COMM_TIMEOUT_MS") ) wait_ms = atoll(e);
 
@@ -811,7 +829,14 @@ uint64_t run_scan(real_gpu * h, int mode)
                         uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
                         unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * occ_p);
                         RG_CUDA(cudaMemsetAsync(meta, 0, 256 * 4, h->st));
-                        if ( any )
+                        if ( own_only ) RG_CUDA(cudaMemsetAsync(P.list_count, 0, 8, h->st));
+                        if ( any && own_only )
+                        {
+                                uint64_t const oft = P.x_begin / OL_TILE_POS, oet = (P.x_end + OL_TILE_POS - 1) / OL_TILE_POS;
+                                k_own_list<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * 8), OL_THREADS, 0, h->st>>>(P);
+                                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
+                        }
+                        else if ( any )
                         {
                                 k_part_hist<<<pgrid, SC_THREADS, psmem, h->st>>>(P);
                                 RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
@@ -830,12 +855,9 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
                                 unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
                                 if ( own_only )
-                                {
-                                        uint64_t const oft = P.x_begin / PF_SUPER_POS, oet = (P.x_end + PF_SUPER_POS - 1) / PF_SUPER_POS;
-                                        k_part_scatter_own<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * occ_o), PF_THREADS, osmem, h->st>>>(P, own_step_words);
-                                }
+                                        k_part_scatter<true><<<(unsigned)(h->sm_count * occ_s), SC_THREADS, ssmem, h->st>>>(P);
                                 else
-                                        k_part_scatter<<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
+                                        k_part_scatter<false><<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
                                 RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
                         }
                         mark();
@@ -904,10 +926,10 @@ void preload_kernels(int device)
         RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_seeds_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
         RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
-        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter); RG_PRELOAD(k_part_scatter_own); RG_PRELOAD((k_bucket_probe<false, false>)); RG_PRELOAD((k_bucket_probe<true, false>)); RG_PRELOAD((k_bucket_probe<false, true>)); RG_PRELOAD((k_bucket_probe<true, true>));
+        RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter<false>); RG_PRELOAD(k_part_scatter<true>); RG_PRELOAD(k_own_list); RG_PRELOAD((k_bucket_probe<false, false>)); RG_PRELOAD((k_bucket_probe<true, false>)); RG_PRELOAD((k_bucket_probe<false, true>)); RG_PRELOAD((k_bucket_probe<true, true>));
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
-        RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay);
+        RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay); RG_PRELOAD(k_fold_push); RG_PRELOAD(k_fold_merge); RG_PRELOAD(k_unique_checksum);
         RG_PRELOAD(k_fa_summary); RG_PRELOAD(k_fa_scan); RG_PRELOAD(k_fa_pack);
         RG_PRELOAD(k_window_counts); RG_PRELOAD(k_block_bounds); RG_PRELOAD(k_gap_dp); RG_PRELOAD(k_gap_replay);
 #undef RG_PRELOAD
@@ -990,7 +1012,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
                            &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
@@ -998,6 +1020,10 @@ int real_gpu_destroy(real_gpu * h)
                 if ( h->comm.ipc_opened[r] ) { cudaIpcCloseMemHandle(h->comm.base[r]); h->comm.ipc_opened[r] = false; }
         for ( int i = 0; i < 2; ++i ) if ( h->comm.ev[i] ) cudaEventDestroy(h->comm.ev[i]);
         dev_free(h, h->comm.window); dev_free(h, h->comm.ptrs); dev_free(h, h->comm.pairs); dev_free(h, h->comm.error);
+        for ( int r = 0; r < SC_MAX_RANKS; ++r )
+                if ( h->fold.ipc_opened[r] ) { cudaIpcCloseMemHandle(h->fold.base[r]); h->fold.ipc_opened[r] = false; }
+        if ( h->fold.ev ) cudaEventDestroy(h->fold.ev);
+        dev_free(h, h->fold.window); dev_free(h, h->fold.ptrs); dev_free(h, h->fold.error);
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
         for ( int i = 0; i < 8; ++i ) if ( h->ev[i] ) cudaEventDestroy(h->ev[i]);
         for ( int i = 0; i < 2; ++i ) if ( h->evc[i] ) cudaEventDestroy(h->evc[i]);
@@ -1420,6 +1446,28 @@ int real_gpu_get_unique(real_gpu * h, uint64_t * info, float * scores)
         return real_gpu_get_unique_range(h, 0, h->nreads, info, scores);
 }
 
+int real_gpu_unique_checksum(real_gpu * h, uint64_t first, uint64_t count, uint64_t * checksum)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( ! checksum ) return fail(h, REAL_GPU_E_ARG, "unique_checksum: null pointer");
+        if ( first > h->nreads || count > h->nreads - first ) return fail(h, REAL_GPU_E_ARG, "unique_checksum: range outside the read set");
+        dev_reserve(h, h->counters, 8 * 8);
+        RG_CUDA(cudaMemsetAsync(h->counters.p, 0, 8, h->st));
+        if ( count )
+        {
+                k_unique_checksum<<<(unsigned)std::min<uint64_t>(blocks_for(count, 256), (uint64_t)h->sm_count * 8), 256, 0, h->st>>>(
+                        ptr<unsigned long long>(h->info), first, count, ptr<unsigned long long>(h->counters));
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        unsigned long long v = 0;
+        RG_CUDA(cudaMemcpyAsync(&v, h->counters.p, 8, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        *checksum = v;
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
 int real_gpu_reset_unique(real_gpu * h)
 {
         RG_API_BEGIN(h)
@@ -1650,6 +1698,207 @@ int real_gpu_comm_connect_local(real_gpu * h, real_gpu * const * peers)
         }
         return comm_finish_connect(h);
         RG_API_END(h)
+}
+
+// ---- peer-memory fold ---------------------------------------------------------------------------
+
+static int fold_finish_connect(real_gpu * h)
+{
+        real_gpu::Fold & FD = h->fold;
+        uint32_t * fl[SC_MAX_RANKS];
+        for ( int r = 0; r < SC_MAX_RANKS; ++r ) fl[r] = reinterpret_cast<uint32_t *>(FD.base[(uint32_t)r < FD.nranks ? r : 0]);
+        RG_CUDA(cudaMemcpy(FD.ptrs.p, fl, sizeof(fl), cudaMemcpyHostToDevice));
+        FD.connected = true;
+        return REAL_GPU_OK;
+}
+
+static FoldPeers fold_peers(real_gpu::Fold const & FD, uint32_t parity)
+{
+        FoldPeers FP;
+        for ( uint32_t r = 0; r < (uint32_t)SC_MAX_RANKS; ++r )
+                FP.stage[r] = reinterpret_cast<unsigned long long *>(FD.base[r < FD.nranks ? r : 0] + FD.stage_off) + (uint64_t)parity * FD.nranks * FD.seg;
+        return FP;
+}
+
+static void fold_push(real_gpu * h, uint32_t parity)
+{
+        real_gpu::Fold & FD = h->fold;
+        uint64_t const per = (h->nreads + FD.nranks - 1) / FD.nranks;
+        dim3 const grid((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((per + 255) / 256, 4096)), FD.nranks);
+        k_fold_push<<<grid, 256, 0, h->st>>>(ptr<unsigned long long>(h->info), h->nreads, FD.nranks, FD.rank, FD.seg, fold_peers(FD, parity));
+        RG_KERNEL_CHECK(); launch_count(h);
+}
+
+static void fold_merge(real_gpu * h, uint32_t parity)
+{
+        real_gpu::Fold & FD = h->fold;
+        uint64_t const b = (h->nreads * FD.rank) / FD.nranks, e = (h->nreads * (FD.rank + 1)) / FD.nranks;
+        if ( e > b )
+        {
+                k_fold_merge<<<blocks_for(e - b, 256), 256, 0, h->st>>>(fold_peers(FD, parity).stage[FD.rank], FD.nranks, FD.seg, e - b, ptr<unsigned long long>(h->info) + b);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+}
+
+static int fold_check(real_gpu * h)
+{
+        real_gpu::Fold & FD = h->fold;
+        if ( ! FD.window.p || ! FD.connected ) return fail(h, REAL_GPU_E_STATE, "fold_unique: call real_gpu_fold_init and real_gpu_fold_connect* first");
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( h->prm.scores ) return fail(h, REAL_GPU_E_ARG, "fold_unique: the fold with scores is order dependent (needs one handle)");
+        if ( h->nreads > FD.cap ) return fail(h, REAL_GPU_E_LIMIT, "fold_unique: more reads than real_gpu_fold_init was sized for");
+        return REAL_GPU_OK;
+}
+
+int real_gpu_fold_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t max_reads, void * handle_out)
+{
+        RG_API_BEGIN(h)
+        if ( nranks < 1 || nranks > (uint32_t)SC_MAX_RANKS || rank >= nranks ) return fail(h, REAL_GPU_E_ARG, "fold_init: rank/nranks out of range (at most 8 ranks)");
+        real_gpu::Fold & FD = h->fold;
+        if ( FD.window.p ) return fail(h, REAL_GPU_E_STATE, "fold_init: already initialised");
+        FD.nranks = nranks; FD.rank = rank; FD.epoch = 0; FD.cap = max_reads; FD.connected = false;
+        FD.seg = (((max_reads + nranks - 1) / nranks) + 1) & ~1ULL;
+        size_t const bytes = FD.stage_off + (size_t)2 * nranks * FD.seg * 8 + 64;
+        dev_alloc(h, FD.window, bytes);
+        dev_alloc(h, FD.ptrs, SC_MAX_RANKS * sizeof(void *));
+        dev_alloc(h, FD.error, 16);
+        RG_CUDA(cudaMemset(FD.window.p, 0, FD.stage_off));
+        RG_CUDA(cudaMemset(FD.error.p, 0, 16));
+        RG_CUDA(cudaEventCreateWithFlags(&FD.ev, cudaEventDisableTiming));
+        RG_CUDA(cudaDeviceSynchronize());
+        FD.base[rank] = reinterpret_cast<char *>(FD.window.p);
+        if ( handle_out )
+        {
+                cudaIpcMemHandle_t ih;
+                RG_CUDA(cudaIpcGetMemHandle(&ih, FD.window.p));
+                memcpy(handle_out, &ih, sizeof(ih));
+        }
+        if ( nranks == 1 ) return fold_finish_connect(h);
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_fold_connect(real_gpu * h, const void * all_handles)
+{
+        RG_API_BEGIN(h)
+        real_gpu::Fold & FD = h->fold;
+        if ( ! FD.window.p ) return fail(h, REAL_GPU_E_STATE, "fold_connect: call real_gpu_fold_init first");
+        if ( ! all_handles ) return fail(h, REAL_GPU_E_ARG, "fold_connect: null pointer");
+        for ( uint32_t r = 0; r < FD.nranks; ++r )
+        {
+                if ( r == FD.rank || FD.ipc_opened[r] ) continue;
+                cudaIpcMemHandle_t ih;
+                memcpy(&ih, static_cast<const char *>(all_handles) + (size_t)r * REAL_GPU_COMM_HANDLE_BYTES, sizeof(ih));
+                void * p = nullptr;
+                RG_CUDA(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+                FD.base[r] = reinterpret_cast<char *>(p);
+                FD.ipc_opened[r] = true;
+        }
+        return fold_finish_connect(h);
+        RG_API_END(h)
+}
+
+int real_gpu_fold_connect_local(real_gpu * h, real_gpu * const * peers)
+{
+        RG_API_BEGIN(h)
+        real_gpu::Fold & FD = h->fold;
+        if ( ! FD.window.p ) return fail(h, REAL_GPU_E_STATE, "fold_connect_local: call real_gpu_fold_init first");
+        if ( ! peers ) return fail(h, REAL_GPU_E_ARG, "fold_connect_local: null pointer");
+        for ( uint32_t r = 0; r < FD.nranks; ++r )
+        {
+                real_gpu * q = peers[r];
+                if ( ! q || ! q->fold.window.p || q->fold.nranks != FD.nranks || q->fold.rank != r || q->fold.seg != FD.seg )
+                        return fail(h, REAL_GPU_E_ARG, "fold_connect_local: peer handle is not an initialised rank of the same group");
+                if ( q->prm.device != h->prm.device )
+                {
+                        cudaError_t const e = cudaDeviceEnablePeerAccess(q->prm.device, 0);
+                        if ( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled ) RG_CUDA(e);
+                        (void)cudaGetLastError();
+                }
+                FD.base[r] = reinterpret_cast<char *>(q->fold.window.p);
+                FD.local[r] = q;
+        }
+        return fold_finish_connect(h);
+        RG_API_END(h)
+}
+
+int real_gpu_fold_unique(real_gpu * h)
+{
+        RG_API_BEGIN(h)
+        int const rc = fold_check(h);
+        if ( rc ) return rc;
+        real_gpu::Fold & FD = h->fold;
+        if ( FD.local[FD.rank] ) return fail(h, REAL_GPU_E_STATE, "fold_unique: ranks of one process fold with real_gpu_fold_unique_group");
+        long long wait_ms = 30000;
+        if ( const char * e = getenv("REAL_GPU_COMM_TIMEOUT_MS") ) wait_ms = atoll(e);
+        ++FD.epoch;
+        uint32_t const parity = FD.epoch & 1;
+        // Two staging areas, used alternately: a peer can be at most one exchange ahead of this rank (its next exchange waits
+        // for this rank's signal, which is issued behind this rank's merge), so nobody writes into an area that is still read.
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        fold_push(h, parity);
+        k_comm_signal<<<1, 32, 0, h->st>>>(ptr<uint32_t *>(FD.ptrs), FD.nranks, FD.rank, 0, FD.epoch);
+        RG_KERNEL_CHECK();
+        k_comm_wait<<<1, 32, 0, h->st>>>(reinterpret_cast<uint32_t *>(FD.base[FD.rank]), FD.nranks, 0, FD.epoch, wait_ms * 2000000LL, ptr<uint32_t>(FD.error));
+        RG_KERNEL_CHECK(); launch_count(h, 2);
+        fold_merge(h, parity);
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        uint32_t cerr = 0;
+        RG_CUDA(cudaMemcpyAsync(&cerr, FD.error.p, 4, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.fold_ms = elapsed(h->ev[0], h->ev[1]);
+        if ( cerr ) return fail(h, REAL_GPU_E_CUDA, "fold_unique: timed out waiting for rank " + std::to_string(cerr - 1));
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_fold_unique_group(real_gpu * const * handles, uint32_t n)
+{
+        if ( ! handles || n == 0 || n > (uint32_t)SC_MAX_RANKS ) return REAL_GPU_E_ARG;
+        for ( uint32_t r = 0; r < n; ++r )
+                if ( ! handles[r] ) return REAL_GPU_E_ARG;
+        real_gpu * h = handles[0];
+        try
+        {
+                for ( uint32_t r = 0; r < n; ++r )
+                {
+                        h = handles[r];
+                        RG_CUDA(cudaSetDevice(h->prm.device));
+                        finish_build(h);
+                        int const rc = fold_check(h);
+                        if ( rc ) return rc;
+                        if ( h->fold.nranks != n || h->fold.rank != r || ! h->fold.local[r] )
+                                return fail(h, REAL_GPU_E_ARG, "fold_unique_group: handles[r] must be rank r of a group connected with real_gpu_fold_connect_local");
+                        if ( h->nreads != handles[0]->nreads ) return fail(h, REAL_GPU_E_ARG, "fold_unique_group: the ranks hold different read sets");
+                }
+                // everybody pushes, then everybody merges what it was sent: the streams wait for each other through events
+                for ( uint32_t r = 0; r < n; ++r )
+                {
+                        h = handles[r];
+                        RG_CUDA(cudaSetDevice(h->prm.device));
+                        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+                        fold_push(h, 0);
+                        RG_CUDA(cudaEventRecord(h->fold.ev, h->st));
+                }
+                for ( uint32_t r = 0; r < n; ++r )
+                {
+                        h = handles[r];
+                        RG_CUDA(cudaSetDevice(h->prm.device));
+                        for ( uint32_t q = 0; q < n; ++q )
+                                if ( q != r ) RG_CUDA(cudaStreamWaitEvent(h->st, handles[q]->fold.ev, 0));
+                        fold_merge(h, 0);
+                        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+                }
+                for ( uint32_t r = 0; r < n; ++r )
+                {
+                        h = handles[r];
+                        RG_CUDA(cudaSetDevice(h->prm.device));
+                        RG_CUDA(cudaStreamSynchronize(h->st));
+                        h->stats.fold_ms = elapsed(h->ev[0], h->ev[1]);
+                }
+        }
+        catch ( std::exception const & e ) { return fail(h, REAL_GPU_E_CUDA, e.what()); }
+        return REAL_GPU_OK;
 }
 
 int real_gpu_get_stats(real_gpu * h, real_gpu_stats * out)

@@ -19,6 +19,8 @@
 //   k_part_offsets  bucket starts (padded to whole work units) + sentinel records in the padding
 //   k_part_scatter  TMA-staged text tiles -> 16-byte records {window word, the 16 bases in front of it,
 //                   position} grouped by bucket (staged in shared memory, written run by run)
+//   k_own_list      bucket shards (multi-GPU): the positions whose bucket this rank owns, as a dense list + their
+//                   bucket histogram in one pass; k_part_scatter<true> then forms the records of the list
 //   k_bucket_probe  warps pull 512-record grabs in bucket order and walk them 64 records at a time:
 //                   6 independent 4-byte probes per lane; set slot bits are compacted
 //                   into the warp's shared-memory queue (stage A: rank -> entry chain -> seed test ->
@@ -112,6 +114,8 @@ struct ScanParams
         // own_b_cnt = SC_MAX_BUCKETS: no filter.
         uint32_t own_b_lo, own_b_cnt;
         uint32_t hist_pick_max;       // k_part_hist picks the kept positions out one by one when own_b_cnt <= this
+        uint32_t * list;              // bucket shard: positions (relative to pos_base) of the chunk this handle keeps
+        unsigned long long * list_count;
         unsigned long long * nprobed; // positions this handle has formed records of (statistics)
 };
 
@@ -416,13 +420,16 @@ struct ScatterSmem
         uint8_t stage_b[PS_TILE_POS];
 };
 
+// LIST: the positions come from the kept-position list of a bucket shard (k_own_list) instead of the text tiles
+template<bool LIST>
 __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
         ScatterSmem & S = *reinterpret_cast<ScatterSmem *>(sc_smem);
 
-        uint64_t const first_tile = P.x_begin / PS_TILE_POS;
-        uint64_t const end_tile = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
+        uint64_t const nlist = LIST ? *P.list_count : 0;
+        uint64_t const first_tile = LIST ? 0 : P.x_begin / PS_TILE_POS;
+        uint64_t const end_tile = LIST ? (nlist + PS_TILE_POS - 1) / PS_TILE_POS : (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
         uint32_t const bbits = P.bucket_bits;
         uint32_t const bsh = 64 - (bbits ? bbits : 1);
         uint32_t const bmask = bbits ? 0xFFFFFFFFu : 0u;
@@ -430,7 +437,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         uint32_t const lt = (1u << lane) - 1;
 
-        if ( threadIdx.x == 0 )
+        if ( ! LIST && threadIdx.x == 0 )
         {
                 mbar_init(&S.bar[0], 1);
                 mbar_init(&S.bar[1], 1);
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
         __syncthreads();
 
         uint64_t tile_id = first_tile + blockIdx.x;
-        if ( threadIdx.x == 0 && tile_id < end_tile )
+        if ( ! LIST && threadIdx.x == 0 && tile_id < end_tile )
         {
                 mbar_expect_tx(&S.bar[0], PS_SMEM_WORDS * 8);
                 bulk_load(&S.tile[0][0], P.text + (int64_t)tile_id * PS_TILE_WORDS - SC_HALO, PS_SMEM_WORDS * 8, &S.bar[0]);
@@ -450,30 +457,61 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
 
         for ( uint32_t it = 0; tile_id < end_tile; tile_id += gridDim.x, ++it )
         {
-                uint32_t const buf = it & 1;
-                uint64_t const next_tile = tile_id + gridDim.x;
-                if ( threadIdx.x == 0 && next_tile < end_tile )
+                // the PS_PPT positions of this thread: window word v, the 32 bases in front of it, position field, validity mask m
+                uint64_t wv[PS_PPT];
+                uint32_t wbefore[PS_PPT], wpos[PS_PPT];
+                uint32_t m;
+                uint32_t pos0;
+                if constexpr ( LIST )
                 {
-                        mbar_expect_tx(&S.bar[buf ^ 1], PS_SMEM_WORDS * 8);
-                        bulk_load(&S.tile[buf ^ 1][0], P.text + (int64_t)next_tile * PS_TILE_WORDS - SC_HALO, PS_SMEM_WORDS * 8, &S.bar[buf ^ 1]);
-                }
-                mbar_wait(&S.bar[buf], (it >> 1) & 1);
-                uint64_t const tile_x0 = tile_id * PS_TILE_POS;
-                uint32_t const wi = threadIdx.x / PS_TPW, j0 = (threadIdx.x % PS_TPW) * PS_PPT;
-                uint64_t const wm = S.tile[buf][SC_HALO + wi - 1], w0 = S.tile[buf][SC_HALO + wi], w1 = S.tile[buf][SC_HALO + wi + 1];
-                uint32_t const m = (clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end) >> j0) & (uint32_t)((1ull << PS_PPT) - 1);
-
-                // (1) per-warp bucket counts (reductions without return value)
-                {
-                        uint32_t mm = m;
-                        while ( mm )
+                        uint64_t const i0 = tile_id * PS_TILE_POS + (uint64_t)threadIdx.x * PS_PPT;
+                        m = 0;
+                        pos0 = 0;
+                        #pragma unroll
+                        for ( uint32_t u = 0; u < PS_PPT; ++u )
                         {
-                                uint32_t const j = j0 + __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                atomicAdd(&S.wcnt[wid][(uint32_t)(v >> bsh) & bmask], 1u);
+                                bool const ok = i0 + u < nlist;
+                                uint32_t const p = ok ? __ldcs(P.list + i0 + u) : 0u;
+                                uint64_t const lx = P.pos_base + p;
+                                const uint64_t * tw = P.text + (lx >> 5);
+                                uint32_t const j = (uint32_t)(lx & 31);
+                                uint64_t const wm = __ldg(tw - 1), w0 = __ldg(tw), w1 = __ldg(tw + 1);
+                                wv[u] = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                wbefore[u] = (uint32_t)(j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm);
+                                wpos[u] = p;
+                                m |= (ok ? 1u : 0u) << u;
                         }
                 }
+                else
+                {
+                        uint32_t const buf = it & 1;
+                        uint64_t const next_tile = tile_id + gridDim.x;
+                        if ( threadIdx.x == 0 && next_tile < end_tile )
+                        {
+                                mbar_expect_tx(&S.bar[buf ^ 1], PS_SMEM_WORDS * 8);
+                                bulk_load(&S.tile[buf ^ 1][0], P.text + (int64_t)next_tile * PS_TILE_WORDS - SC_HALO, PS_SMEM_WORDS * 8, &S.bar[buf ^ 1]);
+                        }
+                        mbar_wait(&S.bar[buf], (it >> 1) & 1);
+                        uint64_t const tile_x0 = tile_id * PS_TILE_POS;
+                        uint32_t const wi = threadIdx.x / PS_TPW, j0 = (threadIdx.x % PS_TPW) * PS_PPT;
+                        uint64_t const wm = S.tile[buf][SC_HALO + wi - 1], w0 = S.tile[buf][SC_HALO + wi], w1 = S.tile[buf][SC_HALO + wi + 1];
+                        m = (clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end) >> j0) & (uint32_t)((1ull << PS_PPT) - 1);
+                        pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums below do not
+                        #pragma unroll
+                        for ( uint32_t u = 0; u < PS_PPT; ++u )
+                        {
+                                uint32_t const j = j0 + u;
+                                wv[u] = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
+                                wbefore[u] = (uint32_t)(j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm);       // the 16 bases that end in front of the window
+                                wpos[u] = wi * 32 + j;
+                        }
+                }
+
+                // (1) per-warp bucket counts (reductions without return value)
+                #pragma unroll
+                for ( uint32_t u = 0; u < PS_PPT; ++u )
+                        if ( (m >> u) & 1 )
+                                atomicAdd(&S.wcnt[wid][(uint32_t)(wv[u] >> bsh) & bmask], 1u);
                 __syncthreads();
                 // (2) bucket b (thread b): totals -> staging layout, global run reservation, per-warp running slots
                 uint32_t bstart = 0, reserved = 0;       // basev = bstart + reserved, summed only where it is needed (see below)
@@ -505,22 +543,19 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 __syncthreads();
                 // (3) warp multisplit: one position per lane and step; the group leader advances the warp's slot counter.
                 // The matches of four steps are issued together: their result latency is what this phase waits for.
-                #pragma unroll 1
+                #pragma unroll
                 for ( uint32_t jb = 0; jb < PS_PPT; jb += 4 )
                 {
-                        uint64_t v[4]; uint32_t b[4], peers[4];
+                        uint32_t b[4], peers[4];
                         #pragma unroll
                         for ( uint32_t u = 0; u < 4; ++u )
                         {
-                                uint32_t const j = j0 + jb + u;
-                                v[u] = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                                b[u] = (uint32_t)(v[u] >> bsh) & bmask;
+                                b[u] = (uint32_t)(wv[jb + u] >> bsh) & bmask;
                                 peers[u] = peers_u8(b[u], (m >> (jb + u)) & 1);
                         }
                         #pragma unroll
                         for ( uint32_t u = 0; u < 4; ++u )
                         {
-                                uint32_t const j = j0 + jb + u;
                                 bool const ok = (m >> (jb + u)) & 1;
                                 uint32_t const below = __popc(peers[u] & lt);
                                 uint32_t pre = 0;
@@ -531,9 +566,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                                 if ( ok )
                                 {
                                         uint32_t const slot = pre + below;
-                                        uint64_t const win = v[u] >> fsh;
-                                        uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;       // the 32 bases that end in front of the window
-                                        S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, wi * 32 + j);
+                                        uint64_t const win = wv[jb + u] >> fsh;
+                                        S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), wbefore[jb + u], wpos[jb + u]);
                                         S.stage_b[slot] = (uint8_t)b[u];
                                 }
                         }
@@ -545,7 +579,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                 // one dependent shared-memory load each
                 {
                         uint32_t const n = S.loc[SC_MAX_BUCKETS];
-                        uint32_t const pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums below do not
                         uint32_t i = threadIdx.x;
                         for ( ; i + 3 * SC_THREADS < n; i += 4 * SC_THREADS )
                         {
@@ -572,261 +605,64 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
 }
 
 // ---- partition of a bucket shard -------------------------------------------------------------------
-// The multi-GPU form of the scatter pass when the tables are sharded by bucket and every GPU holds the whole text
-// (real_gpu_set_bucket_shard): the CTA reads EVERY position of its text tiles but keeps only those whose bucket
-// belongs to this handle, 1/nranks of them.  Testing a position costs about one instruction (kept_positions: bit
-// sliced over the 32 positions of a text word); what is expensive is the ranking and the staged copy-out, so the
-// kept positions are first compacted into a shared-memory list of descriptors (bucket << 24 | position inside the
-// super tile) and the list is ranked and written out 2048 descriptors at a time with full warps, like a tile of
-// k_part_scatter.  No record crosses NVLink: the only exchange of a bucket-sharded scan is the fold of the per-read
-// results at its end.
-#ifndef REAL_PF_THREADS
-#define REAL_PF_THREADS 256
-#endif
-#ifndef REAL_PF_BATCH
-#define REAL_PF_BATCH 2048
-#endif
-static const int PF_THREADS = REAL_PF_THREADS;
-static const int PF_SUPER_WORDS = 2048;                       // text words per super tile
-static const int PF_SUPER_POS = PF_SUPER_WORDS * 32;          // 65536 positions: 16 bits of a descriptor
-static const int PF_SMEM_WORDS = PF_SUPER_WORDS + 2 * SC_HALO;
-static const int PF_BATCH = REAL_PF_BATCH;                    // descriptors ranked and written out at a time
-static const int PF_DPT = PF_BATCH / PF_THREADS;              // per thread
-static const int PF_LIST_CAP = 3 * PF_BATCH;
-static const int PF_PIECE_WORDS = PF_BATCH / 32;              // a piece of a step whose kept positions always fit into the list
+// The multi-GPU form of the partition when the tables are sharded by bucket and every GPU holds the whole text
+// (real_gpu_set_bucket_shard): the rank reads EVERY position of the chunk but keeps only those whose bucket belongs
+// to it, 1/nranks of them.  Testing a position costs about one instruction (kept_positions: bit sliced over the 32
+// positions of a text word); ranking and staging a record is what is expensive.  So one light pass (k_own_list) writes
+// the kept positions as a dense list of 4-byte descriptors and counts them per bucket on the way -- no separate
+// histogram pass -- and the staged scatter kernel then runs on the list (k_part_scatter<true>) at its usual cost per
+// record.  No record crosses NVLink: the only exchange of a bucket-sharded scan is the fold of the per-read results.
+static const int OL_THREADS = 256;
+static const int OL_WPT = 4;                                  // consecutive text words per thread and tile
+static const int OL_TILE_WORDS = OL_THREADS * OL_WPT;
+static const int OL_TILE_POS = OL_TILE_WORDS * 32;            // 32768 positions
 
-struct OwnScatterSmem
+__global__ void __launch_bounds__(OL_THREADS) k_own_list(ScanParams P)
 {
-        uint4 stage[PF_BATCH];
-        uint64_t tile[PF_SMEM_WORDS];
-        uint64_t bar;
-        uint32_t list[PF_LIST_CAP];
-        uint32_t wcnt[PF_THREADS / 32][SC_MAX_BUCKETS];
-        uint32_t loc[SC_MAX_BUCKETS + 1];
-        uint32_t base[SC_MAX_BUCKETS];
-        uint32_t add[4];
-        uint8_t stage_b[PF_BATCH];
-};
-
-// ranks the descriptors list[first, first+n), n <= PF_BATCH, and writes their records; all threads of the CTA
-__device__ __forceinline__ void own_flush(ScanParams const & P, OwnScatterSmem & S, const uint64_t * __restrict__ tw, uint32_t first, uint32_t n,
-                                          uint32_t pos0, uint32_t fsh)
-{
-        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        uint32_t const lt = (1u << lane) - 1;
-        uint32_t d[PF_DPT];
-        #pragma unroll
-        for ( int k = 0; k < PF_DPT; ++k )
-        {
-                uint32_t const i = (uint32_t)k * PF_THREADS + threadIdx.x;
-                d[k] = (i < n) ? S.list[first + i] : 0xFFFFFFFFu;
-                if ( i < n ) atomicAdd(&S.wcnt[wid][d[k] >> 24], 1u);
-        }
+        __shared__ uint32_t cnt[SC_MAX_BUCKETS];
+        __shared__ unsigned long long tile_base;
+        cnt[threadIdx.x] = 0;
         __syncthreads();
-        uint32_t bstart = 0, reserved = 0;   // their sum = first record of the batch's run in bucket threadIdx.x: needed at the copy-out
-                                             // only, so the global atomic that reserves the run is in flight while the batch is ranked
+        uint64_t const first_tile = P.x_begin / OL_TILE_POS;
+        uint64_t const end_tile = (P.x_end + OL_TILE_POS - 1) / OL_TILE_POS;
+        for ( uint64_t tile_id = first_tile + blockIdx.x; tile_id < end_tile; tile_id += gridDim.x )
         {
-                uint32_t tot = 0;
-                if ( threadIdx.x < SC_MAX_BUCKETS )
+                uint64_t const w0i = tile_id * OL_TILE_WORDS + (uint64_t)threadIdx.x * OL_WPT;
+                uint64_t w[OL_WPT + 1];
+                #pragma unroll
+                for ( int k = 0; k <= OL_WPT; ++k ) w[k] = __ldg(P.text + w0i + k);
+                uint64_t eq[OL_WPT];
+                uint32_t c = 0;
+                #pragma unroll
+                for ( int k = 0; k < OL_WPT; ++k )
                 {
-                        #pragma unroll
-                        for ( int w = 0; w < PF_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                        eq[k] = kept_positions_clipped(w[k], w[k+1], P.own_b_lo, P.own_b_cnt, (w0i + k) * 32, P.x_begin, P.x_end);
+                        c += (uint32_t)__popcll(eq[k]);
                 }
-                uint32_t blocktot;
-                uint32_t const ex = block_excl_scan(tot, &blocktot);
-                if ( threadIdx.x < SC_MAX_BUCKETS )
+                uint32_t total;
+                uint32_t const ex = block_excl_scan(c, &total);
+                if ( threadIdx.x == 0 && total ) tile_base = atomicAdd(P.list_count, (unsigned long long)total);
+                __syncthreads();
+                if ( ! total ) continue;
+                uint32_t * out = P.list + tile_base + ex;
+                #pragma unroll
+                for ( int k = 0; k < OL_WPT; ++k )
                 {
-                        S.loc[threadIdx.x] = ex;
-                        if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
-                        if ( tot )
+                        uint64_t e = eq[k];
+                        uint32_t const p0 = (uint32_t)((w0i + k) * 32 - P.pos_base);
+                        while ( e )
                         {
-                                bstart = P.bucket_start[threadIdx.x];
-                                reserved = atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot);
-                        }
-                        uint32_t run = ex;
-                        #pragma unroll
-                        for ( int w = 0; w < PF_THREADS / 32; ++w )
-                        {
-                                uint32_t const c = S.wcnt[w][threadIdx.x];
-                                S.wcnt[w][threadIdx.x] = run;
-                                run += c;
+                                uint32_t const j = (uint32_t)__clzll(e) >> 1;
+                                e &= ~(0x8000000000000000ULL >> (2 * j));
+                                uint64_t const v = j ? ((w[k] << (2*j)) | (w[k+1] >> (64 - 2*j))) : w[k];
+                                *out++ = p0 + j;
+                                atomicAdd(&cnt[(uint32_t)(v >> 56)], 1u);
                         }
                 }
+                __syncthreads();           // tile_base is free again
         }
         __syncthreads();
-        // buckets of an aligned power-of-two range differ in their low bits only
-        uint32_t const vbits = ((P.own_b_cnt & (P.own_b_cnt - 1)) == 0 && (P.own_b_lo & (P.own_b_cnt - 1)) == 0) ? (uint32_t)(31 - __clz(P.own_b_cnt)) : 8u;
-        uint32_t peers[PF_DPT];
-        #pragma unroll
-        for ( uint32_t u = 0; u < PF_DPT; ++u )
-                peers[u] = peers_low(d[u] >> 24, d[u] != 0xFFFFFFFFu, vbits);
-        #pragma unroll
-        for ( uint32_t u = 0; u < PF_DPT; ++u )
-        {
-                uint32_t const dd = d[u];
-                bool const ok = dd != 0xFFFFFFFFu;
-                uint32_t const b = dd >> 24;
-                uint32_t const below = __popc(peers[u] & lt);
-                uint32_t pre = 0;
-                if ( ok ) pre = S.wcnt[wid][b];
-                __syncwarp();
-                if ( ok && below == 0 ) S.wcnt[wid][b] = pre + __popc(peers[u]);
-                __syncwarp();
-                if ( ok )
-                {
-                        uint32_t const slot = pre + below;
-                        uint32_t const p = dd & 0xFFFFFFu, wi = p >> 5, j = p & 31;
-                        uint64_t const wm = tw[(int)wi - 1], w0 = tw[wi], w1 = tw[wi + 1];
-                        uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                        uint64_t const win = v >> fsh;
-                        uint64_t const before = j ? ((wm << (2*j)) | (w0 >> (64 - 2*j))) : wm;
-                        S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), (uint32_t)before, p + pos0);
-                        S.stage_b[slot] = (uint8_t)b;
-                }
-        }
-        if ( threadIdx.x < SC_MAX_BUCKETS ) S.base[threadIdx.x] = bstart + reserved - S.loc[threadIdx.x];     // + staging slot = record index (mod 2^32)
-        __syncthreads();
-        {
-                uint32_t const m = S.loc[SC_MAX_BUCKETS];
-                uint32_t i = threadIdx.x;
-                for ( ; i + 3 * PF_THREADS < m; i += 4 * PF_THREADS )
-                {
-                        uint32_t o[4]; uint4 r[4];
-                        #pragma unroll
-                        for ( int u = 0; u < 4; ++u ) { o[u] = S.stage_b[i + u * PF_THREADS]; r[u] = S.stage[i + u * PF_THREADS]; }
-                        #pragma unroll
-                        for ( int u = 0; u < 4; ++u ) o[u] = S.base[o[u]] + (i + u * PF_THREADS);
-                        #pragma unroll
-                        for ( int u = 0; u < 4; ++u ) P.recs[o[u]] = r[u];
-                }
-                for ( ; i < m; i += PF_THREADS )
-                        P.recs[S.base[S.stage_b[i]] + i] = S.stage[i];
-        }
-        #pragma unroll
-        for ( int w = threadIdx.x >> 8; w < PF_THREADS / 32; w += PF_THREADS / 256 ) S.wcnt[w][threadIdx.x & 255] = 0;     // read last before the barrier above
-        __syncthreads();
-}
-
-// appends the kept positions eq of text word wi to the list from slot o on
-__device__ __forceinline__ void own_append(OwnScatterSmem & S, uint64_t eq, uint64_t w0, uint64_t w1, uint32_t wi, uint32_t o)
-{
-        while ( eq )
-        {
-                uint32_t const j = (uint32_t)__clzll(eq) >> 1;
-                eq &= ~(0x8000000000000000ULL >> (2 * j));
-                uint64_t const v = j ? ((w0 << (2*j)) | (w1 >> (64 - 2*j))) : w0;
-                S.list[o++] = ((uint32_t)(v >> 56) << 24) | (wi * 32 + j);
-        }
-}
-
-// step_words = text words handled between two barriers (PF_THREADS / 1, 2, 4 or 8, a multiple of PF_PIECE_WORDS that
-// divides PF_SUPER_WORDS): chosen by the host so that a step is expected to keep about PF_BATCH positions
-__global__ void __launch_bounds__(PF_THREADS) k_part_scatter_own(ScanParams P, uint32_t step_words)
-{
-        extern __shared__ __align__(128) unsigned char sc_smem[];
-        OwnScatterSmem & S = *reinterpret_cast<OwnScatterSmem *>(sc_smem);
-
-        uint64_t const first_tile = P.x_begin / PF_SUPER_POS;
-        uint64_t const end_tile = (P.x_end + PF_SUPER_POS - 1) / PF_SUPER_POS;
-        uint32_t const fsh = 64 - 2 * P.seedl;
-        int const lane = threadIdx.x & 31;
-
-        if ( threadIdx.x == 0 )
-        {
-                mbar_init(&S.bar, 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                S.add[0] = S.add[1] = S.add[2] = S.add[3] = 0;
-        }
-        for ( int w = threadIdx.x >> 8; w < PF_THREADS / 32; w += PF_THREADS / 256 ) S.wcnt[w][threadIdx.x & 255] = 0;
-        __syncthreads();
-        uint32_t n = 0;          // descriptors in the list (CTA uniform)
-        uint32_t gstep = 0;      // steps so far
-        unsigned long long kept = 0;
-        const uint64_t * tw = &S.tile[SC_HALO];
-        uint32_t const nsteps = PF_SUPER_WORDS / step_words;
-        uint32_t const lanes_per_word = PF_THREADS / step_words, ppt = 32 / lanes_per_word;
-        uint64_t const sub_mask = ppt == 32 ? ~0ULL : ~(~0ULL >> (2 * ppt));         // the first ppt positions of a word (two bits each, first position on top)
-
-        uint32_t it = 0;
-        for ( uint64_t tile_id = first_tile + blockIdx.x; tile_id < end_tile; tile_id += gridDim.x, ++it )
-        {
-                // one text buffer: a super tile is 16 KB and is worked on for tens of microseconds, the load is not worth hiding
-                if ( threadIdx.x == 0 )
-                {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_expect_tx(&S.bar, PF_SMEM_WORDS * 8);
-                        bulk_load(&S.tile[0], P.text + (int64_t)tile_id * PF_SUPER_WORDS - SC_HALO, PF_SMEM_WORDS * 8, &S.bar);
-                }
-                mbar_wait(&S.bar, it & 1);
-                uint64_t const tile_x0 = tile_id * PF_SUPER_POS;
-                uint32_t const pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums do not
-
-                for ( uint32_t step = 0; step < nsteps; ++step, ++gstep )
-                {
-                        // one text word = 32 positions per thread; the kept ones are appended to the list with one shared-memory
-                        // atomic per warp.  The additions of a step are summed in one of three rotating counters (the one of the
-                        // next step is cleared here), so a step costs one barrier; the list length n is CTA uniform.
-                        // G = PF_THREADS / step_words threads share a text word, each takes 32 / G of its positions: whatever
-                        // fraction of the positions a rank keeps, the whole CTA tests and appends
-                        bool const active = true;
-                        uint32_t const wi = step * step_words + threadIdx.x / lanes_per_word;
-                        uint64_t const w0 = tw[wi], w1 = tw[wi + 1];
-                        uint64_t const eq = kept_positions_clipped(w0, w1, P.own_b_lo, P.own_b_cnt, tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end)
-                                            & (sub_mask >> (2 * ppt * (threadIdx.x % lanes_per_word)));
-                        uint32_t const c = (uint32_t)__popcll(eq);
-                        uint32_t const incl = warp_incl_scan(c, lane);
-                        uint32_t wbase = 0;
-                        if ( lane == 31 && incl ) wbase = atomicAdd(&S.add[gstep % 3], incl);
-                        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                        if ( threadIdx.x == 0 ) S.add[(gstep + 1) % 3] = 0;
-                        __syncthreads();
-                        uint32_t const T = S.add[gstep % 3];
-                        if ( n + T <= (uint32_t)PF_LIST_CAP )
-                        {
-                                own_append(S, eq, w0, w1, wi, n + wbase + incl - c);
-                                n += T;
-                        }
-                        else
-                        {
-                                // far more positions kept than expected (a text that falls into few buckets): piece by piece
-                                for ( uint32_t piece = 0; piece < step_words / PF_PIECE_WORDS; ++piece )
-                                {
-                                        __syncthreads();
-                                        if ( threadIdx.x == 0 ) S.add[3] = 0;
-                                        __syncthreads();
-                                        bool const mine = active && (threadIdx.x / lanes_per_word) / PF_PIECE_WORDS == piece;
-                                        uint32_t const c2 = mine ? c : 0;
-                                        uint32_t const incl2 = warp_incl_scan(c2, lane);
-                                        uint32_t wb2 = 0;
-                                        if ( lane == 31 && incl2 ) wb2 = atomicAdd(&S.add[3], incl2);
-                                        wb2 = __shfl_sync(0xffffffffu, wb2, 31);
-                                        if ( mine ) own_append(S, eq, w0, w1, wi, n + wb2 + incl2 - c2);
-                                        __syncthreads();
-                                        n += S.add[3];
-                                        while ( n >= (uint32_t)PF_BATCH )
-                                        {
-                                                own_flush(P, S, tw, n - PF_BATCH, PF_BATCH, pos0, fsh);
-                                                kept += (threadIdx.x == 0) ? PF_BATCH : 0;
-                                                n -= PF_BATCH;
-                                        }
-                                }
-                        }
-                        bool const last = step + 1 == nsteps;
-                        if ( n >= (uint32_t)PF_BATCH || (last && n) )
-                        {
-                                __syncthreads();
-                                while ( n >= (uint32_t)PF_BATCH || (last && n) )
-                                {
-                                        uint32_t const take = min(n, (uint32_t)PF_BATCH);
-                                        own_flush(P, S, tw, n - take, take, pos0, fsh);
-                                        kept += (threadIdx.x == 0) ? take : 0;
-                                        n -= take;
-                                }
-                        }
-                }
-                __syncthreads();         // everybody is done with the text buffer
-        }
-        if ( threadIdx.x == 0 && kept ) atomicAdd(P.nprobed, kept);
+        if ( cnt[threadIdx.x] ) atomicAdd(P.bucket_count + threadIdx.x, cnt[threadIdx.x]);
 }
 
 // one block: bucket starts (every bucket padded to whole grabs), cursors, sentinel records in the padding.
@@ -849,6 +685,7 @@ __global__ void __launch_bounds__(SC_MAX_BUCKETS) k_part_offsets(ScanParams P)
                 }
                 st[SC_MAX_BUCKETS] = a;            // single rank: the total (all buckets are in one area)
                 *P.unit_counter = 0;
+                if ( P.own_b_cnt < SC_MAX_BUCKETS && P.list_count ) atomicAdd(P.nprobed, *P.list_count);
         }
         __syncthreads();
         uint32_t const owner = bucket_owner(P, threadIdx.x);

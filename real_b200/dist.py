@@ -66,6 +66,44 @@ def unique_exchange(shard, group: Optional[dist.ProcessGroup] = None, keys: Opti
     shard.import_merged(keys, ties)
 
 
+def connect_fold(handle, device: torch.device, max_reads: int, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Sets up the peer-memory fold of the unique state (include/real_gpu.h, real_gpu_fold_*) between the ranks of `group`:
+    every rank allocates its window, the 64-byte CUDA IPC handles travel over torch.distributed, the peers' windows are
+    mapped.  Afterwards fold_unique(handle) replaces unique_exchange: ONE exchange over NVLink peer stores instead of two
+    NCCL all-reduces, in reduce-scatter form -- rank r ends up with the merged words of the reads [R r / N, R (r+1) / N)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = handle.fold_init(rank, world, max_reads)
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    handle.fold_connect(b"".join(bytes(p.cpu().tolist()) for p in parts))
+    dist.barrier(group=group)
+
+
+def own_read_range(nreads: int, rank: int, world: int):
+    """The reads whose merged state rank `rank` holds after fold_unique (real_gpu_fold_unique)."""
+    return (nreads * rank) // world, (nreads * (rank + 1)) // world
+
+
+def fold_reduce_scatter_reference(words_by_rank, rank: int):
+    """numpy restatement of real_gpu_fold_unique for the CPU tests: the merged UniqueMatchInfo words of rank `rank`'s own
+    reads from the state words of all ranks (k_fold_merge, csrc/post.cuh; the rule of unique_exchange in one pass)."""
+    import numpy as np
+    from . import matcher as _m
+    world = len(words_by_rank)
+    n = len(words_by_rank[0])
+    lo, hi = own_read_range(n, rank, world)
+    keys = np.stack([_m.unique_key(np.asarray(w[lo:hi], dtype=np.uint64)) for w in words_by_rank])
+    win = keys.min(axis=0)
+    same = (((keys ^ win[None, :]) >> 17) & ((1 << 41) - 1)) == 0
+    ties = ((keys != UNIQUE_KEY_NONE) & ((keys >> 59) == (win >> 59)[None, :]) & ~same).sum(axis=0)
+    out = np.asarray(words_by_rank[rank][lo:hi], dtype=np.uint64).copy()
+    hit = win != UNIQUE_KEY_NONE
+    out[hit] = _m.unique_word_from_key(win, ties)[hit]
+    return out
+
+
 def connect_sharded_tables(handle, device: torch.device, round_positions: int = 0, group: Optional[dist.ProcessGroup] = None) -> None:
     """Puts `handle` (this rank's real_gpu handle) into sharded-table mode with all ranks of `group`: allocates the
     rank's window, exchanges the CUDA IPC handles (64 bytes per rank) and maps the peers' windows.  Call before

@@ -34,7 +34,7 @@ class Stats(C.Structure):
                 ("scan_ms", C.c_float), ("post_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("scan_launches", C.c_uint32), ("total_launches", C.c_uint32),
                 ("n_windows", C.c_uint64), ("n_probes", C.c_uint64), ("n_candidates", C.c_uint64),
-                ("n_seedpass", C.c_uint64), ("n_hits", C.c_uint64)]
+                ("n_seedpass", C.c_uint64), ("n_hits", C.c_uint64), ("fold_ms", C.c_float), ("reserved", C.c_float)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -98,6 +98,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_get_unique.argtypes = [vp, vp, vp]
     L.real_gpu_get_unique_range.argtypes = [vp, u64, u64, vp, vp]
     L.real_gpu_reset_unique.argtypes = [vp]
+    L.real_gpu_unique_checksum.argtypes = [vp, u64, u64, C.POINTER(u64)]
     L.real_gpu_set_block_windows.argtypes = [vp, u64]
     L.real_gpu_unique_export_keys.argtypes = [vp, vp]
     L.real_gpu_unique_export_ties.argtypes = [vp, vp, vp]
@@ -108,6 +109,11 @@ def load(build_if_missing: bool = True):
     L.real_gpu_comm_connect.argtypes = [vp, vp]
     L.real_gpu_comm_connect_local.argtypes = [vp, vp]
     L.real_gpu_set_reads_packed_device.argtypes = [vp, vp, u32, vp, vp, u64]
+    L.real_gpu_fold_init.argtypes = [vp, u32, u32, u64, vp]
+    L.real_gpu_fold_connect.argtypes = [vp, vp]
+    L.real_gpu_fold_connect_local.argtypes = [vp, vp]
+    L.real_gpu_fold_unique.argtypes = [vp]
+    L.real_gpu_fold_unique_group.argtypes = [vp, u32]
     L.real_gpu_set_bucket_shard.argtypes = [vp, u32, u32]
     L.real_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.real_gpu_stream.argtypes = [vp]
@@ -268,6 +274,13 @@ class Handle:
         self._check(self.L.real_gpu_get_unique_range(self.h, first, count, info.ctypes.data, sc.ctypes.data if sc is not None else None))
         return info, sc
 
+    def unique_checksum(self, first: int = 0, count: int | None = None) -> int:
+        """Digest of the canonical unique state of the reads [first, first+count) (matcher.unique_checksum is the numpy form)."""
+        count = self.nreads - first if count is None else count
+        v = C.c_uint64()
+        self._check(self.L.real_gpu_unique_checksum(self.h, first, count, C.byref(v)))
+        return int(v.value)
+
     def reset_unique(self):
         self._check(self.L.real_gpu_reset_unique(self.h))
 
@@ -300,6 +313,32 @@ class Handle:
     def comm_connect_local(self, peers):
         arr = (C.c_void_p * len(peers))(*[p.h for p in peers])
         self._check(self.L.real_gpu_comm_connect_local(self.h, arr))
+
+    # ---- peer-memory fold of the unique state (one handle per rank)
+    def fold_init(self, rank: int, nranks: int, max_reads: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.L.real_gpu_fold_init(self.h, rank, nranks, max_reads, buf))
+        return buf.raw
+
+    def fold_connect(self, all_handles: bytes):
+        self._check(self.L.real_gpu_fold_connect(self.h, all_handles))
+
+    def fold_connect_local(self, peers):
+        arr = (C.c_void_p * len(peers))(*[p.h for p in peers])
+        self._check(self.L.real_gpu_fold_connect_local(self.h, arr))
+
+    def fold_unique(self):
+        """Collective (one process per GPU): afterwards this rank holds the merged words of its own 1/nranks of the reads."""
+        self._check(self.L.real_gpu_fold_unique(self.h))
+
+    @staticmethod
+    def fold_unique_group(handles):
+        """The ranks of one process: handles[r] = rank r."""
+        arr = (C.c_void_p * len(handles))(*[p.h for p in handles])
+        rc = handles[0].L.real_gpu_fold_unique_group(arr, len(handles))
+        if rc != 0:
+            msgs = [p.L.real_gpu_last_error(p.h).decode() for p in handles]
+            raise RealGpuError(rc, "; ".join(m for m in msgs if m))
 
     def match_gaps(self, n_list: int = 0):
         self._check(self.L.real_gpu_match_gaps(self.h, n_list))

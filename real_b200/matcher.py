@@ -313,6 +313,29 @@ def umi_err(d): return ((np.asarray(d, dtype=np.uint64) >> np.uint64(41)) & np.u
 def umi_frag(d): return ((np.asarray(d, dtype=np.uint64) >> np.uint64(45)) & np.uint64(0xFFFF)).astype(np.int64)
 
 
+UNIQUE_KEY_NONE = 0x7FFFFFFFFFFFFFFF
+
+
+def unique_key(d) -> np.ndarray:
+    """The order-preserving key of the cross-shard fold (unique_key, csrc/post.cuh), as int64: err(4) | unique flag |
+    file(6) | pos(35) | strand | frag(16); NoMatch/Gapped = UNIQUE_KEY_NONE."""
+    st = umi_state(d)
+    key = (umi_err(d) << 59) | ((st != 4).astype(np.int64) << 58) | (umi_file(d) << 52) | (umi_pos(d) << 17) | \
+          ((st == 2).astype(np.int64) << 16) | umi_frag(d)
+    key[(st == 0) | (st == 3)] = UNIQUE_KEY_NONE
+    return key.astype(np.int64)
+
+
+def unique_word_from_key(key, tie_sums) -> np.ndarray:
+    """UniqueMatchInfo words of the winning keys (k_unique_import / k_fold_merge, csrc/post.cuh); entries whose key is
+    UNIQUE_KEY_NONE are meaningless."""
+    key = np.asarray(key, dtype=np.int64)
+    uniq = (((key >> 58) & 1) == 1) & (np.asarray(tie_sums) == 0)
+    strand = (key >> 16) & 1
+    st = np.where(uniq, np.where(strand == 1, 2, 1), 4)
+    return (((key >> 17) & ((1 << 35) - 1)) | (((key >> 52) & 63) << 35) | ((key >> 59) << 41) | ((key & 0xFFFF) << 45) | (st << 61)).astype(np.uint64)
+
+
 def canonical_unique(d: np.ndarray) -> np.ndarray:
     """What is defined about a UniqueMatchInfo word independently of visiting order: everything for
     Straight/Reverse, (state, errors) for NonUnique (the reference leaves the position of whichever
@@ -323,3 +346,31 @@ def canonical_unique(d: np.ndarray) -> np.ndarray:
     d[non] &= np.uint64((7 << 61) | (15 << 41))
     d[st == 0] = 0
     return d
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def unique_checksum(info, first: int = 0) -> int:
+    """numpy form of real_gpu_unique_checksum: digest of the canonical state of reads first .. first+len(info)-1."""
+    d = canonical_unique(info)
+    idx = np.arange(first, first + d.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int(np.sum(_splitmix64(d ^ _splitmix64(idx)), dtype=np.uint64))
+
+
+def hits_checksum(hits) -> int:
+    """Order independent digest of matchAll rows (patid, pos, file, frag, k, inverted, score bits)."""
+    h = np.asarray(hits)
+    if h.size == 0:
+        return 0
+    with np.errstate(over="ignore"):
+        a = _splitmix64(h["patid"].astype(np.uint64)) ^ _splitmix64(h["pos"].astype(np.uint64) + np.uint64(0x1234567))
+        b = (h["file"].astype(np.uint64) << np.uint64(40)) | (h["frag"].astype(np.uint64) << np.uint64(8)) | (h["k"].astype(np.uint64) << np.uint64(1)) | h["inverted"].astype(np.uint64)
+        c = np.ascontiguousarray(h["score"]).view(np.uint32).astype(np.uint64)
+        return int(np.sum(_splitmix64(a ^ _splitmix64(b ^ (c << np.uint64(32)))), dtype=np.uint64))

@@ -44,12 +44,7 @@ def fold_hits(nreads, hits):
     return info
 
 
-def np_key(info):
-    st = matcher.umi_state(info)
-    key = (matcher.umi_err(info) << 59) | ((st != 4).astype(np.int64) << 58) | (matcher.umi_file(info) << 52) | (matcher.umi_pos(info) << 17) | \
-          ((st == 2).astype(np.int64) << 16) | matcher.umi_frag(info)
-    key[(st == 0) | (st == 3)] = NONE
-    return key.astype(np.int64)
+np_key = matcher.unique_key
 
 
 class NumpyShard:
@@ -92,6 +87,13 @@ class FakeHandle:
     def comm_connect(self, all_handles):
         self.got = all_handles
 
+    def fold_init(self, rank, nranks, max_reads):
+        self.fargs = (rank, nranks, max_reads)
+        return bytes([rank + 101]) * 64
+
+    def fold_connect(self, all_handles):
+        self.fgot = all_handles
+
 
 def _worker(rank, world, port, shard_infos, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -102,7 +104,17 @@ def _worker(rank, world, port, shard_infos, out_path):
         rdist.connect_sharded_tables(fh, torch.device("cpu"), round_positions=1 << 20)
         assert fh.args == (rank, world, 1 << 20)
         assert fh.got == b"".join(bytes([r + 1]) * 64 for r in range(world))       # the handles of all ranks, in rank order
+        rdist.connect_fold(fh, torch.device("cpu"), max_reads=1234)
+        assert fh.fargs == (rank, world, 1234)
+        assert fh.fgot == b"".join(bytes([r + 101]) * 64 for r in range(world))
         sh = NumpyShard(shard_infos[rank].copy())
+        # the reduce-scatter form of the fold (real_gpu_fold_unique): every rank sees the words of all ranks for ITS reads --
+        # here they travel by an all-gather over gloo -- and folds them in one pass
+        mine = torch.from_numpy(shard_infos[rank].view(np.int64).copy())
+        allw = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allw, mine)
+        own = rdist.fold_reduce_scatter_reference([w.numpy().view(np.uint64) for w in allw], rank)
+        np.save((out_path % rank) + ".own.npy", own)
         rdist.unique_exchange(sh)
         np.save(out_path % rank, sh.info)
     finally:
@@ -141,6 +153,9 @@ def test_unique_exchange_world2_gloo(tmp_path, split):
     for r in range(world):
         got = np.load(out % r)
         assert np.array_equal(matcher.canonical_unique(got), matcher.canonical_unique(want))
+    # the reduce-scatter form: the ranks' own ranges, put together, are the same state -- bit for bit what the all-reduce form gives
+    own = np.concatenate([np.load((out % r) + ".own.npy") for r in range(world)])
+    assert np.array_equal(own, np.load(out % 0))
 
 
 def _upload_worker(rank, world, port, out_path):

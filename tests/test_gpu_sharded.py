@@ -270,3 +270,149 @@ def test_sharded_two_processes_ipc():
     a, b = canon_hits(np.concatenate(parts)), canon_hits(ref)
     assert len(b) > 3000 and a.shape == b.shape and np.array_equal(a, b)
     assert all(len(p) for p in parts)
+
+
+# ---- peer-memory fold of the unique state (real_gpu_fold_*) ----------------------------------------------------------
+
+def _two_file_job(seed=41):
+    t0, reads0 = _fresh(seed, n=500_000, nreads=8000)
+    t1, reads1 = _fresh(seed + 2, n=300_000, nreads=4000, nrec=2)
+    sym = t1.symbols.copy()
+    sym[5000:45000] = t0.symbols[30000:70000]            # cross-file repeats
+    t1 = synth.Text(sym, t1.records)
+    reads = synth.concat_reads([reads0, reads1])
+    kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    info_ref, _ = O.unique_init(reads.nreads, False)
+    for fi, t in enumerate((t0, t1)):
+        O.match_unique(t, reads, info_ref, None, fileid=fi, **kw)
+    return (t0, t1), reads, kw, info_ref
+
+
+@pytest.mark.parametrize("nranks,packed", [(2, False), (3, True), (8, False)])
+def test_bucket_shards_fold_group_vs_oracle(nranks, packed):
+    """Bucket shards of ONE process folded with real_gpu_fold_unique_group (k_fold_push / k_fold_merge over peer pointers):
+    after every file rank r holds the merged words of its own reads; they must equal the oracle's words and the numpy
+    restatement of the fold (real_b200.dist.fold_reduce_scatter_reference) applied to the ranks' pre-fold states."""
+    from real_b200 import dist as rdist
+    from real_b200 import lib as rlib
+    texts, reads, kw, info_ref = _two_file_job()
+    ms = _bucket_ranks(matcher.UniqueMatcher, matcher.RealOptions(**kw), nranks)
+    R = reads.nreads
+    try:
+        for r, m in enumerate(ms):
+            m.handle.fold_init(r, nranks, R + 5)
+        for m in ms:
+            m.handle.fold_connect_local([x.handle for x in ms])
+        for m in ms:
+            if packed:
+                pk, boffs, lens, flags = synth.pack_reads_2bit(reads)
+                m.handle.set_reads_packed(pk, R, byte_offsets=boffs, lengths=lens, wildcard_flags=flags)
+            else:
+                m.set_reads(reads.mapped, reads.offsets, None)
+        for fi, t in enumerate(texts):
+            words, nmask = t.packed()
+            for m in ms:
+                m.set_text(words, nmask, t.n, t.record_starts, fileid=fi)
+                m.match()
+            before = [m.handle.get_unique()[0] for m in ms]
+            rlib.Handle.fold_unique_group([m.handle for m in ms])
+            for r, m in enumerate(ms):
+                lo, hi = rdist.own_read_range(R, r, nranks)
+                got, _ = m.handle.get_unique(first=lo, count=hi - lo)
+                assert np.array_equal(got, rdist.fold_reduce_scatter_reference(before, r)), (fi, r)
+        merged = np.concatenate([m.handle.get_unique(first=rdist.own_read_range(R, r, nranks)[0],
+                                                     count=rdist.own_read_range(R, r, nranks)[1] - rdist.own_read_range(R, r, nranks)[0])[0]
+                                 for r, m in enumerate(ms)])
+        fold_ms = [m.stats()["fold_ms"] for m in ms]
+    finally:
+        for m in ms:
+            m.close()
+    st = matcher.umi_state(info_ref)
+    assert (st == 4).sum() > 50 and (st == 1).sum() > 1000 and (st == 2).sum() > 1000
+    assert np.array_equal(matcher.canonical_unique(merged), matcher.canonical_unique(info_ref))
+    assert all(t > 0 for t in fold_ms)
+
+
+def test_fold_refusals():
+    from real_b200 import lib as rlib
+    text, reads = _fresh(79, n=200_000, nreads=1000)
+    words, nmask = text.packed()
+    m = matcher.UniqueMatcher(matcher.RealOptions(seedl=32, seedkmax=2, totalkmax=4, scores=False))
+    try:
+        m.set_reads(reads.mapped, reads.offsets, None)
+        m.set_text(words, nmask, text.n, text.record_starts)
+        m.match()
+        with pytest.raises(rlib.RealGpuError):           # never initialised
+            m.handle.fold_unique()
+        m.handle.fold_init(0, 2, 500)                    # sized for fewer reads than are set, and never connected
+        with pytest.raises(rlib.RealGpuError):
+            m.handle.fold_unique()
+        with pytest.raises(rlib.RealGpuError):
+            m.handle.fold_init(0, 2, 5000)               # twice
+    finally:
+        m.close()
+
+
+def _fold_ipc_rank(rank, nranks, conn, seed):
+    """One rank in its own process: bucket shard + fold window mapped with CUDA IPC, hand-over with device flags."""
+    import os
+    os.environ["REAL_GPU_COMM_TIMEOUT_MS"] = "60000"
+    from real_b200 import matcher as M
+    from real_b200 import dist as D
+    text, reads = _fresh(seed, n=400_000, nreads=6000)
+    m = M.UniqueMatcher(M.RealOptions(seedl=32, seedkmax=2, totalkmax=4, scores=False))
+    try:
+        m.handle.set_bucket_shard(rank, nranks)
+        conn.send(m.handle.fold_init(rank, nranks, reads.nreads))
+        m.handle.fold_connect(conn.recv())
+        m.set_reads(reads.mapped, reads.offsets, None)
+        words, nmask = text.packed()
+        m.set_text(words, nmask, text.n, text.record_starts)
+        conn.send("ready")
+        conn.recv()
+        outs = []
+        for _ in range(3):                               # three exchanges in a row: both staging areas are reused
+            m.match()
+            m.handle.fold_unique()
+            lo, hi = D.own_read_range(reads.nreads, rank, nranks)
+            outs.append(m.handle.get_unique(first=lo, count=hi - lo)[0])
+        conn.send(outs)
+        conn.recv()                 # keep the window mapped until every rank is done
+    finally:
+        m.close()
+
+
+def test_fold_two_processes_ipc():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    nranks, seed = 2, 57
+    pipes = [ctx.Pipe() for _ in range(nranks)]
+    procs = [ctx.Process(target=_fold_ipc_rank, args=(r, nranks, pipes[r][1], seed)) for r in range(nranks)]
+    for p in procs:
+        p.start()
+    try:
+        def get(c):
+            assert c.poll(240), "a rank process did not answer"
+            return c.recv()
+        handles = b"".join(get(pipes[r][0]) for r in range(nranks))
+        for r in range(nranks):
+            pipes[r][0].send(handles)
+        for r in range(nranks):
+            assert get(pipes[r][0]) == "ready"
+        for r in range(nranks):
+            pipes[r][0].send("go")
+        parts = [get(pipes[r][0]) for r in range(nranks)]
+        for r in range(nranks):
+            pipes[r][0].send("done")
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.terminate()
+    text, reads = _fresh(seed, n=400_000, nreads=6000)
+    want, _ = O.unique_init(reads.nreads, False)
+    O.match_unique(text, reads, want, None, seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    for it in range(3):
+        got = np.concatenate([parts[r][it] for r in range(nranks)])
+        assert np.array_equal(matcher.canonical_unique(got), matcher.canonical_unique(want)), it
+    assert (matcher.umi_state(want) != 0).sum() > 3000
