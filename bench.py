@@ -47,10 +47,26 @@ WORKLOADS = {
                desc="C1: 10 Mbp text, 1M x 36bp reads, matchAll -e 2, no scores"),
     "c5": dict(n=3_100_000_000, reads=20_000_000, L=250, e=8, mode="all", scores=False, sub=0.01, nrec=24, npm=1000,
                desc="C5: 3.1 Gbp genome, 20M x 250bp reads, matchAll -e 8"),
+    "c4": dict(n=250_000_000, reads=5_000_000, L=150, e=3, mode="gaps", scores=True, sub=0.01, nrec=1, npm=0,
+               desc="C4: synthetic 250 Mbp text, 5M x 150bp FastQ reads (30% of the '+' reads with one planted 1-3 base deletion), "
+                    "matchUnique -e 3 with scores, then the gapped extension pass (matchGaps, MAXgap 3)"),
     "tiny": dict(n=20_000_000, reads=500_000, L=100, e=4, mode="unique", scores=False, sub=0.01, nrec=3, npm=1000,
                  desc="tiny: 20 Mbp, 500k x 100bp reads, matchUnique -e 4 (smoke-size)"),
 }
 SEED = 0x5EA1
+
+# Digest of the result of one step, per workload, as the single-GPU run produces it (real_gpu_unique_checksum of the
+# canonical unique state / matcher.hits_checksum of the matchAll rows).  The single-GPU run is gated on the reference
+# (parity_checked) and property-checked at full size (tests/test_gpu_fullsize.py); a multi-GPU run must reproduce the digest.
+EXPECTED_DIGEST = {
+}
+
+
+def workload_config(wl: dict) -> dict:
+    """The `config` object of the bench line: the same for both arms."""
+    return {"workload": wl["desc"], "text_bases": wl["n"], "reads": wl["reads"], "read_len": wl["L"], "mode": wl["mode"], "scores": wl["scores"],
+            "l2": "no flush between steps: every step streams inputs and tables far larger than the 126 MB L2 (text %.0f MB 2 bit/base, read set %.0f MB, "
+                  "index tables and window records of several GB)" % (wl["n"] / 4 / 1e6, wl["reads"] * ((wl["L"] + 3) // 4) / 1e6)}
 
 
 def record_starts(n: int, nrec: int):
@@ -139,6 +155,8 @@ def cpu_reference(wl: dict, sample_text: int, sample_reads: int, threads: int) -
     if key not in _REF_SAMPLE:
         text = synth.make_text(SEED, n_s, nrecords=min(wl["nrec"], 4), n_per_million=wl["npm"])
         reads = synth.make_reads(text, SEED + 1, r_s, wl["L"], wl["sub"], fastq=fastq)
+        if wl["mode"] == "gaps":
+            synth.plant_deletions(text, reads, SEED + 1, wl["L"])
         work = None
         if O.have_ref():
             import atexit
@@ -148,29 +166,111 @@ def cpu_reference(wl: dict, sample_text: int, sample_reads: int, threads: int) -
             synth.write_reads(os.path.join(work, "r.fq" if fastq else "r.fa"), reads, fastq)
         _REF_SAMPLE[key] = (text, reads, work)
     text, reads, work = _REF_SAMPLE[key]
+    gaps = wl["mode"] == "gaps"
+    unique = wl["mode"] != "all"
+    result = {}
     if work is not None:
+        if gaps:
+            threads = 1            # the reference's gapped pass races on its gapinfos map with more than one thread
         rf = os.path.join(work, "r.fq" if fastq else "r.fa")
-        args = ["-t", os.path.join(work, "t.fa"), "-p", rf, "-o", "x", "-u", "1" if wl["mode"] == "unique" else "0", "-R", "0",
+        args = ["-t", os.path.join(work, "t.fa"), "-p", rf, "-o", "x", "-u", "1" if unique else "0", "-R", "0",
                 "-s", "2", "-e", str(wl["e"]), "-l", "32", "-q", "1" if wl["scores"] else "0", "-T", str(threads)]
         if fastq:
             args += ["-Q", "33"]
-        timing, _, _ = O.run_ref(wl["mode"], work, args, threads=threads)
+        if gaps:
+            args += ["-g", "1"]
+        # one reference text block for the sample (with scores the unique fold depends on the block boundaries)
+        timing, dump, gdump = O.run_ref("unique" if unique else "all", work, args, gap_dump=gaps, env={"REAL_HARNESS_NLIST": str(n_s)}, threads=threads)
         index_s, match_s, kind = timing["index_s"], timing["match_s"], "reference"
+        if unique:
+            result["unique"] = np.fromfile(dump, dtype=O.UNIQUE_DTYPE)
+            if gaps:
+                result["gaps"] = np.fromfile(gdump, dtype=O.GAP_DTYPE)
+        else:
+            result["hits"] = np.fromfile(dump, dtype=O.HIT_DTYPE)
     else:
         O.lib()
         t0 = time.perf_counter()
-        if wl["mode"] == "unique":
+        if unique:
             info, sc = O.unique_init(reads.nreads, wl["scores"])
             O.match_unique(text, reads, info, sc, totalkmax=wl["e"], scores=wl["scores"])
+            if gaps:
+                g = np.zeros(reads.nreads, dtype=O.GAP_DTYPE)
+                O.match_gaps(text, reads, info, sc, g, totalkmax=wl["e"], scores=wl["scores"])
+                result["gaps"] = g[g["present"] == 1]
+            u = np.zeros(reads.nreads, dtype=O.UNIQUE_DTYPE)
+            u["data"] = info
+            if sc is not None:
+                u["score"] = sc
+            result["unique"] = u
         else:
-            O.match_all(text, reads, totalkmax=wl["e"], scores=wl["scores"])
+            result["hits"] = O.match_all(text, reads, totalkmax=wl["e"], scores=wl["scores"])
         index_s, match_s, kind, threads = 0.0, time.perf_counter() - t0, "port", 1
     full_s = index_s * (wl["n"] / n_s) + match_s * (wl["reads"] / r_s)
-    return {"value": wl["reads"] / full_s, "unit": "reads/s", "cores": threads, "kind": kind,
+    return {"value": wl["reads"] / full_s, "unit": "reads/s", "cores": threads, "kind": kind, "_sample": (text, reads), "_result": result,
             "text_gbp_per_s": wl["n"] / full_s / 1e9,
             "sample": "%d bp text + %d reads of the workload: index build %.2f s, OpenMP matching region %.2f s; extrapolated linearly "
                       "(index x text length, matching x reads, one text block at full scale)" % (n_s, r_s, index_s, match_s),
             "sample_index_s": index_s, "sample_match_s": match_s, "extrapolated_full_s": full_s}
+
+
+def parity_gate(wl: dict, sample, result: dict) -> dict:
+    """"match sets bit-exact vs the oracle harness on the same inputs before any timing counts".  Runs the GPU
+    path on the very sample the CPU reference leg was timed on and compares with what the reference produced there:
+    matchAll rows field for field (scores by bit pattern); matchUnique words -- Straight/Reverse words whole, NonUnique words
+    by state and error count (the position a NonUnique word keeps is the first one the reference happened to visit; this
+    path keeps the smallest) -- and with scores the words and score bits whole; gapped pass: words, score bits, GapInfo rows."""
+    import numpy as np
+    from real_b200 import matcher
+    text, reads = sample
+    gaps = wl["mode"] == "gaps"
+    opts = matcher.RealOptions(totalkmax=wl["e"], scores=wl["scores"])
+    opts.gaps = gaps
+    words, nmask = text.packed()
+    out = {"reads": int(reads.nreads), "text_bases": int(text.n)}
+    if wl["mode"] == "all":
+        m = matcher.AllMatcher(opts)
+        try:
+            m.set_reads(reads.mapped, reads.offsets, reads.quality if wl["scores"] else None)
+            m.set_text(words, nmask, text.n, text.record_starts)
+            got = m.match()
+        finally:
+            m.close()
+        ref = result["hits"]
+
+        def canon(h):
+            a = np.stack([h["patid"].astype(np.int64), h["k"].astype(np.int64), h["pos"].astype(np.int64), h["frag"].astype(np.int64),
+                          h["inverted"].astype(np.int64), np.ascontiguousarray(h["score"]).view(np.uint32).astype(np.int64)], 1)
+            return a[np.lexsort(a.T[::-1])]
+        a, b = canon(got), canon(ref)
+        out.update(rows=int(len(b)), ok=bool(a.shape == b.shape and np.array_equal(a, b)))
+        return out
+    m = matcher.UniqueMatcher(opts)
+    try:
+        m.set_reads(reads.mapped, reads.offsets, reads.quality if wl["scores"] else None)
+        m.handle.set_block_windows(0)
+        m.set_text(words, nmask, text.n, text.record_starts)
+        m.match()
+        if gaps:
+            m.matchGaps(0)
+        info, sc = m.info()
+        grows = m.gaps() if gaps else None
+    finally:
+        m.close()
+    ref = result["unique"]
+    if wl["scores"]:
+        ok = np.array_equal(info, ref["data"]) and np.array_equal(sc.view(np.uint32), ref["score"].view(np.uint32))
+    else:
+        ok = np.array_equal(matcher.canonical_unique(info), matcher.canonical_unique(ref["data"]))
+    st = matcher.umi_state(ref["data"])
+    out.update(placed=int((st != 0).sum()), nonunique=int((st == 4).sum()), gapped=int((st == 3).sum()))
+    if gaps:
+        g, r = grows[grows["present"] == 1], result["gaps"]
+        r = r[r["present"] == 1] if "present" in r.dtype.names else r
+        ok = ok and len(g) == len(r) and all(np.array_equal(g[f], r[f]) for f in ("patid", "mingap", "where", "start", "gap_pos"))
+        out["gapinfo_rows"] = int(len(r))
+    out["ok"] = bool(ok)
+    return out
 
 
 def run_reference_arm(args, wl):
@@ -178,17 +278,21 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
+    # every execution runs the identical bounded sample from scratch (6-7 s): at most one warm-up and three timed
+    # executions are made however large --steps is, and their mean is the line's value
+    n_warm, n_timed = min(args.warmup, 1), max(1, min(args.steps, 3))
     vals = []
     last = None
-    for i in range(args.warmup + args.steps):
+    for i in range(n_warm + n_timed):
         last = cpu_reference(wl, args.ref_text, args.ref_reads, threads)
-        if i >= args.warmup:
+        if i >= n_warm:
             vals.append(last)
     v = statistics.mean(x["value"] for x in vals)
     full_s = statistics.mean(x["extrapolated_full_s"] for x in vals)
     line = {"impl": "reference", "metric": "matching-path reads/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": full_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": {"workload": wl["desc"], "text_bases": wl["n"], "reads": wl["reads"], "read_len": wl["L"]},
+            "dtype": "u64", "data": "synthetic", "config": workload_config(wl),
+            "executions": {"warmup": n_warm, "timed": n_timed, "note": "the sample is run from scratch each time; more repetitions would only repeat it"},
             "text_gbp_per_s": wl["n"] / full_s / 1e9,
             "cpu_baseline": {k: last[k] for k in ("kind", "cores", "sample")} | {"value": v, "unit": "reads/s"},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -268,6 +372,10 @@ def main():
                     help="layout of the HBM-resident read set of the timed step: 'packed' = 2 bit/base, the reference's rewritten pattern file "
                          "(TemporaryFile.hpp:231-268; verified in place, only the seeds are extracted); 'bytes' = one mapped byte per base "
                          "(Pattern::mapped; packed into both strands by K1)")
+    ap.add_argument("--fold", default="peer", choices=["peer", "nccl"],
+                    help="N>1, matchUnique: 'peer' = the fold as one exchange over NVLink peer memory (real_gpu_fold_unique, reduce-scatter "
+                         "form: every rank ends up with the merged state of its own 1/N of the reads); 'nccl' = MIN + SUM all-reduce "
+                         "(real_b200.dist.unique_exchange: every rank ends up with the whole merged state)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ingest", action="store_true", help="skip the K0 (device text loader) extra of the bench line")
@@ -304,7 +412,10 @@ def main():
         print("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
     n, R, L = wl["n"], wl["reads"], wl["L"]
-    unique = wl["mode"] == "unique"
+    unique = wl["mode"] in ("unique", "gaps")
+    gaps = wl["mode"] == "gaps"
+    if gaps and world > 1:
+        raise SystemExit("the gapped pass is order dependent: one handle per job (replicas only, DESIGN.md 5)")
     rs = record_starts(n, wl["nrec"])
     tables_mode = world > 1 and args.parallel == "tables"
     buckets_mode = world > 1 and args.parallel == "buckets"
@@ -315,6 +426,11 @@ def main():
     full_w, full_m = devsynth.text_device(SEED, n, device=local, n_per_million=wl["npm"])
     mapped, qual, offs = devsynth.reads_device(SEED + 1, full_w, full_m if wl["npm"] else None, n, R, L, wl["sub"], device=local,
                                                quality=wl["scores"])
+    if gaps:
+        sym = devsynth.unpack_symbols(full_w, full_m, n)
+        ppos, pstrand = devsynth.read_plan_device(SEED + 1, R, n - L + 1, dev)
+        devsynth.plant_deletions(mapped, sym, ppos, pstrand, n, L)
+        del sym, ppos, pstrand
     w0, w1 = sb // 32, (sb + sl + 31) // 32
     m0, m1 = sb // 64, (sb + sl + 63) // 64
     sh_w = full_w[w0:w1 + 2].clone()
@@ -322,7 +438,7 @@ def main():
     del full_w, full_m
     torch.cuda.empty_cache()
 
-    ll = matcher.scoring_table() if wl["scores"] else None
+    ll = matcher.scoring_table() if (wl["scores"] or gaps) else None
     h = rlib.Handle(seedl=32, seedkmax=2, totalkmax=wl["e"], scores=wl["scores"], ll_table=ll, device=local, table_bits=args.table_bits)
     if tables_mode:
         rdist.connect_sharded_tables(h, dev, round_positions=args.round_mpos << 20)
@@ -333,11 +449,23 @@ def main():
         h.set_bucket_shard(er, en)
         print("note: --as-rank %d/%d: one rank's share of a bucket-sharded job; not a reportable number" % (er, en), file=sys.stderr)
     shard = rdist.HandleShard(h, R)
-    keys = torch.empty(R, dtype=torch.int64, device=dev) if unique else None
-    ties = torch.empty(R, dtype=torch.uint8, device=dev) if unique else None
+    peer_fold = world > 1 and unique and args.fold == "peer"
+    if peer_fold:
+        rdist.connect_fold(h, dev, R)
+    keys = torch.empty(R, dtype=torch.int64, device=dev) if (unique and world > 1 and not peer_fold) else None
+    ties = torch.empty(R, dtype=torch.uint8, device=dev) if (unique and world > 1 and not peer_fold) else None
+    r_lo, r_hi = rdist.own_read_range(R, rank, world)
+
+    def exchange():
+        """The one cross-GPU step of matchUnique."""
+        if peer_fold:
+            h.fold_unique()
+        else:
+            rdist.unique_exchange(shard, keys=keys, ties=ties)
     hstream = torch.cuda.ExternalStream(h.stream(), device=dev)
 
-    phase = {"pack_ms": [], "index_ms": [], "scan_ms": [], "post_ms": [], "d2h_ms": [], "h2d_text_ms": [], "exchange_ms": [],
+    phase = {"pack_ms": [], "index_ms": [], "scan_ms": [], "post_ms": [], "d2h_ms": [], "h2d_text_ms": [], "exchange_ms": [], "fold_ms": [],
+             "gap_scan_ms": [], "gap_post_ms": [],
              "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": []}
     last_stats = {}
     nhits_holder = [0]
@@ -371,8 +499,13 @@ def main():
             h.match_unique()
             t3 = time.perf_counter()
             st = h.stats()
+            if gaps:
+                h.match_gaps(0)
+                g = h.stats()
+                st["gap_scan_ms"], st["gap_post_ms"] = g["scan_ms"], g["post_ms"]
             if world > 1:
-                rdist.unique_exchange(shard, keys=keys, ties=ties)
+                exchange()
+                st["fold_ms"] = h.stats()["fold_ms"]
             t4 = time.perf_counter()
         else:
             nhits_holder[0] = h.match_all_count()
@@ -419,6 +552,23 @@ def main():
     clk = clocks.stop() if rank == 0 else {}
     ms_per_step = total_ms / args.steps
     value = R / (ms_per_step * 1e-3)
+
+    # ---- digest of the result of the last step (outside the timed region): must not depend on the number of GPUs
+    if unique:
+        if world > 1 and not peer_fold:
+            part = h.unique_checksum(r_lo, r_hi - r_lo)          # every rank holds the whole merged state: digest the own share
+        else:
+            part = h.unique_checksum(r_lo, r_hi - r_lo) if world > 1 else h.unique_checksum()
+    else:
+        part = matcher.hits_checksum(h.match_all())
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, int(part))
+        digest = sum(parts) & 0xFFFFFFFFFFFFFFFF
+    else:
+        digest = part & 0xFFFFFFFFFFFFFFFF
+    expected = EXPECTED_DIGEST.get(args.workload)
+    digest_ok = None if (expected is None or args.as_rank) else (digest == expected)
 
     # ---- roofline of the dominant kernel (K3 text scan), algorithmic bytes per SURVEY.md 8(d)
     scan_ms = statistics.mean(phase["scan_ms"])
@@ -493,10 +643,11 @@ def main():
                 h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
             if unique:
                 h.match_unique()
+                if gaps:
+                    h.match_gaps(0)
                 if world > 1:
-                    rdist.unique_exchange(shard, keys=keys, ties=ties)
-                # after the exchange every rank holds the merged state: each reads back its own 1/N of the reads
-                r_lo, r_hi = (R * rank) // world, (R * (rank + 1)) // world
+                    exchange()
+                # after the exchange every rank holds the merged state of (at least) its own 1/N of the reads: it reads that back
                 h.get_unique(out=np_info[r_lo:r_hi], first=r_lo, count=r_hi - r_lo)
                 d2h[0] = (r_hi - r_lo) * 8
             else:
@@ -529,23 +680,29 @@ def main():
             ingest = {"error": "%s: %s" % (type(e).__name__, e)}
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(wl, args.cpu_text, args.cpu_reads, os.cpu_count() or 1)
+        # the gate: the GPU path on the very sample the reference was just timed on, against what the reference produced there
+        parity = parity_gate(wl, cpu.pop("_sample"), cpu.pop("_result"))
+        parity["against"] = "oracle/_ref/ref_harness (the reference's own objects)" if cpu["kind"] == "reference" else "oracle/liboracle.so (restatement)"
 
     if rank == 0:
         tot = nwin_tot.tolist()
         line = {
             "metric": "matching-path reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "text_bases": n, "reads": R, "read_len": L, "mode": wl["mode"], "scores": wl["scores"],
-                       "parallelism": ("signature tables sharded by scan bucket x%d: every rank indexes 1/%d of the signature space, reads the whole text and "
-                                       "keeps the positions of its own buckets (no record exchange); reads and text replicated; one NCCL fold of the "
+            "config": workload_config(wl),
+            "parity_checked": (parity["ok"] if parity is not None else None), "parity": parity,
+            "result_digest": "%016x" % digest, "digest_expected": ("%016x" % expected) if expected is not None else None, "digest_ok": digest_ok,
+            "setup": {"parallelism": ("signature tables sharded by scan bucket x%d: every rank indexes 1/%d of the signature space, reads the whole text and "
+                                       "keeps the positions of its own buckets (no record exchange); reads and text replicated; one fold of the "
                                        "per-read results" % (world, world)) if buckets_mode else
                                       ("signature tables sharded x%d: every rank indexes 1/%d of the buckets, partitions 1/%d of the text positions of a round "
                                        "and stores the window records into the owners' windows (peer memory over NVLink); reads and text replicated"
                                        % (world, world, world)) if tables_mode else
-                                      ("text sharded x%d with %d-base halo, read index replicated" % (world, L)),
-                       "l2": "inputs larger than L2 (text %.0f MB/GPU, index tables > 1.8 GB): no flush needed" % (sl / 4 / 1e6),
+                                      ("text sharded x%d with %d-base halo, read index replicated" % (world, L)) if world > 1 else "one GPU",
+                       "fold": ("peer memory, reduce-scatter form (real_gpu_fold_unique)" if peer_fold else "NCCL MIN + SUM all-reduce") if (world > 1 and unique) else None,
                        "table_bits": args.table_bits or 32,
                        "reads_format": "2 bit/base (the reference's rewritten pattern layout), verified in place" if args.reads_format == "packed"
                                        else "1 byte/base (Pattern::mapped)"},
@@ -560,6 +717,12 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        print("PARITY GATE FAILED: the GPU result differs from the reference on the sample", file=sys.stderr)
+        return 3
+    if rank == 0 and digest_ok is False:
+        print("DIGEST MISMATCH: the result of this run differs from the recorded single-GPU result", file=sys.stderr)
+        return 4
     return 0
 
 

@@ -243,6 +243,27 @@ def make_reads(text: Text, seed: int, nreads: int, length: int, sub_rate: float,
     return Reads(mapped=out.astype(np.uint8).reshape(-1), offsets=offsets, quality=quality, ids=ids)
 
 
+def plant_deletions(text: Text, reads: Reads, seed: int, length: int) -> np.ndarray:
+    """C4: 30 % of the '+' strand reads get one deletion of 1..3 bases behind the seed -- read[off+g:] moves up
+    and the tail is refilled from the text behind the window (the formula of devsynth.plant_deletions).  In place on
+    reads.mapped (uniform `length`, made by make_reads with the same seed); returns the planted mask."""
+    R = reads.nreads
+    pos, strand = read_plan_total(seed, R, text.n - length + 1, 0, R)
+    pos = pos.astype(np.int64)
+    rid = np.arange(R, dtype=np.int64)
+    g = 1 + rid % 3
+    off = 60 + rid % 50
+    planted = (rid % 10 < 3) & (strand == 0) & (pos + length + 3 < text.n)
+    m2 = reads.mapped.reshape(R, length)
+    col = np.arange(length, dtype=np.int64)[None, :]
+    src_col = np.where(col >= off[:, None], col + g[:, None], col)
+    a = np.take_along_axis(m2, np.minimum(src_col, length - 1), axis=1)
+    b = text.symbols[np.minimum(pos[:, None] + src_col, text.n - 1)]
+    new = np.where(src_col < length, a, b)
+    m2[planted] = new[planted]
+    return planted
+
+
 def reads_from_list(seqs: Sequence[np.ndarray], quals: Optional[Sequence[np.ndarray]] = None,
                     ids: Optional[Sequence[str]] = None) -> Reads:
     """Ragged read set from explicit arrays (tests)."""
