@@ -82,6 +82,131 @@ __device__ __forceinline__ bool hit_before(RawHit const & a, RawHit const & b)
         return rawhit_strand(a.pm) < rawhit_strand(b.pm);
 }
 
+// ---- segments too long for one thread --------------------------------------------------------------
+// The per-read kernels below order a read's hits with an insertion sort run by one thread: fine for the handful of
+// hits a read normally has, quadratic for a repeat-rich read with 10^4..10^5 of them (the reference uses std::sort in
+// unifyMatches).  Segments of more than SEG_SMALL hits are therefore sorted beforehand, one CTA per segment, by a
+// bottom-up merge sort (runs of SEG_SMALL by insertion, then merge passes in which every thread places one element by a
+// binary search into the partner run); the scratch half of every pass is the same range of the raw hit buffer, which is
+// free once the hits have been grouped by read.
+static const uint32_t SEG_SMALL = 32;
+
+__global__ void __launch_bounds__(256) k_mark_large(const uint32_t * __restrict__ counts, uint64_t nreads, uint32_t * __restrict__ list, uint32_t * __restrict__ nlarge)
+{
+        uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( r < nreads && counts[r] > SEG_SMALL ) list[atomicAdd(nlarge, 1u)] = (uint32_t)r;
+}
+
+template<typename Less>
+__device__ __forceinline__ void seg_insertion_sort(RawHit * s, uint32_t n, Less less)
+{
+        for ( uint32_t i = 1; i < n; ++i )
+        {
+                RawHit const x = s[i];
+                uint32_t j = i;
+                while ( j > 0 && less(x, s[j-1]) ) { s[j] = s[j-1]; --j; }
+                s[j] = x;
+        }
+}
+
+// all threads of the CTA; s and tmp hold n elements each; the sorted segment ends up in s
+template<typename Less>
+__device__ void cta_merge_sort(RawHit * s, RawHit * tmp, uint32_t n, Less less)
+{
+        for ( uint32_t run = threadIdx.x; run * SEG_SMALL < n; run += blockDim.x )
+                seg_insertion_sort(s + run * SEG_SMALL, min(SEG_SMALL, n - run * SEG_SMALL), less);
+        __syncthreads();
+        RawHit * src = s, * dst = tmp;
+        for ( uint32_t w = SEG_SMALL; w < n; w <<= 1 )
+        {
+                for ( uint32_t i = threadIdx.x; i < n; i += blockDim.x )
+                {
+                        uint32_t const p0 = (i / (2 * w)) * (2 * w), mid = min(p0 + w, n), end = min(p0 + 2 * w, n);
+                        RawHit const x = src[i];
+                        uint32_t pos;
+                        if ( i < mid )
+                        {
+                                uint32_t lo = mid, hi = end;            // elements of the right run that come before x
+                                while ( lo < hi ) { uint32_t const m = (lo + hi) >> 1; if ( less(src[m], x) ) lo = m + 1; else hi = m; }
+                                pos = i + (lo - mid);
+                        }
+                        else
+                        {
+                                uint32_t lo = p0, hi = mid;             // elements of the left run that do not come after x
+                                while ( lo < hi ) { uint32_t const m = (lo + hi) >> 1; if ( ! less(x, src[m]) ) lo = m + 1; else hi = m; }
+                                pos = lo + (i - mid);
+                        }
+                        dst[pos] = x;
+                }
+                __syncthreads();
+                RawHit * t = src; src = dst; dst = t;
+        }
+        if ( src != s )
+        {
+                for ( uint32_t i = threadIdx.x; i < n; i += blockDim.x ) s[i] = src[i];
+                __syncthreads();
+        }
+}
+
+struct LessHit { __device__ bool operator()(RawHit const & a, RawHit const & b) const { return hit_before(a, b); } };
+struct LessPos { __device__ bool operator()(RawHit const & a, RawHit const & b) const { return rawhit_pos(a.pm) < rawhit_pos(b.pm); } };
+
+struct SortLargeParams
+{
+        RawHit * seg; RawHit * tmp;
+        const uint32_t * starts; const uint32_t * counts;
+        const uint32_t * list; const uint32_t * nlarge;
+        // order-faithful replay: (text block, strand, seed window position)
+        const uint32_t * rlen; uint32_t seedl;
+        const uint64_t * bounds; uint32_t nblocks;
+};
+
+__device__ __forceinline__ uint32_t block_index(const uint64_t * __restrict__ bounds, uint32_t nblocks, uint64_t rpos)
+{
+        if ( ! bounds ) return 0;
+        uint32_t lo = 0, hi = nblocks;
+        while ( hi - lo > 1 )
+        {
+                uint32_t const mid = (lo + hi) >> 1;
+                if ( bounds[mid] <= rpos ) lo = mid; else hi = mid;
+        }
+        return lo;
+}
+
+struct LessReplay
+{
+        const uint64_t * bounds; uint32_t nblocks, moff;
+        __device__ bool operator()(RawHit const & a, RawHit const & b) const
+        {
+                uint32_t const sa = rawhit_strand(a.pm), sb = rawhit_strand(b.pm);
+                uint64_t const ra = rawhit_pos(a.pm) + (sa ? moff : 0), rb = rawhit_pos(b.pm) + (sb ? moff : 0);
+                uint32_t const ba = block_index(bounds, nblocks, ra), bb = block_index(bounds, nblocks, rb);
+                if ( ba != bb ) return ba < bb;
+                if ( sa != sb ) return sa < sb;
+                return ra < rb;
+        }
+};
+
+// MODE 0: unifyMatches order, 1: replay order of matchUnique with scores, 2: ascending position (gapped pass)
+template<int MODE>
+__global__ void __launch_bounds__(256) k_sort_large(SortLargeParams P)
+{
+        uint32_t const nl = *P.nlarge;
+        for ( uint32_t li = blockIdx.x; li < nl; li += gridDim.x )
+        {
+                uint32_t const r = P.list[li];
+                uint32_t const o = P.starts[r], n = P.counts[r];
+                if ( MODE == 0 ) cta_merge_sort(P.seg + o, P.tmp + o, n, LessHit());
+                else if ( MODE == 1 )
+                {
+                        LessReplay L; L.bounds = P.bounds; L.nblocks = P.nblocks; L.moff = P.rlen[r] - P.seedl;
+                        cta_merge_sort(P.seg + o, P.tmp + o, n, L);
+                }
+                else cta_merge_sort(P.seg + o, P.tmp + o, n, LessPos());
+                __syncthreads();
+        }
+}
+
 // one thread per read: insertion sort of its (short) segment, then expansion to the ABI record
 template<typename HitOut>
 __global__ void __launch_bounds__(128) k_hit_order(RawHit * __restrict__ seg, const uint32_t * __restrict__ starts, const uint32_t * __restrict__ counts,
@@ -92,13 +217,7 @@ __global__ void __launch_bounds__(128) k_hit_order(RawHit * __restrict__ seg, co
         uint32_t const n = counts[r];
         if ( ! n ) return;
         RawHit * s = seg + starts[r];
-        for ( uint32_t i = 1; i < n; ++i )
-        {
-                RawHit const x = s[i];
-                uint32_t j = i;
-                while ( j > 0 && hit_before(x, s[j-1]) ) { s[j] = s[j-1]; --j; }
-                s[j] = x;
-        }
+        if ( n <= SEG_SMALL ) seg_insertion_sort(s, n, LessHit());          // longer segments: k_sort_large<0> has run
         HitOut * o = out + starts[r];
         for ( uint32_t i = 0; i < n; ++i )
         {
@@ -206,23 +325,11 @@ __global__ void __launch_bounds__(128) k_unique_replay(ReplayParams P)
         uint32_t const L = P.rlen[r];
         float const epsilon = (float)(P.filter_mult * (double)L);
         uint32_t const moff = L - P.seedl;
-        // order by (block, strand, seed window position); the block is kept in the (now free) frag bits above bit 16 ...
-        // frag is < 65536 in unique mode, so pm bits 56..63 are free for nothing we need: compute the key on the fly instead
-        auto key_less = [&](RawHit const & a, RawHit const & b) -> bool
+        // order by (block, strand, seed window position); longer segments: k_sort_large<1> has run
+        if ( n <= SEG_SMALL )
         {
-                uint32_t const sa = rawhit_strand(a.pm), sb = rawhit_strand(b.pm);
-                uint64_t const ra = rawhit_pos(a.pm) + (sa ? moff : 0), rb = rawhit_pos(b.pm) + (sb ? moff : 0);
-                uint32_t const ba = block_of(P, ra), bb = block_of(P, rb);
-                if ( ba != bb ) return ba < bb;
-                if ( sa != sb ) return sa < sb;
-                return ra < rb;
-        };
-        for ( uint32_t i = 1; i < n; ++i )
-        {
-                RawHit const x = s[i];
-                uint32_t j = i;
-                while ( j > 0 && key_less(x, s[j-1]) ) { s[j] = s[j-1]; --j; }
-                s[j] = x;
+                LessReplay LR; LR.bounds = P.bounds; LR.nblocks = P.nblocks; LR.moff = moff;
+                seg_insertion_sort(s, n, LR);
         }
         unsigned long long d = P.info[r];
         float sc = P.score[r];
@@ -449,7 +556,9 @@ __global__ void __launch_bounds__(128) k_gap_replay(GapReplayParams P)
                 while ( hi - lo > 1 ) { uint32_t const mid = (lo + hi) >> 1; if ( P.bounds[mid] <= rpos ) lo = mid; else hi = mid; }
                 return lo;
         };
-        for ( uint32_t i = 1; i < n; ++i )                 // ascending window position (which also orders the blocks)
+        // ascending window position (which also orders the blocks); longer segments were sorted before k_gap_dp ran
+        // (k_sort_large<2>), so their results already stand in that order
+        for ( uint32_t i = 1; i < n && n <= SEG_SMALL; ++i )
         {
                 RawHit const x = s[i]; GapRes const y = gr[i];
                 uint32_t j = i;

@@ -23,6 +23,11 @@ using namespace realgpu;
 namespace
 {
 
+struct LimitError : public std::runtime_error
+{
+        explicit LimitError(std::string const & s) : std::runtime_error(s) {}
+};
+
 struct DevBuf
 {
         void * p;
@@ -75,7 +80,7 @@ struct real_gpu
         uint32_t F, keybits;
 
         // results
-        DevBuf rec_win, rec_pos, part_meta, own_list;
+        DevBuf rec_win, rec_pos, part_meta, own_list, large_list;
         DevBuf win_valid, win_counts, bounds, gapres, gaps, boffs, flags8;   // reference text blocks (order-faithful replay)
         uint64_t n_list;               // windows per reference text block, 0 = one block per file
         DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
@@ -194,7 +199,8 @@ void finish_build(real_gpu * h);
 // whose transfer is meant to overlap it
 #define RG_API_BEGIN(h)  if ( ! (h) ) return REAL_GPU_E_ARG; try { RG_CUDA(cudaSetDevice((h)->prm.device)); finish_build(h);
 #define RG_API_BEGIN_ASYNC(h)  if ( ! (h) ) return REAL_GPU_E_ARG; try { RG_CUDA(cudaSetDevice((h)->prm.device));
-#define RG_API_END(h)    } catch ( realgpu::CudaError const & e ) { return fail((h), REAL_GPU_E_CUDA, e.what()); } \
+#define RG_API_END(h)    } catch ( LimitError const & e ) { return fail((h), REAL_GPU_E_LIMIT, e.what()); } \
+                           catch ( realgpu::CudaError const & e ) { return fail((h), REAL_GPU_E_CUDA, e.what()); } \
                            catch ( std::exception const & e ) { return fail((h), REAL_GPU_E_CUDA, e.what()); }
 
 // ---------------------------------------------------------------------------------------------
@@ -217,6 +223,12 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
                 return fail(h, REAL_GPU_E_LIMIT, "set_text: fileid >= 64 (UniqueMatchInfo.hpp:31)");
         if ( record_starts[nrecords] != n_total )
                 return fail(h, REAL_GPU_E_ARG, "set_text: record_starts[nrecords] must equal n_total");
+
+        if ( own_end > shard_begin + shard_len )
+                return fail(h, REAL_GPU_E_ARG, "set_text: the own range must lie inside the shard");
+        if ( nrecords >= (1u << 24) )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text: more than 2^24 records (the record index of a hit has 24 bits)");
+        h->have_text = false;          // whatever fails below, the old text is gone
 
         uint64_t const nw = (shard_len + 31) / 32, nmw = (shard_len + 63) / 64;
         size_t const tail = TEXT_PAD_WORDS + 2 * SC_SMEM_WORDS + SC_TILE_WORDS + 2 * OL_TILE_WORDS;     // the last tile of every kernel stays inside the allocation
@@ -289,8 +301,8 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
         *n_bases = n; *nrecords = nrec;
         if ( n >= (1ULL << 35) )
                 return fail(h, REAL_GPU_E_LIMIT, "set_text: text longer than 2^35 bases (UniqueMatchInfo.hpp:29-33)");
-        if ( nrec >= (1ULL << 32) )
-                return fail(h, REAL_GPU_E_LIMIT, "set_text_fasta: more than 2^32 records");
+        if ( nrec >= (1ULL << 24) )
+                return fail(h, REAL_GPU_E_LIMIT, "set_text_fasta: more than 2^24 records (the record index of a hit has 24 bits)");
         if ( n == 0 || nrec == 0 )
                 return REAL_GPU_OK;                             // nothing to match against; no text is set
 
@@ -560,8 +572,9 @@ int build_from_device(real_gpu * h)
         if ( h->comm.nranks > 1 && h->hit_cap == 0 )
         {
                 // sharded tables: nothing may be allocated or freed between the hand-over kernels of a scan
-                h->hit_cap = std::max<uint64_t>(1u << 16, 4 * h->nreads);
-                dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
+                uint64_t const cap = std::max<uint64_t>(1u << 16, 4 * h->nreads);
+                dev_alloc(h, h->hits_raw, cap * sizeof(RawHit));
+                h->hit_cap = cap;
         }
         // Everything above is enqueued; the build is waited for by the next call that needs the index (finish_build),
         // so that a text transfer issued in between overlaps it.
@@ -929,7 +942,7 @@ void preload_kernels(int device)
         RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter<false>); RG_PRELOAD(k_part_scatter<true>); RG_PRELOAD(k_own_list); RG_PRELOAD((k_bucket_probe<false, false>)); RG_PRELOAD((k_bucket_probe<true, false>)); RG_PRELOAD((k_bucket_probe<false, true>)); RG_PRELOAD((k_bucket_probe<true, true>));
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
-        RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay); RG_PRELOAD(k_fold_push); RG_PRELOAD(k_fold_merge); RG_PRELOAD(k_unique_checksum);
+        RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay); RG_PRELOAD(k_fold_push); RG_PRELOAD(k_fold_merge); RG_PRELOAD(k_unique_checksum); RG_PRELOAD(k_mark_large); RG_PRELOAD(k_sort_large<0>); RG_PRELOAD(k_sort_large<1>); RG_PRELOAD(k_sort_large<2>);
         RG_PRELOAD(k_fa_summary); RG_PRELOAD(k_fa_scan); RG_PRELOAD(k_fa_pack);
         RG_PRELOAD(k_window_counts); RG_PRELOAD(k_block_bounds); RG_PRELOAD(k_gap_dp); RG_PRELOAD(k_gap_replay);
 #undef RG_PRELOAD
@@ -940,6 +953,8 @@ int check_ready(real_gpu * h)
 {
         if ( ! h->have_text ) return fail(h, REAL_GPU_E_STATE, "no text set");
         if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( std::min<uint64_t>(h->n_total, h->own_end + h->maxlen) > h->shard_begin + h->shard_len )
+                return fail(h, REAL_GPU_E_ARG, "the shard does not hold the read-length halo behind its own range (real_gpu_set_text: [own_begin, min(n_total, own_end + maxreadlen)))");
         return REAL_GPU_OK;
 }
 
@@ -1012,7 +1027,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
                            &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
@@ -1274,19 +1289,28 @@ static uint64_t collect_hits_by_read(real_gpu * h, int mode = 0)
 {
         if ( h->hit_cap == 0 )
         {
-                h->hit_cap = std::max<uint64_t>(1u << 16, 2 * h->nreads);
-                dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
+                uint64_t const cap = std::max<uint64_t>(1u << 16, 2 * h->nreads);
+                dev_alloc(h, h->hits_raw, cap * sizeof(RawHit));
+                h->hit_cap = cap;              // only once the buffer exists
         }
         uint64_t found = run_scan(h, mode);
         if ( found > h->hit_cap )
         {
-                // the buffer was too small: the kernel counted everything, so size it exactly and rescan
-                h->hit_cap = found + found / 8 + 1024;
-                dev_alloc(h, h->hits_raw, h->hit_cap * sizeof(RawHit));
+                // the buffer was too small: the kernel counted everything, so size it exactly
+                uint64_t const cap = found + found / 8 + 1024;
+                h->hit_cap = 0;
+                dev_alloc(h, h->hits_raw, cap * sizeof(RawHit));
+                h->hit_cap = cap;
+                if ( h->comm.nranks > 1 && h->comm.window.p )
+                        // Sharded tables: a scan is a sequence of rounds all ranks take part in (the hand-over flags count them).
+                        // A rank that rescanned on its own would run rounds no peer joins -- and would pair with the peers' NEXT
+                        // call.  The decision has to be collective: this call fails on this rank, the buffer is already enlarged.
+                        throw LimitError("sharded tables: the hit buffer of this rank was too small for " + std::to_string(found) +
+                                         " hits; it has been enlarged -- repeat the call on EVERY rank");
                 found = run_scan(h, mode);
                 if ( found > h->hit_cap ) throw CudaError("hit count changed between scans");
         }
-        if ( found >= (1ULL << 32) ) throw CudaError("more than 2^32 hits in one call");
+        if ( found >= (1ULL << 32) ) throw LimitError("more than 2^32 hits in one call");
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
         dev_reserve(h, h->counts, h->nreads * 4 + 16);
         dev_reserve(h, h->starts, h->nreads * 4 + 16);
@@ -1312,8 +1336,28 @@ static uint64_t collect_hits_by_read(real_gpu * h, int mode = 0)
                 launch_count(h, nl);
                 k_hit_scatter<<<blocks_for(found, 256), 256, 0, h->st>>>(ptr<RawHit>(h->hits_raw), found, ptr<uint32_t>(h->starts), ptr<uint32_t>(h->cursor), ptr<RawHit>(h->hits_seg));
                 RG_KERNEL_CHECK(); launch_count(h);
+                // reads with more hits than one thread should sort (post.cuh, SEG_SMALL)
+                dev_reserve(h, h->large_list, (found / SEG_SMALL + 16) * 4);
+                RG_CUDA(cudaMemsetAsync(h->large_list.p, 0, 4, h->st));
+                k_mark_large<<<blocks_for(h->nreads, 256), 256, 0, h->st>>>(ptr<uint32_t>(h->counts), h->nreads, ptr<uint32_t>(h->large_list) + 4, ptr<uint32_t>(h->large_list));
+                RG_KERNEL_CHECK(); launch_count(h);
         }
         return found;
+}
+
+// sorts the segments of the reads k_mark_large has listed (one CTA each); the raw hit buffer serves as scratch space
+static void sort_large_segments(real_gpu * h, int mode, const uint64_t * bounds, uint32_t nblocks)
+{
+        SortLargeParams SP;
+        SP.seg = ptr<RawHit>(h->hits_seg); SP.tmp = ptr<RawHit>(h->hits_raw);
+        SP.starts = ptr<uint32_t>(h->starts); SP.counts = ptr<uint32_t>(h->counts);
+        SP.list = ptr<uint32_t>(h->large_list) + 4; SP.nlarge = ptr<uint32_t>(h->large_list);
+        SP.rlen = ptr<uint32_t>(h->rlen); SP.seedl = h->prm.seedl; SP.bounds = bounds; SP.nblocks = nblocks;
+        unsigned const grid = (unsigned)(h->sm_count * 4);
+        if ( mode == 0 ) k_sort_large<0><<<grid, 256, 0, h->st>>>(SP);
+        else if ( mode == 1 ) k_sort_large<1><<<grid, 256, 0, h->st>>>(SP);
+        else k_sort_large<2><<<grid, 256, 0, h->st>>>(SP);
+        RG_KERNEL_CHECK(); launch_count(h);
 }
 
 int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhits)
@@ -1328,6 +1372,7 @@ int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhit
         if ( found )
         {
                 dev_reserve(h, h->hits_out, found * sizeof(real_gpu_hit));
+                sort_large_segments(h, 0, nullptr, 1);
                 k_hit_order<real_gpu_hit><<<blocks_for(h->nreads, 128), 128, 0, h->st>>>(ptr<RawHit>(h->hits_seg), ptr<uint32_t>(h->starts), ptr<uint32_t>(h->counts),
                                                                                         h->nreads, h->fileid, ptr<real_gpu_hit>(h->hits_out));
                 RG_KERNEL_CHECK(); launch_count(h);
@@ -1371,6 +1416,8 @@ static uint32_t block_bounds(real_gpu * h)
         launch_count(h, nl);
         RG_CUDA(cudaMemcpyAsync(&lastp, ptr<uint32_t>(h->win_counts) + (ngroups - 1), 4, cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
+        if ( h->n_total >= (1ULL << 32) )
+                throw LimitError("reference text blocks (n_list) on a text of 2^32 or more bases: the window prefix sums are 32 bit");
         uint64_t const nwin = (uint64_t)lastc + lastp;
         uint64_t const nb = nwin ? (nwin + h->n_list - 1) / h->n_list : 1;
         if ( nb <= 1 ) return 1;
@@ -1410,6 +1457,7 @@ int real_gpu_match_unique(real_gpu * h)
                 R.nreads = h->nreads; R.seedl = h->prm.seedl; R.fileid = h->fileid; R.filter_mult = h->prm.filter_mult;
                 R.bounds = nb > 1 ? ptr<uint64_t>(h->bounds) : nullptr; R.nblocks = nb;
                 R.info = ptr<unsigned long long>(h->info); R.score = ptr<float>(h->scores);
+                sort_large_segments(h, 1, R.bounds, nb);
                 k_unique_replay<<<blocks_for(h->nreads, 128), 128, 0, h->st>>>(R);
                 RG_KERNEL_CHECK(); launch_count(h);
         }
@@ -1555,6 +1603,7 @@ int real_gpu_match_gaps(real_gpu * h, uint64_t n_list_windows)
         if ( found )
         {
                 dev_reserve(h, h->gapres, found * sizeof(GapRes) + 64);
+                sort_large_segments(h, 2, nullptr, 1);          // long segments in replay order before their results are computed
                 GapParams G;
                 G.seg = ptr<RawHit>(h->hits_seg); G.ncand = found; G.ll = ptr<double>(h->ll);
                 G.text = ptr<uint64_t>(h->text) + TEXT_PAD_WORDS; G.nmask = ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS; G.shard_begin = h->shard_begin;
