@@ -789,19 +789,40 @@ __device__ __forceinline__ bool wide_seed_test(ScanParams const & P, uint32_t id
 }
 
 // whole-read Hamming distance of strand id of a 2 bit/base input read against the text at word tp, bit offset sh; gives up
-// (returns more than kmax) as soon as the count exceeds kmax.  (PACKED instantiations of the probe kernel only.)
+// (returns more than kmax) once the count exceeds kmax.  The words are cut out four at a time, all their loads issued
+// before the first is used: a warp that verifies does not probe, so the round trips must overlap, not queue up
+// (one word per iteration cost the C3 scan 11 ms).
 __device__ __forceinline__ uint32_t distance_packed(ReadSrc const & rs, uint32_t id, uint32_t L, const uint64_t * __restrict__ tp, uint32_t sh, uint32_t kmax)
 {
         uint32_t const nw = (L + 31) >> 5;
+        const uint8_t * p = packed_read(rs, id >> 1);
+        bool const minus = id & 1;
         uint64_t prev = __ldg(tp);
         uint32_t k = 0;
-        for ( uint32_t w = 0; w < nw; ++w )
+        for ( uint32_t w0 = 0; w0 < nw; w0 += 4 )
         {
-                uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
-                uint64_t const nx = __ldg(tp + w + 1);
-                uint64_t const tv = sh ? ((prev << sh) | (nx >> (64 - sh))) : prev;
-                prev = nx;
-                k += diffcount64(strand_bases(rs, id, L, 32*w, len) >> (64 - 2*len), tv >> (64 - 2*len));
+                uint64_t rw[4], tw[4];
+                #pragma unroll
+                for ( uint32_t u = 0; u < 4; ++u )
+                        if ( w0 + u < nw )
+                        {
+                                uint32_t const w = w0 + u;
+                                uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
+                                rw[u] = packed_bases(p, minus ? (L - 32*w - len) : 32*w, len);
+                                tw[u] = __ldg(tp + w + 1);
+                        }
+                #pragma unroll
+                for ( uint32_t u = 0; u < 4; ++u )
+                        if ( w0 + u < nw )
+                        {
+                                uint32_t const w = w0 + u;
+                                uint32_t const len = (w + 1 == nw) ? (L - 32*w) : 32;
+                                uint64_t r = rw[u] >> (64 - 2*len);
+                                if ( minus ) r = revcomp_word(r, len);
+                                uint64_t const tv = sh ? ((prev << sh) | (tw[u] >> (64 - sh))) : prev;
+                                prev = tw[u];
+                                k += diffcount64(r, tv >> (64 - 2*len));
+                        }
                 if ( k > kmax ) break;
         }
         return k;

@@ -416,3 +416,53 @@ def test_fold_two_processes_ipc():
         got = np.concatenate([parts[r][it] for r in range(nranks)])
         assert np.array_equal(matcher.canonical_unique(got), matcher.canonical_unique(want)), it
     assert (matcher.umi_state(want) != 0).sum() > 3000
+
+
+def test_sharded_tables_hit_buffer_overflow_is_collective():
+    """Sharded tables, one rank finds far more hits than its buffer holds (poly-A reads on a poly-A stretch: every hit lies
+    in bucket AAAA = rank 0).  That rank must NOT rescan on its own -- its extra rounds would pair with the peers' next
+    call -- but fail with REAL_GPU_E_LIMIT after enlarging its buffer; the repeated call on every rank then succeeds and
+    the rounds of the ranks are still in step (the union of the rows is the oracle's)."""
+    from real_b200 import lib as rlib
+    text, reads = _fresh(91, n=400_000, nreads=3000)
+    sym = text.symbols.copy()
+    sym[150_000:151_200] = 0
+    text = synth.Text(sym, text.records)
+    rng = np.random.RandomState(5)
+    polya = []
+    for _ in range(300):
+        s = np.zeros(100, np.uint8)
+        s[rng.randint(40, 100, size=2)] = rng.randint(1, 4, size=2)       # <= 2 substitutions behind the seed
+        polya.append(s)
+    reads = synth.concat_reads([reads, synth.reads_from_list(polya)])
+    kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    ref = O.match_all(text, reads, **kw)
+    assert len(ref) > 200_000
+    nranks = 2
+    ms = _ranks(matcher.AllMatcher, matcher.RealOptions(**kw), nranks, 1 << 18)
+
+    def attempt(m):
+        def run():
+            try:
+                return m.match()
+            except rlib.RealGpuError as e:
+                return e.code
+        return run
+    try:
+        words, nmask = text.packed()
+        for m in ms:
+            m.set_reads(reads.mapped, reads.offsets, None)
+            m.set_text(words, nmask, text.n, text.record_starts)
+        first = _run_threads([attempt(m) for m in ms])
+        assert first[0] == rlib.REAL_GPU_E_LIMIT and not isinstance(first[1], int)
+        second = _run_threads([attempt(m) for m in ms])
+        assert not any(isinstance(p, int) for p in second)
+        third = _run_threads([attempt(m) for m in ms])            # and again: the rounds are still in step
+    finally:
+        for m in ms:
+            m.close()
+    b = canon_hits(ref)
+    for parts in (second, third):
+        a = canon_hits(np.concatenate(parts))
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert len(second[0]) > 200_000
