@@ -154,6 +154,11 @@ def cpu_reference(wl: dict, sample_text: int, sample_reads: int, threads: int) -
     key = (wl["desc"], n_s, r_s)
     if key not in _REF_SAMPLE:
         text = synth.make_text(SEED, n_s, nrecords=min(wl["nrec"], 4), n_per_million=wl["npm"])
+        if n_s >= 1_000_000:
+            # a planted 20 kb repeat: reads with two placements (NonUnique words, multi-row reads) are part of what the gate compares
+            sym = text.symbols.copy()
+            sym[n_s // 2:n_s // 2 + 20_000] = sym[5000:25_000]
+            text = synth.Text(sym, text.records)
         reads = synth.make_reads(text, SEED + 1, r_s, wl["L"], wl["sub"], fastq=fastq)
         if wl["mode"] == "gaps":
             synth.plant_deletions(text, reads, SEED + 1, wl["L"])
