@@ -134,8 +134,9 @@ struct real_gpu
         int pass_bits_override;        // REAL_GPU_PASS_BITS (tuning), -1 = automatic
         uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
+        int own_list_max;              // bucket shards: own buckets up to which the kept positions are listed first (REAL_GPU_OWN_LIST_MAX)
 
-        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), own_list_max(64), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -788,7 +789,11 @@ uint64_t run_scan(real_gpu * h, int mode)
                 P.bucket_cursor = meta + 1088;
 
                 size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem);
-                if ( own_only )
+                // Bucket shard: with few own buckets (four ranks or more) one light pass lists the kept positions and counts them per
+                // bucket, and the staged scatter runs on the list; with many (two ranks: half of all positions are kept) listing
+                // costs more than it saves, and the dense kernels run with a filter on the bucket (measured, profiles/r02_*)
+                bool const own_list = own_only && P.own_b_cnt <= (uint32_t)h->own_list_max;
+                if ( own_list )
                 {
                         // the positions of a chunk this rank keeps, 4 bytes each (all of them if the text falls into its buckets only)
                         dev_reserve(h, h->own_list, chunk_cap * 4 + 64);
@@ -806,7 +811,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                 RG_CUDA(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
                 int occ_p = 0, occ_b = 0, occ_s = 0;
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, psmem));
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, own_only ? k_part_scatter<true> : k_part_scatter<false>, SC_THREADS, ssmem));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, own_list ? k_part_scatter<true> : k_part_scatter<false>, SC_THREADS, ssmem));
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, probe, SC_THREADS, bsmem));
                 if ( occ_p < 1 ) occ_p = 1;
                 if ( occ_s < 1 ) occ_s = 1;
@@ -842,8 +847,8 @@ uint64_t run_scan(real_gpu * h, int mode)
                         uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
                         unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * occ_p);
                         RG_CUDA(cudaMemsetAsync(meta, 0, 256 * 4, h->st));
-                        if ( own_only ) RG_CUDA(cudaMemsetAsync(P.list_count, 0, 8, h->st));
-                        if ( any && own_only )
+                        if ( own_list ) RG_CUDA(cudaMemsetAsync(P.list_count, 0, 8, h->st));
+                        if ( any && own_list )
                         {
                                 uint64_t const oft = P.x_begin / OL_TILE_POS, oet = (P.x_end + OL_TILE_POS - 1) / OL_TILE_POS;
                                 k_own_list<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * 8), OL_THREADS, 0, h->st>>>(P);
@@ -867,7 +872,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                         {
                                 uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
                                 unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
-                                if ( own_only )
+                                if ( own_list )
                                         k_part_scatter<true><<<(unsigned)(h->sm_count * occ_s), SC_THREADS, ssmem, h->st>>>(P);
                                 else
                                         k_part_scatter<false><<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
@@ -996,6 +1001,7 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 preload_kernels(params->device);
                 if ( const char * e = getenv("REAL_GPU_PASS_BITS") ) h->pass_bits_override = atoi(e);
                 if ( const char * e = getenv("REAL_GPU_L2_SLICE_MB") ) h->l2_slice_bytes = (uint64_t)atoi(e) << 20;
+                if ( const char * e = getenv("REAL_GPU_OWN_LIST_MAX") ) h->own_list_max = atoi(e);
                 if ( const char * e = getenv("REAL_GPU_CHUNK_MPOS") ) h->chunk_positions = std::max<uint64_t>(SC_TILE_POS, ((uint64_t)atoi(e) << 20) / SC_TILE_POS * SC_TILE_POS);
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));

@@ -422,7 +422,7 @@ struct ScatterSmem
 
 // LIST: the positions come from the kept-position list of a bucket shard (k_own_list) instead of the text tiles
 template<bool LIST>
-__global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
+__global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
         ScatterSmem & S = *reinterpret_cast<ScatterSmem *>(sc_smem);
@@ -496,6 +496,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(ScanParams P)
                         uint32_t const wi = threadIdx.x / PS_TPW, j0 = (threadIdx.x % PS_TPW) * PS_PPT;
                         uint64_t const wm = S.tile[buf][SC_HALO + wi - 1], w0 = S.tile[buf][SC_HALO + wi], w1 = S.tile[buf][SC_HALO + wi + 1];
                         m = (clip_mask(tile_x0 + (uint64_t)wi * 32, P.x_begin, P.x_end) >> j0) & (uint32_t)((1ull << PS_PPT) - 1);
+                        if ( PS_PPT == 8 && P.own_b_cnt < SC_MAX_BUCKETS )
+                        {
+                                // bucket shard with many own buckets (two ranks): every position is looked at here, only the own ones
+                                // are ranked and staged (with few own buckets the list form above is cheaper)
+                                uint32_t top;
+                                m &= own_mask8(w0, w1, j0, P.own_b_lo, P.own_b_cnt, top);
+                        }
                         pos0 = (uint32_t)(tile_x0 - P.pos_base);     // may wrap for the clipped first tile; the sums below do not
                         #pragma unroll
                         for ( uint32_t u = 0; u < PS_PPT; ++u )
@@ -685,7 +692,12 @@ __global__ void __launch_bounds__(SC_MAX_BUCKETS) k_part_offsets(ScanParams P)
                 }
                 st[SC_MAX_BUCKETS] = a;            // single rank: the total (all buckets are in one area)
                 *P.unit_counter = 0;
-                if ( P.own_b_cnt < SC_MAX_BUCKETS && P.list_count ) atomicAdd(P.nprobed, *P.list_count);
+                if ( P.own_b_cnt < SC_MAX_BUCKETS )
+                {
+                        unsigned long long kept = 0;
+                        for ( uint32_t b = 0; b < (uint32_t)SC_MAX_BUCKETS; ++b ) kept += P.bucket_count[b];
+                        atomicAdd(P.nprobed, kept);
+                }
         }
         __syncthreads();
         uint32_t const owner = bucket_owner(P, threadIdx.x);
