@@ -219,6 +219,16 @@ def cpu_reference(wl: dict, sample_text: int, sample_reads: int, threads: int) -
             "sample_index_s": index_s, "sample_match_s": match_s, "extrapolated_full_s": full_s}
 
 
+def table_bits_of(wl: dict) -> int:
+    """log2 of the slots the library gives the presence tables of the FULL workload (about 32 slots per entry of the largest
+    table, 2^20 .. 2^32): the gate runs its sample with the same geometry, so that it takes the same kernels as the timed step."""
+    want = max(1, wl["reads"] * 2 * 3) * 32
+    b = 20
+    while b < 32 and (1 << b) < want:
+        b += 1
+    return b
+
+
 def parity_gate(wl: dict, sample, result: dict) -> dict:
     """"match sets bit-exact vs the oracle harness on the same inputs before any timing counts".  Runs the GPU
     path on the very sample the CPU reference leg was timed on and compares with what the reference produced there:
@@ -232,9 +242,9 @@ def parity_gate(wl: dict, sample, result: dict) -> dict:
     opts = matcher.RealOptions(totalkmax=wl["e"], scores=wl["scores"])
     opts.gaps = gaps
     words, nmask = text.packed()
-    out = {"reads": int(reads.nreads), "text_bases": int(text.n)}
+    out = {"reads": int(reads.nreads), "text_bases": int(text.n), "table_bits": table_bits_of(wl)}
     if wl["mode"] == "all":
-        m = matcher.AllMatcher(opts)
+        m = matcher.AllMatcher(opts, table_bits=table_bits_of(wl))
         try:
             m.set_reads(reads.mapped, reads.offsets, reads.quality if wl["scores"] else None)
             m.set_text(words, nmask, text.n, text.record_starts)
@@ -250,7 +260,7 @@ def parity_gate(wl: dict, sample, result: dict) -> dict:
         a, b = canon(got), canon(ref)
         out.update(rows=int(len(b)), ok=bool(a.shape == b.shape and np.array_equal(a, b)))
         return out
-    m = matcher.UniqueMatcher(opts)
+    m = matcher.UniqueMatcher(opts, table_bits=table_bits_of(wl))
     try:
         m.set_reads(reads.mapped, reads.offsets, reads.quality if wl["scores"] else None)
         m.handle.set_block_windows(0)

@@ -290,8 +290,19 @@ __device__ __forceinline__ bool entry_owned(EntryPartParams const & P, uint32_t 
         return p >= P.own_lo && p <= P.own_last;
 }
 
+// G.table == TABLE_ITEMS: the geometry of the fused build (build_tables_fused, real_gpu.cu).  When the slots are the keys
+// themselves (hb == keybits), the slot of entry (table, t) starts with fragment t of the seed whatever the table is, so
+// the entries (A,t), (B,t), (C,t) of a strand fall into the same bucket at every partition level of at most 2F bits: the
+// build partitions ITEMS (strand, t) -- half as many as there are entries -- and only the sub-bucket kernel tells the
+// tables apart.  The "slot" of an item is fragment t followed by zeros.
+static const int TABLE_ITEMS = 3;
 __device__ __forceinline__ uint32_t entry_slot(uint64_t seed, TableGeom const & G, uint32_t t)
 {
+        if ( G.table == TABLE_ITEMS )
+        {
+                uint32_t const fb = 2 * G.F;
+                return (uint32_t)((seed >> (fb * (3 - t))) & ((1ULL << fb) - 1)) << (G.hb - fb);
+        }
         return slot_of(pair_key(seed, G.F, (int)t, pair_second(G.table, (int)t)), G.keybits, G.hb);
 }
 
@@ -840,6 +851,162 @@ __global__ void __launch_bounds__(256, 7) k_build_sub(const uint64_t * __restric
                 Entry en; en.seed = dd.seed; en.val = dd.val;
                 en.next = atomicExch(&E[dd.r].next, o);
                 E[o] = en;
+        }
+}
+
+// The sub-bucket kernel of the fused build: the grouped ITEMS [sub_start[sb], sub_start[sb+1]) all carry a fragment t that
+// starts with the prefix sb, so for every table the slots of their entries lie in [sb << sub_shift, (sb+1) << sub_shift).
+// One CTA builds that piece of all three tables: item (strand, t) is an entry of table tb when t < nl[tb] (A: pairs (t,t+1),
+// B: (t,t+2), C: (t,t+3)).  The entry arrays of the three tables use the ITEM numbering: the entries of a sub-bucket sit at
+// the front of E[tb][sub_start[sb] ...) -- no per-table offsets are needed; B and C leave the tail of each range unused.
+// Dynamic shared memory per table: presence bits and claimed bits (words u32 each) and the ranks of the words' first slots
+// (words u16, relative to the sub-bucket: a sub-bucket spans at most 2^16 slots).
+static const uint32_t SUB3_DUP_CAP = 256;
+struct Build3Params
+{
+        const uint64_t * item_seed; const uint32_t * item_val; const uint32_t * sub_start;
+        TableGeom G[3];                 // G[tb].nlists == 0: table not built
+        uint32_t sub_shift, words, first_sub;
+        SlotWord * slots[3]; Entry * E[3];
+        uint32_t * ndistinct[3];
+};
+
+__global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ Build3Params P)
+{
+        extern __shared__ __align__(16) uint32_t sub_smem[];
+        uint32_t const words = P.words;
+        __shared__ SubDup dup[3][SUB3_DUP_CAP];
+        __shared__ uint32_t ovf[3], ndup[3], dist[3];
+        uint32_t const sb = P.first_sub + blockIdx.x;
+        uint32_t const s0 = P.sub_start[sb], s1 = P.sub_start[sb+1];
+        uint32_t const slot0 = sb << P.sub_shift;
+        uint32_t const tstride = 2 * words + (words + 1) / 2;          // per table: presence bits, claimed bits (u32 each), ranks (u16, relative to s0)
+        for ( uint32_t w = threadIdx.x; w < 3 * tstride; w += 256 ) sub_smem[w] = 0;
+        if ( threadIdx.x < 3 ) { ovf[threadIdx.x] = 0; ndup[threadIdx.x] = 0; }
+        __syncthreads();
+        // presence bits of the three tables; four items per thread and step, their loads issued together
+        for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
+        {
+                uint64_t seed[4]; uint32_t val[4];
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                {
+                        uint32_t const i = i0 + (uint32_t)k * 256;
+                        seed[k] = (i < s1) ? __ldg(P.item_seed + i) : 0;
+                        val[k] = (i < s1) ? __ldg(P.item_val + i) : 0;
+                }
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                        if ( i0 + (uint32_t)k * 256 < s1 )
+                        {
+                                uint32_t const t = val[k] & 3;
+                                #pragma unroll
+                                for ( int tb = 0; tb < 3; ++tb )
+                                        if ( t < P.G[tb].nlists )
+                                        {
+                                                uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
+                                                atomicOr(&sub_smem[tb * tstride + (l >> 5)], 1u << (l & 31));
+                                        }
+                        }
+        }
+        __syncthreads();
+        // ranks: every thread owns a run of consecutive words of every table
+        uint32_t const wpt = (words + 255) / 256;
+        uint32_t const w0 = threadIdx.x * wpt;
+        #pragma unroll 1
+        for ( int tb = 0; tb < 3; ++tb )
+        {
+                uint32_t * bits = sub_smem + tb * tstride;
+                uint16_t * rank = reinterpret_cast<uint16_t *>(bits + 2 * words);
+                uint32_t c = 0;
+                for ( uint32_t w = w0; w < min(words, w0 + wpt); ++w ) c += __popc(bits[w]);
+                uint32_t d;
+                uint32_t run = block_excl_scan(c, &d);                    // < 2^16: a sub-bucket spans at most 2^16 slots
+                for ( uint32_t w = w0; w < min(words, w0 + wpt); ++w ) { rank[w] = (uint16_t)run; run += __popc(bits[w]); }
+                if ( threadIdx.x == 0 ) dist[tb] = d;
+        }
+        __syncthreads();
+        #pragma unroll 1
+        for ( int tb = 0; tb < 3; ++tb )
+        {
+                if ( ! P.G[tb].nlists ) continue;
+                const uint32_t * bits = sub_smem + tb * tstride;
+                const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + 2 * words);
+                for ( uint32_t w = threadIdx.x; w < words; w += 256 )
+                {
+                        SlotWord sw; sw.bits = bits[w]; sw.rank = s0 + rank[w];
+                        P.slots[tb][(uint64_t)sb * words + w] = sw;
+                }
+                uint32_t const d = dist[tb];
+                for ( uint32_t r = threadIdx.x; r < d; r += 256 ) P.E[tb][s0 + r].next = ENTRY_NONE;
+                if ( threadIdx.x == 0 && d ) atomicAdd(P.ndistinct[tb], d);
+        }
+        __syncthreads();
+        // entries: the first one of a slot claims E[rank]; the others (few: the tables are sparse) are set aside and chained below
+        for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
+        {
+                uint64_t seed[4]; uint32_t val[4];
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                {
+                        uint32_t const i = i0 + (uint32_t)k * 256;
+                        seed[k] = (i < s1) ? __ldg(P.item_seed + i) : 0;
+                        val[k] = (i < s1) ? __ldg(P.item_val + i) : 0;
+                }
+                #pragma unroll
+                for ( int k = 0; k < 4; ++k )
+                        if ( i0 + (uint32_t)k * 256 < s1 )
+                        {
+                                uint32_t const t = val[k] & 3;
+                                #pragma unroll
+                                for ( int tb = 0; tb < 3; ++tb )
+                                        if ( t < P.G[tb].nlists )
+                                        {
+                                                uint32_t * bits = sub_smem + tb * tstride, * claimed = bits + words;
+                                                const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + 2 * words);
+                                                uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
+                                                uint32_t const bit = 1u << (l & 31);
+                                                uint32_t const r = s0 + rank[l >> 5] + __popc(bits[l >> 5] & (bit - 1));
+                                                Entry * E = P.E[tb];
+                                                if ( ! (atomicOr(&claimed[l >> 5], bit) & bit) )
+                                                {
+                                                        E[r].seed = seed[k];
+                                                        E[r].val = val[k];
+                                                }
+                                                else
+                                                {
+                                                        uint32_t const j = atomicAdd(&ndup[tb], 1u);
+                                                        if ( j < SUB3_DUP_CAP )
+                                                        {
+                                                                SubDup dd; dd.seed = seed[k]; dd.val = val[k]; dd.r = r;
+                                                                dup[tb][j] = dd;
+                                                        }
+                                                        else
+                                                        {
+                                                                uint32_t const o = s0 + dist[tb] + SUB3_DUP_CAP + atomicAdd(&ovf[tb], 1u);
+                                                                Entry en; en.seed = seed[k]; en.val = val[k];
+                                                                en.next = atomicExch(&E[r].next, o);
+                                                                E[o] = en;
+                                                        }
+                                                }
+                                        }
+                        }
+        }
+        __syncthreads();
+        // the set-aside entries go behind the distinct ones of this sub-bucket
+        #pragma unroll 1
+        for ( int tb = 0; tb < 3; ++tb )
+        {
+                uint32_t const nd = min(ndup[tb], SUB3_DUP_CAP);
+                Entry * E = P.E[tb];
+                for ( uint32_t j = threadIdx.x; j < nd; j += 256 )
+                {
+                        SubDup const dd = dup[tb][j];
+                        uint32_t const o = s0 + dist[tb] + j;
+                        Entry en; en.seed = dd.seed; en.val = dd.val;
+                        en.next = atomicExch(&E[dd.r].next, o);
+                        E[o] = en;
+                }
         }
 }
 

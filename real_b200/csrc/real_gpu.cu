@@ -54,6 +54,7 @@ struct real_gpu
         cudaStream_t st2;              // host<->device copies of the text, so that they overlap the index build on st
         cudaEvent_t ev[8];
         cudaEvent_t evc[2];
+        bool fused_build;              // the current tables were built by build_tables_fused (entry arrays in item numbering)
         bool build_pending;            // the index build of the current read set has been enqueued but not yet waited for
         uint64_t held;
         int sm_count;
@@ -136,7 +137,7 @@ struct real_gpu
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
         int own_list_max;              // bucket shards: own buckets up to which the kept positions are listed first (REAL_GPU_OWN_LIST_MAX)
 
-        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), own_list_max(64), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), fused_build(false), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), own_list_max(64), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -382,7 +383,6 @@ TablePlan plan_table(real_gpu * h, int t, uint32_t * meta)
         T.nblocks = TP.nsub;
         T.bitmap_bytes = (size_t)TP.nsub * TP.words * sizeof(SlotWord);
         dev_reserve(h, T.bitmap, T.bitmap_bytes);
-        dev_reserve(h, T.E, std::max<size_t>(16, cap_entries * sizeof(Entry)) + 256);
         EntryPartParams & EP = TP.EP;
         EP.G.F = h->F; EP.G.keybits = h->keybits; EP.G.hb = T.hb; EP.G.nlists = 0; EP.G.table = t;
         if ( T.nlists == 0 || h->nreads == 0 )
@@ -424,10 +424,11 @@ TablePlan plan_table(real_gpu * h, int t, uint32_t * meta)
 // one table, its level-1 histogram already counted: group the entries by slot prefix (two levels; the grouped
 // entries of the tables share one workspace, so the tables are built one after the other), then build every
 // sub-bucket in shared memory
-void build_table(real_gpu * h, int t, TablePlan const & TP)
+struct Grouped { const uint64_t * seed; const uint32_t * val; const uint32_t * start; };
+
+// the two staged partition passes over the entries (or items) of TP: grouped by the top e1, then by the next e2 bits of the slot
+Grouped partition_entries(real_gpu * h, TablePlan const & TP)
 {
-        if ( TP.empty ) return;
-        Table & T = h->tab[t];
         EntryPartParams const & EP = TP.EP;
         k_ent_offsets<<<1, EP_MAX_BUCKETS, 0, h->st>>>(EP, TP.d_total);
         RG_KERNEL_CHECK();
@@ -467,9 +468,83 @@ void build_table(real_gpu * h, int t, TablePlan const & TP)
                 RG_KERNEL_CHECK(); launch_count(h);
                 fin_seed = EP.ent2_seed; fin_val = EP.ent2_val; fin_start = EP.sub_start;
         }
+        Grouped G; G.seed = fin_seed; G.val = fin_val; G.start = fin_start;
+        return G;
+}
+
+void build_table(real_gpu * h, int t, TablePlan const & TP)
+{
+        if ( TP.empty ) return;
+        Table & T = h->tab[t];
+        EntryPartParams const & EP = TP.EP;
+        Grouped const GR = partition_entries(h, TP);
+        const uint64_t * fin_seed = GR.seed; const uint32_t * fin_val = GR.val; const uint32_t * fin_start = GR.start;
         k_build_sub<<<TP.own_subs, 256, (size_t)3 * TP.words * 4, h->st>>>(fin_seed, fin_val, fin_start, EP.G, TP.sub_shift, TP.words, ptr<SlotWord>(T.bitmap), ptr<Entry>(T.E), TP.d_ndist, TP.first_sub);
         RG_KERNEL_CHECK(); launch_count(h);
         RG_CUDA(cudaMemcpyAsync(&h->table_counts[2*t], TP.d_total, 8, cudaMemcpyDeviceToHost, h->st));   // total, ndistinct
+}
+
+// The fused build (index.cuh, TABLE_ITEMS): possible when the slots are the keys themselves and the partition depth does not
+// exceed a fragment -- then the entries (A,t), (B,t), (C,t) of a strand share their bucket at both partition levels, ITEMS
+// (strand, t) are partitioned once for all three tables, and one CTA per sub-bucket builds its piece of each table.
+// Returns false when the geometry does not allow it (folded slots: the per-table build runs).
+bool build_tables_fused(real_gpu * h, TablePlan * plan)
+{
+        uint32_t const hb = h->tab[0].hb, fb = 2 * h->F;
+        if ( hb != h->keybits || h->nreads == 0 || plan[0].empty ) return false;
+        if ( getenv("REAL_GPU_NO_FUSED_BUILD") ) return false;
+        uint32_t const nlA = table_lists(0, h->prm.seedkmax);
+        uint64_t const cap_items = h->nreads * 2 * nlA;
+        uint32_t const pbmin = hb > 16 ? hb - 16 : 0, pbmax = std::min<uint32_t>(std::min<uint32_t>(16, hb > 5 ? hb - 5 : 0), fb);
+        if ( pbmin > pbmax ) return false;
+        uint32_t pb = 0;
+        while ( (cap_items >> pb) > SUB_TARGET_ENTRIES ) ++pb;
+        pb = std::min(std::max(pb, pbmin), pbmax);
+        if ( h->comm.nranks > 1 && pb < 8 ) return false;
+
+        TablePlan TP = plan[0];                       // buffers, meta block, ownership of table A's plan
+        uint32_t * meta = TP.EP.bucket_count;
+        uint32_t const e1 = std::min<uint32_t>(8, pb);
+        TP.e2 = pb - e1; TP.nsub = 1u << pb; TP.sub_shift = hb - pb;
+        TP.words = TP.sub_shift >= 5 ? (1u << (TP.sub_shift - 5)) : 1u;
+        TP.EP.G.table = TABLE_ITEMS; TP.EP.G.nlists = nlA;
+        TP.EP.ebits = e1; TP.EP.e2bits = TP.e2;
+        TP.first_sub = 0; TP.own_subs = TP.nsub;
+        if ( h->comm.nranks > 1 )
+        {
+                TP.first_sub = TP.EP.own_lo << (pb - 8);
+                TP.own_subs = (TP.EP.own_last + 1 - TP.EP.own_lo) << (pb - 8);
+        }
+        Build3Params B;
+        memset(&B, 0, sizeof(B));
+        for ( int t = 0; t < 3; ++t )
+        {
+                Table & T = h->tab[t];
+                T.nblocks = TP.nsub;
+                T.bitmap_bytes = (size_t)TP.nsub * TP.words * sizeof(SlotWord);
+                dev_reserve(h, T.bitmap, T.bitmap_bytes);
+                // the entry arrays of all three tables use the item numbering (k_build_sub3)
+                dev_reserve(h, T.E, std::max<size_t>(16, cap_items * sizeof(Entry)) + 256);
+                if ( plan[t].empty ) RG_CUDA(cudaMemsetAsync(T.bitmap.p, 0, T.bitmap_bytes, h->st));
+                B.G[t] = plan[t].EP.G; B.G[t].table = t; B.G[t].nlists = plan[t].empty ? 0 : T.nlists;
+                B.slots[t] = ptr<SlotWord>(T.bitmap); B.E[t] = ptr<Entry>(T.E);
+                B.ndistinct[t] = meta + 521 + t;
+        }
+        // level-1 histogram of the items, then the two partition passes
+        EntryPartParams3 Q;
+        for ( int t = 0; t < 3; ++t ) { Q.P[t] = TP.EP; if ( t ) Q.P[t].G.nlists = 0; }
+        k_ent_hist3<<<(unsigned)(h->sm_count * 8), 256, 0, h->st>>>(Q);
+        RG_KERNEL_CHECK(); launch_count(h);
+        Grouped const GR = partition_entries(h, TP);
+        B.item_seed = GR.seed; B.item_val = GR.val; B.sub_start = GR.start;
+        B.sub_shift = TP.sub_shift; B.words = TP.words; B.first_sub = TP.first_sub;
+        size_t const smem = (size_t)3 * (2 * TP.words + (TP.words + 1) / 2) * 4;
+        RG_CUDA(cudaFuncSetAttribute(k_build_sub3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_build_sub3<<<TP.own_subs, 256, smem, h->st>>>(B);
+        RG_KERNEL_CHECK(); launch_count(h);
+        RG_CUDA(cudaMemcpyAsync(&h->table_counts[0], TP.d_total, 16, cudaMemcpyDeviceToHost, h->st));   // items, distinct slots of A, B, C
+        h->fused_build = true;
+        return true;
 }
 
 int build_from_device(real_gpu * h)
@@ -542,6 +617,17 @@ int build_from_device(real_gpu * h)
                 Q.P[t] = plan[t].EP;
                 any_table = any_table || ! plan[t].empty;
         }
+        h->fused_build = false;
+        if ( any_table && build_tables_fused(h, plan) )
+                any_table = false;             // built
+        else
+        for ( int t = 0; t < 3 && any_table; ++t )
+                if ( ! plan[t].empty )
+                {
+                        // per-table build: the entry array holds exactly the table's entries
+                        Table & T = h->tab[t];
+                        dev_reserve(h, T.E, std::max<size_t>(16, h->nreads * 2 * T.nlists * sizeof(Entry)) + 256);
+                }
         if ( any_table )
         {
                 // the level-1 histograms of the three tables in one pass over the seeds
@@ -552,7 +638,7 @@ int build_from_device(real_gpu * h)
                 k_ent_hist3<<<(unsigned)(h->sm_count * 8), 256, 0, h->st>>>(Q);
                 RG_KERNEL_CHECK(); launch_count(h);
         }
-        for ( int t = 0; t < 3; ++t )
+        for ( int t = 0; t < 3 && any_table; ++t )
                 build_table(h, t, plan[t]);
         RG_CUDA(cudaEventRecord(h->ev[4], h->st));
 
@@ -590,6 +676,18 @@ void finish_build(real_gpu * h)
         h->build_pending = false;
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->n_usable = 0;
+        if ( h->fused_build )
+        {
+                // table_counts = items, distinct slots of A, B, C; an item (strand, t) is an entry of every table with more than t lists
+                uint32_t const nlA = table_lists(0, h->prm.seedkmax);
+                uint64_t const strands = nlA ? h->table_counts[0] / nlA : 0;
+                for ( int t = 0; t < 3; ++t )
+                {
+                        h->tab[t].nentries = strands * h->tab[t].nlists;
+                        h->tab[t].ndistinct = h->table_counts[1 + t];
+                }
+        }
+        else
         for ( int t = 0; t < 3; ++t )
         {
                 h->tab[t].nentries = h->table_counts[2*t];
@@ -942,7 +1040,7 @@ void preload_kernels(int device)
         cudaFuncAttributes a;
 #define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
         RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_seeds_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
-        RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub);
+        RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub); RG_PRELOAD(k_build_sub3);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
         RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter<false>); RG_PRELOAD(k_part_scatter<true>); RG_PRELOAD(k_own_list); RG_PRELOAD((k_bucket_probe<false, false>)); RG_PRELOAD((k_bucket_probe<true, false>)); RG_PRELOAD((k_bucket_probe<false, true>)); RG_PRELOAD((k_bucket_probe<true, true>));
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);

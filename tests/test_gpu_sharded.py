@@ -55,7 +55,7 @@ def _run_threads(fns):
     return outs
 
 
-@pytest.mark.parametrize("nranks,round_positions,e,table_bits", [(2, 1 << 18, 4, 0), (4, 1 << 19, 3, 0), (3, 1 << 30, 4, 24), (8, 1 << 17, 4, 0)])
+@pytest.mark.parametrize("nranks,round_positions,e,table_bits", [(2, 1 << 18, 4, 0), (4, 1 << 19, 3, 0), (3, 1 << 30, 4, 24), (8, 1 << 17, 4, 0), (4, 1 << 18, 4, 32)])
 def test_sharded_match_all_vs_oracle(nranks, round_positions, e, table_bits):
     text, reads = _fresh(100 + nranks)
     kw = dict(seedl=32, seedkmax=2, totalkmax=e, scores=False)
@@ -132,7 +132,8 @@ def _bucket_ranks(cls, opts, nranks, table_bits=0):
     return ms
 
 
-@pytest.mark.parametrize("nranks,e,table_bits,n", [(2, 4, 0, 900_000), (8, 4, 0, 900_000), (3, 3, 24, 700_000), (5, 4, 0, 2_300_000)])
+@pytest.mark.parametrize("nranks,e,table_bits,n", [(2, 4, 0, 900_000), (8, 4, 0, 900_000), (3, 3, 24, 700_000), (5, 4, 0, 2_300_000),
+                                                   (4, 4, 32, 900_000), (8, 4, 32, 700_000), (2, 3, 32, 700_000)])      # 32: the fused index build
 def test_bucket_shards_match_all_vs_oracle(nranks, e, table_bits, n):
     """Bucket shards (real_gpu_set_bucket_shard): every rank reads the whole text but keeps the positions of its own
     buckets; no exchange.  The union of the ranks' hits must be the oracle's hit set, every hit found exactly once."""
@@ -288,15 +289,15 @@ def _two_file_job(seed=41):
     return (t0, t1), reads, kw, info_ref
 
 
-@pytest.mark.parametrize("nranks,packed", [(2, False), (3, True), (8, False)])
-def test_bucket_shards_fold_group_vs_oracle(nranks, packed):
+@pytest.mark.parametrize("nranks,packed,table_bits", [(2, False, 0), (3, True, 0), (8, False, 0), (4, True, 32)])
+def test_bucket_shards_fold_group_vs_oracle(nranks, packed, table_bits):
     """Bucket shards of ONE process folded with real_gpu_fold_unique_group (k_fold_push / k_fold_merge over peer pointers):
     after every file rank r holds the merged words of its own reads; they must equal the oracle's words and the numpy
     restatement of the fold (real_b200.dist.fold_reduce_scatter_reference) applied to the ranks' pre-fold states."""
     from real_b200 import dist as rdist
     from real_b200 import lib as rlib
     texts, reads, kw, info_ref = _two_file_job()
-    ms = _bucket_ranks(matcher.UniqueMatcher, matcher.RealOptions(**kw), nranks)
+    ms = _bucket_ranks(matcher.UniqueMatcher, matcher.RealOptions(**kw), nranks, table_bits)
     R = reads.nreads
     try:
         for r, m in enumerate(ms):
