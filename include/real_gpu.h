@@ -109,6 +109,9 @@ typedef struct
 } real_gpu_stats;
 
 int real_gpu_abi_version(void);
+/* CUDA devices visible to the process (0 when there is none or the runtime fails): host drivers that put one handle on
+ * every GPU of the box size their team with it. */
+int real_gpu_device_count(void);
 
 /* Creates a handle on params->device.  Replaces the construction of SignatureConstruction,
  * Scoring and the matcher object (matchAllImplementation.cpp:381-390,447). */

@@ -172,9 +172,30 @@ RealOptions::RealOptions(int argc, char * argv[])
         if ( ! outputfilename.size() )
                 throw std::runtime_error("Mandatory argument -o (output file name) is not given.");
         fracmem = std::min(1.0, fracmem);
+        ngpus = 1;
+        if ( char const * e = getenv("REAL_GPUS") ) ngpus = std::max(1, atoi(e));
         if ( patternfilename == "-" )
-                throw std::runtime_error("Reading patterns from standard input is not supported by the GPU driver.");
-        fastq = isFastQ(patternfilename);
+        {
+                // RealOptions.cpp:418-426: the type is decided by the first byte of standard input, rewriting is switched on.
+                // The whole stream is taken in here (the reference spools it into its rewritten pattern file).
+                stdin_bytes.reset(new std::vector<char>());
+                char tmp[1 << 16];
+                ssize_t got;
+                while ( (got = ::read(STDIN_FILENO, tmp, sizeof(tmp))) > 0 ) stdin_bytes->insert(stdin_bytes->end(), tmp, tmp + got);
+                if ( stdin_bytes->empty() )
+                        throw std::runtime_error("Failed to read first character from pattern file.");
+                char const first = (*stdin_bytes)[0];
+                if ( first == '>' ) fastq = false;
+                else if ( first == '@' ) fastq = true;
+                else throw std::runtime_error("Unable to determine type of pattern file.");
+                if ( ! rewritepatterns )
+                {
+                        std::cerr << "Reading patterns from stdin, switching on pattern rewriting." << std::endl;
+                        rewritepatterns = true;
+                }
+        }
+        else
+                fastq = isFastQ(patternfilename);
         std::cerr << "pattern file is " << (fastq ? "FASTQ" : "FASTA") << " rewrite is " << (rewritepatterns ? "on" : "off") << std::endl;
         if ( seedl > 64 )
         {
@@ -297,6 +318,13 @@ void FileBytes::open(std::string const & filename)
         ::close(fd);
         if ( got < 0 )
                 throw std::runtime_error("Failed to read file " + filename);
+        p = owned.empty() ? 0 : &owned[0]; n = owned.size();
+}
+
+void FileBytes::adopt(std::vector<char> & bytes)
+{
+        close();
+        owned.swap(bytes);
         p = owned.empty() ? 0 : &owned[0]; n = owned.size();
 }
 
@@ -713,6 +741,56 @@ void reorderLikeRewrite(ReadSet & reads)
 // drivers
 // ---------------------------------------------------------------------------------------------
 
+void packReads(ReadSet const & reads, PackedReads & out, unsigned int threads)
+{
+        uint64_t const n = reads.size();
+        out.byte_offsets.assign(n + 1, 0);
+        out.lengths.assign(n, 0);
+        out.wildcard.assign(n, 0);
+        for ( uint64_t r = 0; r < n; ++r )
+        {
+                uint64_t const L = reads.offsets[r+1] - reads.offsets[r];
+                out.lengths[r] = (uint32_t)L;
+                out.byte_offsets[r+1] = out.byte_offsets[r] + (L + 3) / 4;
+        }
+        out.packed.assign(out.byte_offsets[n] + 8, 0);
+        if ( threads < 1 ) threads = 1;
+        threads = (unsigned int)std::min<uint64_t>(threads, std::max<uint64_t>(1, n / 4096));
+        auto work = [&reads, &out, n, threads](unsigned int t)
+        {
+                uint64_t const a = n * t / threads, b = n * (t + 1) / threads;
+                for ( uint64_t r = a; r < b; ++r )
+                {
+                        uint8_t const * m = &reads.mapped[0] + reads.offsets[r];
+                        uint32_t const L = out.lengths[r];
+                        uint8_t * q = &out.packed[0] + out.byte_offsets[r];
+                        uint8_t bad = 0;
+                        uint32_t i = 0;
+                        for ( ; i + 4 <= L; i += 4 )
+                        {
+                                bad |= (m[i] | m[i+1] | m[i+2] | m[i+3]) & 0xFC;
+                                *q++ = (uint8_t)(((m[i] & 3) << 6) | ((m[i+1] & 3) << 4) | ((m[i+2] & 3) << 2) | (m[i+3] & 3));
+                        }
+                        if ( i < L )
+                        {
+                                uint8_t v = 0;
+                                for ( uint32_t j = 0; i + j < L; ++j ) { bad |= m[i+j] & 0xFC; v |= (uint8_t)((m[i+j] & 3) << (6 - 2 * j)); }
+                                *q++ = v;
+                        }
+                        if ( bad )
+                        {
+                                // a wildcard: flagged, its bases stored as A (the flag is what keeps the read from matching)
+                                out.wildcard[r] = 1;
+                                memset(&out.packed[0] + out.byte_offsets[r], 0, (L + 3) / 4);
+                        }
+                }
+        };
+        if ( threads == 1 ) { work(0); return; }
+        std::vector<std::thread> team;
+        for ( unsigned int t = 0; t < threads; ++t ) team.push_back(std::thread(work, t));
+        for ( size_t t = 0; t < team.size(); ++t ) team[t].join();
+}
+
 namespace
 {
         struct Gpu
@@ -835,12 +913,12 @@ namespace
                 }
         };
 
-        void createHandle(Gpu & G, RealOptions const & opts, std::vector<double> & ll)
+        void createHandle(Gpu & G, RealOptions const & opts, std::vector<double> & ll, int device = -1)
         {
                 real_gpu_params P;
                 memset(&P, 0, sizeof(P));
                 P.struct_size = sizeof(P);
-                P.device = opts.device;
+                P.device = device >= 0 ? device : opts.device;
                 P.seedl = opts.seedl; P.seedkmax = opts.seedkmax; P.totalkmax = opts.totalkmax; P.scores = opts.scores ? 1 : 0;
                 P.filter_mult = opts.filter_mult;
                 if ( opts.scores || opts.gaps )
@@ -853,19 +931,6 @@ namespace
                 if ( rc != REAL_GPU_OK )
                         throw std::runtime_error("real_gpu_create failed (no CUDA device or unsupported option); there is no CPU fallback");
         }
-
-        // real_gpu_create on a thread of its own (context creation and module load take a few hundred milliseconds);
-        // wait() joins it and rethrows its error.  The destructor joins too, so G outlives the thread on every path.
-        struct HandleStarter
-        {
-                std::thread th; std::exception_ptr err;
-                HandleStarter(Gpu & G, RealOptions const & opts, std::vector<double> & ll)
-                {
-                        th = std::thread([this, &G, &opts, &ll]() { try { createHandle(G, opts, ll); } catch ( ... ) { err = std::current_exception(); } });
-                }
-                void wait() { if ( th.joinable() ) th.join(); if ( err ) { std::exception_ptr e = err; err = nullptr; std::rethrow_exception(e); } }
-                ~HandleStarter() { if ( th.joinable() ) th.join(); }
-        };
 
         // getText (getText.hpp:31-58) for the device: the bytes of the file go to real_gpu_set_text_fasta, which parses and
         // packs them there and sets the text; the record table comes back for the output lines.  T.words / T.nmask stay empty.
@@ -922,14 +987,147 @@ namespace
                 return true;
         }
 
+        // runs fn(i) for i in [0,n) on n host threads (one per GPU handle) and rethrows the first error
+        template<typename F>
+        void parallelFor(unsigned int n, F fn)
+        {
+                if ( n == 1 ) { fn(0u); return; }
+                std::vector<std::thread> team;
+                std::vector<std::exception_ptr> err(n);
+                for ( unsigned int i = 0; i < n; ++i )
+                        team.push_back(std::thread([&fn, &err, i]() { try { fn(i); } catch ( ... ) { err[i] = std::current_exception(); } }));
+                for ( unsigned int i = 0; i < n; ++i ) team[i].join();
+                for ( unsigned int i = 0; i < n; ++i ) if ( err[i] ) std::rethrow_exception(err[i]);
+        }
+
+        // The GPUs of the box in one process (real.cpp:203-230 is one process): REAL_GPUS handles, handle i on device
+        // (REAL_GPU_DEVICE + i) modulo the devices present, each indexing and probing 1/N of the signature space
+        // (real_gpu_set_bucket_shard) against the whole text.  matchAll: the rows of the handles are merged on the host;
+        // matchUnique: the per-read states are folded over peer memory (real_gpu_fold_unique_group).  One host thread per handle
+        // drives the uploads and the scans.  The order dependent folds (scores, gapped pass) need all hits of a read in one
+        // place and stay on one handle.
+        struct GpuTeam
+        {
+                std::vector<Gpu> g;
+                std::vector<double> ll;
+                std::thread starter; std::exception_ptr starter_err;
+                unsigned int size() const { return (unsigned int)g.size(); }
+                GpuTeam(RealOptions const & opts, bool order_dependent)
+                {
+                        unsigned int n = (unsigned int)opts.ngpus;
+                        if ( n > 8 ) n = 8;
+                        if ( order_dependent && n > 1 )
+                        {
+                                std::cerr << "REAL_GPUS=" << n << " ignored: the fold of this mode depends on the visiting order and runs on one GPU" << std::endl;
+                                n = 1;
+                        }
+                        g.resize(n);
+                        // real_gpu_create on threads of their own (context creation and module load take a few hundred
+                        // milliseconds) while the pattern file is read
+                        starter = std::thread([this, &opts]()
+                        {
+                                try
+                                {
+                                        int const ndev = std::max(1, real_gpu_device_count());
+                                        std::vector<double> * llp = &ll;
+                                        std::vector< std::vector<double> > lls(g.size());
+                                        parallelFor((unsigned int)g.size(), [this, &opts, &lls, ndev](unsigned int i)
+                                        { createHandle(g[i], opts, lls[i], (opts.device + (int)i) % ndev); });
+                                        (void)llp;
+                                }
+                                catch ( ... ) { starter_err = std::current_exception(); }
+                        });
+                }
+                void wait()
+                {
+                        if ( starter.joinable() ) starter.join();
+                        if ( starter_err ) { std::exception_ptr e = starter_err; starter_err = nullptr; std::rethrow_exception(e); }
+                }
+                ~GpuTeam() { if ( starter.joinable() ) starter.join(); }
+                // after wait(): bucket shards and, for matchUnique, the fold windows
+                void connect(uint64_t nreads, bool unique)
+                {
+                        unsigned int const n = size();
+                        if ( n == 1 ) return;
+                        for ( unsigned int i = 0; i < n; ++i )
+                        {
+                                g[i].check(real_gpu_set_bucket_shard(g[i].h, i, n), "set_bucket_shard");
+                                if ( unique ) g[i].check(real_gpu_fold_init(g[i].h, i, n, nreads, 0), "fold_init");
+                        }
+                        if ( unique )
+                        {
+                                std::vector<real_gpu *> hs(n);
+                                for ( unsigned int i = 0; i < n; ++i ) hs[i] = g[i].h;
+                                for ( unsigned int i = 0; i < n; ++i ) g[i].check(real_gpu_fold_connect_local(g[i].h, &hs[0]), "fold_connect_local");
+                        }
+                }
+                void setReads(ReadSet const & reads, PackedReads const & P)
+                {
+                        parallelFor(size(), [this, &reads, &P](unsigned int i)
+                        {
+                                g[i].check(real_gpu_set_reads_packed(g[i].h, &P.packed[0], &P.byte_offsets[0], P.lengths.empty() ? 0 : &P.lengths[0], 0,
+                                                                     P.wildcard.empty() ? 0 : &P.wildcard[0], reads.quality.empty() ? 0 : &reads.quality[0], reads.size()), "set_reads_packed");
+                        });
+                }
+                void foldUnique()
+                {
+                        if ( size() == 1 ) return;
+                        std::vector<real_gpu *> hs(size());
+                        for ( unsigned int i = 0; i < size(); ++i ) hs[i] = g[i].h;
+                        int const rc = real_gpu_fold_unique_group(&hs[0], size());
+                        if ( rc != REAL_GPU_OK )
+                                for ( unsigned int i = 0; i < size(); ++i ) g[i].check(real_gpu_last_error(g[i].h)[0] ? rc : REAL_GPU_OK, "fold_unique_group");
+                        g[0].check(rc, "fold_unique_group");
+                }
+        };
+
+        // setText for every handle of the team (the bytes of the file are read once; every handle parses them on its GPU)
+        bool setTextTeam(GpuTeam & team, RealOptions const & opts, uint32_t fileid, std::string const & filename, TextFile & T, bool skip_over_limits)
+        {
+                if ( team.size() == 1 )
+                        return setText(team.g[0], opts, fileid, filename, T, skip_over_limits);
+                bool const usable = setText(team.g[0], opts, fileid, filename, T, skip_over_limits);
+                if ( ! usable )
+                        return false;
+                // the other handles: the same call without the messages (its stderr lines are part of the stock behaviour, once)
+                FileBytes buf;
+                char const * const loader = getenv("REAL_TEXT_LOADER");
+                bool const host_loader = loader && std::string(loader) == "host";
+                std::vector<uint64_t> const starts = host_loader ? T.starts() : std::vector<uint64_t>();
+                if ( ! host_loader ) slurp(filename, buf);
+                parallelFor(team.size() - 1, [&](unsigned int k)
+                {
+                        Gpu & G = team.g[k + 1];
+                        if ( host_loader )
+                                G.check(real_gpu_set_text(G.h, fileid, &T.words[0], &T.nmask[0], T.n, 0, T.n, 0, T.n, &starts[0], (uint32_t)(starts.size() - 1)), "set_text");
+                        else
+                        {
+                                uint64_t n = 0, nrec = 0;
+                                G.check(real_gpu_set_text_fasta(G.h, fileid, buf.empty() ? 0 : &buf[0], buf.size(), &n, &nrec), "set_text_fasta");
+                        }
+                });
+                return true;
+        }
+
         void loadReads(RealOptions const & opts, ReadSet & reads)
         {
                 FileBytes buf;
                 PhaseTimer PT;
+                if ( opts.stdin_bytes )
+                        buf.adopt(*opts.stdin_bytes);
+                else
                 slurp(opts.patternfilename, buf);
                 PT.lap("  read pattern file");
                 int qualityOffset = 0;
-                if ( opts.fastq )
+                if ( opts.fastq && opts.stdin_bytes && ! opts.qualityOffset )
+                {
+                        // real.cpp:248-257
+                        std::cerr << "WARNING: automatic quality offset detection not supported when" << std::endl;
+                        std::cerr << "         reading patterns from standard input. Assuming input" << std::endl;
+                        std::cerr << "         was produced by an Illumina  GA (i.e. -Q 64)" << std::endl;
+                        qualityOffset = 64;
+                }
+                else if ( opts.fastq )
                 {
                         qualityOffset = opts.qualityOffset ? opts.qualityOffset : detectQualityOffsetBuffer(buf);
                         if ( ! qualityOffset )
@@ -940,30 +1138,59 @@ namespace
         }
 }
 
+// (patid, k, pos, file, frag, score, inverted): MatchPosAndError::operator< per read (matchAllImplementation.cpp:122-136)
+static bool hitBefore(real_gpu_hit const & a, real_gpu_hit const & b)
+{
+        if ( a.patid != b.patid ) return a.patid < b.patid;
+        if ( a.k != b.k ) return a.k < b.k;
+        if ( a.pos != b.pos ) return a.pos < b.pos;
+        if ( a.file != b.file ) return a.file < b.file;
+        if ( a.frag != b.frag ) return a.frag < b.frag;
+        if ( a.score != b.score ) return a.score < b.score;
+        return a.inverted < b.inverted;
+}
+
 int doMatchingAll(RealOptions const & opts)
 {
         PhaseTimer PT;
-        Gpu G; std::vector<double> ll;
-        HandleStarter starter(G, opts, ll);  // the CUDA context comes up while the pattern file is read
+        GpuTeam team(opts, false);           // the CUDA contexts come up while the pattern file is read
         ReadSet reads;
         loadReads(opts, reads);
         PT.lap("read patterns");            // (the stock -u 0 path parses FASTQ files with the FASTA reader, real.cpp:325-328; here FASTQ is honoured)
+        PackedReads packed;
+        packReads(reads, packed, hostThreads(opts));
         std::vector<std::string> filenames;
         getFileList(opts.textfilename, filenames, ".fa");
-        starter.wait();
-        G.check(real_gpu_set_reads(G.h, reads.mapped.empty() ? 0 : &reads.mapped[0], reads.quality.empty() ? 0 : &reads.quality[0], &reads.offsets[0], reads.size()), "set_reads");
+        team.wait();
+        team.connect(reads.size(), false);
+        team.setReads(reads, packed);
         PT.lap("create + set_reads");
         Output out(opts.outputfilename);
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
         {
                 TextFile T;
-                if ( ! setText(G, opts, (uint32_t)fi, filenames[fi], T, false) )
+                if ( ! setTextTeam(team, opts, (uint32_t)fi, filenames[fi], T, false) )
                 {
                         std::cerr << "file " << filenames[fi] << " is too short for seed length " << opts.seedl << std::endl;
                         continue;
                 }
-                real_gpu_hit const * hits = 0; uint64_t nhits = 0;
-                G.check(real_gpu_match_all(G.h, &hits, &nhits), "match_all");
+                std::vector<real_gpu_hit const *> part(team.size(), (real_gpu_hit const *)0);
+                std::vector<uint64_t> npart(team.size(), 0);
+                parallelFor(team.size(), [&team, &part, &npart](unsigned int i)
+                { team.g[i].check(real_gpu_match_all(team.g[i].h, &part[i], &npart[i]), "match_all"); });
+                // one handle: its rows are in the order of the output already; several: every hit was found by exactly one of them,
+                // the rows are merged into that order here
+                real_gpu_hit const * hits = part[0]; uint64_t nhits = npart[0];
+                std::vector<real_gpu_hit> merged;
+                if ( team.size() > 1 )
+                {
+                        nhits = 0;
+                        for ( unsigned int i = 0; i < team.size(); ++i ) nhits += npart[i];
+                        merged.reserve(nhits);
+                        for ( unsigned int i = 0; i < team.size(); ++i ) merged.insert(merged.end(), part[i], part[i] + npart[i]);
+                        std::sort(merged.begin(), merged.end(), hitBefore);
+                        hits = merged.empty() ? 0 : &merged[0];
+                }
                 PT.lap("text + match_all");
                 bool const scores = opts.scores;
                 formatParallel(nhits, hostThreads(opts), out, [&reads, &T, hits, scores](std::string & o, uint64_t i) -> uint64_t
@@ -1008,22 +1235,25 @@ static uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, u
 int doMatchingUnique(RealOptions const & opts)
 {
         PhaseTimer PT;
-        Gpu G; std::vector<double> ll;
-        HandleStarter starter(G, opts, ll);  // the CUDA context comes up while the pattern file is read
+        GpuTeam team(opts, opts.scores || opts.gaps);     // the CUDA contexts come up while the pattern file is read
         ReadSet reads;
         loadReads(opts, reads);
         PT.lap("read patterns");
         if ( opts.rewritepatterns )
                 reorderLikeRewrite(reads);
+        PackedReads packed;
+        packReads(reads, packed, hostThreads(opts));
         std::vector<std::string> filenames;
         getFileList(opts.textfilename, filenames, ".fa");
-        starter.wait();
-        G.check(real_gpu_set_reads(G.h, reads.mapped.empty() ? 0 : &reads.mapped[0], reads.quality.empty() ? 0 : &reads.quality[0], &reads.offsets[0], reads.size()), "set_reads");
+        team.wait();
+        team.connect(reads.size(), true);
+        team.setReads(reads, packed);
+        Gpu & G = team.g[0];
         std::vector< std::vector< std::pair<std::string, uint64_t> > > rangeset(filenames.size());       // RangeSet
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
         {
                 TextFile T;
-                bool const usable = setText(G, opts, (uint32_t)fi, filenames[fi], T, true);
+                bool const usable = setTextTeam(team, opts, (uint32_t)fi, filenames[fi], T, true);
                 rangeset[fi] = T.ranges;
                 if ( fi >= 64 || T.n >= (1ULL << 35) || T.ranges.size() > 65536 )
                 {
@@ -1034,7 +1264,8 @@ int doMatchingUnique(RealOptions const & opts)
                         continue;
                 if ( opts.scores )
                         G.check(real_gpu_set_block_windows(G.h, planBlockWindows(opts, T, reads.size())), "set_block_windows");
-                G.check(real_gpu_match_unique(G.h), "match_unique");
+                parallelFor(team.size(), [&team](unsigned int i) { team.g[i].check(real_gpu_match_unique(team.g[i].h), "match_unique"); });
+                team.foldUnique();          // several handles: every one now holds the merged state of its own share of the reads
         }
         if ( opts.gaps )
         {
@@ -1050,7 +1281,15 @@ int doMatchingUnique(RealOptions const & opts)
         }
         std::vector<uint64_t> info(reads.size() + 1);
         std::vector<float> score(reads.size() + 1);
-        G.check(real_gpu_get_unique(G.h, &info[0], opts.scores ? &score[0] : 0), "get_unique");
+        {
+                unsigned int const n = team.size();
+                uint64_t const R = reads.size();
+                parallelFor(n, [&team, &info, &score, &opts, n, R](unsigned int i)
+                {
+                        uint64_t const lo = R * i / n, hi = R * (i + 1) / n;          // the reads whose merged state handle i holds
+                        team.g[i].check(real_gpu_get_unique_range(team.g[i].h, lo, hi - lo, &info[lo], opts.scores ? &score[lo] : 0), "get_unique");
+                });
+        }
 
         PT.lap("texts + matching");
         Output out(opts.outputfilename);

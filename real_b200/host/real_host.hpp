@@ -17,6 +17,7 @@
 #define REAL_HOST_HPP
 
 #include <stdint.h>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -50,6 +51,9 @@ struct RealOptions
         bool fastq;
         int threads;            // -T: host threads that format the output (0 = all); the matching runs on the GPU
         int device;             // REAL_GPU_DEVICE, default 0
+        int ngpus;              // REAL_GPUS, default 1: handles (= bucket shards) the matching is spread over, device + i modulo the
+                                // devices present; the order dependent folds (-q 1, -g 1) always run on one handle
+        std::shared_ptr< std::vector<char> > stdin_bytes;   // -p -: the pattern file as read from standard input (RealOptions.cpp:418-426)
 
         RealOptions(int argc, char * argv[]);
         void printHelp() const;
@@ -80,6 +84,7 @@ class FileBytes
         FileBytes() : p(0), n(0), mapped(false) {}
         ~FileBytes();
         void open(std::string const & filename);
+        void adopt(std::vector<char> & bytes);          // takes the bytes over (standard input)
         void close();
         size_t size() const { return n; }
         char const * data() const { return p; }
@@ -100,6 +105,18 @@ void readPatterns(std::string const & filename, bool fastq, int qualityOffset, R
 void readPatternsBuffer(FileBytes const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads);
 // the order the rewritten pattern file hands the reads out in (-R 1): by length, wildcard-free reads first
 void reorderLikeRewrite(ReadSet & reads);
+// The reads 2 bit/base in the layout of the reference's rewritten pattern file (TemporaryFile.hpp:231-268,
+// writePatternDontCareFree): 4 bases per byte, first base in bits 7..6, every read on a byte boundary; reads with a
+// wildcard are flagged (the reference keeps them in a 4 bit/base section of their own) and stored as A.  This is what
+// crosses PCIe (real_gpu_set_reads_packed): a quarter of the byte-per-base form.
+struct PackedReads
+{
+        std::vector<uint8_t> packed;
+        std::vector<uint64_t> byte_offsets;   // nreads + 1
+        std::vector<uint32_t> lengths;
+        std::vector<uint8_t> wildcard;
+};
+void packReads(ReadSet const & reads, PackedReads & out, unsigned int threads);
 
 int doMatchingAll(RealOptions const & opts);
 int doMatchingUnique(RealOptions const & opts);

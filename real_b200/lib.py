@@ -124,7 +124,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_synth_reads.argtypes = [i32, u64, vp, vp, u64, u64, u64, u64, u32, u32, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name)
-        if name not in ("real_gpu_last_error", "real_gpu_stream", "real_gpu_device_bytes"):
+        if name not in ("real_gpu_last_error", "real_gpu_stream", "real_gpu_device_bytes"):      # (real_gpu_device_count returns a plain int)
             fn.restype = i32
     if L.real_gpu_abi_version() != 1:
         raise RuntimeError("libreal_gpu.so ABI version mismatch")

@@ -24,3 +24,15 @@ for name in CASES:
         lines = open(out).read()
         open(os.path.join(OUT, "cli_%s.txt" % name), "w").write(lines)
         print(name, len(lines.splitlines()), "lines")
+
+# patterns from standard input (-p -, RealOptions.cpp:418-426: the type is taken from the first byte, rewriting is forced on)
+STDIN_CASES = ["unique_fq_R0", "unique_fa_R1"]
+for name in STDIN_CASES:
+    with tempfile.TemporaryDirectory() as work:
+        targ, rf, flags = make_case(name, work)
+        out = os.path.join(work, "out.txt")
+        with open(rf, "rb") as fin:
+            p = subprocess.run([REAL, "-t", targ, "-p", "-", "-o", out] + flags, cwd=work, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        lines = open(out).read()
+        open(os.path.join(OUT, "cli_stdin_%s.txt" % name), "w").write(lines)
+        print("stdin", name, len(lines.splitlines()), "lines")
