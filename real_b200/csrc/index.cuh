@@ -859,39 +859,32 @@ __global__ void __launch_bounds__(256, 7) k_build_sub(const uint64_t * __restric
 // One CTA builds that piece of all three tables: item (strand, t) is an entry of table tb when t < nl[tb] (A: pairs (t,t+1),
 // B: (t,t+2), C: (t,t+3)).  The entry arrays of the three tables use the ITEM numbering: the entries of a sub-bucket sit at
 // the front of E[tb][sub_start[sb] ...) -- no per-table offsets are needed; B and C leave the tail of each range unused.
-//   pass 1  presence bits (shared-memory atomics that RETURN the old word: the entry that sets a bit first is the one that
-//           will own the slot's head entry; that fact goes into one flag byte per item in global memory)
-//   ranks   popcount scan per table; slot words written out
-//   pass 2  head entries are written whole (16 bytes, next = none) at E[rank]; same-slot entries (few: the tables are
-//           sparse) are set aside and chained behind the distinct ones after a barrier -- no claim atomics, no next-pointer
-//           initialisation pass
-// Dynamic shared memory per table: presence bits (words u32) and the ranks of the words' first slots (words u16, relative
-// to the sub-bucket: a sub-bucket spans at most 2^16 slots).
+// Dynamic shared memory per table: presence bits and claimed bits (words u32 each) and the ranks of the words' first slots
+// (words u16, relative to the sub-bucket: a sub-bucket spans at most 2^16 slots).
 static const uint32_t SUB3_DUP_CAP = 256;
 struct Build3Params
 {
         const uint64_t * item_seed; const uint32_t * item_val; const uint32_t * sub_start;
-        uint8_t * item_flag;            // one byte per item: bit tb = the item's entry of table tb heads its slot
         TableGeom G[3];                 // G[tb].nlists == 0: table not built
         uint32_t sub_shift, words, first_sub;
         SlotWord * slots[3]; Entry * E[3];
         uint32_t * ndistinct[3];
 };
 
-__global__ void __launch_bounds__(256, 4) k_build_sub3(const __grid_constant__ Build3Params P)
+__global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ Build3Params P)
 {
         extern __shared__ __align__(16) uint32_t sub_smem[];
         uint32_t const words = P.words;
         __shared__ SubDup dup[3][SUB3_DUP_CAP];
-        __shared__ uint32_t ndup[3], dist[3];
+        __shared__ uint32_t ovf[3], ndup[3], dist[3];
         uint32_t const sb = P.first_sub + blockIdx.x;
         uint32_t const s0 = P.sub_start[sb], s1 = P.sub_start[sb+1];
         uint32_t const slot0 = sb << P.sub_shift;
-        uint32_t const tstride = words + (words + 1) / 2;          // per table: presence bits (u32), ranks (u16, relative to s0)
+        uint32_t const tstride = 2 * words + (words + 1) / 2;          // per table: presence bits, claimed bits (u32 each), ranks (u16, relative to s0)
         for ( uint32_t w = threadIdx.x; w < 3 * tstride; w += 256 ) sub_smem[w] = 0;
-        if ( threadIdx.x < 3 ) ndup[threadIdx.x] = 0;
+        if ( threadIdx.x < 3 ) { ovf[threadIdx.x] = 0; ndup[threadIdx.x] = 0; }
         __syncthreads();
-        // pass 1; four items per thread and step, their loads issued together
+        // presence bits of the three tables; four items per thread and step, their loads issued together
         for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
         {
                 uint64_t seed[4]; uint32_t val[4];
@@ -902,31 +895,18 @@ __global__ void __launch_bounds__(256, 4) k_build_sub3(const __grid_constant__ B
                         seed[k] = (i < s1) ? __ldg(P.item_seed + i) : 0;
                         val[k] = (i < s1) ? __ldg(P.item_val + i) : 0;
                 }
-                uint32_t old[4][3], bit[4][3];
-                #pragma unroll
-                for ( int k = 0; k < 4; ++k )
-                {
-                        uint32_t const t = val[k] & 3;
-                        #pragma unroll
-                        for ( int tb = 0; tb < 3; ++tb )
-                        {
-                                old[k][tb] = 0xFFFFFFFFu; bit[k][tb] = 0;
-                                if ( i0 + (uint32_t)k * 256 < s1 && t < P.G[tb].nlists )
-                                {
-                                        uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
-                                        bit[k][tb] = 1u << (l & 31);
-                                        old[k][tb] = atomicOr(&sub_smem[tb * tstride + (l >> 5)], bit[k][tb]);
-                                }
-                        }
-                }
                 #pragma unroll
                 for ( int k = 0; k < 4; ++k )
                         if ( i0 + (uint32_t)k * 256 < s1 )
                         {
-                                uint32_t f = 0;
+                                uint32_t const t = val[k] & 3;
                                 #pragma unroll
-                                for ( int tb = 0; tb < 3; ++tb ) f |= ((old[k][tb] & bit[k][tb]) == 0 && bit[k][tb]) ? (1u << tb) : 0u;
-                                P.item_flag[i0 + (uint32_t)k * 256] = (uint8_t)f;
+                                for ( int tb = 0; tb < 3; ++tb )
+                                        if ( t < P.G[tb].nlists )
+                                        {
+                                                uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
+                                                atomicOr(&sub_smem[tb * tstride + (l >> 5)], 1u << (l & 31));
+                                        }
                         }
         }
         __syncthreads();
@@ -937,7 +917,7 @@ __global__ void __launch_bounds__(256, 4) k_build_sub3(const __grid_constant__ B
         for ( int tb = 0; tb < 3; ++tb )
         {
                 uint32_t * bits = sub_smem + tb * tstride;
-                uint16_t * rank = reinterpret_cast<uint16_t *>(bits + words);
+                uint16_t * rank = reinterpret_cast<uint16_t *>(bits + 2 * words);
                 uint32_t c = 0;
                 for ( uint32_t w = w0; w < min(words, w0 + wpt); ++w ) c += __popc(bits[w]);
                 uint32_t d;
@@ -951,25 +931,27 @@ __global__ void __launch_bounds__(256, 4) k_build_sub3(const __grid_constant__ B
         {
                 if ( ! P.G[tb].nlists ) continue;
                 const uint32_t * bits = sub_smem + tb * tstride;
-                const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + words);
+                const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + 2 * words);
                 for ( uint32_t w = threadIdx.x; w < words; w += 256 )
                 {
                         SlotWord sw; sw.bits = bits[w]; sw.rank = s0 + rank[w];
                         P.slots[tb][(uint64_t)sb * words + w] = sw;
                 }
-                if ( threadIdx.x == 0 && dist[tb] ) atomicAdd(P.ndistinct[tb], dist[tb]);
+                uint32_t const d = dist[tb];
+                for ( uint32_t r = threadIdx.x; r < d; r += 256 ) P.E[tb][s0 + r].next = ENTRY_NONE;
+                if ( threadIdx.x == 0 && d ) atomicAdd(P.ndistinct[tb], d);
         }
-        // pass 2 (the presence bits and ranks are only read from here on: no barrier needed in front)
+        __syncthreads();
+        // entries: the first one of a slot claims E[rank]; the others (few: the tables are sparse) are set aside and chained below
         for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
         {
-                uint64_t seed[4]; uint32_t val[4], flag[4];
+                uint64_t seed[4]; uint32_t val[4];
                 #pragma unroll
                 for ( int k = 0; k < 4; ++k )
                 {
                         uint32_t const i = i0 + (uint32_t)k * 256;
                         seed[k] = (i < s1) ? __ldg(P.item_seed + i) : 0;
                         val[k] = (i < s1) ? __ldg(P.item_val + i) : 0;
-                        flag[k] = (i < s1) ? P.item_flag[i] : 0u;         // written by this very thread in pass 1
                 }
                 #pragma unroll
                 for ( int k = 0; k < 4; ++k )
@@ -980,16 +962,16 @@ __global__ void __launch_bounds__(256, 4) k_build_sub3(const __grid_constant__ B
                                 for ( int tb = 0; tb < 3; ++tb )
                                         if ( t < P.G[tb].nlists )
                                         {
-                                                const uint32_t * bits = sub_smem + tb * tstride;
-                                                const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + words);
+                                                uint32_t * bits = sub_smem + tb * tstride, * claimed = bits + words;
+                                                const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + 2 * words);
                                                 uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
-                                                uint32_t const bitm = 1u << (l & 31);
-                                                uint32_t const r = s0 + rank[l >> 5] + __popc(bits[l >> 5] & (bitm - 1));
+                                                uint32_t const bit = 1u << (l & 31);
+                                                uint32_t const r = s0 + rank[l >> 5] + __popc(bits[l >> 5] & (bit - 1));
                                                 Entry * E = P.E[tb];
-                                                if ( (flag[k] >> tb) & 1 )
+                                                if ( ! (atomicOr(&claimed[l >> 5], bit) & bit) )
                                                 {
-                                                        Entry en; en.seed = seed[k]; en.val = val[k]; en.next = ENTRY_NONE;
-                                                        *reinterpret_cast<uint4 *>(E + r) = *reinterpret_cast<uint4 *>(&en);
+                                                        E[r].seed = seed[k];
+                                                        E[r].val = val[k];
                                                 }
                                                 else
                                                 {
@@ -1001,20 +983,21 @@ __global__ void __launch_bounds__(256, 4) k_build_sub3(const __grid_constant__ B
                                                         }
                                                         else
                                                         {
-                                                                // more same-slot entries than are set aside: parked in their final place, linked below
-                                                                Entry en; en.seed = seed[k]; en.val = val[k]; en.next = r;
-                                                                E[s0 + dist[tb] + j] = en;
+                                                                uint32_t const o = s0 + dist[tb] + SUB3_DUP_CAP + atomicAdd(&ovf[tb], 1u);
+                                                                Entry en; en.seed = seed[k]; en.val = val[k];
+                                                                en.next = atomicExch(&E[r].next, o);
+                                                                E[o] = en;
                                                         }
                                                 }
                                         }
                         }
         }
         __syncthreads();
-        // the same-slot entries go behind the distinct ones of this sub-bucket and are chained to their slot's head
+        // the set-aside entries go behind the distinct ones of this sub-bucket
         #pragma unroll 1
         for ( int tb = 0; tb < 3; ++tb )
         {
-                uint32_t const nall = ndup[tb], nd = min(nall, SUB3_DUP_CAP);
+                uint32_t const nd = min(ndup[tb], SUB3_DUP_CAP);
                 Entry * E = P.E[tb];
                 for ( uint32_t j = threadIdx.x; j < nd; j += 256 )
                 {
@@ -1023,12 +1006,6 @@ __global__ void __launch_bounds__(256, 4) k_build_sub3(const __grid_constant__ B
                         Entry en; en.seed = dd.seed; en.val = dd.val;
                         en.next = atomicExch(&E[dd.r].next, o);
                         E[o] = en;
-                }
-                for ( uint32_t j = SUB3_DUP_CAP + threadIdx.x; j < nall; j += 256 )
-                {
-                        uint32_t const o = s0 + dist[tb] + j;
-                        uint32_t const r = E[o].next;                        // the head's index was parked here
-                        E[o].next = atomicExch(&E[r].next, o);
                 }
         }
 }

@@ -84,7 +84,7 @@ struct real_gpu
         DevBuf rec_win, rec_pos, part_meta, own_list, large_list;
         DevBuf win_valid, win_counts, bounds, gapres, gaps, boffs, flags8;   // reference text blocks (order-faithful replay)
         uint64_t n_list;               // windows per reference text block, 0 = one block per file
-        DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp, ws_iflag;   // index build workspace, kept between calls
+        DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
         uint32_t * table_counts;       // [6] pinned host memory; per table: entries, distinct slots (copied back asynchronously by the build)
         const uint8_t * src_packed; const uint64_t * src_byte_offsets; uint32_t src_packed_uniform;   // 2-bit input (set_reads_packed)
         const uint8_t * src_mapped;    // device pointer the reads are packed from (caller's buffer or h->mapped)
@@ -538,9 +538,7 @@ bool build_tables_fused(real_gpu * h, TablePlan * plan)
         Grouped const GR = partition_entries(h, TP);
         B.item_seed = GR.seed; B.item_val = GR.val; B.sub_start = GR.start;
         B.sub_shift = TP.sub_shift; B.words = TP.words; B.first_sub = TP.first_sub;
-        dev_reserve(h, h->ws_iflag, cap_items + 64);
-        B.item_flag = ptr<uint8_t>(h->ws_iflag);
-        size_t const smem = (size_t)3 * (TP.words + (TP.words + 1) / 2) * 4;
+        size_t const smem = (size_t)3 * (2 * TP.words + (TP.words + 1) / 2) * 4;
         RG_CUDA(cudaFuncSetAttribute(k_build_sub3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_build_sub3<<<TP.own_subs, 256, smem, h->st>>>(B);
         RG_KERNEL_CHECK(); launch_count(h);
@@ -1140,7 +1138,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ws_iflag, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
                            &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
