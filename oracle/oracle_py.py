@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_HARNESS = os.path.join(HERE, "_ref", "ref_harness")
+REF_BOUND = os.path.join(HERE, "_ref", "real_bound")
 
 HIT_DTYPE = np.dtype([("patid", "<u8"), ("pos", "<u8"), ("file", "<u4"), ("frag", "<u4"),
                       ("k", "<u4"), ("inverted", "<u4"), ("score", "<f4"), ("block", "<u4")])
@@ -44,6 +45,9 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir("/root/reference/src"):
         subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+        # the reference binary with its matching loops bound to libreal_gpu.so; needs the library
+        if os.path.exists(os.path.join(HERE, "..", "real_b200", "libreal_gpu.so")):
+            subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref_bound"])
 
 
 _lib = None
