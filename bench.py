@@ -59,6 +59,8 @@ SEED = 0x5EA1
 # canonical unique state / matcher.hits_checksum of the matchAll rows).  The single-GPU run is gated on the reference
 # (parity_checked) and property-checked at full size (tests/test_gpu_fullsize.py); a multi-GPU run must reproduce the digest.
 EXPECTED_DIGEST = {
+    "c3": 0xf32fdc56b7229760,
+    "tiny": 0x70668eb87d6ea3c8,
 }
 
 
@@ -646,7 +648,11 @@ def main():
             gather = rdist.ShardedUpload(sections, dev)
             gather_text = rdist.ShardedUpload([("words", h_w.view(torch.uint8)), ("nmask", h_m.view(torch.uint8))], dev)
 
+        e2e_phase = {"h2d_reads_ms": [], "h2d_text_ms": [], "pack_ms": [], "index_ms": [], "scan_ms": [], "fold_ms": [], "d2h_ms": [],
+                     "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": [], "api_exchange_ms": [], "api_get_ms": []}
+
         def step_host():
+            t0 = time.perf_counter()
             if gather is not None:
                 d = gather.run()
                 h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
@@ -655,28 +661,47 @@ def main():
                 h.set_text_device(d["words"].data_ptr(), d["nmask"].data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
             else:
                 h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
+                t1 = time.perf_counter()
                 h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+            t2 = time.perf_counter()
+            if gather is not None:
+                t1 = t2
+            t4 = t3 = t2
             if unique:
                 h.match_unique()
                 if gaps:
                     h.match_gaps(0)
+                t3 = time.perf_counter()
+                st = h.stats()
                 if world > 1:
                     exchange()
+                    st["fold_ms"] = h.stats()["fold_ms"]
+                t4 = time.perf_counter()
                 # after the exchange every rank holds the merged state of (at least) its own 1/N of the reads: it reads that back
                 h.get_unique(out=np_info[r_lo:r_hi], first=r_lo, count=r_hi - r_lo)
+                st["d2h_ms"] = h.stats()["d2h_ms"]
                 d2h[0] = (r_hi - r_lo) * 8
             else:
                 nh = h.match_all_count()          # records land in the library's pinned host buffer
+                t4 = t3 = time.perf_counter()
+                st = h.stats()
                 d2h[0] = nh * 40
-            return {}
+            t5 = time.perf_counter()
+            st.update(api_set_reads_ms=(t1 - t0) * 1e3, api_set_text_ms=(t2 - t1) * 1e3, api_match_ms=(t3 - t2) * 1e3,
+                      api_exchange_ms=(t4 - t3) * 1e3, api_get_ms=(t5 - t4) * 1e3)
+            return st
+
+        def collect_e2e(st):
+            for k in e2e_phase:
+                e2e_phase[k].append(st.get(k, 0.0))
 
         e_steps = max(1, min(args.steps, 3))
-        e_ms, _ = timed(step_host, e_steps, 1)
+        e_ms, _ = timed(step_host, e_steps, 1, collect_e2e)
         h2d = R * L4 + R + (R * L if qual is not None else 0) + np_w.nbytes + np_m.nbytes + rs.nbytes
         if gather is not None:
             h2d = gather.chunk + gather_text.chunk + rs.nbytes          # per rank; the rest arrives over NVLink
         e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-               "ms_per_step": e_ms / e_steps, "steps": e_steps,
+               "ms_per_step": e_ms / e_steps, "steps": e_steps, "phases_ms": {k: statistics.mean(v) for k, v in e2e_phase.items() if v},
                "input": "host buffers: text 2 bit/base + N mask, reads 2 bit/base (the reference's rewritten pattern file layout), "
                         "qualities 1 byte/base when scoring; result read back to pinned host memory"
                         + ("; every rank uploads 1/%d of the bytes, NCCL all-gather over NVLink for the rest (h2d_bytes_per_step is per rank)" % world

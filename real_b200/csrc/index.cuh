@@ -876,13 +876,13 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
         extern __shared__ __align__(16) uint32_t sub_smem[];
         uint32_t const words = P.words;
         __shared__ SubDup dup[3][SUB3_DUP_CAP];
-        __shared__ uint32_t ovf[3], ndup[3], dist[3];
+        __shared__ uint32_t ndup[3], dist[3];
         uint32_t const sb = P.first_sub + blockIdx.x;
         uint32_t const s0 = P.sub_start[sb], s1 = P.sub_start[sb+1];
         uint32_t const slot0 = sb << P.sub_shift;
         uint32_t const tstride = 2 * words + (words + 1) / 2;          // per table: presence bits, claimed bits (u32 each), ranks (u16, relative to s0)
         for ( uint32_t w = threadIdx.x; w < 3 * tstride; w += 256 ) sub_smem[w] = 0;
-        if ( threadIdx.x < 3 ) { ovf[threadIdx.x] = 0; ndup[threadIdx.x] = 0; }
+        if ( threadIdx.x < 3 ) ndup[threadIdx.x] = 0;
         __syncthreads();
         // presence bits of the three tables; four items per thread and step, their loads issued together
         for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
@@ -937,12 +937,12 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
                         SlotWord sw; sw.bits = bits[w]; sw.rank = s0 + rank[w];
                         P.slots[tb][(uint64_t)sb * words + w] = sw;
                 }
-                uint32_t const d = dist[tb];
-                for ( uint32_t r = threadIdx.x; r < d; r += 256 ) P.E[tb][s0 + r].next = ENTRY_NONE;
-                if ( threadIdx.x == 0 && d ) atomicAdd(P.ndistinct[tb], d);
+                if ( threadIdx.x == 0 && dist[tb] ) atomicAdd(P.ndistinct[tb], dist[tb]);
         }
         __syncthreads();
-        // entries: the first one of a slot claims E[rank]; the others (few: the tables are sparse) are set aside and chained below
+        // entries: the first one of a slot claims E[rank] and writes the whole 16-byte head (next = none) with one store; the
+        // others (few: the tables are sparse) are set aside -- or, beyond the capacity of the list, parked in their final place
+        // with the head's index in `next` -- and chained after the barrier, when every head stands
         for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
         {
                 uint64_t seed[4]; uint32_t val[4];
@@ -970,8 +970,8 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
                                                 Entry * E = P.E[tb];
                                                 if ( ! (atomicOr(&claimed[l >> 5], bit) & bit) )
                                                 {
-                                                        E[r].seed = seed[k];
-                                                        E[r].val = val[k];
+                                                        Entry en; en.seed = seed[k]; en.val = val[k]; en.next = ENTRY_NONE;
+                                                        *reinterpret_cast<uint4 *>(E + r) = *reinterpret_cast<const uint4 *>(&en);
                                                 }
                                                 else
                                                 {
@@ -983,10 +983,8 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
                                                         }
                                                         else
                                                         {
-                                                                uint32_t const o = s0 + dist[tb] + SUB3_DUP_CAP + atomicAdd(&ovf[tb], 1u);
-                                                                Entry en; en.seed = seed[k]; en.val = val[k];
-                                                                en.next = atomicExch(&E[r].next, o);
-                                                                E[o] = en;
+                                                                Entry en; en.seed = seed[k]; en.val = val[k]; en.next = r;
+                                                                *reinterpret_cast<uint4 *>(E + s0 + dist[tb] + j) = *reinterpret_cast<const uint4 *>(&en);
                                                         }
                                                 }
                                         }
@@ -997,7 +995,7 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
         #pragma unroll 1
         for ( int tb = 0; tb < 3; ++tb )
         {
-                uint32_t const nd = min(ndup[tb], SUB3_DUP_CAP);
+                uint32_t const nd = min(ndup[tb], SUB3_DUP_CAP);          // (ndup counts every same-slot entry, parked ones included)
                 Entry * E = P.E[tb];
                 for ( uint32_t j = threadIdx.x; j < nd; j += 256 )
                 {
@@ -1005,7 +1003,13 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
                         uint32_t const o = s0 + dist[tb] + j;
                         Entry en; en.seed = dd.seed; en.val = dd.val;
                         en.next = atomicExch(&E[dd.r].next, o);
-                        E[o] = en;
+                        *reinterpret_cast<uint4 *>(E + o) = *reinterpret_cast<const uint4 *>(&en);
+                }
+                for ( uint32_t j = SUB3_DUP_CAP + threadIdx.x; j < ndup[tb]; j += 256 )
+                {
+                        uint32_t const o = s0 + dist[tb] + j;
+                        uint32_t const r = E[o].next;                        // the head's index was parked here
+                        E[o].next = atomicExch(&E[r].next, o);
                 }
         }
 }
