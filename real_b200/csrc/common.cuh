@@ -221,6 +221,12 @@ __device__ __forceinline__ uint64_t policy_evict_last()
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
         return pol;
 }
+__device__ __forceinline__ uint64_t policy_evict_normal()
+{
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+        return pol;
+}
 __device__ __forceinline__ uint64_t policy_evict_first()
 {
         uint64_t pol;

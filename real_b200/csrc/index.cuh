@@ -871,20 +871,26 @@ struct Build3Params
         uint32_t * ndistinct[3];
 };
 
-__global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ Build3Params P)
+// SPLIT: one CTA per (sub-bucket, table) -- a third of the shared memory and fewer registers per CTA, so that enough CTAs
+// are resident to hide the latencies of a kernel that is a chain of short phases (items -> presence bits -> ranks -> heads)
+template<bool SPLIT>
+__global__ void __launch_bounds__(256, SPLIT ? 6 : 3) k_build_sub3(const __grid_constant__ Build3Params P)
 {
         extern __shared__ __align__(16) uint32_t sub_smem[];
         uint32_t const words = P.words;
-        __shared__ SubDup dup[3][SUB3_DUP_CAP];
-        __shared__ uint32_t ndup[3], dist[3];
-        uint32_t const sb = P.first_sub + blockIdx.x;
+        constexpr int NT = SPLIT ? 1 : 3;                          // tables of this CTA
+        __shared__ SubDup dup[NT][SUB3_DUP_CAP];
+        __shared__ uint32_t ndup[NT], dist[NT];
+        uint32_t const sb = P.first_sub + (SPLIT ? blockIdx.x / 3 : blockIdx.x);
+        int const tb0 = SPLIT ? (int)(blockIdx.x % 3) : 0;
+        if ( SPLIT && ! P.G[tb0].nlists ) return;
         uint32_t const s0 = P.sub_start[sb], s1 = P.sub_start[sb+1];
         uint32_t const slot0 = sb << P.sub_shift;
         uint32_t const tstride = 2 * words + (words + 1) / 2;          // per table: presence bits, claimed bits (u32 each), ranks (u16, relative to s0)
-        for ( uint32_t w = threadIdx.x; w < 3 * tstride; w += 256 ) sub_smem[w] = 0;
-        if ( threadIdx.x < 3 ) ndup[threadIdx.x] = 0;
+        for ( uint32_t w = threadIdx.x; w < NT * tstride; w += 256 ) sub_smem[w] = 0;
+        if ( threadIdx.x < NT ) ndup[threadIdx.x] = 0;
         __syncthreads();
-        // presence bits of the three tables; four items per thread and step, their loads issued together
+        // presence bits; four items per thread and step, their loads issued together
         for ( uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 1024 )
         {
                 uint64_t seed[4]; uint32_t val[4];
@@ -901,12 +907,15 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
                         {
                                 uint32_t const t = val[k] & 3;
                                 #pragma unroll
-                                for ( int tb = 0; tb < 3; ++tb )
+                                for ( int u = 0; u < NT; ++u )
+                                {
+                                        int const tb = tb0 + u;
                                         if ( t < P.G[tb].nlists )
                                         {
                                                 uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
-                                                atomicOr(&sub_smem[tb * tstride + (l >> 5)], 1u << (l & 31));
+                                                atomicOr(&sub_smem[u * tstride + (l >> 5)], 1u << (l & 31));
                                         }
+                                }
                         }
         }
         __syncthreads();
@@ -914,30 +923,31 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
         uint32_t const wpt = (words + 255) / 256;
         uint32_t const w0 = threadIdx.x * wpt;
         #pragma unroll 1
-        for ( int tb = 0; tb < 3; ++tb )
+        for ( int u = 0; u < NT; ++u )
         {
-                uint32_t * bits = sub_smem + tb * tstride;
+                uint32_t * bits = sub_smem + u * tstride;
                 uint16_t * rank = reinterpret_cast<uint16_t *>(bits + 2 * words);
                 uint32_t c = 0;
                 for ( uint32_t w = w0; w < min(words, w0 + wpt); ++w ) c += __popc(bits[w]);
                 uint32_t d;
                 uint32_t run = block_excl_scan(c, &d);                    // < 2^16: a sub-bucket spans at most 2^16 slots
                 for ( uint32_t w = w0; w < min(words, w0 + wpt); ++w ) { rank[w] = (uint16_t)run; run += __popc(bits[w]); }
-                if ( threadIdx.x == 0 ) dist[tb] = d;
+                if ( threadIdx.x == 0 ) dist[u] = d;
         }
         __syncthreads();
         #pragma unroll 1
-        for ( int tb = 0; tb < 3; ++tb )
+        for ( int u = 0; u < NT; ++u )
         {
+                int const tb = tb0 + u;
                 if ( ! P.G[tb].nlists ) continue;
-                const uint32_t * bits = sub_smem + tb * tstride;
+                const uint32_t * bits = sub_smem + u * tstride;
                 const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + 2 * words);
                 for ( uint32_t w = threadIdx.x; w < words; w += 256 )
                 {
                         SlotWord sw; sw.bits = bits[w]; sw.rank = s0 + rank[w];
                         P.slots[tb][(uint64_t)sb * words + w] = sw;
                 }
-                if ( threadIdx.x == 0 && dist[tb] ) atomicAdd(P.ndistinct[tb], dist[tb]);
+                if ( threadIdx.x == 0 && dist[u] ) atomicAdd(P.ndistinct[tb], dist[u]);
         }
         __syncthreads();
         // entries: the first one of a slot claims E[rank] and writes the whole 16-byte head (next = none) with one store; the
@@ -959,10 +969,12 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
                         {
                                 uint32_t const t = val[k] & 3;
                                 #pragma unroll
-                                for ( int tb = 0; tb < 3; ++tb )
+                                for ( int u = 0; u < NT; ++u )
+                                {
+                                        int const tb = tb0 + u;
                                         if ( t < P.G[tb].nlists )
                                         {
-                                                uint32_t * bits = sub_smem + tb * tstride, * claimed = bits + words;
+                                                uint32_t * bits = sub_smem + u * tstride, * claimed = bits + words;
                                                 const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + 2 * words);
                                                 uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
                                                 uint32_t const bit = 1u << (l & 31);
@@ -975,39 +987,40 @@ __global__ void __launch_bounds__(256, 3) k_build_sub3(const __grid_constant__ B
                                                 }
                                                 else
                                                 {
-                                                        uint32_t const j = atomicAdd(&ndup[tb], 1u);
+                                                        uint32_t const j = atomicAdd(&ndup[u], 1u);
                                                         if ( j < SUB3_DUP_CAP )
                                                         {
                                                                 SubDup dd; dd.seed = seed[k]; dd.val = val[k]; dd.r = r;
-                                                                dup[tb][j] = dd;
+                                                                dup[u][j] = dd;
                                                         }
                                                         else
                                                         {
                                                                 Entry en; en.seed = seed[k]; en.val = val[k]; en.next = r;
-                                                                *reinterpret_cast<uint4 *>(E + s0 + dist[tb] + j) = *reinterpret_cast<const uint4 *>(&en);
+                                                                *reinterpret_cast<uint4 *>(E + s0 + dist[u] + j) = *reinterpret_cast<const uint4 *>(&en);
                                                         }
                                                 }
                                         }
+                                }
                         }
         }
         __syncthreads();
         // the set-aside entries go behind the distinct ones of this sub-bucket
         #pragma unroll 1
-        for ( int tb = 0; tb < 3; ++tb )
+        for ( int u = 0; u < NT; ++u )
         {
-                uint32_t const nd = min(ndup[tb], SUB3_DUP_CAP);          // (ndup counts every same-slot entry, parked ones included)
-                Entry * E = P.E[tb];
+                uint32_t const nd = min(ndup[u], SUB3_DUP_CAP);          // (ndup counts every same-slot entry, parked ones included)
+                Entry * E = P.E[tb0 + u];
                 for ( uint32_t j = threadIdx.x; j < nd; j += 256 )
                 {
-                        SubDup const dd = dup[tb][j];
-                        uint32_t const o = s0 + dist[tb] + j;
+                        SubDup const dd = dup[u][j];
+                        uint32_t const o = s0 + dist[u] + j;
                         Entry en; en.seed = dd.seed; en.val = dd.val;
                         en.next = atomicExch(&E[dd.r].next, o);
                         *reinterpret_cast<uint4 *>(E + o) = *reinterpret_cast<const uint4 *>(&en);
                 }
-                for ( uint32_t j = SUB3_DUP_CAP + threadIdx.x; j < ndup[tb]; j += 256 )
+                for ( uint32_t j = SUB3_DUP_CAP + threadIdx.x; j < ndup[u]; j += 256 )
                 {
-                        uint32_t const o = s0 + dist[tb] + j;
+                        uint32_t const o = s0 + dist[u] + j;
                         uint32_t const r = E[o].next;                        // the head's index was parked here
                         E[o].next = atomicExch(&E[r].next, o);
                 }

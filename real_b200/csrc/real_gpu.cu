@@ -538,9 +538,22 @@ bool build_tables_fused(real_gpu * h, TablePlan * plan)
         Grouped const GR = partition_entries(h, TP);
         B.item_seed = GR.seed; B.item_val = GR.val; B.sub_start = GR.start;
         B.sub_shift = TP.sub_shift; B.words = TP.words; B.first_sub = TP.first_sub;
-        size_t const smem = (size_t)3 * (2 * TP.words + (TP.words + 1) / 2) * 4;
-        RG_CUDA(cudaFuncSetAttribute(k_build_sub3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_build_sub3<<<TP.own_subs, 256, smem, h->st>>>(B);
+        // one CTA per (sub-bucket, table) by default: three times the CTAs with a third of the shared memory each (measured, r02);
+        // REAL_GPU_BUILD_SPLIT=0: one CTA builds the sub-bucket of all three tables
+        bool split = true;
+        if ( const char * e = getenv("REAL_GPU_BUILD_SPLIT") ) split = atoi(e) != 0;
+        size_t const smem1 = (size_t)(2 * TP.words + (TP.words + 1) / 2) * 4;
+        size_t const smem = split ? smem1 : 3 * smem1;
+        if ( split )
+        {
+                RG_CUDA(cudaFuncSetAttribute(k_build_sub3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_build_sub3<true><<<TP.own_subs * 3, 256, smem, h->st>>>(B);
+        }
+        else
+        {
+                RG_CUDA(cudaFuncSetAttribute(k_build_sub3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_build_sub3<false><<<TP.own_subs, 256, smem, h->st>>>(B);
+        }
         RG_KERNEL_CHECK(); launch_count(h);
         RG_CUDA(cudaMemcpyAsync(&h->table_counts[0], TP.d_total, 16, cudaMemcpyDeviceToHost, h->st));   // items, distinct slots of A, B, C
         h->fused_build = true;
@@ -1040,7 +1053,7 @@ void preload_kernels(int device)
         cudaFuncAttributes a;
 #define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
         RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_seeds_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
-        RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub); RG_PRELOAD(k_build_sub3);
+        RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub); RG_PRELOAD(k_build_sub3<true>); RG_PRELOAD(k_build_sub3<false>);
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
         RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter<false>); RG_PRELOAD(k_part_scatter<true>); RG_PRELOAD(k_own_list); RG_PRELOAD((k_bucket_probe<false, false>)); RG_PRELOAD((k_bucket_probe<true, false>)); RG_PRELOAD((k_bucket_probe<false, true>)); RG_PRELOAD((k_bucket_probe<true, true>));
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
@@ -1770,8 +1783,8 @@ int real_gpu_comm_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t ro
         if ( nranks < 1 || nranks > (uint32_t)SC_MAX_RANKS || rank >= nranks ) return fail(h, REAL_GPU_E_ARG, "comm_init: rank/nranks out of range (at most 8 ranks)");
         real_gpu::Comm & CM = h->comm;
         if ( CM.window.p ) return fail(h, REAL_GPU_E_STATE, "comm_init: already initialised");
-        if ( round_positions == 0 ) round_positions = SC_MAX_CHUNK;
-        round_positions = std::min<uint64_t>(SC_MAX_CHUNK, ((round_positions + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
+        if ( round_positions == 0 ) round_positions = SC_MAX_ROUND;
+        round_positions = std::min<uint64_t>(SC_MAX_ROUND, ((round_positions + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
         CM.nranks = nranks; CM.rank = rank; CM.epoch = 0; CM.round_positions = round_positions; CM.connected = false;
         for ( uint32_t r = 0; r <= nranks; ++r ) CM.bucket_lo[r] = (uint32_t)(((uint64_t)r * SC_MAX_BUCKETS) / nranks);
         uint64_t const per = (round_positions + nranks - 1) / nranks;

@@ -54,7 +54,8 @@ static const int SC_RPT = REAL_SC_RPT;                       // records per lane
 static const int SC_QA_CAP = 32 + 96 * SC_RPT;               // per-warp stage A queue (set slot bits): drained from 32 up, a step adds <= 96 per record and lane
 static const int SC_QB_CAP = 64;                             // per-warp stage B queue (seed test passed)
 static const uint32_t SC_POS_NONE = 0xFFFFFFFFu;             // position word of a padding record
-static const uint64_t SC_MAX_CHUNK = 1ull << 30;             // positions per chunk: position (30 bits) and table (2 bits) share a word
+static const uint64_t SC_MAX_CHUNK = 0xFFF00000ull;         // positions per chunk: a record holds its position relative to the chunk in 32 bits (all ones = padding)
+static const uint64_t SC_MAX_ROUND = 1ull << 30;             // sharded tables: positions per round (sizes the record areas of the windows)
 
 static const int SC_MAX_RANKS = 8;                           // GPUs of one NVSwitch box that can share a scan (sharded tables)
 static const int SC_META_STRIDE = SC_MAX_BUCKETS + 8;        // u32 per source in a rank's bucket-count area
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(SC_PAIR_THREADS) k_comm_pairs(ScanParams P, co
 
 // ---- probe -------------------------------------------------------------------------------------
 
-struct ItemA { uint64_t win; uint32_t before; uint32_t post; };      // a set slot bit: window, bases in front, position | table << 30 (entry index: ProbeSmem::qe)
+struct ItemA { uint64_t win; uint32_t before; uint32_t post; };      // a set slot bit: window, bases in front, position in the chunk (entry index: ProbeSmem::qe, table: ProbeSmem::qt)
 struct ItemB { uint64_t lp; uint32_t id; uint32_t exact; };           // an entry that passed the seed test (exact: bit f = fragment f matches exactly)
 
 struct ProbeSmem
@@ -776,6 +777,7 @@ struct ProbeSmem
         ItemA qa[SC_THREADS / 32][SC_QA_CAP];
         ItemB qb[SC_THREADS / 32][SC_QB_CAP];
         uint32_t qe[SC_THREADS / 32][SC_QA_CAP];        // entry index (rank of the slot) of the stage A items
+        uint8_t qt[SC_THREADS / 32][SC_QA_CAP];         // table of the stage A items
         uint32_t qbn[SC_THREADS / 32];
         uint32_t stat[3][SC_THREADS];                   // per thread: candidates, seed passes, hits (far below 2^32 per launch)
 };
@@ -951,12 +953,11 @@ __device__ __forceinline__ uint32_t verify_and_report(ScanParams const & P, uint
 // (match.hpp:386-388) and the canonical-list rule: of the up to six lists that reach a position,
 // only the pair made of the two LOWEST exact fragments reports it (replaces unifyMatches' dedup)
 template<bool WIDE, bool PACKED>
-__device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, uint32_t e, ItemB * qb, uint32_t * qbn, uint32_t * lstats, uint64_t pol_e)
+__device__ __forceinline__ void follow_item(ScanParams const & P, ItemA const & it, uint32_t e, int const table, ItemB * qb, uint32_t * qbn, uint32_t * lstats, uint64_t pol_e)
 {
-        int const table = (int)(it.post >> 30);
         uint32_t const F = P.F;
         uint64_t const fm = (1ULL << (2*F)) - 1;
-        uint64_t const lx = P.pos_base + (it.post & 0x3FFFFFFFu);
+        uint64_t const lx = P.pos_base + it.post;
         while ( e != ENTRY_NONE )
         {
                 uint4 const raw = ld_hot_v4(P.tab[table].E + e, pol_e);
@@ -1021,17 +1022,18 @@ __device__ __forceinline__ uint32_t drain_a_warp(ScanParams const & P, ProbeSmem
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const ItemA * qa = S.qa[wid];
         const uint32_t * qe = S.qe[wid];
+        const uint8_t * qt = S.qt[wid];
         ItemB * qb = S.qb[wid];
         uint32_t * qbn = &S.qbn[wid];
         uint32_t lstats[3] = {0, 0, 0};
         // entries are touched about once per bucket pass: by default they go through L2 with evict_first priority so
         // that they do not push the presence words (probed several times per line) out of the protected set
-        uint64_t const pol_e = (P.debug_flags & 2) ? policy_evict_last() : policy_evict_first();
+        uint64_t const pol_e = (P.debug_flags & 2) ? policy_evict_last() : ((P.debug_flags & 4) ? policy_evict_normal() : policy_evict_first());
         while ( n >= 32 || (flush && n) )
         {
                 uint32_t const take = n >= 32 ? 32u : n;
                 if ( (uint32_t)lane < take )
-                        follow_item<WIDE, PACKED>(P, qa[n - take + lane], qe[n - take + lane], qb, qbn, lstats, pol_e);
+                        follow_item<WIDE, PACKED>(P, qa[n - take + lane], qe[n - take + lane], (int)qt[n - take + lane], qb, qbn, lstats, pol_e);
                 __syncwarp();
                 n -= take;
                 if ( *qbn >= 32 )
@@ -1069,6 +1071,7 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
         uint32_t const lt = (1u << lane) - 1;
         ItemA * qa = S.qa[wid];
         uint32_t * qe = S.qe[wid];
+        uint8_t * qt = S.qt[wid];
         uint32_t qn = 0;                 // items in the stage A queue; warp uniform, kept in a register
 
         if ( lane == 0 ) S.qbn[wid] = 0;
@@ -1160,8 +1163,9 @@ __global__ void __launch_bounds__(SC_THREADS, REAL_PROBE_MINB) k_bucket_probe(co
                                                 if ( set )
                                                 {
                                                         uint32_t const o = qn + __popc(bal & lt);
-                                                        ItemA ia; ia.win = ((uint64_t)cur[k].y << 32) | cur[k].x; ia.before = cur[k].z; ia.post = cur[k].w | ((uint32_t)t << 30);
+                                                        ItemA ia; ia.win = ((uint64_t)cur[k].y << 32) | cur[k].x; ia.before = cur[k].z; ia.post = cur[k].w;
                                                         qa[o] = ia;
+                                                        qt[o] = (uint8_t)t;
                                                         qe[o] = sw[k][t].rank + __popc(sw[k][t].bits & ((1u << ((bits5[k] >> (5 * t)) & 31)) - 1));
                                                 }
                                                 qn += __popc(bal);
