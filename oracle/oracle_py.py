@@ -64,6 +64,8 @@ def lib():
         L.oracle_match_unique.argtypes = [C.POINTER(Params), C.POINTER(TextS), C.POINTER(ReadsS), C.c_void_p, C.c_void_p]
         L.oracle_match_gaps.restype = C.c_int
         L.oracle_match_gaps.argtypes = [C.POINTER(Params), C.POINTER(TextS), C.POINTER(ReadsS), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_match_gaps_flagged.restype = C.c_int
+        L.oracle_match_gaps_flagged.argtypes = [C.POINTER(Params), C.POINTER(TextS), C.POINTER(ReadsS), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_unique_init.restype = None
         L.oracle_unique_init.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p]
         L.oracle_build_ll.restype = None
@@ -171,13 +173,16 @@ def match_unique(text, reads, info, score, seedl=32, seedkmax=2, totalkmax=5, sc
 
 
 def match_gaps(text, reads, info, score, gaps, seedl=32, seedkmax=2, totalkmax=5, scores=True, ll=None, n_list=0,
-               fileid=0, filter_level=2) -> None:
+               fileid=0, filter_level=2, undefined=None) -> None:
+    """undefined (uint8 per read, optional): set where the reference's own result is not defined -- a candidate whose band
+    never reaches MINscore leaves ::matchGaps' uninitialised locals unassigned (match.hpp:518-522)."""
     keep = _Keep()
     if ll is None:
         ll = build_ll()
     P, T, R = _mk(keep, seedl, seedkmax, totalkmax, scores, filter_mult(totalkmax, filter_level), ll, n_list, text, reads, fileid)
-    r = lib().oracle_match_gaps(C.byref(P), C.byref(T), C.byref(R), info.ctypes.data,
-                                score.ctypes.data if score is not None else None, gaps.ctypes.data)
+    r = lib().oracle_match_gaps_flagged(C.byref(P), C.byref(T), C.byref(R), info.ctypes.data,
+                                        score.ctypes.data if score is not None else None, gaps.ctypes.data,
+                                        undefined.ctypes.data if undefined is not None else None)
     if r != 0:
         raise RuntimeError("oracle_match_gaps failed")
 

@@ -805,7 +805,7 @@ static double total_scoring(uint32_t gap, double cur, double open, double extend
         return cur + (gap * extend) + open;
 }
 
-typedef struct { double maxscore; uint32_t mingap, where, start, gap_pos; } gap_result;
+typedef struct { double maxscore; uint32_t mingap, where, start, gap_pos; int assigned; } gap_result;
 
 /* agm (match.hpp:267-332) + opt_solution (:159-260) + backtracing (:115-152) on full, zeroed
  * (n+1)x(m+1) matrices exactly as AgmMatrix (:66-81) lays them out */
@@ -846,7 +846,13 @@ static gap_result gapped_dp(const oracle_params * P, const oracle_text * T, cons
                 }
         }
 
-        gap_result R; R.maxscore = 0; R.mingap = 0; R.where = 0; R.start = 0; R.gap_pos = 0;
+        /* The reference's MAXscore / MINgap / where / start are UNINITIALISED locals of ::matchGaps (match.hpp:518-522) that
+         * opt_solution assigns only when some end cell of the band reaches MINscore.  When none does (a seed hit whose rest
+         * of the read does not align at all) the reference goes on with whatever its stack held -- in practice the values
+         * of the candidate evaluated before, possibly of another read: undefined behaviour that no restatement can follow.
+         * Here such a candidate counts as "no gap found" (MINgap = 0), and `assigned` = 0 tells the caller that the
+         * reference's own result for this read is not defined. */
+        gap_result R; R.maxscore = 0; R.mingap = 0; R.where = 0; R.start = 0; R.gap_pos = 0; R.assigned = 0;
         double score = MINscore;
         uint32_t const up = ((int)m - (int)MAXgap < 0) ? 0 : (m - MAXgap);                    /* i_limits, match.hpp:33-47 */
         uint32_t const down = (m + MAXgap > n) ? n : (m + MAXgap);
@@ -858,7 +864,7 @@ static gap_result gapped_dp(const oracle_params * P, const oracle_text * T, cons
                         if ( g >= MINscore && m - i <= MAXgap )
                         {
                                 double const t = total_scoring(m - i, g, open, extend, offset);
-                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = m - i; R.where = 1; R.start = i; }
+                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = m - i; R.where = 1; R.start = i; R.assigned = 1; }
                         }
                 }
                 else if ( i > m )
@@ -866,7 +872,7 @@ static gap_result gapped_dp(const oracle_params * P, const oracle_text * T, cons
                         if ( g >= MINscore && i - m <= MAXgap )
                         {
                                 double const t = total_scoring(i - m, g, open, extend, offset);
-                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = i - m; R.where = 2; R.start = i; }
+                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = i - m; R.where = 2; R.start = i; R.assigned = 1; }
                         }
                 }
                 else
@@ -874,7 +880,7 @@ static gap_result gapped_dp(const oracle_params * P, const oracle_text * T, cons
                         if ( g >= MINscore )
                         {
                                 double const t = total_scoring(0, g, open, extend, offset);
-                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = 0; R.where = 0; R.start = m; }
+                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = 0; R.where = 0; R.start = m; R.assigned = 1; }
                         }
                 }
         }
@@ -888,7 +894,7 @@ static gap_result gapped_dp(const oracle_params * P, const oracle_text * T, cons
                         if ( g >= MINscore && n - j <= MAXgap )
                         {
                                 double const t = total_scoring(n - j, g, open, extend, offset);
-                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = n - j; R.where = 3; R.start = j; }
+                                if ( t > score ) { score = t; R.maxscore = t; R.mingap = n - j; R.where = 3; R.start = j; R.assigned = 1; }
                         }
                 }
         }
@@ -911,7 +917,7 @@ static gap_result gapped_dp(const oracle_params * P, const oracle_text * T, cons
 
 /* ::matchGaps, match.hpp:428-602 */
 static void probe_list_gaps(const oracle_params * P, const oracle_text * T, const block_index * B, const read_ctx * C,
-                            int k, int inverted, uint64_t * info, float * sc, oracle_gap * gap)
+                            int k, int inverted, uint64_t * info, float * sc, oracle_gap * gap, uint8_t * undefined)
 {
         uint64_t const s_a = inverted ? C->rv[k] : C->fw[k];
         uint64_t const s_b = inverted ? C->rv[5-k] : C->fw[5-k];
@@ -940,6 +946,8 @@ static void probe_list_gaps(const oracle_params * P, const oracle_text * T, cons
                 if ( !( n && m && oracle_dontcare_free(T->nmask, (uint64_t)rpos + P->seedl, n) ) )
                         continue;
                 gap_result const G = gapped_dp(P, T, C, rpos, (uint32_t)n, (uint32_t)m);
+                if ( ! G.assigned && undefined )
+                        *undefined = 1;
                 if ( ! G.mingap )
                         continue;
                 double const complete = seedscore + G.maxscore;
@@ -970,6 +978,13 @@ static void probe_list_gaps(const oracle_params * P, const oracle_text * T, cons
 
 int oracle_match_gaps(const oracle_params * P, const oracle_text * T, const oracle_reads * R, uint64_t * info, float * score, oracle_gap * gaps)
 {
+        return oracle_match_gaps_flagged(P, T, R, info, score, gaps, 0);
+}
+
+/* undefined (may be null): one byte per read, set when a candidate of the read left opt_solution's outputs unassigned */
+int oracle_match_gaps_flagged(const oracle_params * P, const oracle_text * T, const oracle_reads * R, uint64_t * info, float * score, oracle_gap * gaps,
+                              uint8_t * undefined)
+{
         if ( T->n < P->seedl ) return 0;
         if ( T->nrecords + 1 > 65536 ) return 0;
         if ( ! P->ll ) return -1;
@@ -991,8 +1006,8 @@ int oracle_match_gaps(const oracle_params * P, const oracle_text * T, const orac
                         read_setup(&C, P, R, (uint64_t)r);
                         if ( ! C.usable )
                                 continue;
-                        for ( int k = 0; k < 6; ++k ) probe_list_gaps(P, T, &B, &C, k, 0, &info[r], score ? &score[r] : 0, &gaps[r]);
-                        for ( int k = 0; k < 6; ++k ) probe_list_gaps(P, T, &B, &C, k, 1, &info[r], score ? &score[r] : 0, &gaps[r]);
+                        for ( int k = 0; k < 6; ++k ) probe_list_gaps(P, T, &B, &C, k, 0, &info[r], score ? &score[r] : 0, &gaps[r], undefined ? &undefined[r] : 0);
+                        for ( int k = 0; k < 6; ++k ) probe_list_gaps(P, T, &B, &C, k, 1, &info[r], score ? &score[r] : 0, &gaps[r], undefined ? &undefined[r] : 0);
                 }
                 block_free(&B);
         }

@@ -11,7 +11,29 @@ namespace realgpu
 // ---- K4 : ComputeScore<...,true>::computeScore (ComputeScore.hpp:50-190) ----------------------
 // float(1.0 + sum_i LL[ref_i][read_i][q_i]), double accumulation in index order; the '-' strand is
 // scored with the reverse complement and the qualities back to front (ComputeScore.hpp:79).
-// One thread per hit: the additions are a dependent chain by definition of the result.
+// One thread per hit: the additions are a dependent chain by definition of the result -- but nothing else is.  The bases
+// and qualities of 32 positions are fetched together (the qualities as aligned 32-bit words: a byte load per position
+// and thread made the kernel wait for one round trip per position, 4.7 ms for C4's 4 M hits), then the chain runs over
+// registers.
+// The 32 quality bytes of q[first .. first+32), byte j in out[j/4] bits 8*(j%4)..; only [first, first+len) is wanted,
+// and only the aligned words that hold a wanted byte are read.
+__device__ __forceinline__ void quality_run(const uint8_t * __restrict__ q, int64_t first, uint32_t want_from, uint32_t want_to, uint32_t (&out)[8])
+{
+        intptr_t const a = reinterpret_cast<intptr_t>(q) + first;
+        const uint32_t * p = reinterpret_cast<const uint32_t *>(a & ~(intptr_t)3);
+        uint32_t const mis = (uint32_t)(a & 3), sh = mis * 8;
+        uint32_t w[9];
+        #pragma unroll
+        for ( int k = 0; k < 9; ++k )
+        {
+                // word k holds the bytes [4k - mis, 4k + 4 - mis) of the run
+                int const b0 = 4 * k - (int)mis, b1 = b0 + 4;
+                w[k] = (b1 > (int)want_from && b0 < (int)want_to) ? __ldg(p + k) : 0u;
+        }
+        #pragma unroll
+        for ( int k = 0; k < 8; ++k ) out[k] = __funnelshift_r(w[k], w[k+1], sh);
+}
+
 // n = bases scored (the whole read, or its seed for the gapped pass), Lr = length of the read
 __device__ __forceinline__ float score_hit(const double * __restrict__ sll, const uint64_t * __restrict__ text, uint64_t lpos,
                                            ReadSrc const & rs, uint32_t id, uint32_t Lr, const uint8_t * __restrict__ q, uint32_t L, uint32_t strand)
@@ -22,14 +44,29 @@ __device__ __forceinline__ float score_hit(const double * __restrict__ sll, cons
                 uint32_t const len = (L - 32*w < 32) ? (L - 32*w) : 32;
                 uint64_t const tw = text_word(text, lpos + 32*w, len) << (64 - 2*len);   // left aligned
                 uint64_t const rw = strand_bases(rs, id, Lr, 32*w, len);
-                for ( uint32_t j = 0; j < len; ++j )
+                uint32_t qv[8];
+                if ( q )
                 {
-                        uint32_t const i = 32*w + j;
-                        uint32_t const refb = (uint32_t)(tw >> (62 - 2*j)) & 3;
-                        uint32_t const readb = (uint32_t)(rw >> (62 - 2*j)) & 3;
-                        uint32_t const qq = q ? (uint32_t)__ldg(q + (strand ? (L - 1 - i) : i)) : 30u;
-                        raw = __dadd_rn(raw, sll[((refb << 8) | (readb << 6) | qq) & 1023]);
+                        if ( ! strand )
+                                quality_run(q, (int64_t)32*w, 0, len, qv);
+                        else
+                        {
+                                // position i of the strand carries quality L-1-i: the 32 bytes that END at L - 32w, back to front
+                                uint32_t t[8];
+                                quality_run(q, (int64_t)L - 32*(int64_t)w - 32, 32 - len, 32, t);
+                                #pragma unroll
+                                for ( int k = 0; k < 8; ++k ) qv[k] = __byte_perm(t[7-k], 0, 0x0123);
+                        }
                 }
+                #pragma unroll
+                for ( uint32_t j = 0; j < 32; ++j )
+                        if ( j < len )
+                        {
+                                uint32_t const refb = (uint32_t)(tw >> (62 - 2*j)) & 3;
+                                uint32_t const readb = (uint32_t)(rw >> (62 - 2*j)) & 3;
+                                uint32_t const qq = q ? ((qv[j >> 2] >> (8 * (j & 3))) & 0xFFu) : 30u;
+                                raw = __dadd_rn(raw, sll[((refb << 8) | (readb << 6) | qq) & 1023]);
+                        }
         }
         return (float)raw;
 }
@@ -437,13 +474,33 @@ __global__ void __launch_bounds__(128) k_gap_dp(GapParams P)
         for ( int d = 0; d < 7; ++d ) { g[d] = 0.0; lastgap[d] = 0; }
         double mainh[4] = {0.0, 0.0, 0.0, 0.0};    // G[i-1][i-1], G[i-2][i-2], G[i-3][i-3] at [1..3]; [0] = G[i][i]
 
+        // The substitution term of cell (i, j) depends on the text base of row i and on (read base, quality) of column j; a
+        // row touches the columns i-3 .. i+3, so the columns slide through a seven-entry window and every row fetches ONE
+        // new column (win[k] = (base << 6 | quality) of column i - 3 + k) -- the cells used to fetch their column each,
+        // fourteen loads per row, and the kernel waited on them (L1TEX 78 % busy, 5.3 ms for C4's candidates).
+        auto column = [&](uint32_t j) -> uint32_t
+        {
+                uint32_t const rpos_read = j + seedl - 1;
+                uint32_t const rb = rp ? ((uint32_t)(__ldg(rp + (rpos_read >> 5)) >> (62 - 2 * (rpos_read & 31))) & 3)
+                                       : (((uint32_t)__ldg(pp + (rpos_read >> 2)) >> (6 - 2 * (rpos_read & 3))) & 3);
+                uint32_t const qq = q ? (uint32_t)__ldg(q + rpos_read) : 30u;
+                return (rb << 6) | qq;
+        };
+        uint32_t win[7] = {0, 0, 0, 0, 0, 0, 0};
+        #pragma unroll
+        for ( uint32_t j = 1; j <= 3; ++j ) if ( j <= m ) win[3 + j] = column(j);      // becomes win[2 + j] of row 1
+        uint64_t tword = 0;
         for ( uint32_t i = 1; i <= n; ++i )
         {
                 int const left = ((int)i - MAXgap > 0) ? ((int)i - MAXgap) : 1;
                 int const right = (i + MAXgap > m) ? (int)m : (int)(i + MAXgap);
                 if ( left > right ) break;                                   // the band has left the matrix: nothing below is ever read
+                #pragma unroll
+                for ( int k = 0; k < 6; ++k ) win[k] = win[k+1];
+                win[6] = (i + 3 <= m) ? column(i + 3) : 0u;
                 uint64_t const tpos = lbase + seedl - 1 + i;
-                uint32_t const tb = (uint32_t)(__ldg(P.text + (tpos >> 5)) >> (62 - 2 * (tpos & 31))) & 3;
+                if ( i == 1 || (tpos & 31) == 0 ) tword = __ldg(P.text + (tpos >> 5));
+                uint32_t const tb = (uint32_t)(tword >> (62 - 2 * (tpos & 31))) & 3;
                 // main diagonal history: shift before the row is computed
                 mainh[3] = mainh[2]; mainh[2] = mainh[1]; mainh[1] = mainh[0];
                 #pragma unroll
@@ -451,11 +508,7 @@ __global__ void __launch_bounds__(128) k_gap_dp(GapParams P)
                 {
                         int const j = (int)i - dd;
                         if ( j < left || j > right ) continue;
-                        uint32_t const rpos_read = (uint32_t)j + seedl - 1;
-                        uint32_t const rb = rp ? ((uint32_t)(__ldg(rp + (rpos_read >> 5)) >> (62 - 2 * (rpos_read & 31))) & 3)
-                                               : (((uint32_t)__ldg(pp + (rpos_read >> 2)) >> (6 - 2 * (rpos_read & 3))) & 3);
-                        uint32_t const qq = q ? (uint32_t)__ldg(q + rpos_read) : 30u;
-                        double const sub = sll[((tb << 8) | (rb << 6) | qq) & 1023];
+                        double const sub = sll[((tb << 8) | win[3 - dd]) & 1023];
                         double const mis = __dadd_rn(g[dd + 3], sub);
                         if ( dd == 0 )
                         {

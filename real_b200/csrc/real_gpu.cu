@@ -134,10 +134,10 @@ struct real_gpu
         real_gpu_stats stats;
         int pass_bits_override;        // REAL_GPU_PASS_BITS (tuning), -1 = automatic
         uint64_t l2_slice_bytes;       // table bytes (presence bits + entries) one bucket may touch (REAL_GPU_L2_SLICE_MB)
-        uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS)
+        uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS); 0 = automatic
         int own_list_max;              // bucket shards: own buckets up to which the kept positions are listed first (REAL_GPU_OWN_LIST_MAX)
 
-        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), fused_build(false), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(1ull << 30), own_list_max(64), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), fused_build(false), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(0), own_list_max(64), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -867,9 +867,35 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 throw CudaError("sharded tables: every rank must be given the whole text (the ranks split the positions among themselves)");
                         P.bucket_bits = 8;
                 }
-                uint64_t const chunk_max = sharded ? CM.round_positions : std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
                 uint64_t const x_begin = P.x_begin, x_end = P.x_end;
+                // Positions partitioned at a time.  One handle with the whole signature space: as many as fit -- the records of
+                // C3's 3.1 G positions take 50 GB of the 180 -- because every chunk walks through all the tables again (three chunks
+                // of 2^30 positions read the entries three times over: 105 GB of DRAM traffic instead of 10, 2 ms of the C3 scan).
+                // Equal chunks when the text does not fit; REAL_GPU_CHUNK_MPOS overrides.
+                uint64_t chunk_max = sharded ? CM.round_positions : std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
+                if ( ! sharded && ! own_only && h->chunk_positions == 0 )
+                {
+                        uint64_t const span = ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS;
+                        uint64_t const pad = (uint64_t)SC_MAX_BUCKETS * SC_UNIT;
+                        uint64_t fit = SC_MAX_CHUNK;
+                        // the memory query costs milliseconds (3.7 ms measured on C1, whose whole scan takes 0.5): it is made only
+                        // when the record buffer already held is too small for the span
+                        if ( (std::min<uint64_t>(span, SC_MAX_CHUNK) + pad) * sizeof(uint4) + 64 > h->rec_win.bytes )
+                        {
+                                size_t free_b = 0, total_b = 0;
+                                RG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                                uint64_t const room = (uint64_t)((free_b + h->rec_win.bytes) * 0.6) / sizeof(uint4);     // the buffer already held counts as room
+                                fit = std::max<uint64_t>(SC_TILE_POS, std::min<uint64_t>(SC_MAX_CHUNK, room > pad ? room - pad : 0) / SC_TILE_POS * SC_TILE_POS);
+                        }
+                        uint64_t const nchunks = (span + fit - 1) / fit;
+                        chunk_max = std::max<uint64_t>(SC_TILE_POS, ((span + nchunks - 1) / nchunks + SC_TILE_POS - 1) / SC_TILE_POS * SC_TILE_POS);
+                }
+                else if ( h->chunk_positions == 0 )
+                        chunk_max = sharded ? CM.round_positions : SC_MAX_ROUND;
                 uint64_t const chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
+                // entries are touched about once per chunk and bucket: several chunks stream them past the probed slot words
+                // (evict_first); a single chunk re-uses every entry line about nine times while its bucket is probed (evict_normal)
+                if ( ! getenv("REAL_GPU_DEBUG") && x_end - x_begin <= chunk_cap ) P.debug_flags |= 4;
                 uint32_t * meta = nullptr;
                 if ( sharded )
                 {

@@ -1,7 +1,9 @@
 // Test helper: dumps what the host layer hands to the C ABI (packed text, parsed reads, scoring table, options)
 // as JSON, so the CPU test-suite can check the parsers without a GPU.
 #include "real_host.hpp"
+#include "../csrc/fmt_g.h"
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 #include <iostream>
@@ -77,6 +79,47 @@ int main(int argc, char * argv[])
                         printf("[");
                         for ( size_t i = 0; i < f.size(); ++i ) { if ( i ) putchar(','); jstr(f[i]); }
                         printf("]\n");
+                }
+                else if ( mode == "fmtg" )
+                {
+                        // the score formatter of the device (csrc/fmt_g.h) against snprintf("%g") on `count` floats: pseudo-random bit
+                        // patterns, values near the powers of ten (rounding up into the next exponent), halves, small integers
+                        unsigned long long const count = strtoull(argv[2], 0, 10);
+                        unsigned long long x = 0x9E3779B97F4A7C15ULL, bad = 0, done = 0;
+                        auto check = [&](float f)
+                        {
+                                char a[32], b[32];
+                                int const na = fmtg::format_g6(f, a);
+                                int const nb = snprintf(b, sizeof(b), "%g", (double)f);
+                                ++done;
+                                if ( na != nb || memcmp(a, b, na) )
+                                {
+                                        if ( f != f && na == nb - 0 && (nb == 3 || nb == 4) ) { }       // nan: compared below by its letters only
+                                        a[na] = 0;
+                                        if ( ! (f != f) && bad++ < 10 ) { unsigned int u; memcpy(&u, &f, 4); fprintf(stderr, "%08x: ours '%s' libc '%s'\n", u, a, b); }
+                                }
+                        };
+                        for ( unsigned long long i = 0; i < count; ++i )
+                        {
+                                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                                unsigned int u = (unsigned int)(x >> 16);
+                                float f; memcpy(&f, &u, 4);
+                                check(f);
+                                // scores live here: a few hundred at most, six digits cut in the middle of the mantissa
+                                check((float)((double)(long long)(x % 2000000) / 997.0 - 1000.0));
+                        }
+                        for ( int e = -45; e <= 38; ++e )
+                                for ( int k = -40; k <= 40; ++k )
+                                {
+                                        double const v = pow(10.0, e);
+                                        float f = (float)v;
+                                        for ( int s = 0; s < (k < 0 ? -k : k); ++s ) f = nextafterf(f, k < 0 ? 0.0f : INFINITY);
+                                        check(f); check(-f);
+                                        check((float)(v * 9.999995)); check((float)(v * 9.9999949)); check((float)(v * 1.2345650)); check((float)(v * 1.2345649));
+                                }
+                        for ( int i = 0; i < 3000000; ++i ) { check((float)i * 0.5f); check((float)i * 0.03125f); }
+                        check(0.0f); check(-0.0f); check(INFINITY); check(-INFINITY);
+                        printf("{\"checked\":%llu,\"bad\":%llu}\n", done, bad);
                 }
                 else return 2;
                 return 0;
