@@ -93,7 +93,7 @@ typedef struct
         float h2d_text_ms;      /* text transfer; after real_gpu_set_text_fasta*: transfer of the file bytes + the K0 kernels */
         float h2d_reads_ms;
         float pack_ms;          /* K1: read packing + seed extraction */
-        float index_ms;         /* K2: entry generation + radix sorts + table build */
+        float index_ms;         /* K2: the two partition passes over the index items + the sub-bucket build of the tables */
         float scan_ms;          /* K3: text scan (probe + verify), the dominant kernel */
         float post_ms;          /* K4/K6: scoring, per-read ordering */
         float d2h_ms;
@@ -297,6 +297,33 @@ int real_gpu_set_bucket_shard(real_gpu * h, uint32_t rank, uint32_t nranks);
  * entry exists. */
 int real_gpu_match_gaps(real_gpu * h, uint64_t n_list_windows);
 int real_gpu_get_gaps(real_gpu * h, real_gpu_gapinfo * gaps);
+
+/* Output lines formatted on the device (K8, csrc/format.cuh).  Replaces the serial print loops of the reference:
+ * matchAllImplementation.cpp:485-510 (one line per MatchPosAndError) and matchUniqueImplementation.cpp:252-321,1455-1486 (one
+ * line per read whose state is Straight or Reverse):
+ *     id \t bases \t [score] \t1\ta\t L \t +|- \t record name \t 1-based position in the record \t\t k \n
+ * bases = toollib::remapString of the read ('-': of its reverse complement); the score is printed like an ostream with default
+ * flags does (printf %g, bit-exact incl. rounding: csrc/fmt_g.h); no score column content when scores are off.
+ *   real_gpu_set_read_ids      ids (the part of the '>'/'@' line the reference keeps) of the reads [first, first+count):
+ *                              bytes + count+1 offsets.  Call after real_gpu_set_reads*; a rank of a multi-GPU job sets the
+ *                              ids of the reads it will format (its own share after the fold).
+ *   real_gpu_set_record_names  per text file: names of its records (bytes + nrecords+1 offsets) and their start offsets
+ *   real_gpu_format_unique     the lines of the reads [first, first+count) from the current unique state (+ scores), in read order;
+ *                              *nlines = reads that printed a line
+ *   real_gpu_format_all        the lines of the rows [first_row, first_row+count) of the last real_gpu_match_all, in row order
+ * *bytes points to library-owned pinned host memory that stays valid until the next-but-one format call (two buffers are
+ * handed out in turn, so a writer thread can drain one batch while the next is formatted).  A batch is limited to 4 GiB of
+ * output (REAL_GPU_E_LIMIT: format fewer items per call).  For reads given by real_gpu_set_reads_packed_device the caller's
+ * device buffer must still be valid. */
+int real_gpu_set_read_ids(real_gpu * h, uint64_t first, uint64_t count, const char * bytes, const uint64_t * offsets);
+int real_gpu_set_record_names(real_gpu * h, uint32_t fileid, uint32_t nrecords, const char * bytes, const uint64_t * offsets,
+                              const uint64_t * record_starts);
+int real_gpu_format_unique(real_gpu * h, uint64_t first, uint64_t count, const char ** bytes, uint64_t * nbytes, uint64_t * nlines);
+int real_gpu_format_all(real_gpu * h, uint64_t first_row, uint64_t count, const char ** bytes, uint64_t * nbytes);
+
+/* Test hook: the score formatter of the device (csrc/fmt_g.h) on n host floats; out16 receives 16 bytes per value, the
+ * characters followed by zero bytes. */
+int real_gpu_selftest_format_scores(int device, const float * values, uint64_t n, char * out16);
 
 /* Introspection for benchmarks and tests. */
 int real_gpu_get_stats(real_gpu * h, real_gpu_stats * out);

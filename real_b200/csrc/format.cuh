@@ -32,6 +32,7 @@ struct FormatParams
         const unsigned long long * info; const float * score;
         const real_gpu_hit * hits;
         uint64_t first, count;
+        unsigned long long * nlines;  // items that print a line
         uint32_t * len;               // [count] bytes of every item's line
         const uint32_t * off;         // [count] exclusive scan of len
         char * out;
@@ -78,8 +79,11 @@ template<bool ALL>
 __global__ void __launch_bounds__(256) k_fmt_len(FormatParams P)
 {
         uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        FormatItem it; it.prints = false;
+        if ( i < P.count ) it = format_item<ALL>(P, i);
+        uint32_t const bal = __ballot_sync(0xffffffffu, it.prints);
+        if ( (threadIdx.x & 31) == 0 && bal ) atomicAdd(P.nlines, (unsigned long long)__popc(bal));
         if ( i >= P.count ) return;
-        FormatItem const it = format_item<ALL>(P, i);
         uint32_t n = 0;
         if ( it.prints )
         {
@@ -150,6 +154,16 @@ __global__ void __launch_bounds__(FMT_WARPS * 32) k_fmt_write(FormatParams P)
                 for ( uint32_t b = lane; b < nt; b += 32 ) o[b] = tail[wid][b];
                 __syncwarp();
         }
+}
+
+// test hook: the score formatter on arbitrary floats; out[i] = 16 bytes, the characters followed by a zero byte
+__global__ void __launch_bounds__(256) k_fmt_selftest(const float * __restrict__ v, uint64_t n, char * __restrict__ out)
+{
+        uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( i >= n ) return;
+        char tmp[16];
+        int const k = fmtg::format_g6(v[i], tmp);
+        for ( int j = 0; j < 16; ++j ) out[i * 16 + j] = j < k ? tmp[j] : 0;
 }
 
 } // namespace realgpu

@@ -8,6 +8,7 @@
 #include "scan.cuh"
 #include "post.cuh"
 #include "ingest.cuh"
+#include "format.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -130,6 +131,19 @@ struct real_gpu
                 Fold() : nranks(1), rank(0), epoch(0), cap(0), seg(0), stage_off(4096), connected(false), ev(nullptr)
                 { for ( int i = 0; i < SC_MAX_RANKS; ++i ) { base[i] = nullptr; ipc_opened[i] = false; local[i] = nullptr; } }
         } fold;
+
+        // output lines formatted on the device (real_gpu_format_*, csrc/format.cuh)
+        struct Format
+        {
+                DevBuf ids, id_off, names, name_off, rec_start, file_first, len, off, out;
+                uint64_t id_first, id_count, id_bytes, max_name;
+                std::vector<char> file_names[64];                // per file: the record names back to back
+                std::vector<uint64_t> file_name_off[64], file_starts[64];
+                bool tables_dirty;
+                char * host[2]; size_t host_cap[2]; int flip;    // two pinned buffers handed out in turn
+                uint64_t nrows_all;                              // rows of the last real_gpu_match_all
+                Format() : id_first(0), id_count(0), id_bytes(0), max_name(0), tables_dirty(true), flip(0), nrows_all(0) { host[0] = host[1] = nullptr; host_cap[0] = host_cap[1] = 0; }
+        } fmt;
 
         real_gpu_stats stats;
         int pass_bits_override;        // REAL_GPU_PASS_BITS (tuning), -1 = automatic
@@ -1085,6 +1099,7 @@ void preload_kernels(int device)
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
         RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay); RG_PRELOAD(k_fold_push); RG_PRELOAD(k_fold_merge); RG_PRELOAD(k_unique_checksum); RG_PRELOAD(k_mark_large); RG_PRELOAD(k_sort_large<0>); RG_PRELOAD(k_sort_large<1>); RG_PRELOAD(k_sort_large<2>);
+        RG_PRELOAD(k_fmt_len<false>); RG_PRELOAD(k_fmt_len<true>); RG_PRELOAD(k_fmt_write<false>); RG_PRELOAD(k_fmt_write<true>);
         RG_PRELOAD(k_fa_summary); RG_PRELOAD(k_fa_scan); RG_PRELOAD(k_fa_pack);
         RG_PRELOAD(k_window_counts); RG_PRELOAD(k_block_bounds); RG_PRELOAD(k_gap_dp); RG_PRELOAD(k_gap_replay);
 #undef RG_PRELOAD
@@ -1190,6 +1205,11 @@ int real_gpu_destroy(real_gpu * h)
         if ( h->fold.ev ) cudaEventDestroy(h->fold.ev);
         dev_free(h, h->fold.window); dev_free(h, h->fold.ptrs); dev_free(h, h->fold.error);
         if ( h->host_hits ) cudaFreeHost(h->host_hits);
+        {
+                DevBuf * fb[] = { &h->fmt.ids, &h->fmt.id_off, &h->fmt.names, &h->fmt.name_off, &h->fmt.rec_start, &h->fmt.file_first, &h->fmt.len, &h->fmt.off, &h->fmt.out };
+                for ( DevBuf * b : fb ) dev_free(h, *b);
+                for ( int i = 0; i < 2; ++i ) if ( h->fmt.host[i] ) cudaFreeHost(h->fmt.host[i]);
+        }
         for ( int i = 0; i < 8; ++i ) if ( h->ev[i] ) cudaEventDestroy(h->ev[i]);
         for ( int i = 0; i < 2; ++i ) if ( h->evc[i] ) cudaEventDestroy(h->evc[i]);
         if ( h->st2 ) cudaStreamDestroy(h->st2);
@@ -1544,6 +1564,7 @@ int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhit
         h->stats.d2h_ms = elapsed(h->ev[1], h->ev[2]);
         *hits = h->host_hits;
         *nhits = found;
+        h->fmt.nrows_all = found;
         return REAL_GPU_OK;
         RG_API_END(h)
 }
@@ -2098,6 +2119,202 @@ int real_gpu_fold_unique_group(real_gpu * const * handles, uint32_t n)
         }
         catch ( std::exception const & e ) { return fail(h, REAL_GPU_E_CUDA, e.what()); }
         return REAL_GPU_OK;
+}
+
+
+// ---- output lines formatted on the device (csrc/format.cuh) -----------------------------------------
+
+int real_gpu_set_read_ids(real_gpu * h, uint64_t first, uint64_t count, const char * bytes, const uint64_t * offsets)
+{
+        RG_API_BEGIN(h)
+        if ( ! offsets || (count && ! bytes && offsets[count] != offsets[0]) ) return fail(h, REAL_GPU_E_ARG, "set_read_ids: null pointer");
+        for ( uint64_t i = 0; i < count; ++i )
+                if ( offsets[i+1] < offsets[i] ) return fail(h, REAL_GPU_E_ARG, "set_read_ids: offsets not ascending");
+        uint64_t const nbytes = offsets[count] - offsets[0];
+        dev_reserve(h, h->fmt.ids, nbytes + 16);
+        dev_reserve(h, h->fmt.id_off, (count + 1) * 8);
+        if ( nbytes ) RG_CUDA(cudaMemcpyAsync(h->fmt.ids.p, bytes + offsets[0], nbytes, cudaMemcpyHostToDevice, h->st));
+        std::vector<uint64_t> rel;
+        const uint64_t * src = offsets;
+        if ( offsets[0] != 0 )
+        {
+                rel.resize(count + 1);
+                for ( uint64_t i = 0; i <= count; ++i ) rel[i] = offsets[i] - offsets[0];
+                src = rel.data();
+        }
+        RG_CUDA(cudaMemcpyAsync(h->fmt.id_off.p, src, (count + 1) * 8, cudaMemcpyHostToDevice, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->fmt.id_first = first; h->fmt.id_count = count; h->fmt.id_bytes = nbytes;
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+int real_gpu_set_record_names(real_gpu * h, uint32_t fileid, uint32_t nrecords, const char * bytes, const uint64_t * offsets, const uint64_t * record_starts)
+{
+        RG_API_BEGIN(h)
+        if ( fileid >= 64 ) return fail(h, REAL_GPU_E_LIMIT, "set_record_names: fileid >= 64");
+        if ( ! offsets || ! record_starts || (nrecords && ! bytes && offsets[nrecords] != offsets[0]) ) return fail(h, REAL_GPU_E_ARG, "set_record_names: null pointer");
+        for ( uint32_t i = 0; i < nrecords; ++i )
+                if ( offsets[i+1] < offsets[i] ) return fail(h, REAL_GPU_E_ARG, "set_record_names: offsets not ascending");
+        real_gpu::Format & F = h->fmt;
+        F.file_names[fileid].assign(bytes + offsets[0], bytes + offsets[nrecords]);
+        F.file_name_off[fileid].resize(nrecords + 1);
+        for ( uint32_t i = 0; i <= nrecords; ++i ) F.file_name_off[fileid][i] = offsets[i] - offsets[0];
+        F.file_starts[fileid].assign(record_starts, record_starts + nrecords);
+        for ( uint32_t i = 0; i < nrecords; ++i ) F.max_name = std::max<uint64_t>(F.max_name, offsets[i+1] - offsets[i]);
+        F.tables_dirty = true;
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+} // extern "C"
+
+namespace
+{
+
+// the record tables of all files on the device: names, name offsets and record starts by global record index
+void format_upload_tables(real_gpu * h)
+{
+        real_gpu::Format & F = h->fmt;
+        if ( ! F.tables_dirty ) return;
+        std::vector<uint32_t> first(65, 0);
+        std::vector<char> names; std::vector<uint64_t> noff, starts;
+        for ( int f = 0; f < 64; ++f )
+        {
+                first[f] = (uint32_t)starts.size();
+                for ( size_t r = 0; r < F.file_starts[f].size(); ++r )
+                {
+                        noff.push_back(names.size() + F.file_name_off[f][r]);
+                        starts.push_back(F.file_starts[f][r]);
+                }
+                names.insert(names.end(), F.file_names[f].begin(), F.file_names[f].end());
+        }
+        first[64] = (uint32_t)starts.size();
+        noff.push_back(names.size());
+        starts.push_back(0);
+        // (noff[r+1] is the end of record r's name: the names of a file are back to back and the files follow each other)
+        dev_reserve(h, F.names, names.size() + 16);
+        dev_reserve(h, F.name_off, noff.size() * 8);
+        dev_reserve(h, F.rec_start, starts.size() * 8);
+        dev_reserve(h, F.file_first, 65 * 4);
+        if ( ! names.empty() ) RG_CUDA(cudaMemcpyAsync(F.names.p, names.data(), names.size(), cudaMemcpyHostToDevice, h->st));
+        RG_CUDA(cudaMemcpyAsync(F.name_off.p, noff.data(), noff.size() * 8, cudaMemcpyHostToDevice, h->st));
+        RG_CUDA(cudaMemcpyAsync(F.rec_start.p, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, h->st));
+        RG_CUDA(cudaMemcpyAsync(F.file_first.p, first.data(), 65 * 4, cudaMemcpyHostToDevice, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));      // the staging vectors go out of scope
+        F.tables_dirty = false;
+}
+
+template<bool ALL>
+int format_items(real_gpu * h, uint64_t first, uint64_t count, const char ** bytes, uint64_t * nbytes, uint64_t * nlines)
+{
+        real_gpu::Format & F = h->fmt;
+        *bytes = nullptr; *nbytes = 0;
+        if ( nlines ) *nlines = 0;
+        if ( ! count ) return REAL_GPU_OK;
+        format_upload_tables(h);
+        FormatParams P;
+        memset(&P, 0, sizeof(P));
+        P.rs = read_src(h); P.rlen = ptr<uint32_t>(h->rlen);
+        P.ids = ptr<char>(F.ids); P.id_off = ptr<uint64_t>(F.id_off); P.id_first = F.id_first;
+        P.file_first = ptr<uint32_t>(F.file_first); P.names = ptr<char>(F.names); P.name_off = ptr<uint64_t>(F.name_off); P.rec_start = ptr<uint64_t>(F.rec_start);
+        P.scores = h->prm.scores;
+        P.info = ptr<unsigned long long>(h->info); P.score = ptr<float>(h->scores); P.hits = ptr<real_gpu_hit>(h->hits_out);
+        P.first = first; P.count = count;
+        dev_reserve(h, F.len, (count + 2) * 4);
+        dev_reserve(h, F.off, (count + 2) * 4);
+        dev_reserve(h, h->scantmp, scan_temp_elems(count) * 4 + 64);
+        P.len = ptr<uint32_t>(F.len); P.off = ptr<uint32_t>(F.off);
+        dev_reserve(h, h->counters, 8 * 8);
+        RG_CUDA(cudaMemsetAsync(h->counters.p, 0, 8, h->st));
+        P.nlines = ptr<unsigned long long>(h->counters);
+        // the byte offsets of a batch are 32 bit: a bound on its bytes (ids of the whole set + the longest possible rest per item)
+        if ( F.id_bytes + count * ((uint64_t)h->maxlen + F.max_name + 96) >= (1ULL << 32) )
+                throw LimitError("format: this many items may take more than 4 GiB of output; format fewer per call");
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        k_fmt_len<ALL><<<blocks_for(count, 256), 256, 0, h->st>>>(P);
+        RG_KERNEL_CHECK(); launch_count(h);
+        uint32_t nl = 0;
+        exclusive_scan_u32(P.len, ptr<uint32_t>(F.off), count, ptr<uint32_t>(h->scantmp), h->st, &nl);
+        launch_count(h, nl);
+        uint32_t last[2] = {0, 0};
+        unsigned long long nl_host = 0;
+        RG_CUDA(cudaMemcpyAsync(&nl_host, P.nlines, 8, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaMemcpyAsync(&last[0], ptr<uint32_t>(F.off) + (count - 1), 4, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaMemcpyAsync(&last[1], ptr<uint32_t>(F.len) + (count - 1), 4, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        uint64_t const total = (uint64_t)last[0] + last[1];
+        if ( ! total ) { if ( nlines ) *nlines = 0; return REAL_GPU_OK; }
+        dev_reserve(h, F.out, total + 16);
+        P.out = ptr<char>(F.out);
+        k_fmt_write<ALL><<<(unsigned)std::min<uint64_t>((count + FMT_WARPS - 1) / FMT_WARPS, (uint64_t)h->sm_count * 16), FMT_WARPS * 32, 0, h->st>>>(P);
+        RG_KERNEL_CHECK(); launch_count(h);
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        int const b = F.flip; F.flip ^= 1;
+        if ( F.host_cap[b] < total )
+        {
+                if ( F.host[b] ) cudaFreeHost(F.host[b]);
+                F.host[b] = nullptr; F.host_cap[b] = 0;
+                size_t const cap = total + total / 8 + 4096;
+                RG_CUDA(cudaMallocHost(&F.host[b], cap));
+                F.host_cap[b] = cap;
+        }
+        RG_CUDA(cudaMemcpyAsync(F.host[b], F.out.p, total, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaEventRecord(h->ev[2], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        h->stats.post_ms = elapsed(h->ev[0], h->ev[1]);
+        h->stats.d2h_ms = elapsed(h->ev[1], h->ev[2]);
+        *bytes = F.host[b]; *nbytes = total;
+        if ( nlines ) *nlines = nl_host;
+        return REAL_GPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int real_gpu_format_unique(real_gpu * h, uint64_t first, uint64_t count, const char ** bytes, uint64_t * nbytes, uint64_t * nlines)
+{
+        RG_API_BEGIN(h)
+        if ( ! bytes || ! nbytes ) return fail(h, REAL_GPU_E_ARG, "format_unique: null pointer");
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( first > h->nreads || count > h->nreads - first ) return fail(h, REAL_GPU_E_ARG, "format_unique: range outside the read set");
+        if ( first < h->fmt.id_first || first + count > h->fmt.id_first + h->fmt.id_count )
+                return fail(h, REAL_GPU_E_STATE, "format_unique: the ids of these reads have not been set (real_gpu_set_read_ids)");
+        if ( count >= (1ULL << 26) ) return fail(h, REAL_GPU_E_LIMIT, "format_unique: more than 2^26 reads in one call");
+        return format_items<false>(h, first, count, bytes, nbytes, nlines);
+        RG_API_END(h)
+}
+
+int real_gpu_format_all(real_gpu * h, uint64_t first_row, uint64_t count, const char ** bytes, uint64_t * nbytes)
+{
+        RG_API_BEGIN(h)
+        if ( ! bytes || ! nbytes ) return fail(h, REAL_GPU_E_ARG, "format_all: null pointer");
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( first_row > h->fmt.nrows_all || count > h->fmt.nrows_all - first_row ) return fail(h, REAL_GPU_E_ARG, "format_all: range outside the rows of the last real_gpu_match_all");
+        if ( h->fmt.id_first != 0 || h->fmt.id_count < h->nreads )
+                return fail(h, REAL_GPU_E_STATE, "format_all: the ids of all reads must be set (real_gpu_set_read_ids)");
+        if ( count >= (1ULL << 26) ) return fail(h, REAL_GPU_E_LIMIT, "format_all: more than 2^26 rows in one call");
+        return format_items<true>(h, first_row, count, bytes, nbytes, nullptr);
+        RG_API_END(h)
+}
+
+int real_gpu_selftest_format_scores(int device, const float * values, uint64_t n, char * out16)
+{
+        try
+        {
+                RG_CUDA(cudaSetDevice(device));
+                float * dv = nullptr; char * dout = nullptr;
+                RG_CUDA(cudaMalloc(&dv, n * 4 + 16));
+                RG_CUDA(cudaMalloc(&dout, n * 16 + 16));
+                RG_CUDA(cudaMemcpy(dv, values, n * 4, cudaMemcpyHostToDevice));
+                if ( n ) k_fmt_selftest<<<blocks_for(n, 256), 256>>>(dv, n, dout);
+                cudaError_t const e = cudaDeviceSynchronize();
+                if ( e == cudaSuccess ) cudaMemcpy(out16, dout, n * 16, cudaMemcpyDeviceToHost);
+                cudaFree(dv); cudaFree(dout);
+                return e == cudaSuccess ? REAL_GPU_OK : REAL_GPU_E_CUDA;
+        }
+        catch ( ... ) { return REAL_GPU_E_CUDA; }
 }
 
 int real_gpu_get_stats(real_gpu * h, real_gpu_stats * out)

@@ -1136,6 +1136,59 @@ namespace
                 readPatternsBuffer(buf, opts.fastq, qualityOffset, reads, hostThreads(opts));
                 std::cerr << "Number of patterns is " << reads.size() << std::endl;
         }
+
+        // REAL_FORMAT=host: the lines are assembled by the host team (formatLine) instead of on the device (tests, timing)
+        bool deviceFormat()
+        {
+                char const * const e = getenv("REAL_FORMAT");
+                return ! (e && std::string(e) == "host");
+        }
+
+        // ids of the reads [lo, hi) as one byte string + offsets, for real_gpu_set_read_ids
+        void setReadIds(Gpu & G, ReadSet const & reads, uint64_t lo, uint64_t hi)
+        {
+                std::vector<uint64_t> off(hi - lo + 1, 0);
+                for ( uint64_t r = lo; r < hi; ++r ) off[r - lo + 1] = off[r - lo] + reads.ids[r].size();
+                std::vector<char> bytes(off[hi - lo] + 1);
+                for ( uint64_t r = lo; r < hi; ++r ) memcpy(&bytes[off[r - lo]], reads.ids[r].data(), reads.ids[r].size());
+                G.check(real_gpu_set_read_ids(G.h, lo, hi - lo, &bytes[0], &off[0]), "set_read_ids");
+        }
+
+        // names and start offsets of the records of file fi (T.ranges without its terminal entry), for the lines that name them
+        void setRecordNames(Gpu & G, uint32_t fi, std::vector< std::pair<std::string, uint64_t> > const & ranges)
+        {
+                if ( ranges.size() < 2 ) return;
+                size_t const n = ranges.size() - 1;
+                std::vector<uint64_t> off(n + 1, 0), starts(n);
+                for ( size_t r = 0; r < n; ++r ) { off[r+1] = off[r] + ranges[r].first.size(); starts[r] = ranges[r].second; }
+                std::vector<char> bytes(off[n] + 1);
+                for ( size_t r = 0; r < n; ++r ) memcpy(&bytes[off[r]], ranges[r].first.data(), ranges[r].first.size());
+                G.check(real_gpu_set_record_names(G.h, fi, (uint32_t)n, &bytes[0], &off[0], &starts[0]), "set_record_names");
+        }
+
+        // Writes the batches a formatter hands out, one behind the other, while the next batch is being formatted: next(&bytes,
+        // &nbytes) formats the next batch into library-owned memory that stays valid until its next-but-one call, and returns
+        // false when there is none left.
+        template<typename F>
+        void writeBatches(Output & out, F next)
+        {
+                std::thread writer; std::exception_ptr err;
+                char const * bytes = 0; uint64_t nbytes = 0;
+                while ( next(&bytes, &nbytes) )
+                {
+                        if ( writer.joinable() ) writer.join();
+                        if ( err ) std::rethrow_exception(err);
+                        if ( ! nbytes ) continue;
+                        char const * const b = bytes; uint64_t const n = nbytes;
+                        writer = std::thread([&out, &err, b, n]()
+                        {
+                                try { if ( fwrite(b, 1, n, out.f) != n ) throw std::runtime_error("write failed"); }
+                                catch ( ... ) { err = std::current_exception(); }
+                        });
+                }
+                if ( writer.joinable() ) writer.join();
+                if ( err ) std::rethrow_exception(err);
+        }
 }
 
 // (patid, k, pos, file, frag, score, inverted): MatchPosAndError::operator< per read (matchAllImplementation.cpp:122-136)
@@ -1164,6 +1217,8 @@ int doMatchingAll(RealOptions const & opts)
         team.wait();
         team.connect(reads.size(), false);
         team.setReads(reads, packed);
+        bool const devfmt = deviceFormat() && team.size() == 1;       // several handles: their rows are merged (and formatted) on the host
+        if ( devfmt ) setReadIds(team.g[0], reads, 0, reads.size());
         PT.lap("create + set_reads");
         Output out(opts.outputfilename);
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
@@ -1193,6 +1248,24 @@ int doMatchingAll(RealOptions const & opts)
                 }
                 PT.lap("text + match_all");
                 bool const scores = opts.scores;
+                if ( devfmt )
+                {
+                        // the lines are formatted on the device, batch by batch, and written while the next batch is formatted
+                        Gpu & G = team.g[0];
+                        setRecordNames(G, (uint32_t)fi, T.ranges);
+                        uint64_t const per = 1u << 18;
+                        uint64_t at = 0;
+                        writeBatches(out, [&G, &at, nhits, per](char const ** bytes, uint64_t * nbytes) -> bool
+                        {
+                                if ( at >= nhits ) return false;
+                                uint64_t const c = std::min<uint64_t>(per, nhits - at);
+                                G.check(real_gpu_format_all(G.h, at, c, bytes, nbytes), "format_all");
+                                at += c;
+                                return true;
+                        });
+                        PT.lap("format + write");
+                        continue;
+                }
                 formatParallel(nhits, hostThreads(opts), out, [&reads, &T, hits, scores](std::string & o, uint64_t i) -> uint64_t
                 {
                         real_gpu_hit const & H = hits[i];
@@ -1248,6 +1321,14 @@ int doMatchingUnique(RealOptions const & opts)
         team.wait();
         team.connect(reads.size(), true);
         team.setReads(reads, packed);
+        bool const devfmt = deviceFormat();
+        if ( devfmt )
+        {
+                // every handle formats the lines of the reads whose merged state it holds after the fold
+                unsigned int const n = team.size();
+                uint64_t const R = reads.size();
+                parallelFor(n, [&team, &reads, n, R](unsigned int i) { setReadIds(team.g[i], reads, R * i / n, R * (i + 1) / n); });
+        }
         Gpu & G = team.g[0];
         std::vector< std::vector< std::pair<std::string, uint64_t> > > rangeset(filenames.size());       // RangeSet
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
@@ -1255,6 +1336,8 @@ int doMatchingUnique(RealOptions const & opts)
                 TextFile T;
                 bool const usable = setTextTeam(team, opts, (uint32_t)fi, filenames[fi], T, true);
                 rangeset[fi] = T.ranges;
+                if ( devfmt && fi < 64 )
+                        for ( unsigned int i = 0; i < team.size(); ++i ) setRecordNames(team.g[i], (uint32_t)fi, T.ranges);
                 if ( fi >= 64 || T.n >= (1ULL << 35) || T.ranges.size() > 65536 )
                 {
                         std::cerr << "Skipping file " << filenames[fi] << " as it exceeds the limits of UniqueMatchInfo." << std::endl;
@@ -1278,6 +1361,33 @@ int doMatchingUnique(RealOptions const & opts)
                                 continue;
                         G.check(real_gpu_match_gaps(G.h, planBlockWindows(opts, T, reads.size())), "match_gaps");
                 }
+        }
+        if ( devfmt )
+        {
+                PT.lap("texts + matching");
+                Output out(opts.outputfilename);
+                unsigned int const n = team.size();
+                uint64_t const R = reads.size();
+                uint64_t unique = 0;
+                for ( unsigned int i = 0; i < n; ++i )
+                {
+                        Gpu & Gi = team.g[i];
+                        uint64_t const hi = R * (i + 1) / n;
+                        uint64_t at = R * i / n;
+                        uint64_t const per = 1u << 18;
+                        writeBatches(out, [&Gi, &at, &unique, hi, per](char const ** bytes, uint64_t * nbytes) -> bool
+                        {
+                                if ( at >= hi ) return false;
+                                uint64_t const c = std::min<uint64_t>(per, hi - at);
+                                uint64_t nl = 0;
+                                Gi.check(real_gpu_format_unique(Gi.h, at, c, bytes, nbytes, &nl), "format_unique");
+                                unique += nl; at += c;
+                                return true;
+                        });
+                }
+                PT.lap("format + write");
+                std::cerr << "unique: " << unique << std::endl;
+                return EXIT_SUCCESS;
         }
         std::vector<uint64_t> info(reads.size() + 1);
         std::vector<float> score(reads.size() + 1);

@@ -115,6 +115,11 @@ def load(build_if_missing: bool = True):
     L.real_gpu_fold_unique.argtypes = [vp]
     L.real_gpu_fold_unique_group.argtypes = [vp, u32]
     L.real_gpu_set_bucket_shard.argtypes = [vp, u32, u32]
+    L.real_gpu_set_read_ids.argtypes = [vp, u64, u64, vp, vp]
+    L.real_gpu_set_record_names.argtypes = [vp, u32, u32, vp, vp, vp]
+    L.real_gpu_format_unique.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    L.real_gpu_format_all.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.real_gpu_selftest_format_scores.argtypes = [i32, vp, u64, vp]
     L.real_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.real_gpu_stream.argtypes = [vp]
     L.real_gpu_stream.restype = vp
@@ -135,6 +140,16 @@ def load(build_if_missing: bool = True):
 def _np_ptr(a: np.ndarray, dtype) -> int:
     assert a.dtype == np.dtype(dtype) and a.flags["C_CONTIGUOUS"], (a.dtype, dtype)
     return a.ctypes.data
+
+
+def selftest_format_scores(values: np.ndarray, device: int = 0):
+    """The device's score formatter (printf %g) on float32 values; returns a list of byte strings."""
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    out = np.zeros((v.size, 16), dtype=np.uint8)
+    rc = load().real_gpu_selftest_format_scores(device, v.ctypes.data, v.size, out.ctypes.data)
+    if rc != 0:
+        raise RealGpuError(rc, "selftest_format_scores failed")
+    return [bytes(r).split(b"\0", 1)[0] for r in out]
 
 
 class Handle:
@@ -347,6 +362,40 @@ class Handle:
         g = np.zeros(self.nreads, dtype=GAP_DTYPE)
         self._check(self.L.real_gpu_get_gaps(self.h, g.ctypes.data))
         return g
+
+    # ---- output lines formatted on the device (K8)
+    @staticmethod
+    def _strings(items):
+        """bytes + offsets of a list of byte strings"""
+        blob = b"".join(items)
+        offs = np.zeros(len(items) + 1, dtype=np.uint64)
+        if items:
+            offs[1:] = np.cumsum([len(x) for x in items], dtype=np.uint64)
+        return blob, offs
+
+    def set_read_ids(self, ids, first: int = 0):
+        blob, offs = self._strings([x if isinstance(x, bytes) else x.encode() for x in ids])
+        buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+        self._check(self.L.real_gpu_set_read_ids(self.h, first, len(ids), buf.ctypes.data, offs.ctypes.data))
+
+    def set_record_names(self, names, record_starts, fileid: int = 0):
+        blob, offs = self._strings([x if isinstance(x, bytes) else x.encode() for x in names])
+        buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+        rs = np.ascontiguousarray(record_starts, dtype=np.uint64)
+        assert rs.size >= len(names)
+        self._check(self.L.real_gpu_set_record_names(self.h, fileid, len(names), buf.ctypes.data, offs.ctypes.data, rs.ctypes.data))
+
+    def format_unique(self, first: int = 0, count: int | None = None):
+        """(bytes of the lines of the reads [first, first+count), number of lines)"""
+        count = self.nreads - first if count is None else count
+        p, nb, nl = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.real_gpu_format_unique(self.h, first, count, C.byref(p), C.byref(nb), C.byref(nl)))
+        return (C.string_at(p.value, nb.value) if nb.value else b""), int(nl.value)
+
+    def format_all(self, first_row: int, count: int) -> bytes:
+        p, nb = C.c_void_p(), C.c_uint64()
+        self._check(self.L.real_gpu_format_all(self.h, first_row, count, C.byref(p), C.byref(nb)))
+        return C.string_at(p.value, nb.value) if nb.value else b""
 
     def stats(self) -> dict:
         s = Stats()

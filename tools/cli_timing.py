@@ -21,6 +21,7 @@ flags = ["-u", "1", "-s", "2", "-e", "4", "-l", "32", "-q", "0", "-R", "0"]
 res = {}
 for name, exe, extra, env in (("gpu_T1", rbuild.HOST_BIN, ["-T", "1"], {"REAL_TIMING": "1"}),
                               ("gpu_Tall", rbuild.HOST_BIN, [], {"REAL_TIMING": "1"}),
+                              ("gpu_Tall_hostfmt", rbuild.HOST_BIN, [], {"REAL_TIMING": "1", "REAL_FORMAT": "host"}),
                               ("gpu_Tall_hosttext", rbuild.HOST_BIN, [], {"REAL_TIMING": "1", "REAL_TEXT_LOADER": "host"}),
                               ("stock_cpu", os.path.join(ROOT, "oracle", "_ref", "real"), ["-T", str(os.cpu_count() or 1)], {})):
     if not os.path.exists(exe):
@@ -40,5 +41,7 @@ if "gpu_Tall" in res and "stock_cpu" in res:
     print("outputs identical to the stock binary:", same)
 if "gpu_Tall_hosttext" in res and "gpu_Tall" in res:
     print("outputs identical between the device and the host text loader:", open(res["gpu_Tall_hosttext"], "rb").read() == open(res["gpu_Tall"], "rb").read())
+if "gpu_Tall_hostfmt" in res and "gpu_Tall" in res:
+    print("outputs identical between the device and the host formatter:", open(res["gpu_Tall_hostfmt"], "rb").read() == open(res["gpu_Tall"], "rb").read())
 if "gpu_T1" in res and "gpu_Tall" in res:
     print("outputs identical between -T 1 and all threads:", open(res["gpu_T1"], "rb").read() == open(res["gpu_Tall"], "rb").read())
