@@ -64,6 +64,7 @@ bool RealOptions::isFastQ(std::string const & filename)
                 throw std::runtime_error("Failed to read first character from pattern file.");
         if ( first == '>' ) return false;
         if ( first == '@' ) return true;
+        if ( first == 0 ) return false;         // a rewritten pattern file kept from an earlier run (readRewritten decides)
         throw std::runtime_error("Unable to determine type of pattern file.");
 }
 
@@ -195,7 +196,19 @@ RealOptions::RealOptions(int argc, char * argv[])
                 }
         }
         else
+        {
                 fastq = isFastQ(patternfilename);
+                FileBytes head;
+                head.open(patternfilename);
+                if ( looksRewritten(head) )
+                {
+                        // the reference's rewritten pattern file, kept from an earlier run (REAL_KEEP_REWRITTEN): the reads come out of
+                        // it in rewritten order, qualities already reduced by their offset
+                        rewritten_reads.reset(new ReadSet());
+                        readRewritten(head, *rewritten_reads, fastq);
+                        std::cerr << "pattern file is a rewritten pattern file" << std::endl;
+                }
+        }
         std::cerr << "pattern file is " << (fastq ? "FASTQ" : "FASTA") << " rewrite is " << (rewritepatterns ? "on" : "off") << std::endl;
         if ( seedl > 64 )
         {
@@ -735,6 +748,149 @@ void reorderLikeRewrite(ReadSet & reads)
                 o.ids.push_back(reads.ids[r]);
         }
         reads.mapped.swap(o.mapped); reads.quality.swap(o.quality); reads.offsets.swap(o.offsets); reads.ids.swap(o.ids);
+}
+
+
+// ---- the reference's rewritten pattern file ---------------------------------------------------------
+
+namespace
+{
+        inline void putU32(std::vector<char> & o, uint32_t v) { o.push_back((char)(v >> 24)); o.push_back((char)(v >> 16)); o.push_back((char)(v >> 8)); o.push_back((char)v); }
+        inline void putU64(std::vector<char> & o, uint64_t v) { putU32(o, (uint32_t)(v >> 32)); putU32(o, (uint32_t)v); }
+        // section header: byte count (magic included; TemporaryFile::writeContent writes the length of its file), magic
+        inline void putSection(std::vector<char> & o, uint64_t payload, uint32_t magic)
+        {
+                uint64_t const bl = payload + 4;
+                if ( bl >= 0xFFFFFFFFULL ) { putU32(o, 0xFFFFFFFFu); putU64(o, bl); }
+                else putU32(o, (uint32_t)bl);
+                putU32(o, magic);
+        }
+}
+
+void writeRewritten(ReadSet const & reads, bool fastq, std::vector<char> & out)
+{
+        out.clear();
+        uint64_t const n = reads.size();
+        uint64_t r = 0;
+        while ( r < n )
+        {
+                uint64_t const L = reads.offsets[r+1] - reads.offsets[r];
+                // the reads of this length: wildcard free ones first [r, rn), then the others [rn, re)
+                uint64_t rn = r, re = r;
+                bool inN = false;
+                while ( re < n && reads.offsets[re+1] - reads.offsets[re] == L )
+                {
+                        bool hasn = false;
+                        for ( uint64_t i = reads.offsets[re]; i < reads.offsets[re+1]; ++i ) if ( reads.mapped[i] > 3 ) { hasn = true; break; }
+                        if ( hasn ) inN = true;
+                        else if ( inN ) throw std::runtime_error("writeRewritten: the reads are not in rewritten order");
+                        if ( ! inN ) rn = re + 1;
+                        ++re;
+                }
+                putU32(out, (uint32_t)L);
+                uint64_t const q = fastq ? L : 0;
+                for ( int part = 0; part < 2; ++part )
+                {
+                        uint64_t const a = part ? rn : r, b = part ? re : rn;
+                        uint64_t const code = part ? (L + 1) / 2 : (L + 3) / 4;
+                        putSection(out, (b - a) * (code + q), part ? 2u : 0u);
+                        for ( uint64_t x = a; x < b; ++x )
+                        {
+                                const uint8_t * m = &reads.mapped[0] + reads.offsets[x];
+                                if ( ! part )
+                                        for ( uint64_t i = 0; i < L; i += 4 )
+                                        {
+                                                unsigned int c = 0;
+                                                for ( uint64_t j = 0; j < 4 && i + j < L; ++j ) c |= (unsigned int)(m[i+j] & 3) << (6 - 2*j);
+                                                out.push_back((char)c);
+                                        }
+                                else
+                                        for ( uint64_t i = 0; i < L; i += 2 )
+                                                out.push_back((char)((std::min<unsigned int>(m[i], 4) << 4) | (i + 1 < L ? std::min<unsigned int>(m[i+1], 4) : 0u)));
+                                if ( fastq ) out.insert(out.end(), reads.quality.begin() + reads.offsets[x], reads.quality.begin() + reads.offsets[x+1]);
+                        }
+                        uint64_t idbytes = 0;
+                        for ( uint64_t x = a; x < b; ++x ) idbytes += 2 + reads.ids[x].size();
+                        putSection(out, idbytes, part ? 3u : 1u);
+                        for ( uint64_t x = a; x < b; ++x )
+                        {
+                                out.push_back((char)(reads.ids[x].size() >> 8)); out.push_back((char)reads.ids[x].size());      // writeNumber2
+                                out.insert(out.end(), reads.ids[x].begin(), reads.ids[x].end());
+                        }
+                }
+                r = re;
+        }
+}
+
+bool looksRewritten(FileBytes const & buf) { return buf.size() >= 8 && buf[0] == 0; }
+
+void readRewritten(FileBytes const & buf, ReadSet & reads, bool & fastq)
+{
+        reads.mapped.clear(); reads.quality.clear(); reads.ids.clear(); reads.offsets.assign(1, 0);
+        uint64_t at = 0;
+        uint64_t const size = buf.size();
+        auto need = [&](uint64_t k) { if ( at + k > size ) throw std::runtime_error("rewritten pattern file: truncated"); };
+        auto getU32 = [&]() -> uint32_t { need(4); const unsigned char * p = (const unsigned char *)&buf[at]; at += 4; return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; };
+        auto getSection = [&](uint32_t magic) -> uint64_t
+        {
+                uint64_t bl = getU32();
+                if ( bl == 0xFFFFFFFFULL ) { uint64_t const hi = getU32(), lo = getU32(); bl = (hi << 32) | lo; }
+                if ( bl < 4 || getU32() != magic ) throw std::runtime_error("rewritten pattern file: unexpected section");
+                need(bl - 4);
+                return bl - 4;
+        };
+        bool known = false;
+        fastq = false;
+        while ( at < size )
+        {
+                uint64_t const L = getU32();
+                struct Part { uint64_t data, ndata, ids, nids, nreads; } P[2];
+                for ( int part = 0; part < 2; ++part )
+                {
+                        P[part].ndata = getSection(part ? 2u : 0u); P[part].data = at; at += P[part].ndata;
+                        P[part].nids = getSection(part ? 3u : 1u); P[part].ids = at; at += P[part].nids;
+                        // the ids tell how many reads the section holds (the record size tells FASTA from FASTQ)
+                        uint64_t c = 0, x = P[part].ids, const_end = P[part].ids + P[part].nids;
+                        while ( x < const_end )
+                        {
+                                if ( x + 2 > const_end ) throw std::runtime_error("rewritten pattern file: broken id section");
+                                x += 2 + (((uint64_t)(unsigned char)buf[x] << 8) | (unsigned char)buf[x+1]);
+                                ++c;
+                        }
+                        if ( x != const_end ) throw std::runtime_error("rewritten pattern file: broken id section");
+                        P[part].nreads = c;
+                        uint64_t const code = part ? (L + 1) / 2 : (L + 3) / 4;
+                        if ( c && L )
+                        {
+                                bool fq;
+                                if ( P[part].ndata == c * code ) fq = false;
+                                else if ( P[part].ndata == c * (code + L) ) fq = true;
+                                else throw std::runtime_error("rewritten pattern file: section size does not match its ids");
+                                if ( known && fq != fastq ) throw std::runtime_error("rewritten pattern file: mixed record kinds");
+                                known = true; fastq = fq;
+                        }
+                }
+                for ( int part = 0; part < 2; ++part )
+                {
+                        uint64_t const code = part ? (L + 1) / 2 : (L + 3) / 4, rec = code + (fastq ? L : 0);
+                        uint64_t x = P[part].ids;
+                        for ( uint64_t i = 0; i < P[part].nreads; ++i )
+                        {
+                                const unsigned char * d = (const unsigned char *)&buf[0] + P[part].data + i * rec;
+                                size_t const o = reads.mapped.size();
+                                reads.mapped.resize(o + L);
+                                if ( ! part )
+                                        for ( uint64_t j = 0; j < L; ++j ) reads.mapped[o + j] = (d[j >> 2] >> (6 - 2 * (j & 3))) & 3;
+                                else
+                                        for ( uint64_t j = 0; j < L; ++j ) reads.mapped[o + j] = std::min<unsigned int>((d[j >> 1] >> ((j & 1) ? 0 : 4)) & 15, 4);
+                                if ( fastq ) reads.quality.insert(reads.quality.end(), d + code, d + code + L);
+                                reads.offsets.push_back(reads.mapped.size());
+                                uint64_t const il = ((uint64_t)(unsigned char)buf[x] << 8) | (unsigned char)buf[x+1];
+                                reads.ids.push_back(std::string(&buf[0] + x + 2, &buf[0] + x + 2 + il));
+                                x += 2 + il;
+                        }
+                }
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1312,8 +1468,20 @@ int doMatchingUnique(RealOptions const & opts)
         ReadSet reads;
         loadReads(opts, reads);
         PT.lap("read patterns");
-        if ( opts.rewritepatterns )
+        if ( opts.rewritepatterns && ! opts.rewritten_reads )
                 reorderLikeRewrite(reads);
+        if ( char const * keep = getenv("REAL_KEEP_REWRITTEN") )
+        {
+                // the reference writes this file for every -R 1 run and deletes it afterwards (real.cpp:238-311); kept, it can be
+                // given back as -p and spares the next run the parsing of the pattern file
+                if ( opts.rewritepatterns || opts.rewritten_reads )
+                {
+                        std::vector<char> bytes;
+                        writeRewritten(reads, opts.fastq, bytes);
+                        Output keepf(keep);
+                        if ( ! bytes.empty() && fwrite(&bytes[0], 1, bytes.size(), keepf.f) != bytes.size() ) throw std::runtime_error("write failed");
+                }
+        }
         PackedReads packed;
         packReads(reads, packed, hostThreads(opts));
         std::vector<std::string> filenames;

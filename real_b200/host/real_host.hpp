@@ -53,6 +53,7 @@ struct RealOptions
         int device;             // REAL_GPU_DEVICE, default 0
         int ngpus;              // REAL_GPUS, default 1: handles (= bucket shards) the matching is spread over, device + i modulo the
                                 // devices present; the order dependent folds (-q 1, -g 1) always run on one handle
+        std::shared_ptr<struct ReadSet> rewritten_reads;    // -p names a rewritten pattern file (first byte 0): its reads, in rewritten order
         std::shared_ptr< std::vector<char> > stdin_bytes;   // -p -: the pattern file as read from standard input (RealOptions.cpp:418-426)
 
         RealOptions(int argc, char * argv[]);
@@ -105,6 +106,21 @@ void readPatterns(std::string const & filename, bool fastq, int qualityOffset, R
 void readPatternsBuffer(FileBytes const & buf, bool fastq, int qualityOffset, ReadSet & out, unsigned int threads);
 // the order the rewritten pattern file hands the reads out in (-R 1): by length, wildcard-free reads first
 void reorderLikeRewrite(ReadSet & reads);
+// The reference's rewritten pattern file itself (reorderFastA / reorderFastQ, ReorderFastA.hpp, ReorderFastQ.hpp,
+// TemporaryFile.hpp:194-403; read back by FastDecoder.hpp:66-130, FastSubDecoder.hpp:53-168): per pattern length, ascending,
+//     u32be length | ACGT section | ACGT ids | ACGTN section | ACGTN ids
+// every section = u32be byte count (magic included) | u32be magic 0..3 | payload.  ACGT payload: per read ceil(L/4) bytes,
+// 2 bit/base, first base in bits 7..6 (FASTQ: followed by the L quality values); ACGTN payload: per read ceil(L/2) bytes,
+// 4 bit/base, first base in the high nibble (FASTQ: + L quality values); id payload: per read u16be length | bytes.
+// The reference deletes the file when it is done (real.cpp:281-311); here it can be kept (REAL_KEEP_REWRITTEN=<path>) and
+// given back as -p: a pattern file whose first byte is 0 is taken as a rewritten file, and its ACGT sections go to the
+// device as they are.  A section of 4 GiB or more does not fit the format's 32-bit count (the reference writes the
+// count modulo 2^32 and cannot read such a file back): it is written as count 0xFFFFFFFF followed by a u64be count.
+// `reads` must be in rewritten order (reorderLikeRewrite).
+void writeRewritten(ReadSet const & reads, bool fastq, std::vector<char> & out);
+bool looksRewritten(FileBytes const & buf);
+// fills `reads` (in rewritten order) from the bytes of a rewritten file; fastq = whether its records carry qualities
+void readRewritten(FileBytes const & buf, ReadSet & reads, bool & fastq);
 // The reads 2 bit/base in the layout of the reference's rewritten pattern file (TemporaryFile.hpp:231-268,
 // writePatternDontCareFree): 4 bases per byte, first base in bits 7..6, every read on a byte boundary; reads with a
 // wildcard are flagged (the reference keeps them in a 4 bit/base section of their own) and stored as A.  This is what

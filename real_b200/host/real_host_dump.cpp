@@ -57,6 +57,35 @@ int main(int argc, char * argv[])
                         for ( size_t i = 0; i < R.quality.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)R.quality[i]);
                         printf("]}\n");
                 }
+                else if ( mode == "rewrite" )
+                {
+                        // <pattern file> <fastq> <quality offset> <out>: the reference's rewritten pattern file of it (writeRewritten)
+                        bool const fastq = atoi(argv[3]); int qoff = atoi(argv[4]);
+                        if ( fastq && ! qoff ) qoff = detectQualityOffset(argv[2]);
+                        ReadSet R; readPatterns(argv[2], fastq, qoff, R);
+                        reorderLikeRewrite(R);
+                        std::vector<char> bytes; writeRewritten(R, fastq, bytes);
+                        FILE * f = fopen(argv[5], "wb");
+                        if ( ! f || (bytes.size() && fwrite(&bytes[0], 1, bytes.size(), f) != bytes.size()) ) throw std::runtime_error("cannot write");
+                        fclose(f);
+                        printf("{\"bytes\":%llu}\n", (unsigned long long)bytes.size());
+                }
+                else if ( mode == "unrewrite" )
+                {
+                        FileBytes buf; buf.open(argv[2]);
+                        ReadSet R; bool fastq = false;
+                        if ( ! looksRewritten(buf) ) throw std::runtime_error("not a rewritten pattern file");
+                        readRewritten(buf, R, fastq);
+                        printf("{\"fastq\":%d,\"ids\":[", (int)fastq);
+                        for ( size_t i = 0; i < R.ids.size(); ++i ) { if ( i ) putchar(','); jstr(R.ids[i]); }
+                        printf("],\"offsets\":[");
+                        for ( size_t i = 0; i < R.offsets.size(); ++i ) printf("%s%llu", i ? "," : "", (unsigned long long)R.offsets[i]);
+                        printf("],\"mapped\":[");
+                        for ( size_t i = 0; i < R.mapped.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)R.mapped[i]);
+                        printf("],\"quality\":[");
+                        for ( size_t i = 0; i < R.quality.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)R.quality[i]);
+                        printf("]}\n");
+                }
                 else if ( mode == "ll" )
                 {
                         double ll[1024];

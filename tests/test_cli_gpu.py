@@ -122,3 +122,26 @@ def test_cli_match_all_several_handles(tmp_path):
         assert p.returncode == 0, p.stderr[-2000:]
         outs.append(out.read_text())
     assert len(outs[0].splitlines()) > 900 and outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("name", ["unique_fa_R1", "unique_fq_scores_default"])
+def test_cli_kept_rewritten_pattern_file(name, tmp_path):
+    """next-4: REAL_KEEP_REWRITTEN keeps the reference's rewritten pattern file (which the stock binary deletes); given back as
+    -p it is read instead of parsing the FASTA/FASTQ file again, and the output is the stock binary's."""
+    rbuild.build()
+    rbuild.build_host()
+    targ, rf, flags = make_case(name, str(tmp_path))
+    want = open(os.path.join(GOLDEN, "cli_%s.txt" % name)).read()
+    kept = tmp_path / "kept.bin"
+    out = tmp_path / "out.txt"
+    p = subprocess.run([rbuild.HOST_BIN, "-t", targ, "-p", rf, "-o", str(out)] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, REAL_STRICT_EXIT="1", REAL_KEEP_REWRITTEN=str(kept)))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert out.read_text() == want and kept.stat().st_size > 1000 and kept.read_bytes()[0] == 0
+    out2 = tmp_path / "out2.txt"
+    flags2 = [f for f in flags]
+    p = subprocess.run([rbuild.HOST_BIN, "-t", targ, "-p", str(kept), "-o", str(out2)] + flags2, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, REAL_STRICT_EXIT="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "rewritten pattern file" in p.stderr
+    assert out2.read_text() == want
