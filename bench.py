@@ -13,8 +13,10 @@ exchange; total work is fixed as N grows ("strong").
 `e2e`    : the same from pinned host buffers (H2D of text + 2-bit reads and D2H of the per-read
            results inside the timed region); N=1 through the host-pointer C ABI, N>1 every rank
            uploads 1/N of the bytes and NCCL all-gathers the rest over NVLink.
-`roofline`: the text-scan kernels against the measured HBM peak, algorithmic bytes per SURVEY 8(d),
-           `traffic` = DRAM bytes of the committed ncu capture (profiles/r01_traffic_c3.json).
+`roofline`: the text-scan kernels against the measured HBM peak, algorithmic bytes per SURVEY 8(d);
+           `traffic` = DRAM bytes of the committed ncu capture (profiles/r02_kernels_c3.json), `hbm_traffic_frac` what
+           that is of the HBM peak over the measured scan time, `l1tex` the bound the probe kernel runs against
+           (scattered loads out of L2), `kernels` the per-kernel table of the capture.
 `cpu_baseline` / --impl reference: the reference's own CPU code (oracle/_ref/ref_harness, compiled
 from the reference sources) on a bounded sample, extrapolated linearly to the workload.
 `ingest` : (N=1, an extra outside the timed step) K0, the FASTA text loader on the device, on a 260 MB
@@ -344,16 +346,25 @@ def run_reference_arm(args, wl):
     return 0
 
 
-def scan_traffic(workload: str, world: int, as_rank: str):
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) the scan kernels of ONE step moved in the committed
-    `ncu --set full` capture of this workload (profiles/r01_traffic_<workload>.json), or None when no capture matches."""
+def kernel_table(workload: str, world: int, as_rank: str):
+    """The committed per-kernel summary of an `ncu --set full` capture of one step of this workload on one GPU
+    (profiles/r02_kernels_<workload>.json, made by tools/kernel_table.py; falls back to the round-1 traffic file), or None."""
     if world != 1 or as_rank:
         return None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % workload)) as f:
-            return float(json.load(f)["scan_dram_bytes_per_step"])
-    except Exception:
-        return None
+    for name in ("r02_kernels_%s.json", "r01_traffic_%s.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name % workload)) as f:
+                d = json.load(f)
+            d["file"] = "profiles/" + name % workload
+            return d
+        except Exception:
+            continue
+    return None
+
+
+# scattered loads served by L2: one distinct 128-byte line per cycle and SM through the L1TEX tag stage -- 277-281 G lines/s on
+# this pool's B200 for resident sets up to ~96 MB (tools/l2_resident_bench.cu, profiles/r01_l2_resident_bench.txt)
+L1TEX_LINES_PER_S = 280e9
 
 
 def ingest_probe(torch, rlib, peak_gbs: float) -> dict:
@@ -508,7 +519,7 @@ def main():
             rdist.unique_exchange(shard, keys=keys, ties=ties)
     hstream = torch.cuda.ExternalStream(h.stream(), device=dev)
 
-    phase = {"pack_ms": [], "index_ms": [], "scan_ms": [], "post_ms": [], "d2h_ms": [], "h2d_text_ms": [], "exchange_ms": [], "fold_ms": [],
+    phase = {"pack_ms": [], "index_ms": [], "scan_ms": [], "probe_ms": [], "post_ms": [], "d2h_ms": [], "h2d_text_ms": [], "exchange_ms": [], "fold_ms": [],
              "gap_scan_ms": [], "gap_post_ms": [],
              "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": []}
     last_stats = {}
@@ -629,12 +640,31 @@ def main():
     alg_bytes = 0.375 * n_text_local + 192.0 * last_stats["n_windows"] + 64.0 * last_stats["n_candidates"] + 16.0 * last_stats["n_hits"]
     design_bytes = 0.375 * n_text_local + 32.0 * last_stats["n_probes"] + 64.0 * last_stats["n_candidates"] + 16.0 * last_stats["n_hits"]
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    ktab = kernel_table(args.workload, world, args.as_rank)
+    traffic = float(ktab["scan_dram_bytes_per_step"]) if ktab else None
+    probe_ms = statistics.mean(phase["probe_ms"]) if phase["probe_ms"] else 0.0
+    # what the probe kernel pushes through the L1TEX tag stage: one line per probe, per entry followed, per 128 bytes of records
+    lines = last_stats["n_probes"] + last_stats["n_candidates"] + last_stats["n_windows"] * 16.0 / 128.0
     roofline = {"bound": "hbm", "kernel": "k_bucket_probe (+k_part): text scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                "traffic": scan_traffic(args.workload, world, args.as_rank), "alg_bytes_per_launch": alg_bytes, "scan_ms": scan_ms,
+                "traffic": traffic, "alg_bytes_per_launch": alg_bytes, "scan_ms": scan_ms,
                 "design_bytes_per_launch": design_bytes, "design_frac": design_bytes / (scan_ms * 1e-3) / 1e9 / peak,
+                # the physical picture next to the contract's figure: DRAM bytes the scan kernels really moved (ncu) over the
+                # measured scan time, as a fraction of the HBM peak
+                "hbm_traffic_frac": (traffic / (scan_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                # the bound the design runs against: probes are scattered 8-byte loads served by L2
+                "l1tex": {"bound": "L1TEX tag stage, one distinct 128-byte line per cycle and SM (scattered loads out of L2)",
+                          "lines_per_step": lines, "probe_ms": probe_ms, "partition_ms": scan_ms - probe_ms,
+                          "achieved_lines_per_s": (lines / (probe_ms * 1e-3)) if probe_ms else None, "peak_lines_per_s": L1TEX_LINES_PER_S,
+                          "frac": (lines / (probe_ms * 1e-3) / L1TEX_LINES_PER_S) if probe_ms else None,
+                          "peak_source": "tools/l2_resident_bench.cu on this pool (profiles/r01_l2_resident_bench.txt)"},
+                "kernels": ({"file": ktab.get("file"), "source": ktab.get("source"),
+                             "table": [{k: a.get(k) for k in ("kernel", "launches", "ms_under_ncu", "dram_read_bytes", "dram_write_bytes", "dram_GBps_under_ncu", "registers",
+                                                              "warps_active_pct", "issue_active_pct", "busiest_unit", "unit_pct_of_peak", "l2_hit_rate_pct", "top_stalls")}
+                                       for a in ktab.get("kernels", [])[:8]]} if ktab and "kernels" in ktab else None),
                 "note": "alg bytes = 0.375*N_text + 6*32*N_win + 64*N_cand + 16*N_hit (SURVEY 8d, six lists); the kernel probes 3 merged "
-                        "tables per window (design bytes = 3*32*N_win + ...), so frac can exceed the sector-traffic fraction"}
+                        "tables per window out of L2-resident slices (design bytes = 3*32*N_win + ...), so frac exceeds the sector-traffic "
+                        "fraction: hbm_traffic_frac is what DRAM really carried, l1tex.frac is the bound the probe kernel runs against"}
     if world > 1:
         dist.all_reduce(nwin_tot, op=dist.ReduceOp.SUM)
 

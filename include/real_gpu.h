@@ -105,7 +105,7 @@ typedef struct
         uint64_t n_seedpass;    /* candidates that passed the seed test and the canonical-list rule */
         uint64_t n_hits;        /* hits emitted */
         float fold_ms;          /* real_gpu_fold_unique*: push + hand-over + merge */
-        float reserved;
+        float probe_ms;         /* the probe kernels' part of scan_ms (the rest is the partition of the text positions) */
 } real_gpu_stats;
 
 int real_gpu_abi_version(void);

@@ -55,6 +55,7 @@ struct real_gpu
         cudaStream_t st2;              // host<->device copies of the text, so that they overlap the index build on st
         cudaEvent_t ev[8];
         cudaEvent_t evc[2];
+        std::vector<cudaEvent_t> evp;  // pairs around the probe kernel of every chunk of a scan (stats.probe_ms)
         bool fused_build;              // the current tables were built by build_tables_fused (entry arrays in item numbering)
         bool build_pending;            // the index build of the current read set has been enqueued but not yet waited for
         uint64_t held;
@@ -845,6 +846,7 @@ uint64_t run_scan(real_gpu * h, int mode)
         uint64_t const first_tile = P.x_begin / SC_TILE_POS, end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
         uint64_t const ntiles = (P.x_end > P.x_begin) ? (end_tile - first_tile) : 0;
         RG_CUDA(cudaEventRecord(h->ev[5], h->st));
+        size_t nprobe_ev = 0;
         if ( ntiles )
         {
                 // buckets: cut the tables into key-prefix slices that stay resident in L2 while a bucket is probed
@@ -981,6 +983,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                 auto mark = [&]() { if ( trace ) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->st); tev.push_back(e); } };
                 for ( uint64_t cb = x_begin; cb < x_end; cb += chunk_cap )
                 {
+                        if ( nprobe_ev >= 64 ) nprobe_ev = 63;              // (very long texts: the last pairs are re-used)
                         mark();
                         uint64_t const ce = std::min<uint64_t>(x_end, cb + chunk_cap);
                         P.pos_base = cb;
@@ -1038,8 +1041,17 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 RG_KERNEL_CHECK(); launch_count(h);
                         }
                         mark();
+                        if ( h->evp.size() < 2 * (nprobe_ev + 1) )
+                        {
+                                cudaEvent_t a, b;
+                                RG_CUDA(cudaEventCreate(&a)); RG_CUDA(cudaEventCreate(&b));
+                                h->evp.push_back(a); h->evp.push_back(b);
+                        }
+                        RG_CUDA(cudaEventRecord(h->evp[2 * nprobe_ev], h->st));
                         probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
+                        RG_CUDA(cudaEventRecord(h->evp[2 * nprobe_ev + 1], h->st));
+                        ++nprobe_ev;
                         mark();
                         if ( sharded )
                         {
@@ -1066,6 +1078,8 @@ uint64_t run_scan(real_gpu * h, int mode)
         RG_CUDA(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.scan_ms = elapsed(h->ev[5], h->ev[6]);
+        h->stats.probe_ms = 0;
+        for ( size_t i = 0; i < nprobe_ev; ++i ) h->stats.probe_ms += elapsed(h->evp[2*i], h->evp[2*i+1]);
         if ( ! ntiles ) h->stats.n_windows = 0;
         else if ( h->comm.nranks > 1 && ! h->comm.window.p ) h->stats.n_windows = c[4];     // bucket shard: the positions this handle kept
         if ( h->comm.nranks > 1 && h->comm.window.p )
@@ -1211,6 +1225,7 @@ int real_gpu_destroy(real_gpu * h)
                 for ( int i = 0; i < 2; ++i ) if ( h->fmt.host[i] ) cudaFreeHost(h->fmt.host[i]);
         }
         for ( int i = 0; i < 8; ++i ) if ( h->ev[i] ) cudaEventDestroy(h->ev[i]);
+        for ( cudaEvent_t e : h->evp ) cudaEventDestroy(e);
         for ( int i = 0; i < 2; ++i ) if ( h->evc[i] ) cudaEventDestroy(h->evc[i]);
         if ( h->st2 ) cudaStreamDestroy(h->st2);
         if ( h->table_counts ) cudaFreeHost(h->table_counts);

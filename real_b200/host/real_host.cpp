@@ -1269,6 +1269,14 @@ namespace
         {
                 FileBytes buf;
                 PhaseTimer PT;
+                if ( opts.rewritten_reads )
+                {
+                        // -p named a rewritten pattern file: its reads were taken out of it when the options were read
+                        reads.mapped.swap(opts.rewritten_reads->mapped); reads.quality.swap(opts.rewritten_reads->quality);
+                        reads.offsets.swap(opts.rewritten_reads->offsets); reads.ids.swap(opts.rewritten_reads->ids);
+                        std::cerr << "Number of patterns is " << reads.size() << std::endl;
+                        return;
+                }
                 if ( opts.stdin_bytes )
                         buf.adopt(*opts.stdin_bytes);
                 else

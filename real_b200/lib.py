@@ -34,7 +34,7 @@ class Stats(C.Structure):
                 ("scan_ms", C.c_float), ("post_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("scan_launches", C.c_uint32), ("total_launches", C.c_uint32),
                 ("n_windows", C.c_uint64), ("n_probes", C.c_uint64), ("n_candidates", C.c_uint64),
-                ("n_seedpass", C.c_uint64), ("n_hits", C.c_uint64), ("fold_ms", C.c_float), ("reserved", C.c_float)]
+                ("n_seedpass", C.c_uint64), ("n_hits", C.c_uint64), ("fold_ms", C.c_float), ("probe_ms", C.c_float)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
