@@ -418,7 +418,6 @@ struct ScatterSmem
         uint32_t loc[SC_MAX_BUCKETS + 1];                  // first staging slot of a bucket
         uint4 * dst[SC_MAX_BUCKETS];                       // per tile: record area of the bucket's owner + first record of the tile's run - first staging slot
         uint4 * area[SC_MAX_BUCKETS];                      // record area of the bucket's owner
-        uint8_t stage_b[PS_TILE_POS];
 };
 
 // LIST: the positions come from the kept-position list of a bucket shard (k_own_list) instead of the text tiles
@@ -575,34 +574,33 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
                                 {
                                         uint32_t const slot = pre + below;
                                         uint64_t const win = wv[jb + u] >> fsh;
-                                        S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), wbefore[jb + u], wpos[jb + u]);
-                                        S.stage_b[slot] = (uint8_t)b[u];
+                                        S.stage[slot] = make_uint4((uint32_t)win, (uint32_t)(win >> 32), wbefore[jb + u], wpos[jb + u] + pos0);
                                 }
                         }
                 }
                 // where staging slot 0 would go if it belonged to this bucket: the copy-out adds the slot number
                 S.dst[threadIdx.x] = S.area[threadIdx.x] + ((int64_t)(bstart + reserved) - (int64_t)S.loc[threadIdx.x]);
                 __syncthreads();
-                // (4) copy out: consecutive threads write consecutive records of a bucket run; four records in flight per thread,
-                // one dependent shared-memory load each
+                // (4) copy out: consecutive threads write consecutive records of a bucket run; four records in flight per thread.
+                // The bucket of a record is recomputed from its window (three ALU instructions) instead of being staged beside it:
+                // the kernel is limited by its shared-memory instructions, not by arithmetic
                 {
                         uint32_t const n = S.loc[SC_MAX_BUCKETS];
                         uint32_t i = threadIdx.x;
                         for ( ; i + 3 * SC_THREADS < n; i += 4 * SC_THREADS )
                         {
-                                uint32_t b[4]; uint4 r[4]; uint4 * d[4];
+                                uint4 r[4]; uint4 * d[4];
                                 #pragma unroll
-                                for ( int u = 0; u < 4; ++u ) { b[u] = S.stage_b[i + u * SC_THREADS]; r[u] = S.stage[i + u * SC_THREADS]; }
+                                for ( int u = 0; u < 4; ++u ) r[u] = S.stage[i + u * SC_THREADS];
                                 #pragma unroll
-                                for ( int u = 0; u < 4; ++u ) d[u] = S.dst[b[u]];
+                                for ( int u = 0; u < 4; ++u ) d[u] = S.dst[(uint32_t)(((((uint64_t)r[u].y << 32) | r[u].x) << fsh) >> bsh) & bmask];
                                 #pragma unroll
-                                for ( int u = 0; u < 4; ++u ) { r[u].w += pos0; d[u][i + u * SC_THREADS] = r[u]; }
+                                for ( int u = 0; u < 4; ++u ) d[u][i + u * SC_THREADS] = r[u];
                         }
                         for ( ; i < n; i += SC_THREADS )
                         {
-                                uint4 r = S.stage[i];
-                                r.w += pos0;
-                                S.dst[S.stage_b[i]][i] = r;
+                                uint4 const r = S.stage[i];
+                                S.dst[(uint32_t)(((((uint64_t)r.y << 32) | r.x) << fsh) >> bsh) & bmask][i] = r;
                         }
                 }
                 __syncthreads();

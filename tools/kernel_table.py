@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """profiles/rNN_kernels_<workload>.json from an `ncu --set full` capture of one bench step.
 
-usage: ncu -i x.ncu-rep --page raw --csv > raw.csv; python tools/kernel_table.py raw.csv c3 "<source note>" > profiles/r02_kernels_c3.json
+usage: ncu -i x.ncu-rep --page raw --csv > raw.csv; python tools/kernel_table.py raw.csv c3 "<source note>" [scan_steps] > profiles/r02_kernels_c3.json
+scan_steps = how many steps' worth of scan launches the capture holds (the capture window may span the warm-up step), default 1.
 
 Per kernel of the step (summed over its launches): launches, time under ncu, DRAM bytes read + written, and -- from the
 launch with the longest duration -- registers, achieved occupancy, issue-slot use, the busiest unit (DRAM / L1TEX / LTS /
@@ -56,9 +57,10 @@ for a in agg.values():
     a["dram_GBps_under_ncu"] = round((a["dram_read_bytes"] + a["dram_write_bytes"]) / max(a["ms_under_ncu"], 1e-9) / 1e6, 1)
     kernels.append(a)
 kernels.sort(key=lambda a: -a["ms_under_ncu"])
-scan = sum(a["dram_read_bytes"] + a["dram_write_bytes"] for a in kernels if any(a["kernel"].startswith(s) for s in SCAN))
+scan_steps = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+scan = sum(a["dram_read_bytes"] + a["dram_write_bytes"] for a in kernels if any(a["kernel"].startswith(s) for s in SCAN)) / scan_steps
 print(json.dumps({"source": sys.argv[3] if len(sys.argv) > 3 else sys.argv[1], "workload": sys.argv[2], "n_gpus": 1,
-                  "scan_dram_bytes_per_step": scan,
+                  "scan_dram_bytes_per_step": scan, "scan_steps_in_capture": scan_steps,
                   "note": "one step under `ncu --set full --clock-control none` (cold caches, serialised launches: shares, not absolute times); "
                           "scan_dram_bytes_per_step = dram__bytes_read.sum + dram__bytes_write.sum of the scan kernels",
                   "kernels": kernels}, indent=1))
