@@ -173,7 +173,9 @@ int real_gpu_get_text_packed(real_gpu * h, uint64_t n_bases, uint64_t * words, u
  *   offsets  nreads+1 byte offsets into mapped/quality
  * Reads shorter than seedl or containing a wildcard are kept but never match
  * (matchAllImplementation.cpp:273-289).  Resets the unique-match state.
- * Limits: nreads < 2^28, read length <= 65535. */
+ * Limits: nreads < 2^28 per read set (a raw hit carries the read ordinal in 28 bits beside its exact-fragment mask; the
+ * reference counts reads in 64 bits -- larger sets are matched in batches of reads, each batch against every file, and their
+ * output concatenated: reads are independent of each other), read length <= 65535. */
 int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * quality,
                        const uint64_t * offsets, uint64_t nreads);
 /* Same as real_gpu_set_reads for reads that are already packed 2 bit/base the way the reference's rewritten pattern
@@ -208,7 +210,14 @@ int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhit
 
 /* Folds the current text into the per-read unique state (UniqueMatcher::match for every read);
  * call once per file/shard, state persists like the reference's uniqueinfo array
- * (matchUniqueImplementation.cpp:1097). */
+ * (matchUniqueImplementation.cpp:1097).
+ * Without scores the fold is order independent and the words equal the reference's bit for bit, with one exception the
+ * reference itself leaves to its visiting order: the position / file / record fields of a word whose state is NonUnique
+ * (two placements at the lowest error count) hold the placement the reference happened to visit first; here they hold the
+ * smallest one (file, then position), which makes the word deterministic.  NonUnique reads are never printed, and tests and
+ * gates compare those words by state and error count (matcher.canonical_unique, real_gpu_unique_checksum).
+ * With scores (order dependent) the words and score bits equal the reference's exactly, given its text-block size
+ * (real_gpu_set_block_windows). */
 int real_gpu_match_unique(real_gpu * h);
 /* Copies out the state: info[nreads] in UniqueMatchInfo bit layout (UniqueMatchInfo.hpp:26-39:
  * pos 35 | file 6 | err 4 | frag 16 | state 3, low to high), scores[nreads] or NULL. */

@@ -873,7 +873,18 @@ struct Build3Params
 
 // SPLIT: one CTA per (sub-bucket, table) -- a third of the shared memory and fewer registers per CTA, so that enough CTAs
 // are resident to hide the latencies of a kernel that is a chain of short phases (items -> presence bits -> ranks -> heads)
-template<bool SPLIT>
+// FAST: -l 32 (fragments of 8 bases, 2^32 slots, sub-buckets of 2^16 slots): the slot of an entry relative to its sub-bucket is
+// simply the second fragment of its pair, one 16-bit field of the seed -- the general path (entry_slot) spends some twenty
+// instructions per entry and pass on runtime geometry
+template<bool FAST>
+__device__ __forceinline__ uint32_t sub_local_slot(uint64_t seed, TableGeom const & G, uint32_t t, int tb, uint32_t slot0)
+{
+        if ( FAST )
+                return (uint32_t)(seed >> (16u * (2u - t - (uint32_t)tb))) & 0xFFFFu;
+        return entry_slot(seed, G, t) - slot0;
+}
+
+template<bool SPLIT, bool FAST>
 __global__ void __launch_bounds__(256, SPLIT ? 6 : 3) k_build_sub3(const __grid_constant__ Build3Params P)
 {
         extern __shared__ __align__(16) uint32_t sub_smem[];
@@ -887,6 +898,13 @@ __global__ void __launch_bounds__(256, SPLIT ? 6 : 3) k_build_sub3(const __grid_
         uint32_t const s0 = P.sub_start[sb], s1 = P.sub_start[sb+1];
         uint32_t const slot0 = sb << P.sub_shift;
         uint32_t const tstride = 2 * words + (words + 1) / 2;          // per table: presence bits, claimed bits (u32 each), ranks (u16, relative to s0)
+        // the items of the sub-bucket (some 55 KB) are pulled into L2 while the shared memory is cleared: the two passes below
+        // wait for their item loads more than for anything else (a third of the stall samples), four loads per thread at a time
+        for ( uint32_t i = s0 + threadIdx.x * 16; i < s1; i += 256 * 16 )
+        {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(P.item_seed + i));
+                if ( ((i - s0) & 31) == 0 ) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.item_val + i));
+        }
         for ( uint32_t w = threadIdx.x; w < NT * tstride; w += 256 ) sub_smem[w] = 0;
         if ( threadIdx.x < NT ) ndup[threadIdx.x] = 0;
         __syncthreads();
@@ -912,7 +930,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 6 : 3) k_build_sub3(const __grid_
                                         int const tb = tb0 + u;
                                         if ( t < P.G[tb].nlists )
                                         {
-                                                uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
+                                                uint32_t const l = sub_local_slot<FAST>(seed[k], P.G[tb], t, tb, slot0);
                                                 atomicOr(&sub_smem[u * tstride + (l >> 5)], 1u << (l & 31));
                                         }
                                 }
@@ -976,7 +994,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 6 : 3) k_build_sub3(const __grid_
                                         {
                                                 uint32_t * bits = sub_smem + u * tstride, * claimed = bits + words;
                                                 const uint16_t * rank = reinterpret_cast<const uint16_t *>(bits + 2 * words);
-                                                uint32_t const l = entry_slot(seed[k], P.G[tb], t) - slot0;
+                                                uint32_t const l = sub_local_slot<FAST>(seed[k], P.G[tb], t, tb, slot0);
                                                 uint32_t const bit = 1u << (l & 31);
                                                 uint32_t const r = s0 + rank[l >> 5] + __popc(bits[l >> 5] & (bit - 1));
                                                 Entry * E = P.E[tb];

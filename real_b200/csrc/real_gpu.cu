@@ -559,16 +559,13 @@ bool build_tables_fused(real_gpu * h, TablePlan * plan)
         if ( const char * e = getenv("REAL_GPU_BUILD_SPLIT") ) split = atoi(e) != 0;
         size_t const smem1 = (size_t)(2 * TP.words + (TP.words + 1) / 2) * 4;
         size_t const smem = split ? smem1 : 3 * smem1;
-        if ( split )
-        {
-                RG_CUDA(cudaFuncSetAttribute(k_build_sub3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_build_sub3<true><<<TP.own_subs * 3, 256, smem, h->st>>>(B);
-        }
-        else
-        {
-                RG_CUDA(cudaFuncSetAttribute(k_build_sub3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_build_sub3<false><<<TP.own_subs, 256, smem, h->st>>>(B);
-        }
+        // -l 32: fragments of 8 bases, direct addressing, sub-buckets of 2^16 slots (sub_local_slot)
+        bool const fast = h->F == 8 && hb == 32 && TP.sub_shift == 16 && ! getenv("REAL_GPU_BUILD_GENERAL");
+        typedef void (*build_fn)(const Build3Params);
+        build_fn const kb = split ? (fast ? (build_fn)k_build_sub3<true, true> : (build_fn)k_build_sub3<true, false>)
+                                  : (fast ? (build_fn)k_build_sub3<false, true> : (build_fn)k_build_sub3<false, false>);
+        RG_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kb<<<split ? TP.own_subs * 3 : TP.own_subs, 256, smem, h->st>>>(B);
         RG_KERNEL_CHECK(); launch_count(h);
         RG_CUDA(cudaMemcpyAsync(&h->table_counts[0], TP.d_total, 16, cudaMemcpyDeviceToHost, h->st));   // items, distinct slots of A, B, C
         h->fused_build = true;
@@ -964,7 +961,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                 RG_CUDA(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
                 int occ_p = 0, occ_b = 0, occ_s = 0;
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, psmem));
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, own_list ? k_part_scatter<true> : k_part_scatter<false>, SC_THREADS, ssmem));
+                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, own_list ? k_part_scatter<true> : k_part_scatter<false>, PS_THREADS, ssmem));
                 RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, probe, SC_THREADS, bsmem));
                 if ( occ_p < 1 ) occ_p = 1;
                 if ( occ_s < 1 ) occ_s = 1;
@@ -1027,9 +1024,9 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
                                 unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
                                 if ( own_list )
-                                        k_part_scatter<true><<<(unsigned)(h->sm_count * occ_s), SC_THREADS, ssmem, h->st>>>(P);
+                                        k_part_scatter<true><<<(unsigned)(h->sm_count * occ_s), PS_THREADS, ssmem, h->st>>>(P);
                                 else
-                                        k_part_scatter<false><<<sgrid, SC_THREADS, ssmem, h->st>>>(P);
+                                        k_part_scatter<false><<<sgrid, PS_THREADS, ssmem, h->st>>>(P);
                                 RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
                         }
                         mark();
@@ -1107,7 +1104,7 @@ void preload_kernels(int device)
         cudaFuncAttributes a;
 #define RG_PRELOAD(k) RG_CUDA(cudaFuncGetAttributes(&a, k))
         RG_PRELOAD(k_pack_reads); RG_PRELOAD(k_pack_both); RG_PRELOAD(k_seeds_packed); RG_PRELOAD(k_read_seeds); RG_PRELOAD(k_uniform_offsets); RG_PRELOAD(k_flags_to_bad);
-        RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub); RG_PRELOAD(k_build_sub3<true>); RG_PRELOAD(k_build_sub3<false>);
+        RG_PRELOAD(k_ent_hist3); RG_PRELOAD(k_ent_offsets); RG_PRELOAD(k_ent_scatter); RG_PRELOAD(k_ent_scatter_own); RG_PRELOAD(k_ent2_hist); RG_PRELOAD(k_ent2_scatter); RG_PRELOAD(k_build_sub); RG_PRELOAD((k_build_sub3<true, true>)); RG_PRELOAD((k_build_sub3<true, false>)); RG_PRELOAD((k_build_sub3<false, true>)); RG_PRELOAD((k_build_sub3<false, false>));
         RG_PRELOAD(k_scan_reduce); RG_PRELOAD(k_scan_apply); RG_PRELOAD(k_fill_f32);
         RG_PRELOAD(k_part_hist); RG_PRELOAD(k_part_offsets); RG_PRELOAD(k_part_scatter<false>); RG_PRELOAD(k_part_scatter<true>); RG_PRELOAD(k_own_list); RG_PRELOAD((k_bucket_probe<false, false>)); RG_PRELOAD((k_bucket_probe<true, false>)); RG_PRELOAD((k_bucket_probe<false, true>)); RG_PRELOAD((k_bucket_probe<true, true>));
         RG_PRELOAD(k_comm_signal); RG_PRELOAD(k_comm_wait); RG_PRELOAD(k_comm_pairs);

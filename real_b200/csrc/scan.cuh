@@ -403,9 +403,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_hist(ScanParams P)
 #ifndef REAL_PS_PPT
 #define REAL_PS_PPT 8
 #endif
+#ifndef REAL_PS_THREADS
+#define REAL_PS_THREADS 256
+#endif
+static const int PS_THREADS = REAL_PS_THREADS;                // threads per CTA (256 or 512); the first 256 also act for one bucket each
 static const int PS_PPT = REAL_PS_PPT;                        // positions per thread (4, 8, 16 or 32)
 static const int PS_TPW = 32 / PS_PPT;                            // threads per text word
-static const int PS_TILE_POS = SC_THREADS * PS_PPT;           // 4096
+static const int PS_TILE_POS = PS_THREADS * PS_PPT;           // 2048 (4096 with 512 threads)
 static const int PS_TILE_WORDS = PS_TILE_POS / 32;            // 128
 static const int PS_SMEM_WORDS = PS_TILE_WORDS + 2 * SC_HALO; // 132 words = 1056 bytes
 
@@ -414,7 +418,7 @@ struct ScatterSmem
         uint4 stage[PS_TILE_POS];                          // record, position field relative to the tile
         uint64_t tile[2][PS_SMEM_WORDS];
         uint64_t bar[2];
-        uint32_t wcnt[SC_THREADS / 32][SC_MAX_BUCKETS];    // per-warp counts, then running slots
+        uint32_t wcnt[PS_THREADS / 32][SC_MAX_BUCKETS];    // per-warp counts, then running slots
         uint32_t loc[SC_MAX_BUCKETS + 1];                  // first staging slot of a bucket
         uint4 * dst[SC_MAX_BUCKETS];                       // per tile: record area of the bucket's owner + first record of the tile's run - first staging slot
         uint4 * area[SC_MAX_BUCKETS];                      // record area of the bucket's owner
@@ -422,7 +426,7 @@ struct ScatterSmem
 
 // LIST: the positions come from the kept-position list of a bucket shard (k_own_list) instead of the text tiles
 template<bool LIST>
-__global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
+__global__ void __launch_bounds__(PS_THREADS, 1024 / PS_THREADS) k_part_scatter(ScanParams P)
 {
         extern __shared__ __align__(128) unsigned char sc_smem[];
         ScatterSmem & S = *reinterpret_cast<ScatterSmem *>(sc_smem);
@@ -443,9 +447,13 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
                 mbar_init(&S.bar[1], 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        #pragma unroll
-        for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
-        S.area[threadIdx.x] = P.peer_recs[bucket_owner(P, threadIdx.x)];
+        bool const bt = threadIdx.x < (uint32_t)SC_MAX_BUCKETS;       // this thread also acts for bucket threadIdx.x
+        if ( bt )
+        {
+                #pragma unroll
+                for ( int w = 0; w < PS_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+                S.area[threadIdx.x] = P.peer_recs[bucket_owner(P, threadIdx.x)];
+        }
         __syncthreads();
 
         uint64_t tile_id = first_tile + blockIdx.x;
@@ -524,11 +532,14 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
                 uint32_t bstart = 0, reserved = 0;       // basev = bstart + reserved, summed only where it is needed (see below)
                 {
                         uint32_t tot = 0;
-                        #pragma unroll
-                        for ( int w = 0; w < SC_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                        if ( bt )
+                        {
+                                #pragma unroll
+                                for ( int w = 0; w < PS_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
+                        }
                         uint32_t blocktot;
                         uint32_t const ex = block_excl_scan(tot, &blocktot);
-                        S.loc[threadIdx.x] = ex;
+                        if ( bt ) S.loc[threadIdx.x] = ex;
                         if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
                         // the run's first record is needed at the copy-out only: the global atomic that reserves it stays in
                         // flight while the tile is ranked -- its result must not be touched before (an addition right here
@@ -539,12 +550,15 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
                                 reserved = atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot);
                         }
                         uint32_t run = ex;
-                        #pragma unroll
-                        for ( int w = 0; w < SC_THREADS / 32; ++w )
+                        if ( bt )
                         {
-                                uint32_t const c = S.wcnt[w][threadIdx.x];
-                                S.wcnt[w][threadIdx.x] = run;
-                                run += c;
+                                #pragma unroll
+                                for ( int w = 0; w < PS_THREADS / 32; ++w )
+                                {
+                                        uint32_t const c = S.wcnt[w][threadIdx.x];
+                                        S.wcnt[w][threadIdx.x] = run;
+                                        run += c;
+                                }
                         }
                 }
                 __syncthreads();
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
                         }
                 }
                 // where staging slot 0 would go if it belonged to this bucket: the copy-out adds the slot number
-                S.dst[threadIdx.x] = S.area[threadIdx.x] + ((int64_t)(bstart + reserved) - (int64_t)S.loc[threadIdx.x]);
+                if ( bt ) S.dst[threadIdx.x] = S.area[threadIdx.x] + ((int64_t)(bstart + reserved) - (int64_t)S.loc[threadIdx.x]);
                 __syncthreads();
                 // (4) copy out: consecutive threads write consecutive records of a bucket run; four records in flight per thread.
                 // The bucket of a record is recomputed from its window (three ALU instructions) instead of being staged beside it:
@@ -587,25 +601,28 @@ __global__ void __launch_bounds__(SC_THREADS, 4) k_part_scatter(ScanParams P)
                 {
                         uint32_t const n = S.loc[SC_MAX_BUCKETS];
                         uint32_t i = threadIdx.x;
-                        for ( ; i + 3 * SC_THREADS < n; i += 4 * SC_THREADS )
+                        for ( ; i + 3 * PS_THREADS < n; i += 4 * PS_THREADS )
                         {
                                 uint4 r[4]; uint4 * d[4];
                                 #pragma unroll
-                                for ( int u = 0; u < 4; ++u ) r[u] = S.stage[i + u * SC_THREADS];
+                                for ( int u = 0; u < 4; ++u ) r[u] = S.stage[i + u * PS_THREADS];
                                 #pragma unroll
                                 for ( int u = 0; u < 4; ++u ) d[u] = S.dst[(uint32_t)(((((uint64_t)r[u].y << 32) | r[u].x) << fsh) >> bsh) & bmask];
                                 #pragma unroll
-                                for ( int u = 0; u < 4; ++u ) d[u][i + u * SC_THREADS] = r[u];
+                                for ( int u = 0; u < 4; ++u ) d[u][i + u * PS_THREADS] = r[u];
                         }
-                        for ( ; i < n; i += SC_THREADS )
+                        for ( ; i < n; i += PS_THREADS )
                         {
                                 uint4 const r = S.stage[i];
                                 S.dst[(uint32_t)(((((uint64_t)r.y << 32) | r.x) << fsh) >> bsh) & bmask][i] = r;
                         }
                 }
                 __syncthreads();
-                #pragma unroll
-                for ( int w = 0; w < SC_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+                if ( bt )
+                {
+                        #pragma unroll
+                        for ( int w = 0; w < PS_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+                }
                 __syncthreads();   // tile[buf], staging and the counters are free again
         }
 }
@@ -651,17 +668,26 @@ __global__ void __launch_bounds__(OL_THREADS) k_own_list(ScanParams P)
                 __syncthreads();
                 if ( ! total ) continue;
                 uint32_t * out = P.list + tile_base + ex;
-                #pragma unroll
-                for ( int k = 0; k < OL_WPT; ++k )
+                // one loop over the kept positions of all OL_WPT words of the thread: a loop per word leaves the lanes of a warp
+                // waiting for the one with most kept positions in THAT word, four times over (13 of 32 lanes active, r02 capture)
                 {
-                        uint64_t e = eq[k];
-                        uint32_t const p0 = (uint32_t)((w0i + k) * 32 - P.pos_base);
-                        while ( e )
+                        static_assert(OL_WPT == 4, "the word selects below are written out for four words");
+                        uint32_t k = 0;
+                        uint64_t e = eq[0], wa = w[0], wb = w[1];
+                        while ( true )
                         {
+                                while ( ! e && k < OL_WPT - 1 )
+                                {
+                                        ++k;
+                                        e = (k == 1) ? eq[1] : ((k == 2) ? eq[2] : eq[3]);
+                                        wa = wb;
+                                        wb = (k == 1) ? w[2] : ((k == 2) ? w[3] : w[4]);
+                                }
+                                if ( ! e ) break;
                                 uint32_t const j = (uint32_t)__clzll(e) >> 1;
                                 e &= ~(0x8000000000000000ULL >> (2 * j));
-                                uint64_t const v = j ? ((w[k] << (2*j)) | (w[k+1] >> (64 - 2*j))) : w[k];
-                                *out++ = p0 + j;
+                                uint64_t const v = j ? ((wa << (2*j)) | (wb >> (64 - 2*j))) : wa;
+                                *out++ = (uint32_t)((w0i + k) * 32 - P.pos_base) + j;
                                 atomicAdd(&cnt[(uint32_t)(v >> 56)], 1u);
                         }
                 }
