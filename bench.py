@@ -563,7 +563,7 @@ def main():
                 st["fold_ms"] = h.stats()["fold_ms"]
             t4 = time.perf_counter()
         else:
-            nhits_holder[0] = h.match_all_count()
+            nhits_holder[0] = h.match_all_count(packed=True)          # rows read back as real_gpu_hit16
             t3 = t4 = time.perf_counter()
             st = h.stats()
         st["exchange_ms"] = (t4 - t3) * 1e3
@@ -739,10 +739,10 @@ def main():
                 st["d2h_ms"] = h.stats()["d2h_ms"]
                 d2h[0] = (r_hi - r_lo) * 8
             else:
-                nh = h.match_all_count()          # records land in the library's pinned host buffer
+                nh = h.match_all_count(packed=True)          # 16-byte rows land in the library's pinned host buffer
                 t4 = t3 = time.perf_counter()
                 st = h.stats()
-                d2h[0] = nh * 40
+                d2h[0] = nh * 16
             t5 = time.perf_counter()
             st.update(api_set_reads_ms=(t1 - t0) * 1e3, api_set_text_ms=(t2 - t1) * 1e3, api_match_ms=(t3 - t2) * 1e3,
                       api_exchange_ms=(t4 - t3) * 1e3, api_get_ms=(t5 - t4) * 1e3)

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) k_sort_large(SortLargeParams P)
 // one thread per read: insertion sort of its (short) segment, then expansion to the ABI record
 template<typename HitOut>
 __global__ void __launch_bounds__(128) k_hit_order(RawHit * __restrict__ seg, const uint32_t * __restrict__ starts, const uint32_t * __restrict__ counts,
-                                                 uint64_t nreads, uint32_t fileid, HitOut * __restrict__ out)
+                                                 uint64_t nreads, uint32_t fileid, HitOut * __restrict__ out, real_gpu_hit16 * __restrict__ out16)
 {
         uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if ( r >= nreads ) return;
@@ -256,8 +256,16 @@ __global__ void __launch_bounds__(128) k_hit_order(RawHit * __restrict__ seg, co
         RawHit * s = seg + starts[r];
         if ( n <= SEG_SMALL ) seg_insertion_sort(s, n, LessHit());          // longer segments: k_sort_large<0> has run
         HitOut * o = out + starts[r];
+        real_gpu_hit16 * o16 = out16 ? out16 + starts[r] : nullptr;
         for ( uint32_t i = 0; i < n; ++i )
         {
+                if ( o16 )
+                {
+                        // the compact row: position, error count, strand and record in one word (the layout of RawHit::pm)
+                        real_gpu_hit16 C;
+                        C.pos_k_inv_frag = s[i].pm; C.patid = (uint32_t)r; C.score = s[i].score;
+                        o16[i] = C;
+                }
                 HitOut H;
                 H.patid = r;
                 H.pos = rawhit_pos(s[i].pm);

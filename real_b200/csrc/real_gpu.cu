@@ -90,7 +90,7 @@ struct real_gpu
         uint32_t * table_counts;       // [6] pinned host memory; per table: entries, distinct slots (copied back asynchronously by the build)
         const uint8_t * src_packed; const uint64_t * src_byte_offsets; uint32_t src_packed_uniform;   // 2-bit input (set_reads_packed)
         const uint8_t * src_mapped;    // device pointer the reads are packed from (caller's buffer or h->mapped)
-        DevBuf ll, hits_raw, hits_seg, hits_out, counters, counts, starts, cursor, scantmp, info, scores;
+        DevBuf ll, hits_raw, hits_seg, hits_out, hits_out16, counters, counts, starts, cursor, scantmp, info, scores;
         uint64_t hit_cap;
         real_gpu_hit * host_hits;
         uint64_t host_hits_cap;
@@ -1203,7 +1203,7 @@ int real_gpu_destroy(real_gpu * h)
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
-                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
+                           &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->hits_out16, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
                            &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
@@ -1542,42 +1542,66 @@ static void sort_large_segments(real_gpu * h, int mode, const uint64_t * bounds,
         RG_KERNEL_CHECK(); launch_count(h);
 }
 
-int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhits)
+} // extern "C"
+
+namespace
 {
-        RG_API_BEGIN(h)
-        if ( ! hits || ! nhits ) return fail(h, REAL_GPU_E_ARG, "match_all: null pointer");
+// the body of real_gpu_match_all / real_gpu_match_all_packed: rows of 40 bytes (ABI struct) or of 16 bytes to the host
+int match_all_common(real_gpu * h, bool packed, const void ** rows, uint64_t * nhits)
+{
         int const rc = check_ready(h);
         if ( rc ) return rc;
-        *hits = nullptr; *nhits = 0;
+        *rows = nullptr; *nhits = 0;
         h->stats.scan_launches = 0;
         uint64_t const found = collect_hits_by_read(h);
+        size_t const rowbytes = packed ? sizeof(real_gpu_hit16) : sizeof(real_gpu_hit);
         if ( found )
         {
                 dev_reserve(h, h->hits_out, found * sizeof(real_gpu_hit));
+                if ( packed ) dev_reserve(h, h->hits_out16, found * sizeof(real_gpu_hit16));
                 sort_large_segments(h, 0, nullptr, 1);
                 k_hit_order<real_gpu_hit><<<blocks_for(h->nreads, 128), 128, 0, h->st>>>(ptr<RawHit>(h->hits_seg), ptr<uint32_t>(h->starts), ptr<uint32_t>(h->counts),
-                                                                                        h->nreads, h->fileid, ptr<real_gpu_hit>(h->hits_out));
+                                                                                        h->nreads, h->fileid, ptr<real_gpu_hit>(h->hits_out),
+                                                                                        packed ? ptr<real_gpu_hit16>(h->hits_out16) : nullptr);
                 RG_KERNEL_CHECK(); launch_count(h);
         }
         RG_CUDA(cudaEventRecord(h->ev[1], h->st));
-        if ( found > h->host_hits_cap )
+        if ( found * rowbytes > h->host_hits_cap * sizeof(real_gpu_hit) )
         {
                 if ( h->host_hits ) cudaFreeHost(h->host_hits);
                 h->host_hits = nullptr; h->host_hits_cap = 0;
-                uint64_t const cap = found + found / 4 + 1024;
+                uint64_t const cap = found * rowbytes / sizeof(real_gpu_hit) + found / 4 + 1024;
                 RG_CUDA(cudaMallocHost(&h->host_hits, cap * sizeof(real_gpu_hit)));
                 h->host_hits_cap = cap;
         }
         if ( found )
-                RG_CUDA(cudaMemcpyAsync(h->host_hits, h->hits_out.p, found * sizeof(real_gpu_hit), cudaMemcpyDeviceToHost, h->st));
+                RG_CUDA(cudaMemcpyAsync(h->host_hits, packed ? h->hits_out16.p : h->hits_out.p, found * rowbytes, cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaEventRecord(h->ev[2], h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.post_ms = elapsed(h->ev[0], h->ev[1]);
         h->stats.d2h_ms = elapsed(h->ev[1], h->ev[2]);
-        *hits = h->host_hits;
+        *rows = h->host_hits;
         *nhits = found;
         h->fmt.nrows_all = found;
         return REAL_GPU_OK;
+}
+} // namespace
+
+extern "C" {
+
+int real_gpu_match_all(real_gpu * h, const real_gpu_hit ** hits, uint64_t * nhits)
+{
+        RG_API_BEGIN(h)
+        if ( ! hits || ! nhits ) return fail(h, REAL_GPU_E_ARG, "match_all: null pointer");
+        return match_all_common(h, false, reinterpret_cast<const void **>(hits), nhits);
+        RG_API_END(h)
+}
+
+int real_gpu_match_all_packed(real_gpu * h, const real_gpu_hit16 ** rows, uint64_t * nhits)
+{
+        RG_API_BEGIN(h)
+        if ( ! rows || ! nhits ) return fail(h, REAL_GPU_E_ARG, "match_all_packed: null pointer");
+        return match_all_common(h, true, reinterpret_cast<const void **>(rows), nhits);
         RG_API_END(h)
 }
 

@@ -42,6 +42,7 @@ class Stats(C.Structure):
 
 HIT_DTYPE = np.dtype([("patid", "<u8"), ("pos", "<u8"), ("file", "<u4"), ("frag", "<u4"),
                       ("k", "<u4"), ("inverted", "<u4"), ("score", "<f4"), ("reserved", "<u4")])
+HIT16_DTYPE = np.dtype([("pos_k_inv_frag", "<u8"), ("patid", "<u4"), ("score", "<f4")])
 GAP_DTYPE = np.dtype([("patid", "<u4"), ("mingap", "<u4"), ("where", "<u4"), ("start", "<u4"),
                       ("gap_pos", "<u4"), ("present", "<u4")])
 
@@ -94,6 +95,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_set_reads_device.argtypes = [vp, vp, vp, vp, u64, u64, u32]
     L.real_gpu_set_reads_packed.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64]
     L.real_gpu_match_all.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.real_gpu_match_all_packed.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.real_gpu_match_unique.argtypes = [vp]
     L.real_gpu_get_unique.argtypes = [vp, vp, vp]
     L.real_gpu_get_unique_range.argtypes = [vp, u64, u64, vp, vp]
@@ -271,12 +273,26 @@ class Handle:
         buf = (C.c_char * (n.value * HIT_DTYPE.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=HIT_DTYPE).copy()
 
-    def match_all_count(self) -> int:
-        """match_all without copying the records out of the library's pinned buffer."""
+    def match_all_count(self, packed: bool = False) -> int:
+        """match_all without copying the records out of the library's pinned buffer (packed: 16-byte rows)."""
         p = C.c_void_p()
         n = C.c_uint64()
-        self._check(self.L.real_gpu_match_all(self.h, C.byref(p), C.byref(n)))
+        self._check((self.L.real_gpu_match_all_packed if packed else self.L.real_gpu_match_all)(self.h, C.byref(p), C.byref(n)))
         return int(n.value)
+
+    def match_all_packed(self) -> np.ndarray:
+        """The rows of match_all as real_gpu_hit16, expanded to the fields of HIT_DTYPE."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.L.real_gpu_match_all_packed(self.h, C.byref(p), C.byref(n)))
+        out = np.zeros(n.value, dtype=HIT_DTYPE)
+        if n.value:
+            buf = (C.c_char * (n.value * HIT16_DTYPE.itemsize)).from_address(p.value)
+            r = np.frombuffer(buf, dtype=HIT16_DTYPE)
+            w = r["pos_k_inv_frag"]
+            out["patid"] = r["patid"]; out["pos"] = w & np.uint64((1 << 35) - 1); out["k"] = (w >> np.uint64(35)) & np.uint64(15)
+            out["inverted"] = (w >> np.uint64(39)) & np.uint64(1); out["frag"] = (w >> np.uint64(40)) & np.uint64(0xFFFFFF); out["score"] = r["score"]
+        return out
 
     def match_unique(self):
         self._check(self.L.real_gpu_match_unique(self.h))

@@ -53,6 +53,11 @@ def test_format_all_lines(scores):
         h.set_text(words, nmask, text.n, text.record_starts)
         rows = h.match_all()
         assert len(rows) > 4000
+        # the compact rows are the same rows
+        rows16 = h.match_all_packed()
+        for f in ("patid", "pos", "frag", "k", "inverted"):
+            assert np.array_equal(rows16[f], rows[f]), f
+        assert np.array_equal(rows16["score"].view(np.uint32), rows["score"].view(np.uint32))
         h.set_read_ids(ids)
         h.set_record_names(names, text.record_starts[:-1])
         want = [_line(ids[int(x["patid"])], _bases(reads, int(x["patid"]), bool(x["inverted"])), x["score"] if scores else None, 75, bool(x["inverted"]),
