@@ -379,6 +379,7 @@ struct EntryPartSmem
         uint32_t wcnt[8][EP_MAX_BUCKETS];
         uint32_t loc[EP_MAX_BUCKETS + 1];
         uint32_t base[EP_MAX_BUCKETS];
+        uint32_t wsum[8];
         uint8_t stage_b[EP_TILE_ENTRIES];
 };
 
@@ -394,7 +395,7 @@ __device__ __forceinline__ uint2 ep_layout(EntryPartSmem & S, const uint32_t * _
         #pragma unroll
         for ( int w = 0; w < 8; ++w ) tot += S.wcnt[w][threadIdx.x];
         uint32_t blocktot;
-        uint32_t const ex = block_excl_scan(tot, &blocktot);
+        uint32_t const ex = block_excl_scan256(tot, &blocktot, S.wsum);        // (one barrier; every tile has more behind it)
         S.loc[threadIdx.x] = ex;
         if ( threadIdx.x == EP_MAX_BUCKETS - 1 ) S.loc[EP_MAX_BUCKETS] = blocktot;
         uint2 basev = make_uint2(0u, 0u);

@@ -95,6 +95,26 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t * total
         return base + incl - v;
 }
 
+// The same for a block of 256 threads with ONE barrier: scratch = eight words of the caller's shared memory that no thread
+// writes again before every thread has passed another block barrier (the staged partition kernels have several per tile).
+__device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t * total, uint32_t * scratch)
+{
+        int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        uint32_t const incl = warp_incl_scan(v, lane);
+        if ( lane == 31 ) scratch[wid] = incl;
+        __syncthreads();
+        uint32_t base = 0, all = 0;
+        #pragma unroll
+        for ( int w = 0; w < 8; ++w )
+        {
+                uint32_t const x = scratch[w];
+                if ( w < wid ) base += x;
+                all += x;
+        }
+        *total = all;
+        return base + incl - v;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t * __restrict__ in, uint32_t * __restrict__ sums, uint64_t n)
 {
         uint64_t const base = (uint64_t)blockIdx.x * SCAN_TILE;

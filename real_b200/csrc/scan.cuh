@@ -420,6 +420,7 @@ struct ScatterSmem
         uint64_t bar[2];
         uint32_t wcnt[PS_THREADS / 32][SC_MAX_BUCKETS];    // per-warp counts, then running slots
         uint32_t loc[SC_MAX_BUCKETS + 1];                  // first staging slot of a bucket
+        uint32_t wsum[SC_MAX_BUCKETS / 32];                // bucket totals per warp of bucket threads (exclusive scan)
         uint4 * dst[SC_MAX_BUCKETS];                       // per tile: record area of the bucket's owner + first record of the tile's run - first staging slot
         uint4 * area[SC_MAX_BUCKETS];                      // record area of the bucket's owner
 };
@@ -528,7 +529,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1024 / PS_THREADS) k_part_scatter(
                         if ( (m >> u) & 1 )
                                 atomicAdd(&S.wcnt[wid][(uint32_t)(wv[u] >> bsh) & bmask], 1u);
                 __syncthreads();
-                // (2) bucket b (thread b): totals -> staging layout, global run reservation, per-warp running slots
+                // (2) bucket b (thread b): totals -> staging layout, global run reservation, per-warp running slots.  The exclusive
+                // scan over the 256 bucket totals is a warp scan + one barrier (the generic block scan has three, and the block
+                // barriers are a fifth of this kernel's stall samples)
                 uint32_t bstart = 0, reserved = 0;       // basev = bstart + reserved, summed only where it is needed (see below)
                 {
                         uint32_t tot = 0;
@@ -537,10 +540,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1024 / PS_THREADS) k_part_scatter(
                                 #pragma unroll
                                 for ( int w = 0; w < PS_THREADS / 32; ++w ) tot += S.wcnt[w][threadIdx.x];
                         }
-                        uint32_t blocktot;
-                        uint32_t const ex = block_excl_scan(tot, &blocktot);
-                        if ( bt ) S.loc[threadIdx.x] = ex;
-                        if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = blocktot;
+                        uint32_t const incl = warp_incl_scan(tot, lane);
+                        if ( bt && lane == 31 ) S.wsum[wid] = incl;
                         // the run's first record is needed at the copy-out only: the global atomic that reserves it stays in
                         // flight while the tile is ranked -- its result must not be touched before (an addition right here
                         // made every thread wait for the round trip: 12 % of the kernel's stall samples)
@@ -549,9 +550,17 @@ __global__ void __launch_bounds__(PS_THREADS, 1024 / PS_THREADS) k_part_scatter(
                                 bstart = P.bucket_start[threadIdx.x];
                                 reserved = atomicAdd(P.bucket_cursor + threadIdx.x * SC_CURSOR_STRIDE, tot);
                         }
-                        uint32_t run = ex;
+                        __syncthreads();
                         if ( bt )
                         {
+                                uint32_t base = 0;
+                                #pragma unroll
+                                for ( int w = 0; w < SC_MAX_BUCKETS / 32 - 1; ++w )
+                                        if ( w < wid ) base += S.wsum[w];
+                                uint32_t const ex = base + incl - tot;
+                                S.loc[threadIdx.x] = ex;
+                                if ( threadIdx.x == SC_MAX_BUCKETS - 1 ) S.loc[SC_MAX_BUCKETS] = ex + tot;
+                                uint32_t run = ex;
                                 #pragma unroll
                                 for ( int w = 0; w < PS_THREADS / 32; ++w )
                                 {
@@ -595,6 +604,13 @@ __global__ void __launch_bounds__(PS_THREADS, 1024 / PS_THREADS) k_part_scatter(
                 // where staging slot 0 would go if it belonged to this bucket: the copy-out adds the slot number
                 if ( bt ) S.dst[threadIdx.x] = S.area[threadIdx.x] + ((int64_t)(bstart + reserved) - (int64_t)S.loc[threadIdx.x]);
                 __syncthreads();
+                // the per-warp counters are free from here on (the copy-out does not read them): cleared for the next tile now,
+                // under the barrier that ends the copy-out
+                if ( bt )
+                {
+                        #pragma unroll
+                        for ( int w = 0; w < PS_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
+                }
                 // (4) copy out: consecutive threads write consecutive records of a bucket run; four records in flight per thread.
                 // The bucket of a record is recomputed from its window (three ALU instructions) instead of being staged beside it:
                 // the kernel is limited by its shared-memory instructions, not by arithmetic
@@ -616,12 +632,6 @@ __global__ void __launch_bounds__(PS_THREADS, 1024 / PS_THREADS) k_part_scatter(
                                 uint4 const r = S.stage[i];
                                 S.dst[(uint32_t)(((((uint64_t)r.y << 32) | r.x) << fsh) >> bsh) & bmask][i] = r;
                         }
-                }
-                __syncthreads();
-                if ( bt )
-                {
-                        #pragma unroll
-                        for ( int w = 0; w < PS_THREADS / 32; ++w ) S.wcnt[w][threadIdx.x] = 0;
                 }
                 __syncthreads();   // tile[buf], staging and the counters are free again
         }
