@@ -1388,7 +1388,9 @@ int doMatchingAll(RealOptions const & opts)
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
         {
                 TextFile T;
-                if ( ! setTextTeam(team, opts, (uint32_t)fi, filenames[fi], T, false) )
+                // (file slot 0 for every file: the rows of matchAll are printed file by file and their file field is not part of a
+                // line, so the 64-file limit of the UniqueMatchInfo word does not apply here -- the reference has none either)
+                if ( ! setTextTeam(team, opts, 0, filenames[fi], T, false) )
                 {
                         std::cerr << "file " << filenames[fi] << " is too short for seed length " << opts.seedl << std::endl;
                         continue;
@@ -1416,7 +1418,7 @@ int doMatchingAll(RealOptions const & opts)
                 {
                         // the lines are formatted on the device, batch by batch, and written while the next batch is formatted
                         Gpu & G = team.g[0];
-                        setRecordNames(G, (uint32_t)fi, T.ranges);
+                        setRecordNames(G, 0, T.ranges);
                         uint64_t const per = 1u << 18;
                         uint64_t at = 0;
                         writeBatches(out, [&G, &at, nhits, per](char const ** bytes, uint64_t * nbytes) -> bool
@@ -1442,26 +1444,38 @@ int doMatchingAll(RealOptions const & opts)
 }
 
 // The reference's memory planner (matchUniqueImplementation.cpp:1208-1244): how many seed windows one text-side
-// index block holds.  Only the order-dependent folds (scores, gaps) depend on it.  The byte counts of the
-// reference's text and rank structures are restated approximately; REAL_NLIST pins the value.
-static uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, uint64_t nreads)
+// index block holds.  Only the order-dependent folds (scores, gaps) depend on it.  The byte counts are the reference's own,
+// including their defect: AutoArray::size() returns unsigned int (AutoArray.hpp:33-36), so the size of every array is taken
+// modulo 2^32 -- and the text's two arrays are even added in 32 bits (AutoTextArray.hpp:93-96) -- which on a genome makes
+// the planner believe it has more room than it has.  REAL_NLIST pins the value.
+namespace
+{
+        inline uint64_t aaSize(uint64_t n, uint64_t elt) { return (uint32_t)(sizeof(size_t) + sizeof(void *) + n * elt); }        // AutoArray<N>::size()
+        inline uint64_t rankSize(uint64_t nbits)                                                                              // ERank222B::size(), ERank222B.hpp:548-555
+        { return sizeof(void *) + 3 * sizeof(uint64_t) + aaSize((nbits + 65535) / 65536, 8) + aaSize((nbits + 63) / 64, 2); }
+}
+uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, uint64_t nreads)
 {
         if ( char const * e = getenv("REAL_NLIST") ) return strtoull(e, 0, 10);
-        long const pages = sysconf(_SC_PHYS_PAGES), pagesize = sysconf(_SC_PAGE_SIZE);
-        uint64_t const usemem = (uint64_t)((double)pages * (double)pagesize * opts.fracmem);
-        uint64_t const bits = ((T.n + 63) / 64) * 64;
-        uint64_t const rank = (bits / 65536 + 1) * 8 + (bits / 64) * 2;
-        uint64_t const textmemory = T.n / 4 + bits / 8 + rank + 16;
-        uint64_t const rangevectormemory = bits / 8 + rank + 8;
-        uint64_t const lookupmemory = 2ULL * 6 * (1ULL << 22) * sizeof(size_t);
-        uint64_t const uniqueinfomemory = nreads * (opts.scores ? 16 : 8);
+        long const pages = sysconf(_SC_PHYS_PAGES), pagesize = sysconf(_SC_PAGE_SIZE);           // = MemTotal of /proc/meminfo (getPhysicalMemory.cpp)
+        uint64_t const usemem = (uint64_t)((double)((uint64_t)pages * (uint64_t)pagesize) * opts.fracmem);     // RealOptions.cpp:414-415
+        uint64_t const n = T.n;
+        uint64_t const textwords = ((2 * n + 63) / 64), wildwords = (n + 63) / 64;                                  // AutoTextArray.hpp:27-61
+        uint64_t const textmemory = (uint64_t)(uint32_t)((uint32_t)aaSize(textwords, 8) + (uint32_t)aaSize(wildwords, 8)) + 2 * sizeof(void *) + rankSize(wildwords * 64);
+        uint64_t const rvwords = (n + 1 + 63) / 64;                                                                // RangeVector.hpp:18-21,27,49
+        uint64_t const rangevectormemory = aaSize(rvwords, 8) + sizeof(void *) + rankSize(rvwords * 64);
+        uint64_t const lookupmemory = 2ULL * 6 * (1ULL << 22) * sizeof(size_t);                                    // 2 * getNumLists() * getHistSize() * sizeof(size_t)
+        uint64_t const uniqueinfomemory = aaSize(nreads, opts.scores ? 16 : 8);                                    // AutoArray< UniqueMatchInfo<scores> >(numpat).size()
         uint64_t const nonlist = textmemory + rangevectormemory + lookupmemory + uniqueinfomemory;
         if ( nonlist > usemem )
-                throw std::runtime_error("Insufficient memory.");
-        uint64_t const elementmemory = opts.seedl <= 32 ? 72 : 112;
+        {
+                std::cerr << "Insufficient memory." << std::endl;
+                throw std::bad_alloc();
+        }
+        uint64_t const elementmemory = opts.seedl <= 32 ? 72 : 112;       // 3 BaseMask + (3 + getRadixSortTemp()) Mask: 3*8 + 4*12 (u32 signatures), 3*16 + 4*16 (u64)
         uint64_t const n_list_max = (usemem - nonlist) / elementmemory;
         if ( ! n_list_max )
-                throw std::runtime_error("Insufficient memory.");
+                throw std::bad_alloc();
         uint64_t const expblocks = (T.n - opts.seedl + 1 + (n_list_max - 1)) / n_list_max;
         std::cerr << "Expected number of blocks = " << expblocks << std::endl;
         uint64_t const n_list = (T.n + (expblocks - 1)) / expblocks;

@@ -118,6 +118,9 @@ void reorderLikeRewrite(ReadSet & reads);
 // count modulo 2^32 and cannot read such a file back): it is written as count 0xFFFFFFFF followed by a u64be count.
 // `reads` must be in rewritten order (reorderLikeRewrite).
 void writeRewritten(ReadSet const & reads, bool fastq, std::vector<char> & out);
+// the reference's memory planner (matchUniqueImplementation.cpp:1208-1244): seed windows per text-side index block
+struct TextFile;
+uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, uint64_t nreads);
 bool looksRewritten(FileBytes const & buf);
 // fills `reads` (in rewritten order) from the bytes of a rewritten file; fastq = whether its records carry qualities
 void readRewritten(FileBytes const & buf, ReadSet & reads, bool & fastq);

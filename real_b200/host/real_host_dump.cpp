@@ -86,6 +86,14 @@ int main(int argc, char * argv[])
                         for ( size_t i = 0; i < R.quality.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)R.quality[i]);
                         printf("]}\n");
                 }
+                else if ( mode == "plan" )
+                {
+                        // <text bases> <reads> -- <REAL options>: the n_list the memory planner chooses (its messages go to stderr)
+                        TextFile T; T.n = strtoull(argv[2], 0, 10);
+                        uint64_t const nreads = strtoull(argv[3], 0, 10);
+                        RealOptions o(argc - 3, argv + 3);
+                        printf("{\"n_list\":%llu}\n", (unsigned long long)planBlockWindows(o, T, nreads));
+                }
                 else if ( mode == "ll" )
                 {
                         double ll[1024];

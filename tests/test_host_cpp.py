@@ -207,3 +207,26 @@ def test_fasta_writer_roundtrip():
     s, names, st = O.fasta_text(f.getvalue())
     assert np.array_equal(s, t.symbols) and np.array_equal(st, t.record_starts)
     assert [x.decode() for x in names] == [a for a, _ in t.records]
+
+
+@pytest.mark.parametrize("n,nreads,frac,scores", [(3_000_000, 2000, 0.0062, 1), (3_000_000, 2000, 0.0063, 0), (1_234_567, 777, 0.0068, 1), (1_234_567, 777, 0.75, 0)])
+def test_memory_planner_equals_stock_binary(dump, tmp_path, n, nreads, frac, scores):
+    """The text-block size (n_list) decides the visiting order of the order-dependent folds: the host driver's planner against
+    the 'Using n_list' line of the stock binary on texts that need several blocks (small -f).  Needs oracle/_ref/real (built
+    where /root/reference exists); the figure depends on the machine's MemTotal, so it is compared live."""
+    stock = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "real")
+    if not os.path.exists(stock):
+        pytest.skip("stock binary not built")
+    text = synth.make_text(5, n, nrecords=3, n_per_million=500)
+    reads = synth.make_reads(text, 6, nreads, 50, 0.01, fastq=True)
+    synth.write_fasta(str(tmp_path / "t.fa"), text)
+    synth.write_reads(str(tmp_path / "r.fq"), reads, True)
+    args = ["-t", str(tmp_path / "t.fa"), "-p", str(tmp_path / "r.fq"), "-o", str(tmp_path / "o.txt"), "-u", "1", "-q", str(scores), "-Q", "33", "-R", "0", "-f", str(frac)]
+    p = subprocess.run([stock] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    want = [l for l in p.stderr.splitlines() if l.startswith("Using n_list")]
+    assert want, p.stderr[-500:]
+    q = dump("plan", text.n, nreads, *args, ok=False)
+    assert q.returncode == 0, q.stderr[-500:]
+    got = [l for l in q.stderr.splitlines() if l.startswith("Using n_list")]
+    assert got == want[:1]
+    assert json.loads(q.stdout)["n_list"] == int(want[0].split("=")[1])
