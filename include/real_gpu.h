@@ -201,6 +201,20 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
  *   quality        one byte per BASE, reads back to back (as in real_gpu_set_reads), or NULL */
 int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64_t * byte_offsets, const uint32_t * lengths,
                               uint32_t uniform_length, const uint8_t * wildcard_flags, const uint8_t * quality, uint64_t nreads);
+/* Read set straight from the BYTES of a FASTA pattern file: the library runs the reference's pattern reader on the device (K0
+ * in pattern-file mode, csrc/ingest.cuh) -- FastAReader::getNextPatternUnlocked (FastAReader.hpp:107-138: everything in front of
+ * the first '>' is skipped; a '>' opens an id line that runs to the next '\n'; behind it every byte that is not white space is a
+ * base of the read, up to the next '>' or the end of the file; an id line the file ends in without a '\n' opens no read) and
+ * Pattern::computeMapped (Pattern.hpp:105-128: A C G T, anything else is a wildcard) -- and sets the result as the current read
+ * set, 2 bit/base, as real_gpu_set_reads_packed would.  rewrite_order != 0 numbers the reads in the order of the reference's
+ * rewritten pattern file (-R 1: by length, reads without wildcards first, file order inside a group; ReorderFastA.hpp) instead
+ * of file order.  The ids (the bytes between '>' and '\n') are kept on the device for real_gpu_format_*; real_gpu_get_read_ids
+ * and real_gpu_get_read_table copy ids, lengths and wildcard flags out, real_gpu_get_reads_packed the packed bytes.
+ * *nreads = reads found.  Limits as for real_gpu_set_reads, and 2^32 bytes of packed reads / of ids per call. */
+int real_gpu_set_reads_fasta(real_gpu * h, const void * fasta_bytes, uint64_t nbytes, uint32_t rewrite_order, uint64_t * nreads);
+int real_gpu_get_read_table(real_gpu * h, uint32_t * lengths, uint8_t * wildcard_flags);
+int real_gpu_get_read_ids(real_gpu * h, char * bytes, uint64_t * offsets);
+int real_gpu_get_reads_packed(real_gpu * h, uint8_t * packed, uint64_t * byte_offsets);
 int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint8_t * d_quality,
                               const uint64_t * d_offsets, uint64_t nreads, uint64_t total_bases, uint32_t maxlen);
 /* real_gpu_set_reads_packed for a read set of uniform length that is already in device memory (all pointers are

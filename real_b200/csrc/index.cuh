@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(256) k_read_seeds(const uint64_t * __restrict_
 // caller's bytes (ReadSrc, common.cuh) -- so K1 shrinks to the usable length and the two strand seeds of every read.
 // One thread per read; lengths null = all reads have `uniform` bases.
 __global__ void __launch_bounds__(256) k_seeds_packed(const uint8_t * __restrict__ packed, const uint64_t * __restrict__ byte_offsets,
-                                                    const uint64_t * __restrict__ offsets, uint32_t uniform, uint64_t nreads, uint32_t seedl, uint32_t minlen,
+                                                    const uint64_t * __restrict__ offsets, const uint32_t * __restrict__ len32, uint32_t uniform, uint64_t nreads, uint32_t seedl, uint32_t minlen,
                                                     const uint32_t * __restrict__ bad, uint32_t * __restrict__ rlen, uint64_t * __restrict__ seeds,
                                                     uint32_t * __restrict__ usable)
 {
         uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if ( r >= nreads ) return;
-        uint32_t const L = offsets ? (uint32_t)(offsets[r+1] - offsets[r]) : uniform;
+        uint32_t const L = offsets ? (uint32_t)(offsets[r+1] - offsets[r]) : (len32 ? len32[r] : uniform);     // base offsets, lengths, or one length for all
         bool const ok = (L >= minlen) && ! bad[r];
         uint64_t sf = 0;
         if ( ok )

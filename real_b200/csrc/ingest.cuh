@@ -83,12 +83,19 @@ template<typename S> __device__ __forceinline__ S fa_shfl_up(S const & a, int o)
         return r;
 }
 
-// table entry of a byte: x = flags in the low bit of the four byte lanes (kept outside headers, N, '>', '\n'), y = 2-bit code
-__device__ __forceinline__ uint2 fa_entry(uint32_t c)
+// table entry of a byte: x = flags in the low bit of the four byte lanes (kept outside headers, N, '>', '\n'), y = 2-bit code.
+// mode 0 = text file (countReads.cpp:28-125): A C G T N are kept, everything else is dropped.
+// mode 1 = pattern file (FastAReader::getNextPatternUnlocked, FastAReader.hpp:107-138): every byte that is not white space is a
+// base of the read (SpaceTable.hpp:12-19); A C G T map to 0..3, anything else -- lower case included -- is a wildcard
+// (Pattern::computeMapped, Pattern.hpp:105-128).
+__device__ __forceinline__ uint2 fa_entry(uint32_t c, uint32_t mode)
 {
-        uint32_t const base = (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N') ? 1u : 0u;
+        uint32_t const acgt = (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? 1u : 0u;
+        bool const space = c == ' ' || (c >= 9 && c <= 13);
+        uint32_t const base = mode ? ((! space && c != '>') ? 1u : 0u) : ((acgt || c == 'N') ? 1u : 0u);
+        uint32_t const wild = mode ? (base & (acgt ^ 1u)) : (c == 'N' ? 1u : 0u);
         uint32_t const code = c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u;
-        return make_uint2(base | ((c == 'N' ? 1u : 0u) << 8) | ((c == '>' ? 1u : 0u) << 16) | ((c == '\n' ? 1u : 0u) << 24), code);
+        return make_uint2(base | (wild << 8) | ((c == '>' ? 1u : 0u) << 16) | ((c == '\n' ? 1u : 0u) << 24), code);
 }
 
 // one bit per byte of a 32-byte piece (byte i = bit i); codes of the bytes 0..15 / 16..31, byte 0 (16) in the two top bits
@@ -162,23 +169,23 @@ __device__ __forceinline__ FaSum32 fa_piece_summary(FaMasks const & M)
         return s;
 }
 
-// 16 bytes at file offset off (a multiple of 16; the buffer is 16-byte aligned); bytes behind the end of the file read as 0,
-// a dropped byte that leaves the state alone
+// 16 bytes at file offset off (a multiple of 16; the buffer is 16-byte aligned); bytes behind the end of the file read as blanks,
+// dropped bytes that leave the state alone in both modes
 __device__ __forceinline__ uint4 fa_load(const uint8_t * bytes, uint64_t nbytes, uint64_t off)
 {
         if ( off + 16 <= nbytes )
                 return __ldg(reinterpret_cast<const uint4 *>(bytes + off));
-        uint32_t w[4] = { 0, 0, 0, 0 };
+        uint32_t w[4] = { 0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u };
         for ( int i = 0; i < 16; ++i )
-                if ( off + i < nbytes ) w[i >> 2] |= (uint32_t)bytes[off + i] << (8 * (i & 3));
+                if ( off + i < nbytes ) w[i >> 2] = (w[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)bytes[off + i] << (8 * (i & 3)));
         return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(FA_THREADS) k_fa_summary(const uint8_t * __restrict__ bytes, uint64_t nbytes, FaSum32 * __restrict__ sums)
+__global__ void __launch_bounds__(FA_THREADS) k_fa_summary(const uint8_t * __restrict__ bytes, uint64_t nbytes, FaSum32 * __restrict__ sums, uint32_t mode)
 {
         __shared__ uint32_t lut[256];
         __shared__ FaSum32 wsum[FA_THREADS / 32];
-        lut[threadIdx.x] = fa_entry(threadIdx.x).x;
+        lut[threadIdx.x] = fa_entry(threadIdx.x, mode).x;
         uint64_t const byte0 = (uint64_t)blockIdx.x * FA_TILE + threadIdx.x * FA_PER_THREAD;
         uint4 v[4];
         #pragma unroll
@@ -281,14 +288,15 @@ static const uint32_t FA_CU = FA_TILE / 16 + 4, FA_NU = FA_TILE / 32 + 4;
 // text / nmask: word 0 of the (zeroed) arrays; rec_start / rec_nl: one entry per record (rec_nl = file offset of the '\n' that filed it)
 __global__ void __launch_bounds__(FA_THREADS) k_fa_pack(const uint8_t * __restrict__ bytes, uint64_t nbytes, const uint64_t * __restrict__ tile_base,
                                                         const uint64_t * __restrict__ tile_rec, unsigned long long * __restrict__ text,
-                                                        unsigned long long * __restrict__ nmask, uint64_t * __restrict__ rec_start, uint64_t * __restrict__ rec_nl)
+                                                        unsigned long long * __restrict__ nmask, uint64_t * __restrict__ rec_start, uint64_t * __restrict__ rec_nl,
+                                                        uint64_t * __restrict__ rec_open, uint32_t mode)
 {
         __shared__ uint2 lut[256];
         __shared__ uint32_t wf[FA_THREADS / 32];
         __shared__ uint32_t cu[FA_CU];                          // 2-bit codes, 16 bases per unit, most significant first; unit pairs = text words
         __shared__ uint32_t nu[FA_NU];                          // wildcard bits, 32 bases per unit; unit pairs = mask words
         int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        lut[threadIdx.x] = fa_entry(threadIdx.x);
+        lut[threadIdx.x] = fa_entry(threadIdx.x, mode);
         for ( uint32_t i = threadIdx.x; i < FA_CU; i += FA_THREADS ) cu[i] = 0;
         for ( uint32_t i = threadIdx.x; i < FA_NU; i += FA_THREADS ) nu[i] = 0;
         uint64_t const byte0 = (uint64_t)blockIdx.x * FA_TILE + threadIdx.x * FA_PER_THREAD;
@@ -316,13 +324,13 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_pack(const uint8_t * __restri
         for ( int w = 0; w < wid; ++w ) if ( wf[w] ) in = wf[w] == 2;
         uint32_t const lower = m_set & ((1u << lane) - 1);
         if ( lower ) in = (m_one >> (31 - __clz(lower))) & 1;
-        uint32_t kept[2], ends[2];
+        uint32_t kept[2], ends[2], opens[2];
         #pragma unroll
         for ( int s = 0; s < 2; ++s )
         {
                 uint32_t out;
                 uint32_t const st = fa_states(M[s].gt, M[s].nl, in, &out);
-                kept[s] = M[s].base & ~st; ends[s] = M[s].nl & st;
+                kept[s] = M[s].base & ~st; ends[s] = M[s].nl & st; opens[s] = M[s].gt & ~st;
                 in = out;
         }
         uint32_t const k = __popc(kept[0]) + __popc(kept[1]), nh = __popc(ends[0]) + __popc(ends[1]);
@@ -330,7 +338,23 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_pack(const uint8_t * __restri
         uint32_t const ex = block_excl_scan((nh << 16) | k, &tot);
         uint32_t const K = tot & 0xFFFFu;
         uint64_t g = B0 + (ex & 0xFFFFu);                        // index of this thread's next kept base
-        uint64_t r = nh ? tile_rec[blockIdx.x] + (ex >> 16) : 0;
+        uint64_t r = (nh || (rec_open && (opens[0] | opens[1]))) ? tile_rec[blockIdx.x] + (ex >> 16) : 0;
+        if ( rec_open )
+        {
+                // the '>' that opens header number k (pattern files: the id starts behind it): every header opened earlier has been
+                // closed when another one opens, so k = the records filed in front of the '>'
+                uint64_t rr = r;
+                #pragma unroll
+                for ( int s = 0; s < 2; ++s )
+                {
+                        for ( uint32_t m = opens[s]; m; m &= m - 1 )
+                        {
+                                int const i = __ffs(m) - 1;
+                                rec_open[rr + __popc(ends[s] & ((1u << i) - 1))] = byte0 + 32 * s + i;
+                        }
+                        rr += __popc(ends[s]);
+                }
+        }
         #pragma unroll
         for ( int s = 0; s < 2; ++s )
         {
@@ -380,6 +404,112 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_pack(const uint8_t * __restri
                 if ( w * 64 >= B0 && w * 64 + 64 <= B1 ) nmask[w] = val;
                 else if ( val ) atomicOr(&nmask[w], val);
         }
+}
+
+// ---- K0 for pattern files: FASTA reads on the device ----------------------------------------------------------------
+// k_fa_summary / k_fa_scan / k_fa_pack in mode 1 leave: the bases of all reads as ONE 2-bit stream (wildcards as code 0 + a
+// mask bit), read_start[r] = index of read r's first base (read_start[nreads] = all bases), and per read the file offsets of
+// the '>' that opens its id line and of the '\n' that closes it.  Bases in front of the first '>' belong to no read
+// (FastAReader::findFirstMarker); an id line the file ends in without a '\n' opens no read (FastAReader.hpp:120-121).
+// The kernels below turn that into what real_gpu_set_reads_packed takes -- every read on a byte boundary, 4 bases per byte --
+// in the order perm gives (the rewritten order of the reference, or file order), plus the ids for K8.
+
+// per read: length, wildcard flag, packed bytes, id bytes
+__global__ void __launch_bounds__(256) k_rd_table(const uint64_t * __restrict__ read_start, const uint64_t * __restrict__ nmask, const uint64_t * __restrict__ rec_open,
+                                                  const uint64_t * __restrict__ rec_nl, uint64_t nreads, uint32_t * __restrict__ len, uint32_t * __restrict__ wild,
+                                                  uint32_t * __restrict__ idlen, unsigned int * __restrict__ maxlen /* [3]: max length, min key, max key */)
+{
+        uint64_t const r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t L = 0;
+        if ( r < nreads )
+        {
+                uint64_t const b = read_start[r], e = read_start[r+1];
+                L = (uint32_t)min((unsigned long long)(e - b), 0xFFFFFFFFull);
+                len[r] = L;
+                bool w = false;
+                if ( L )
+                {
+                        uint64_t const first = b >> 6, last = (e - 1) >> 6;
+                        for ( uint64_t x = first; x <= last && ! w; ++x )
+                        {
+                                uint64_t m = nmask[x];
+                                if ( x == first ) m &= (~0ULL) >> (b & 63);
+                                if ( x == last ) m &= (~0ULL) << (63 - ((e - 1) & 63));
+                                w = m != 0;
+                        }
+                }
+                wild[r] = w ? 1u : 0u;
+                idlen[r] = (uint32_t)(rec_nl[r] - rec_open[r] - 1);
+        }
+        // key of the rewritten order: (length, has a wildcard); when all reads share one key the order is the file order
+        uint32_t mx = L, kmin = 0xFFFFFFFFu, kmax = 0;
+        if ( r < nreads ) { uint32_t const key = (min(L, 0x7FFFFFFFu) << 1) | wild[r]; kmin = key; kmax = key; }
+        #pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 )
+        {
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if ( (threadIdx.x & 31) == 0 )
+        {
+                if ( mx ) atomicMax(maxlen, mx);
+                atomicMin(maxlen + 1, kmin);
+                atomicMax(maxlen + 2, kmax);
+        }
+}
+
+// 64-bit sums of two u32 arrays (the totals their 32-bit exclusive scans must stay below)
+__global__ void __launch_bounds__(256) k_rd_sums(const uint32_t * __restrict__ a, const uint32_t * __restrict__ b, uint64_t n, unsigned long long * __restrict__ out)
+{
+        unsigned long long sa = 0, sb = 0;
+        for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x ) { sa += a[i]; sb += b[i]; }
+        #pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 ) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+        if ( (threadIdx.x & 31) == 0 ) { if ( sa ) atomicAdd(out, sa); if ( sb ) atomicAdd(out + 1, sb); }
+}
+
+// slot j of the output order holds read perm[j] (perm == nullptr: file order): lengths, flags, sizes in output order
+__global__ void __launch_bounds__(256) k_rd_permute(const uint32_t * __restrict__ perm, uint64_t nreads, const uint32_t * __restrict__ len, const uint32_t * __restrict__ wild,
+                                                    const uint32_t * __restrict__ idlen, uint32_t * __restrict__ olen, uint8_t * __restrict__ oflag,
+                                                    uint32_t * __restrict__ obytes, uint32_t * __restrict__ oidlen)
+{
+        uint64_t const j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( j >= nreads ) return;
+        uint32_t const r = perm ? perm[j] : (uint32_t)j;
+        uint32_t const L = len[r];
+        olen[j] = L; oflag[j] = (uint8_t)wild[r]; obytes[j] = (L + 3) >> 2; oidlen[j] = idlen[r];
+}
+
+// the packed bytes and the id of output slot j; offsets = exclusive scans of obytes / oidlen (u32: the totals are checked by the host)
+__global__ void __launch_bounds__(256) k_rd_repack(const uint32_t * __restrict__ perm, uint64_t nreads, const uint64_t * __restrict__ stream,
+                                                   const uint64_t * __restrict__ read_start, const uint32_t * __restrict__ boff32, uint8_t * __restrict__ packed,
+                                                   uint64_t * __restrict__ boff64, const uint8_t * __restrict__ file, const uint64_t * __restrict__ rec_open,
+                                                   const uint32_t * __restrict__ oidlen, const uint32_t * __restrict__ ioff32, char * __restrict__ ids, uint64_t * __restrict__ ioff64,
+                                                   uint64_t total_bytes, uint64_t total_id)
+{
+        uint64_t const j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ( j > nreads ) return;
+        if ( j == nreads ) { boff64[j] = total_bytes; ioff64[j] = total_id; return; }
+        uint32_t const r = perm ? perm[j] : (uint32_t)j;
+        uint64_t const b = read_start[r];
+        uint32_t const L = (uint32_t)(read_start[r+1] - b);
+        uint8_t * o = packed + boff32[j];
+        boff64[j] = boff32[j];
+        for ( uint32_t w = 0; w * 32 < L; ++w )
+        {
+                uint32_t const n = min(32u, L - 32 * w);
+                uint64_t const v = text_word(stream, b + 32 * w, n) << (64 - 2 * n);        // left aligned, zero filled
+                uint32_t const nb = (n + 3) >> 2;
+                #pragma unroll
+                for ( uint32_t k = 0; k < 8; ++k )
+                        if ( k < nb ) o[8 * w + k] = (uint8_t)(v >> (56 - 8 * k));
+        }
+        char * io = ids + ioff32[j];
+        ioff64[j] = ioff32[j];
+        const uint8_t * src = file + rec_open[r] + 1;
+        uint32_t const n = oidlen[j];
+        for ( uint32_t k = 0; k < n; ++k ) io[k] = (char)src[k];
 }
 
 } // namespace realgpu

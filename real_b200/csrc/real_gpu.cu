@@ -89,6 +89,8 @@ struct real_gpu
         DevBuf ws_k0, ws_v0, ws_k1, ws_v1, ws_flags, ws_hist, ws_stmp;   // index build workspace, kept between calls
         uint32_t * table_counts;       // [6] pinned host memory; per table: entries, distinct slots (copied back asynchronously by the build)
         const uint8_t * src_packed; const uint64_t * src_byte_offsets; uint32_t src_packed_uniform;   // 2-bit input (set_reads_packed)
+        const uint32_t * src_len32;    // 2-bit input with per-read lengths instead of base offsets (set_reads_fasta)
+        DevBuf rd_raw, rd_sums, rd_tbase, rd_trec, rd_stream, rd_mask, rd_start, rd_nl, rd_open, rd_len, rd_wild, rd_idlen, rd_perm, rd_olen, rd_obytes, rd_oidlen, rd_boff, rd_ioff, rd_misc;   // K0 for pattern files
         const uint8_t * src_mapped;    // device pointer the reads are packed from (caller's buffer or h->mapped)
         DevBuf ll, hits_raw, hits_seg, hits_out, hits_out16, counters, counts, starts, cursor, scantmp, info, scores;
         uint64_t hit_cap;
@@ -152,7 +154,7 @@ struct real_gpu
         uint64_t chunk_positions;      // text positions partitioned at a time (REAL_GPU_CHUNK_MPOS); 0 = automatic
         int own_list_max;              // bucket shards: own buckets up to which the kept positions are listed first (REAL_GPU_OWN_LIST_MAX)
 
-        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_mapped(nullptr), fused_build(false), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(0), own_list_max(64), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
+        real_gpu() : n_list(0), src_packed(nullptr), src_byte_offsets(nullptr), src_packed_uniform(0), src_len32(nullptr), src_mapped(nullptr), fused_build(false), pass_bits_override(-1), l2_slice_bytes(48ull << 20), chunk_positions(0), own_list_max(64), st(nullptr), st2(nullptr), build_pending(false), table_counts(nullptr), fa_totals(nullptr), held(0), sm_count(148), have_text(false), n_total(0), shard_begin(0), shard_len(0), own_begin(0), own_end(0),
                      nrec(0), fileid(0), have_reads(false), nreads(0), n_usable(0), total_bases(0), W(0), maxlen(0), qual_present(false),
                      F(0), keybits(0), hit_cap(0), host_hits(nullptr), host_hits_cap(0)
         {
@@ -308,7 +310,7 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
         dev_reserve(h, h->fa_trec, ntiles * 8);
         dev_reserve(h, h->fa_tot, 16);
         if ( ntiles )
-                k_fa_summary<<<(unsigned)ntiles, FA_THREADS, 0, h->st2>>>(d_raw, nbytes, ptr<FaSum32>(h->fa_sums));
+                k_fa_summary<<<(unsigned)ntiles, FA_THREADS, 0, h->st2>>>(d_raw, nbytes, ptr<FaSum32>(h->fa_sums), 0u);
         k_fa_scan<<<1, FA_SCAN_THREADS, 0, h->st2>>>(ptr<FaSum32>(h->fa_sums), ntiles, ptr<uint64_t>(h->fa_tbase), ptr<uint64_t>(h->fa_trec), ptr<uint64_t>(h->fa_tot));
         RG_CUDA(cudaGetLastError());
         launch_count(h, ntiles ? 2 : 1);
@@ -334,7 +336,7 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
         RG_CUDA(cudaMemsetAsync(h->nmask.p, 0, mbytes, h->st2));
         k_fa_pack<<<(unsigned)ntiles, FA_THREADS, 0, h->st2>>>(d_raw, nbytes, ptr<uint64_t>(h->fa_tbase), ptr<uint64_t>(h->fa_trec),
                                                                ptr<unsigned long long>(h->text) + TEXT_PAD_WORDS, ptr<unsigned long long>(h->nmask) + TEXT_PAD_WORDS,
-                                                               ptr<uint64_t>(h->rec), ptr<uint64_t>(h->fa_recnl));
+                                                               ptr<uint64_t>(h->rec), ptr<uint64_t>(h->fa_recnl), nullptr, 0u);
         RG_CUDA(cudaGetLastError());
         launch_count(h);
         RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->rec) + nrec, h->fa_totals, 8, cudaMemcpyHostToDevice, h->st2));
@@ -605,7 +607,8 @@ int build_from_device(real_gpu * h)
                 else if ( h->src_packed )
                 {
                         // 2 bit/base input stays as it is (the verification reads it in place): only lengths and seeds
-                        k_seeds_packed<<<blocks_for(nreads, 256), 256, 0, h->st>>>(h->src_packed, h->src_byte_offsets, h->src_packed_uniform ? nullptr : ptr<uint64_t>(h->offs),
+                        k_seeds_packed<<<blocks_for(nreads, 256), 256, 0, h->st>>>(h->src_packed, h->src_byte_offsets,
+                                                                                 (h->src_packed_uniform || h->src_len32) ? nullptr : ptr<uint64_t>(h->offs), h->src_len32,
                                                                                  h->src_packed_uniform, nreads, seedl, h->prm.seedl, ptr<uint32_t>(h->bad),
                                                                                  ptr<uint32_t>(h->rlen), ptr<uint64_t>(h->seeds), ptr<uint32_t>(h->usable));
                         RG_KERNEL_CHECK(); launch_count(h);
@@ -1111,7 +1114,7 @@ void preload_kernels(int device)
         RG_PRELOAD(k_score_hits); RG_PRELOAD(k_hit_count); RG_PRELOAD(k_hit_scatter); RG_PRELOAD(k_hit_order<real_gpu_hit>);
         RG_PRELOAD(k_unique_export); RG_PRELOAD(k_unique_ties); RG_PRELOAD(k_unique_import); RG_PRELOAD(k_unique_replay); RG_PRELOAD(k_fold_push); RG_PRELOAD(k_fold_merge); RG_PRELOAD(k_unique_checksum); RG_PRELOAD(k_mark_large); RG_PRELOAD(k_sort_large<0>); RG_PRELOAD(k_sort_large<1>); RG_PRELOAD(k_sort_large<2>);
         RG_PRELOAD(k_fmt_len<false>); RG_PRELOAD(k_fmt_len<true>); RG_PRELOAD(k_fmt_write<false>); RG_PRELOAD(k_fmt_write<true>);
-        RG_PRELOAD(k_fa_summary); RG_PRELOAD(k_fa_scan); RG_PRELOAD(k_fa_pack);
+        RG_PRELOAD(k_fa_summary); RG_PRELOAD(k_rd_table); RG_PRELOAD(k_rd_permute); RG_PRELOAD(k_rd_repack); RG_PRELOAD(k_rd_sums); RG_PRELOAD(k_fa_scan); RG_PRELOAD(k_fa_pack);
         RG_PRELOAD(k_window_counts); RG_PRELOAD(k_block_bounds); RG_PRELOAD(k_gap_dp); RG_PRELOAD(k_gap_replay);
 #undef RG_PRELOAD
         done[device] = true;
@@ -1204,7 +1207,9 @@ int real_gpu_destroy(real_gpu * h)
         cudaSetDevice(h->prm.device);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
                            &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->hits_out16, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
-                           &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot };
+                           &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot,
+                           &h->rd_raw, &h->rd_sums, &h->rd_tbase, &h->rd_trec, &h->rd_stream, &h->rd_mask, &h->rd_start, &h->rd_nl, &h->rd_open, &h->rd_len, &h->rd_wild, &h->rd_idlen,
+                           &h->rd_perm, &h->rd_olen, &h->rd_obytes, &h->rd_oidlen, &h->rd_boff, &h->rd_ioff, &h->rd_misc };
         for ( DevBuf * b : all ) dev_free(h, *b);
         for ( int t = 0; t < 3; ++t ) { dev_free(h, h->tab[t].bitmap); dev_free(h, h->tab[t].E); }
         for ( int r = 0; r < SC_MAX_RANKS; ++r )
@@ -1308,7 +1313,7 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
         dev_reserve(h, h->mapped, total + 64);
         dev_reserve(h, h->offs, (nreads + 1) * 8);
-        h->src_mapped = ptr<uint8_t>(h->mapped); h->src_packed = nullptr;
+        h->src_mapped = ptr<uint8_t>(h->mapped); h->src_packed = nullptr; h->src_len32 = nullptr;
         if ( total ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, mapped + offsets[0], total, cudaMemcpyHostToDevice, h->st));
         if ( offsets[0] != 0 )
         {
@@ -1344,7 +1349,7 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
         h->have_reads = false;
         h->nreads = nreads; h->total_bases = total_bases; h->maxlen = maxlen;
         dev_reserve(h, h->offs, (nreads + 1) * 8);
-        h->src_packed = nullptr;
+        h->src_packed = nullptr; h->src_len32 = nullptr;
         h->src_mapped = d_mapped;          // packed before this call returns; the caller's buffer is not referenced afterwards
         RG_CUDA(cudaMemcpyAsync(h->offs.p, d_offsets, (nreads + 1) * 8, cudaMemcpyDeviceToDevice, h->st));
         h->qual_present = false;
@@ -1393,7 +1398,7 @@ int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64
         dev_reserve(h, h->offs, (nreads + 1) * 8);
         dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
         if ( total_bytes ) RG_CUDA(cudaMemcpyAsync(h->mapped.p, packed + (uniform_length ? 0 : byte_offsets[0]), total_bytes, cudaMemcpyHostToDevice, h->st));
-        h->src_packed = ptr<uint8_t>(h->mapped); h->src_mapped = nullptr; h->src_packed_uniform = uniform_length; h->src_byte_offsets = nullptr;
+        h->src_packed = ptr<uint8_t>(h->mapped); h->src_mapped = nullptr; h->src_packed_uniform = uniform_length; h->src_byte_offsets = nullptr; h->src_len32 = nullptr;
         if ( uniform_length )
         {
                 k_uniform_offsets<<<blocks_for(nreads + 1, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, uniform_length);
@@ -1430,6 +1435,190 @@ int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64
         RG_API_END(h)
 }
 
+
+int real_gpu_set_reads_fasta(real_gpu * h, const void * fasta_bytes, uint64_t nbytes, uint32_t rewrite_order, uint64_t * nreads_out)
+{
+        RG_API_BEGIN(h)
+        if ( (! fasta_bytes && nbytes) || ! nreads_out ) return fail(h, REAL_GPU_E_ARG, "set_reads_fasta: null pointer");
+        *nreads_out = 0;
+        uint64_t const ntiles = (nbytes + FA_TILE - 1) / FA_TILE;
+        if ( ntiles >= (1ULL << 31) ) return fail(h, REAL_GPU_E_LIMIT, "set_reads_fasta: file longer than 2^43 bytes");
+        h->have_reads = false;
+        RG_CUDA(cudaEventRecord(h->ev[0], h->st));
+        // the bytes of the file, then the three ingest kernels in pattern-file mode
+        dev_reserve(h, h->rd_raw, nbytes + 64);
+        if ( nbytes ) RG_CUDA(cudaMemcpyAsync(h->rd_raw.p, fasta_bytes, nbytes, cudaMemcpyHostToDevice, h->st));
+        dev_reserve(h, h->rd_sums, std::max<uint64_t>(1, ntiles) * sizeof(FaSum32));
+        dev_reserve(h, h->rd_tbase, std::max<uint64_t>(1, ntiles) * 8);
+        dev_reserve(h, h->rd_trec, std::max<uint64_t>(1, ntiles) * 8);
+        dev_reserve(h, h->rd_misc, 64);
+        RG_CUDA(cudaMemsetAsync(h->rd_misc.p, 0, 64, h->st));
+        const uint8_t * d_raw = ptr<uint8_t>(h->rd_raw);
+        if ( ntiles )
+                k_fa_summary<<<(unsigned)ntiles, FA_THREADS, 0, h->st>>>(d_raw, nbytes, ptr<FaSum32>(h->rd_sums), 1u);
+        k_fa_scan<<<1, FA_SCAN_THREADS, 0, h->st>>>(ptr<FaSum32>(h->rd_sums), ntiles, ptr<uint64_t>(h->rd_tbase), ptr<uint64_t>(h->rd_trec), ptr<uint64_t>(h->rd_misc));
+        RG_KERNEL_CHECK(); launch_count(h, ntiles ? 2 : 1);
+        RG_CUDA(cudaMemcpyAsync(h->fa_totals, h->rd_misc.p, 16, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaEventRecord(h->ev[1], h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));                  // the caller's bytes are on the device; bases and reads are counted
+        h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
+        uint64_t const nb = h->fa_totals[0], nreads = h->fa_totals[1];
+        if ( nreads >= (1ULL << 28) ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: more than 2^28 reads in one set");
+        if ( nb / 4 + nreads >= (1ULL << 32) ) return fail(h, REAL_GPU_E_LIMIT, "set_reads_fasta: more than 2^32 bytes of packed reads; hand the reads over in batches");
+        uint64_t const nw = (nb + 31) / 32 + 4, nmw = (nb + 63) / 64 + 4;
+        dev_reserve(h, h->rd_stream, nw * 8);
+        dev_reserve(h, h->rd_mask, nmw * 8);
+        dev_reserve(h, h->rd_start, (nreads + 2) * 8);
+        dev_reserve(h, h->rd_nl, (nreads + 2) * 8);
+        dev_reserve(h, h->rd_open, (nreads + 2) * 8);
+        RG_CUDA(cudaMemsetAsync(h->rd_stream.p, 0, nw * 8, h->st));
+        RG_CUDA(cudaMemsetAsync(h->rd_mask.p, 0, nmw * 8, h->st));
+        if ( ntiles )
+                k_fa_pack<<<(unsigned)ntiles, FA_THREADS, 0, h->st>>>(d_raw, nbytes, ptr<uint64_t>(h->rd_tbase), ptr<uint64_t>(h->rd_trec),
+                                                                      ptr<unsigned long long>(h->rd_stream), ptr<unsigned long long>(h->rd_mask),
+                                                                      ptr<uint64_t>(h->rd_start), ptr<uint64_t>(h->rd_nl), ptr<uint64_t>(h->rd_open), 1u);
+        RG_KERNEL_CHECK(); launch_count(h);
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->rd_start) + nreads, h->fa_totals, 8, cudaMemcpyHostToDevice, h->st));      // read_start[nreads] = all bases
+        // per read: length, wildcard flag, id length; the longest read and the range of the ordering keys
+        dev_reserve(h, h->rd_len, (nreads + 1) * 4);
+        dev_reserve(h, h->rd_wild, (nreads + 1) * 4);
+        dev_reserve(h, h->rd_idlen, (nreads + 1) * 4);
+        unsigned int * d_mx = ptr<unsigned int>(h->rd_misc) + 8;           // [8] max length, [9] min key, [10] max key
+        unsigned int const init[3] = { 0u, 0xFFFFFFFFu, 0u };
+        RG_CUDA(cudaMemcpyAsync(d_mx, init, 12, cudaMemcpyHostToDevice, h->st));
+        if ( nreads )
+        {
+                k_rd_table<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->rd_start), ptr<uint64_t>(h->rd_mask), ptr<uint64_t>(h->rd_open), ptr<uint64_t>(h->rd_nl),
+                                                                       nreads, ptr<uint32_t>(h->rd_len), ptr<uint32_t>(h->rd_wild), ptr<uint32_t>(h->rd_idlen), d_mx);
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        unsigned int mx[3] = { 0, 0, 0 };
+        RG_CUDA(cudaMemcpyAsync(mx, d_mx, 12, cudaMemcpyDeviceToHost, h->st));
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        if ( mx[0] > 65535 ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: read longer than 65535 bases");
+        // The order of the reference's rewritten pattern file (reorderFastA, ReorderFastA.hpp: by length, reads without wildcards
+        // first, file order inside a group).  When all reads share one key -- the usual case -- it is the file order; otherwise the
+        // keys (8 bytes per read) go to the host for one stable counting sort and the permutation comes back.
+        const uint32_t * d_perm = nullptr;
+        if ( rewrite_order && nreads && mx[1] != mx[2] )
+        {
+                std::vector<uint32_t> len(nreads), wild(nreads), perm(nreads);
+                RG_CUDA(cudaMemcpyAsync(len.data(), h->rd_len.p, nreads * 4, cudaMemcpyDeviceToHost, h->st));
+                RG_CUDA(cudaMemcpyAsync(wild.data(), h->rd_wild.p, nreads * 4, cudaMemcpyDeviceToHost, h->st));
+                RG_CUDA(cudaStreamSynchronize(h->st));
+                std::vector<uint64_t> cnt((size_t)2 * (mx[0] + 1) + 1, 0);
+                for ( uint64_t r = 0; r < nreads; ++r ) ++cnt[(size_t)2 * len[r] + wild[r] + 1];
+                for ( size_t k = 1; k < cnt.size(); ++k ) cnt[k] += cnt[k-1];
+                for ( uint64_t r = 0; r < nreads; ++r ) perm[cnt[(size_t)2 * len[r] + wild[r]]++] = (uint32_t)r;
+                dev_reserve(h, h->rd_perm, nreads * 4);
+                RG_CUDA(cudaMemcpyAsync(h->rd_perm.p, perm.data(), nreads * 4, cudaMemcpyHostToDevice, h->st));
+                RG_CUDA(cudaStreamSynchronize(h->st));
+                d_perm = ptr<uint32_t>(h->rd_perm);
+        }
+        // lengths, flags and sizes in output order; byte offsets of the packed reads and of the ids
+        dev_reserve(h, h->rd_olen, (nreads + 1) * 4);
+        dev_reserve(h, h->flags8, nreads + 64);
+        dev_reserve(h, h->rd_obytes, (nreads + 1) * 4);
+        dev_reserve(h, h->rd_oidlen, (nreads + 1) * 4);
+        dev_reserve(h, h->rd_boff, (nreads + 1) * 4);
+        dev_reserve(h, h->rd_ioff, (nreads + 1) * 4);
+        dev_reserve(h, h->scantmp, scan_temp_elems(nreads + 1) * 4 + 64);
+        unsigned long long tot[2] = { 0, 0 };
+        if ( nreads )
+        {
+                k_rd_permute<<<blocks_for(nreads, 256), 256, 0, h->st>>>(d_perm, nreads, ptr<uint32_t>(h->rd_len), ptr<uint32_t>(h->rd_wild), ptr<uint32_t>(h->rd_idlen),
+                                                                         ptr<uint32_t>(h->rd_olen), ptr<uint8_t>(h->flags8), ptr<uint32_t>(h->rd_obytes), ptr<uint32_t>(h->rd_oidlen));
+                RG_KERNEL_CHECK(); launch_count(h);
+                RG_CUDA(cudaMemsetAsync(h->rd_misc.p, 0, 16, h->st));
+                k_rd_sums<<<(unsigned)std::min<uint64_t>(blocks_for(nreads, 256), (uint64_t)h->sm_count * 8), 256, 0, h->st>>>(ptr<uint32_t>(h->rd_obytes), ptr<uint32_t>(h->rd_oidlen), nreads,
+                                                                                                                       ptr<unsigned long long>(h->rd_misc));
+                RG_KERNEL_CHECK(); launch_count(h);
+                RG_CUDA(cudaMemcpyAsync(tot, h->rd_misc.p, 16, cudaMemcpyDeviceToHost, h->st));
+                uint32_t nl = 0;
+                exclusive_scan_u32(ptr<uint32_t>(h->rd_obytes), ptr<uint32_t>(h->rd_boff), nreads, ptr<uint32_t>(h->scantmp), h->st, &nl);
+                exclusive_scan_u32(ptr<uint32_t>(h->rd_oidlen), ptr<uint32_t>(h->rd_ioff), nreads, ptr<uint32_t>(h->scantmp), h->st, &nl);
+                launch_count(h, nl);
+                RG_CUDA(cudaStreamSynchronize(h->st));
+        }
+        if ( tot[0] >= (1ULL << 32) || tot[1] >= (1ULL << 32) )
+                return fail(h, REAL_GPU_E_LIMIT, "set_reads_fasta: more than 2^32 bytes of packed reads or of ids; hand the reads over in batches");
+        // the read set as real_gpu_set_reads_packed leaves it: packed bytes, byte offsets, lengths, flags -- and the ids for K8
+        h->nreads = nreads; h->total_bases = nb; h->maxlen = mx[0];
+        dev_reserve(h, h->mapped, tot[0] + 64);
+        dev_reserve(h, h->boffs, (nreads + 1) * 8);
+        dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
+        real_gpu::Format & F = h->fmt;
+        dev_reserve(h, F.ids, tot[1] + 16);
+        dev_reserve(h, F.id_off, (nreads + 1) * 8);
+        k_rd_repack<<<blocks_for(nreads + 1, 256), 256, 0, h->st>>>(d_perm, nreads, ptr<uint64_t>(h->rd_stream), ptr<uint64_t>(h->rd_start), ptr<uint32_t>(h->rd_boff),
+                                                                    ptr<uint8_t>(h->mapped), ptr<uint64_t>(h->boffs), d_raw, ptr<uint64_t>(h->rd_open), ptr<uint32_t>(h->rd_oidlen),
+                                                                    ptr<uint32_t>(h->rd_ioff), ptr<char>(F.ids), ptr<uint64_t>(F.id_off), tot[0], tot[1]);
+        RG_KERNEL_CHECK(); launch_count(h);
+        F.id_first = 0; F.id_count = nreads; F.id_bytes = tot[1];
+        if ( nreads )
+        {
+                k_flags_to_bad<<<blocks_for(nreads, 256), 256, 0, h->st>>>(ptr<uint8_t>(h->flags8), nreads, ptr<uint32_t>(h->bad));
+                RG_KERNEL_CHECK(); launch_count(h);
+        }
+        h->src_packed = ptr<uint8_t>(h->mapped); h->src_mapped = nullptr; h->src_packed_uniform = 0;
+        h->src_byte_offsets = ptr<uint64_t>(h->boffs); h->src_len32 = ptr<uint32_t>(h->rd_olen);
+        h->qual_present = false;
+        RG_CUDA(cudaStreamSynchronize(h->st));
+        // the file bytes and the intermediate stream are several times the packed reads: released
+        DevBuf * rel[] = { &h->rd_raw, &h->rd_stream, &h->rd_mask, &h->rd_sums, &h->rd_tbase, &h->rd_trec, &h->rd_start, &h->rd_nl, &h->rd_open, &h->rd_len, &h->rd_wild,
+                           &h->rd_idlen, &h->rd_perm, &h->rd_obytes, &h->rd_oidlen, &h->rd_boff, &h->rd_ioff };
+        for ( DevBuf * b : rel ) dev_free(h, *b);
+        *nreads_out = nreads;
+        return build_from_device(h);
+        RG_API_END(h)
+}
+
+// the read table of the current set: lengths and wildcard flags (either may be NULL), in read order
+int real_gpu_get_read_table(real_gpu * h, uint32_t * lengths, uint8_t * wildcard_flags)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( lengths && h->nreads )
+        {
+                if ( ! h->src_len32 ) return fail(h, REAL_GPU_E_STATE, "get_read_table: the lengths are kept only for reads set by real_gpu_set_reads_fasta");
+                { RG_CUDA(cudaMemcpyAsync(lengths, h->src_len32, h->nreads * 4, cudaMemcpyDeviceToHost, h->st)); RG_CUDA(cudaStreamSynchronize(h->st)); }
+        }
+        if ( wildcard_flags && h->nreads )
+        {
+                std::vector<uint32_t> bad(h->nreads);
+                { RG_CUDA(cudaMemcpyAsync(bad.data(), h->bad.p, h->nreads * 4, cudaMemcpyDeviceToHost, h->st)); RG_CUDA(cudaStreamSynchronize(h->st)); }
+                for ( uint64_t i = 0; i < h->nreads; ++i ) wildcard_flags[i] = bad[i] ? 1 : 0;
+        }
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+// the ids of the reads as set by real_gpu_set_read_ids / real_gpu_set_reads_fasta: offsets[count+1] and, when bytes is given,
+// the id bytes (offsets[count] of them; call once with bytes = NULL to learn the size)
+int real_gpu_get_read_ids(real_gpu * h, char * bytes, uint64_t * offsets)
+{
+        RG_API_BEGIN(h)
+        if ( ! offsets ) return fail(h, REAL_GPU_E_ARG, "get_read_ids: null pointer");
+        real_gpu::Format & F = h->fmt;
+        if ( ! F.id_off.p ) return fail(h, REAL_GPU_E_STATE, "no ids set");
+        { RG_CUDA(cudaMemcpyAsync(offsets, F.id_off.p, (F.id_count + 1) * 8, cudaMemcpyDeviceToHost, h->st)); RG_CUDA(cudaStreamSynchronize(h->st)); }
+        if ( bytes && offsets[F.id_count] ) { RG_CUDA(cudaMemcpyAsync(bytes, F.ids.p, offsets[F.id_count], cudaMemcpyDeviceToHost, h->st)); RG_CUDA(cudaStreamSynchronize(h->st)); }
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
+// the packed bytes of the reads [first, first+count) of a 2 bit/base read set and their byte offsets (count+1, relative to the first)
+int real_gpu_get_reads_packed(real_gpu * h, uint8_t * packed, uint64_t * byte_offsets)
+{
+        RG_API_BEGIN(h)
+        if ( ! h->have_reads ) return fail(h, REAL_GPU_E_STATE, "no reads set");
+        if ( ! h->src_packed || ! h->src_byte_offsets || ! byte_offsets ) return fail(h, REAL_GPU_E_STATE, "get_reads_packed: no packed read set with byte offsets");
+        { RG_CUDA(cudaMemcpyAsync(byte_offsets, h->src_byte_offsets, (h->nreads + 1) * 8, cudaMemcpyDeviceToHost, h->st)); RG_CUDA(cudaStreamSynchronize(h->st)); }
+        if ( packed && byte_offsets[h->nreads] ) { RG_CUDA(cudaMemcpyAsync(packed, h->src_packed, byte_offsets[h->nreads], cudaMemcpyDeviceToHost, h->st)); RG_CUDA(cudaStreamSynchronize(h->st)); }
+        return REAL_GPU_OK;
+        RG_API_END(h)
+}
+
 int real_gpu_set_reads_packed_device(real_gpu * h, const uint8_t * d_packed, uint32_t uniform_length, const uint8_t * d_wildcard_flags,
                                      const uint8_t * d_quality, uint64_t nreads)
 {
@@ -1441,7 +1630,7 @@ int real_gpu_set_reads_packed_device(real_gpu * h, const uint8_t * d_packed, uin
         h->nreads = nreads; h->total_bases = (uint64_t)uniform_length * nreads; h->maxlen = uniform_length;
         dev_reserve(h, h->offs, (nreads + 1) * 8);
         dev_reserve(h, h->bad, (size_t)nreads * 4 + 16);
-        h->src_packed = d_packed; h->src_mapped = nullptr; h->src_packed_uniform = uniform_length; h->src_byte_offsets = nullptr;
+        h->src_packed = d_packed; h->src_mapped = nullptr; h->src_packed_uniform = uniform_length; h->src_byte_offsets = nullptr; h->src_len32 = nullptr;
         k_uniform_offsets<<<blocks_for(nreads + 1, 256), 256, 0, h->st>>>(ptr<uint64_t>(h->offs), nreads, uniform_length);
         RG_KERNEL_CHECK(); launch_count(h);
         if ( d_wildcard_flags && nreads )

@@ -94,6 +94,10 @@ def load(build_if_missing: bool = True):
     L.real_gpu_set_reads.argtypes = [vp, vp, vp, vp, u64]
     L.real_gpu_set_reads_device.argtypes = [vp, vp, vp, vp, u64, u64, u32]
     L.real_gpu_set_reads_packed.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64]
+    L.real_gpu_set_reads_fasta.argtypes = [vp, vp, u64, u32, C.POINTER(u64)]
+    L.real_gpu_get_read_table.argtypes = [vp, vp, vp]
+    L.real_gpu_get_read_ids.argtypes = [vp, vp, vp]
+    L.real_gpu_get_reads_packed.argtypes = [vp, vp, vp]
     L.real_gpu_match_all.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.real_gpu_match_all_packed.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.real_gpu_match_unique.argtypes = [vp]
@@ -254,6 +258,43 @@ class Handle:
                 for a, dt in ((packed, np.uint8), (byte_offsets, np.uint64), (lengths, np.uint32), (wildcard_flags, np.uint8), (quality, np.uint8))]
         ptrs = [a.ctypes.data if a is not None else None for a in keep]
         self._check(self.L.real_gpu_set_reads_packed(self.h, ptrs[0], ptrs[1], ptrs[2], uniform_length, ptrs[3], ptrs[4], nreads))
+
+    def set_reads_fasta(self, data, rewrite_order: bool = False) -> int:
+        """Read set straight from the bytes of a FASTA pattern file (parsed and packed on the device); returns the number of reads."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        n = C.c_uint64()
+        self._check(self.L.real_gpu_set_reads_fasta(self.h, buf.ctypes.data if buf.size else None, buf.size, 1 if rewrite_order else 0, C.byref(n)))
+        self.nreads = int(n.value)
+        return self.nreads
+
+    def get_read_table(self):
+        """(lengths, wildcard flags) of the reads set by set_reads_fasta"""
+        ln = np.zeros(max(1, self.nreads), dtype=np.uint32)
+        fl = np.zeros(max(1, self.nreads), dtype=np.uint8)
+        self._check(self.L.real_gpu_get_read_table(self.h, ln.ctypes.data, fl.ctypes.data))
+        return ln[:self.nreads], fl[:self.nreads]
+
+    def get_read_ids(self):
+        offs = np.zeros(self.nreads + 1, dtype=np.uint64)
+        self._check(self.L.real_gpu_get_read_ids(self.h, None, offs.ctypes.data))
+        blob = np.zeros(max(1, int(offs[-1])), dtype=np.uint8)
+        self._check(self.L.real_gpu_get_read_ids(self.h, blob.ctypes.data, offs.ctypes.data))
+        b = blob.tobytes()
+        return [b[int(offs[i]):int(offs[i + 1])] for i in range(self.nreads)]
+
+    def get_reads_mapped(self):
+        """The reads of a 2 bit/base read set unpacked to one list of base codes per read (wildcards read as 0)."""
+        offs = np.zeros(self.nreads + 1, dtype=np.uint64)
+        self._check(self.L.real_gpu_get_reads_packed(self.h, None, offs.ctypes.data))
+        blob = np.zeros(max(1, int(offs[-1])), dtype=np.uint8)
+        self._check(self.L.real_gpu_get_reads_packed(self.h, blob.ctypes.data, offs.ctypes.data))
+        ln, _ = self.get_read_table()
+        out = []
+        for i in range(self.nreads):
+            p = blob[int(offs[i]):int(offs[i + 1])]
+            codes = np.stack([(p >> 6) & 3, (p >> 4) & 3, (p >> 2) & 3, p & 3], 1).reshape(-1)[:int(ln[i])]
+            out.append(codes)
+        return out
 
     def set_reads_packed_device(self, d_packed: int, nreads: int, uniform_length: int, d_wildcard_flags: int | None = None, d_quality: int | None = None):
         self.nreads = nreads
