@@ -1200,22 +1200,36 @@ namespace
                         if ( starter_err ) { std::exception_ptr e = starter_err; starter_err = nullptr; std::rethrow_exception(e); }
                 }
                 ~GpuTeam() { if ( starter.joinable() ) starter.join(); }
-                // after wait(): bucket shards and, for matchUnique, the fold windows
-                void connect(uint64_t nreads, bool unique)
+                // after wait(): bucket shards (before the reads are set) ...
+                void shard()
                 {
                         unsigned int const n = size();
                         if ( n == 1 ) return;
-                        for ( unsigned int i = 0; i < n; ++i )
-                        {
-                                g[i].check(real_gpu_set_bucket_shard(g[i].h, i, n), "set_bucket_shard");
-                                if ( unique ) g[i].check(real_gpu_fold_init(g[i].h, i, n, nreads, 0), "fold_init");
-                        }
-                        if ( unique )
-                        {
-                                std::vector<real_gpu *> hs(n);
-                                for ( unsigned int i = 0; i < n; ++i ) hs[i] = g[i].h;
-                                for ( unsigned int i = 0; i < n; ++i ) g[i].check(real_gpu_fold_connect_local(g[i].h, &hs[0]), "fold_connect_local");
-                        }
+                        for ( unsigned int i = 0; i < n; ++i ) g[i].check(real_gpu_set_bucket_shard(g[i].h, i, n), "set_bucket_shard");
+                }
+                // ... and, for matchUnique, the fold windows (once the number of reads is known)
+                void connectFold(uint64_t nreads)
+                {
+                        unsigned int const n = size();
+                        if ( n == 1 ) return;
+                        for ( unsigned int i = 0; i < n; ++i ) g[i].check(real_gpu_fold_init(g[i].h, i, n, nreads, 0), "fold_init");
+                        std::vector<real_gpu *> hs(n);
+                        for ( unsigned int i = 0; i < n; ++i ) hs[i] = g[i].h;
+                        for ( unsigned int i = 0; i < n; ++i ) g[i].check(real_gpu_fold_connect_local(g[i].h, &hs[0]), "fold_connect_local");
+                }
+                void connect(uint64_t nreads, bool unique)
+                {
+                        shard();
+                        if ( unique ) connectFold(nreads);
+                }
+                // The pattern file parsed on the device (K0 in pattern-file mode, real_gpu_set_reads_fasta): every handle is given the
+                // bytes of the FASTA file and parses, packs and orders the reads itself; the ids stay on the device for the formatter.
+                uint64_t setReadsFasta(FileBytes const & buf, bool rewrite_order)
+                {
+                        std::vector<uint64_t> n(size(), 0);
+                        parallelFor(size(), [this, &buf, &n, rewrite_order](unsigned int i)
+                        { g[i].check(real_gpu_set_reads_fasta(g[i].h, buf.empty() ? 0 : &buf[0], buf.size(), rewrite_order ? 1u : 0u, &n[i]), "set_reads_fasta"); });
+                        return n[0];
                 }
                 void setReads(ReadSet const & reads, PackedReads const & P)
                 {
@@ -1308,6 +1322,23 @@ namespace
                 return ! (e && std::string(e) == "host");
         }
 
+        // REAL_READS_LOADER=host: the pattern file is parsed by the host team instead of on the device.  The device reader takes
+        // FASTA files (FASTQ needs the length-counted quality block and stays with the host team), and only when the lines are
+        // formatted on the device too -- the host formatter needs the reads in host memory.
+        bool deviceReadsLoader(RealOptions const & opts, bool devfmt)
+        {
+                char const * const e = getenv("REAL_READS_LOADER");
+                if ( e && std::string(e) == "host" ) return false;
+                return devfmt && ! opts.fastq && ! opts.rewritten_reads && ! getenv("REAL_KEEP_REWRITTEN");
+        }
+
+        // the bytes of the pattern file (or of standard input)
+        void patternBytes(RealOptions const & opts, FileBytes & buf)
+        {
+                if ( opts.stdin_bytes ) buf.adopt(*opts.stdin_bytes);
+                else buf.open(opts.patternfilename);
+        }
+
         // ids of the reads [lo, hi) as one byte string + offsets, for real_gpu_set_read_ids
         void setReadIds(Gpu & G, ReadSet const & reads, uint64_t lo, uint64_t hi)
         {
@@ -1371,18 +1402,33 @@ int doMatchingAll(RealOptions const & opts)
 {
         PhaseTimer PT;
         GpuTeam team(opts, false);           // the CUDA contexts come up while the pattern file is read
-        ReadSet reads;
-        loadReads(opts, reads);
-        PT.lap("read patterns");            // (the stock -u 0 path parses FASTQ files with the FASTA reader, real.cpp:325-328; here FASTQ is honoured)
-        PackedReads packed;
-        packReads(reads, packed, hostThreads(opts));
-        std::vector<std::string> filenames;
-        getFileList(opts.textfilename, filenames, ".fa");
-        team.wait();
-        team.connect(reads.size(), false);
-        team.setReads(reads, packed);
         bool const devfmt = deviceFormat() && team.size() == 1;       // several handles: their rows are merged (and formatted) on the host
-        if ( devfmt ) setReadIds(team.g[0], reads, 0, reads.size());
+        ReadSet reads;
+        std::vector<std::string> filenames;
+        if ( deviceReadsLoader(opts, devfmt) )
+        {
+                // the pattern file goes to the device as it is: parsed, packed and indexed there, ids kept there for the formatter
+                FileBytes buf;
+                patternBytes(opts, buf);
+                PT.lap("read patterns");
+                getFileList(opts.textfilename, filenames, ".fa");
+                team.wait();
+                team.shard();
+                uint64_t const n = team.setReadsFasta(buf, false);
+                std::cerr << "Number of patterns is " << n << std::endl;
+        }
+        else
+        {
+                loadReads(opts, reads);
+                PT.lap("read patterns");            // (the stock -u 0 path parses FASTQ files with the FASTA reader, real.cpp:325-328; here FASTQ is honoured)
+                PackedReads packed;
+                packReads(reads, packed, hostThreads(opts));
+                getFileList(opts.textfilename, filenames, ".fa");
+                team.wait();
+                team.connect(reads.size(), false);
+                team.setReads(reads, packed);
+                if ( devfmt ) setReadIds(team.g[0], reads, 0, reads.size());
+        }
         PT.lap("create + set_reads");
         Output out(opts.outputfilename);
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
@@ -1487,38 +1533,58 @@ int doMatchingUnique(RealOptions const & opts)
 {
         PhaseTimer PT;
         GpuTeam team(opts, opts.scores || opts.gaps);     // the CUDA contexts come up while the pattern file is read
+        bool const devfmt = deviceFormat();
         ReadSet reads;
-        loadReads(opts, reads);
-        PT.lap("read patterns");
-        if ( opts.rewritepatterns && ! opts.rewritten_reads )
-                reorderLikeRewrite(reads);
-        if ( char const * keep = getenv("REAL_KEEP_REWRITTEN") )
+        uint64_t nreads = 0;
+        std::vector<std::string> filenames;
+        if ( deviceReadsLoader(opts, devfmt) )
         {
-                // the reference writes this file for every -R 1 run and deletes it afterwards (real.cpp:238-311); kept, it can be
-                // given back as -p and spares the next run the parsing of the pattern file
-                if ( opts.rewritepatterns || opts.rewritten_reads )
+                // the pattern file goes to the device as it is: parsed, packed, put into the rewritten order (-R 1) and indexed there;
+                // the ids stay on the device for the formatter
+                FileBytes buf;
+                patternBytes(opts, buf);
+                PT.lap("read patterns");
+                getFileList(opts.textfilename, filenames, ".fa");
+                team.wait();
+                team.shard();
+                nreads = team.setReadsFasta(buf, opts.rewritepatterns);
+                std::cerr << "Number of patterns is " << nreads << std::endl;
+                team.connectFold(nreads);
+        }
+        else
+        {
+                loadReads(opts, reads);
+                PT.lap("read patterns");
+                if ( opts.rewritepatterns && ! opts.rewritten_reads )
+                        reorderLikeRewrite(reads);
+                if ( char const * keep = getenv("REAL_KEEP_REWRITTEN") )
                 {
-                        std::vector<char> bytes;
-                        writeRewritten(reads, opts.fastq, bytes);
-                        Output keepf(keep);
-                        if ( ! bytes.empty() && fwrite(&bytes[0], 1, bytes.size(), keepf.f) != bytes.size() ) throw std::runtime_error("write failed");
+                        // the reference writes this file for every -R 1 run and deletes it afterwards (real.cpp:238-311); kept, it can be
+                        // given back as -p and spares the next run the parsing of the pattern file
+                        if ( opts.rewritepatterns || opts.rewritten_reads )
+                        {
+                                std::vector<char> bytes;
+                                writeRewritten(reads, opts.fastq, bytes);
+                                Output keepf(keep);
+                                if ( ! bytes.empty() && fwrite(&bytes[0], 1, bytes.size(), keepf.f) != bytes.size() ) throw std::runtime_error("write failed");
+                        }
+                }
+                PackedReads packed;
+                packReads(reads, packed, hostThreads(opts));
+                getFileList(opts.textfilename, filenames, ".fa");
+                nreads = reads.size();
+                team.wait();
+                team.connect(nreads, true);
+                team.setReads(reads, packed);
+                if ( devfmt )
+                {
+                        // every handle formats the lines of the reads whose merged state it holds after the fold
+                        unsigned int const n = team.size();
+                        uint64_t const R = nreads;
+                        parallelFor(n, [&team, &reads, n, R](unsigned int i) { setReadIds(team.g[i], reads, R * i / n, R * (i + 1) / n); });
                 }
         }
-        PackedReads packed;
-        packReads(reads, packed, hostThreads(opts));
-        std::vector<std::string> filenames;
-        getFileList(opts.textfilename, filenames, ".fa");
-        team.wait();
-        team.connect(reads.size(), true);
-        team.setReads(reads, packed);
-        bool const devfmt = deviceFormat();
-        if ( devfmt )
-        {
-                // every handle formats the lines of the reads whose merged state it holds after the fold
-                unsigned int const n = team.size();
-                uint64_t const R = reads.size();
-                parallelFor(n, [&team, &reads, n, R](unsigned int i) { setReadIds(team.g[i], reads, R * i / n, R * (i + 1) / n); });
-        }
+        PT.lap("create + set_reads");
         Gpu & G = team.g[0];
         std::vector< std::vector< std::pair<std::string, uint64_t> > > rangeset(filenames.size());       // RangeSet
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
@@ -1536,7 +1602,7 @@ int doMatchingUnique(RealOptions const & opts)
                 if ( ! usable )
                         continue;
                 if ( opts.scores )
-                        G.check(real_gpu_set_block_windows(G.h, planBlockWindows(opts, T, reads.size())), "set_block_windows");
+                        G.check(real_gpu_set_block_windows(G.h, planBlockWindows(opts, T, nreads)), "set_block_windows");
                 parallelFor(team.size(), [&team](unsigned int i) { team.g[i].check(real_gpu_match_unique(team.g[i].h), "match_unique"); });
                 team.foldUnique();          // several handles: every one now holds the merged state of its own share of the reads
         }
@@ -1549,7 +1615,7 @@ int doMatchingUnique(RealOptions const & opts)
                         TextFile T;
                         if ( ! setText(G, opts, (uint32_t)fi, filenames[fi], T, true) || T.ranges.size() > 65536 )
                                 continue;
-                        G.check(real_gpu_match_gaps(G.h, planBlockWindows(opts, T, reads.size())), "match_gaps");
+                        G.check(real_gpu_match_gaps(G.h, planBlockWindows(opts, T, nreads)), "match_gaps");
                 }
         }
         if ( devfmt )
@@ -1557,7 +1623,7 @@ int doMatchingUnique(RealOptions const & opts)
                 PT.lap("texts + matching");
                 Output out(opts.outputfilename);
                 unsigned int const n = team.size();
-                uint64_t const R = reads.size();
+                uint64_t const R = nreads;
                 uint64_t unique = 0;
                 for ( unsigned int i = 0; i < n; ++i )
                 {
@@ -1579,11 +1645,11 @@ int doMatchingUnique(RealOptions const & opts)
                 std::cerr << "unique: " << unique << std::endl;
                 return EXIT_SUCCESS;
         }
-        std::vector<uint64_t> info(reads.size() + 1);
-        std::vector<float> score(reads.size() + 1);
+        std::vector<uint64_t> info(nreads + 1);
+        std::vector<float> score(nreads + 1);
         {
                 unsigned int const n = team.size();
-                uint64_t const R = reads.size();
+                uint64_t const R = nreads;
                 parallelFor(n, [&team, &info, &score, &opts, n, R](unsigned int i)
                 {
                         uint64_t const lo = R * i / n, hi = R * (i + 1) / n;          // the reads whose merged state handle i holds
@@ -1594,7 +1660,7 @@ int doMatchingUnique(RealOptions const & opts)
         PT.lap("texts + matching");
         Output out(opts.outputfilename);
         bool const scores = opts.scores;
-        uint64_t const unique = formatParallel(reads.size(), hostThreads(opts), out,
+        uint64_t const unique = formatParallel(nreads, hostThreads(opts), out,
                 [&reads, &info, &score, &rangeset, scores](std::string & o, uint64_t r) -> uint64_t
         {
                 uint64_t const d = info[r];

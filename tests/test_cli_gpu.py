@@ -12,17 +12,18 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("formatter", ["device", "host"])
+@pytest.mark.parametrize("formatter", ["device", "host", "device+hostreads"])
 @pytest.mark.parametrize("name", CASES)
 def test_cli_output_identical_to_stock_real(name, formatter, tmp_path):
-    """The lines are formatted on the device (K8, real_gpu_format_*: the default) or by the host team (REAL_FORMAT=host): both
-    write the stock binary's bytes."""
+    """The lines are formatted on the device (K8, real_gpu_format_*: the default) or by the host team (REAL_FORMAT=host), FASTA
+    pattern files are parsed on the device (real_gpu_set_reads_fasta: the default with the device formatter) or by the host team
+    (REAL_READS_LOADER=host): every combination writes the stock binary's bytes."""
     rbuild.build()
     rbuild.build_host()
     targ, rf, flags = make_case(name, str(tmp_path))
     out = tmp_path / "out.txt"
     p = subprocess.run([rbuild.HOST_BIN, "-t", targ, "-p", rf, "-o", str(out)] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                       env=dict(os.environ, REAL_STRICT_EXIT="1", REAL_FORMAT=formatter))
+                       env=dict(os.environ, REAL_STRICT_EXIT="1", REAL_FORMAT=formatter.split("+")[0], REAL_READS_LOADER="host" if "hostreads" in formatter else "device"))
     assert p.returncode == 0, p.stderr[-2000:]
     want = open(os.path.join(GOLDEN, "cli_%s.txt" % name)).read()
     got = out.read_text()

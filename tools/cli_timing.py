@@ -19,8 +19,12 @@ print("inputs: %d bp, %d reads, generated in %.1f s" % (n, R, time.time() - t0),
 rbuild.build(); rbuild.build_host()
 flags = ["-u", "1", "-s", "2", "-e", "4", "-l", "32", "-q", "0", "-R", "0"]
 res = {}
+# one discarded invocation first: the first process on a fresh box pays for paging in the CUDA libraries
+subprocess.run([rbuild.HOST_BIN, "-t", os.path.join(work, "t.fa"), "-p", os.path.join(work, "r.fa"), "-o", os.path.join(work, "warm.txt")] + flags,
+               stdout=subprocess.PIPE, stderr=subprocess.PIPE)
 for name, exe, extra, env in (("gpu_T1", rbuild.HOST_BIN, ["-T", "1"], {"REAL_TIMING": "1"}),
                               ("gpu_Tall", rbuild.HOST_BIN, [], {"REAL_TIMING": "1"}),
+                              ("gpu_Tall_hostreads", rbuild.HOST_BIN, [], {"REAL_TIMING": "1", "REAL_READS_LOADER": "host"}),
                               ("gpu_Tall_hostfmt", rbuild.HOST_BIN, [], {"REAL_TIMING": "1", "REAL_FORMAT": "host"}),
                               ("gpu_Tall_hosttext", rbuild.HOST_BIN, [], {"REAL_TIMING": "1", "REAL_TEXT_LOADER": "host"}),
                               ("stock_cpu", os.path.join(ROOT, "oracle", "_ref", "real"), ["-T", str(os.cpu_count() or 1)], {})):
@@ -41,6 +45,8 @@ if "gpu_Tall" in res and "stock_cpu" in res:
     print("outputs identical to the stock binary:", same)
 if "gpu_Tall_hosttext" in res and "gpu_Tall" in res:
     print("outputs identical between the device and the host text loader:", open(res["gpu_Tall_hosttext"], "rb").read() == open(res["gpu_Tall"], "rb").read())
+if "gpu_Tall_hostreads" in res and "gpu_Tall" in res:
+    print("outputs identical between the device and the host reads loader:", open(res["gpu_Tall_hostreads"], "rb").read() == open(res["gpu_Tall"], "rb").read())
 if "gpu_Tall_hostfmt" in res and "gpu_Tall" in res:
     print("outputs identical between the device and the host formatter:", open(res["gpu_Tall_hostfmt"], "rb").read() == open(res["gpu_Tall"], "rb").read())
 if "gpu_T1" in res and "gpu_Tall" in res:
