@@ -1546,8 +1546,10 @@ int doMatchingUnique(RealOptions const & opts)
                 PT.lap("read patterns");
                 getFileList(opts.textfilename, filenames, ".fa");
                 team.wait();
+                PT.lap("  contexts");
                 team.shard();
                 nreads = team.setReadsFasta(buf, opts.rewritepatterns);
+                PT.lap("  set_reads_fasta");
                 std::cerr << "Number of patterns is " << nreads << std::endl;
                 team.connectFold(nreads);
         }
@@ -1573,9 +1575,12 @@ int doMatchingUnique(RealOptions const & opts)
                 packReads(reads, packed, hostThreads(opts));
                 getFileList(opts.textfilename, filenames, ".fa");
                 nreads = reads.size();
+                PT.lap("  pack reads");
                 team.wait();
+                PT.lap("  contexts");
                 team.connect(nreads, true);
                 team.setReads(reads, packed);
+                PT.lap("  set_reads_packed");
                 if ( devfmt )
                 {
                         // every handle formats the lines of the reads whose merged state it holds after the fold
