@@ -1364,20 +1364,56 @@ namespace
         // Writes the batches a formatter hands out, one behind the other, while the next batch is being formatted: next(&bytes,
         // &nbytes) formats the next batch into library-owned memory that stays valid until its next-but-one call, and returns
         // false when there is none left.
+        // one batch to the output: a regular file takes it as four slices written side by side at their offsets (a single
+        // writer copies at ~2.5 GB/s into the page cache: 3.1 of the 6.8 s of a run on C3-size inputs); a pipe or a device in order
+        void writeBytes(Output & out, uint64_t at, char const * b, uint64_t n)
+        {
+                struct stat st;
+                bool const regular = out.own && fstat(fileno(out.f), &st) == 0 && S_ISREG(st.st_mode);
+                if ( ! regular )
+                {
+                        if ( fwrite(b, 1, n, out.f) != n ) throw std::runtime_error("write failed");
+                        return;
+                }
+                int const fd = fileno(out.f);
+                unsigned int const parts = n >= (32u << 20) ? 4u : 1u;
+                std::atomic<int> failed(0);
+                auto slice = [fd, at, b, n, parts, &failed](unsigned int p)
+                {
+                        uint64_t o = n * p / parts; uint64_t const e = n * (p + 1) / parts;
+                        while ( o < e )
+                        {
+                                ssize_t const w = pwrite(fd, b + o, e - o, (off_t)(at + o));
+                                if ( w <= 0 ) { failed = 1; return; }
+                                o += (uint64_t)w;
+                        }
+                };
+                std::vector<std::thread> team;
+                for ( unsigned int p = 1; p < parts; ++p ) team.push_back(std::thread(slice, p));
+                slice(0);
+                for ( size_t t = 0; t < team.size(); ++t ) team[t].join();
+                if ( failed ) throw std::runtime_error("write failed");
+        }
+
+        // Writes the batches a formatter hands out, one behind the other, while the next batch is being formatted: next(&bytes,
+        // &nbytes) formats the next batch into library-owned memory that stays valid until its next-but-one call, and returns
+        // false when there is none left.  `at` = bytes written to the output so far (kept by the caller across several calls).
         template<typename F>
-        void writeBatches(Output & out, F next)
+        void writeBatches(Output & out, uint64_t & at, F next)
         {
                 std::thread writer; std::exception_ptr err;
                 char const * bytes = 0; uint64_t nbytes = 0;
+                fflush(out.f);
                 while ( next(&bytes, &nbytes) )
                 {
                         if ( writer.joinable() ) writer.join();
                         if ( err ) std::rethrow_exception(err);
                         if ( ! nbytes ) continue;
-                        char const * const b = bytes; uint64_t const n = nbytes;
-                        writer = std::thread([&out, &err, b, n]()
+                        char const * const b = bytes; uint64_t const n = nbytes, pos = at;
+                        at += n;
+                        writer = std::thread([&out, &err, b, n, pos]()
                         {
-                                try { if ( fwrite(b, 1, n, out.f) != n ) throw std::runtime_error("write failed"); }
+                                try { writeBytes(out, pos, b, n); }
                                 catch ( ... ) { err = std::current_exception(); }
                         });
                 }
@@ -1431,6 +1467,7 @@ int doMatchingAll(RealOptions const & opts)
         }
         PT.lap("create + set_reads");
         Output out(opts.outputfilename);
+        uint64_t written = 0;
         for ( size_t fi = 0; fi < filenames.size(); ++fi )
         {
                 TextFile T;
@@ -1467,7 +1504,7 @@ int doMatchingAll(RealOptions const & opts)
                         setRecordNames(G, 0, T.ranges);
                         uint64_t const per = 1u << 18;
                         uint64_t at = 0;
-                        writeBatches(out, [&G, &at, nhits, per](char const ** bytes, uint64_t * nbytes) -> bool
+                        writeBatches(out, written, [&G, &at, nhits, per](char const ** bytes, uint64_t * nbytes) -> bool
                         {
                                 if ( at >= nhits ) return false;
                                 uint64_t const c = std::min<uint64_t>(per, nhits - at);
@@ -1629,14 +1666,14 @@ int doMatchingUnique(RealOptions const & opts)
                 Output out(opts.outputfilename);
                 unsigned int const n = team.size();
                 uint64_t const R = nreads;
-                uint64_t unique = 0;
+                uint64_t unique = 0, written = 0;
                 for ( unsigned int i = 0; i < n; ++i )
                 {
                         Gpu & Gi = team.g[i];
                         uint64_t const hi = R * (i + 1) / n;
                         uint64_t at = R * i / n;
                         uint64_t const per = 1u << 18;
-                        writeBatches(out, [&Gi, &at, &unique, hi, per](char const ** bytes, uint64_t * nbytes) -> bool
+                        writeBatches(out, written, [&Gi, &at, &unique, hi, per](char const ** bytes, uint64_t * nbytes) -> bool
                         {
                                 if ( at >= hi ) return false;
                                 uint64_t const c = std::min<uint64_t>(per, hi - at);
