@@ -885,8 +885,11 @@ __device__ __forceinline__ uint32_t sub_local_slot(uint64_t seed, TableGeom cons
         return entry_slot(seed, G, t) - slot0;
 }
 
+#ifndef REAL_BUILD_MINB
+#define REAL_BUILD_MINB 6
+#endif
 template<bool SPLIT, bool FAST>
-__global__ void __launch_bounds__(256, SPLIT ? 6 : 3) k_build_sub3(const __grid_constant__ Build3Params P)
+__global__ void __launch_bounds__(256, SPLIT ? REAL_BUILD_MINB : 3) k_build_sub3(const __grid_constant__ Build3Params P)
 {
         extern __shared__ __align__(16) uint32_t sub_smem[];
         uint32_t const words = P.words;

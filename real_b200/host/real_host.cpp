@@ -173,6 +173,7 @@ RealOptions::RealOptions(int argc, char * argv[])
         if ( ! outputfilename.size() )
                 throw std::runtime_error("Mandatory argument -o (output file name) is not given.");
         fracmem = std::min(1.0, fracmem);
+        rewritten_input = false;
         ngpus = 1;
         if ( char const * e = getenv("REAL_GPUS") ) ngpus = std::max(1, atoi(e));
         if ( patternfilename == "-" )
@@ -204,8 +205,8 @@ RealOptions::RealOptions(int argc, char * argv[])
                 {
                         // the reference's rewritten pattern file, kept from an earlier run (REAL_KEEP_REWRITTEN): the reads come out of
                         // it in rewritten order, qualities already reduced by their offset
-                        rewritten_reads.reset(new ReadSet());
-                        readRewritten(head, *rewritten_reads, fastq);
+                        rewritten_input = true;
+                        fastq = rewrittenIsFastq(head);
                         std::cerr << "pattern file is a rewritten pattern file" << std::endl;
                 }
         }
@@ -824,71 +825,148 @@ void writeRewritten(ReadSet const & reads, bool fastq, std::vector<char> & out)
 
 bool looksRewritten(FileBytes const & buf) { return buf.size() >= 8 && buf[0] == 0; }
 
+// the sections of a rewritten file: per pattern length the wildcard-free part (0) and the part with wildcards (1)
+namespace
+{
+        struct RewrittenPart { uint64_t L, data, ids, nreads; int part; };
+
+        void rewrittenLayout(FileBytes const & buf, std::vector<RewrittenPart> & parts, bool & fastq)
+        {
+                parts.clear();
+                uint64_t at = 0;
+                uint64_t const size = buf.size();
+                auto need = [&](uint64_t k) { if ( at + k > size ) throw std::runtime_error("rewritten pattern file: truncated"); };
+                auto getU32 = [&]() -> uint32_t { need(4); const unsigned char * p = (const unsigned char *)&buf[at]; at += 4; return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; };
+                auto getSection = [&](uint32_t magic) -> uint64_t
+                {
+                        uint64_t bl = getU32();
+                        if ( bl == 0xFFFFFFFFULL ) { uint64_t const hi = getU32(), lo = getU32(); bl = (hi << 32) | lo; }
+                        if ( bl < 4 || getU32() != magic ) throw std::runtime_error("rewritten pattern file: unexpected section");
+                        need(bl - 4);
+                        return bl - 4;
+                };
+                bool known = false;
+                fastq = false;
+                while ( at < size )
+                {
+                        uint64_t const L = getU32();
+                        for ( int part = 0; part < 2; ++part )
+                        {
+                                RewrittenPart P;
+                                P.L = L; P.part = part;
+                                uint64_t const ndata = getSection(part ? 2u : 0u); P.data = at; at += ndata;
+                                uint64_t const nids = getSection(part ? 3u : 1u); P.ids = at; at += nids;
+                                // the ids tell how many reads the section holds (the record size tells FASTA from FASTQ)
+                                uint64_t c = 0, x = P.ids;
+                                uint64_t const end = P.ids + nids;
+                                while ( x < end )
+                                {
+                                        if ( x + 2 > end ) throw std::runtime_error("rewritten pattern file: broken id section");
+                                        x += 2 + (((uint64_t)(unsigned char)buf[x] << 8) | (unsigned char)buf[x+1]);
+                                        ++c;
+                                }
+                                if ( x != end ) throw std::runtime_error("rewritten pattern file: broken id section");
+                                P.nreads = c;
+                                uint64_t const code = part ? (L + 1) / 2 : (L + 3) / 4;
+                                if ( c && L )
+                                {
+                                        bool fq;
+                                        if ( ndata == c * code ) fq = false;
+                                        else if ( ndata == c * (code + L) ) fq = true;
+                                        else throw std::runtime_error("rewritten pattern file: section size does not match its ids");
+                                        if ( known && fq != fastq ) throw std::runtime_error("rewritten pattern file: mixed record kinds");
+                                        known = true; fastq = fq;
+                                }
+                                else if ( ! c && ndata ) throw std::runtime_error("rewritten pattern file: section size does not match its ids");
+                                parts.push_back(P);
+                        }
+                }
+        }
+}
+
+bool rewrittenIsFastq(FileBytes const & buf)
+{
+        std::vector<RewrittenPart> parts; bool fastq = false;
+        rewrittenLayout(buf, parts, fastq);
+        return fastq;
+}
+
 void readRewritten(FileBytes const & buf, ReadSet & reads, bool & fastq)
 {
         reads.mapped.clear(); reads.quality.clear(); reads.ids.clear(); reads.offsets.assign(1, 0);
-        uint64_t at = 0;
-        uint64_t const size = buf.size();
-        auto need = [&](uint64_t k) { if ( at + k > size ) throw std::runtime_error("rewritten pattern file: truncated"); };
-        auto getU32 = [&]() -> uint32_t { need(4); const unsigned char * p = (const unsigned char *)&buf[at]; at += 4; return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; };
-        auto getSection = [&](uint32_t magic) -> uint64_t
+        std::vector<RewrittenPart> parts;
+        rewrittenLayout(buf, parts, fastq);
+        for ( size_t g = 0; g < parts.size(); ++g )
         {
-                uint64_t bl = getU32();
-                if ( bl == 0xFFFFFFFFULL ) { uint64_t const hi = getU32(), lo = getU32(); bl = (hi << 32) | lo; }
-                if ( bl < 4 || getU32() != magic ) throw std::runtime_error("rewritten pattern file: unexpected section");
-                need(bl - 4);
-                return bl - 4;
-        };
-        bool known = false;
-        fastq = false;
-        while ( at < size )
-        {
-                uint64_t const L = getU32();
-                struct Part { uint64_t data, ndata, ids, nids, nreads; } P[2];
-                for ( int part = 0; part < 2; ++part )
+                RewrittenPart const & P = parts[g];
+                uint64_t const L = P.L, code = P.part ? (L + 1) / 2 : (L + 3) / 4, rec = code + (fastq ? L : 0);
+                uint64_t x = P.ids;
+                for ( uint64_t i = 0; i < P.nreads; ++i )
                 {
-                        P[part].ndata = getSection(part ? 2u : 0u); P[part].data = at; at += P[part].ndata;
-                        P[part].nids = getSection(part ? 3u : 1u); P[part].ids = at; at += P[part].nids;
-                        // the ids tell how many reads the section holds (the record size tells FASTA from FASTQ)
-                        uint64_t c = 0, x = P[part].ids, const_end = P[part].ids + P[part].nids;
-                        while ( x < const_end )
-                        {
-                                if ( x + 2 > const_end ) throw std::runtime_error("rewritten pattern file: broken id section");
-                                x += 2 + (((uint64_t)(unsigned char)buf[x] << 8) | (unsigned char)buf[x+1]);
-                                ++c;
-                        }
-                        if ( x != const_end ) throw std::runtime_error("rewritten pattern file: broken id section");
-                        P[part].nreads = c;
-                        uint64_t const code = part ? (L + 1) / 2 : (L + 3) / 4;
-                        if ( c && L )
-                        {
-                                bool fq;
-                                if ( P[part].ndata == c * code ) fq = false;
-                                else if ( P[part].ndata == c * (code + L) ) fq = true;
-                                else throw std::runtime_error("rewritten pattern file: section size does not match its ids");
-                                if ( known && fq != fastq ) throw std::runtime_error("rewritten pattern file: mixed record kinds");
-                                known = true; fastq = fq;
-                        }
+                        const unsigned char * d = (const unsigned char *)&buf[0] + P.data + i * rec;
+                        size_t const o = reads.mapped.size();
+                        reads.mapped.resize(o + L);
+                        if ( ! P.part )
+                                for ( uint64_t j = 0; j < L; ++j ) reads.mapped[o + j] = (d[j >> 2] >> (6 - 2 * (j & 3))) & 3;
+                        else
+                                for ( uint64_t j = 0; j < L; ++j ) reads.mapped[o + j] = std::min<unsigned int>((d[j >> 1] >> ((j & 1) ? 0 : 4)) & 15, 4);
+                        if ( fastq ) reads.quality.insert(reads.quality.end(), d + code, d + code + L);
+                        reads.offsets.push_back(reads.mapped.size());
+                        uint64_t const il = ((uint64_t)(unsigned char)buf[x] << 8) | (unsigned char)buf[x+1];
+                        reads.ids.push_back(std::string(&buf[0] + x + 2, &buf[0] + x + 2 + il));
+                        x += 2 + il;
                 }
-                for ( int part = 0; part < 2; ++part )
+        }
+}
+
+// The same file straight into what the device takes: the ACGT sections ARE the 2 bit/base layout of real_gpu_set_reads_packed
+// (every read on a byte boundary, 4 bases per byte) and are copied as they stand -- one memcpy per section for FASTA, one per
+// read for FASTQ, whose records carry their qualities behind the bases; the reads of the ACGTN sections are flagged and stored
+// as A.  No byte-per-base copy of the reads is made.  ids: one byte string + offsets (real_gpu_set_read_ids).
+void readRewrittenPacked(FileBytes const & buf, PackedReads & out, std::vector<uint8_t> & quality, std::vector<char> & idbytes, std::vector<uint64_t> & idoff, bool & fastq)
+{
+        std::vector<RewrittenPart> parts;
+        rewrittenLayout(buf, parts, fastq);
+        uint64_t n = 0, nbytes = 0, nbases = 0, nid = 0;
+        for ( size_t g = 0; g < parts.size(); ++g )
+        {
+                n += parts[g].nreads; nbytes += parts[g].nreads * ((parts[g].L + 3) / 4); nbases += parts[g].nreads * parts[g].L;
+        }
+        out.packed.assign(nbytes + 8, 0);
+        out.byte_offsets.assign(n + 1, 0); out.lengths.assign(n, 0); out.wildcard.assign(n, 0);
+        quality.clear();
+        if ( fastq ) quality.resize(nbases);
+        idoff.assign(n + 1, 0);
+        uint64_t r = 0, bo = 0, qo = 0;
+        for ( size_t g = 0; g < parts.size(); ++g )
+        {
+                RewrittenPart const & P = parts[g];
+                uint64_t const L = P.L, pk = (L + 3) / 4, code = P.part ? (L + 1) / 2 : pk, rec = code + (fastq ? L : 0);
+                const unsigned char * d = (const unsigned char *)&buf[0] + P.data;
+                if ( ! P.part && ! fastq && P.nreads )
+                        memcpy(&out.packed[bo], d, P.nreads * pk);                 // the section as it stands
+                uint64_t x = P.ids;
+                for ( uint64_t i = 0; i < P.nreads; ++i, ++r )
                 {
-                        uint64_t const code = part ? (L + 1) / 2 : (L + 3) / 4, rec = code + (fastq ? L : 0);
-                        uint64_t x = P[part].ids;
-                        for ( uint64_t i = 0; i < P[part].nreads; ++i )
-                        {
-                                const unsigned char * d = (const unsigned char *)&buf[0] + P[part].data + i * rec;
-                                size_t const o = reads.mapped.size();
-                                reads.mapped.resize(o + L);
-                                if ( ! part )
-                                        for ( uint64_t j = 0; j < L; ++j ) reads.mapped[o + j] = (d[j >> 2] >> (6 - 2 * (j & 3))) & 3;
-                                else
-                                        for ( uint64_t j = 0; j < L; ++j ) reads.mapped[o + j] = std::min<unsigned int>((d[j >> 1] >> ((j & 1) ? 0 : 4)) & 15, 4);
-                                if ( fastq ) reads.quality.insert(reads.quality.end(), d + code, d + code + L);
-                                reads.offsets.push_back(reads.mapped.size());
-                                uint64_t const il = ((uint64_t)(unsigned char)buf[x] << 8) | (unsigned char)buf[x+1];
-                                reads.ids.push_back(std::string(&buf[0] + x + 2, &buf[0] + x + 2 + il));
-                                x += 2 + il;
-                        }
+                        if ( ! P.part && fastq ) memcpy(&out.packed[bo], d + i * rec, pk);
+                        if ( fastq ) { memcpy(&quality[qo], d + i * rec + code, L); qo += L; }
+                        out.lengths[r] = (uint32_t)L; out.wildcard[r] = P.part ? 1 : 0;
+                        bo += pk; out.byte_offsets[r+1] = bo;
+                        uint64_t const il = ((uint64_t)(unsigned char)buf[x] << 8) | (unsigned char)buf[x+1];
+                        idoff[r+1] = idoff[r] + il; nid += il;
+                        x += 2 + il;
+                }
+        }
+        idbytes.resize(nid + 1);
+        r = 0;
+        for ( size_t g = 0; g < parts.size(); ++g )
+        {
+                uint64_t x = parts[g].ids;
+                for ( uint64_t i = 0; i < parts[g].nreads; ++i, ++r )
+                {
+                        uint64_t const il = idoff[r+1] - idoff[r];
+                        memcpy(&idbytes[idoff[r]], &buf[0] + x + 2, il);
+                        x += 2 + il;
                 }
         }
 }
@@ -1231,6 +1309,15 @@ namespace
                         { g[i].check(real_gpu_set_reads_fasta(g[i].h, buf.empty() ? 0 : &buf[0], buf.size(), rewrite_order ? 1u : 0u, &n[i]), "set_reads_fasta"); });
                         return n[0];
                 }
+                void setReadsPacked(PackedReads const & P, std::vector<uint8_t> const & quality)
+                {
+                        uint64_t const n = P.lengths.size();
+                        parallelFor(size(), [this, &P, &quality, n](unsigned int i)
+                        {
+                                g[i].check(real_gpu_set_reads_packed(g[i].h, &P.packed[0], &P.byte_offsets[0], P.lengths.empty() ? 0 : &P.lengths[0], 0,
+                                                                     P.wildcard.empty() ? 0 : &P.wildcard[0], quality.empty() ? 0 : &quality[0], n), "set_reads_packed");
+                        });
+                }
                 void setReads(ReadSet const & reads, PackedReads const & P)
                 {
                         parallelFor(size(), [this, &reads, &P](unsigned int i)
@@ -1283,11 +1370,12 @@ namespace
         {
                 FileBytes buf;
                 PhaseTimer PT;
-                if ( opts.rewritten_reads )
+                if ( opts.rewritten_input )
                 {
-                        // -p named a rewritten pattern file: its reads were taken out of it when the options were read
-                        reads.mapped.swap(opts.rewritten_reads->mapped); reads.quality.swap(opts.rewritten_reads->quality);
-                        reads.offsets.swap(opts.rewritten_reads->offsets); reads.ids.swap(opts.rewritten_reads->ids);
+                        // -p named a rewritten pattern file (the host formatter needs the reads one byte per base)
+                        buf.open(opts.patternfilename);
+                        bool fq = false;
+                        readRewritten(buf, reads, fq);
                         std::cerr << "Number of patterns is " << reads.size() << std::endl;
                         return;
                 }
@@ -1329,7 +1417,7 @@ namespace
         {
                 char const * const e = getenv("REAL_READS_LOADER");
                 if ( e && std::string(e) == "host" ) return false;
-                return devfmt && ! opts.fastq && ! opts.rewritten_reads && ! getenv("REAL_KEEP_REWRITTEN");
+                return devfmt && ! opts.fastq && ! opts.rewritten_input && ! getenv("REAL_KEEP_REWRITTEN");
         }
 
         // the bytes of the pattern file (or of standard input)
@@ -1337,6 +1425,12 @@ namespace
         {
                 if ( opts.stdin_bytes ) buf.adopt(*opts.stdin_bytes);
                 else buf.open(opts.patternfilename);
+        }
+
+        // ids [lo, hi) out of one byte string + offsets
+        void setReadIdsBlob(Gpu & G, std::vector<char> const & bytes, std::vector<uint64_t> const & off, uint64_t lo, uint64_t hi)
+        {
+                G.check(real_gpu_set_read_ids(G.h, lo, hi - lo, &bytes[0], &off[lo]), "set_read_ids");
         }
 
         // ids of the reads [lo, hi) as one byte string + offsets, for real_gpu_set_read_ids
@@ -1452,6 +1546,21 @@ int doMatchingAll(RealOptions const & opts)
                 team.shard();
                 uint64_t const n = team.setReadsFasta(buf, false);
                 std::cerr << "Number of patterns is " << n << std::endl;
+        }
+        else if ( opts.rewritten_input && devfmt )
+        {
+                // a kept rewritten pattern file: its 2 bit/base sections go to the device as they stand
+                FileBytes buf;
+                buf.open(opts.patternfilename);
+                PackedReads packed; std::vector<uint8_t> quality; std::vector<char> idbytes; std::vector<uint64_t> idoff; bool fq = false;
+                readRewrittenPacked(buf, packed, quality, idbytes, idoff, fq);
+                std::cerr << "Number of patterns is " << packed.lengths.size() << std::endl;
+                PT.lap("read patterns");
+                getFileList(opts.textfilename, filenames, ".fa");
+                team.wait();
+                team.connect(packed.lengths.size(), false);
+                team.setReadsPacked(packed, quality);
+                setReadIdsBlob(team.g[0], idbytes, idoff, 0, packed.lengths.size());
         }
         else
         {
@@ -1590,17 +1699,35 @@ int doMatchingUnique(RealOptions const & opts)
                 std::cerr << "Number of patterns is " << nreads << std::endl;
                 team.connectFold(nreads);
         }
+        else if ( opts.rewritten_input && devfmt && ! getenv("REAL_KEEP_REWRITTEN") )
+        {
+                // a kept rewritten pattern file: its 2 bit/base sections go to the device as they stand
+                FileBytes buf;
+                buf.open(opts.patternfilename);
+                PackedReads packed; std::vector<uint8_t> quality; std::vector<char> idbytes; std::vector<uint64_t> idoff; bool fq = false;
+                readRewrittenPacked(buf, packed, quality, idbytes, idoff, fq);
+                nreads = packed.lengths.size();
+                std::cerr << "Number of patterns is " << nreads << std::endl;
+                PT.lap("read patterns");
+                getFileList(opts.textfilename, filenames, ".fa");
+                team.wait();
+                team.connect(nreads, true);
+                team.setReadsPacked(packed, quality);
+                unsigned int const n = team.size();
+                uint64_t const R = nreads;
+                parallelFor(n, [&team, &idbytes, &idoff, n, R](unsigned int i) { setReadIdsBlob(team.g[i], idbytes, idoff, R * i / n, R * (i + 1) / n); });
+        }
         else
         {
                 loadReads(opts, reads);
                 PT.lap("read patterns");
-                if ( opts.rewritepatterns && ! opts.rewritten_reads )
+                if ( opts.rewritepatterns && ! opts.rewritten_input )
                         reorderLikeRewrite(reads);
                 if ( char const * keep = getenv("REAL_KEEP_REWRITTEN") )
                 {
                         // the reference writes this file for every -R 1 run and deletes it afterwards (real.cpp:238-311); kept, it can be
                         // given back as -p and spares the next run the parsing of the pattern file
-                        if ( opts.rewritepatterns || opts.rewritten_reads )
+                        if ( opts.rewritepatterns || opts.rewritten_input )
                         {
                                 std::vector<char> bytes;
                                 writeRewritten(reads, opts.fastq, bytes);

@@ -53,7 +53,7 @@ struct RealOptions
         int device;             // REAL_GPU_DEVICE, default 0
         int ngpus;              // REAL_GPUS, default 1: handles (= bucket shards) the matching is spread over, device + i modulo the
                                 // devices present; the order dependent folds (-q 1, -g 1) always run on one handle
-        std::shared_ptr<struct ReadSet> rewritten_reads;    // -p names a rewritten pattern file (first byte 0): its reads, in rewritten order
+        bool rewritten_input;   // -p names a rewritten pattern file (first byte 0): its reads are in rewritten order already
         std::shared_ptr< std::vector<char> > stdin_bytes;   // -p -: the pattern file as read from standard input (RealOptions.cpp:418-426)
 
         RealOptions(int argc, char * argv[]);
@@ -124,6 +124,10 @@ uint64_t planBlockWindows(RealOptions const & opts, TextFile const & T, uint64_t
 bool looksRewritten(FileBytes const & buf);
 // fills `reads` (in rewritten order) from the bytes of a rewritten file; fastq = whether its records carry qualities
 void readRewritten(FileBytes const & buf, ReadSet & reads, bool & fastq);
+bool rewrittenIsFastq(FileBytes const & buf);
+// the same straight into the device's 2 bit/base layout (the ACGT sections copied as they stand), qualities and ids
+struct PackedReads;
+void readRewrittenPacked(FileBytes const & buf, PackedReads & out, std::vector<uint8_t> & quality, std::vector<char> & idbytes, std::vector<uint64_t> & idoff, bool & fastq);
 // The reads 2 bit/base in the layout of the reference's rewritten pattern file (TemporaryFile.hpp:231-268,
 // writePatternDontCareFree): 4 bases per byte, first base in bits 7..6, every read on a byte boundary; reads with a
 // wildcard are flagged (the reference keeps them in a 4 bit/base section of their own) and stored as A.  This is what

@@ -94,6 +94,26 @@ int main(int argc, char * argv[])
                         RealOptions o(argc - 3, argv + 3);
                         printf("{\"n_list\":%llu}\n", (unsigned long long)planBlockWindows(o, T, nreads));
                 }
+                else if ( mode == "unrewrite_packed" )
+                {
+                        // the rewritten file straight into the device layout (readRewrittenPacked)
+                        FileBytes buf; buf.open(argv[2]);
+                        PackedReads P; std::vector<uint8_t> q; std::vector<char> idb; std::vector<uint64_t> ido; bool fastq = false;
+                        readRewrittenPacked(buf, P, q, idb, ido, fastq);
+                        printf("{\"fastq\":%d,\"lengths\":[", (int)fastq);
+                        for ( size_t i = 0; i < P.lengths.size(); ++i ) printf("%s%u", i ? "," : "", P.lengths[i]);
+                        printf("],\"wildcard\":[");
+                        for ( size_t i = 0; i < P.wildcard.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)P.wildcard[i]);
+                        printf("],\"byte_offsets\":[");
+                        for ( size_t i = 0; i < P.byte_offsets.size(); ++i ) printf("%s%llu", i ? "," : "", (unsigned long long)P.byte_offsets[i]);
+                        printf("],\"packed\":[");
+                        for ( size_t i = 0; i < (size_t)P.byte_offsets.back(); ++i ) printf("%s%u", i ? "," : "", (unsigned)P.packed[i]);
+                        printf("],\"quality\":[");
+                        for ( size_t i = 0; i < q.size(); ++i ) printf("%s%u", i ? "," : "", (unsigned)q[i]);
+                        printf("],\"ids\":[");
+                        for ( size_t i = 0; i + 1 < ido.size(); ++i ) { if ( i ) putchar(','); jstr(std::string(&idb[ido[i]], &idb[ido[i+1]])); }
+                        printf("]}\n");
+                }
                 else if ( mode == "ll" )
                 {
                         double ll[1024];

@@ -44,6 +44,32 @@ def test_writer_and_reader_against_reference_fixture(dump, kind, tmp_path):
         assert p[k] == r[k], k
 
 
+@pytest.mark.parametrize("kind", ["fa", "fq"])
+def test_rewritten_file_straight_into_the_device_layout(dump, kind, tmp_path):
+    """readRewrittenPacked (the ACGT sections copied as they stand) gives what packing the parsed reads gives."""
+    z = np.load(os.path.join(GOLDEN, "rewritten_%s.npz" % kind))
+    ref = tmp_path / "ref.bin"
+    ref.write_bytes(z["rewritten"].tobytes())
+    src = tmp_path / ("r." + kind)
+    src.write_bytes(z["input"].tobytes())
+    r = json.loads(subprocess.run([dump, "unrewrite_packed", str(ref)], check=True, stdout=subprocess.PIPE).stdout)
+    p = json.loads(subprocess.run([dump, "reads", str(src), "1" if kind == "fq" else "0", "0", "1"], check=True, stdout=subprocess.PIPE).stdout)
+    offs, mapped = p["offsets"], np.asarray(p["mapped"], dtype=np.int64)
+    assert r["ids"] == p["ids"] and r["quality"] == p["quality"] and r["fastq"] == (1 if kind == "fq" else 0)
+    assert r["lengths"] == [offs[i + 1] - offs[i] for i in range(len(offs) - 1)]
+    packed = np.asarray(r["packed"], dtype=np.int64)
+    for i in range(len(offs) - 1):
+        m = mapped[offs[i]:offs[i + 1]]
+        wild = bool((m > 3).any())
+        assert r["wildcard"][i] == int(wild)
+        got = packed[r["byte_offsets"][i]:r["byte_offsets"][i + 1]]
+        want = np.zeros((len(m) + 3) // 4, dtype=np.int64)
+        if not wild:
+            for j, c in enumerate(m):
+                want[j // 4] |= int(c) << (6 - 2 * (j % 4))
+        assert np.array_equal(got, want), i
+
+
 def test_reader_rejects_broken_files(dump, tmp_path):
     z = np.load(os.path.join(GOLDEN, "rewritten_fa.npz"))
     data = z["rewritten"].tobytes()
