@@ -719,7 +719,9 @@ def main():
             else:
                 h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
                 t1 = time.perf_counter()
-                h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+                # the copies of the text are enqueued (real_gpu_set_text_async): the partition of the scan starts when the words have
+                # arrived, the wildcard mask travels meanwhile; the pinned buffers stay untouched until the match call has returned
+                h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
             t2 = time.perf_counter()
             if gather is not None:
                 t1 = t2

@@ -149,6 +149,15 @@ int real_gpu_set_text(real_gpu * h, uint32_t fileid,
                       uint64_t n_total, uint64_t shard_begin, uint64_t shard_len,
                       uint64_t own_begin, uint64_t own_end,
                       const uint64_t * record_starts, uint32_t nrecords);
+/* real_gpu_set_text whose copies are only ENQUEUED when the call returns: words, nmask and record_starts must stay valid and
+ * unchanged until the next real_gpu_match_* call on the handle has returned (or another real_gpu_set_text* / real_gpu_get_text*
+ * call, which wait for the copies).  The scan then starts partitioning as soon as the text words have arrived -- the wildcard
+ * mask (a third of the bytes) is needed by the probe only and travels meanwhile.  Pinned host memory, or the copies block. */
+int real_gpu_set_text_async(real_gpu * h, uint32_t fileid,
+                            const uint64_t * words, const uint64_t * nmask,
+                            uint64_t n_total, uint64_t shard_begin, uint64_t shard_len,
+                            uint64_t own_begin, uint64_t own_end,
+                            const uint64_t * record_starts, uint32_t nrecords);
 /* Same, with words/nmask already resident in device memory (record_starts stays a host pointer). */
 int real_gpu_set_text_device(real_gpu * h, uint32_t fileid,
                              const uint64_t * d_words, const uint64_t * d_nmask,

@@ -55,6 +55,8 @@ struct real_gpu
         cudaStream_t st2;              // host<->device copies of the text, so that they overlap the index build on st
         cudaEvent_t ev[8];
         cudaEvent_t evc[2];
+        cudaEvent_t ev_words;          // real_gpu_set_text_async: the text words are on the device (the partition may start; the probe waits for evc[1])
+        bool text_pending;             // an asynchronous text copy has been enqueued and not yet waited for by the host
         std::vector<cudaEvent_t> evp;  // pairs around the probe kernel of every chunk of a scan (stats.probe_ms)
         bool fused_build;              // the current tables were built by build_tables_fused (entry arrays in item numbering)
         bool build_pending;            // the index build of the current read set has been enqueued but not yet waited for
@@ -164,7 +166,7 @@ struct real_gpu
                 memset(&prm, 0, sizeof(prm));
                 memset(&stats, 0, sizeof(stats));
                 for ( int i = 0; i < 8; ++i ) ev[i] = nullptr;
-                evc[0] = evc[1] = nullptr;
+                evc[0] = evc[1] = nullptr; ev_words = nullptr; text_pending = false;
                 for ( int i = 0; i < 8; ++i ) stage_buf[i] = nullptr;
                 for ( int i = 0; i < 4; ++i ) stage_st[i] = nullptr;
         }
@@ -281,10 +283,20 @@ void h2d_from_host(real_gpu * h, void * dst, const void * src, size_t nbytes, cu
 // text
 // ---------------------------------------------------------------------------------------------
 
+// waits (on the host) for a text copy real_gpu_set_text_async has left in flight
+void finish_text(real_gpu * h)
+{
+        if ( ! h->text_pending ) return;
+        h->text_pending = false;
+        RG_CUDA(cudaEventSynchronize(h->evc[1]));
+        h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);
+}
+
 int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const uint64_t * nmask, bool on_device,
                     uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
-                    const uint64_t * record_starts, uint32_t nrecords)
+                    const uint64_t * record_starts, uint32_t nrecords, bool async_copy = false)
 {
+        finish_text(h);
         if ( ! words || ! nmask || ! record_starts || nrecords == 0 )
                 return fail(h, REAL_GPU_E_ARG, "set_text: null pointer or no records");
         if ( shard_begin % 64 )
@@ -321,12 +333,19 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
         RG_CUDA(cudaMemsetAsync(h->nmask.p, 0, TEXT_PAD_WORDS * 8, h->st2));
         RG_CUDA(cudaMemsetAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS + nmw, 0, tail * 8, h->st2));
         cudaMemcpyKind const kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, words, nw * 8, kind, h->st2));
-        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, nmask, nmw * 8, kind, h->st2));
+        // the words first: the partition kernels of a scan need nothing else (the wildcard mask is read by the probe only)
         RG_CUDA(cudaMemcpyAsync(h->rec.p, record_starts, (size_t)(nrecords + 1) * 8, cudaMemcpyHostToDevice, h->st2));
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, words, nw * 8, kind, h->st2));
+        RG_CUDA(cudaEventRecord(h->ev_words, h->st2));
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, nmask, nmw * 8, kind, h->st2));
         RG_CUDA(cudaEventRecord(h->evc[1], h->st2));
-        RG_CUDA(cudaEventSynchronize(h->evc[1]));       // the caller's buffers are free again; later launches on the kernel stream come after
-        h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);
+        if ( async_copy )
+                h->text_pending = true;                 // real_gpu_set_text_async: the scan waits on the device, the host at its end
+        else
+        {
+                RG_CUDA(cudaEventSynchronize(h->evc[1]));       // the caller's buffers are free again; later launches on the kernel stream come after
+                h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);
+        }
 
         h->fileid = fileid; h->n_total = n_total; h->shard_begin = shard_begin; h->shard_len = shard_len;
         h->own_begin = own_begin; h->own_end = own_end; h->nrec = nrecords;
@@ -348,6 +367,7 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
         uint64_t const ntiles = (nbytes + FA_TILE - 1) / FA_TILE;
         if ( ntiles >= (1ULL << 31) )
                 return fail(h, REAL_GPU_E_LIMIT, "set_text_fasta: file longer than 2^43 bytes");
+        finish_text(h);
         h->have_text = false;
         h->fa_rec_starts.clear(); h->fa_rec_nl.clear();
         *n_bases = 0; *nrecords = 0;
@@ -900,6 +920,7 @@ uint64_t run_scan(real_gpu * h, int mode)
         fill_scan_params(h, P, mode);
         uint64_t const first_tile = P.x_begin / SC_TILE_POS, end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
         uint64_t const ntiles = (P.x_end > P.x_begin) ? (end_tile - first_tile) : 0;
+        if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st, h->ev_words, 0));      // asynchronous text copy: the words must have arrived
         RG_CUDA(cudaEventRecord(h->ev[5], h->st));
         size_t nprobe_ev = 0;
         if ( ntiles )
@@ -1102,6 +1123,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 RG_CUDA(cudaEventCreate(&a)); RG_CUDA(cudaEventCreate(&b));
                                 h->evp.push_back(a); h->evp.push_back(b);
                         }
+                        if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st, h->evc[1], 0));          // ... and now the wildcard mask
                         RG_CUDA(cudaEventRecord(h->evp[2 * nprobe_ev], h->st));
                         probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
@@ -1133,6 +1155,7 @@ uint64_t run_scan(real_gpu * h, int mode)
         RG_CUDA(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
         h->stats.scan_ms = elapsed(h->ev[5], h->ev[6]);
+        finish_text(h);
         h->stats.probe_ms = 0;
         for ( size_t i = 0; i < nprobe_ev; ++i ) h->stats.probe_ms += elapsed(h->evp[2*i], h->evp[2*i+1]);
         if ( ! ntiles ) h->stats.n_windows = 0;
@@ -1237,6 +1260,7 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 RG_CUDA(cudaMallocHost(&h->fa_totals, 2 * sizeof(uint64_t)));
                 for ( int i = 0; i < 8; ++i ) RG_CUDA(cudaEventCreate(&h->ev[i]));
                 for ( int i = 0; i < 2; ++i ) RG_CUDA(cudaEventCreate(&h->evc[i]));
+                RG_CUDA(cudaEventCreateWithFlags(&h->ev_words, cudaEventDisableTiming));
                 if ( params->ll_table )
                 {
                         dev_alloc(h, h->ll, 1024 * 8);
@@ -1260,6 +1284,7 @@ int real_gpu_destroy(real_gpu * h)
 {
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
+        if ( h->text_pending ) cudaEventSynchronize(h->evc[1]);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
                            &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->hits_out16, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
                            &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot,
@@ -1286,6 +1311,7 @@ int real_gpu_destroy(real_gpu * h)
         for ( int i = 0; i < 8; ++i ) if ( h->stage_buf[i] ) cudaFreeHost(h->stage_buf[i]);
         for ( int i = 0; i < 4; ++i ) if ( h->stage_st[i] ) cudaStreamDestroy(h->stage_st[i]);
         for ( int i = 0; i < 2; ++i ) if ( h->evc[i] ) cudaEventDestroy(h->evc[i]);
+        if ( h->ev_words ) cudaEventDestroy(h->ev_words);
         if ( h->st2 ) cudaStreamDestroy(h->st2);
         if ( h->table_counts ) cudaFreeHost(h->table_counts);
         if ( h->fa_totals ) cudaFreeHost(h->fa_totals);
@@ -1302,6 +1328,15 @@ int real_gpu_set_text(real_gpu * h, uint32_t fileid, const uint64_t * words, con
 {
         RG_API_BEGIN_ASYNC(h)
         return set_text_common(h, fileid, words, nmask, false, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords);
+        RG_API_END(h)
+}
+
+int real_gpu_set_text_async(real_gpu * h, uint32_t fileid, const uint64_t * words, const uint64_t * nmask,
+                            uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
+                            const uint64_t * record_starts, uint32_t nrecords)
+{
+        RG_API_BEGIN_ASYNC(h)
+        return set_text_common(h, fileid, words, nmask, false, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords, true);
         RG_API_END(h)
 }
 

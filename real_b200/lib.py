@@ -87,6 +87,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_last_error.restype = C.c_char_p
     L.real_gpu_set_text.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_text_device.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
+    L.real_gpu_set_text_async.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_text_fasta.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.real_gpu_set_text_fasta_device.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.real_gpu_get_text_records.argtypes = [vp, vp, vp]
@@ -196,11 +197,17 @@ class Handle:
 
     # ---- text
     def set_text(self, words: np.ndarray, nmask: np.ndarray, n_total: int, record_starts: np.ndarray, fileid: int = 0,
-                 shard_begin: int = 0, shard_len: int | None = None, own_begin: int | None = None, own_end: int | None = None):
+                 shard_begin: int = 0, shard_len: int | None = None, own_begin: int | None = None, own_end: int | None = None, async_copy: bool = False):
+        """async_copy: real_gpu_set_text_async -- the buffers (pinned) must stay valid until the next match call has returned"""
         shard_len = n_total - shard_begin if shard_len is None else shard_len
         own_begin = shard_begin if own_begin is None else own_begin
         own_end = shard_begin + shard_len if own_end is None else own_end
         rs = np.ascontiguousarray(record_starts, dtype=np.uint64)
+        if async_copy:
+            self._keep_text = (words, nmask, rs)
+            self._check(self.L.real_gpu_set_text_async(self.h, fileid, _np_ptr(words, np.uint64), _np_ptr(nmask, np.uint64), n_total,
+                                                       shard_begin, shard_len, own_begin, own_end, rs.ctypes.data, rs.size - 1))
+            return
         self._check(self.L.real_gpu_set_text(self.h, fileid, _np_ptr(words, np.uint64), _np_ptr(nmask, np.uint64), n_total,
                                              shard_begin, shard_len, own_begin, own_end, rs.ctypes.data, rs.size - 1))
 
