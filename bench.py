@@ -432,6 +432,9 @@ def main():
                          "form: every rank ends up with the merged state of its own 1/N of the reads); 'nccl' = MIN + SUM all-reduce "
                          "(real_b200.dist.unique_exchange: every rank ends up with the whole merged state)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-order", choices=["text-first", "reads-first"], default="text-first",
+                    help="end-to-end leg: text-first = set_text_async, prepare_scan, set_reads, match (the partition of the text runs while "
+                         "the reads cross PCIe); reads-first = set_reads, set_text_async, match")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ingest", action="store_true", help="skip the K0 (device text loader) extra of the bench line")
     ap.add_argument("--ref-text", type=int, default=32_000_000, help="reference arm: text bases of the sample")
@@ -609,19 +612,21 @@ def main():
     value = R / (ms_per_step * 1e-3)
 
     # ---- digest of the result of the last step (outside the timed region): must not depend on the number of GPUs
-    if unique:
-        if world > 1 and not peer_fold:
-            part = h.unique_checksum(r_lo, r_hi - r_lo)          # every rank holds the whole merged state: digest the own share
+    def result_digest():
+        if unique:
+            if world > 1 and not peer_fold:
+                part = h.unique_checksum(r_lo, r_hi - r_lo)          # every rank holds the whole merged state: digest the own share
+            else:
+                part = h.unique_checksum(r_lo, r_hi - r_lo) if world > 1 else h.unique_checksum()
         else:
-            part = h.unique_checksum(r_lo, r_hi - r_lo) if world > 1 else h.unique_checksum()
-    else:
-        part = matcher.hits_checksum(h.match_all())
-    if world > 1:
-        parts = [None] * world
-        dist.all_gather_object(parts, int(part))
-        digest = sum(parts) & 0xFFFFFFFFFFFFFFFF
-    else:
-        digest = part & 0xFFFFFFFFFFFFFFFF
+            part = matcher.hits_checksum(h.match_all())
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, int(part))
+            return sum(parts) & 0xFFFFFFFFFFFFFFFF
+        return part & 0xFFFFFFFFFFFFFFFF
+
+    digest = result_digest()
     expected = EXPECTED_DIGEST.get(args.workload)
     digest_ok = None if (expected is None or args.as_rank) else (digest == expected)
 
@@ -705,26 +710,51 @@ def main():
             gather = rdist.ShardedUpload(sections, dev)
             gather_text = rdist.ShardedUpload([("words", h_w.view(torch.uint8)), ("nmask", h_m.view(torch.uint8))], dev)
 
-        e2e_phase = {"h2d_reads_ms": [], "h2d_text_ms": [], "pack_ms": [], "index_ms": [], "scan_ms": [], "fold_ms": [], "d2h_ms": [],
+        e2e_phase = {"h2d_reads_ms": [], "h2d_text_ms": [], "pack_ms": [], "index_ms": [], "scan_ms": [], "part_ms": [], "probe_ms": [], "fold_ms": [], "d2h_ms": [],
                      "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": [], "api_exchange_ms": [], "api_get_ms": []}
+
+        text_first = args.e2e_order == "text-first"
 
         def step_host():
             t0 = time.perf_counter()
-            if gather is not None:
+            if gather is not None and text_first:
+                # text first: its records are formed (real_gpu_prepare_scan, a stream of its own) while the reads are uploaded and gathered
+                d = gather_text.run()
+                h.set_text_device(d["words"].data_ptr(), d["nmask"].data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+                h.prepare_scan(L)
+                t1 = time.perf_counter()
+                d = gather.run()
+                h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
+                                          d_quality=d["qual"].data_ptr() if "qual" in d else None)
+                t2 = time.perf_counter()
+                t_text, t_reads = t1 - t0, t2 - t1
+            elif gather is not None:
                 d = gather.run()
                 h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
                                           d_quality=d["qual"].data_ptr() if "qual" in d else None)
                 d = gather_text.run()             # upload + all-gather of the text while the index build runs
                 h.set_text_device(d["words"].data_ptr(), d["nmask"].data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+                t2 = time.perf_counter()
+                t_text, t_reads = 0.0, t2 - t0
+            elif text_first:
+                # text first (real_gpu_set_text_async: the copies are only enqueued; the pinned buffers stay untouched until the match
+                # call has returned): the partition kernels of the scan (real_gpu_prepare_scan) start when the words have arrived and
+                # run while the reads cross PCIe; the wildcard mask, which the probe alone reads, travels behind the reads, under the
+                # index build
+                h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
+                h.prepare_scan(L)
+                t1 = time.perf_counter()
+                h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
+                t2 = time.perf_counter()
+                t_text, t_reads = t1 - t0, t2 - t1
             else:
                 h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
                 t1 = time.perf_counter()
                 # the copies of the text are enqueued (real_gpu_set_text_async): the partition of the scan starts when the words have
                 # arrived, the wildcard mask travels meanwhile; the pinned buffers stay untouched until the match call has returned
                 h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
-            t2 = time.perf_counter()
-            if gather is not None:
-                t1 = t2
+                t2 = time.perf_counter()
+                t_text, t_reads = t2 - t1, t1 - t0
             t4 = t3 = t2
             if unique:
                 h.match_unique()
@@ -746,7 +776,7 @@ def main():
                 st = h.stats()
                 d2h[0] = nh * 16
             t5 = time.perf_counter()
-            st.update(api_set_reads_ms=(t1 - t0) * 1e3, api_set_text_ms=(t2 - t1) * 1e3, api_match_ms=(t3 - t2) * 1e3,
+            st.update(api_set_reads_ms=t_reads * 1e3, api_set_text_ms=t_text * 1e3, api_match_ms=(t3 - t2) * 1e3,
                       api_exchange_ms=(t4 - t3) * 1e3, api_get_ms=(t5 - t4) * 1e3)
             return st
 
@@ -756,11 +786,17 @@ def main():
 
         e_steps = max(1, min(args.steps, 3))
         e_ms, _ = timed(step_host, e_steps, 1, collect_e2e)
+        # the state the last end-to-end step left on the device must be the one of the device-resident steps
+        e2e_digest = result_digest()
+        if e2e_digest != digest:
+            print("bench: the end-to-end leg produced another result (digest %016x, device-resident %016x)" % (e2e_digest, digest), file=sys.stderr)
+            sys.exit(3)
         h2d = R * L4 + R + (R * L if qual is not None else 0) + np_w.nbytes + np_m.nbytes + rs.nbytes
         if gather is not None:
             h2d = gather.chunk + gather_text.chunk + rs.nbytes          # per rank; the rest arrives over NVLink
         e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-               "ms_per_step": e_ms / e_steps, "steps": e_steps, "phases_ms": {k: statistics.mean(v) for k, v in e2e_phase.items() if v},
+               "ms_per_step": e_ms / e_steps, "steps": e_steps, "order": args.e2e_order, "digest_ok": True, "prepared_scans": int(h.stats().get("prepared_scans", 0)),
+               "phases_ms": {k: statistics.mean(v) for k, v in e2e_phase.items() if v},
                "input": "host buffers: text 2 bit/base + N mask, reads 2 bit/base (the reference's rewritten pattern file layout), "
                         "qualities 1 byte/base when scoring; result read back to pinned host memory"
                         + ("; every rank uploads 1/%d of the bytes, NCCL all-gather over NVLink for the rest (h2d_bytes_per_step is per rank)" % world

@@ -119,6 +119,8 @@ typedef struct
         uint64_t n_hits;        /* hits emitted */
         float fold_ms;          /* real_gpu_fold_unique*: push + hand-over + merge */
         float probe_ms;         /* the probe kernels' part of scan_ms (the rest is the partition of the text positions) */
+        float part_ms;          /* the partition kernels of the last scan; part of scan_ms unless real_gpu_prepare_scan ran them ahead */
+        uint32_t prepared_scans; /* scans of this handle that found their records formed by real_gpu_prepare_scan */
 } real_gpu_stats;
 
 int real_gpu_abi_version(void);
@@ -158,6 +160,16 @@ int real_gpu_set_text_async(real_gpu * h, uint32_t fileid,
                             uint64_t n_total, uint64_t shard_begin, uint64_t shard_len,
                             uint64_t own_begin, uint64_t own_end,
                             const uint64_t * record_starts, uint32_t nrecords);
+/* Text first, reads second: forms the scan's records of the current text NOW -- the partition kernels (K3, step 1) are enqueued
+ * on a stream of their own, behind the arrival of the words of a real_gpu_set_text_async, and the call returns at once -- so
+ * that they run while a following real_gpu_set_reads* call moves the reads over PCIe (the partition needs the text only; the
+ * index build needs all the reads).  max_read_len = the longest read of the set that will be matched (it bounds the last seed
+ * window of a text shard).  The next real_gpu_match_* call uses the records if it would form the very same ones (same text,
+ * shard, bucket split, window range) and forms its own otherwise: a hint, never a change of the result.  One scan per call;
+ * nothing is prepared (and REAL_GPU_OK returned) when the text needs several chunks or the handle exchanges records with
+ * peers (real_gpu_comm_*).  The order set_text_async -> prepare_scan -> set_reads* -> match also sends the text's wildcard
+ * mask behind the reads (it is read by the probe only). */
+int real_gpu_prepare_scan(real_gpu * h, uint32_t max_read_len);
 /* Same, with words/nmask already resident in device memory (record_starts stays a host pointer). */
 int real_gpu_set_text_device(real_gpu * h, uint32_t fileid,
                              const uint64_t * d_words, const uint64_t * d_nmask,

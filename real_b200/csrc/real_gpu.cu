@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cfloat>
 #include <vector>
+#include <functional>
 
 using namespace realgpu;
 
@@ -57,6 +58,22 @@ struct real_gpu
         cudaEvent_t evc[2];
         cudaEvent_t ev_words;          // real_gpu_set_text_async: the text words are on the device (the partition may start; the probe waits for evc[1])
         bool text_pending;             // an asynchronous text copy has been enqueued and not yet waited for by the host
+        // real_gpu_set_text_async leaves the copy of the wildcard mask to the next call that can place it: behind the reads of a
+        // real_gpu_set_reads* call that follows (the index build needs the reads, the mask is read by the probe only) or, at the
+        // latest, at the start of the scan
+        const uint64_t * mask_src; uint64_t mask_words; bool mask_deferred;
+        // real_gpu_prepare_scan: the text records formed ahead of the match call, on a stream of their own
+        struct Prepared
+        {
+                bool valid, inflight;
+                uint64_t x_begin, x_end, win_begin, win_end, chunk_cap;
+                uint32_t bucket_bits, own_b_lo, own_b_cnt;
+                bool own_list;
+                cudaEvent_t ev0, done;
+                Prepared() : valid(false), inflight(false), x_begin(0), x_end(0), win_begin(0), win_end(0), chunk_cap(0), bucket_bits(0), own_b_lo(0), own_b_cnt(0),
+                             own_list(false), ev0(nullptr), done(nullptr) {}
+        } prep;
+        cudaStream_t st3;              // the partition kernels of real_gpu_prepare_scan
         std::vector<cudaEvent_t> evp;  // pairs around the probe kernel of every chunk of a scan (stats.probe_ms)
         bool fused_build;              // the current tables were built by build_tables_fused (entry arrays in item numbering)
         bool build_pending;            // the index build of the current read set has been enqueued but not yet waited for
@@ -167,6 +184,7 @@ struct real_gpu
                 memset(&stats, 0, sizeof(stats));
                 for ( int i = 0; i < 8; ++i ) ev[i] = nullptr;
                 evc[0] = evc[1] = nullptr; ev_words = nullptr; text_pending = false;
+                mask_src = nullptr; mask_words = 0; mask_deferred = false; st3 = nullptr;
                 for ( int i = 0; i < 8; ++i ) stage_buf[i] = nullptr;
                 for ( int i = 0; i < 4; ++i ) stage_st[i] = nullptr;
         }
@@ -283,13 +301,31 @@ void h2d_from_host(real_gpu * h, void * dst, const void * src, size_t nbytes, cu
 // text
 // ---------------------------------------------------------------------------------------------
 
+// enqueues the copy of the wildcard mask real_gpu_set_text_async has left to a later call
+void flush_mask(real_gpu * h)
+{
+        if ( ! h->mask_deferred ) return;
+        h->mask_deferred = false;
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, h->mask_src, h->mask_words * 8, cudaMemcpyHostToDevice, h->st2));
+        RG_CUDA(cudaEventRecord(h->evc[1], h->st2));
+}
+
 // waits (on the host) for a text copy real_gpu_set_text_async has left in flight
 void finish_text(real_gpu * h)
 {
         if ( ! h->text_pending ) return;
+        flush_mask(h);
         h->text_pending = false;
         RG_CUDA(cudaEventSynchronize(h->evc[1]));
         h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);
+}
+
+// the records real_gpu_prepare_scan has formed (or is forming) are given up: the text, the shard or the buffers change
+void drop_prepared(real_gpu * h)
+{
+        if ( h->prep.inflight ) cudaEventSynchronize(h->prep.done);
+        h->prep.inflight = false;
+        h->prep.valid = false;
 }
 
 int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const uint64_t * nmask, bool on_device,
@@ -297,6 +333,7 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
                     const uint64_t * record_starts, uint32_t nrecords, bool async_copy = false)
 {
         finish_text(h);
+        drop_prepared(h);
         if ( ! words || ! nmask || ! record_starts || nrecords == 0 )
                 return fail(h, REAL_GPU_E_ARG, "set_text: null pointer or no records");
         if ( shard_begin % 64 )
@@ -337,8 +374,17 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
         RG_CUDA(cudaMemcpyAsync(h->rec.p, record_starts, (size_t)(nrecords + 1) * 8, cudaMemcpyHostToDevice, h->st2));
         RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, words, nw * 8, kind, h->st2));
         RG_CUDA(cudaEventRecord(h->ev_words, h->st2));
-        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, nmask, nmw * 8, kind, h->st2));
-        RG_CUDA(cudaEventRecord(h->evc[1], h->st2));
+        if ( async_copy && ! on_device )
+        {
+                // the mask is read by the probe only: its copy is placed by flush_mask -- behind the reads of a real_gpu_set_reads*
+                // call that comes next (text first, reads second: the partition runs while the reads arrive), else when the scan starts
+                h->mask_src = nmask; h->mask_words = nmw; h->mask_deferred = true;
+        }
+        else
+        {
+                RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, nmask, nmw * 8, kind, h->st2));
+                RG_CUDA(cudaEventRecord(h->evc[1], h->st2));
+        }
         if ( async_copy )
                 h->text_pending = true;                 // real_gpu_set_text_async: the scan waits on the device, the host at its end
         else
@@ -368,6 +414,7 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
         if ( ntiles >= (1ULL << 31) )
                 return fail(h, REAL_GPU_E_LIMIT, "set_text_fasta: file longer than 2^43 bytes");
         finish_text(h);
+        drop_prepared(h);
         h->have_text = false;
         h->fa_rec_starts.clear(); h->fa_rec_nl.clear();
         *n_bases = 0; *nrecords = 0;
@@ -911,147 +958,272 @@ void comm_wait(real_gpu * h, uint32_t slot, uint32_t epoch, long long wait_ms)
         RG_KERNEL_CHECK(); launch_count(h);
 }
 
+// What a scan decides before its chunk loop: the windows it evaluates, the bucket bits, the positions per chunk, its buffers
+// and the shapes of its kernels.  real_gpu_prepare_scan makes the same plan ahead of the match call (prepare = true: the read
+// set is not known yet, the finest bucket split is taken).
+struct ScanPlan
+{
+        ScanParams P;
+        uint64_t x_begin, x_end, chunk_cap, ntiles;
+        uint32_t * meta;
+        bool sharded, own_only, own_list;
+        int occ_p, occ_s, occ_b;
+        size_t psmem, ssmem, bsmem;
+        long long wait_ms;
+        typedef void (*probe_fn)(const ScanParams);
+        probe_fn probe;
+};
+
+void plan_scan(real_gpu * h, int mode, bool prepare, ScanPlan & S)
+{
+        ScanParams & P = S.P;
+        fill_scan_params(h, P, mode);
+        uint64_t const first_tile = P.x_begin / SC_TILE_POS, end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
+        S.ntiles = (P.x_end > P.x_begin) ? (end_tile - first_tile) : 0;
+        S.x_begin = P.x_begin; S.x_end = P.x_end; S.chunk_cap = 0; S.meta = nullptr;
+        S.sharded = S.own_only = S.own_list = false;
+        if ( ! S.ntiles ) return;
+
+        // buckets: cut the tables into key-prefix slices that stay resident in L2 while a bucket is probed
+        uint64_t table_bytes = 0;
+        uint32_t const maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
+        for ( int t = 0; t < 3; ++t )
+                if ( P.tab[t].nlists )
+                        table_bytes += h->tab[t].bitmap_bytes + h->tab[t].nentries * sizeof(Entry);
+        uint32_t bbits = 0;
+        if ( h->pass_bits_override >= 0 )
+                bbits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
+        else if ( prepare )
+                bbits = maxbits;
+        else
+                while ( bbits < maxbits && (table_bytes >> bbits) > h->l2_slice_bytes ) ++bbits;
+        P.bucket_bits = bbits;
+        if ( const char * e = getenv("REAL_GPU_DEBUG") ) P.debug_flags = (uint32_t)atoi(e);
+
+        real_gpu::Comm & CM = h->comm;
+        bool const sharded = S.sharded = CM.nranks > 1 && CM.window.p;          // records exchanged through peer memory
+        bool const own_only = S.own_only = CM.nranks > 1 && ! CM.window.p;      // bucket shard: this handle keeps the positions of its own buckets
+        if ( own_only )
+        {
+                if ( maxbits < 8 ) throw CudaError("bucket shards need seeds of at least 16 bases");
+                if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
+                        throw CudaError("bucket shards: every rank must be given the whole text (the ranks split the signature space, not the text)");
+                P.bucket_bits = 8;
+                P.own_b_lo = CM.bucket_lo[CM.rank];
+                P.own_b_cnt = CM.bucket_lo[CM.rank + 1] - CM.bucket_lo[CM.rank];
+        }
+        if ( sharded )
+        {
+                if ( ! CM.connected ) throw CudaError("sharded tables: real_gpu_comm_connect has not been called");
+                if ( maxbits < 8 ) throw CudaError("sharded tables need seeds of at least 16 bases");
+                if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
+                        throw CudaError("sharded tables: every rank must be given the whole text (the ranks split the positions among themselves)");
+                P.bucket_bits = 8;
+        }
+        uint64_t const x_begin = P.x_begin, x_end = P.x_end;
+        // Positions partitioned at a time.  One handle with the whole signature space: as many as fit -- the records of
+        // C3's 3.1 G positions take 50 GB of the 180 -- because every chunk walks through all the tables again (three chunks
+        // of 2^30 positions read the entries three times over: 105 GB of DRAM traffic instead of 10, 2 ms of the C3 scan).
+        // Equal chunks when the text does not fit; REAL_GPU_CHUNK_MPOS overrides.
+        uint64_t chunk_max = sharded ? CM.round_positions : std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
+        if ( ! sharded && ! own_only && h->chunk_positions == 0 )
+        {
+                uint64_t const span = ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS;
+                uint64_t const pad = (uint64_t)SC_MAX_BUCKETS * SC_UNIT;
+                uint64_t fit = SC_MAX_CHUNK;
+                // the memory query costs milliseconds (3.7 ms measured on C1, whose whole scan takes 0.5): it is made only
+                // when the record buffer already held is too small for the span
+                if ( (std::min<uint64_t>(span, SC_MAX_CHUNK) + pad) * sizeof(uint4) + 64 > h->rec_win.bytes )
+                {
+                        size_t free_b = 0, total_b = 0;
+                        RG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                        // the buffer already held counts as room; ahead of the match call the read set and its tables are still to come
+                        uint64_t const room = (uint64_t)((free_b + h->rec_win.bytes) * (prepare ? 0.4 : 0.6)) / sizeof(uint4);
+                        fit = std::max<uint64_t>(SC_TILE_POS, std::min<uint64_t>(SC_MAX_CHUNK, room > pad ? room - pad : 0) / SC_TILE_POS * SC_TILE_POS);
+                }
+                uint64_t const nchunks = (span + fit - 1) / fit;
+                chunk_max = std::max<uint64_t>(SC_TILE_POS, ((span + nchunks - 1) / nchunks + SC_TILE_POS - 1) / SC_TILE_POS * SC_TILE_POS);
+        }
+        else if ( h->chunk_positions == 0 )
+                chunk_max = sharded ? CM.round_positions : SC_MAX_ROUND;
+        uint64_t const chunk_cap = S.chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
+        if ( prepare && (sharded || x_end - x_begin > chunk_cap) ) return;      // nothing to form ahead: the caller gives up
+        // entries are touched about once per chunk and bucket: several chunks stream them past the probed slot words
+        // (evict_first); a single chunk re-uses every entry line about nine times while its bucket is probed (evict_normal)
+        if ( ! getenv("REAL_GPU_DEBUG") && x_end - x_begin <= chunk_cap ) P.debug_flags |= 4;
+        uint32_t * meta = nullptr;
+        if ( sharded )
+        {
+                // everything was allocated by real_gpu_comm_init: no allocation may happen between the hand-over kernels
+                meta = ptr<uint32_t>(h->part_meta);
+                P.recs = reinterpret_cast<uint4 *>(CM.base[CM.rank] + CM.recs_off);
+                P.nranks = CM.nranks; P.rank = CM.rank; P.seg_cap = CM.seg_cap;
+                for ( uint32_t r = 0; r <= CM.nranks; ++r ) P.bucket_lo[r] = CM.bucket_lo[r];
+                for ( uint32_t r = 0; r < CM.nranks; ++r )
+                {
+                        P.peer_recs[r] = reinterpret_cast<uint4 *>(CM.base[r] + CM.recs_off);
+                        P.peer_meta[r] = reinterpret_cast<uint32_t *>(CM.base[r] + CM.meta_off);
+                }
+                P.pair_grab = ptr<uint32_t>(CM.pairs); P.pair_rec = ptr<uint32_t>(CM.pairs) + 1024;
+                P.npairs = (CM.bucket_lo[CM.rank + 1] - CM.bucket_lo[CM.rank]) * CM.nranks;
+        }
+        else
+        {
+                dev_reserve(h, h->rec_win, (chunk_cap + (uint64_t)SC_MAX_BUCKETS * SC_UNIT) * sizeof(uint4) + 64);
+                dev_reserve(h, h->part_meta, (1100 + 256 * SC_CURSOR_STRIDE) * 4);
+                meta = ptr<uint32_t>(h->part_meta);
+                P.recs = ptr<uint4>(h->rec_win);
+                P.peer_recs[0] = P.recs;
+        }
+        S.meta = meta;
+        P.bucket_count = meta;
+        P.bucket_start = meta + 256;
+        P.unit_counter = meta + 256 + 520;
+        P.bucket_cursor = meta + 1088;
+
+        S.psmem = sizeof(HistSmem); S.ssmem = sizeof(ScatterSmem); S.bsmem = sizeof(ProbeSmem);
+        // Bucket shard: with few own buckets (four ranks or more) one light pass lists the kept positions and counts them per
+        // bucket, and the staged scatter runs on the list; with many (two ranks: half of all positions are kept) listing
+        // costs more than it saves, and the dense kernels run with a filter on the bucket (measured, profiles/r02_*)
+        bool const own_list = S.own_list = own_only && P.own_b_cnt <= (uint32_t)h->own_list_max;
+        if ( own_list )
+        {
+                // the positions of a chunk this rank keeps, 4 bytes each (all of them if the text falls into its buckets only)
+                dev_reserve(h, h->own_list, chunk_cap * 4 + 64);
+                P.list = ptr<uint32_t>(h->own_list);
+                P.list_count = reinterpret_cast<unsigned long long *>(meta + 780);
+        }
+        RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.psmem));
+        RG_CUDA(cudaFuncSetAttribute(k_part_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.ssmem));
+        RG_CUDA(cudaFuncSetAttribute(k_part_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.ssmem));
+        bool const wide = h->prm.seedl > 32;
+        typedef ScanPlan::probe_fn probe_fn;
+        bool const packed_src = h->src_packed != nullptr;
+        S.probe = wide ? (packed_src ? (probe_fn)k_bucket_probe<true, true> : (probe_fn)k_bucket_probe<true, false>)
+                       : (packed_src ? (probe_fn)k_bucket_probe<false, true> : (probe_fn)k_bucket_probe<false, false>);
+        RG_CUDA(cudaFuncSetAttribute(S.probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bsmem));
+        int occ_p = 0, occ_b = 0, occ_s = 0;
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, S.psmem));
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, own_list ? k_part_scatter<true> : k_part_scatter<false>, PS_THREADS, S.ssmem));
+        RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, S.probe, SC_THREADS, S.bsmem));
+        if ( occ_p < 1 ) occ_p = 1;
+        if ( occ_s < 1 ) occ_s = 1;
+        if ( occ_b < 1 ) occ_b = 1;
+        // more than REAL_PROBE_MINB CTAs per SM make the probe slower (measured: 87 vs 74 ms scan on C3 with four): the grabs
+        // of more warps spread over more of the bucket order and the probed slices lose their place in L2
+        if ( occ_b > REAL_PROBE_MINB ) occ_b = REAL_PROBE_MINB;
+        if ( const char * e = getenv("REAL_GPU_PROBE_OCC") ) occ_b = std::max(1, atoi(e));
+        S.occ_p = occ_p; S.occ_s = occ_s; S.occ_b = occ_b;
+        S.wait_ms = 30000;             // a peer that never arrives is reported, not waited for forever
+        if ( const char * e = getenv("REAL_GPU_COMM_TIMEOUT_MS") ) S.wait_ms = atoll(e);
+}
+
+// the partition kernels of one chunk (P.x_begin .. P.x_end) on stream st: bucket histogram (or the kept-position list of a
+// bucket shard), bucket offsets, staged scatter of the records.  nprobed: where a bucket shard counts the positions it kept.
+void launch_partition(real_gpu * h, ScanPlan const & S, ScanParams const & P, cudaStream_t st, std::function<void()> const & mark)
+{
+        real_gpu::Comm & CM = h->comm;
+        bool const any = P.x_end > P.x_begin;
+        uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
+        unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * S.occ_p);
+        RG_CUDA(cudaMemsetAsync(S.meta, 0, 256 * 4, st));
+        if ( S.own_list ) RG_CUDA(cudaMemsetAsync(P.list_count, 0, 8, st));
+        if ( any && S.own_list )
+        {
+                uint64_t const oft = P.x_begin / OL_TILE_POS, oet = (P.x_end + OL_TILE_POS - 1) / OL_TILE_POS;
+                k_own_list<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * 8), OL_THREADS, 0, st>>>(P);
+                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
+        }
+        else if ( any )
+        {
+                k_part_hist<<<pgrid, SC_THREADS, S.psmem, st>>>(P);
+                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
+        }
+        mark();
+        if ( S.sharded )
+        {
+                // the owners must have consumed the previous round before their record areas are written again
+                comm_wait(h, 1, CM.epoch - 1, S.wait_ms);
+        }
+        mark();
+        k_part_offsets<<<1, SC_MAX_BUCKETS, 0, st>>>(P);
+        RG_KERNEL_CHECK();
+        if ( any )
+        {
+                uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
+                unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * S.occ_s);
+                if ( S.own_list )
+                        k_part_scatter<true><<<(unsigned)(h->sm_count * S.occ_s), PS_THREADS, S.ssmem, st>>>(P);
+                else
+                        k_part_scatter<false><<<sgrid, PS_THREADS, S.ssmem, st>>>(P);
+                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
+        }
+        launch_count(h);               // k_part_offsets
+        h->stats.scan_launches += 1;
+}
+
+// real_gpu_prepare_scan: the partition of the current text, enqueued on a stream of its own behind the arrival of the words
+void prepare_scan(real_gpu * h, uint32_t max_read_len)
+{
+        drop_prepared(h);
+        uint32_t const seedl = std::min<uint32_t>(h->prm.seedl, 32);
+        h->F = seedl / 4; h->keybits = seedl;
+        uint32_t const kept_maxlen = h->maxlen;
+        h->maxlen = max_read_len;
+        ScanPlan S;
+        try { plan_scan(h, 0, true, S); } catch ( ... ) { h->maxlen = kept_maxlen; throw; }
+        h->maxlen = kept_maxlen;
+        if ( ! S.ntiles || S.sharded || S.x_end - S.x_begin > S.chunk_cap ) return;         // several chunks, or records that cross NVLink: formed by the scan itself
+        real_gpu::Prepared & R = h->prep;
+        if ( ! h->st3 ) RG_CUDA(cudaStreamCreateWithFlags(&h->st3, cudaStreamNonBlocking));
+        if ( ! R.ev0 ) { RG_CUDA(cudaEventCreate(&R.ev0)); RG_CUDA(cudaEventCreate(&R.done)); }
+        ScanParams & P = S.P;
+        P.pos_base = S.x_begin;
+        P.nprobed = reinterpret_cast<unsigned long long *>(S.meta + 784);          // taken over by the scan (bucket shards count their kept positions)
+        if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st3, h->ev_words, 0));
+        RG_CUDA(cudaMemsetAsync(S.meta + 784, 0, 8, h->st3));
+        RG_CUDA(cudaEventRecord(R.ev0, h->st3));
+        launch_partition(h, S, P, h->st3, [](){});
+        RG_CUDA(cudaEventRecord(R.done, h->st3));
+        R.x_begin = S.x_begin; R.x_end = S.x_end; R.win_begin = P.win_begin; R.win_end = P.win_end; R.chunk_cap = S.chunk_cap;
+        R.bucket_bits = P.bucket_bits; R.own_b_lo = P.own_b_lo; R.own_b_cnt = P.own_b_cnt; R.own_list = S.own_list;
+        R.valid = true; R.inflight = true;
+}
+
 // launches K3 once; returns the number of hits the kernel counted
 uint64_t run_scan(real_gpu * h, int mode)
 {
         dev_reserve(h, h->counters, 8 * 8);
         RG_CUDA(cudaMemsetAsync(h->counters.p, 0, 8 * 8, h->st));
-        ScanParams P;
-        fill_scan_params(h, P, mode);
-        uint64_t const first_tile = P.x_begin / SC_TILE_POS, end_tile = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
-        uint64_t const ntiles = (P.x_end > P.x_begin) ? (end_tile - first_tile) : 0;
-        if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st, h->ev_words, 0));      // asynchronous text copy: the words must have arrived
+        ScanPlan S;
+        plan_scan(h, mode, false, S);
+        ScanParams & P = S.P;
+        uint64_t const ntiles = S.ntiles;
+        if ( h->text_pending )
+        {
+                flush_mask(h);                                                  // the wildcard mask follows the words, unless it is on its way already
+                RG_CUDA(cudaStreamWaitEvent(h->st, h->ev_words, 0));            // asynchronous text copy: the words must have arrived
+        }
+        // records formed ahead by real_gpu_prepare_scan serve this scan if it would form the very same ones
+        real_gpu::Prepared & R = h->prep;
+        bool const use_prep = R.valid && ntiles && ! S.sharded && S.x_end - S.x_begin <= S.chunk_cap
+                              && R.x_begin == S.x_begin && R.x_end == S.x_end && R.win_begin == P.win_begin && R.win_end == P.win_end
+                              && R.bucket_bits >= P.bucket_bits && R.own_b_lo == P.own_b_lo && R.own_b_cnt == P.own_b_cnt && R.own_list == S.own_list;
+        if ( R.inflight ) RG_CUDA(cudaStreamWaitEvent(h->st, R.done, 0));        // either way: the record buffer is written or read next
+        bool const was_inflight = R.inflight;
+        R.valid = false;                // one scan per preparation: every scan leaves the records of its own last chunk behind
         RG_CUDA(cudaEventRecord(h->ev[5], h->st));
         size_t nprobe_ev = 0;
         if ( ntiles )
         {
-                // buckets: cut the tables into key-prefix slices that stay resident in L2 while a bucket is probed
-                uint64_t table_bytes = 0;
-                uint32_t const maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
-                for ( int t = 0; t < 3; ++t )
-                        if ( P.tab[t].nlists )
-                                table_bytes += h->tab[t].bitmap_bytes + h->tab[t].nentries * sizeof(Entry);
-                uint32_t bbits = 0;
-                if ( h->pass_bits_override >= 0 )
-                        bbits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
-                else
-                        while ( bbits < maxbits && (table_bytes >> bbits) > h->l2_slice_bytes ) ++bbits;
-                P.bucket_bits = bbits;
-                if ( const char * e = getenv("REAL_GPU_DEBUG") ) P.debug_flags = (uint32_t)atoi(e);
-
                 real_gpu::Comm & CM = h->comm;
-                bool const sharded = CM.nranks > 1 && CM.window.p;          // records exchanged through peer memory
-                bool const own_only = CM.nranks > 1 && ! CM.window.p;       // bucket shard: this handle keeps the positions of its own buckets
-                if ( own_only )
+                bool const sharded = S.sharded, own_only = S.own_only;
+                uint64_t const x_begin = S.x_begin, x_end = S.x_end, chunk_cap = S.chunk_cap;
+                if ( use_prep )
                 {
-                        if ( maxbits < 8 ) throw CudaError("bucket shards need seeds of at least 16 bases");
-                        if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
-                                throw CudaError("bucket shards: every rank must be given the whole text (the ranks split the signature space, not the text)");
-                        P.bucket_bits = 8;
-                        P.own_b_lo = CM.bucket_lo[CM.rank];
-                        P.own_b_cnt = CM.bucket_lo[CM.rank + 1] - CM.bucket_lo[CM.rank];
+                        P.bucket_bits = R.bucket_bits;
+                        RG_CUDA(cudaMemcpyAsync(ptr<unsigned long long>(h->counters) + 4, S.meta + 784, 8, cudaMemcpyDeviceToDevice, h->st));
                 }
-                if ( sharded )
-                {
-                        if ( ! CM.connected ) throw CudaError("sharded tables: real_gpu_comm_connect has not been called");
-                        if ( maxbits < 8 ) throw CudaError("sharded tables need seeds of at least 16 bases");
-                        if ( h->shard_begin != 0 || h->shard_len != h->n_total || h->own_begin != 0 || h->own_end != h->n_total )
-                                throw CudaError("sharded tables: every rank must be given the whole text (the ranks split the positions among themselves)");
-                        P.bucket_bits = 8;
-                }
-                uint64_t const x_begin = P.x_begin, x_end = P.x_end;
-                // Positions partitioned at a time.  One handle with the whole signature space: as many as fit -- the records of
-                // C3's 3.1 G positions take 50 GB of the 180 -- because every chunk walks through all the tables again (three chunks
-                // of 2^30 positions read the entries three times over: 105 GB of DRAM traffic instead of 10, 2 ms of the C3 scan).
-                // Equal chunks when the text does not fit; REAL_GPU_CHUNK_MPOS overrides.
-                uint64_t chunk_max = sharded ? CM.round_positions : std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
-                if ( ! sharded && ! own_only && h->chunk_positions == 0 )
-                {
-                        uint64_t const span = ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS;
-                        uint64_t const pad = (uint64_t)SC_MAX_BUCKETS * SC_UNIT;
-                        uint64_t fit = SC_MAX_CHUNK;
-                        // the memory query costs milliseconds (3.7 ms measured on C1, whose whole scan takes 0.5): it is made only
-                        // when the record buffer already held is too small for the span
-                        if ( (std::min<uint64_t>(span, SC_MAX_CHUNK) + pad) * sizeof(uint4) + 64 > h->rec_win.bytes )
-                        {
-                                size_t free_b = 0, total_b = 0;
-                                RG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-                                uint64_t const room = (uint64_t)((free_b + h->rec_win.bytes) * 0.6) / sizeof(uint4);     // the buffer already held counts as room
-                                fit = std::max<uint64_t>(SC_TILE_POS, std::min<uint64_t>(SC_MAX_CHUNK, room > pad ? room - pad : 0) / SC_TILE_POS * SC_TILE_POS);
-                        }
-                        uint64_t const nchunks = (span + fit - 1) / fit;
-                        chunk_max = std::max<uint64_t>(SC_TILE_POS, ((span + nchunks - 1) / nchunks + SC_TILE_POS - 1) / SC_TILE_POS * SC_TILE_POS);
-                }
-                else if ( h->chunk_positions == 0 )
-                        chunk_max = sharded ? CM.round_positions : SC_MAX_ROUND;
-                uint64_t const chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
-                // entries are touched about once per chunk and bucket: several chunks stream them past the probed slot words
-                // (evict_first); a single chunk re-uses every entry line about nine times while its bucket is probed (evict_normal)
-                if ( ! getenv("REAL_GPU_DEBUG") && x_end - x_begin <= chunk_cap ) P.debug_flags |= 4;
-                uint32_t * meta = nullptr;
-                if ( sharded )
-                {
-                        // everything was allocated by real_gpu_comm_init: no allocation may happen between the hand-over kernels
-                        meta = ptr<uint32_t>(h->part_meta);
-                        P.recs = reinterpret_cast<uint4 *>(CM.base[CM.rank] + CM.recs_off);
-                        P.nranks = CM.nranks; P.rank = CM.rank; P.seg_cap = CM.seg_cap;
-                        for ( uint32_t r = 0; r <= CM.nranks; ++r ) P.bucket_lo[r] = CM.bucket_lo[r];
-                        for ( uint32_t r = 0; r < CM.nranks; ++r )
-                        {
-                                P.peer_recs[r] = reinterpret_cast<uint4 *>(CM.base[r] + CM.recs_off);
-                                P.peer_meta[r] = reinterpret_cast<uint32_t *>(CM.base[r] + CM.meta_off);
-                        }
-                        P.pair_grab = ptr<uint32_t>(CM.pairs); P.pair_rec = ptr<uint32_t>(CM.pairs) + 1024;
-                        P.npairs = (CM.bucket_lo[CM.rank + 1] - CM.bucket_lo[CM.rank]) * CM.nranks;
-                }
-                else
-                {
-                        dev_reserve(h, h->rec_win, (chunk_cap + (uint64_t)SC_MAX_BUCKETS * SC_UNIT) * sizeof(uint4) + 64);
-                        dev_reserve(h, h->part_meta, (1100 + 256 * SC_CURSOR_STRIDE) * 4);
-                        meta = ptr<uint32_t>(h->part_meta);
-                        P.recs = ptr<uint4>(h->rec_win);
-                        P.peer_recs[0] = P.recs;
-                }
-                P.bucket_count = meta;
-                P.bucket_start = meta + 256;
-                P.unit_counter = meta + 256 + 520;
-                P.bucket_cursor = meta + 1088;
-
-                size_t const psmem = sizeof(HistSmem), ssmem = sizeof(ScatterSmem), bsmem = sizeof(ProbeSmem);
-                // Bucket shard: with few own buckets (four ranks or more) one light pass lists the kept positions and counts them per
-                // bucket, and the staged scatter runs on the list; with many (two ranks: half of all positions are kept) listing
-                // costs more than it saves, and the dense kernels run with a filter on the bucket (measured, profiles/r02_*)
-                bool const own_list = own_only && P.own_b_cnt <= (uint32_t)h->own_list_max;
-                if ( own_list )
-                {
-                        // the positions of a chunk this rank keeps, 4 bytes each (all of them if the text falls into its buckets only)
-                        dev_reserve(h, h->own_list, chunk_cap * 4 + 64);
-                        P.list = ptr<uint32_t>(h->own_list);
-                        P.list_count = reinterpret_cast<unsigned long long *>(meta + 780);
-                }
-                RG_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-                RG_CUDA(cudaFuncSetAttribute(k_part_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-                RG_CUDA(cudaFuncSetAttribute(k_part_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-                bool const wide = h->prm.seedl > 32;
-                typedef void (*probe_fn)(const ScanParams);
-                bool const packed_src = h->src_packed != nullptr;
-                probe_fn const probe = wide ? (packed_src ? (probe_fn)k_bucket_probe<true, true> : (probe_fn)k_bucket_probe<true, false>)
-                                            : (packed_src ? (probe_fn)k_bucket_probe<false, true> : (probe_fn)k_bucket_probe<false, false>);
-                RG_CUDA(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-                int occ_p = 0, occ_b = 0, occ_s = 0;
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_part_hist, SC_THREADS, psmem));
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, own_list ? k_part_scatter<true> : k_part_scatter<false>, PS_THREADS, ssmem));
-                RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, probe, SC_THREADS, bsmem));
-                if ( occ_p < 1 ) occ_p = 1;
-                if ( occ_s < 1 ) occ_s = 1;
-                if ( occ_b < 1 ) occ_b = 1;
-                // more than REAL_PROBE_MINB CTAs per SM make the probe slower (measured: 87 vs 74 ms scan on C3 with four): the grabs
-                // of more warps spread over more of the bucket order and the probed slices lose their place in L2
-                if ( occ_b > REAL_PROBE_MINB ) occ_b = REAL_PROBE_MINB;
-                if ( const char * e = getenv("REAL_GPU_PROBE_OCC") ) occ_b = std::max(1, atoi(e));
-                long long wait_ms = 30000;             // a peer that never arrives is reported, not waited for forever
-                if ( const char * e = getenv("REAL_GPU_COMM_TIMEOUT_MS") ) wait_ms = atoll(e);
-
                 h->stats.n_windows = 0;
                 // REAL_GPU_TRACE=1: per-round phase times on stderr (development)
                 bool const trace = getenv("REAL_GPU_TRACE") != nullptr;
@@ -1073,46 +1245,13 @@ uint64_t run_scan(real_gpu * h, int mode)
                                 ++CM.epoch;
                         }
                         if ( ! own_only ) h->stats.n_windows += P.x_end - P.x_begin;
-                        bool const any = P.x_end > P.x_begin;
-                        uint64_t const ft = P.x_begin / SC_TILE_POS, et = (P.x_end + SC_TILE_POS - 1) / SC_TILE_POS;
-                        unsigned const pgrid = (unsigned)std::min<uint64_t>(et - ft, (uint64_t)h->sm_count * occ_p);
-                        RG_CUDA(cudaMemsetAsync(meta, 0, 256 * 4, h->st));
-                        if ( own_list ) RG_CUDA(cudaMemsetAsync(P.list_count, 0, 8, h->st));
-                        if ( any && own_list )
-                        {
-                                uint64_t const oft = P.x_begin / OL_TILE_POS, oet = (P.x_end + OL_TILE_POS - 1) / OL_TILE_POS;
-                                k_own_list<<<(unsigned)std::min<uint64_t>(oet - oft, (uint64_t)h->sm_count * 8), OL_THREADS, 0, h->st>>>(P);
-                                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
-                        }
-                        else if ( any )
-                        {
-                                k_part_hist<<<pgrid, SC_THREADS, psmem, h->st>>>(P);
-                                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
-                        }
-                        mark();
-                        if ( sharded )
-                        {
-                                // the owners must have consumed the previous round before their record areas are written again
-                                comm_wait(h, 1, CM.epoch - 1, wait_ms);
-                        }
-                        mark();
-                        k_part_offsets<<<1, SC_MAX_BUCKETS, 0, h->st>>>(P);
-                        RG_KERNEL_CHECK();
-                        if ( any )
-                        {
-                                uint64_t const sft = P.x_begin / PS_TILE_POS, set = (P.x_end + PS_TILE_POS - 1) / PS_TILE_POS;
-                                unsigned const sgrid = (unsigned)std::min<uint64_t>(set - sft, (uint64_t)h->sm_count * occ_s);
-                                if ( own_list )
-                                        k_part_scatter<true><<<(unsigned)(h->sm_count * occ_s), PS_THREADS, ssmem, h->st>>>(P);
-                                else
-                                        k_part_scatter<false><<<sgrid, PS_THREADS, ssmem, h->st>>>(P);
-                                RG_KERNEL_CHECK(); launch_count(h); h->stats.scan_launches += 1;
-                        }
+                        if ( use_prep ) { mark(); mark(); }
+                        else launch_partition(h, S, P, h->st, mark);
                         mark();
                         if ( sharded )
                         {
                                 comm_signal(h, 0);
-                                comm_wait(h, 0, CM.epoch, wait_ms);
+                                comm_wait(h, 0, CM.epoch, S.wait_ms);
                                 k_comm_pairs<<<1, SC_PAIR_THREADS, 0, h->st>>>(P, reinterpret_cast<uint32_t *>(CM.base[CM.rank] + CM.meta_off));
                                 RG_KERNEL_CHECK(); launch_count(h);
                         }
@@ -1125,7 +1264,7 @@ uint64_t run_scan(real_gpu * h, int mode)
                         }
                         if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st, h->evc[1], 0));          // ... and now the wildcard mask
                         RG_CUDA(cudaEventRecord(h->evp[2 * nprobe_ev], h->st));
-                        probe<<<(unsigned)(h->sm_count * occ_b), SC_THREADS, bsmem, h->st>>>(P);
+                        S.probe<<<(unsigned)(h->sm_count * S.occ_b), SC_THREADS, S.bsmem, h->st>>>(P);
                         RG_KERNEL_CHECK();
                         RG_CUDA(cudaEventRecord(h->evp[2 * nprobe_ev + 1], h->st));
                         ++nprobe_ev;
@@ -1134,8 +1273,8 @@ uint64_t run_scan(real_gpu * h, int mode)
                         {
                                 comm_signal(h, 1);
                         }
-                        launch_count(h, 2);
-                        h->stats.scan_launches += 2;
+                        launch_count(h);
+                        h->stats.scan_launches += 1;
                 }
                 P.x_begin = x_begin; P.x_end = x_end;
                 if ( trace )
@@ -1154,10 +1293,14 @@ uint64_t run_scan(real_gpu * h, int mode)
         unsigned long long c[5] = {0, 0, 0, 0, 0};
         RG_CUDA(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->st));
         RG_CUDA(cudaStreamSynchronize(h->st));
+        R.inflight = false;
         h->stats.scan_ms = elapsed(h->ev[5], h->ev[6]);
         finish_text(h);
         h->stats.probe_ms = 0;
         for ( size_t i = 0; i < nprobe_ev; ++i ) h->stats.probe_ms += elapsed(h->evp[2*i], h->evp[2*i+1]);
+        // the partition kernels' time: part of scan_ms, unless the records were formed ahead (then it ran beside the transfer of the reads)
+        h->stats.part_ms = (use_prep && was_inflight) ? elapsed(R.ev0, R.done) : (use_prep ? 0.f : h->stats.scan_ms - h->stats.probe_ms);
+        h->stats.prepared_scans += use_prep ? 1 : 0;
         if ( ! ntiles ) h->stats.n_windows = 0;
         else if ( h->comm.nranks > 1 && ! h->comm.window.p ) h->stats.n_windows = c[4];     // bucket shard: the positions this handle kept
         if ( h->comm.nranks > 1 && h->comm.window.p )
@@ -1284,7 +1427,11 @@ int real_gpu_destroy(real_gpu * h)
 {
         if ( ! h ) return REAL_GPU_OK;
         cudaSetDevice(h->prm.device);
-        if ( h->text_pending ) cudaEventSynchronize(h->evc[1]);
+        if ( h->text_pending && ! h->mask_deferred ) cudaEventSynchronize(h->evc[1]);
+        if ( h->text_pending ) cudaStreamSynchronize(h->st2);
+        if ( h->prep.inflight ) cudaEventSynchronize(h->prep.done);
+        if ( h->prep.ev0 ) { cudaEventDestroy(h->prep.ev0); cudaEventDestroy(h->prep.done); }
+        if ( h->st3 ) cudaStreamDestroy(h->st3);
         DevBuf * all[] = { &h->text, &h->nmask, &h->rec, &h->mapped, &h->qual, &h->offs, &h->rpack, &h->rlen, &h->seeds, &h->usable, &h->usable_rank, &h->bad,
                            &h->rec_win, &h->rec_pos, &h->part_meta, &h->own_list, &h->large_list, &h->win_valid, &h->win_counts, &h->bounds, &h->gapres, &h->gaps, &h->boffs, &h->flags8, &h->ws_k0, &h->ws_v0, &h->ws_k1, &h->ws_v1, &h->ws_flags, &h->ws_hist, &h->ws_stmp, &h->ll, &h->hits_raw, &h->hits_seg, &h->hits_out, &h->hits_out16, &h->counters, &h->counts, &h->starts, &h->cursor, &h->scantmp, &h->info, &h->scores,
                            &h->fa_raw, &h->fa_sums, &h->fa_tbase, &h->fa_trec, &h->fa_recnl, &h->fa_tot,
@@ -1337,6 +1484,15 @@ int real_gpu_set_text_async(real_gpu * h, uint32_t fileid, const uint64_t * word
 {
         RG_API_BEGIN_ASYNC(h)
         return set_text_common(h, fileid, words, nmask, false, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords, true);
+        RG_API_END(h)
+}
+
+int real_gpu_prepare_scan(real_gpu * h, uint32_t max_read_len)
+{
+        RG_API_BEGIN_ASYNC(h)
+        if ( ! h->have_text ) return fail(h, REAL_GPU_E_STATE, "prepare_scan: no text set");
+        prepare_scan(h, max_read_len);
+        return REAL_GPU_OK;
         RG_API_END(h)
 }
 
@@ -1402,6 +1558,7 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
         }
         h->have_reads = false;
         h->nreads = nreads; h->total_bases = total; h->maxlen = maxlen;
+        if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st, h->ev_words, 0));   // one transfer after the other (see real_gpu_set_reads_packed)
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
         dev_reserve(h, h->mapped, total + 64);
         dev_reserve(h, h->offs, (nreads + 1) * 8);
@@ -1427,6 +1584,7 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
         int const brc = build_from_device(h);           // enqueued; waited for by the next call that needs the index
         RG_CUDA(cudaEventSynchronize(h->ev[1]));        // the caller's buffers have been copied
         h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
+        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }
@@ -1454,6 +1612,7 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
         h->stats.h2d_reads_ms = 0;
         int const brc = build_from_device(h);
         RG_CUDA(cudaEventSynchronize(h->ev[3]));        // the reads are packed: the caller's buffers are not referenced any more
+        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }
@@ -1485,6 +1644,9 @@ int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64
         else if ( uniform_length > 65535 ) return fail(h, REAL_GPU_E_LIMIT, "set_reads: read longer than 65535 bases");
         h->have_reads = false;
         h->nreads = nreads; h->total_bases = total; h->maxlen = maxlen;
+        // text words still on their way (real_gpu_set_text_async before the reads): one transfer after the other -- the partition
+        // of real_gpu_prepare_scan starts when the words are complete and runs while the reads arrive
+        if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st, h->ev_words, 0));
         RG_CUDA(cudaEventRecord(h->ev[0], h->st));
         dev_reserve(h, h->mapped, total_bytes + 64);
         dev_reserve(h, h->offs, (nreads + 1) * 8);
@@ -1523,6 +1685,7 @@ int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64
         int const brc = build_from_device(h);           // enqueued; waited for by the next call that needs the index
         RG_CUDA(cudaEventSynchronize(h->ev[1]));        // the caller's buffers (and the staging vectors above) have been copied
         h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
+        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }
@@ -1742,6 +1905,7 @@ int real_gpu_set_reads_packed_device(real_gpu * h, const uint8_t * d_packed, uin
         h->stats.h2d_reads_ms = 0;
         int const brc = build_from_device(h);
         RG_CUDA(cudaEventSynchronize(h->ev[3]));        // the reads are packed: the caller's buffers are not referenced any more
+        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }
@@ -2147,6 +2311,7 @@ int real_gpu_comm_init(real_gpu * h, uint32_t rank, uint32_t nranks, uint64_t ro
         if ( nranks < 1 || nranks > (uint32_t)SC_MAX_RANKS || rank >= nranks ) return fail(h, REAL_GPU_E_ARG, "comm_init: rank/nranks out of range (at most 8 ranks)");
         real_gpu::Comm & CM = h->comm;
         if ( CM.window.p ) return fail(h, REAL_GPU_E_STATE, "comm_init: already initialised");
+        drop_prepared(h);
         if ( round_positions == 0 ) round_positions = SC_MAX_ROUND;
         round_positions = std::min<uint64_t>(SC_MAX_ROUND, ((round_positions + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
         CM.nranks = nranks; CM.rank = rank; CM.epoch = 0; CM.round_positions = round_positions; CM.connected = false;
@@ -2186,6 +2351,7 @@ int real_gpu_set_bucket_shard(real_gpu * h, uint32_t rank, uint32_t nranks)
         if ( nranks < 1 || nranks > (uint32_t)SC_MAX_RANKS || rank >= nranks ) return fail(h, REAL_GPU_E_ARG, "set_bucket_shard: rank/nranks out of range (at most 8 ranks)");
         real_gpu::Comm & CM = h->comm;
         if ( CM.window.p ) return fail(h, REAL_GPU_E_STATE, "set_bucket_shard: the handle is already a rank of a peer-memory group (real_gpu_comm_init)");
+        drop_prepared(h);
         CM.nranks = nranks; CM.rank = rank; CM.connected = false;
         for ( uint32_t r = 0; r <= nranks; ++r ) CM.bucket_lo[r] = (uint32_t)(((uint64_t)r * SC_MAX_BUCKETS) / nranks);
         h->have_reads = false;            // the index has to be (re)built for this rank's buckets

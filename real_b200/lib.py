@@ -34,7 +34,8 @@ class Stats(C.Structure):
                 ("scan_ms", C.c_float), ("post_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("scan_launches", C.c_uint32), ("total_launches", C.c_uint32),
                 ("n_windows", C.c_uint64), ("n_probes", C.c_uint64), ("n_candidates", C.c_uint64),
-                ("n_seedpass", C.c_uint64), ("n_hits", C.c_uint64), ("fold_ms", C.c_float), ("probe_ms", C.c_float)]
+                ("n_seedpass", C.c_uint64), ("n_hits", C.c_uint64), ("fold_ms", C.c_float), ("probe_ms", C.c_float),
+                ("part_ms", C.c_float), ("prepared_scans", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -88,6 +89,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_set_text.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_text_device.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_text_async.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
+    L.real_gpu_prepare_scan.argtypes = [vp, u32]
     L.real_gpu_set_text_fasta.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.real_gpu_set_text_fasta_device.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.real_gpu_get_text_records.argtypes = [vp, vp, vp]
@@ -210,6 +212,11 @@ class Handle:
             return
         self._check(self.L.real_gpu_set_text(self.h, fileid, _np_ptr(words, np.uint64), _np_ptr(nmask, np.uint64), n_total,
                                              shard_begin, shard_len, own_begin, own_end, rs.ctypes.data, rs.size - 1))
+
+    def prepare_scan(self, max_read_len: int):
+        """real_gpu_prepare_scan: text first, reads second -- the scan's records of the current text are formed now, on a stream of
+        their own, while a following set_reads* call moves the reads; the next match call uses them."""
+        self._check(self.L.real_gpu_prepare_scan(self.h, max_read_len))
 
     def set_text_device(self, d_words: int, d_nmask: int, n_total: int, record_starts: np.ndarray, fileid: int = 0,
                         shard_begin: int = 0, shard_len: int | None = None, own_begin: int | None = None, own_end: int | None = None):
