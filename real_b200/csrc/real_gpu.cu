@@ -1025,27 +1025,32 @@ void plan_scan(real_gpu * h, int mode, bool prepare, ScanPlan & S)
         // C3's 3.1 G positions take 50 GB of the 180 -- because every chunk walks through all the tables again (three chunks
         // of 2^30 positions read the entries three times over: 105 GB of DRAM traffic instead of 10, 2 ms of the C3 scan).
         // Equal chunks when the text does not fit; REAL_GPU_CHUNK_MPOS overrides.
+        // A bucket shard is sized like a single handle -- all positions of a chunk may fall into its buckets -- plus the 4-byte
+        // list of the kept positions: one chunk for C3 on every rank too (r02 up to here: rounds of 2^30 positions).
+        bool const will_list = own_only && P.own_b_cnt <= (uint32_t)h->own_list_max;
         uint64_t chunk_max = sharded ? CM.round_positions : std::min<uint64_t>(h->chunk_positions, SC_MAX_CHUNK);
-        if ( ! sharded && ! own_only && h->chunk_positions == 0 )
+        if ( ! sharded && h->chunk_positions == 0 )
         {
                 uint64_t const span = ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS;
                 uint64_t const pad = (uint64_t)SC_MAX_BUCKETS * SC_UNIT;
                 uint64_t fit = SC_MAX_CHUNK;
                 // the memory query costs milliseconds (3.7 ms measured on C1, whose whole scan takes 0.5): it is made only
-                // when the record buffer already held is too small for the span
-                if ( (std::min<uint64_t>(span, SC_MAX_CHUNK) + pad) * sizeof(uint4) + 64 > h->rec_win.bytes )
+                // when the buffers already held are too small for the span
+                uint64_t const want = std::min<uint64_t>(span, SC_MAX_CHUNK);
+                if ( (want + pad) * sizeof(uint4) + 64 > h->rec_win.bytes || (will_list && want * 4 + 64 > h->own_list.bytes) )
                 {
                         size_t free_b = 0, total_b = 0;
                         RG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-                        // the buffer already held counts as room; ahead of the match call the read set and its tables are still to come
-                        uint64_t const room = (uint64_t)((free_b + h->rec_win.bytes) * (prepare ? 0.4 : 0.6)) / sizeof(uint4);
+                        // the buffers already held count as room; ahead of the match call the read set and its tables are still to come
+                        uint64_t const held = h->rec_win.bytes + (will_list ? h->own_list.bytes : 0);
+                        uint64_t const room = (uint64_t)((free_b + held) * (prepare ? 0.4 : 0.6)) / (sizeof(uint4) + (will_list ? 4 : 0));
                         fit = std::max<uint64_t>(SC_TILE_POS, std::min<uint64_t>(SC_MAX_CHUNK, room > pad ? room - pad : 0) / SC_TILE_POS * SC_TILE_POS);
                 }
                 uint64_t const nchunks = (span + fit - 1) / fit;
                 chunk_max = std::max<uint64_t>(SC_TILE_POS, ((span + nchunks - 1) / nchunks + SC_TILE_POS - 1) / SC_TILE_POS * SC_TILE_POS);
         }
         else if ( h->chunk_positions == 0 )
-                chunk_max = sharded ? CM.round_positions : SC_MAX_ROUND;
+                chunk_max = CM.round_positions;
         uint64_t const chunk_cap = S.chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
         if ( prepare && (sharded || x_end - x_begin > chunk_cap) ) return;      // nothing to form ahead: the caller gives up
         // entries are touched about once per chunk and bucket: several chunks stream them past the probed slot words
@@ -1085,7 +1090,7 @@ void plan_scan(real_gpu * h, int mode, bool prepare, ScanPlan & S)
         // Bucket shard: with few own buckets (four ranks or more) one light pass lists the kept positions and counts them per
         // bucket, and the staged scatter runs on the list; with many (two ranks: half of all positions are kept) listing
         // costs more than it saves, and the dense kernels run with a filter on the bucket (measured, profiles/r02_*)
-        bool const own_list = S.own_list = own_only && P.own_b_cnt <= (uint32_t)h->own_list_max;
+        bool const own_list = S.own_list = will_list;
         if ( own_list )
         {
                 // the positions of a chunk this rank keeps, 4 bytes each (all of them if the text falls into its buckets only)
