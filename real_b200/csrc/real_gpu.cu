@@ -65,15 +65,17 @@ struct real_gpu
         // real_gpu_prepare_scan: the text records formed ahead of the match call, on a stream of their own
         struct Prepared
         {
-                bool valid, inflight;
+                bool valid, inflight, ahead;   // ahead: formed by real_gpu_prepare_scan (else: left behind by the last scan)
                 uint64_t x_begin, x_end, win_begin, win_end, chunk_cap;
                 uint32_t bucket_bits, own_b_lo, own_b_cnt;
                 bool own_list;
+                const void * recs;             // where the records are: a buffer that has been re-allocated since does not hold them
                 cudaEvent_t ev0, done;
-                Prepared() : valid(false), inflight(false), x_begin(0), x_end(0), win_begin(0), win_end(0), chunk_cap(0), bucket_bits(0), own_b_lo(0), own_b_cnt(0),
-                             own_list(false), ev0(nullptr), done(nullptr) {}
+                Prepared() : valid(false), inflight(false), ahead(false), x_begin(0), x_end(0), win_begin(0), win_end(0), chunk_cap(0), bucket_bits(0), own_b_lo(0), own_b_cnt(0),
+                             own_list(false), recs(nullptr), ev0(nullptr), done(nullptr) {}
         } prep;
         cudaStream_t st3;              // the partition kernels of real_gpu_prepare_scan
+        bool auto_prepare;             // real_gpu_set_text* prepares the scan itself when the read set is known (REAL_GPU_AUTO_PREPARE=0 turns it off)
         std::vector<cudaEvent_t> evp;  // pairs around the probe kernel of every chunk of a scan (stats.probe_ms)
         bool fused_build;              // the current tables were built by build_tables_fused (entry arrays in item numbering)
         bool build_pending;            // the index build of the current read set has been enqueued but not yet waited for
@@ -184,7 +186,7 @@ struct real_gpu
                 memset(&stats, 0, sizeof(stats));
                 for ( int i = 0; i < 8; ++i ) ev[i] = nullptr;
                 evc[0] = evc[1] = nullptr; ev_words = nullptr; text_pending = false;
-                mask_src = nullptr; mask_words = 0; mask_deferred = false; st3 = nullptr;
+                mask_src = nullptr; mask_words = 0; mask_deferred = false; st3 = nullptr; auto_prepare = true;
                 for ( int i = 0; i < 8; ++i ) stage_buf[i] = nullptr;
                 for ( int i = 0; i < 4; ++i ) stage_st[i] = nullptr;
         }
@@ -320,6 +322,8 @@ void finish_text(real_gpu * h)
         h->stats.h2d_text_ms = elapsed(h->evc[0], h->evc[1]);
 }
 
+void auto_prepare_scan(real_gpu * h);
+
 // the records real_gpu_prepare_scan has formed (or is forming) are given up: the text, the shard or the buffers change
 void drop_prepared(real_gpu * h)
 {
@@ -397,6 +401,7 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
         h->own_begin = own_begin; h->own_end = own_end; h->nrec = nrecords;
         h->fa_rec_starts.clear(); h->fa_rec_nl.clear();
         h->have_text = true;
+        auto_prepare_scan(h);
         return REAL_GPU_OK;
 }
 
@@ -474,6 +479,7 @@ int set_text_fasta_common(real_gpu * h, uint32_t fileid, const void * bytes, uin
         h->fileid = fileid; h->n_total = n; h->shard_begin = 0; h->shard_len = n;
         h->own_begin = 0; h->own_end = n; h->nrec = (uint32_t)nrec;
         h->have_text = true;
+        auto_prepare_scan(h);
         return REAL_GPU_OK;
 }
 
@@ -993,7 +999,7 @@ void plan_scan(real_gpu * h, int mode, bool prepare, ScanPlan & S)
         uint32_t bbits = 0;
         if ( h->pass_bits_override >= 0 )
                 bbits = std::min<uint32_t>((uint32_t)h->pass_bits_override, maxbits);
-        else if ( prepare )
+        else if ( prepare || h->build_pending )
                 bbits = maxbits;
         else
                 while ( bbits < maxbits && (table_bytes >> bbits) > h->l2_slice_bytes ) ++bbits;
@@ -1052,7 +1058,7 @@ void plan_scan(real_gpu * h, int mode, bool prepare, ScanPlan & S)
         else if ( h->chunk_positions == 0 )
                 chunk_max = CM.round_positions;
         uint64_t const chunk_cap = S.chunk_cap = std::min<uint64_t>(chunk_max, ((x_end - x_begin + SC_TILE_POS - 1) / SC_TILE_POS) * SC_TILE_POS);
-        if ( prepare && (sharded || x_end - x_begin > chunk_cap) ) return;      // nothing to form ahead: the caller gives up
+        if ( sharded && prepare ) return;                                        // nothing to form ahead: the caller gives up
         // entries are touched about once per chunk and bucket: several chunks stream them past the probed slot words
         // (evict_first); a single chunk re-uses every entry line about nine times while its bucket is probed (evict_normal)
         if ( ! getenv("REAL_GPU_DEBUG") && x_end - x_begin <= chunk_cap ) P.debug_flags |= 4;
@@ -1081,6 +1087,7 @@ void plan_scan(real_gpu * h, int mode, bool prepare, ScanPlan & S)
                 P.peer_recs[0] = P.recs;
         }
         S.meta = meta;
+        P.nprobed = reinterpret_cast<unsigned long long *>(meta + 784);          // kept with the records: a scan that re-uses them takes the count over
         P.bucket_count = meta;
         P.bucket_start = meta + 256;
         P.unit_counter = meta + 256 + 520;
@@ -1168,31 +1175,59 @@ void launch_partition(real_gpu * h, ScanPlan const & S, ScanParams const & P, cu
 }
 
 // real_gpu_prepare_scan: the partition of the current text, enqueued on a stream of its own behind the arrival of the words
-void prepare_scan(real_gpu * h, uint32_t max_read_len)
+void prepare_scan(real_gpu * h, uint32_t max_read_len, bool reads_known)
 {
-        drop_prepared(h);
         uint32_t const seedl = std::min<uint32_t>(h->prm.seedl, 32);
         h->F = seedl / 4; h->keybits = seedl;
+        real_gpu::Prepared & R = h->prep;
+        if ( R.valid )
+        {
+                // records of this text are there already (or on their way: real_gpu_set_text* has started them because a read set
+                // was known): they serve if they cover the windows asked for
+                uint32_t const kept_maxlen = h->maxlen;
+                h->maxlen = max_read_len;
+                ScanParams Q;
+                fill_scan_params(h, Q, 0);
+                h->maxlen = kept_maxlen;
+                uint32_t const maxbits = std::min<uint32_t>(SLOT_PREFIX_BITS, 2 * h->F);
+                if ( R.x_begin == Q.x_begin && R.x_end == Q.x_end && R.win_begin == Q.win_begin && R.win_end == Q.win_end
+                     && (reads_known || R.bucket_bits >= maxbits || h->comm.nranks > 1) )
+                        return;
+        }
+        drop_prepared(h);
         uint32_t const kept_maxlen = h->maxlen;
         h->maxlen = max_read_len;
         ScanPlan S;
-        try { plan_scan(h, 0, true, S); } catch ( ... ) { h->maxlen = kept_maxlen; throw; }
+        try { plan_scan(h, 0, ! reads_known, S); } catch ( ... ) { h->maxlen = kept_maxlen; throw; }
         h->maxlen = kept_maxlen;
         if ( ! S.ntiles || S.sharded || S.x_end - S.x_begin > S.chunk_cap ) return;         // several chunks, or records that cross NVLink: formed by the scan itself
-        real_gpu::Prepared & R = h->prep;
         if ( ! h->st3 ) RG_CUDA(cudaStreamCreateWithFlags(&h->st3, cudaStreamNonBlocking));
         if ( ! R.ev0 ) { RG_CUDA(cudaEventCreate(&R.ev0)); RG_CUDA(cudaEventCreate(&R.done)); }
         ScanParams & P = S.P;
         P.pos_base = S.x_begin;
-        P.nprobed = reinterpret_cast<unsigned long long *>(S.meta + 784);          // taken over by the scan (bucket shards count their kept positions)
         if ( h->text_pending ) RG_CUDA(cudaStreamWaitEvent(h->st3, h->ev_words, 0));
-        RG_CUDA(cudaMemsetAsync(S.meta + 784, 0, 8, h->st3));
+        RG_CUDA(cudaMemsetAsync(P.nprobed, 0, 8, h->st3));
         RG_CUDA(cudaEventRecord(R.ev0, h->st3));
         launch_partition(h, S, P, h->st3, [](){});
         RG_CUDA(cudaEventRecord(R.done, h->st3));
         R.x_begin = S.x_begin; R.x_end = S.x_end; R.win_begin = P.win_begin; R.win_end = P.win_end; R.chunk_cap = S.chunk_cap;
-        R.bucket_bits = P.bucket_bits; R.own_b_lo = P.own_b_lo; R.own_b_cnt = P.own_b_cnt; R.own_list = S.own_list;
-        R.valid = true; R.inflight = true;
+        R.bucket_bits = P.bucket_bits; R.own_b_lo = P.own_b_lo; R.own_b_cnt = P.own_b_cnt; R.own_list = S.own_list; R.recs = P.recs;
+        R.valid = true; R.inflight = true; R.ahead = true;
+}
+
+// real_gpu_set_text* with the read set already known (the usual order: reads, then text file after text file): the partition
+// of the new text is enqueued at once, on its own stream -- beside an index build that real_gpu_set_reads* has left running.
+// Measured: texts of a few ten Mbp gain (C1, 10 Mbp: 2.09 -> 1.64 ms per step -- short kernels that are bound by latencies
+// fill each other's gaps); on C3 the two kernel groups take as long together as one after the other (37.3 against 15.2 + 22.8 ms:
+// both live on shared-memory bandwidth), so long texts are left to the scan itself and the phase times stay readable.
+static const uint64_t AUTO_PREPARE_MAX_POSITIONS = 1ull << 26;
+void auto_prepare_scan(real_gpu * h)
+{
+        if ( ! h->auto_prepare || ! h->have_text || ! (h->have_reads || h->build_pending) || ! h->maxlen ) return;
+        if ( h->shard_len > AUTO_PREPARE_MAX_POSITIONS && ! getenv("REAL_GPU_AUTO_PREPARE") ) return;
+        try { prepare_scan(h, h->maxlen, true); }
+        catch ( LimitError const & ) { h->prep.valid = false; }
+        catch ( CudaError const & ) { cudaGetLastError(); h->prep.valid = false; }          // what is wrong with the set-up is reported by the match call
 }
 
 // launches K3 once; returns the number of hits the kernel counted
@@ -1213,10 +1248,10 @@ uint64_t run_scan(real_gpu * h, int mode)
         real_gpu::Prepared & R = h->prep;
         bool const use_prep = R.valid && ntiles && ! S.sharded && S.x_end - S.x_begin <= S.chunk_cap
                               && R.x_begin == S.x_begin && R.x_end == S.x_end && R.win_begin == P.win_begin && R.win_end == P.win_end
-                              && R.bucket_bits >= P.bucket_bits && R.own_b_lo == P.own_b_lo && R.own_b_cnt == P.own_b_cnt && R.own_list == S.own_list;
+                              && R.bucket_bits >= P.bucket_bits && R.own_b_lo == P.own_b_lo && R.own_b_cnt == P.own_b_cnt && R.own_list == S.own_list && R.recs == P.recs;
         if ( R.inflight ) RG_CUDA(cudaStreamWaitEvent(h->st, R.done, 0));        // either way: the record buffer is written or read next
-        bool const was_inflight = R.inflight;
-        R.valid = false;                // one scan per preparation: every scan leaves the records of its own last chunk behind
+        bool const was_ahead = use_prep && R.ahead;
+        R.valid = false;
         RG_CUDA(cudaEventRecord(h->ev[5], h->st));
         size_t nprobe_ev = 0;
         if ( ntiles )
@@ -1227,8 +1262,10 @@ uint64_t run_scan(real_gpu * h, int mode)
                 if ( use_prep )
                 {
                         P.bucket_bits = R.bucket_bits;
-                        RG_CUDA(cudaMemcpyAsync(ptr<unsigned long long>(h->counters) + 4, S.meta + 784, 8, cudaMemcpyDeviceToDevice, h->st));
+                        RG_CUDA(cudaMemsetAsync(P.unit_counter, 0, 4, h->st));          // the work counter of the probe (k_part_offsets clears it otherwise)
                 }
+                else
+                        RG_CUDA(cudaMemsetAsync(P.nprobed, 0, 8, h->st));
                 h->stats.n_windows = 0;
                 // REAL_GPU_TRACE=1: per-round phase times on stderr (development)
                 bool const trace = getenv("REAL_GPU_TRACE") != nullptr;
@@ -1282,6 +1319,15 @@ uint64_t run_scan(real_gpu * h, int mode)
                         h->stats.scan_launches += 1;
                 }
                 P.x_begin = x_begin; P.x_end = x_end;
+                RG_CUDA(cudaMemcpyAsync(ptr<unsigned long long>(h->counters) + 4, P.nprobed, 8, cudaMemcpyDeviceToDevice, h->st));
+                // a scan of one chunk leaves the records of the whole text behind: the next scan of the same text (the gapped pass
+                // after matchUnique, a second file set against ... the same text) finds them; a new text drops them
+                if ( ! sharded && x_end - x_begin <= chunk_cap )
+                {
+                        R.x_begin = S.x_begin; R.x_end = S.x_end; R.win_begin = P.win_begin; R.win_end = P.win_end; R.chunk_cap = S.chunk_cap;
+                        R.bucket_bits = P.bucket_bits; R.own_b_lo = P.own_b_lo; R.own_b_cnt = P.own_b_cnt; R.own_list = S.own_list; R.recs = P.recs;
+                        R.valid = true; R.ahead = false;
+                }
                 if ( trace )
                 {
                         RG_CUDA(cudaStreamSynchronize(h->st));
@@ -1304,8 +1350,8 @@ uint64_t run_scan(real_gpu * h, int mode)
         h->stats.probe_ms = 0;
         for ( size_t i = 0; i < nprobe_ev; ++i ) h->stats.probe_ms += elapsed(h->evp[2*i], h->evp[2*i+1]);
         // the partition kernels' time: part of scan_ms, unless the records were formed ahead (then it ran beside the transfer of the reads)
-        h->stats.part_ms = (use_prep && was_inflight) ? elapsed(R.ev0, R.done) : (use_prep ? 0.f : h->stats.scan_ms - h->stats.probe_ms);
-        h->stats.prepared_scans += use_prep ? 1 : 0;
+        h->stats.part_ms = was_ahead ? elapsed(R.ev0, R.done) : (use_prep ? 0.f : h->stats.scan_ms - h->stats.probe_ms);
+        h->stats.prepared_scans += was_ahead ? 1 : 0;
         if ( ! ntiles ) h->stats.n_windows = 0;
         else if ( h->comm.nranks > 1 && ! h->comm.window.p ) h->stats.n_windows = c[4];     // bucket shard: the positions this handle kept
         if ( h->comm.nranks > 1 && h->comm.window.p )
@@ -1401,6 +1447,7 @@ int real_gpu_create(const real_gpu_params * params, real_gpu ** out)
                 if ( const char * e = getenv("REAL_GPU_PASS_BITS") ) h->pass_bits_override = atoi(e);
                 if ( const char * e = getenv("REAL_GPU_L2_SLICE_MB") ) h->l2_slice_bytes = (uint64_t)atoi(e) << 20;
                 if ( const char * e = getenv("REAL_GPU_OWN_LIST_MAX") ) h->own_list_max = atoi(e);
+                if ( const char * e = getenv("REAL_GPU_AUTO_PREPARE") ) h->auto_prepare = atoi(e) != 0;
                 if ( const char * e = getenv("REAL_GPU_CHUNK_MPOS") ) h->chunk_positions = std::max<uint64_t>(SC_TILE_POS, ((uint64_t)atoi(e) << 20) / SC_TILE_POS * SC_TILE_POS);
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
                 RG_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
@@ -1496,7 +1543,7 @@ int real_gpu_prepare_scan(real_gpu * h, uint32_t max_read_len)
 {
         RG_API_BEGIN_ASYNC(h)
         if ( ! h->have_text ) return fail(h, REAL_GPU_E_STATE, "prepare_scan: no text set");
-        prepare_scan(h, max_read_len);
+        prepare_scan(h, max_read_len, false);
         return REAL_GPU_OK;
         RG_API_END(h)
 }

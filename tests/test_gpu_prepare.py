@@ -116,9 +116,41 @@ def test_prepared_bucket_shards(nranks):
     assert sum(kept) == text.n - 32 + 1 + 2 * 8 and min(kept) > 0
 
 
-def test_preparation_that_does_not_fit_is_ignored():
+def test_text_set_after_reads_prepares_itself():
+    """The usual order (reads, then text after text): real_gpu_set_text starts the partition of the new text itself; the
+    match call finds the records, a second match call on the same text re-uses them (nothing is formed twice), a scan of the
+    same reads after another text forms new ones.  Results equal the oracle's every time."""
+    text, reads = _fresh(511, n=700_000, nreads=9000)
+    other, _ = _fresh(512, n=500_000, nreads=10)
+    kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    ref = canon_hits(O.match_all(text, reads, **kw))
+    ref_other = canon_hits(O.match_all(other, reads, **kw))
+    m = matcher.AllMatcher(matcher.RealOptions(**kw))
+    try:
+        m.set_reads(reads.mapped, reads.offsets, None)
+        m.set_text(*text.packed(), text.n, text.record_starts)
+        assert np.array_equal(canon_hits(m.match()), ref)
+        st = m.stats()
+        assert st["prepared_scans"] == 1 and st["part_ms"] > 0
+        assert np.array_equal(canon_hits(m.match()), ref)
+        st = m.stats()
+        assert st["prepared_scans"] == 1 and st["part_ms"] == 0          # the records of the last scan
+        m.set_text(*other.packed(), other.n, other.record_starts)
+        assert np.array_equal(canon_hits(m.match()), ref_other)
+        assert m.stats()["prepared_scans"] == 2
+        m.set_text(*text.packed(), text.n, text.record_starts)
+        m.handle.prepare_scan(100)                                       # already on its way: nothing happens
+        assert np.array_equal(canon_hits(m.match()), ref)
+        assert m.stats()["prepared_scans"] == 3
+    finally:
+        m.close()
+
+
+def test_preparation_that_does_not_fit_is_ignored(monkeypatch):
     """A text shard prepared for reads of 60 bases and matched with reads of 100 (other last window), a text replaced after
-    the preparation, a bucket shard set after it: the scan forms its own records; results equal the plain order's."""
+    the preparation, a bucket shard set after it: the scan forms its own records; results equal the plain order's.
+    (REAL_GPU_AUTO_PREPARE=0: only the explicit calls prepare.)"""
+    monkeypatch.setenv("REAL_GPU_AUTO_PREPARE", "0")
     text, reads = _fresh(411, n=600_000, nreads=8000)
     kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
     ref = O.match_all(text, reads, **kw)
