@@ -408,6 +408,41 @@ def ingest_probe(torch, rlib, peak_gbs: float) -> dict:
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa(torch, local: int) -> dict:
+    """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs of the NUMA node the GPU hangs on, so that
+    the host<->device copies of the end-to-end leg do not cross the socket interconnect -- with eight ranks pulling their slices out
+    of host memory at once that interconnect, not PCIe, was the bound.  Reads the GPU's PCI address from torch and its
+    local_cpulist from sysfs; does nothing when either is not there."""
+    info = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        node = None
+        try:
+            with open(base + "/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
+        info.update(pci=bdf, numa_node=node, cpus=len(cpus), allowed=len(allowed))
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except Exception as e:          # no sysfs, no such property: stay where the launcher put us
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,6 +471,7 @@ def main():
                     help="end-to-end leg: text-first = set_text_async, prepare_scan, set_reads, match (the partition of the text runs while "
                          "the reads cross PCIe); reads-first = set_reads, set_text_async, match")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not bind the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-ingest", action="store_true", help="skip the K0 (device text loader) extra of the bench line")
     ap.add_argument("--ref-text", type=int, default=32_000_000, help="reference arm: text bases of the sample")
     ap.add_argument("--ref-reads", type=int, default=500_000, help="reference arm: reads of the sample")
@@ -463,6 +499,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the matching path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(torch, local) if (world > 1 and not args.no_numa_bind) else {"bound": False}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -851,7 +888,7 @@ def main():
             "phases_ms": {k: statistics.mean(v) for k, v in phase.items()},
             "counts": {"windows": tot[0], "candidates": tot[1], "hits": tot[2], "seedpass": tot[3], "matchall_hits": nhits_holder[0]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
-            "device_bytes": dev_bytes, "ingest": ingest,
+            "device_bytes": dev_bytes, "ingest": ingest, "cpu_affinity": affinity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
