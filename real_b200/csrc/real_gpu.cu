@@ -1590,6 +1590,7 @@ int real_gpu_get_text_packed(real_gpu * h, uint64_t n_bases, uint64_t * words, u
         RG_API_BEGIN_ASYNC(h)
         if ( ! h->have_text ) return fail(h, REAL_GPU_E_STATE, "no text set");
         if ( n_bases != h->shard_len ) return fail(h, REAL_GPU_E_ARG, "get_text_packed: n_bases is not the length of the current text (shard)");
+        flush_mask(h);                  // a wildcard mask real_gpu_set_text_async has left behind goes first (same stream)
         if ( words ) RG_CUDA(cudaMemcpyAsync(words, ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, (h->shard_len + 31) / 32 * 8, cudaMemcpyDeviceToHost, h->st2));
         if ( nmask ) RG_CUDA(cudaMemcpyAsync(nmask, ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, (h->shard_len + 63) / 64 * 8, cudaMemcpyDeviceToHost, h->st2));
         RG_CUDA(cudaStreamSynchronize(h->st2));
@@ -2109,6 +2110,12 @@ int real_gpu_match_all_packed(real_gpu * h, const real_gpu_hit16 ** rows, uint64
 static uint32_t block_bounds(real_gpu * h)
 {
         if ( ! h->n_list ) return 1;
+        if ( h->text_pending )
+        {
+                // real_gpu_set_text_async: the window counts read the wildcard mask, which may still be on its way (or not even sent)
+                flush_mask(h);
+                RG_CUDA(cudaStreamWaitEvent(h->st, h->evc[1], 0));
+        }
         uint32_t const seedl = h->prm.seedl;
         uint64_t const ngroups = (h->n_total + 63) / 64;
         dev_reserve(h, h->win_valid, ngroups * 8 + 64);
