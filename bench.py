@@ -886,6 +886,9 @@ def main():
             "scan_only": {"ms": scan_ms, "text_gbp_per_s_per_gpu": last_stats["n_windows"] / (scan_ms * 1e-3) / 1e9,
                           "reads_per_s": R / (scan_ms * 1e-3)},
             "phases_ms": {k: statistics.mean(v) for k, v in phase.items()},
+            # short texts and bucket shards: real_gpu_set_text* starts the partition of the text beside the index build;
+            # index_ms and part_ms then cover the same stretch of time and scan_ms holds the probe only
+            "partition_beside_build": bool(last_stats.get("prepared_scans", 0)),
             "counts": {"windows": tot[0], "candidates": tot[1], "hits": tot[2], "seedpass": tot[3], "matchall_hits": nhits_holder[0]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
             "device_bytes": dev_bytes, "ingest": ingest, "cpu_affinity": affinity,
