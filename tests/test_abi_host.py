@@ -86,3 +86,16 @@ def test_shard_ranges_cover_and_halo():
             assert sb + sl <= n
             if nxt is not None:
                 assert nxt[0] == oe
+
+
+def test_stats_struct_mirrors_header():
+    """real_b200.lib.Stats (ctypes) lists the fields of real_gpu_stats in the header's order and types: the struct is copied
+    whole by real_gpu_get_stats, a drift would shift every later field."""
+    import re
+    src = open(rlib.HEADER_PATH).read()
+    body = re.search(r"typedef struct\s*\{([^}]*)\}\s*real_gpu_stats;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(float|uint32_t|uint64_t)\s+([a-z_0-9]+)\s*;", body)
+    ctype = {"float": C.c_float, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64}
+    assert [(n, ctype[t]) for t, n in fields] == list(rlib.Stats._fields_)
+    assert C.sizeof(rlib.Stats) % 8 == 0
