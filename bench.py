@@ -750,6 +750,13 @@ def main():
                 sections.append(("qual", h_qual))
             gather = rdist.ShardedUpload(sections, dev)
             gather_text = rdist.ShardedUpload([("words", h_w.view(torch.uint8)), ("nmask", h_m.view(torch.uint8))], dev)
+            if args.e2e_order == "text-first":
+                # the words alone in front of the partition; the wildcard mask (read by the probe only) is gathered under the index build
+                gather_text = None
+                gather_words = rdist.ShardedUpload([("words", h_w.view(torch.uint8))], dev)
+                gather_mask = rdist.ShardedUpload([("nmask", h_m.view(torch.uint8))], dev)
+                mask_off, mask_len = gather_mask.offsets["nmask"]
+                d_mask_ptr = gather_mask.d_all[mask_off:mask_off + mask_len].data_ptr()
 
         e2e_phase = {"h2d_reads_ms": [], "h2d_text_ms": [], "pack_ms": [], "index_ms": [], "scan_ms": [], "part_ms": [], "probe_ms": [], "fold_ms": [], "d2h_ms": [],
                      "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": [], "api_exchange_ms": [], "api_get_ms": []}
@@ -760,13 +767,14 @@ def main():
             t0 = time.perf_counter()
             if gather is not None and text_first:
                 # text first: its records are formed (real_gpu_prepare_scan, a stream of its own) while the reads are uploaded and gathered
-                d = gather_text.run()
-                h.set_text_device(d["words"].data_ptr(), d["nmask"].data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+                d = gather_words.run()
+                h.set_text_device(d["words"].data_ptr(), d_mask_ptr, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
                 h.prepare_scan(L)
                 t1 = time.perf_counter()
                 d = gather.run()
                 h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
                                           d_quality=d["qual"].data_ptr() if "qual" in d else None)
+                gather_mask.run()                 # the mask arrives while the index builds; the library reads it when the match call starts
                 t2 = time.perf_counter()
                 t_text, t_reads = t1 - t0, t2 - t1
             elif gather is not None:
@@ -834,7 +842,7 @@ def main():
             sys.exit(3)
         h2d = R * L4 + R + (R * L if qual is not None else 0) + np_w.nbytes + np_m.nbytes + rs.nbytes
         if gather is not None:
-            h2d = gather.chunk + gather_text.chunk + rs.nbytes          # per rank; the rest arrives over NVLink
+            h2d = gather.chunk + (gather_text.chunk if gather_text is not None else gather_words.chunk + gather_mask.chunk) + rs.nbytes          # per rank; the rest arrives over NVLink
         e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
                "ms_per_step": e_ms / e_steps, "steps": e_steps, "order": args.e2e_order, "digest_ok": True, "prepared_scans": int(h.stats().get("prepared_scans", 0)),
                "phases_ms": {k: statistics.mean(v) for k, v in e2e_phase.items() if v},

@@ -170,6 +170,15 @@ int real_gpu_set_text_async(real_gpu * h, uint32_t fileid,
  * peers (real_gpu_comm_*).  The order set_text_async -> prepare_scan -> set_reads* -> match also sends the text's wildcard
  * mask behind the reads (it is read by the probe only). */
 int real_gpu_prepare_scan(real_gpu * h, uint32_t max_read_len);
+/* real_gpu_set_text_async for a text already in device memory: the copy of the words is enqueued; d_nmask is only REMEMBERED and
+ * copied when the next real_gpu_match_* call (or real_gpu_set_text* / real_gpu_get_text*) starts, so the caller may still be
+ * completing the mask while it hands over the reads -- ranks that upload 1/N of every input and all-gather the rest send the
+ * words, let the partition start (real_gpu_prepare_scan), gather the reads, and gather the mask while the index builds. */
+int real_gpu_set_text_device_async(real_gpu * h, uint32_t fileid,
+                                   const uint64_t * d_words, const uint64_t * d_nmask,
+                                   uint64_t n_total, uint64_t shard_begin, uint64_t shard_len,
+                                   uint64_t own_begin, uint64_t own_end,
+                                   const uint64_t * record_starts, uint32_t nrecords);
 /* Same, with words/nmask already resident in device memory (record_starts stays a host pointer). */
 int real_gpu_set_text_device(real_gpu * h, uint32_t fileid,
                              const uint64_t * d_words, const uint64_t * d_nmask,

@@ -62,6 +62,7 @@ struct real_gpu
         // real_gpu_set_reads* call that follows (the index build needs the reads, the mask is read by the probe only) or, at the
         // latest, at the start of the scan
         const uint64_t * mask_src; uint64_t mask_words; bool mask_deferred;
+        bool mask_on_device;           // real_gpu_set_text_device_async: mask_src is a device pointer whose contents the caller completes before the match call
         // real_gpu_prepare_scan: the text records formed ahead of the match call, on a stream of their own
         struct Prepared
         {
@@ -186,7 +187,7 @@ struct real_gpu
                 memset(&stats, 0, sizeof(stats));
                 for ( int i = 0; i < 8; ++i ) ev[i] = nullptr;
                 evc[0] = evc[1] = nullptr; ev_words = nullptr; text_pending = false;
-                mask_src = nullptr; mask_words = 0; mask_deferred = false; st3 = nullptr; auto_prepare = true;
+                mask_src = nullptr; mask_words = 0; mask_deferred = false; mask_on_device = false; st3 = nullptr; auto_prepare = true;
                 for ( int i = 0; i < 8; ++i ) stage_buf[i] = nullptr;
                 for ( int i = 0; i < 4; ++i ) stage_st[i] = nullptr;
         }
@@ -303,12 +304,16 @@ void h2d_from_host(real_gpu * h, void * dst, const void * src, size_t nbytes, cu
 // text
 // ---------------------------------------------------------------------------------------------
 
-// enqueues the copy of the wildcard mask real_gpu_set_text_async has left to a later call
-void flush_mask(real_gpu * h)
+// enqueues the copy of the wildcard mask real_gpu_set_text_async has left to a later call.  behind_reads: called by a
+// real_gpu_set_reads* -- a mask in device memory (real_gpu_set_text_device_async) is not touched yet: its owner may still be
+// completing it (it has until the match call)
+void flush_mask(real_gpu * h, bool behind_reads = false)
 {
         if ( ! h->mask_deferred ) return;
+        if ( behind_reads && h->mask_on_device ) return;
         h->mask_deferred = false;
-        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, h->mask_src, h->mask_words * 8, cudaMemcpyHostToDevice, h->st2));
+        RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->nmask) + TEXT_PAD_WORDS, h->mask_src, h->mask_words * 8,
+                                h->mask_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st2));
         RG_CUDA(cudaEventRecord(h->evc[1], h->st2));
 }
 
@@ -378,11 +383,12 @@ int set_text_common(real_gpu * h, uint32_t fileid, const uint64_t * words, const
         RG_CUDA(cudaMemcpyAsync(h->rec.p, record_starts, (size_t)(nrecords + 1) * 8, cudaMemcpyHostToDevice, h->st2));
         RG_CUDA(cudaMemcpyAsync(ptr<uint64_t>(h->text) + TEXT_PAD_WORDS, words, nw * 8, kind, h->st2));
         RG_CUDA(cudaEventRecord(h->ev_words, h->st2));
-        if ( async_copy && ! on_device )
+        if ( async_copy )
         {
                 // the mask is read by the probe only: its copy is placed by flush_mask -- behind the reads of a real_gpu_set_reads*
-                // call that comes next (text first, reads second: the partition runs while the reads arrive), else when the scan starts
-                h->mask_src = nmask; h->mask_words = nmw; h->mask_deferred = true;
+                // call that comes next (text first, reads second: the partition runs while the reads arrive), else when the scan starts;
+                // a mask in device memory is copied when the scan starts (the caller may complete it until then)
+                h->mask_src = nmask; h->mask_words = nmw; h->mask_deferred = true; h->mask_on_device = on_device;
         }
         else
         {
@@ -1560,6 +1566,15 @@ int real_gpu_set_text_device(real_gpu * h, uint32_t fileid, const uint64_t * d_w
         RG_API_END(h)
 }
 
+int real_gpu_set_text_device_async(real_gpu * h, uint32_t fileid, const uint64_t * d_words, const uint64_t * d_nmask,
+                                   uint64_t n_total, uint64_t shard_begin, uint64_t shard_len, uint64_t own_begin, uint64_t own_end,
+                                   const uint64_t * record_starts, uint32_t nrecords)
+{
+        RG_API_BEGIN_ASYNC(h)
+        return set_text_common(h, fileid, d_words, d_nmask, true, n_total, shard_begin, shard_len, own_begin, own_end, record_starts, nrecords, true);
+        RG_API_END(h)
+}
+
 int real_gpu_set_text_fasta(real_gpu * h, uint32_t fileid, const void * fasta_bytes, uint64_t nbytes, uint64_t * n_bases, uint64_t * nrecords)
 {
         RG_API_BEGIN_ASYNC(h)
@@ -1640,7 +1655,7 @@ int real_gpu_set_reads(real_gpu * h, const uint8_t * mapped, const uint8_t * qua
         int const brc = build_from_device(h);           // enqueued; waited for by the next call that needs the index
         RG_CUDA(cudaEventSynchronize(h->ev[1]));        // the caller's buffers have been copied
         h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
-        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
+        flush_mask(h, true);    // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }
@@ -1668,7 +1683,7 @@ int real_gpu_set_reads_device(real_gpu * h, const uint8_t * d_mapped, const uint
         h->stats.h2d_reads_ms = 0;
         int const brc = build_from_device(h);
         RG_CUDA(cudaEventSynchronize(h->ev[3]));        // the reads are packed: the caller's buffers are not referenced any more
-        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
+        flush_mask(h, true);    // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }
@@ -1741,7 +1756,7 @@ int real_gpu_set_reads_packed(real_gpu * h, const uint8_t * packed, const uint64
         int const brc = build_from_device(h);           // enqueued; waited for by the next call that needs the index
         RG_CUDA(cudaEventSynchronize(h->ev[1]));        // the caller's buffers (and the staging vectors above) have been copied
         h->stats.h2d_reads_ms = elapsed(h->ev[0], h->ev[1]);
-        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
+        flush_mask(h, true);    // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }
@@ -1961,7 +1976,7 @@ int real_gpu_set_reads_packed_device(real_gpu * h, const uint8_t * d_packed, uin
         h->stats.h2d_reads_ms = 0;
         int const brc = build_from_device(h);
         RG_CUDA(cudaEventSynchronize(h->ev[3]));        // the reads are packed: the caller's buffers are not referenced any more
-        flush_mask(h);          // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
+        flush_mask(h, true);    // a wildcard mask real_gpu_set_text_async has left behind travels now, behind the reads
         return brc;
         RG_API_END(h)
 }

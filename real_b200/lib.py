@@ -88,6 +88,7 @@ def load(build_if_missing: bool = True):
     L.real_gpu_last_error.restype = C.c_char_p
     L.real_gpu_set_text.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_text_device.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
+    L.real_gpu_set_text_device_async.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_set_text_async.argtypes = [vp, u32, vp, vp, u64, u64, u64, u64, u64, vp, u32]
     L.real_gpu_prepare_scan.argtypes = [vp, u32]
     L.real_gpu_set_text_fasta.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
@@ -219,11 +220,19 @@ class Handle:
         self._check(self.L.real_gpu_prepare_scan(self.h, max_read_len))
 
     def set_text_device(self, d_words: int, d_nmask: int, n_total: int, record_starts: np.ndarray, fileid: int = 0,
-                        shard_begin: int = 0, shard_len: int | None = None, own_begin: int | None = None, own_end: int | None = None):
+                        shard_begin: int = 0, shard_len: int | None = None, own_begin: int | None = None, own_end: int | None = None,
+                        async_copy: bool = False):
+        """async_copy: real_gpu_set_text_device_async -- the words' copy is enqueued, the mask behind d_nmask is read when the next
+        match call starts (the caller may complete it until then); both buffers stay valid until that call has returned"""
         shard_len = n_total - shard_begin if shard_len is None else shard_len
         own_begin = shard_begin if own_begin is None else own_begin
         own_end = shard_begin + shard_len if own_end is None else own_end
         rs = np.ascontiguousarray(record_starts, dtype=np.uint64)
+        if async_copy:
+            self._keep_text = (rs,)
+            self._check(self.L.real_gpu_set_text_device_async(self.h, fileid, d_words, d_nmask, n_total, shard_begin, shard_len,
+                                                              own_begin, own_end, rs.ctypes.data, rs.size - 1))
+            return
         self._check(self.L.real_gpu_set_text_device(self.h, fileid, d_words, d_nmask, n_total, shard_begin, shard_len,
                                                     own_begin, own_end, rs.ctypes.data, rs.size - 1))
 

@@ -186,3 +186,51 @@ def test_preparation_that_does_not_fit_is_ignored(monkeypatch):
         assert 0 < len(half) < len(ref)
     finally:
         m.close()
+
+
+def test_device_text_with_late_mask():
+    """real_gpu_set_text_device_async: the words are taken at once, the wildcard mask when the match call starts -- the caller
+    completes it in between (ranks that all-gather their inputs gather the mask while the index builds).  Reads cut across the
+    text's N runs with A in place of N: they match only if the mask is ignored, so a stale mask would show."""
+    text, reads = _fresh(611, n=600_000, nreads=6000, npm=3000)
+    sym = text.symbols
+    npos = np.flatnonzero(sym == 4)
+    assert npos.size > 500
+    rng = np.random.default_rng(5)
+    picks = rng.choice(npos[(npos > 200) & (npos < text.n - 200)], size=300, replace=False)
+    seqs = []
+    for p in picks:
+        s0 = int(p) - int(rng.integers(0, 100))
+        q = sym[s0:s0 + 100].copy()
+        q[q == 4] = 0
+        seqs.append(q)
+    across = synth.reads_from_list(seqs)
+    allreads = synth.concat_reads([reads, across])
+    kw = dict(seedl=32, seedkmax=2, totalkmax=4, scores=False)
+    ref = canon_hits(O.match_all(text, allreads, **kw))
+    words, nmask = text.packed()
+    dev = torch.device("cuda", 0)
+    d_words = torch.from_numpy(np.ascontiguousarray(words).view(np.int64)).to(dev)
+    d_mask = torch.zeros(np.ascontiguousarray(nmask).size, dtype=torch.int64, device=dev)          # not there yet
+    torch.cuda.synchronize()
+    m = matcher.AllMatcher(matcher.RealOptions(**kw))
+    try:
+        for rep in range(2):
+            d_mask.zero_()
+            torch.cuda.synchronize()
+            m.handle.set_text_device(d_words.data_ptr(), d_mask.data_ptr(), text.n, text.record_starts, async_copy=True)
+            m.handle.prepare_scan(100)
+            m.set_reads(allreads.mapped, allreads.offsets, None)
+            d_mask.copy_(torch.from_numpy(np.ascontiguousarray(nmask).view(np.int64)))                 # the mask arrives after the reads
+            torch.cuda.synchronize()
+            got = canon_hits(m.match())
+            assert got.shape == ref.shape and np.array_equal(got, ref)
+        assert m.stats()["prepared_scans"] == 2
+        # the same with the mask left empty: the reads across the N runs match -- the test does look at the mask
+        d_mask.zero_()
+        torch.cuda.synchronize()
+        m.handle.set_text_device(d_words.data_ptr(), d_mask.data_ptr(), text.n, text.record_starts, async_copy=True)
+        wrong = canon_hits(m.match())
+        assert len(wrong) > len(ref)
+    finally:
+        m.close()
