@@ -717,141 +717,146 @@ def main():
     # ---- e2e: host buffers through the host-pointer ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        # reads cross PCIe 2 bit/base, the layout of the reference's own rewritten pattern file (-R 1, the default of
-        # matchUnique; TemporaryFile.hpp:231-268); qualities (only with scores) stay 1 byte/base
-        L4 = (L + 3) // 4
-        h_mapped = torch.empty(R * L4, dtype=torch.uint8).pin_memory()
-        h_mapped.copy_(d_packed)
-        h_flags = torch.empty(R, dtype=torch.uint8).pin_memory()
-        h_flags.copy_(d_flags)
-        del d_packed, d_flags
-        torch.cuda.empty_cache()
-        h_qual = None
-        if qual is not None:
-            h_qual = torch.empty(R * L, dtype=torch.uint8).pin_memory()
-            h_qual.copy_(qual)
-        h_w = sh_w.cpu().pin_memory()
-        h_m = sh_m.cpu().pin_memory()
-        h_info = torch.empty(R, dtype=torch.int64).pin_memory()
-        np_w = h_w.numpy().view(np.uint64)
-        np_m = h_m.numpy().view(np.uint64)
-        np_mapped = h_mapped.numpy()
-        np_flags = h_flags.numpy()
-        np_qual = h_qual.numpy() if h_qual is not None else None
-        np_info = h_info.numpy().view(np.uint64)
-        d2h = [0]
+        try:
+            # reads cross PCIe 2 bit/base, the layout of the reference's own rewritten pattern file (-R 1, the default of
+            # matchUnique; TemporaryFile.hpp:231-268); qualities (only with scores) stay 1 byte/base
+            L4 = (L + 3) // 4
+            h_mapped = torch.empty(R * L4, dtype=torch.uint8).pin_memory()
+            h_mapped.copy_(d_packed)
+            h_flags = torch.empty(R, dtype=torch.uint8).pin_memory()
+            h_flags.copy_(d_flags)
+            del d_packed, d_flags
+            torch.cuda.empty_cache()
+            h_qual = None
+            if qual is not None:
+                h_qual = torch.empty(R * L, dtype=torch.uint8).pin_memory()
+                h_qual.copy_(qual)
+            h_w = sh_w.cpu().pin_memory()
+            h_m = sh_m.cpu().pin_memory()
+            h_info = torch.empty(R, dtype=torch.int64).pin_memory()
+            np_w = h_w.numpy().view(np.uint64)
+            np_m = h_m.numpy().view(np.uint64)
+            np_mapped = h_mapped.numpy()
+            np_flags = h_flags.numpy()
+            np_qual = h_qual.numpy() if h_qual is not None else None
+            np_info = h_info.numpy().view(np.uint64)
+            d2h = [0]
 
-        # N > 1 with replicated inputs (bucket shards): every rank uploads 1/N of the input bytes from its pinned host copy and
-        # the ranks all-gather them over NVLink, instead of every rank pulling everything through its own PCIe link
-        gather = None
-        if world > 1 and (buckets_mode or tables_mode):
-            sections = [("reads", h_mapped), ("flags", h_flags)]
-            if h_qual is not None:
-                sections.append(("qual", h_qual))
-            gather = rdist.ShardedUpload(sections, dev)
-            gather_text = rdist.ShardedUpload([("words", h_w.view(torch.uint8)), ("nmask", h_m.view(torch.uint8))], dev)
-            if args.e2e_order == "text-first":
-                # the words alone in front of the partition; the wildcard mask (read by the probe only) is gathered under the index build
-                gather_text = None
-                gather_words = rdist.ShardedUpload([("words", h_w.view(torch.uint8))], dev)
-                gather_mask = rdist.ShardedUpload([("nmask", h_m.view(torch.uint8))], dev)
-                mask_off, mask_len = gather_mask.offsets["nmask"]
-                d_mask_ptr = gather_mask.d_all[mask_off:mask_off + mask_len].data_ptr()
+            # N > 1 with replicated inputs (bucket shards): every rank uploads 1/N of the input bytes from its pinned host copy and
+            # the ranks all-gather them over NVLink, instead of every rank pulling everything through its own PCIe link
+            gather = None
+            if world > 1 and (buckets_mode or tables_mode):
+                sections = [("reads", h_mapped), ("flags", h_flags)]
+                if h_qual is not None:
+                    sections.append(("qual", h_qual))
+                gather = rdist.ShardedUpload(sections, dev)
+                gather_text = rdist.ShardedUpload([("words", h_w.view(torch.uint8)), ("nmask", h_m.view(torch.uint8))], dev)
+                if args.e2e_order == "text-first":
+                    # the words alone in front of the partition; the wildcard mask (read by the probe only) is gathered under the index build
+                    gather_text = None
+                    gather_words = rdist.ShardedUpload([("words", h_w.view(torch.uint8))], dev)
+                    gather_mask = rdist.ShardedUpload([("nmask", h_m.view(torch.uint8))], dev)
+                    mask_off, mask_len = gather_mask.offsets["nmask"]
+                    d_mask_ptr = gather_mask.d_all[mask_off:mask_off + mask_len].data_ptr()
 
-        e2e_phase = {"h2d_reads_ms": [], "h2d_text_ms": [], "pack_ms": [], "index_ms": [], "scan_ms": [], "part_ms": [], "probe_ms": [], "fold_ms": [], "d2h_ms": [],
-                     "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": [], "api_exchange_ms": [], "api_get_ms": []}
+            e2e_phase = {"h2d_reads_ms": [], "h2d_text_ms": [], "pack_ms": [], "index_ms": [], "scan_ms": [], "part_ms": [], "probe_ms": [], "fold_ms": [], "d2h_ms": [],
+                         "api_set_reads_ms": [], "api_set_text_ms": [], "api_match_ms": [], "api_exchange_ms": [], "api_get_ms": []}
 
-        text_first = args.e2e_order == "text-first"
+            text_first = args.e2e_order == "text-first"
 
-        def step_host():
-            t0 = time.perf_counter()
-            if gather is not None and text_first:
-                # text first: its records are formed (real_gpu_prepare_scan, a stream of its own) while the reads are uploaded and gathered
-                d = gather_words.run()
-                h.set_text_device(d["words"].data_ptr(), d_mask_ptr, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
-                h.prepare_scan(L)
-                t1 = time.perf_counter()
-                d = gather.run()
-                h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
-                                          d_quality=d["qual"].data_ptr() if "qual" in d else None)
-                gather_mask.run()                 # the mask arrives while the index builds; the library reads it when the match call starts
-                t2 = time.perf_counter()
-                t_text, t_reads = t1 - t0, t2 - t1
-            elif gather is not None:
-                d = gather.run()
-                h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
-                                          d_quality=d["qual"].data_ptr() if "qual" in d else None)
-                d = gather_text.run()             # upload + all-gather of the text while the index build runs
-                h.set_text_device(d["words"].data_ptr(), d["nmask"].data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
-                t2 = time.perf_counter()
-                t_text, t_reads = 0.0, t2 - t0
-            elif text_first:
-                # text first (real_gpu_set_text_async: the copies are only enqueued; the pinned buffers stay untouched until the match
-                # call has returned): the partition kernels of the scan (real_gpu_prepare_scan) start when the words have arrived and
-                # run while the reads cross PCIe; the wildcard mask, which the probe alone reads, travels behind the reads, under the
-                # index build
-                h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
-                h.prepare_scan(L)
-                t1 = time.perf_counter()
-                h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
-                t2 = time.perf_counter()
-                t_text, t_reads = t1 - t0, t2 - t1
-            else:
-                h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
-                t1 = time.perf_counter()
-                # the copies of the text are enqueued (real_gpu_set_text_async): the partition of the scan starts when the words have
-                # arrived, the wildcard mask travels meanwhile; the pinned buffers stay untouched until the match call has returned
-                h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
-                t2 = time.perf_counter()
-                t_text, t_reads = t2 - t1, t1 - t0
-            t4 = t3 = t2
-            if unique:
-                h.match_unique()
-                if gaps:
-                    h.match_gaps(0)
-                t3 = time.perf_counter()
-                st = h.stats()
-                if world > 1:
-                    exchange()
-                    st["fold_ms"] = h.stats()["fold_ms"]
-                t4 = time.perf_counter()
-                # after the exchange every rank holds the merged state of (at least) its own 1/N of the reads: it reads that back
-                h.get_unique(out=np_info[r_lo:r_hi], first=r_lo, count=r_hi - r_lo)
-                st["d2h_ms"] = h.stats()["d2h_ms"]
-                d2h[0] = (r_hi - r_lo) * 8
-            else:
-                nh = h.match_all_count(packed=True)          # 16-byte rows land in the library's pinned host buffer
-                t4 = t3 = time.perf_counter()
-                st = h.stats()
-                d2h[0] = nh * 16
-            t5 = time.perf_counter()
-            st.update(api_set_reads_ms=t_reads * 1e3, api_set_text_ms=t_text * 1e3, api_match_ms=(t3 - t2) * 1e3,
-                      api_exchange_ms=(t4 - t3) * 1e3, api_get_ms=(t5 - t4) * 1e3)
-            return st
+            def step_host():
+                t0 = time.perf_counter()
+                if gather is not None and text_first:
+                    # text first: its records are formed (real_gpu_prepare_scan, a stream of its own) while the reads are uploaded and gathered
+                    d = gather_words.run()
+                    h.set_text_device(d["words"].data_ptr(), d_mask_ptr, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
+                    h.prepare_scan(L)
+                    t1 = time.perf_counter()
+                    d = gather.run()
+                    h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
+                                              d_quality=d["qual"].data_ptr() if "qual" in d else None)
+                    gather_mask.run()                 # the mask arrives while the index builds; the library reads it when the match call starts
+                    t2 = time.perf_counter()
+                    t_text, t_reads = t1 - t0, t2 - t1
+                elif gather is not None:
+                    d = gather.run()
+                    h.set_reads_packed_device(d["reads"].data_ptr(), R, L, d_wildcard_flags=d["flags"].data_ptr(),
+                                              d_quality=d["qual"].data_ptr() if "qual" in d else None)
+                    d = gather_text.run()             # upload + all-gather of the text while the index build runs
+                    h.set_text_device(d["words"].data_ptr(), d["nmask"].data_ptr(), n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe)
+                    t2 = time.perf_counter()
+                    t_text, t_reads = 0.0, t2 - t0
+                elif text_first:
+                    # text first (real_gpu_set_text_async: the copies are only enqueued; the pinned buffers stay untouched until the match
+                    # call has returned): the partition kernels of the scan (real_gpu_prepare_scan) start when the words have arrived and
+                    # run while the reads cross PCIe; the wildcard mask, which the probe alone reads, travels behind the reads, under the
+                    # index build
+                    h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
+                    h.prepare_scan(L)
+                    t1 = time.perf_counter()
+                    h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
+                    t2 = time.perf_counter()
+                    t_text, t_reads = t1 - t0, t2 - t1
+                else:
+                    h.set_reads_packed(np_mapped, R, uniform_length=L, wildcard_flags=np_flags, quality=np_qual)
+                    t1 = time.perf_counter()
+                    # the copies of the text are enqueued (real_gpu_set_text_async): the partition of the scan starts when the words have
+                    # arrived, the wildcard mask travels meanwhile; the pinned buffers stay untouched until the match call has returned
+                    h.set_text(np_w, np_m, n, rs, shard_begin=sb, shard_len=sl, own_begin=ob, own_end=oe, async_copy=True)
+                    t2 = time.perf_counter()
+                    t_text, t_reads = t2 - t1, t1 - t0
+                t4 = t3 = t2
+                if unique:
+                    h.match_unique()
+                    if gaps:
+                        h.match_gaps(0)
+                    t3 = time.perf_counter()
+                    st = h.stats()
+                    if world > 1:
+                        exchange()
+                        st["fold_ms"] = h.stats()["fold_ms"]
+                    t4 = time.perf_counter()
+                    # after the exchange every rank holds the merged state of (at least) its own 1/N of the reads: it reads that back
+                    h.get_unique(out=np_info[r_lo:r_hi], first=r_lo, count=r_hi - r_lo)
+                    st["d2h_ms"] = h.stats()["d2h_ms"]
+                    d2h[0] = (r_hi - r_lo) * 8
+                else:
+                    nh = h.match_all_count(packed=True)          # 16-byte rows land in the library's pinned host buffer
+                    t4 = t3 = time.perf_counter()
+                    st = h.stats()
+                    d2h[0] = nh * 16
+                t5 = time.perf_counter()
+                st.update(api_set_reads_ms=t_reads * 1e3, api_set_text_ms=t_text * 1e3, api_match_ms=(t3 - t2) * 1e3,
+                          api_exchange_ms=(t4 - t3) * 1e3, api_get_ms=(t5 - t4) * 1e3)
+                return st
 
-        def collect_e2e(st):
-            for k in e2e_phase:
-                e2e_phase[k].append(st.get(k, 0.0))
+            def collect_e2e(st):
+                for k in e2e_phase:
+                    e2e_phase[k].append(st.get(k, 0.0))
 
-        e_steps = max(1, min(args.steps, 3))
-        e_ms, _ = timed(step_host, e_steps, 1, collect_e2e)
-        # the state the last end-to-end step left on the device must be the one of the device-resident steps
-        e2e_digest = result_digest()
-        if e2e_digest != digest:
-            print("bench: the end-to-end leg produced another result (digest %016x, device-resident %016x)" % (e2e_digest, digest), file=sys.stderr)
-            sys.exit(3)
-        h2d = R * L4 + R + (R * L if qual is not None else 0) + np_w.nbytes + np_m.nbytes + rs.nbytes
-        if gather is not None:
-            h2d = gather.chunk + (gather_text.chunk if gather_text is not None else gather_words.chunk + gather_mask.chunk) + rs.nbytes          # per rank; the rest arrives over NVLink
-        e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-               "ms_per_step": e_ms / e_steps, "steps": e_steps, "order": args.e2e_order, "digest_ok": True, "prepared_scans": int(h.stats().get("prepared_scans", 0)),
-               "phases_ms": {k: statistics.mean(v) for k, v in e2e_phase.items() if v},
-               "input": "host buffers: text 2 bit/base + N mask, reads 2 bit/base (the reference's rewritten pattern file layout), "
-                        "qualities 1 byte/base when scoring; result read back to pinned host memory"
-                        + ("; every rank uploads 1/%d of the bytes, NCCL all-gather over NVLink for the rest (h2d_bytes_per_step is per rank)" % world
-                           if gather is not None else "")
-                        + ("; every rank reads back the merged result of its own 1/%d of the reads (d2h_bytes_per_step is per rank)" % world if world > 1 and unique else "")}
-        del h_mapped, h_qual, h_w, h_m, h_flags
+            e_steps = max(1, min(args.steps, 3))
+            e_ms, _ = timed(step_host, e_steps, 1, collect_e2e)
+            # the state the last end-to-end step left on the device must be the one of the device-resident steps
+            e2e_digest = result_digest()
+            if e2e_digest != digest:
+                print("bench: the end-to-end leg produced another result (digest %016x, device-resident %016x)" % (e2e_digest, digest), file=sys.stderr)
+                sys.exit(3)
+            h2d = R * L4 + R + (R * L if qual is not None else 0) + np_w.nbytes + np_m.nbytes + rs.nbytes
+            if gather is not None:
+                h2d = gather.chunk + (gather_text.chunk if gather_text is not None else gather_words.chunk + gather_mask.chunk) + rs.nbytes          # per rank; the rest arrives over NVLink
+            e2e = {"value": R / (e_ms / e_steps * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
+                   "ms_per_step": e_ms / e_steps, "steps": e_steps, "order": args.e2e_order, "digest_ok": True, "prepared_scans": int(h.stats().get("prepared_scans", 0)),
+                   "phases_ms": {k: statistics.mean(v) for k, v in e2e_phase.items() if v},
+                   "input": "host buffers: text 2 bit/base + N mask, reads 2 bit/base (the reference's rewritten pattern file layout), "
+                            "qualities 1 byte/base when scoring; result read back to pinned host memory"
+                            + ("; every rank uploads 1/%d of the bytes, NCCL all-gather over NVLink for the rest (h2d_bytes_per_step is per rank)" % world
+                               if gather is not None else "")
+                            + ("; every rank reads back the merged result of its own 1/%d of the reads (d2h_bytes_per_step is per rank)" % world if world > 1 and unique else "")}
+            del h_mapped, h_qual, h_w, h_m, h_flags
+        except Exception as exc:          # the device-resident numbers above stand on their own: the line is printed either way
+            import traceback
+            traceback.print_exc()
+            e2e = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     dev_bytes = h.device_bytes()
     h.close()
